@@ -1,0 +1,354 @@
+"""ctypes binding of include/frt_b200.h and the Python mirror of the reference's render entry points."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "libfrt_b200.so"
+_lib = None
+
+FRT_ABI_VERSION = 3
+FRT_FLAG_NO_PRUNE = 1
+FRT_FLAG_COUNT_RAYS = 2
+
+
+class FrtError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (message from frt_last_error())."""
+
+
+# ---------------------------------------------------------------------------------------------- structs
+
+
+class frt_node(C.Structure):
+    _fields_ = [("type", C.c_int32), ("skip", C.c_int32), ("parent", C.c_int32), ("xform", C.c_int32),
+                ("material", C.c_int32), ("param", C.c_int32), ("csg_op", C.c_int32), ("right", C.c_int32),
+                ("bbox_min", C.c_double * 3), ("bbox_max", C.c_double * 3)]
+
+
+class frt_xform(C.Structure):
+    _fields_ = [("inv", C.c_double * 12)]
+
+
+class frt_material(C.Structure):
+    _fields_ = [("Ka", C.c_double * 3), ("Kd", C.c_double * 3), ("Ks", C.c_double * 3), ("Tf", C.c_double * 3),
+                ("refl", C.c_double * 3), ("Ns", C.c_double), ("Ni", C.c_double), ("Tr", C.c_double),
+                ("casts_shadow", C.c_int32), ("reflective", C.c_int32),
+                ("map_Ka", C.c_int32), ("map_Kd", C.c_int32), ("map_Ks", C.c_int32), ("map_Ns", C.c_int32),
+                ("map_d", C.c_int32), ("map_bump", C.c_int32), ("map_refl", C.c_int32), ("pad", C.c_int32)]
+
+
+class frt_pattern(C.Structure):
+    _fields_ = [("type", C.c_int32), ("identity", C.c_int32), ("inv", C.c_double * 12), ("c", C.c_double * 15),
+                ("f", C.c_double * 4), ("i", C.c_int32 * 4)]
+
+
+class frt_texture(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("super_sample", C.c_int32), ("color_fn", C.c_int32),
+                ("texel_offset", C.c_int64)]
+
+
+class frt_light(C.Structure):
+    _fields_ = [("type", C.c_int32), ("num_samples", C.c_int32), ("cache_len", C.c_int32),
+                ("usteps", C.c_int32), ("vsteps", C.c_int32), ("jitter", C.c_int32),
+                ("intensity", C.c_double * 3), ("position", C.c_double * 3), ("normal", C.c_double * 3),
+                ("uvec", C.c_double * 3), ("vvec", C.c_double * 3), ("radius", C.c_double),
+                ("point_offset", C.c_int64)]
+
+
+class frt_camera(C.Structure):
+    _fields_ = [("hsize", C.c_int32), ("vsize", C.c_int32), ("usteps", C.c_int32), ("vsteps", C.c_int32),
+                ("half_width", C.c_double), ("half_height", C.c_double), ("pixel_size", C.c_double),
+                ("canvas_distance", C.c_double), ("inv", C.c_double * 16),
+                ("aperture_type", C.c_int32), ("aperture_jitter", C.c_int32), ("aperture_size", C.c_double),
+                ("aperture_args", C.c_double * 4)]
+
+
+class frt_config(C.Structure):
+    _fields_ = [("include_direct", C.c_int32), ("include_global", C.c_int32),
+                ("visualize_photon_map", C.c_int32), ("visualize_soft_indirect", C.c_int32),
+                ("di_include_ambient", C.c_int32), ("di_include_diffuse", C.c_int32),
+                ("di_include_specular_highlight", C.c_int32), ("di_include_specular", C.c_int32),
+                ("di_path_length", C.c_int32),
+                ("gi_include_caustics", C.c_int32), ("gi_include_final_gather", C.c_int32),
+                ("gi_usteps", C.c_int32), ("gi_vsteps", C.c_int32),
+                ("gi_irradiance_estimate_num", C.c_int32), ("gi_path_length", C.c_int32), ("pad", C.c_int32),
+                ("gi_irradiance_estimate_radius", C.c_double), ("gi_irradiance_estimate_cone_filter_k", C.c_double),
+                ("gi_photon_count", C.c_int64)]
+
+
+class frt_scene_desc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32),
+                ("n_nodes", C.c_int32), ("n_roots", C.c_int32), ("n_xforms", C.c_int32), ("n_materials", C.c_int32),
+                ("n_patterns", C.c_int32), ("n_textures", C.c_int32), ("n_lights", C.c_int32),
+                ("n_prim_params", C.c_int64), ("n_texels", C.c_int64), ("n_light_points", C.c_int64),
+                ("n_pixel_samples", C.c_int64),
+                ("nodes", C.POINTER(frt_node)), ("roots", C.POINTER(C.c_int32)), ("xforms", C.POINTER(frt_xform)),
+                ("prim_params", C.POINTER(C.c_double)), ("materials", C.POINTER(frt_material)),
+                ("patterns", C.POINTER(frt_pattern)), ("textures", C.POINTER(frt_texture)),
+                ("texels", C.POINTER(C.c_double)), ("lights", C.POINTER(frt_light)),
+                ("light_points", C.POINTER(C.c_double)), ("pixel_samples", C.POINTER(C.c_double)),
+                ("camera", frt_camera), ("config", frt_config)]
+
+
+class frt_render_cfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("rows_per_block", C.c_int32),
+                ("usteps", C.c_int32), ("vsteps", C.c_int32), ("jitter", C.c_int32), ("flags", C.c_int32),
+                ("seed", C.c_uint64)]
+
+
+class frt_stats(C.Structure):
+    _fields_ = [("frame_ms", C.c_double), ("light_ms", C.c_double), ("upload_ms", C.c_double), ("download_ms", C.c_double),
+                ("rays_primary", C.c_uint64), ("rays_secondary", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("rays_gather", C.c_uint64), ("rays_photon", C.c_uint64), ("hits_shaded", C.c_uint64),
+                ("light_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("shadow_nodes", C.c_uint64),
+                ("overflow", C.c_uint64), ("photons_stored", C.c_uint64 * 3),
+                ("rows_rendered", C.c_int32), ("pad", C.c_int32)]
+
+
+class frt_photon_cfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("populate_caustic", C.c_int32), ("populate_global", C.c_int32), ("pad", C.c_int32),
+                ("seed", C.c_uint64)]
+
+
+#: every symbol include/frt_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "frt_abi_version", "frt_last_error", "frt_device_count", "frt_scene_create", "frt_scene_destroy",
+    "frt_render", "frt_canvas_download", "frt_owned_rows", "frt_photons_emit", "frt_photons_count",
+    "frt_photons_export", "frt_photons_import", "frt_photons_finish", "frt_measure_fma_peak",
+    "frt_scene_save", "frt_scene_load", "frt_scene_desc_free",
+]
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def load_library():
+    """Load libfrt_b200.so (built in-tree by fast_ray_tracer_b200.build).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise FrtError(f"{_LIB_PATH} is missing: run `python -m fast_ray_tracer_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(str(_LIB_PATH))
+    lib.frt_abi_version.restype = C.c_int
+    lib.frt_last_error.restype = C.c_char_p
+    lib.frt_device_count.restype = C.c_int
+    lib.frt_scene_create.argtypes = [C.POINTER(frt_scene_desc), C.c_int, C.POINTER(C.c_void_p)]
+    lib.frt_scene_destroy.argtypes = [C.c_void_p]
+    lib.frt_scene_destroy.restype = None
+    lib.frt_render.argtypes = [C.c_void_p, C.POINTER(frt_render_cfg), C.c_void_p, C.POINTER(frt_stats)]
+    lib.frt_canvas_download.argtypes = [C.c_void_p, C.c_void_p]
+    lib.frt_owned_rows.argtypes = [C.POINTER(frt_scene_desc), C.POINTER(frt_render_cfg), C.POINTER(C.c_int32), C.c_int]
+    lib.frt_measure_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.frt_scene_save.argtypes = [C.POINTER(frt_scene_desc), C.c_char_p]
+    lib.frt_scene_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(frt_scene_desc))]
+    lib.frt_scene_desc_free.argtypes = [C.POINTER(frt_scene_desc)]
+    lib.frt_scene_desc_free.restype = None
+    lib.frt_photons_emit.argtypes = [C.c_void_p, C.POINTER(frt_photon_cfg), C.POINTER(frt_stats)]
+    lib.frt_photons_count.argtypes = [C.c_void_p, C.c_int]
+    lib.frt_photons_count.restype = C.c_int64
+    lib.frt_photons_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.frt_photons_import.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]
+    lib.frt_photons_finish.argtypes = [C.c_void_p]
+    if lib.frt_abi_version() != FRT_ABI_VERSION:
+        raise FrtError(f"libfrt_b200.so has ABI {lib.frt_abi_version()}, the Python binding expects {FRT_ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise FrtError(f"{what} failed (status {rc}): {load_library().frt_last_error().decode(errors='replace')}")
+
+
+def device_count() -> int:
+    return int(load_library().frt_device_count())
+
+
+def measure_fma_peak(device: int = 0):
+    """(fp64_tflops, fp32_tflops) of a register-resident FMA loop on the device."""
+    lib = load_library()
+    a, b = C.c_double(), C.c_double()
+    _check(lib.frt_measure_fma_peak(device, C.byref(a), C.byref(b)), "frt_measure_fma_peak")
+    return a.value, b.value
+
+
+# ---------------------------------------------------------------------------------------------- scenes
+
+
+class SceneDesc:
+    """A flattened scene held in host memory (frt_scene_desc).  Built from a blob written by the C shim."""
+
+    def __init__(self, ptr, owned: bool):
+        self._ptr = ptr
+        self._owned = owned
+
+    @classmethod
+    def load(cls, path) -> "SceneDesc":
+        lib = load_library()
+        out = C.POINTER(frt_scene_desc)()
+        _check(lib.frt_scene_load(str(path).encode(), C.byref(out)), f"frt_scene_load({path})")
+        return cls(out, True)
+
+    def save(self, path):
+        _check(load_library().frt_scene_save(self._ptr, str(path).encode()), f"frt_scene_save({path})")
+
+    @property
+    def c(self) -> frt_scene_desc:
+        return self._ptr.contents
+
+    @property
+    def camera(self) -> frt_camera:
+        return self.c.camera
+
+    @property
+    def config(self) -> frt_config:
+        return self.c.config
+
+    @property
+    def host_bytes(self) -> int:
+        d = self.c
+        return (d.n_nodes * C.sizeof(frt_node) + d.n_roots * 4 + d.n_xforms * C.sizeof(frt_xform) + d.n_prim_params * 8
+                + d.n_materials * C.sizeof(frt_material) + d.n_patterns * C.sizeof(frt_pattern)
+                + d.n_textures * C.sizeof(frt_texture) + d.n_texels * 24 + d.n_lights * C.sizeof(frt_light)
+                + d.n_light_points * 24 + d.n_pixel_samples * 8)
+
+    def set_resolution(self, hsize: int, vsize: int):
+        """Re-derive the camera for another resolution at the same field of view (reference camera.c:103-138)."""
+        cam = self.c.camera
+        half_view = max(cam.half_width, cam.half_height)
+        aspect = hsize / vsize
+        cam.hsize, cam.vsize = hsize, vsize
+        if aspect >= 1.0:
+            cam.half_width, cam.half_height = half_view, half_view / aspect
+        else:
+            cam.half_width, cam.half_height = half_view * aspect, half_view
+        cam.pixel_size = cam.half_width * 2.0 / hsize
+
+    def set_samples(self, usteps: int, vsteps: int):
+        """Change the per-pixel sample grid; the xi = 0.5 CMJ table is then derived inside the core."""
+        self.c.camera.usteps, self.c.camera.vsteps = usteps, vsteps
+        self.c.n_pixel_samples = 0
+        self.c.pixel_samples = C.POINTER(C.c_double)()
+
+    def owned_rows(self, rank: int, world: int, rows_per_block: int = 4) -> np.ndarray:
+        cfg = frt_render_cfg(rank=rank, world=world, rows_per_block=rows_per_block)
+        n = load_library().frt_owned_rows(self._ptr, C.byref(cfg), None, 0)
+        rows = (C.c_int32 * max(n, 1))()
+        load_library().frt_owned_rows(self._ptr, C.byref(cfg), rows, n)
+        return np.frombuffer(rows, dtype=np.int32, count=n).copy()
+
+    def __del__(self):
+        if getattr(self, "_owned", False) and self._ptr:
+            try:
+                load_library().frt_scene_desc_free(self._ptr)
+            except Exception:
+                pass
+            self._ptr = None
+
+
+@dataclass
+class RenderStats:
+    frame_ms: float = 0.0
+    light_ms: float = 0.0
+    download_ms: float = 0.0
+    rays_primary: int = 0
+    rays_secondary: int = 0
+    rays_shadow: int = 0
+    rays_gather: int = 0
+    hits_shaded: int = 0
+    kernel_launches: int = 0
+    light_launches: int = 0
+    shadow_nodes: int = 0
+    overflow: int = 0
+    rows_rendered: int = 0
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def rays_total(self) -> int:
+        return self.rays_primary + self.rays_secondary + self.rays_shadow + self.rays_gather
+
+
+class Scene:
+    """A scene resident in HBM on one GPU (frt_scene)."""
+
+    def __init__(self, desc: SceneDesc, device: int = 0):
+        self.desc = desc
+        self.device = device
+        self._h = C.c_void_p()
+        _check(load_library().frt_scene_create(desc._ptr, device, C.byref(self._h)), "frt_scene_create")
+
+    def close(self):
+        if self._h:
+            load_library().frt_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, rank: int = 0, world: int = 1, rows_per_block: int = 4, usteps: int = 0, vsteps: int = 0,
+               jitter: int = -1, seed: int = 0, flags: int = 0, out: Optional[np.ndarray] = None,
+               download: bool = True):
+        """Render this rank's rows.  Returns (canvas[vsize, hsize, 4] float64 or None, RenderStats)."""
+        cam = self.desc.camera
+        cfg = frt_render_cfg(device=self.device, rank=rank, world=world, rows_per_block=rows_per_block,
+                             usteps=usteps, vsteps=vsteps, jitter=jitter, flags=flags, seed=seed)
+        st = frt_stats()
+        ptr = None
+        if download:
+            if out is None:
+                out = np.zeros((cam.vsize, cam.hsize, 4), dtype=np.float64)
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (cam.vsize, cam.hsize, 4)
+            ptr = out.ctypes.data_as(C.c_void_p)
+        _check(load_library().frt_render(self._h, C.byref(cfg), ptr, C.byref(st)), "frt_render")
+        stats = RenderStats(frame_ms=st.frame_ms, light_ms=st.light_ms, download_ms=st.download_ms,
+                            rays_primary=st.rays_primary, rays_secondary=st.rays_secondary, rays_shadow=st.rays_shadow,
+                            rays_gather=st.rays_gather, hits_shaded=st.hits_shaded, kernel_launches=st.kernel_launches,
+                            light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow,
+                            rows_rendered=st.rows_rendered)
+        return (out if download else None), stats
+
+    def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        cam = self.desc.camera
+        if out is None:
+            out = np.zeros((cam.vsize, cam.hsize, 4), dtype=np.float64)
+        _check(load_library().frt_canvas_download(self._h, out.ctypes.data_as(C.c_void_p)), "frt_canvas_download")
+        return out
+
+
+# ---------------------------------------------------------------------------------------------- reference-shaped API
+
+
+def render_multi(desc: SceneDesc, usteps: int = 0, vsteps: int = 0, jitter: Optional[bool] = None, device: int = 0,
+                 seed: int = 0, flags: int = 0):
+    """Mirror of `Canvas render_multi(Camera, World, usteps, vsteps, jitter)` (reference renderer.c:243).
+
+    `desc` carries the flattened World + Camera.  Returns the canvas as a [vsize, hsize, 4] float64 array with the
+    layout of Canvas.arr (linear RGB, 4th lane 0) and the RenderStats of the frame.
+    """
+    with Scene(desc, device) as sc:
+        return sc.render(usteps=usteps, vsteps=vsteps, jitter=-1 if jitter is None else int(bool(jitter)), seed=seed,
+                         flags=flags)
+
+
+def render(desc: SceneDesc, usteps: int = 0, vsteps: int = 0, jitter: Optional[bool] = None, device: int = 0,
+           seed: int = 0, flags: int = 0):
+    """Mirror of the single-threaded twin `render()` (renderer.c:283); identical on the device."""
+    return render_multi(desc, usteps, vsteps, jitter, device, seed, flags)

@@ -1,0 +1,1386 @@
+/*
+ * frt_core.cu -- wavefront render kernels of the B200-native core and the C ABI over them.
+ *
+ * Replaces, for one frame, the reference's pthread row pool + recursion (renderer.c:194-281, :347-366):
+ *
+ *   k_raygen   pixel_multi_sample + ray_for_pixel + sample_aperture      renderer.c:131, :95; camera.c:85
+ *   k_extend   intersect_world(false) + hit(false)                       world.c:164, intersection.c:42
+ *   k_shade    prepare_computations + the reflect/refract split of       renderer.c:368, :497, :534, :607, :689
+ *              shade_hit, with per-ray RGB throughput instead of recursion
+ *   k_light    light->intensity_at (shadow rays) + lighting_microfacet   light.c:229/:245, renderer.c:73, :894
+ *
+ * Rays live in SoA queues in HBM; every stage is a persistent grid-stride kernel that reads its item count
+ * from device memory, so a frame needs no host round trip between stages.  Queue appends are warp-aggregated
+ * (one atomic per warp).  Pixels accumulate in the Canvas layout itself (double[4] per pixel) with FP64 atomics.
+ */
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "frt_b200.h"
+#include "frt_internal.h"
+#include "frt_device.cuh"
+#include "frt_patterns.cuh"
+
+/* ------------------------------------------------------------------------------------------------ errors */
+
+static thread_local char g_err[512] = "";
+
+extern "C" int
+frt_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *
+frt_last_error(void)
+{
+    return g_err;
+}
+
+extern "C" int
+frt_abi_version(void)
+{
+    return FRT_ABI_VERSION;
+}
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            return frt_set_error(FRT_ERR_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+        }                                                                                                    \
+    } while (0)
+
+extern "C" int
+frt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        return 0;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------ device data */
+
+struct RayQ { /* SoA ray queue */
+    double *ox, *oy, *oz, *dx, *dy, *dz; /* ray */
+    double *wr, *wg, *wb;                /* RGB throughput of the path so far */
+    int *pixel;                          /* canvas pixel index (row * hsize + col) */
+    unsigned int *rng;                   /* path id for the counter-based RNG */
+};
+
+struct HitQ { /* result of k_extend, indexed like the ray queue */
+    double *t, *u, *v;
+    int *leaf;
+};
+
+struct LightRec { /* one shaded hit handed to k_light (AoS: all lanes of a hit group read the same record) */
+    double over[3], n[3], eye[3];
+    double Ka[3], Kd[3], Ks[3];
+    double Ns;
+    double w[3];
+    int pixel;
+    unsigned int rng;
+};
+
+struct Counters {
+    unsigned int n_rays[8];   /* rays queued for level l */
+    unsigned int n_hits[8];   /* light records of level l */
+    unsigned int overflow_queue, overflow_csg;
+    unsigned long long rays_secondary, rays_shadow, hits_shaded, shadow_nodes;
+};
+
+struct DCamera {
+    int hsize, vsize, usteps, vsteps;
+    double half_width, half_height, pixel_size, canvas_distance;
+    double inv[12];
+    int aperture_type, jitter;
+    double aperture_size;
+    double aperture_args[4];
+    const double *samples; /* 2*usteps*vsteps doubles: the xi = 0.5 table when jitter is off */
+};
+
+struct FrameParams {
+    int rank, world, rows_per_block, n_owned_rows;
+    int flags;
+    int path_length;
+    int include_direct, use_ambient, use_diffuse, use_spec_highlight, include_specular;
+    unsigned long long seed;
+    unsigned int capacity; /* ray queue capacity */
+};
+
+/* ------------------------------------------------------------------------------------------------ RNG */
+
+__host__ __device__ __forceinline__ unsigned long long
+mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__host__ __device__ __forceinline__ double
+u01(unsigned long long x)
+{
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* ------------------------------------------------------------------------------------------------ helpers */
+
+/* warp-aggregated append: one atomicAdd per warp, returns this lane's slot (or 0xffffffff when want == false) */
+__device__ __forceinline__ unsigned int
+warp_append(unsigned int *counter, bool want)
+{
+    unsigned int mask = __ballot_sync(__activemask(), want);
+    if (!want) {
+        return 0xffffffffu;
+    }
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    unsigned int base = 0;
+    if (lane == leader) {
+        base = atomicAdd(counter, (unsigned int)__popc(mask));
+    }
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ int
+owned_row(const FrameParams &F, int j)
+{
+    int b = j / F.rows_per_block;
+    return (b * F.world + F.rank) * F.rows_per_block + j % F.rows_per_block;
+}
+
+/* ------------------------------------------------------------------------------------------------ raygen */
+
+/* the aperture rejection samplers, camera.c:12-82 (drand48 replaced by the counter-based stream) */
+__device__ __noinline__ void
+aperture_sample(const DCamera &C, unsigned long long key, double &ax, double &ay)
+{
+    if (C.aperture_type == 6 /* POINT_APERTURE */ || C.aperture_type == 4 || C.aperture_type == 5 || C.aperture_type == 8) {
+        ax = 0.5;
+        ay = 0.5;
+        return;
+    }
+    for (unsigned int it = 0; it < 4096; ++it) {
+        double x = u01(mix64(key + 2 * it));
+        double y = u01(mix64(key + 2 * it + 1));
+        double u = 2 * x - 1, v = 2 * y - 1;
+        bool ok;
+        switch (C.aperture_type) {
+        case 0: /* CIRCULAR: compares u^2+v^2 with r1, not r1^2 (camera.c:20) */
+            ok = !(u * u + v * v > C.aperture_args[0]);
+            break;
+        case 1: /* CROSS */
+            ok = ((u > C.aperture_args[0]) && (u <= C.aperture_args[1])) || ((v > C.aperture_args[2]) && (v <= C.aperture_args[3]));
+            break;
+        case 2: /* DIAMOND */
+            ok = (u <= 0) ? ((-u + C.aperture_args[0] <= v) && (v < u + C.aperture_args[1]))
+                          : ((u + C.aperture_args[2] <= v) && (v < -u + C.aperture_args[3]));
+            break;
+        case 3: { /* DOUGHNUT */
+            double mag = u * u + v * v;
+            ok = !(mag > C.aperture_args[0] || mag < C.aperture_args[1]);
+            break;
+        }
+        default: /* SQUARE */
+            ok = true;
+            break;
+        }
+        if (ok) {
+            ax = x;
+            ay = y;
+            return;
+        }
+    }
+    ax = 0.5;
+    ay = 0.5;
+}
+
+/*
+ * One CMJ table entry for a jittered pixel: sampler_reset_canonical_2d + sampler_shuffle_2d (sampler.c:415-461)
+ * replayed with the pixel's RNG stream; returns entry [u, v] like sampler_get_point_2d (:472-477).
+ */
+#define FRT_MAX_SPP 64
+__device__ __noinline__ void
+cmj_jittered(int s0, int s1, unsigned long long key, int qu, int qv, double &jx, double &jy)
+{
+    double arr[2 * FRT_MAX_SPP];
+    unsigned int ctr = 0;
+    int n = s0, m = s1; /* canonical pass binds n = steps[0], m = steps[1] (sampler.c:417-418) */
+    for (int j = 0; j < n; ++j) {
+        for (int i = 0; i < m; ++i) {
+            int idx = 2 * (j * m + i);
+            arr[idx] = (i + (j + u01(mix64(key + ctr++))) / (double)n) / (double)m;
+            arr[idx + 1] = (j + (i + u01(mix64(key + ctr++))) / (double)m) / (double)n;
+        }
+    }
+    m = s0;
+    n = s1; /* shuffle binds m = steps[0], n = steps[1] (sampler.c:435-436) */
+    for (int j = 0; j < n; ++j) {
+        int k = (int)(j + u01(mix64(key + ctr++)) * (n - j));
+        for (int i = 0; i < m; ++i) {
+            double tmp = arr[2 * (j * m + i)];
+            arr[2 * (j * m + i)] = arr[2 * (k * m + i)];
+            arr[2 * (k * m + i)] = tmp;
+        }
+    }
+    for (int i = 0; i < m; ++i) {
+        int k = (int)(i + u01(mix64(key + ctr++)) * (m - i));
+        for (int j = 0; j < n; ++j) {
+            double tmp = arr[2 * (j * m + i) + 1];
+            arr[2 * (j * m + i) + 1] = arr[2 * (j * m + k) + 1];
+            arr[2 * (j * m + k) + 1] = tmp;
+        }
+    }
+    jx = arr[2 * (qv * s0 + qu)];
+    jy = arr[2 * (qv * s0 + qu) + 1];
+}
+
+__global__ void __launch_bounds__(256)
+k_raygen(DCamera C, FrameParams F, RayQ q, Counters *cnt, unsigned int first_sample, unsigned int n_samples)
+{
+    const int spp = C.usteps * C.vsteps;
+    const double w0 = 1.0 / (3.0 * (double)spp); /* (A + D + S) / 3 of the per-pixel mean, renderer.c:174-176, :227-230 */
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += gridDim.x * blockDim.x) {
+        unsigned int s = first_sample + i;
+        unsigned int pix_local = s / spp;
+        int sub = (int)(s - pix_local * spp);
+        int j = (int)(pix_local / C.hsize);
+        int px = (int)(pix_local - (unsigned int)j * C.hsize);
+        int py = owned_row(F, j);
+        int su = sub % C.usteps, sv = sub / C.usteps;
+        unsigned int pixel = (unsigned int)py * C.hsize + px;
+
+        double jx, jy;
+        if (C.jitter) {
+            cmj_jittered(C.usteps, C.vsteps, mix64(F.seed ^ (0x5bd1e995ULL * (pixel + 1))) , su, sv, jx, jy);
+        } else {
+            jx = __ldg(C.samples + 2 * (sv * C.usteps + su));
+            jy = __ldg(C.samples + 2 * (sv * C.usteps + su) + 1);
+        }
+        /* ray_for_pixel, renderer.c:95-129 */
+        double xoffset = ((double)px + jx) * C.pixel_size;
+        double yoffset = ((double)py + jy) * C.pixel_size;
+        double wx = C.half_width - xoffset;
+        double wy = C.half_height - yoffset;
+        double wz = -C.canvas_distance;
+        double pxl[3], org[3];
+        for (int k = 0; k < 3; ++k) {
+            pxl[k] = C.inv[4 * k] * wx + C.inv[4 * k + 1] * wy + C.inv[4 * k + 2] * wz + C.inv[4 * k + 3];
+        }
+        double ax, ay;
+        aperture_sample(C, mix64(F.seed ^ (0x7f4a7c15ULL * (s + 1))), ax, ay);
+        ax = (ax - 0.5) * C.aperture_size;
+        ay = (ay - 0.5) * C.aperture_size;
+        for (int k = 0; k < 3; ++k) {
+            org[k] = C.inv[4 * k] * ax + C.inv[4 * k + 1] * ay + C.inv[4 * k + 2] * 0.0 + C.inv[4 * k + 3];
+        }
+        double vx = pxl[0] - org[0], vy = pxl[1] - org[1], vz = pxl[2] - org[2];
+        double inv = 1.0 / sqrt(vx * vx + vy * vy + vz * vz);
+        q.ox[i] = org[0];
+        q.oy[i] = org[1];
+        q.oz[i] = org[2];
+        q.dx[i] = vx * inv;
+        q.dy[i] = vy * inv;
+        q.dz[i] = vz * inv;
+        q.wr[i] = w0;
+        q.wg[i] = w0;
+        q.wb[i] = w0;
+        q.pixel[i] = (int)pixel;
+        q.rng[i] = s * 2654435761u + 1u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cnt->n_rays[0] = n_samples;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ extend */
+
+__global__ void __launch_bounds__(256)
+k_extend(DScene S, RayQ q, HitQ h, Counters *cnt, int level)
+{
+    const unsigned int n = cnt->n_rays[level];
+    int overflow = 0;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Ray r{ q.ox[i], q.oy[i], q.oz[i], q.dx[i], q.dy[i], q.dz[i] };
+        Hit best = trace_closest(S, r, &overflow);
+        h.t[i] = best.t;
+        h.u[i] = best.u;
+        h.v[i] = best.v;
+        h.leaf[i] = best.leaf;
+    }
+    if (overflow) {
+        atomicOr(&cnt->overflow_csg, 1u);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ shade */
+
+__device__ __forceinline__ void
+material_color(const DScene &S, int map, const double *flat, int leaf, const double pt[3], double out[3])
+{
+    if (map >= 0) {
+        pattern_at_shape(S, map, leaf, pt, NULL, out, 0);
+    } else {
+        out[0] = flat[0];
+        out[1] = flat[1];
+        out[2] = flat[2];
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counters *cnt, int level)
+{
+    const unsigned int n = cnt->n_rays[level];
+    const int remaining = F.path_length - level;
+    int overflow = 0;
+    unsigned long long n_secondary = 0, n_shaded = 0;
+
+    for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        unsigned int i = i0 + threadIdx.x;
+        bool live = i < n;
+        int leaf = live ? h.leaf[i] : -1;
+        live = live && leaf >= 0;
+
+        bool want_rec = false, want_refl = false, want_refr = false;
+        LightRec rec;
+        Ray rfl{}, rfr{};
+        double w_refl[3] = { 0, 0, 0 }, w_refr[3] = { 0, 0, 0 };
+        int pixel = 0;
+        unsigned int rng = 0;
+
+        if (live) {
+            /* ---- prepare_computations, renderer.c:368-495 */
+            Ray r{ q.ox[i], q.oy[i], q.oz[i], q.dx[i], q.dy[i], q.dz[i] };
+            double w[3] = { q.wr[i], q.wg[i], q.wb[i] };
+            pixel = q.pixel[i];
+            rng = q.rng[i];
+            double t = h.t[i];
+            NodeA a = load_node_a(S, leaf);
+            NodeB b = load_node_b(S, leaf);
+            const frt_material &M = S.mats[a.material];
+            const double *prm = S.params + (b.param < 0 ? 0 : b.param);
+
+            double p[3] = { r.ox + r.dx * t, r.oy + r.dy * t, r.oz + r.dz * t };
+            double lp[3], ln[3], nrm[3];
+            point_to_local(S, a.xform, p, lp);
+            local_normal(a.type, prm, lp, h.u[i], h.v[i], ln);
+            normal_to_world(S, a.xform, ln, nrm);
+            if (M.map_bump >= 0) { /* shape_normal_at, shapes.c:76-86: n += 2*texel - 1, sampled at the hit point */
+                double tex[3];
+                pattern_at_shape(S, M.map_bump, leaf, p, NULL, tex, 0);
+                nrm[0] += 2.0 * tex[0] - 1.0;
+                nrm[1] += 2.0 * tex[1] - 1.0;
+                nrm[2] += 2.0 * tex[2] - 1.0;
+            }
+            {
+                double inv = 1.0 / sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+                nrm[0] *= inv;
+                nrm[1] *= inv;
+                nrm[2] *= inv;
+            }
+            double eye[3] = { -r.dx, -r.dy, -r.dz };
+            if (nrm[0] * eye[0] + nrm[1] * eye[1] + nrm[2] * eye[2] < 0) { /* inside */
+                nrm[0] = -nrm[0];
+                nrm[1] = -nrm[1];
+                nrm[2] = -nrm[2];
+            }
+            double ddot = 2 * (r.dx * nrm[0] + r.dy * nrm[1] + r.dz * nrm[2]);
+            double reflv[3] = { r.dx - nrm[0] * ddot, r.dy - nrm[1] * ddot, r.dz - nrm[2] * ddot };
+            double over[3] = { p[0] + nrm[0] * FRT_EPS, p[1] + nrm[1] * FRT_EPS, p[2] + nrm[2] * FRT_EPS };
+            double under[3] = { p[0] - nrm[0] * FRT_EPS, p[1] - nrm[1] * FRT_EPS, p[2] - nrm[2] * FRT_EPS };
+
+            double Ka[3], Kd[3], Ks[3], refl[3];
+            material_color(S, M.map_Ka, M.Ka, leaf, over, Ka);
+            material_color(S, M.map_Kd, M.Kd, leaf, over, Kd);
+            material_color(S, M.map_Ks, M.Ks, leaf, over, Ks);
+            material_color(S, M.map_refl, M.refl, leaf, over, refl);
+            double Ns = M.Ns;
+            if (M.map_Ns >= 0) {
+                double tmp[3];
+                pattern_at_shape(S, M.map_Ns, leaf, over, NULL, tmp, 0);
+                Ns = tmp[0];
+            }
+            double over_d = 1.0 - M.Tr;
+            if (M.map_d >= 0) {
+                double tmp[3];
+                pattern_at_shape(S, M.map_d, leaf, over, NULL, tmp, 0);
+                over_d = tmp[0];
+            }
+
+            /* ---- the specular split of shade_hit, renderer.c:772-822, as throughput weights */
+            const bool no_prune = (F.flags & FRT_FLAG_NO_PRUNE) != 0;
+            const bool spawn = F.include_specular && remaining > 0;
+            bool do_refl = spawn && M.reflective;                       /* reflected_color :497-505 */
+            bool do_refr = spawn && !(over_d <= 0.0);                   /* refracted_color :534-542 */
+            bool tf_zero = M.Tf[0] == 0.0 && M.Tf[1] == 0.0 && M.Tf[2] == 0.0;
+            bool refl_zero = refl[0] == 0.0 && refl[1] == 0.0 && refl[2] == 0.0;
+            if (!no_prune) {
+                /* a branch whose weight is exactly zero cannot change the pixel */
+                do_refr = do_refr && !tf_zero;
+                do_refl = do_refl && !refl_zero;
+            }
+            bool use_schlick = M.reflective && over_d < 1.0;            /* :788 */
+            double n1 = 1.0, n2 = 1.0;
+            if (do_refr || (use_schlick && (do_refl || do_refr))) {
+                trace_containers(S, r, leaf, n1, n2, &overflow);
+            }
+            double cos_i = eye[0] * nrm[0] + eye[1] * nrm[1] + eye[2] * nrm[2];
+            double n_ratio = n1 / n2;
+            double sin2_t = n_ratio * n_ratio * (1.0 - cos_i * cos_i);
+            if (do_refr && sin2_t > 1.0) { /* total internal reflection, :548-553 */
+                do_refr = false;
+            }
+            double k_refl = 1.0, k_refr = 1.0;
+            if (use_schlick) { /* schlick, :607-624 */
+                double co = cos_i;
+                double reflectance;
+                bool tir = false;
+                if (n1 > n2) {
+                    double nn = n1 / n2;
+                    double s2 = nn * nn * (1.0 - co * co);
+                    if (s2 > 1.0) {
+                        tir = true;
+                    }
+                    co = sqrt(1.0 - s2);
+                }
+                if (tir) {
+                    reflectance = 1.0;
+                } else {
+                    double r0 = (n1 - n2) / (n1 + n2);
+                    r0 = r0 * r0;
+                    double m1 = 1.0 - co;
+                    reflectance = r0 + (1.0 - r0) * m1 * m1 * m1 * m1 * m1;
+                }
+                k_refl = reflectance;
+                k_refr = 1.0 - reflectance;
+            }
+            double dissolve = (M.Tr > 0.0 && over_d > 0.0) ? (1.0 - over_d) : 1.0; /* :804-817 */
+
+            if (do_refl) {
+                for (int k = 0; k < 3; ++k) {
+                    w_refl[k] = w[k] * dissolve * k_refl * refl[k];
+                }
+                rfl = Ray{ over[0], over[1], over[2], reflv[0], reflv[1], reflv[2] };
+                want_refl = no_prune || w_refl[0] != 0.0 || w_refl[1] != 0.0 || w_refl[2] != 0.0;
+            }
+            if (do_refr) {
+                double cos_t = sqrt(1.0 - sin2_t);
+                double s = n_ratio * cos_i - cos_t;
+                rfr = Ray{ under[0], under[1], under[2],
+                           nrm[0] * s - eye[0] * n_ratio, nrm[1] * s - eye[1] * n_ratio, nrm[2] * s - eye[2] * n_ratio };
+                for (int k = 0; k < 3; ++k) {
+                    w_refr[k] = w[k] * k_refr * M.Tf[k] * over_d;
+                }
+                want_refr = no_prune || w_refr[0] != 0.0 || w_refr[1] != 0.0 || w_refr[2] != 0.0;
+            }
+
+            /* ---- record for the light stage (direct illumination of this hit, weight = throughput * dissolve) */
+            if (F.include_direct && S.n_lights > 0) {
+                want_rec = true;
+                for (int k = 0; k < 3; ++k) {
+                    rec.over[k] = over[k];
+                    rec.n[k] = nrm[k];
+                    rec.eye[k] = eye[k];
+                    rec.Ka[k] = Ka[k];
+                    rec.Kd[k] = Kd[k];
+                    rec.Ks[k] = Ks[k];
+                    rec.w[k] = w[k] * dissolve;
+                }
+                rec.Ns = Ns;
+                rec.pixel = pixel;
+                rec.rng = rng;
+                if (!no_prune && rec.w[0] == 0.0 && rec.w[1] == 0.0 && rec.w[2] == 0.0) {
+                    want_rec = false;
+                }
+            }
+            ++n_shaded;
+        }
+
+        unsigned int slot = warp_append(&cnt->n_hits[level], want_rec);
+        if (want_rec) {
+            if (slot < F.capacity) {
+                recs[slot] = rec;
+            } else {
+                atomicOr(&cnt->overflow_queue, 1u);
+            }
+        }
+        unsigned int s1 = warp_append(&cnt->n_rays[level + 1], want_refl);
+        if (want_refl) {
+            if (s1 < F.capacity) {
+                qn.ox[s1] = rfl.ox; qn.oy[s1] = rfl.oy; qn.oz[s1] = rfl.oz;
+                qn.dx[s1] = rfl.dx; qn.dy[s1] = rfl.dy; qn.dz[s1] = rfl.dz;
+                qn.wr[s1] = w_refl[0]; qn.wg[s1] = w_refl[1]; qn.wb[s1] = w_refl[2];
+                qn.pixel[s1] = pixel;
+                qn.rng[s1] = rng * 2u + 1u;
+                ++n_secondary;
+            } else {
+                atomicOr(&cnt->overflow_queue, 1u);
+            }
+        }
+        unsigned int s2 = warp_append(&cnt->n_rays[level + 1], want_refr);
+        if (want_refr) {
+            if (s2 < F.capacity) {
+                qn.ox[s2] = rfr.ox; qn.oy[s2] = rfr.oy; qn.oz[s2] = rfr.oz;
+                qn.dx[s2] = rfr.dx; qn.dy[s2] = rfr.dy; qn.dz[s2] = rfr.dz;
+                qn.wr[s2] = w_refr[0]; qn.wg[s2] = w_refr[1]; qn.wb[s2] = w_refr[2];
+                qn.pixel[s2] = pixel;
+                qn.rng[s2] = rng * 2u + 2u;
+                ++n_secondary;
+            } else {
+                atomicOr(&cnt->overflow_queue, 1u);
+            }
+        }
+    }
+    if (overflow) {
+        atomicOr(&cnt->overflow_csg, 1u);
+    }
+    /* block-level reduction of the counters: one atomic per warp */
+    for (int o = 16; o > 0; o >>= 1) {
+        n_secondary += __shfl_down_sync(0xffffffffu, n_secondary, o);
+        n_shaded += __shfl_down_sync(0xffffffffu, n_shaded, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_secondary) atomicAdd(&cnt->rays_secondary, n_secondary);
+        if (n_shaded) atomicAdd(&cnt->hits_shaded, n_shaded);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ light */
+
+/*
+ * One light, all shaded hits of one level.  G lanes (a power of two <= 32) share a hit and stride over the
+ * light's surface samples; partial sums are combined with a fixed-order butterfly, so the result does not
+ * depend on scheduling.
+ *
+ *   shadow pass   area_light_intensity_at / point_light_intensity_at  light.c:229-251  -> is_shadowed renderer.c:73
+ *   lighting pass lighting_microfacet                                  renderer.c:894-979
+ *
+ * The reference picks one of cache_len pre-computed sample sets with rand() once per pass (light.c:196); here
+ * the pick is a hash of (seed, path id, light, pass).  With cache_len == 1 both passes use set 0 and the result
+ * is exactly the reference's.
+ */
+template <int G>
+__global__ void __launch_bounds__(256)
+k_light(DScene S, FrameParams F, const LightRec *__restrict__ recs, double *__restrict__ canvas, Counters *cnt,
+        int level, int light_idx)
+{
+    const unsigned int n = min(cnt->n_hits[level], F.capacity);
+    const frt_light L = S.lights[light_idx];
+    const int NS = L.num_samples;
+    const double *pts = S.lpoints + 3 * L.point_offset;
+    const unsigned int lane_g = threadIdx.x % G;
+    const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    const unsigned int groups = gridDim.x * blockDim.x / G;
+    int overflow = 0;
+    unsigned long long n_shadow = 0, n_nodes = 0;
+
+    for (unsigned int hbase = (blockIdx.x * blockDim.x + threadIdx.x) / G;; hbase += groups) {
+        /* all lanes of a warp iterate together so that the group shuffles stay converged */
+        unsigned int h0 = __shfl_sync(0xffffffffu, hbase, 0);
+        if (h0 >= n) {
+            break;
+        }
+        const bool live = hbase < n;
+        const LightRec *R = recs + (live ? hbase : 0);
+
+        double over[3] = { R->over[0], R->over[1], R->over[2] };
+        double nrm[3] = { R->n[0], R->n[1], R->n[2] };
+        double eye[3] = { R->eye[0], R->eye[1], R->eye[2] };
+        double Ns = R->Ns;
+        unsigned int rng = R->rng;
+
+        int set_a = 0, set_b = 0;
+        if (L.cache_len > 1) {
+            unsigned long long key = F.seed ^ ((unsigned long long)rng << 20) ^ ((unsigned long long)light_idx << 4);
+            set_a = (int)(mix64(key) % (unsigned long long)L.cache_len);
+            set_b = (int)(mix64(key + 1) % (unsigned long long)L.cache_len);
+        }
+
+        /* ---- lighting pass: sums over the sample set, renderer.c:927-968 */
+        double sum_ndl = 0.0, sum_b = 0.0, sum_fb = 0.0;
+        if (live && (F.use_diffuse || F.use_spec_highlight)) {
+            const double ndote = nrm[0] * eye[0] + nrm[1] * eye[1] + nrm[2] * eye[2];
+            const double *pb = pts + 3 * (size_t)set_b * NS;
+            for (int s = lane_g; s < NS; s += G) {
+                double lx = __ldg(pb + 3 * s) - over[0], ly = __ldg(pb + 3 * s + 1) - over[1], lz = __ldg(pb + 3 * s + 2) - over[2];
+                double inv = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
+                lx *= inv;
+                ly *= inv;
+                lz *= inv;
+                double ndl = lx * nrm[0] + ly * nrm[1] + lz * nrm[2];
+                if (ndl >= 0.0) {
+                    if (F.use_diffuse) {
+                        sum_ndl += ndl;
+                    }
+                    if (F.use_spec_highlight) {
+                        double hx = lx + eye[0], hy = ly + eye[1], hz = lz + eye[2];
+                        double hinv = 1.0 / sqrt(hx * hx + hy * hy + hz * hz);
+                        hx *= hinv;
+                        hy *= hinv;
+                        hz *= hinv;
+                        double ndh = fmax(0.0, nrm[0] * hx + nrm[1] * hy + nrm[2] * hz);
+                        double edh_inv = 1.0 / fmax(0.0, eye[0] * hx + eye[1] * hy + eye[2] * hz);
+                        double ldh = lx * hx + ly * hy + lz * hz;
+                        double dist_term = (Ns + 2) * pow(ndh, Ns) * 0.5 * M_1_PI;
+                        double gc = 2.0 * ndh * edh_inv;
+                        double geom = fmin(1.0, fmin(gc * ndote, gc * ndl));
+                        double m1 = 1.0 - ldh;
+                        double factor = pow(m1, 5.0);
+                        double brdf = dist_term * geom / (4.0 * ndl * ndote);
+                        sum_b += brdf;
+                        sum_fb += factor * brdf;
+                    }
+                }
+            }
+        }
+        for (int o = G / 2; o > 0; o >>= 1) {
+            sum_ndl += __shfl_xor_sync(gmask, sum_ndl, o);
+            sum_b += __shfl_xor_sync(gmask, sum_b, o);
+            sum_fb += __shfl_xor_sync(gmask, sum_fb, o);
+        }
+
+        /* ---- shadow pass.  When every lighting term is exactly zero the visibility fraction cannot matter. */
+        const bool contributes = (sum_ndl != 0.0) || (sum_b != 0.0) || (sum_fb != 0.0);
+        int unshadowed = 0;
+        if (live && (contributes || (F.flags & FRT_FLAG_NO_PRUNE))) {
+            const double *pa = pts + 3 * (size_t)set_a * NS;
+            for (int s = lane_g; s < NS; s += G) {
+                double vx = __ldg(pa + 3 * s) - over[0], vy = __ldg(pa + 3 * s + 1) - over[1], vz = __ldg(pa + 3 * s + 2) - over[2];
+                double dist = sqrt(vx * vx + vy * vy + vz * vz);
+                double inv = 1.0 / dist;
+                Ray sr{ over[0], over[1], over[2], vx * inv, vy * inv, vz * inv };
+                if (!trace_shadow(S, sr, dist, &overflow, &n_nodes)) {
+                    ++unshadowed;
+                }
+                ++n_shadow;
+            }
+        }
+        for (int o = G / 2; o > 0; o >>= 1) {
+            unshadowed += __shfl_xor_sync(gmask, unshadowed, o);
+        }
+
+        if (live && lane_g == 0) {
+            double c[3] = { 0.0, 0.0, 0.0 };
+            double intensity = (double)unshadowed / (double)NS;
+            if (!(fabs(intensity) < FRT_EPS) && contributes) { /* equal(shade_intensity, 0.0), renderer.c:904 */
+                double scaling = intensity / (double)NS;
+                for (int k = 0; k < 3; ++k) {
+                    double d = R->Kd[k] * L.intensity[k] * sum_ndl;
+                    double sp = L.intensity[k] * (R->Ks[k] * sum_b + (1.0 - R->Ks[k]) * sum_fb);
+                    c[k] = (d + sp) * scaling;
+                }
+            }
+            if (F.use_ambient) {
+                for (int k = 0; k < 3; ++k) {
+                    c[k] += R->Ka[k] * L.intensity[k];
+                }
+            }
+            double *px = canvas + 4 * (size_t)R->pixel;
+            for (int k = 0; k < 3; ++k) {
+                double v = R->w[k] * c[k];
+                if (v != 0.0) {
+                    atomicAdd(px + k, v);
+                }
+            }
+        }
+    }
+    if (overflow) {
+        atomicOr(&cnt->overflow_csg, 1u);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_shadow += __shfl_down_sync(0xffffffffu, n_shadow, o);
+        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_shadow) atomicAdd(&cnt->rays_shadow, n_shadow);
+        if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ FMA peak */
+
+template <typename T>
+__global__ void
+k_fma_peak(T *out, int iters)
+{
+    T a0 = (T)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const T m = (T)0.999, c = (T)0.001;
+    for (int i = 0; i < iters; ++i) {
+        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+template <typename T>
+static int
+measure_fma(double *tflops)
+{
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 15;
+    T *out = nullptr;
+    CK(cudaMalloc(&out, sizeof(T) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_fma_peak<T><<<blocks, threads>>>(out, 1024);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_fma_peak<T><<<blocks, threads>>>(out, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return FRT_OK;
+}
+
+extern "C" int
+frt_measure_fma_peak(int device, double *fp64_tflops, double *fp32_tflops)
+{
+    CK(cudaSetDevice(device));
+    int rc = measure_fma<double>(fp64_tflops);
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    return measure_fma<float>(fp32_tflops);
+}
+
+/* ------------------------------------------------------------------------------------------------ scene */
+
+struct frt_scene {
+    int device = 0;
+    DScene S{};
+    DCamera C{};
+    frt_config cfg{};
+    std::vector<void *> allocs;
+    double *canvas = nullptr;     /* hsize*vsize*4 doubles */
+    double *samples = nullptr;
+    int samples_u = 0, samples_v = 0;
+    /* frame buffers, sized lazily */
+    unsigned int capacity = 0;
+    RayQ q[2]{};
+    HitQ hq{};
+    LightRec *recs = nullptr;
+    Counters *cnt = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4]{};
+    std::vector<void *> frame_allocs;
+};
+
+template <typename T>
+static int
+upload(frt_scene *sc, const T *src, size_t count, const T **dst)
+{
+    T *d = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CK(cudaMalloc(&d, bytes));
+    sc->allocs.push_back(d);
+    if (count) {
+        CK(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    } else {
+        CK(cudaMemset(d, 0, bytes));
+    }
+    *dst = d;
+    return FRT_OK;
+}
+
+static int
+validate_desc(const frt_scene_desc *d)
+{
+    if (d == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "null scene description");
+    }
+    if (d->abi_version != FRT_ABI_VERSION) {
+        return frt_set_error(FRT_ERR_ARG, "scene description has ABI %d, library has %d", d->abi_version, FRT_ABI_VERSION);
+    }
+    if (d->n_nodes <= 0 || d->n_roots <= 0 || d->n_xforms <= 0 || d->nodes == nullptr || d->roots == nullptr || d->xforms == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "scene has no nodes / roots / transforms");
+    }
+    for (int i = 0; i < d->n_nodes; ++i) {
+        const frt_node &n = d->nodes[i];
+        if (n.type < 0 || n.type > FRT_GROUP || n.skip <= i || n.skip > d->n_nodes || n.xform < 0 || n.xform >= d->n_xforms) {
+            return frt_set_error(FRT_ERR_ARG, "node %d is malformed (type %d skip %d xform %d)", i, n.type, n.skip, n.xform);
+        }
+        if (n.type < FRT_CSG && (n.material < 0 || n.material >= d->n_materials)) {
+            return frt_set_error(FRT_ERR_ARG, "leaf node %d has material %d of %d", i, n.material, d->n_materials);
+        }
+        if (n.type == FRT_CSG && (n.right <= i + 1 || n.right >= n.skip)) {
+            return frt_set_error(FRT_ERR_ARG, "CSG node %d has right child %d outside (%d, %d)", i, n.right, i + 1, n.skip);
+        }
+        bool needs_param = n.type == FRT_CONE || n.type == FRT_CYLINDER || n.type == FRT_TOROID || n.type == FRT_TRIANGLE || n.type == FRT_SMOOTH_TRIANGLE;
+        if (needs_param && (n.param < 0 || n.param >= d->n_prim_params)) {
+            return frt_set_error(FRT_ERR_ARG, "leaf node %d has parameter offset %d of %lld", i, n.param, (long long)d->n_prim_params);
+        }
+    }
+    for (int i = 0; i < d->n_roots; ++i) {
+        if (d->roots[i] < 0 || d->roots[i] >= d->n_nodes) {
+            return frt_set_error(FRT_ERR_ARG, "root %d out of range", i);
+        }
+    }
+    for (int i = 0; i < d->n_lights; ++i) {
+        const frt_light &l = d->lights[i];
+        if (l.num_samples <= 0 || l.cache_len <= 0 || l.point_offset < 0 ||
+            l.point_offset + (int64_t)l.num_samples * l.cache_len > d->n_light_points) {
+            return frt_set_error(FRT_ERR_ARG, "light %d has an inconsistent sample cache", i);
+        }
+    }
+    const frt_camera &c = d->camera;
+    if (c.hsize <= 0 || c.vsize <= 0 || c.usteps <= 0 || c.vsteps <= 0) {
+        return frt_set_error(FRT_ERR_ARG, "camera has a non-positive size");
+    }
+    if (d->config.di_path_length < 0 || d->config.di_path_length > 6) {
+        return frt_set_error(FRT_ERR_ARG, "di.path_length %d is outside 0..6", d->config.di_path_length);
+    }
+    return FRT_OK;
+}
+
+/* the xi = 0.5 table: sampler_reset_canonical_2d + sampler_shuffle_2d with no_jitter (sampler.c:401-461) */
+static void
+cmj_table_no_jitter(int s0, int s1, std::vector<double> &arr)
+{
+    arr.assign((size_t)2 * s0 * s1, 0.0);
+    int n = s0, m = s1;
+    for (int j = 0; j < n; ++j) {
+        for (int i = 0; i < m; ++i) {
+            int idx = 2 * (j * m + i);
+            arr[idx] = (i + (j + 0.5) / (double)n) / (double)m;
+            arr[idx + 1] = (j + (i + 0.5) / (double)m) / (double)n;
+        }
+    }
+    m = s0;
+    n = s1;
+    for (int j = 0; j < n; ++j) {
+        int k = (int)(j + 0.5 * (n - j));
+        for (int i = 0; i < m; ++i) {
+            std::swap(arr[2 * (j * m + i)], arr[2 * (k * m + i)]);
+        }
+    }
+    for (int i = 0; i < m; ++i) {
+        int k = (int)(i + 0.5 * (m - i));
+        for (int j = 0; j < n; ++j) {
+            std::swap(arr[2 * (j * m + i) + 1], arr[2 * (j * m + k) + 1]);
+        }
+    }
+}
+
+extern "C" void
+frt_scene_destroy(frt_scene *sc)
+{
+    if (sc == nullptr) {
+        return;
+    }
+    cudaSetDevice(sc->device);
+    for (void *p : sc->allocs) {
+        cudaFree(p);
+    }
+    for (void *p : sc->frame_allocs) {
+        cudaFree(p);
+    }
+    for (auto &e : sc->ev) {
+        if (e) cudaEventDestroy(e);
+    }
+    if (sc->stream) {
+        cudaStreamDestroy(sc->stream);
+    }
+    delete sc;
+}
+
+extern "C" int
+frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
+{
+    if (out == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_scene_create: null out pointer");
+    }
+    *out = nullptr;
+    int rc = validate_desc(d);
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        return frt_set_error(FRT_ERR_CUDA, "no CUDA device is visible: the B200 core has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) {
+        return frt_set_error(FRT_ERR_ARG, "device %d of %d", device, ndev);
+    }
+    CK(cudaSetDevice(device));
+
+    frt_scene *sc = new frt_scene();
+    sc->device = device;
+#define UP(expr)                     \
+    do {                             \
+        int rc_ = (expr);            \
+        if (rc_ != FRT_OK) {         \
+            frt_scene_destroy(sc);   \
+            return rc_;              \
+        }                            \
+    } while (0)
+
+    /* nodes -> 2 x int4, bounding boxes -> 6 doubles */
+    std::vector<int4> nodes((size_t)2 * d->n_nodes);
+    std::vector<double> bbox((size_t)6 * d->n_nodes);
+    for (int i = 0; i < d->n_nodes; ++i) {
+        const frt_node &n = d->nodes[i];
+        nodes[2 * i] = make_int4(n.type, n.skip, n.xform, n.material);
+        nodes[2 * i + 1] = make_int4(n.param, n.csg_op, n.right, n.parent);
+        for (int k = 0; k < 3; ++k) {
+            bbox[6 * i + k] = n.bbox_min[k];
+            bbox[6 * i + 3 + k] = n.bbox_max[k];
+        }
+    }
+    DScene &S = sc->S;
+    UP(upload(sc, nodes.data(), nodes.size(), &S.nodes));
+    UP(upload(sc, bbox.data(), bbox.size(), &S.bbox));
+    UP(upload(sc, (const double *)d->xforms, (size_t)12 * d->n_xforms, &S.xinv));
+    UP(upload(sc, d->prim_params, (size_t)d->n_prim_params, &S.params));
+    UP(upload(sc, d->materials, (size_t)d->n_materials, &S.mats));
+    UP(upload(sc, d->patterns, (size_t)d->n_patterns, &S.pats));
+    UP(upload(sc, d->textures, (size_t)d->n_textures, &S.texs));
+    UP(upload(sc, d->texels, (size_t)3 * d->n_texels, &S.texels));
+    UP(upload(sc, d->lights, (size_t)d->n_lights, &S.lights));
+    UP(upload(sc, d->light_points, (size_t)3 * d->n_light_points, &S.lpoints));
+    UP(upload(sc, d->roots, (size_t)d->n_roots, &S.roots));
+    S.n_roots = d->n_roots;
+    S.n_nodes = d->n_nodes;
+    S.n_lights = d->n_lights;
+
+    const frt_camera &c = d->camera;
+    DCamera &C = sc->C;
+    C.hsize = c.hsize;
+    C.vsize = c.vsize;
+    C.usteps = c.usteps;
+    C.vsteps = c.vsteps;
+    C.half_width = c.half_width;
+    C.half_height = c.half_height;
+    C.pixel_size = c.pixel_size;
+    C.canvas_distance = c.canvas_distance;
+    memcpy(C.inv, c.inv, sizeof(C.inv));
+    C.aperture_type = c.aperture_type;
+    C.jitter = c.aperture_jitter;
+    C.aperture_size = c.aperture_size;
+    memcpy(C.aperture_args, c.aperture_args, sizeof(C.aperture_args));
+
+    std::vector<double> table;
+    if (d->pixel_samples != nullptr && d->n_pixel_samples == (int64_t)2 * c.usteps * c.vsteps) {
+        table.assign(d->pixel_samples, d->pixel_samples + d->n_pixel_samples);
+    } else {
+        cmj_table_no_jitter(c.usteps, c.vsteps, table);
+    }
+    const double *dtab = nullptr;
+    UP(upload(sc, table.data(), table.size(), &dtab));
+    sc->samples = const_cast<double *>(dtab);
+    sc->samples_u = c.usteps;
+    sc->samples_v = c.vsteps;
+    C.samples = dtab;
+
+    sc->cfg = d->config;
+
+    size_t cbytes = (size_t)c.hsize * c.vsize * 4 * sizeof(double);
+    void *cv = nullptr;
+    if (cudaMalloc(&cv, cbytes) != cudaSuccess) {
+        frt_scene_destroy(sc);
+        return frt_set_error(FRT_ERR_CUDA, "cudaMalloc of the canvas failed");
+    }
+    sc->allocs.push_back(cv);
+    sc->canvas = (double *)cv;
+    if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        frt_scene_destroy(sc);
+        return frt_set_error(FRT_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    for (auto &e : sc->ev) {
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            frt_scene_destroy(sc);
+            return frt_set_error(FRT_ERR_CUDA, "cudaEventCreate failed");
+        }
+    }
+#undef UP
+    *out = sc;
+    return FRT_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ frame */
+
+static int
+count_owned_rows(int vsize, int rank, int world, int rpb)
+{
+    int n = 0;
+    for (int y = 0; y < vsize; ++y) {
+        if ((y / rpb) % world == rank) {
+            ++n;
+        }
+    }
+    return n;
+}
+
+extern "C" int
+frt_owned_rows(const frt_scene_desc *d, const frt_render_cfg *cfg, int32_t *rows, int cap)
+{
+    if (d == nullptr || cfg == nullptr) {
+        return 0;
+    }
+    int world = cfg->world > 0 ? cfg->world : 1;
+    int rpb = cfg->rows_per_block > 0 ? cfg->rows_per_block : 4;
+    int n = 0;
+    for (int y = 0; y < d->camera.vsize; ++y) {
+        if ((y / rpb) % world == cfg->rank) {
+            if (rows != nullptr && n < cap) {
+                rows[n] = y;
+            }
+            ++n;
+        }
+    }
+    return n;
+}
+
+template <typename T>
+static int
+frame_alloc(frt_scene *sc, T **p, size_t count)
+{
+    void *d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
+    sc->frame_allocs.push_back(d);
+    *p = (T *)d;
+    return FRT_OK;
+}
+
+static int
+ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
+{
+    if (sc->capacity >= capacity) {
+        return FRT_OK;
+    }
+    for (void *p : sc->frame_allocs) {
+        cudaFree(p);
+    }
+    sc->frame_allocs.clear();
+    sc->capacity = 0;
+#define FA(p) do { int rc_ = frame_alloc(sc, &(p), capacity); if (rc_ != FRT_OK) return rc_; } while (0)
+    for (int k = 0; k < 2; ++k) {
+        RayQ &q = sc->q[k];
+        FA(q.ox); FA(q.oy); FA(q.oz); FA(q.dx); FA(q.dy); FA(q.dz);
+        FA(q.wr); FA(q.wg); FA(q.wb); FA(q.pixel); FA(q.rng);
+    }
+    FA(sc->hq.t); FA(sc->hq.u); FA(sc->hq.v); FA(sc->hq.leaf);
+    FA(sc->recs);
+#undef FA
+    int rc = frame_alloc(sc, &sc->cnt, 1);
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    sc->capacity = capacity;
+    return FRT_OK;
+}
+
+template <int G>
+static void
+launch_light(frt_scene *sc, const FrameParams &F, int blocks, int level, int light)
+{
+    k_light<G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->canvas, sc->cnt, level, light);
+}
+
+static int
+pick_group_width(int num_samples)
+{
+    /* lanes per hit: the largest power of two <= 32 that wastes the fewest lane-iterations on this sample count */
+    const char *env = getenv("FRT_LIGHT_GROUP");
+    if (env != nullptr && *env) {
+        int g = atoi(env);
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) {
+            return g;
+        }
+    }
+    int best = 1;
+    double best_cost = 1e30;
+    for (int g = 1; g <= 32; g *= 2) {
+        int iters = (num_samples + g - 1) / g;
+        double waste = (double)(iters * g) / (double)num_samples;
+        /* prefer wider groups (more coherent warps) when the waste is equal, but never beyond 8 lanes per hit */
+        double cost = waste - 1e-3 * g;
+        if (g <= 8 && cost < best_cost) {
+            best_cost = cost;
+            best = g;
+        }
+    }
+    return best;
+}
+
+extern "C" int
+frt_canvas_download(frt_scene *sc, double *canvas_rgba)
+{
+    if (sc == nullptr || canvas_rgba == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_canvas_download: null argument");
+    }
+    CK(cudaSetDevice(sc->device));
+    size_t bytes = (size_t)sc->C.hsize * sc->C.vsize * 4 * sizeof(double);
+    CK(cudaMemcpyAsync(canvas_rgba, sc->canvas, bytes, cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaStreamSynchronize(sc->stream));
+    return FRT_OK;
+}
+
+static int
+render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned int chunk_samples)
+{
+    const frt_config &g = sc->cfg;
+    DCamera C = sc->C;
+    if (cfg->usteps > 0 && cfg->vsteps > 0 && (cfg->usteps != C.usteps || cfg->vsteps != C.vsteps)) {
+        if (cfg->usteps != sc->samples_u || cfg->vsteps != sc->samples_v) {
+            std::vector<double> table;
+            cmj_table_no_jitter(cfg->usteps, cfg->vsteps, table);
+            double *dtab = nullptr;
+            CK(cudaMalloc(&dtab, table.size() * sizeof(double)));
+            sc->allocs.push_back(dtab);
+            CK(cudaMemcpy(dtab, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
+            sc->samples = dtab;
+            sc->samples_u = cfg->usteps;
+            sc->samples_v = cfg->vsteps;
+        }
+        C.usteps = cfg->usteps;
+        C.vsteps = cfg->vsteps;
+        C.samples = sc->samples;
+    }
+    if (cfg->jitter >= 0) {
+        C.jitter = cfg->jitter;
+    }
+    if (C.jitter && C.usteps * C.vsteps > FRT_MAX_SPP) {
+        return frt_set_error(FRT_ERR_ARG, "jittered supersampling supports at most %d samples per pixel", FRT_MAX_SPP);
+    }
+
+    FrameParams F{};
+    F.world = cfg->world > 0 ? cfg->world : 1;
+    F.rank = cfg->rank;
+    if (F.rank < 0 || F.rank >= F.world) {
+        return frt_set_error(FRT_ERR_ARG, "rank %d of world %d", F.rank, F.world);
+    }
+    F.rows_per_block = cfg->rows_per_block > 0 ? cfg->rows_per_block : 4;
+    F.n_owned_rows = count_owned_rows(C.vsize, F.rank, F.world, F.rows_per_block);
+    F.flags = cfg->flags;
+    F.path_length = g.di_path_length;
+    F.include_direct = g.include_direct;
+    F.use_ambient = g.di_include_ambient;
+    F.use_diffuse = g.di_include_diffuse;
+    F.use_spec_highlight = g.di_include_specular_highlight;
+    F.include_specular = g.di_include_specular;
+    F.seed = mix64(cfg->seed);
+
+    const unsigned int spp = (unsigned int)(C.usteps * C.vsteps);
+    const unsigned long long total = (unsigned long long)F.n_owned_rows * C.hsize * spp;
+    if (total >= 0xfffffff0ULL) {
+        return frt_set_error(FRT_ERR_ARG, "frame has too many samples for 32-bit sample ids");
+    }
+    unsigned int chunk = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(total, 1), chunk_samples);
+    unsigned int capacity = chunk * 2u;
+    int rc = ensure_frame_buffers(sc, capacity);
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    F.capacity = sc->capacity;
+
+    cudaStream_t s = sc->stream;
+    size_t cbytes = (size_t)C.hsize * C.vsize * 4 * sizeof(double);
+    const int sm_blocks = 148;
+    unsigned long long launches = 0, light_launches = 0;
+    Counters totals{};
+    float light_ms = 0.f;
+
+    CK(cudaEventRecord(sc->ev[0], s));
+    CK(cudaMemsetAsync(sc->canvas, 0, cbytes, s));
+
+    std::vector<int> gw(sc->S.n_lights);
+    {
+        std::vector<frt_light> hl(sc->S.n_lights);
+        if (sc->S.n_lights) {
+            CK(cudaMemcpy(hl.data(), sc->S.lights, sizeof(frt_light) * hl.size(), cudaMemcpyDeviceToHost));
+        }
+        for (size_t i = 0; i < hl.size(); ++i) {
+            gw[i] = pick_group_width(hl[i].num_samples);
+        }
+    }
+    const bool time_light = (cfg->flags & FRT_FLAG_COUNT_RAYS) != 0;
+
+    for (unsigned long long first = 0; first < total; first += chunk) {
+        unsigned int n = (unsigned int)std::min<unsigned long long>(chunk, total - first);
+        CK(cudaMemsetAsync(sc->cnt, 0, sizeof(Counters), s));
+        int rg_blocks = (int)std::min<unsigned int>((n + 255) / 256, sm_blocks * 16);
+        k_raygen<<<rg_blocks, 256, 0, s>>>(C, F, sc->q[0], sc->cnt, (unsigned int)first, n);
+        ++launches;
+        for (int level = 0; level <= F.path_length; ++level) {
+            RayQ &qi = sc->q[level & 1];
+            RayQ &qo = sc->q[(level + 1) & 1];
+            /* level 0 has n rays; deeper levels read their count on the device: size the grid for the worst case
+             * the level can hold, but never more than a few waves */
+            int ex_blocks = sm_blocks * 8;
+            k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, qi, sc->hq, sc->cnt, level);
+            k_shade<<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+            launches += 2;
+            if (F.include_direct) {
+                for (int li = 0; li < sc->S.n_lights; ++li) {
+                    if (time_light) CK(cudaEventRecord(sc->ev[2], s));
+                    int blocks = sm_blocks * 8;
+                    switch (gw[li]) {
+                    case 1: launch_light<1>(sc, F, blocks, level, li); break;
+                    case 2: launch_light<2>(sc, F, blocks, level, li); break;
+                    case 4: launch_light<4>(sc, F, blocks, level, li); break;
+                    case 8: launch_light<8>(sc, F, blocks, level, li); break;
+                    case 16: launch_light<16>(sc, F, blocks, level, li); break;
+                    default: launch_light<32>(sc, F, blocks, level, li); break;
+                    }
+                    ++launches;
+                    ++light_launches;
+                    if (time_light) {
+                        CK(cudaEventRecord(sc->ev[3], s));
+                        CK(cudaEventSynchronize(sc->ev[3]));
+                        float ms = 0.f;
+                        CK(cudaEventElapsedTime(&ms, sc->ev[2], sc->ev[3]));
+                        light_ms += ms;
+                    }
+                }
+            }
+        }
+        Counters hc;
+        CK(cudaMemcpyAsync(&hc, sc->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        totals.overflow_queue |= hc.overflow_queue;
+        totals.overflow_csg |= hc.overflow_csg;
+        totals.rays_secondary += hc.rays_secondary;
+        totals.rays_shadow += hc.rays_shadow;
+        totals.hits_shaded += hc.hits_shaded;
+        totals.shadow_nodes += hc.shadow_nodes;
+        if (hc.overflow_queue) {
+            break;
+        }
+    }
+    CK(cudaEventRecord(sc->ev[1], s));
+    CK(cudaEventSynchronize(sc->ev[1]));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, sc->ev[0], sc->ev[1]));
+
+    if (st != nullptr) {
+        st->frame_ms = ms;
+        st->light_ms = light_ms;
+        st->rays_primary = total;
+        st->rays_secondary = totals.rays_secondary;
+        st->rays_shadow = totals.rays_shadow;
+        st->hits_shaded = totals.hits_shaded;
+        st->shadow_nodes = totals.shadow_nodes;
+        st->kernel_launches = launches;
+        st->light_launches = light_launches;
+        st->rows_rendered = F.n_owned_rows;
+    }
+    if (totals.overflow_csg) {
+        return frt_set_error(FRT_ERR_OVERFLOW, "a ray met more than %d CSG crossings (or 8 nested CSG levels)", FRT_CSG_CAP);
+    }
+    if (totals.overflow_queue) {
+        return -1; /* caller retries with smaller chunks */
+    }
+    return FRT_OK;
+}
+
+extern "C" int
+frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_stats *stats)
+{
+    if (sc == nullptr || cfg == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_render: null argument");
+    }
+    CK(cudaSetDevice(sc->device));
+    frt_stats st;
+    memset(&st, 0, sizeof(st));
+
+    unsigned int chunk = 12u << 20;
+    const char *env = getenv("FRT_CHUNK_SAMPLES");
+    if (env != nullptr && *env) {
+        chunk = (unsigned int)std::max(1024L, atol(env));
+    }
+    int rc;
+    for (;;) {
+        rc = render_once(sc, cfg, &st, chunk);
+        if (rc != -1) {
+            break;
+        }
+        st.overflow += 1;
+        if (chunk <= 4096) {
+            return frt_set_error(FRT_ERR_OVERFLOW, "secondary-ray queue overflow even with %u-sample chunks", chunk);
+        }
+        chunk /= 4;
+    }
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    if (canvas_rgba != nullptr) {
+        cudaEvent_t e0 = sc->ev[2], e1 = sc->ev[3];
+        CK(cudaEventRecord(e0, sc->stream));
+        /* only the rows this rank owns are written back; the caller's other rows stay untouched */
+        const int world = cfg->world > 0 ? cfg->world : 1;
+        const int rpb = cfg->rows_per_block > 0 ? cfg->rows_per_block : 4;
+        const size_t row_bytes = (size_t)sc->C.hsize * 4 * sizeof(double);
+        if (world == 1) {
+            CK(cudaMemcpyAsync(canvas_rgba, sc->canvas, row_bytes * sc->C.vsize, cudaMemcpyDeviceToHost, sc->stream));
+        } else {
+            for (int y0 = cfg->rank * rpb; y0 < sc->C.vsize; y0 += world * rpb) {
+                int rows = std::min(rpb, sc->C.vsize - y0);
+                CK(cudaMemcpyAsync((char *)canvas_rgba + row_bytes * y0, (char *)sc->canvas + row_bytes * y0, row_bytes * rows,
+                                   cudaMemcpyDeviceToHost, sc->stream));
+            }
+        }
+        CK(cudaEventRecord(e1, sc->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        st.download_ms = ms;
+    }
+    if (stats != nullptr) {
+        *stats = st;
+    }
+    return FRT_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ photons */
+
+extern "C" int
+frt_photons_emit(frt_scene *, const frt_photon_cfg *, frt_stats *)
+{
+    return frt_set_error(FRT_ERR_ARG, "photon pass: not built yet in this revision");
+}
+extern "C" int64_t
+frt_photons_count(frt_scene *, int)
+{
+    return 0;
+}
+extern "C" int
+frt_photons_export(frt_scene *, int, void *, int)
+{
+    return frt_set_error(FRT_ERR_ARG, "photon pass: not built yet in this revision");
+}
+extern "C" int
+frt_photons_import(frt_scene *, int, const void *, int64_t, int)
+{
+    return frt_set_error(FRT_ERR_ARG, "photon pass: not built yet in this revision");
+}
+extern "C" int
+frt_photons_finish(frt_scene *)
+{
+    return frt_set_error(FRT_ERR_ARG, "photon pass: not built yet in this revision");
+}

@@ -1,0 +1,755 @@
+/*
+ * frt_shim.c -- host side of the drop-in boundary, in the reference's own language (C11).
+ *
+ * This translation unit REPLACES src/renderer/renderer.c and src/renderer/photon_tracer.c of
+ * gbordelon/fast_ray_tracer when the reference program is linked against libfrt_b200.so.  It is
+ * compiled against the reference's own headers (struct layouts are the API: generated main.c pokes
+ * struct fields directly), and exports exactly the symbols the rest of the reference program links
+ * against (nm-verified):
+ *     render_multi, render            renderer.h:46-47   (renderer.c:243, :283)
+ *     trace_photons                   photon_tracer.h:4  (photon_tracer.c:203)
+ *     array_of_photon_maps            photon_tracer.h:6  (photon_tracer.c:259)
+ *     is_shadowed                     renderer.h:42      (referenced by light.c:236,247 only)
+ * plus shade_hit / schlick / prepare_computations, which renderer.h declares but nothing references.
+ *
+ * What it does: walk the finished World / Camera once, flatten them into the SoA description of
+ * include/frt_b200.h (pre-order node array that keeps the reference's divided group tree and child
+ * order), hand that to the CUDA core, and return an ordinary Canvas.  No rendering happens on the
+ * host: if the core fails, the process aborts with a non-zero exit status (no CPU fallback).
+ *
+ * Environment:
+ *   FRT_DEVICE=n            CUDA device ordinal (default 0)
+ *   FRT_RANK / FRT_WORLD    row-block partition for multi-process runs (default 0 / 1)
+ *   FRT_SEED=n              seed of the device RNG (default 0)
+ *   FRT_DUMP_SCENE=path     also write the flattened scene as a blob (frt_scene_save)
+ *   FRT_DUMP_ONLY=1         write the blob and return a black canvas without touching CUDA
+ *   FRT_NO_PRUNE=1          trace zero-weight branches like the reference (ray-count parity)
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "src/libs/linalg/linalg.h"
+#include "src/libs/photon_map/pm.h"
+#include "src/libs/sampler/sampler.h"
+#include "src/libs/canvas/canvas.h"
+#include "src/color/rgb.h"
+#include "src/color/srgb.h"
+#include "src/pattern/pattern.h"
+#include "src/material/material.h"
+#include "src/shapes/shapes.h"
+#include "src/light/light.h"
+#include "src/renderer/renderer.h"
+#include "src/renderer/photon_tracer.h"
+#include "src/renderer/world.h"
+#include "src/renderer/camera.h"
+#include "src/renderer/config.h"
+
+#include "frt_b200.h"
+
+/* ------------------------------------------------------------------ growable arrays */
+
+#define VEC(T) struct { T *p; size_t n, cap; }
+#define VEC_PUSH(v, T) ((v).n == (v).cap ? ((v).cap = (v).cap ? (v).cap * 2 : 64, \
+                        (v).p = (T *)xrealloc((v).p, (v).cap * sizeof(T))) : 0, &(v).p[(v).n++])
+
+static void *
+xrealloc(void *p, size_t n)
+{
+    void *q = realloc(p, n);
+    if (q == NULL && n != 0) {
+        fprintf(stderr, "frt_shim: out of memory\n");
+        exit(70);
+    }
+    return q;
+}
+
+static void
+die(const char *what)
+{
+    fprintf(stderr, "frt_shim: %s: %s\n", what, frt_last_error());
+    exit(71);
+}
+
+/* pointer -> index map (open addressing), used to share materials / patterns / textures */
+struct ptrmap {
+    const void **keys;
+    int32_t *vals;
+    size_t cap, n;
+};
+
+static int32_t
+ptrmap_get(struct ptrmap *m, const void *k)
+{
+    if (m->cap == 0) {
+        return -1;
+    }
+    size_t h = ((uintptr_t)k >> 4) * 0x9E3779B97F4A7C15ULL;
+    for (size_t i = h & (m->cap - 1);; i = (i + 1) & (m->cap - 1)) {
+        if (m->keys[i] == NULL) {
+            return -1;
+        }
+        if (m->keys[i] == k) {
+            return m->vals[i];
+        }
+    }
+}
+
+static void
+ptrmap_put(struct ptrmap *m, const void *k, int32_t v)
+{
+    if ((m->n + 1) * 2 > m->cap) {
+        struct ptrmap old = *m;
+        m->cap = old.cap ? old.cap * 2 : 256;
+        m->keys = (const void **)calloc(m->cap, sizeof(void *));
+        m->vals = (int32_t *)calloc(m->cap, sizeof(int32_t));
+        m->n = 0;
+        for (size_t i = 0; i < old.cap; ++i) {
+            if (old.keys[i] != NULL) {
+                ptrmap_put(m, old.keys[i], old.vals[i]);
+            }
+        }
+        free(old.keys);
+        free(old.vals);
+    }
+    size_t h = ((uintptr_t)k >> 4) * 0x9E3779B97F4A7C15ULL;
+    size_t i = h & (m->cap - 1);
+    while (m->keys[i] != NULL) {
+        i = (i + 1) & (m->cap - 1);
+    }
+    m->keys[i] = k;
+    m->vals[i] = v;
+    m->n++;
+}
+
+/* ------------------------------------------------------------------ flattener state */
+
+struct flat {
+    VEC(frt_node) nodes;
+    VEC(int32_t) roots;
+    VEC(frt_xform) xforms;
+    VEC(double) params;
+    VEC(frt_material) materials;
+    VEC(frt_pattern) patterns;
+    VEC(frt_texture) textures;
+    VEC(double) texels;
+    VEC(frt_light) lights;
+    VEC(double) light_points;
+    VEC(double) pixel_samples;
+    struct ptrmap mat_map, pat_map, tex_map;
+};
+
+static void
+copy3(double *dst, const double *src)
+{
+    dst[0] = src[0];
+    dst[1] = src[1];
+    dst[2] = src[2];
+}
+
+static void
+rows3x4(double *dst, const Matrix m)
+{
+    memcpy(dst, m, 12 * sizeof(double));
+}
+
+static int32_t flatten_pattern(struct flat *f, Pattern p);
+
+static int32_t
+flatten_texture(struct flat *f, Canvas c)
+{
+    int32_t idx = ptrmap_get(&f->tex_map, c);
+    if (idx >= 0) {
+        return idx;
+    }
+    idx = (int32_t)f->textures.n;
+    frt_texture *t = VEC_PUSH(f->textures, frt_texture);
+    memset(t, 0, sizeof(*t));
+    t->width = (int32_t)c->width;
+    t->height = (int32_t)c->height;
+    t->super_sample = c->super_sample ? 1 : 0;
+    if (c->color_space_fn == rgb_to_rgb) {
+        t->color_fn = FRT_COLOR_RGB;
+    } else if (c->color_space_fn == srgb_to_rgb) {
+        t->color_fn = FRT_COLOR_SRGB_TO_RGB;
+    } else {
+        fprintf(stderr, "frt_shim: texture colour space other than RGB/sRGB is not supported on the device\n");
+        exit(72);
+    }
+    t->texel_offset = (int64_t)(f->texels.n / 3);
+    size_t n = c->width * c->height;
+    for (size_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            *VEC_PUSH(f->texels, double) = c->arr[i][k];
+        }
+    }
+    ptrmap_put(&f->tex_map, c, idx);
+    return idx;
+}
+
+static int
+uv_map_faces(enum uv_map_type t)
+{
+    switch (t) {
+    case CUBE_UV_MAP:
+        return 6;
+    case CYLINDER_UV_MAP:
+        return 3;
+    default:
+        return 1;
+    }
+}
+
+static void
+fill_pattern(struct flat *f, int32_t idx, Pattern p)
+{
+    frt_pattern q;
+    memset(&q, 0, sizeof(q));
+    q.type = (int32_t)p->type;
+    q.identity = p->transform_identity ? 1 : 0;
+    rows3x4(q.inv, p->transform_inverse);
+    q.i[0] = q.i[1] = q.i[2] = q.i[3] = -1;
+    switch (p->type) {
+    case CHECKER_PATTERN:
+    case GRADIENT_PATTERN:
+    case RADIAL_GRADIENT_PATTERN:
+    case RING_PATTERN:
+    case STRIPE_PATTERN:
+    case UV_GRADIENT_PATTERN:
+    case UV_RADIAL_GRADIENT_PATTERN:
+        copy3(q.c + 0, p->fields.concrete.a);
+        copy3(q.c + 3, p->fields.concrete.b);
+        break;
+    case UV_ALIGN_CHECKER_PATTERN:
+        copy3(q.c + 0, p->fields.uv_align_check.main);
+        copy3(q.c + 3, p->fields.uv_align_check.ul);
+        copy3(q.c + 6, p->fields.uv_align_check.ur);
+        copy3(q.c + 9, p->fields.uv_align_check.bl);
+        copy3(q.c + 12, p->fields.uv_align_check.br);
+        break;
+    case UV_CHECKER_PATTERN:
+        copy3(q.c + 0, p->fields.uv_check.a);
+        copy3(q.c + 3, p->fields.uv_check.b);
+        q.i[0] = (int32_t)p->fields.uv_check.width;
+        q.i[1] = (int32_t)p->fields.uv_check.height;
+        break;
+    case UV_TEXTURE_PATTERN:
+        q.i[0] = flatten_texture(f, p->fields.uv_texture.canvas);
+        break;
+    case BLENDED_PATTERN:
+        q.i[0] = flatten_pattern(f, p->fields.blended.pattern1);
+        q.i[1] = flatten_pattern(f, p->fields.blended.pattern2);
+        break;
+    case NESTED_PATTERN:
+        q.i[0] = flatten_pattern(f, p->fields.nested.pattern1);
+        q.i[1] = flatten_pattern(f, p->fields.nested.pattern2);
+        q.i[2] = flatten_pattern(f, p->fields.nested.pattern3);
+        break;
+    case PERTURBED_PATTERN:
+        q.i[0] = flatten_pattern(f, p->fields.perturbed.pattern1);
+        q.i[1] = (int32_t)p->fields.perturbed.octaves;
+        q.i[2] = (int32_t)p->fields.perturbed.seed;
+        q.f[0] = p->fields.perturbed.frequency;
+        q.f[1] = p->fields.perturbed.scale_factor;
+        q.f[2] = p->fields.perturbed.persistence;
+        break;
+    case CUBE_MAP_PATTERN:
+    case CYLINDER_MAP_PATTERN:
+    case TEXTURE_MAP_PATTERN: {
+        int nf = uv_map_faces(p->fields.uv_map.type);
+        q.i[0] = (int32_t)p->fields.uv_map.type;
+        /* faces are a contiguous array in the reference (pattern.h:103-106): keep them contiguous */
+        int32_t first = (int32_t)f->patterns.n;
+        for (int k = 0; k < nf; ++k) {
+            frt_pattern *slot = VEC_PUSH(f->patterns, frt_pattern);
+            memset(slot, 0, sizeof(*slot));
+        }
+        for (int k = 0; k < nf; ++k) {
+            fill_pattern(f, first + k, p->fields.uv_map.uv_faces + k);
+        }
+        q.i[1] = first;
+        break;
+    }
+    default:
+        fprintf(stderr, "frt_shim: unknown pattern type %d\n", (int)p->type);
+        exit(72);
+    }
+    f->patterns.p[idx] = q;
+}
+
+static int32_t
+flatten_pattern(struct flat *f, Pattern p)
+{
+    if (p == NULL) {
+        return -1;
+    }
+    int32_t idx = ptrmap_get(&f->pat_map, p);
+    if (idx >= 0) {
+        return idx;
+    }
+    idx = (int32_t)f->patterns.n;
+    frt_pattern *slot = VEC_PUSH(f->patterns, frt_pattern);
+    memset(slot, 0, sizeof(*slot));
+    ptrmap_put(&f->pat_map, p, idx);
+    fill_pattern(f, idx, p);
+    return idx;
+}
+
+static int32_t
+flatten_material(struct flat *f, Material m)
+{
+    if (m == NULL) {
+        return -1;
+    }
+    int32_t idx = ptrmap_get(&f->mat_map, m);
+    if (idx >= 0) {
+        return idx;
+    }
+    frt_material q;
+    memset(&q, 0, sizeof(q));
+    copy3(q.Ka, m->Ka);
+    copy3(q.Kd, m->Kd);
+    copy3(q.Ks, m->Ks);
+    copy3(q.Tf, m->Tf);
+    copy3(q.refl, m->refl);
+    q.Ns = m->Ns;
+    q.Ni = m->Ni;
+    q.Tr = m->Tr;
+    q.casts_shadow = m->casts_shadow ? 1 : 0;
+    q.reflective = m->reflective ? 1 : 0;
+    q.map_Ka = flatten_pattern(f, m->map_Ka);
+    q.map_Kd = flatten_pattern(f, m->map_Kd);
+    q.map_Ks = flatten_pattern(f, m->map_Ks);
+    q.map_Ns = flatten_pattern(f, m->map_Ns);
+    q.map_d = flatten_pattern(f, m->map_d);
+    q.map_bump = flatten_pattern(f, m->map_bump);
+    q.map_refl = flatten_pattern(f, m->map_refl);
+    idx = (int32_t)f->materials.n;
+    *VEC_PUSH(f->materials, frt_material) = q;
+    ptrmap_put(&f->mat_map, m, idx);
+    return idx;
+}
+
+/*
+ * Pre-order walk.  `pinv` is the composite world->parent-local matrix (4x4) and `pxf` its index.
+ * A node whose transform_identity flag is set inherits its parent's composite, exactly like
+ * shape_intersect skips the ray transform (shapes.c:47) and shape_world_to_object /
+ * shape_normal_to_world skip theirs (shapes.c:117-131, :92-114).
+ */
+static int32_t
+flatten_shape(struct flat *f, Shape s, int32_t parent, const Matrix pinv, int32_t pxf)
+{
+    int32_t idx = (int32_t)f->nodes.n;
+    frt_node *slot = VEC_PUSH(f->nodes, frt_node);
+    memset(slot, 0, sizeof(*slot));
+
+    frt_node n;
+    memset(&n, 0, sizeof(n));
+    n.type = (int32_t)s->type;
+    n.parent = parent;
+    n.material = -1;
+    n.param = -1;
+    n.right = -1;
+
+    Matrix comp;
+    int32_t xf = pxf;
+    if (s->transform_identity) {
+        matrix_copy(pinv, comp);
+    } else {
+        matrix_multiply(s->transform_inverse, pinv, comp);
+        xf = (int32_t)f->xforms.n;
+        frt_xform *x = VEC_PUSH(f->xforms, frt_xform);
+        rows3x4(x->inv, comp);
+    }
+    n.xform = xf;
+
+    switch (s->type) {
+    case SHAPE_GROUP: {
+        Bounding_box box;
+        s->bounds(s, &box);
+        copy3(n.bbox_min, box.min);
+        copy3(n.bbox_max, box.max);
+        for (size_t i = 0; i < s->fields.group.num_children; ++i) {
+            flatten_shape(f, s->fields.group.children + i, idx, comp, xf);
+        }
+        break;
+    }
+    case SHAPE_CSG: {
+        Bounding_box box;
+        s->bounds(s, &box);
+        copy3(n.bbox_min, box.min);
+        copy3(n.bbox_max, box.max);
+        n.csg_op = (int32_t)s->fields.csg.op;
+        flatten_shape(f, s->fields.csg.left, idx, comp, xf);
+        n.right = flatten_shape(f, s->fields.csg.right, idx, comp, xf);
+        break;
+    }
+    case SHAPE_CYLINDER:
+    case SHAPE_CONE:
+        n.param = (int32_t)f->params.n;
+        *VEC_PUSH(f->params, double) = s->fields.cylinder.minimum;
+        *VEC_PUSH(f->params, double) = s->fields.cylinder.maximum;
+        *VEC_PUSH(f->params, double) = s->fields.cylinder.closed ? 1.0 : 0.0;
+        n.material = flatten_material(f, s->material);
+        break;
+    case SHAPE_TOROID:
+        n.param = (int32_t)f->params.n;
+        *VEC_PUSH(f->params, double) = s->fields.toroid.r1;
+        *VEC_PUSH(f->params, double) = s->fields.toroid.r2;
+        n.material = flatten_material(f, s->material);
+        break;
+    case SHAPE_TRIANGLE:
+    case SHAPE_SMOOTH_TRIANGLE: {
+        n.param = (int32_t)f->params.n;
+        const double *src[11];
+        src[0] = s->fields.triangle.p1;
+        src[1] = s->fields.triangle.p2;
+        src[2] = s->fields.triangle.p3;
+        src[3] = s->fields.triangle.e1;
+        src[4] = s->fields.triangle.e2;
+        if (s->type == SHAPE_TRIANGLE) {
+            src[5] = src[6] = src[7] = s->fields.triangle.u_normals.normal;
+        } else {
+            src[5] = s->fields.triangle.u_normals.s_normals.n1;
+            src[6] = s->fields.triangle.u_normals.s_normals.n2;
+            src[7] = s->fields.triangle.u_normals.s_normals.n3;
+        }
+        src[8] = s->fields.triangle.t1;
+        src[9] = s->fields.triangle.t2;
+        src[10] = s->fields.triangle.t3;
+        for (int k = 0; k < 11; ++k) {
+            /* t1..t3 are uninitialised in the reference unless use_textures is set */
+            bool live = k < 8 || s->fields.triangle.use_textures;
+            for (int c = 0; c < 3; ++c) {
+                *VEC_PUSH(f->params, double) = live ? src[k][c] : 0.0;
+            }
+        }
+        *VEC_PUSH(f->params, double) = s->fields.triangle.use_textures ? 1.0 : 0.0;
+        n.material = flatten_material(f, s->material);
+        break;
+    }
+    default: /* sphere, cube, plane */
+        n.material = flatten_material(f, s->material);
+        break;
+    }
+
+    n.skip = (int32_t)f->nodes.n;
+    f->nodes.p[idx] = n;
+    return idx;
+}
+
+static void
+flatten_light(struct flat *f, Light l)
+{
+    frt_light q;
+    memset(&q, 0, sizeof(q));
+    q.type = (int32_t)l->type;
+    q.num_samples = (int32_t)l->num_samples;
+    q.cache_len = (int32_t)l->surface_points_cache_len;
+    copy3(q.intensity, l->intensity);
+    switch (l->type) {
+    case AREA_LIGHT: {
+        Vector tmp, nrm;
+        copy3(q.position, l->u.area.corner);
+        copy3(q.uvec, l->u.area.uvec);
+        copy3(q.vvec, l->u.area.vvec);
+        q.usteps = (int32_t)l->u.area.usteps;
+        q.vsteps = (int32_t)l->u.area.vsteps;
+        q.jitter = l->u.area.jitter ? 1 : 0;
+        vector_cross(l->u.area.uvec, l->u.area.vvec, tmp); /* light.c:59-61 */
+        vector_normalize(tmp, nrm);
+        copy3(q.normal, nrm);
+        break;
+    }
+    case CIRCLE_LIGHT:
+        copy3(q.position, l->u.circle.origin);
+        copy3(q.normal, l->u.circle.normal);
+        q.radius = l->u.circle.radius;
+        q.usteps = (int32_t)l->u.circle.usteps;
+        q.vsteps = (int32_t)l->u.circle.vsteps;
+        q.jitter = l->u.circle.jitter ? 1 : 0;
+        break;
+    case HEMISPHERE_LIGHT:
+        copy3(q.position, l->u.hemi.position);
+        copy3(q.normal, l->u.hemi.normal);
+        break;
+    default:
+        copy3(q.position, l->u.point.position);
+        break;
+    }
+    q.point_offset = (int64_t)(f->light_points.n / 3);
+    for (size_t s = 0; s < l->surface_points_cache_len; ++s) {
+        Points pts = l->surface_points_cache + s;
+        if (pts->points_num != l->num_samples) {
+            fprintf(stderr, "frt_shim: light sample set %zu has %zu points, expected %zu\n", s, pts->points_num, l->num_samples);
+            exit(72);
+        }
+        for (size_t k = 0; k < pts->points_num; ++k) {
+            for (int c = 0; c < 3; ++c) {
+                *VEC_PUSH(f->light_points, double) = pts->points[k][c];
+            }
+        }
+    }
+    *VEC_PUSH(f->lights, frt_light) = q;
+}
+
+static void
+flatten_world(struct flat *f, Camera cam, World w, size_t usteps, size_t vsteps, bool jitter, frt_scene_desc *d)
+{
+    memset(f, 0, sizeof(*f));
+    frt_xform *ident = VEC_PUSH(f->xforms, frt_xform);
+    rows3x4(ident->inv, MATRIX_IDENTITY);
+
+    for (size_t i = 0; i < w->shapes_num; ++i) {
+        *VEC_PUSH(f->roots, int32_t) = flatten_shape(f, w->shapes + i, -1, MATRIX_IDENTITY, 0);
+    }
+    for (size_t i = 0; i < w->lights_num; ++i) {
+        flatten_light(f, w->lights + i);
+    }
+
+    memset(d, 0, sizeof(*d));
+    d->abi_version = FRT_ABI_VERSION;
+
+    frt_camera *c = &d->camera;
+    c->hsize = (int32_t)cam->hsize;
+    c->vsize = (int32_t)cam->vsize;
+    c->usteps = (int32_t)usteps;
+    c->vsteps = (int32_t)vsteps;
+    c->half_width = cam->half_width;
+    c->half_height = cam->half_height;
+    c->pixel_size = cam->pixel_size;
+    c->canvas_distance = cam->canvas_distance;
+    memcpy(c->inv, cam->transform_inverse, sizeof(Matrix));
+    c->aperture_type = (int32_t)cam->aperture.type;
+    c->aperture_jitter = jitter ? 1 : 0;
+    c->aperture_size = cam->aperture.size;
+    memcpy(c->aperture_args, &cam->aperture.u, sizeof(cam->aperture.u) < sizeof(c->aperture_args) ? sizeof(cam->aperture.u) : sizeof(c->aperture_args));
+
+    if (!jitter) {
+        /* the per-pixel table is the same for every pixel when xi == 0.5 (sampler.c:401-461): build it with the
+         * reference's own sampler so odd grids keep its index conventions */
+        struct sampler sm;
+        sampler_2d(false, usteps, vsteps, sampler_default_constraint, &sm);
+        for (size_t k = 0; k < 2 * usteps * vsteps; ++k) {
+            *VEC_PUSH(f->pixel_samples, double) = sm.arr[k];
+        }
+        sampler_free(&sm);
+    }
+
+    const struct global_config *g = w->global_config;
+    frt_config *q = &d->config;
+    q->include_direct = g->illumination.include_direct;
+    q->include_global = g->illumination.include_global;
+    q->visualize_photon_map = g->illumination.debug_visualize_photon_map;
+    q->visualize_soft_indirect = g->illumination.debug_visualize_soft_indirect;
+    q->di_include_ambient = g->illumination.di.include_ambient;
+    q->di_include_diffuse = g->illumination.di.include_diffuse;
+    q->di_include_specular_highlight = g->illumination.di.include_specular_highlight;
+    q->di_include_specular = g->illumination.di.include_specular;
+    q->di_path_length = (int32_t)g->illumination.di.path_length;
+    q->gi_include_caustics = g->illumination.gi.include_caustics;
+    q->gi_include_final_gather = g->illumination.gi.include_final_gather;
+    q->gi_usteps = (int32_t)g->illumination.gi.usteps;
+    q->gi_vsteps = (int32_t)g->illumination.gi.vsteps;
+    q->gi_irradiance_estimate_num = (int32_t)g->illumination.gi.irradiance_estimate_num;
+    q->gi_path_length = (int32_t)g->illumination.gi.path_length;
+    q->gi_irradiance_estimate_radius = g->illumination.gi.irradiance_estimate_radius;
+    q->gi_irradiance_estimate_cone_filter_k = g->illumination.gi.irradiance_estimate_cone_filter_k;
+    q->gi_photon_count = (int64_t)g->illumination.gi.photon_count;
+
+    d->n_nodes = (int32_t)f->nodes.n;
+    d->n_roots = (int32_t)f->roots.n;
+    d->n_xforms = (int32_t)f->xforms.n;
+    d->n_materials = (int32_t)f->materials.n;
+    d->n_patterns = (int32_t)f->patterns.n;
+    d->n_textures = (int32_t)f->textures.n;
+    d->n_lights = (int32_t)f->lights.n;
+    d->n_prim_params = (int64_t)f->params.n;
+    d->n_texels = (int64_t)(f->texels.n / 3);
+    d->n_light_points = (int64_t)(f->light_points.n / 3);
+    d->n_pixel_samples = (int64_t)f->pixel_samples.n;
+    d->nodes = f->nodes.p;
+    d->roots = f->roots.p;
+    d->xforms = f->xforms.p;
+    d->prim_params = f->params.p;
+    d->materials = f->materials.p;
+    d->patterns = f->patterns.p;
+    d->textures = f->textures.p;
+    d->texels = f->texels.p;
+    d->lights = f->lights.p;
+    d->light_points = f->light_points.p;
+    d->pixel_samples = f->pixel_samples.n ? f->pixel_samples.p : NULL;
+}
+
+static void
+flat_free(struct flat *f)
+{
+    free(f->nodes.p);
+    free(f->roots.p);
+    free(f->xforms.p);
+    free(f->params.p);
+    free(f->materials.p);
+    free(f->patterns.p);
+    free(f->textures.p);
+    free(f->texels.p);
+    free(f->lights.p);
+    free(f->light_points.p);
+    free(f->pixel_samples.p);
+    free(f->mat_map.keys);
+    free(f->mat_map.vals);
+    free(f->pat_map.keys);
+    free(f->pat_map.vals);
+    free(f->tex_map.keys);
+    free(f->tex_map.vals);
+    memset(f, 0, sizeof(*f));
+}
+
+/* ------------------------------------------------------------------ the boundary */
+
+static long
+env_long(const char *name, long dflt)
+{
+    const char *s = getenv(name);
+    return (s == NULL || *s == '\0') ? dflt : strtol(s, NULL, 10);
+}
+
+/* scene kept between trace_photons() and render_multi(): photons live on the device */
+static frt_scene *g_scene;
+static World g_scene_world;
+
+static Canvas
+render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
+{
+    struct flat f;
+    frt_scene_desc d;
+    flatten_world(&f, cam, w, usteps, vsteps, jitter, &d);
+
+    Canvas image = canvas_alloc(cam->hsize, cam->vsize, false, NULL); /* renderer.c:250 */
+    memset(image->arr, 0, cam->hsize * cam->vsize * sizeof(Color));
+
+    const char *dump = getenv("FRT_DUMP_SCENE");
+    if (dump != NULL && *dump != '\0') {
+        if (frt_scene_save(&d, dump) != FRT_OK) {
+            die("frt_scene_save");
+        }
+    }
+    if (env_long("FRT_DUMP_ONLY", 0)) {
+        flat_free(&f);
+        return image;
+    }
+
+    int device = (int)env_long("FRT_DEVICE", 0);
+    frt_scene *scene = g_scene;
+    if (scene == NULL || g_scene_world != w) {
+        if (frt_scene_create(&d, device, &scene) != FRT_OK) {
+            die("frt_scene_create");
+        }
+    }
+
+    frt_render_cfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.device = device;
+    cfg.rank = (int32_t)env_long("FRT_RANK", 0);
+    cfg.world = (int32_t)env_long("FRT_WORLD", 1);
+    cfg.usteps = (int32_t)usteps;
+    cfg.vsteps = (int32_t)vsteps;
+    cfg.jitter = jitter ? 1 : 0;
+    cfg.seed = (uint64_t)env_long("FRT_SEED", 0);
+    cfg.flags = FRT_FLAG_COUNT_RAYS | (env_long("FRT_NO_PRUNE", 0) ? FRT_FLAG_NO_PRUNE : 0);
+
+    frt_stats st;
+    if (frt_render(scene, &cfg, (double *)image->arr, &st) != FRT_OK) {
+        die("frt_render");
+    }
+    printf("FRT_B200_FRAME_MS %.3f\n", st.frame_ms);
+    printf("FRT_B200_RAYS primary %llu secondary %llu shadow %llu gather %llu\n",
+           (unsigned long long)st.rays_primary, (unsigned long long)st.rays_secondary,
+           (unsigned long long)st.rays_shadow, (unsigned long long)st.rays_gather);
+    fflush(stdout);
+
+    frt_scene_destroy(scene);
+    g_scene = NULL;
+    g_scene_world = NULL;
+    flat_free(&f);
+    return image;
+}
+
+Canvas
+render_multi(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
+{
+    return render_on_device(cam, w, usteps, vsteps, jitter);
+}
+
+Canvas
+render(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
+{
+    return render_on_device(cam, w, usteps, vsteps, jitter);
+}
+
+void
+trace_photons(const World w, size_t num_maps, bool populate_caustic_map, bool populate_global_map)
+{
+    (void)num_maps;
+    if (env_long("FRT_DUMP_ONLY", 0)) {
+        return;
+    }
+    /* The camera is not known yet: flatten with a placeholder camera; render_multi() re-sends the camera. */
+    fprintf(stderr, "frt_shim: trace_photons: device photon pass not wired into the shim yet\n");
+    (void)w;
+    (void)populate_caustic_map;
+    (void)populate_global_map;
+    exit(73);
+}
+
+PhotonMap *
+array_of_photon_maps(size_t num)
+{
+    return (PhotonMap *)malloc(num * sizeof(PhotonMap)); /* photon_tracer.c:259-263 */
+}
+
+/* light.c:236,247 reference this symbol; on the device path shadows never run on the host. */
+bool
+is_shadowed(World w, Point light_position, Point pt)
+{
+    (void)w;
+    (void)light_position;
+    (void)pt;
+    fprintf(stderr, "frt_shim: is_shadowed() called on the host -- the B200 core owns shadow rays\n");
+    abort();
+}
+
+void
+shade_hit(World w, Computations comps, size_t remaining, Color res)
+{
+    (void)w;
+    (void)comps;
+    (void)remaining;
+    (void)res;
+    fprintf(stderr, "frt_shim: shade_hit() is device-only\n");
+    abort();
+}
+
+double
+schlick(Computations comps)
+{
+    (void)comps;
+    fprintf(stderr, "frt_shim: schlick() is device-only\n");
+    abort();
+}
+
+void
+prepare_computations(Intersection i, Ray r, Color photon_power, Intersections xs, Computations res, struct container *container)
+{
+    (void)i;
+    (void)r;
+    (void)photon_power;
+    (void)xs;
+    (void)res;
+    (void)container;
+    fprintf(stderr, "frt_shim: prepare_computations() is device-only\n");
+    abort();
+}

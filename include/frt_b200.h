@@ -1,0 +1,278 @@
+/*
+ * frt_b200.h -- C ABI of libfrt_b200.so, the B200-native render core that
+ * replaces the per-pixel hot path of gbordelon/fast_ray_tracer.
+ *
+ * Boundary: the reference's generated main() calls
+ *     trace_photons(w, 3, caustics, final_gather)      (yaml_parser/yaml_parser.py:209)
+ *     Canvas c = render_multi(cam, w, usteps, vsteps, jitter)   (yaml_parser.py:218)
+ * declared in src/renderer/renderer.h:41-47 and src/renderer/photon_tracer.h:4-6.
+ * The host shim (fast_ray_tracer_b200/csrc/frt_shim.c) keeps those symbols,
+ * walks the finished World/Camera once, fills a frt_scene_desc (below) and
+ * calls the entry points declared here.  Nothing in this header is a C++ or
+ * torch type: plain structs, caller-owned host buffers, int return codes
+ * (0 = ok, non-zero = error, text via frt_last_error()).
+ *
+ * There is NO CPU fallback behind this ABI: every compute entry point fails
+ * with FRT_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef FRT_B200_H
+#define FRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRT_ABI_VERSION 3
+
+enum frt_status {
+    FRT_OK = 0,
+    FRT_ERR_ARG = 1,      /* malformed scene description / bad argument */
+    FRT_ERR_CUDA = 2,     /* CUDA runtime error or no usable device */
+    FRT_ERR_IO = 3,       /* scene blob read/write */
+    FRT_ERR_OVERFLOW = 4  /* a per-ray bounded stack (CSG interval list) overflowed */
+};
+
+/* Same numbering as the reference's enum shape_enum (src/shapes/shapes.h:16-27). */
+enum frt_node_type {
+    FRT_CONE = 0, FRT_CUBE = 1, FRT_CYLINDER = 2, FRT_PLANE = 3, FRT_SMOOTH_TRIANGLE = 4,
+    FRT_SPHERE = 5, FRT_TOROID = 6, FRT_TRIANGLE = 7, FRT_CSG = 8, FRT_GROUP = 9
+};
+
+/* enum csg_ops_enum, src/shapes/shapes.h:29-33 */
+enum frt_csg_op { FRT_CSG_UNION = 0, FRT_CSG_INTERSECT = 1, FRT_CSG_DIFFERENCE = 2 };
+
+/*
+ * One node of the reference's shape tree (struct shape, shapes.h:85-118) after
+ * group_divide, flattened in DFS PRE-ORDER with the reference's child order kept
+ * (shadow rays depend on it: group.c:105-123).  `skip` is the index of the first
+ * node after this node's subtree, so a traversal needs no stack:
+ *     enter a group/CSG -> i+1,   cull or leave a leaf -> skip.
+ */
+typedef struct frt_node {
+    int32_t type;        /* enum frt_node_type */
+    int32_t skip;
+    int32_t parent;      /* -1 for a root */
+    int32_t xform;       /* index into frt_scene_desc.xforms: world->node-local composite; 0 = identity */
+    int32_t material;    /* leaves: index into materials; group/CSG: -1 */
+    int32_t param;       /* leaves: offset (in doubles) into prim_params; -1 when the type has none */
+    int32_t csg_op;      /* CSG only (enum frt_csg_op) */
+    int32_t right;       /* CSG only: pre-order index of the right child (left child is self+1) */
+    double bbox_min[3];  /* group/CSG: bounds in the node's own space (group_bounds group.c:373, csg_bounds csg.c:150) */
+    double bbox_max[3];
+} frt_node;
+
+/*
+ * prim_params layout, by node type (all doubles):
+ *   cylinder / cone : [minimum, maximum, closed(0|1)]                 (shapes.h:54-58)
+ *   toroid          : [r1, r2]                                        (shapes.h:60-63)
+ *   triangle / smooth triangle, FRT_TRI_PARAMS doubles:               (shapes.h:65-82)
+ *       p1[3] p2[3] p3[3] e1[3] e2[3] n1[3] n2[3] n3[3] t1[3] t2[3] t3[3] use_textures
+ *       (flat triangle: n1 = n2 = n3 = normal)
+ */
+#define FRT_TRI_PARAMS 34
+
+/* world->local composite: rows 0..2 of the 4x4 inverse, row-major [r0c0 r0c1 r0c2 r0c3 r1c0 ...] */
+typedef struct frt_xform {
+    double inv[12];
+} frt_xform;
+
+/* struct material, src/material/material.h:196-220 (only the fields the path reads) */
+typedef struct frt_material {
+    double Ka[3], Kd[3], Ks[3], Tf[3], refl[3];
+    double Ns, Ni, Tr;
+    int32_t casts_shadow;
+    int32_t reflective;
+    /* pattern indices or -1: map_Ka, map_Kd, map_Ks, map_Ns, map_d, map_bump, map_refl */
+    int32_t map_Ka, map_Kd, map_Ks, map_Ns, map_d, map_bump, map_refl;
+    int32_t pad;
+} frt_material;
+
+/* enum pattern_type, src/pattern/pattern.h:24-45 (same numbering) */
+enum frt_pattern_type {
+    FRT_PAT_CHECKER = 0, FRT_PAT_GRADIENT = 1, FRT_PAT_RADIAL_GRADIENT = 2, FRT_PAT_RING = 3,
+    FRT_PAT_STRIPE = 4, FRT_PAT_UV_ALIGN_CHECKER = 5, FRT_PAT_UV_CHECKER = 6, FRT_PAT_UV_GRADIENT = 7,
+    FRT_PAT_UV_RADIAL_GRADIENT = 8, FRT_PAT_UV_TEXTURE = 9, FRT_PAT_BLENDED = 10, FRT_PAT_NESTED = 11,
+    FRT_PAT_PERTURBED = 12, FRT_PAT_CUBE_MAP = 13, FRT_PAT_CYLINDER_MAP = 14, FRT_PAT_TEXTURE_MAP = 15
+};
+
+/* enum uv_map_type, pattern.h:94-101 */
+enum frt_uv_map { FRT_UV_CUBE = 0, FRT_UV_CYLINDER = 1, FRT_UV_PLANE = 2, FRT_UV_SPHERE = 3, FRT_UV_TOROID = 4, FRT_UV_TRIANGLE = 5 };
+
+/*
+ * struct pattern, pattern.h:119-142.
+ *   concrete (checker..stripe, uv gradient/radial): c[0..2]=a c[3..5]=b
+ *   uv align check : c[0..14] = main, ul, ur, bl, br
+ *   uv checker     : c = a,b ; i[0]=width i[1]=height
+ *   uv texture     : i[0] = texture index
+ *   blended        : i[0], i[1] = child patterns
+ *   nested         : i[0], i[1], i[2] = pattern1..3
+ *   perturbed      : i[0] = child, i[1] = octaves, i[2] = seed ; f[0]=frequency f[1]=scale_factor f[2]=persistence
+ *   texture map    : i[0] = enum frt_uv_map, i[1] = index of first face pattern (faces contiguous)
+ */
+typedef struct frt_pattern {
+    int32_t type;
+    int32_t identity;   /* transform_identity */
+    double inv[12];     /* rows 0..2 of transform_inverse */
+    double c[15];
+    double f[4];
+    int32_t i[4];
+} frt_pattern;
+
+/* Texture = struct canvas used as an image (canvas.h:10-17); texels are RAW, colour_fn is applied at fetch
+ * exactly like canvas_pixel_at (canvas.c:115-148). */
+enum frt_color_fn { FRT_COLOR_RGB = 0, FRT_COLOR_SRGB_TO_RGB = 1 };
+typedef struct frt_texture {
+    int32_t width, height;
+    int32_t super_sample;
+    int32_t color_fn;       /* enum frt_color_fn */
+    int64_t texel_offset;   /* offset in texels (3 doubles each) into frt_scene_desc.texels */
+} frt_texture;
+
+/* struct light, src/light/light.h:57-76; point/hemisphere lights are num_samples=1, cache_len=1 */
+typedef struct frt_light {
+    int32_t type;           /* enum light_enum, light.h:14-20 */
+    int32_t num_samples;
+    int32_t cache_len;      /* number of pre-computed sample sets */
+    int32_t usteps, vsteps, jitter;
+    double intensity[3];
+    double position[3];     /* point/hemi: position; area: corner; circle: origin */
+    double normal[3];       /* hemi/circle: normal; area: normalize(uvec x vvec) */
+    double uvec[3], vvec[3];/* area light cell vectors (already divided by steps) */
+    double radius;
+    int64_t point_offset;   /* offset in points (3 doubles each) into light_points; set s, sample k at point_offset + s*num_samples + k */
+} frt_light;
+
+/* struct camera + struct aperture, src/renderer/camera.h:44-73 */
+typedef struct frt_camera {
+    int32_t hsize, vsize, usteps, vsteps;
+    double half_width, half_height, pixel_size, canvas_distance;
+    double inv[16];              /* transform_inverse, full 4x4 row-major */
+    int32_t aperture_type;       /* enum aperture_type, camera.h:9-19 */
+    int32_t aperture_jitter;
+    double aperture_size;
+    double aperture_args[4];     /* union u: circle r1 | cross x1 x2 y1 y2 | diamond b1..b4 | doughnut r1 r2 */
+} frt_camera;
+
+/* struct global_config, src/renderer/config.h:4-62 (the fields setup_config reads, renderer.c:53-71) */
+typedef struct frt_config {
+    int32_t include_direct, include_global;
+    int32_t visualize_photon_map, visualize_soft_indirect;
+    int32_t di_include_ambient, di_include_diffuse, di_include_specular_highlight, di_include_specular;
+    int32_t di_path_length;
+    int32_t gi_include_caustics, gi_include_final_gather;
+    int32_t gi_usteps, gi_vsteps;
+    int32_t gi_irradiance_estimate_num;
+    int32_t gi_path_length;
+    int32_t pad;
+    double gi_irradiance_estimate_radius, gi_irradiance_estimate_cone_filter_k;
+    int64_t gi_photon_count;
+} frt_config;
+
+typedef struct frt_scene_desc {
+    int32_t abi_version;         /* FRT_ABI_VERSION */
+    int32_t n_nodes, n_roots, n_xforms, n_materials, n_patterns, n_textures, n_lights;
+    int64_t n_prim_params, n_texels, n_light_points, n_pixel_samples;
+    const frt_node *nodes;
+    const int32_t *roots;        /* pre-order indices of World.shapes[0..shapes_num) (world.h:25-34) */
+    const frt_xform *xforms;     /* xforms[0] must be the identity */
+    const double *prim_params;
+    const frt_material *materials;
+    const frt_pattern *patterns;
+    const frt_texture *textures;
+    const double *texels;        /* n_texels * 3 */
+    const frt_light *lights;
+    const double *light_points;  /* n_light_points * 3 */
+    const double *pixel_samples; /* optional host-built CMJ table (sampler_2d, sampler.c:510), 2*usteps*vsteps doubles,
+                                    used when the primary jitter flag is false; NULL -> the core derives the xi=0.5 table */
+    frt_camera camera;
+    frt_config config;
+} frt_scene_desc;
+
+typedef struct frt_scene frt_scene;   /* opaque: device-resident scene */
+
+enum frt_render_flags {
+    FRT_FLAG_NO_PRUNE = 1,   /* also trace branches whose weight is exactly zero, like the reference does
+                                (renderer.c:534-605 on opaque surfaces) -- for ray-count parity only */
+    FRT_FLAG_COUNT_RAYS = 2  /* fill the ray counters in frt_stats */
+};
+
+typedef struct frt_render_cfg {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t rank, world;     /* this call renders row blocks b with b % world == rank (world <= 0 -> 1) */
+    int32_t rows_per_block;  /* rows in a block (<= 0 -> 4) */
+    int32_t usteps, vsteps;  /* <= 0 -> camera's */
+    int32_t jitter;          /* < 0 -> camera.aperture_jitter */
+    int32_t flags;
+    uint64_t seed;           /* counter-based RNG seed (sample-set picks, jitter, aperture, photons) */
+} frt_render_cfg;
+
+typedef struct frt_stats {
+    double frame_ms;         /* device time of the frame, CUDA events on the render stream */
+    double light_ms;         /* summed device time of the shadow+lighting kernel (dominant kernel) */
+    double upload_ms, download_ms;
+    uint64_t rays_primary, rays_secondary, rays_shadow, rays_gather, rays_photon;
+    uint64_t hits_shaded;
+    uint64_t light_launches; /* launches of the dominant kernel */
+    uint64_t kernel_launches;/* all launches in the frame */
+    uint64_t shadow_nodes;   /* tree nodes visited by shadow rays */
+    uint64_t overflow;       /* non-zero: a bounded queue overflowed and the frame was re-run in smaller chunks */
+    uint64_t photons_stored[3];
+    int32_t rows_rendered;
+    int32_t pad;
+} frt_stats;
+
+typedef struct frt_photon_cfg {
+    int32_t device;
+    int32_t rank, world;     /* emission shard: this call emits photon indices i with i % world == rank */
+    int32_t populate_caustic, populate_global;
+    int32_t pad;
+    uint64_t seed;
+} frt_photon_cfg;
+
+/* ---- entry points ---------------------------------------------------- */
+
+int frt_abi_version(void);
+const char *frt_last_error(void);
+int frt_device_count(void);
+
+/* Upload a flattened scene (host pointers in desc are read during the call only). */
+int frt_scene_create(const frt_scene_desc *desc, int device, frt_scene **out);
+void frt_scene_destroy(frt_scene *scene);
+
+/*
+ * Replaces render_multi()/render() (renderer.c:243/:283).  canvas_rgba has the layout of Canvas.arr
+ * (canvas.h:10-17): hsize*vsize Color = double[4], row-major, linear RGB, 4th lane untouched.
+ * Only the rows owned by (rank, world) are written.  canvas_rgba may be NULL (frame stays on device;
+ * fetch it later with frt_canvas_download).
+ */
+int frt_render(frt_scene *scene, const frt_render_cfg *cfg, double *canvas_rgba, frt_stats *stats);
+int frt_canvas_download(frt_scene *scene, double *canvas_rgba);
+/* rows owned by (rank, world): writes up to cap row indices, returns the count */
+int frt_owned_rows(const frt_scene_desc *desc, const frt_render_cfg *cfg, int32_t *rows, int cap);
+
+/*
+ * Replaces trace_photons() (photon_tracer.c:203): emits this rank's shard of photons on the device.
+ * frt_photons_export/import move the stored photons (32 B records: float3 pos+power packed)
+ * so ranks can all-gather them; frt_photons_finish builds the device kd-tree (pm_balance, pm.c:329).
+ */
+int frt_photons_emit(frt_scene *scene, const frt_photon_cfg *cfg, frt_stats *stats);
+int64_t frt_photons_count(frt_scene *scene, int map);
+int frt_photons_export(frt_scene *scene, int map, void *host_or_device_dst, int dst_is_device);
+int frt_photons_import(frt_scene *scene, int map, const void *src, int64_t count, int src_is_device);
+int frt_photons_finish(frt_scene *scene);
+
+/* Peak FP64/FP32 FMA issue rate of the device, measured by a register-resident FMA loop (TFLOP/s). */
+int frt_measure_fma_peak(int device, double *fp64_tflops, double *fp32_tflops);
+
+/* Scene blobs (test fixtures / cross-process hand-off): flat little-endian dump of frt_scene_desc. */
+int frt_scene_save(const frt_scene_desc *desc, const char *path);
+int frt_scene_load(const char *path, frt_scene_desc **out);
+void frt_scene_desc_free(frt_scene_desc *desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRT_B200_H */

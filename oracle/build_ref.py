@@ -1,0 +1,214 @@
+#!/usr/bin/env python3
+"""Build the reference-backed test artefacts under oracle/_ref/ (TEST INFRASTRUCTURE, not product).
+
+The reference (gbordelon/fast_ray_tracer, C11) compiles from its own source files with plain gcc, so the
+strongest oracle is the reference itself.  This script compiles the sources WHERE THEY LIE under
+/root/reference (nothing is copied into the repository), writes only into oracle/_ref/ (git-ignored, but it
+travels to the GPU box with the gpurun snapshot) and produces, per scene:
+
+    oracle/_ref/<scene>_ref    the unmodified reference program (pthread CPU renderer), wrapped by
+                               oracle/ref_hooks.c for timing / ray counting / raw canvas dumps
+    oracle/_ref/<scene>_b200   the same generated main.c + the reference's host-side scene construction, with
+                               renderer.c and photon_tracer.c replaced by fast_ray_tracer_b200/csrc/frt_shim.c
+                               and linked against libfrt_b200.so  (the drop-in build of INTEGRATION.md)
+    oracle/_ref/blobs/<scene>.frt   the flattened scene (frt_scene_save), made by running <scene>_b200 with
+                               FRT_DUMP_ONLY=1 -- no GPU needed
+
+Accommodations, all harness-side: -std=gnu11 (drand48 / M_PI), core_select.c excluded
+(mach-only), a stub png.h (oracle/png_stub).  The reference's own build system is not run.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+REF = Path(os.environ.get("FRT_REFERENCE_ROOT", "/root/reference"))
+OUT = REPO / "oracle" / "_ref"
+OBJ = OUT / "obj"
+GEN = OUT / "gen"
+BLOBS = OUT / "blobs"
+LIBDIR = REPO / "fast_ray_tracer_b200"
+
+CFLAGS = ["-std=gnu11", "-O2", "-march=x86-64-v3", "-fPIC", "-w"]
+WRAPS = ["-Wl,--wrap=render_multi", "-Wl,--wrap=intersect_world", "-Wl,--wrap=write_ppm_file", "-Wl,--wrap=write_png"]
+
+# name -> (yaml relative to the reference root, edit function on the parsed YAML list)
+
+
+def _config(tree):
+    for obj in tree:
+        if isinstance(obj, dict) and obj.get("add") == "config":
+            return obj
+    return None
+
+
+def _direct_only(tree):
+    cfg = _config(tree)
+    cfg["illumination"]["include-global"] = False
+    cfg["illumination"]["global-illumination"]["photon-count"] = 0
+    return tree
+
+
+def _cache_size(tree, n):
+    for obj in tree:
+        if isinstance(obj, dict) and obj.get("add") == "light" and "corner" in obj:
+            obj["cache-size"] = n
+    return tree
+
+
+def edit_none(tree):
+    return tree
+
+
+def edit_cornell_exact(tree):
+    return _cache_size(_direct_only(tree), 1)
+
+
+def edit_cornell_shipped(tree):
+    return _direct_only(tree)
+
+
+SCENES = {
+    # C1
+    "reflect_refract": ("scenes/reflect_refract/reflect_refract.yml", edit_none),
+    # C2 exact (deterministic: one cached sample set) and as shipped (65535 sets picked with rand())
+    "cornell_exact": ("scenes/cornell_box/cornell_box.yml", edit_cornell_exact),
+    "cornell_shipped": ("scenes/cornell_box/cornell_box.yml", edit_cornell_shipped),
+    # primitive / CSG / group coverage
+    "group_test": ("scenes/group_test/group.yml", edit_none),
+    "csg_test": ("scenes/test/test.yml", edit_none),
+    "reflect_refract_test": ("scenes/reflect_refract_test/test.yml", edit_none),
+    "checkered_torus": ("scenes/checkered_torus/checkered_torus.yml", edit_none),
+    "checkered_sphere": ("scenes/checkered_sphere/checkered_sphere.yml", edit_none),
+    "checkered_cube": ("scenes/checkered_cube/checkered_cube.yml", edit_none),
+    "checkered_cylinder": ("scenes/checkered_cylinder/checkered_cylinder.yml", edit_none),
+    "align_check_plane": ("scenes/align_check_plane/align_check_plane.yml", edit_none),
+    "lens_test": ("scenes/lens_test/lens_test.yml", edit_none),
+    "shadow_glamour_shot": ("scenes/shadow_glamour_shot/shadow_glamour_shot.yml", lambda t: _cache_size(t, 1)),
+    # C3
+    "teapot": ("scenes/teapot/teapot.yml", edit_none),
+    "bounding_boxes": ("scenes/bounding_boxes/bounding_boxes.yml", edit_none),
+}
+
+
+def run(cmd, **kw):
+    r = subprocess.run(cmd, **kw)
+    if r.returncode != 0:
+        raise SystemExit(f"command failed ({r.returncode}): {' '.join(map(str, cmd))}")
+    return r
+
+
+def reference_sources():
+    srcs = sorted(p for p in (REF / "src").rglob("*.c") if "core_select" not in p.parts)
+    return srcs
+
+
+def obj_path(src: Path) -> Path:
+    rel = src.relative_to(REF / "src")
+    return OBJ / ("__".join(rel.with_suffix("").parts) + ".o")
+
+
+def build_objects(force=False):
+    OBJ.mkdir(parents=True, exist_ok=True)
+    for src in reference_sources():
+        o = obj_path(src)
+        if force or not o.exists() or o.stat().st_mtime < src.stat().st_mtime:
+            run(["gcc", *CFLAGS, "-I", str(REPO / "oracle" / "png_stub"), "-c", str(src), "-o", str(o)])
+    hooks = OBJ / "ref_hooks.o"
+    hsrc = REPO / "oracle" / "ref_hooks.c"
+    if force or not hooks.exists() or hooks.stat().st_mtime < hsrc.stat().st_mtime:
+        run(["gcc", *CFLAGS, "-I", str(REF), "-I", str(REPO / "oracle" / "png_stub"), "-c", str(hsrc), "-o", str(hooks)])
+    shim = OBJ / "frt_shim.o"
+    ssrc = LIBDIR / "csrc" / "frt_shim.c"
+    if force or not shim.exists() or shim.stat().st_mtime < ssrc.stat().st_mtime:
+        run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-Wall", "-I", str(REF), "-I", str(REPO / "include"),
+             "-I", str(REPO / "oracle" / "png_stub"), "-c", str(ssrc), "-o", str(shim)])
+
+
+def generate_main(name: str) -> Path:
+    import yaml
+
+    rel, edit = SCENES[name]
+    GEN.mkdir(parents=True, exist_ok=True)
+    with open(REF / rel) as f:
+        tree = yaml.safe_load(f)
+    tree = edit(copy.deepcopy(tree))
+    yml = GEN / f"{name}.yml"
+    with open(yml, "w") as f:
+        yaml.safe_dump(tree, f, default_flow_style=None, sort_keys=False)
+    main_c = GEN / f"{name}.c"
+    # the generator does flat imports and the scenes use reference-root-relative asset paths: run it from there
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    with open(main_c, "w") as f:
+        run([sys.executable, str(REF / "yaml_parser" / "yaml_parser.py"), str(yml)], cwd=str(REF), stdout=f, env=env)
+    return main_c
+
+
+def build_scene(name: str, force=False):
+    main_c = generate_main(name)
+    main_o = OBJ / f"main__{name}.o"
+    run(["gcc", *CFLAGS, "-I", str(REF), "-I", str(REPO / "oracle" / "png_stub"), "-c", str(main_c), "-o", str(main_o)])
+    all_objs = [str(obj_path(s)) for s in reference_sources()]
+    hooks = str(OBJ / "ref_hooks.o")
+    ref_bin = OUT / f"{name}_ref"
+    run(["gcc", "-o", str(ref_bin), str(main_o), *all_objs, hooks, *WRAPS, "-lm", "-lpthread"])
+    replaced = {"renderer__renderer.o", "renderer__photon_tracer.o"}
+    host_objs = [o for o in all_objs if Path(o).name not in replaced]
+    b200_bin = OUT / f"{name}_b200"
+    run(["gcc", "-o", str(b200_bin), str(main_o), *host_objs, str(OBJ / "frt_shim.o"), hooks, *WRAPS,
+         "-L", str(LIBDIR), "-lfrt_b200", "-Wl,-rpath,$ORIGIN/../../fast_ray_tracer_b200", "-lm", "-lpthread"])
+    return ref_bin, b200_bin
+
+
+def dump_blob(name: str, extra_env=None, suffix="") -> Path:
+    """Run the drop-in build with FRT_DUMP_ONLY=1 from the reference root (asset paths) and keep the blob."""
+    BLOBS.mkdir(parents=True, exist_ok=True)
+    blob = BLOBS / f"{name}{suffix}.frt"
+    env = dict(os.environ, FRT_DUMP_SCENE=str(blob), FRT_DUMP_ONLY="1", FRT_SKIP_PPM="1")
+    env.update(extra_env or {})
+    run([str(OUT / f"{name}_b200")], cwd=str(REF), env=env, stdout=subprocess.DEVNULL)
+    return blob
+
+
+def run_reference(name: str, canvas_out: Path, extra_env=None, threads=None):
+    env = dict(os.environ, FRT_CANVAS_OUT=str(canvas_out), FRT_SKIP_PPM="1")
+    env["FRT_REF_THREADS"] = str(threads or os.cpu_count() or 1)
+    env.update(extra_env or {})
+    r = run([str(OUT / f"{name}_ref")], cwd=str(REF), env=env, stdout=subprocess.PIPE, text=True)
+    info = {}
+    for line in r.stdout.splitlines():
+        if line.startswith("FRT_"):
+            k, _, v = line.partition(" ")
+            info[k] = v
+    return info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("scenes", nargs="*", default=[], help="scene names (default: all)")
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--no-blobs", action="store_true")
+    args = ap.parse_args()
+    if not REF.exists():
+        print(f"reference tree {REF} not present: keeping the prebuilt oracle/_ref as is")
+        return 0
+    if not (LIBDIR / "libfrt_b200.so").exists():
+        raise SystemExit("build fast_ray_tracer_b200/libfrt_b200.so first (python -m fast_ray_tracer_b200.build)")
+    names = args.scenes or list(SCENES)
+    build_objects(force=args.force)
+    for name in names:
+        build_scene(name, force=args.force)
+        if not args.no_blobs:
+            dump_blob(name)
+        print(f"built {name}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

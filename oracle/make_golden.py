@@ -1,0 +1,73 @@
+#!/usr/bin/env python3
+"""Render golden canvases with the UNMODIFIED reference (oracle/_ref/<scene>_ref) and store them as small
+fixtures under tests/golden/ together with the flattened scene blob the CUDA path renders.
+
+Run here (the reference tree must be present); the fixtures travel to the GPU box through git.
+    python oracle/make_golden.py            # all entries of GOLDEN
+    python oracle/make_golden.py cornell_exact_200
+Each fixture <name>.npz holds: rgb (float32 linear canvas), srgb8 (uint8), meta (json: scene, size, spp, reference
+seconds / threads / ray count from the wrapped intersect_world counter).
+"""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import build_ref  # noqa: E402
+from compare import read_canvas_dump, to_srgb8  # noqa: E402
+
+REPO = Path(__file__).resolve().parent.parent
+GOLD = REPO / "tests" / "golden"
+
+# fixture name -> (scene, hsize, vsize, usteps, vsteps)   (0 = the scene's own value)
+GOLDEN = {
+    "reflect_refract": ("reflect_refract", 0, 0, 0, 0),
+    "cornell_exact_200": ("cornell_exact", 200, 200, 4, 4),
+    "cornell_exact_96_1spp": ("cornell_exact", 96, 96, 1, 1),
+    "group_test": ("group_test", 0, 0, 0, 0),
+    "csg_test": ("csg_test", 200, 200, 0, 0),
+    "reflect_refract_test": ("reflect_refract_test", 0, 0, 0, 0),
+    "checkered_torus": ("checkered_torus", 200, 200, 0, 0),
+    "checkered_sphere": ("checkered_sphere", 200, 200, 0, 0),
+    "checkered_cube": ("checkered_cube", 400, 200, 0, 0),
+    "checkered_cylinder": ("checkered_cylinder", 200, 200, 0, 0),
+    "align_check_plane": ("align_check_plane", 200, 200, 0, 0),
+    "lens_test": ("lens_test", 300, 150, 0, 0),
+    "shadow_glamour_shot": ("shadow_glamour_shot", 300, 120, 0, 0),
+    "teapot": ("teapot", 200, 200, 0, 0),
+}
+
+
+def make(name: str):
+    scene, hs, vs, us, vsteps = GOLDEN[name]
+    env = {"FRT_COUNT_RAYS": "1"}
+    if hs:
+        env.update(FRT_REF_HSIZE=str(hs), FRT_REF_VSIZE=str(vs))
+    if us:
+        env.update(FRT_REF_USTEPS=str(us), FRT_REF_VSTEPS=str(vsteps))
+    GOLD.mkdir(parents=True, exist_ok=True)
+    with tempfile.TemporaryDirectory() as td:
+        dump = Path(td) / "canvas.bin"
+        info = build_ref.run_reference(scene, dump, env)
+        rgb = read_canvas_dump(dump)
+    blob = build_ref.dump_blob(scene, env, suffix=f"__{name}")
+    shutil.copyfile(blob, GOLD / f"{name}.frt")
+    meta = {"scene": scene, "hsize": rgb.shape[1], "vsize": rgb.shape[0],
+            "reference_seconds": float(info.get("FRT_RENDER_SECONDS", "nan")),
+            "reference_threads": int(info.get("FRT_THREADS", "0")),
+            "reference_rays": int(info.get("FRT_RAYS", "0")), "size_line": info.get("FRT_SIZE", "")}
+    np.savez_compressed(GOLD / f"{name}.npz", rgb=rgb.astype(np.float32), srgb8=to_srgb8(rgb).astype(np.uint8),
+                        meta=json.dumps(meta))
+    print(name, meta)
+
+
+if __name__ == "__main__":
+    for n in (sys.argv[1:] or list(GOLDEN)):
+        make(n)
