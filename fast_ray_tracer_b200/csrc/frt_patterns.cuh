@@ -342,41 +342,41 @@ uv_pattern_at(const DScene &S, const frt_pattern &P, double u, double v, double 
  * parent writes into a concrete child (the reference mutates the shared child, pattern.c:56-57; here it is a
  * per-thread override, which is what a race-free run of the reference computes).
  */
-__device__ void
-pattern_at_shape(const DScene &S, int pat, int leaf, const double wp[3], const double *ov, double out[3], int depth)
+#define FRT_PATTERN_DEPTH 3 /* abstract patterns (blended / nested / perturbed) may nest this deep */
+template <int D>
+__device__ __noinline__ void
+pattern_at_shape_d(const DScene &S, int pat, int leaf, const double wp[3], const double *ov, double out[3])
 {
     const frt_pattern &P = S.pats[pat];
-    if (depth > 6) {
-        out[0] = out[1] = out[2] = 0.0;
-        return;
-    }
-    if (P.type == FRT_PAT_BLENDED) {
-        double c1[3], c2[3];
-        pattern_at_shape(S, P.i[0], leaf, wp, NULL, c1, depth + 1);
-        pattern_at_shape(S, P.i[1], leaf, wp, NULL, c2, depth + 1);
-        for (int k = 0; k < 3; ++k) {
-            out[k] = (c1[k] + c2[k]) / 2.0;
+    if (P.type == FRT_PAT_BLENDED || P.type == FRT_PAT_NESTED || P.type == FRT_PAT_PERTURBED) {
+        if constexpr (D > 0) {
+            if (P.type == FRT_PAT_BLENDED) {
+                double c1[3], c2[3];
+                pattern_at_shape_d<D - 1>(S, P.i[0], leaf, wp, NULL, c1);
+                pattern_at_shape_d<D - 1>(S, P.i[1], leaf, wp, NULL, c2);
+                for (int k = 0; k < 3; ++k) {
+                    out[k] = (c1[k] + c2[k]) / 2.0;
+                }
+            } else if (P.type == FRT_PAT_NESTED) {
+                double ab[6];
+                pattern_at_shape_d<D - 1>(S, P.i[1], leaf, wp, NULL, ab);
+                pattern_at_shape_d<D - 1>(S, P.i[2], leaf, wp, NULL, ab + 3);
+                int ct = S.pats[P.i[0]].type;
+                bool concrete = ct <= FRT_PAT_STRIPE;
+                pattern_at_shape_d<D - 1>(S, P.i[0], leaf, wp, concrete ? ab : NULL, out);
+            } else {
+                double x = wp[0], y = wp[1], z = wp[2];
+                double q[3];
+                q[0] = wp[0] + P.f[1] * perlin_pnoise3d(x, y, z, P.f[2], P.f[0], P.i[1], P.i[2]);
+                z = z < 0 ? z - 1.0 : z + 1.0;
+                q[1] = wp[1] + P.f[1] * perlin_pnoise3d(x, y, z, P.f[2], P.f[0], P.i[1], P.i[2]);
+                z = z < 0 ? z - 1.0 : z + 1.0;
+                q[2] = wp[2] + P.f[1] * perlin_pnoise3d(x, y, z, P.f[2], P.f[0], P.i[1], P.i[2]);
+                pattern_at_shape_d<D - 1>(S, P.i[0], leaf, q, NULL, out);
+            }
+        } else {
+            out[0] = out[1] = out[2] = 0.0; /* nesting deeper than FRT_PATTERN_DEPTH (rejected at scene creation) */
         }
-        return;
-    }
-    if (P.type == FRT_PAT_NESTED) {
-        double ab[6];
-        pattern_at_shape(S, P.i[1], leaf, wp, NULL, ab, depth + 1);
-        pattern_at_shape(S, P.i[2], leaf, wp, NULL, ab + 3, depth + 1);
-        int ct = S.pats[P.i[0]].type;
-        bool concrete = ct <= FRT_PAT_STRIPE;
-        pattern_at_shape(S, P.i[0], leaf, wp, concrete ? ab : NULL, out, depth + 1);
-        return;
-    }
-    if (P.type == FRT_PAT_PERTURBED) {
-        double x = wp[0], y = wp[1], z = wp[2];
-        double q[3];
-        q[0] = wp[0] + P.f[1] * perlin_pnoise3d(x, y, z, P.f[2], P.f[0], P.i[1], P.i[2]);
-        z = z < 0 ? z - 1.0 : z + 1.0;
-        q[1] = wp[1] + P.f[1] * perlin_pnoise3d(x, y, z, P.f[2], P.f[0], P.i[1], P.i[2]);
-        z = z < 0 ? z - 1.0 : z + 1.0;
-        q[2] = wp[2] + P.f[1] * perlin_pnoise3d(x, y, z, P.f[2], P.f[0], P.i[1], P.i[2]);
-        pattern_at_shape(S, P.i[0], leaf, q, NULL, out, depth + 1);
         return;
     }
 
@@ -420,4 +420,10 @@ pattern_at_shape(const DScene &S, int pat, int leaf, const double wp[3], const d
         out[1] = pp[1];
         out[2] = pp[2];
     }
+}
+
+__device__ __forceinline__ void
+pattern_at_shape(const DScene &S, int pat, int leaf, const double wp[3], const double *ov, double out[3], int)
+{
+    pattern_at_shape_d<FRT_PATTERN_DEPTH>(S, pat, leaf, wp, ov, out);
 }

@@ -58,7 +58,7 @@ def make(name: str):
         info = build_ref.run_reference(scene, dump, env)
         rgb = read_canvas_dump(dump)
     blob = build_ref.dump_blob(scene, env, suffix=f"__{name}")
-    shutil.copyfile(blob, GOLD / f"{name}.frt")
+    shutil.move(str(blob), GOLD / f"{name}.frt")
     meta = {"scene": scene, "hsize": rgb.shape[1], "vsize": rgb.shape[0],
             "reference_seconds": float(info.get("FRT_RENDER_SECONDS", "nan")),
             "reference_threads": int(info.get("FRT_THREADS", "0")),
