@@ -119,7 +119,7 @@ class frt_photon_cfg(C.Structure):
 
 #: every symbol include/frt_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "frt_abi_version", "frt_last_error", "frt_device_count", "frt_scene_create", "frt_scene_destroy",
+    "frt_abi_version", "frt_abi_sizeof", "frt_last_error", "frt_device_count", "frt_canvas_device_ptr", "frt_scene_create", "frt_scene_destroy",
     "frt_render", "frt_canvas_download", "frt_owned_rows", "frt_photons_emit", "frt_photons_count",
     "frt_photons_export", "frt_photons_import", "frt_photons_finish", "frt_measure_fma_peak",
     "frt_scene_save", "frt_scene_load", "frt_scene_desc_free",
@@ -146,6 +146,8 @@ def load_library():
     lib.frt_scene_destroy.restype = None
     lib.frt_render.argtypes = [C.c_void_p, C.POINTER(frt_render_cfg), C.c_void_p, C.POINTER(frt_stats)]
     lib.frt_canvas_download.argtypes = [C.c_void_p, C.c_void_p]
+    lib.frt_canvas_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.frt_abi_sizeof.argtypes = [C.c_char_p]
     lib.frt_owned_rows.argtypes = [C.POINTER(frt_scene_desc), C.POINTER(frt_render_cfg), C.POINTER(C.c_int32), C.c_int]
     lib.frt_measure_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.frt_scene_save.argtypes = [C.POINTER(frt_scene_desc), C.c_char_p]
@@ -324,6 +326,20 @@ class Scene:
                             light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow,
                             rows_rendered=st.rows_rendered)
         return (out if download else None), stats
+
+    def canvas_tensor(self):
+        """The device-resident frame as a torch tensor view [vsize, hsize, 4] float64 (no copy)."""
+        import torch
+
+        cam = self.desc.camera
+        ptr = C.c_void_p()
+        _check(load_library().frt_canvas_device_ptr(self._h, C.byref(ptr)), "frt_canvas_device_ptr")
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (cam.vsize, cam.hsize, 4), "typestr": "<f8",
+                                        "data": (int(ptr.value), False), "version": 2}
+
+        return torch.as_tensor(_View(), device=f"cuda:{self.device}")
 
     def download(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         cam = self.desc.camera

@@ -54,6 +54,17 @@ frt_abi_version(void)
     return FRT_ABI_VERSION;
 }
 
+extern "C" int
+frt_abi_sizeof(const char *name)
+{
+    if (name == nullptr) return -1;
+#define SZ(T) if (strcmp(name, #T) == 0) return (int)sizeof(T)
+    SZ(frt_node); SZ(frt_xform); SZ(frt_material); SZ(frt_pattern); SZ(frt_texture); SZ(frt_light);
+    SZ(frt_camera); SZ(frt_config); SZ(frt_scene_desc); SZ(frt_render_cfg); SZ(frt_stats); SZ(frt_photon_cfg);
+#undef SZ
+    return -1;
+}
+
 #define CK(call)                                                                                             \
     do {                                                                                                     \
         cudaError_t e_ = (call);                                                                             \
@@ -1137,6 +1148,16 @@ frt_canvas_download(frt_scene *sc, double *canvas_rgba)
     size_t bytes = (size_t)sc->C.hsize * sc->C.vsize * 4 * sizeof(double);
     CK(cudaMemcpyAsync(canvas_rgba, sc->canvas, bytes, cudaMemcpyDeviceToHost, sc->stream));
     CK(cudaStreamSynchronize(sc->stream));
+    return FRT_OK;
+}
+
+extern "C" int
+frt_canvas_device_ptr(frt_scene *sc, void **device_ptr)
+{
+    if (sc == nullptr || device_ptr == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_canvas_device_ptr: null argument");
+    }
+    *device_ptr = sc->canvas;
     return FRT_OK;
 }
 

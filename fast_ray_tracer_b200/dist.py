@@ -1,0 +1,55 @@
+"""Multi-GPU frame: image row blocks partitioned over ranks, scene replicated, canvas gathered to rank 0.
+
+One process per GPU (torch.distributed; NCCL on the GPU box, gloo in the CPU tests).  The reference already
+decomposes a frame by rows (renderer.c:260-271); here rank r owns the row blocks b with b % world == r, interleaved
+so that the dark and bright halves of a scene are spread over the ranks.  There is no data-path collective while
+rendering; the only exchange is the final gather of each rank's rows (<= 20 MB for 800x800) to rank 0.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def owned_rows(vsize: int, rank: int, world: int, rows_per_block: int = 4) -> np.ndarray:
+    """Rows y with (y // rows_per_block) % world == rank -- same rule as frt_owned_rows in the C ABI."""
+    y = np.arange(vsize)
+    return y[(y // rows_per_block) % world == rank].astype(np.int32)
+
+
+def gather_rows(local_rows: torch.Tensor, vsize: int, rank: int, world: int, rows_per_block: int = 4,
+                group=None) -> Optional[torch.Tensor]:
+    """Gather every rank's packed rows [n_owned, hsize, 4] to rank 0 and scatter them into a full canvas.
+
+    Returns the [vsize, hsize, 4] canvas on rank 0, None elsewhere.
+    """
+    hsize = local_rows.shape[1]
+    counts = [len(owned_rows(vsize, r, world, rows_per_block)) for r in range(world)]
+    assert local_rows.shape[0] == counts[rank]
+    if world == 1:
+        return local_rows
+    pad = max(counts)
+    buf = torch.zeros((pad, hsize, 4), dtype=local_rows.dtype, device=local_rows.device)
+    buf[: counts[rank]] = local_rows
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    canvas = torch.zeros((vsize, hsize, 4), dtype=local_rows.dtype, device=local_rows.device)
+    for r in range(world):
+        rows = torch.as_tensor(owned_rows(vsize, r, world, rows_per_block), device=local_rows.device, dtype=torch.long)
+        canvas[rows] = parts[r][: counts[r]]
+    return canvas
+
+
+def render_distributed(scene, rank: int, world: int, rows_per_block: int = 4, group=None, **render_kw):
+    """Render this rank's rows on its GPU and gather the frame on rank 0 (device tensor).  Returns (canvas|None, stats)."""
+    vsize = scene.desc.camera.vsize
+    _, stats = scene.render(rank=rank, world=world, rows_per_block=rows_per_block, download=False, **render_kw)
+    frame = scene.canvas_tensor()
+    rows = torch.as_tensor(owned_rows(vsize, rank, world, rows_per_block), device=frame.device, dtype=torch.long)
+    local = frame.index_select(0, rows)
+    return gather_rows(local, vsize, rank, world, rows_per_block, group), stats

@@ -237,6 +237,8 @@ typedef struct frt_photon_cfg {
 int frt_abi_version(void);
 const char *frt_last_error(void);
 int frt_device_count(void);
+/* layout check for foreign-language bindings: sizeof of a named ABI struct ("frt_node", "frt_light", ...), or -1 */
+int frt_abi_sizeof(const char *struct_name);
 
 /* Upload a flattened scene (host pointers in desc are read during the call only). */
 int frt_scene_create(const frt_scene_desc *desc, int device, frt_scene **out);
@@ -244,12 +246,14 @@ void frt_scene_destroy(frt_scene *scene);
 
 /*
  * Replaces render_multi()/render() (renderer.c:243/:283).  canvas_rgba has the layout of Canvas.arr
- * (canvas.h:10-17): hsize*vsize Color = double[4], row-major, linear RGB, 4th lane untouched.
+ * (canvas.h:10-17): hsize*vsize Color = double[4], row-major, linear RGB, 4th lane 0 as the reference leaves it.
  * Only the rows owned by (rank, world) are written.  canvas_rgba may be NULL (frame stays on device;
  * fetch it later with frt_canvas_download).
  */
 int frt_render(frt_scene *scene, const frt_render_cfg *cfg, double *canvas_rgba, frt_stats *stats);
 int frt_canvas_download(frt_scene *scene, double *canvas_rgba);
+/* the frame where it lives: device pointer to hsize*vsize*4 doubles, valid until frt_scene_destroy (for NCCL gathers) */
+int frt_canvas_device_ptr(frt_scene *scene, void **device_ptr);
 /* rows owned by (rank, world): writes up to cap row indices, returns the count */
 int frt_owned_rows(const frt_scene_desc *desc, const frt_render_cfg *cfg, int32_t *rows, int cap);
 

@@ -1,0 +1,26 @@
+import sys
+from pathlib import Path
+
+import pytest
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "oracle"))
+
+GOLDEN = REPO / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def frt():
+    import fast_ray_tracer_b200 as frt
+
+    frt.load_library()
+    return frt
+
+
+def golden_names():
+    return sorted(p.stem for p in GOLDEN.glob("*.npz"))

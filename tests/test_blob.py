@@ -1,0 +1,97 @@
+"""Host logic: scene blobs written by the C shim (flattened reference World) load back intact."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_names
+
+GROUP, CSG, CUBE, SPHERE = 9, 8, 1, 5
+
+
+def nodes_of(desc):
+    d = desc.c
+    return [d.nodes[i] for i in range(d.n_nodes)]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_blob_is_well_formed(frt, name):
+    desc = frt.SceneDesc.load(GOLDEN / f"{name}.frt")
+    d = desc.c
+    assert d.n_nodes > 0 and d.n_roots >= 1 and d.n_xforms >= 1
+    ident = np.array(d.xforms[0].inv[:]).reshape(3, 4)
+    assert np.array_equal(ident, np.eye(4)[:3])
+    for i, n in enumerate(nodes_of(desc)):
+        assert i < n.skip <= d.n_nodes
+        assert 0 <= n.xform < d.n_xforms
+        assert -1 <= n.parent < i
+        if n.type < CSG:
+            assert 0 <= n.material < d.n_materials
+        if n.type == CSG:
+            assert i + 1 < n.right < n.skip
+    cam = desc.camera
+    assert cam.hsize > 0 and cam.vsize > 0 and d.n_pixel_samples == 2 * cam.usteps * cam.vsteps
+
+
+def test_cornell_tree_matches_the_reference_divide(frt):
+    """SURVEY.md 3.5 fixture: the Cornell tree after divide(1), child order exactly as the reference holds it."""
+    desc = frt.SceneDesc.load(GOLDEN / "cornell_exact_200.frt")
+    ns = nodes_of(desc)
+
+    def children(i):
+        out, j = [], i + 1
+        while j < ns[i].skip:
+            out.append(j)
+            j = ns[j].skip
+        return out
+
+    root = desc.c.roots[0]
+    top = children(root)
+    assert [ns[i].type for i in top] == [GROUP, GROUP, CUBE, CUBE, CUBE, CUBE]
+    left, right = top[0], top[1]
+    assert [ns[i].type for i in children(left)] == [GROUP, CUBE]
+    assert [ns[i].type for i in children(children(left)[0])] == [SPHERE]
+    assert [ns[i].type for i in children(right)] == [CSG, CUBE]
+    csg = children(right)[0]
+    assert ns[csg].csg_op == 2  # difference
+    inner = children(csg)
+    assert [ns[i].type for i in inner] == [CSG, CUBE] and ns[inner[0]].csg_op == 0  # union
+    assert [ns[i].type for i in children(inner[0])] == [CUBE, CUBE]
+    # divide-created groups are identity; every primitive carries its own transform
+    for i, n in enumerate(ns):
+        if n.type == GROUP:
+            assert n.xform == 0
+        elif n.type < CSG:
+            assert n.xform != 0
+    light = desc.c.lights[0]
+    assert light.num_samples == 100 and light.cache_len == 1 and desc.c.n_light_points == 100
+
+
+def test_save_load_round_trip(frt, tmp_path):
+    a = frt.SceneDesc.load(GOLDEN / "teapot.frt")
+    a.save(tmp_path / "copy.frt")
+    assert (tmp_path / "copy.frt").read_bytes() == (GOLDEN / "teapot.frt").read_bytes()
+    b = frt.SceneDesc.load(tmp_path / "copy.frt")
+    assert b.c.n_nodes == a.c.n_nodes and b.c.n_prim_params == a.c.n_prim_params
+    n = a.c.n_prim_params
+    assert np.array_equal(np.ctypeslib.as_array(a.c.prim_params, (n,)), np.ctypeslib.as_array(b.c.prim_params, (n,)))
+
+
+def test_load_rejects_garbage(frt, tmp_path):
+    p = tmp_path / "bad.frt"
+    p.write_bytes(b"\0" * 4096)
+    with pytest.raises(frt.FrtError):
+        frt.SceneDesc.load(p)
+    with pytest.raises(frt.FrtError):
+        frt.SceneDesc.load(tmp_path / "missing.frt")
+
+
+def test_set_resolution_follows_the_reference_camera(frt):
+    desc = frt.SceneDesc.load(GOLDEN / "reflect_refract.frt")
+    cam = desc.camera
+    hw, ps = cam.half_width, cam.pixel_size
+    desc.set_resolution(800, 400)  # same aspect: half extents unchanged, pixel halves
+    assert cam.half_width == hw and abs(cam.pixel_size - ps / 2) < 1e-15
+    desc.set_resolution(200, 400)  # portrait: camera.c:127-130
+    assert abs(cam.half_height - hw) < 1e-15 and abs(cam.half_width - hw * 0.5) < 1e-15
