@@ -323,9 +323,9 @@ k_raygen(DCamera C, FrameParams F, RayQ q, Counters *cnt, unsigned int first_sam
 /* ------------------------------------------------------------------------------------------------ extend */
 
 __global__ void __launch_bounds__(256)
-k_extend(DScene S, RayQ q, HitQ h, Counters *cnt, int level)
+k_extend(DScene S, RayQ q, HitQ h, Counters *cnt, int level, unsigned int capacity)
 {
-    const unsigned int n = cnt->n_rays[level];
+    const unsigned int n = min(cnt->n_rays[level], capacity); /* an overflowed level is clamped; the frame is re-run */
     int overflow = 0;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Ray r{ q.ox[i], q.oy[i], q.oz[i], q.dx[i], q.dy[i], q.dz[i] };
@@ -357,7 +357,7 @@ material_color(const DScene &S, int map, const double *flat, int leaf, const dou
 __global__ void __launch_bounds__(128)
 k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counters *cnt, int level)
 {
-    const unsigned int n = cnt->n_rays[level];
+    const unsigned int n = min(cnt->n_rays[level], F.capacity);
     const int remaining = F.path_length - level;
     int overflow = 0;
     unsigned long long n_secondary = 0, n_shaded = 0;
@@ -792,6 +792,7 @@ struct frt_scene {
     int samples_u = 0, samples_v = 0;
     /* frame buffers, sized lazily */
     unsigned int capacity = 0;
+    unsigned int chunk_samples = 12u << 20, cap_factor = 2;
     RayQ q[2]{};
     HitQ hq{};
     LightRec *recs = nullptr;
@@ -1162,7 +1163,7 @@ frt_canvas_device_ptr(frt_scene *sc, void **device_ptr)
 }
 
 static int
-render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned int chunk_samples)
+render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned int chunk_samples, unsigned int cap_factor)
 {
     const frt_config &g = sc->cfg;
     DCamera C = sc->C;
@@ -1212,7 +1213,8 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         return frt_set_error(FRT_ERR_ARG, "frame has too many samples for 32-bit sample ids");
     }
     unsigned int chunk = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(total, 1), chunk_samples);
-    unsigned int capacity = chunk * 2u;
+    unsigned long long want = (unsigned long long)chunk * cap_factor;
+    unsigned int capacity = (unsigned int)std::min<unsigned long long>(want, 0x7fffffffULL);
     int rc = ensure_frame_buffers(sc, capacity);
     if (rc != FRT_OK) {
         return rc;
@@ -1253,7 +1255,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             /* level 0 has n rays; deeper levels read their count on the device: size the grid for the worst case
              * the level can hold, but never more than a few waves */
             int ex_blocks = sm_blocks * 8;
-            k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, qi, sc->hq, sc->cnt, level);
+            k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, qi, sc->hq, sc->cnt, level, F.capacity);
             k_shade<<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
             launches += 2;
             if (F.include_direct) {
@@ -1330,22 +1332,37 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
     frt_stats st;
     memset(&st, 0, sizeof(st));
 
-    unsigned int chunk = 12u << 20;
+    /* Queue sizing: a level of the wavefront holds at most chunk * cap_factor rays.  Reflective + refractive
+     * surfaces can double the ray count per level, so on overflow the frame is re-run with a larger factor (while
+     * it fits in a quarter of the free HBM) and then with smaller chunks; the working pair is kept for next frame. */
+    unsigned int chunk = sc->chunk_samples, factor = sc->cap_factor;
     const char *env = getenv("FRT_CHUNK_SAMPLES");
     if (env != nullptr && *env) {
         chunk = (unsigned int)std::max(1024L, atol(env));
     }
     int rc;
     for (;;) {
-        rc = render_once(sc, cfg, &st, chunk);
+        rc = render_once(sc, cfg, &st, chunk, factor);
         if (rc != -1) {
             break;
         }
         st.overflow += 1;
-        if (chunk <= 4096) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const unsigned long long frame_samples = std::max<unsigned long long>(st.rays_primary, 1);
+        const unsigned long long eff_chunk = std::min<unsigned long long>(chunk, frame_samples);
+        const unsigned long long slot_bytes = 2 * 84 + 28 + sizeof(LightRec);
+        if (factor < 64 && eff_chunk * factor * 2 * slot_bytes < (free_b + (unsigned long long)sc->capacity * slot_bytes) / 4) {
+            factor *= 2;
+        } else if (eff_chunk > 4096) {
+            chunk = (unsigned int)(eff_chunk / 2);
+        } else {
             return frt_set_error(FRT_ERR_OVERFLOW, "secondary-ray queue overflow even with %u-sample chunks", chunk);
         }
-        chunk /= 4;
+    }
+    if (rc == FRT_OK && (env == nullptr || !*env)) {
+        sc->chunk_samples = chunk;
+        sc->cap_factor = factor;
     }
     if (rc != FRT_OK) {
         return rc;
