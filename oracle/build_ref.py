@@ -80,6 +80,8 @@ SCENES = {
     # C2 exact (deterministic: one cached sample set) and as shipped (65535 sets picked with rand())
     "cornell_exact": ("scenes/cornell_box/cornell_box.yml", edit_cornell_exact),
     "cornell_shipped": ("scenes/cornell_box/cornell_box.yml", edit_cornell_shipped),
+    # 64 cached sets: small enough to keep as a fixture, pins fast_ray_tracer_b200/lightcache.py bit for bit
+    "cornell_cache64": ("scenes/cornell_box/cornell_box.yml", lambda t: _cache_size(_direct_only(t), 64)),
     # primitive / CSG / group coverage
     "group_test": ("scenes/group_test/group.yml", edit_none),
     "csg_test": ("scenes/test/test.yml", edit_none),

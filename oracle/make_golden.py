@@ -31,6 +31,7 @@ GOLDEN = {
     "reflect_refract": ("reflect_refract", 0, 0, 0, 0),
     "cornell_exact_200": ("cornell_exact", 200, 200, 4, 4),
     "cornell_exact_96_1spp": ("cornell_exact", 96, 96, 1, 1),
+    "cornell_exact_800": ("cornell_exact", 800, 800, 4, 4),  # BASELINE.json configs[1] at full size (~7 min on 8 cores)
     "group_test": ("group_test", 0, 0, 0, 0),
     "csg_test": ("csg_test", 200, 200, 0, 0),
     "reflect_refract_test": ("reflect_refract_test", 0, 0, 0, 0),
