@@ -1,0 +1,387 @@
+#!/usr/bin/env python3
+"""bench.py -- frame time and Mrays/s of the Cornell-box hot path (BASELINE.json: cornell_box 800x800, 4x4 CMJ,
+jittered 10x10 rectangular area light), on N B200s of one node, next to the reference's pthread CPU renderer.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # the CUDA core through the C ABI
+    python bench.py --impl reference [--steps K] [--warmup W]    # the UNMODIFIED reference on the host cores
+
+A step is one frame.  The workload is the reference's own scenes/cornell_box/cornell_box.yml with direct
+illumination only (include-global false, photon-count 0, area-light cache of 65 535 CMJ
+sample sets picked per hit), flattened by the drop-in shim into tests/golden/cornell_exact_200.frt; the camera is
+re-derived for 800x800 and the 65 535-set light cache is rebuilt on the host bit for bit
+(fast_ray_tracer_b200/lightcache.py).
+
+Unit of work, identical on both arms: *reference-counted rays* = calls of the reference's intersect_world()
+(world.c:164) for the frame -- camera, reflection/refraction and shadow rays exactly as the reference spawns them
+(331 per primary ray on this scene).  The CUDA core proves it traces the same set when told not to prune
+(FRT_FLAG_NO_PRUNE: its device counters equal the reference's wrapped counter, tests/test_gpu_parity.py); in the
+timed frames it skips rays whose weight is exactly zero, and the JSON line carries that smaller number too
+(`rays_traced_per_frame`).  value = reference-counted rays of the frame / frame time.
+
+Multi-GPU (torchrun, one process per GPU): the frame's row blocks are partitioned over the ranks, the scene is
+replicated, rank 0 gathers the rows over NCCL inside the timed region; "scaling" is strong (one frame, N GPUs).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+WORKLOAD = "cornell_box 800x800 4x4 CMJ, 10x10 jittered area light (65535 cached sample sets), direct illumination, depth 5"
+METRIC = "Mrays/s (reference-counted rays per second of frame time), cornell_box 800x800 4x4 CMJ"
+BLOB = REPO / "tests" / "golden" / "cornell_exact_200.frt"
+REF_BIN = {"shipped": REPO / "oracle" / "_ref" / "cornell_shipped_ref", "exact": REPO / "oracle" / "_ref" / "cornell_exact_ref"}
+HSIZE = VSIZE = 800
+SPP = 4
+CACHE_SETS = 65535
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md, the clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_frame(binary: Path, size: int, spp: int, threads: int, count_rays: bool) -> dict:
+    env = dict(os.environ, FRT_SKIP_PPM="1", FRT_REF_THREADS=str(threads), FRT_REF_HSIZE=str(size), FRT_REF_VSIZE=str(size),
+               FRT_REF_USTEPS=str(spp), FRT_REF_VSTEPS=str(spp), FRT_COUNT_RAYS="1" if count_rays else "0")
+    r = subprocess.run([str(binary)], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=str(binary.parent),
+                       check=True)
+    info = {}
+    for line in r.stdout.splitlines():
+        if line.startswith("FRT_"):
+            k, _, v = line.partition(" ")
+            info[k] = v
+    return {"seconds": float(info["FRT_RENDER_SECONDS"]), "rays": int(info.get("FRT_RAYS", "0")), "threads": int(info["FRT_THREADS"])}
+
+
+def reference_arm(args) -> dict:
+    """The unmodified reference (oracle/_ref/cornell_*_ref: its own sources compiled where they lie, wrapped for
+    timing) on all host cores.  Each step renders a bounded sample of the workload: the same scene and view at
+    s x s pixels (s chosen so that the run ends within a few minutes), 4x4 CMJ -- the ray mix per pixel is the
+    frame's, so the rate carries over and the 800x800 frame time is the sample's time x (800/s)^2."""
+    binary = REF_BIN[args.variant]
+    if not binary.exists():
+        return {"impl": "reference", "unavailable": f"{binary.relative_to(REPO)} not built (python oracle/build_ref.py)"}
+    threads = host_threads()
+    # calibrate on a tiny frame, then size the sample for ~150 s of total wall time
+    cal = run_reference_frame(binary, 64, SPP, threads, True)
+    px_per_s = 64 * 64 / max(cal["seconds"], 1e-6)
+    rays_per_px = cal["rays"] / (64.0 * 64.0)
+    budget = args.ref_seconds / max(args.steps + args.warmup, 1)
+    size = int(min(HSIZE, max(48, (px_per_s * budget) ** 0.5)))
+    size -= size % 8
+    for _ in range(args.warmup):
+        run_reference_frame(binary, size, SPP, threads, False)
+    times = []
+    for _ in range(args.steps):
+        times.append(run_reference_frame(binary, size, SPP, threads, False)["seconds"])
+    counted = run_reference_frame(binary, size, SPP, threads, True) if size <= 200 else None
+    rays_sample = counted["rays"] if counted else rays_per_px * size * size
+    mean_s = sum(times) / len(times)
+    value = rays_sample / mean_s / 1e6
+    frame_ms = mean_s * (HSIZE * VSIZE) / (size * size) * 1e3
+    sample = f"{size}x{size} px of the same view at 4x4 CMJ per step ({size * size / (HSIZE * VSIZE):.4f} of the frame); frame time scaled by pixel count"
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "variant": args.variant, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "reference", "sample": sample,
+                         "frame_ms_800x800": frame_ms},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+# ---------------------------------------------------------------------------------------------- CUDA arm
+
+
+def load_workload(frt, variant: str, size: int, spp: int):
+    from fast_ray_tracer_b200.lightcache import expand_area_light_caches
+
+    desc = frt.SceneDesc.load(BLOB)
+    desc.set_resolution(size, size)
+    desc.set_samples(spp, spp)
+    if variant == "shipped":
+        expand_area_light_caches(desc, CACHE_SETS)
+    return desc
+
+
+def cuda_arm(args) -> dict:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fast_ray_tracer_b200 as frt
+    from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_NO_PRUNE
+    from fast_ray_tracer_b200.dist import gather_rows, owned_rows
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the render core has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    frt.load_library()
+
+    desc = load_workload(frt, args.variant, args.size, args.spp)
+    rpb = args.rows_per_block
+    vsize, hsize = desc.camera.vsize, desc.camera.hsize
+    rows_idx = torch.as_tensor(owned_rows(vsize, rank, world, rpb), device=dev, dtype=torch.long)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with frt.Scene(desc, device=local) as sc:
+        # ---- counting frames (untimed): the reference's ray count for this frame and this kernel's event flop
+        _, st_ref = sc.render(rank=rank, world=world, rows_per_block=rpb, flags=FRT_FLAG_NO_PRUNE | FRT_FLAG_COUNT_RAYS,
+                              download=False, seed=1)
+        _, st_cnt = sc.render(rank=rank, world=world, rows_per_block=rpb, flags=FRT_FLAG_COUNT_RAYS, download=False, seed=1)
+        counts = torch.tensor([st_ref.rays_total, st_cnt.rays_total, st_cnt.rays_shadow, st_cnt.light_flops, st_cnt.hits_shaded],
+                              dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(counts)
+        ref_rays, traced_rays, shadow_rays, light_flops, hits = (float(x) for x in counts.tolist())
+
+        def step(seed):
+            _, st = sc.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=seed)
+            frame = sc.canvas_tensor()
+            if world > 1:
+                canvas = gather_rows(frame.index_select(0, rows_idx), vsize, rank, world, rpb)
+            else:
+                canvas = frame
+            return st, canvas
+
+        for w in range(args.warmup):
+            step(100 + w)
+            flush.zero_()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        frame_ms, light_ms, launches, light_launches = [], [], 0, 0
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_wall0 = time.perf_counter()
+        dev_ms_total = 0.0
+        for k in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (not part of the frame time)
+            torch.cuda.synchronize()
+            ev0.record()
+            st, canvas = step(1000 + k)
+            ev1.record()
+            torch.cuda.synchronize()
+            # the core times its own stream with CUDA events (frame_ms); the torch events bracket the NCCL gather too
+            dev_ms_total += max(st.frame_ms, ev0.elapsed_time(ev1))
+            frame_ms.append(st.frame_ms)
+            light_ms.append(st.light_ms)
+            launches += st.kernel_launches
+            light_launches += st.light_launches
+        barrier()
+        wall_s = time.perf_counter() - t_wall0
+        clk = clocks.stop() if rank == 0 else None
+
+        t = torch.tensor([dev_ms_total, sum(light_ms), float(launches), float(light_launches)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_per_step = float(tmax[0]) / args.steps
+        light_ms_per_step = float(tmax[1]) / args.steps
+        total_launches = int(t[2])
+        light_launches_per_rank_step = float(t[3]) / world / args.steps
+
+        # ---- e2e: the reference-facing call with HOST buffers: flattened scene in host memory -> upload -> frame ->
+        #      canvas back in (pinned) host memory, every step.  Multi-GPU: each rank uploads, rank 0 receives the frame.
+        pinned = torch.empty((vsize, hsize, 4), dtype=torch.float64).pin_memory()
+        out = pinned.numpy()
+        e2e_steps = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            with frt.Scene(desc, device=local) as sc2:
+                if world == 1:
+                    sc2.render(out=out, seed=2000 + k)
+                else:
+                    sc2.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=2000 + k)
+                    full = gather_rows(sc2.canvas_tensor().index_select(0, rows_idx), vsize, rank, world, rpb)
+                    if rank == 0:
+                        pinned.copy_(full)
+                torch.cuda.synchronize()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_s = float(e2e_t[0])
+
+    fp64_peak, fp32_peak = frt.measure_fma_peak(local)
+    line = None
+    if rank == 0:
+        value = ref_rays / (ms_per_step * 1e-3) / 1e6
+        # roofline of the dominant kernel (k_light: shadow rays + microfacet lighting): algorithmic flop per launch,
+        # counted event by event with the BASELINE.md cost table, over the CUDA-event duration of its launches
+        flops_per_launch = light_flops / max(light_launches_per_rank_step * world, 1)
+        launch_ms = light_ms_per_step / max(light_launches_per_rank_step, 1)
+        achieved = (light_flops / world) / (light_ms_per_step * 1e-3) / 1e12 if light_ms_per_step > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "variant": args.variant, "hsize": hsize, "vsize": vsize, "spp": args.spp * args.spp,
+                       "parallelism": f"rows/{world}" if world > 1 else "single", "rows_per_block": rpb,
+                       "l2": "256 MiB flush write between timed frames; the 157 MB light-sample cache alone exceeds L2"},
+            "frame_ms": ms_per_step,
+            "rays_reference_counted_per_frame": ref_rays, "rays_traced_per_frame": traced_rays,
+            "mrays_s_traced": traced_rays / (ms_per_step * 1e-3) / 1e6,
+            "wall_s_timed_region": wall_s,
+            "clocks": clk,
+            "e2e": {"value": ref_rays / e2e_s / 1e6, "unit": "Mrays/s", "frame_ms": e2e_s * 1e3,
+                    "h2d_bytes_per_step": int(desc.host_bytes) * world, "d2h_bytes_per_step": vsize * hsize * 32,
+                    "path": "frt_scene_create(host desc) + frt_render + canvas to pinned host memory, per step"},
+            "gpu_launches": total_launches,
+            "roofline": {"bound": "fp64-issue", "kernel": "k_light", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "register-resident FP64 FMA loop measured in this run (frt_measure_fma_peak); "
+                                        "MEASURED_PEAKS.json has no FP64/FP32 SIMT entry",
+                         "fp32_peak_tflops": fp32_peak,
+                         "flop_per_launch": flops_per_launch, "launch_ms": launch_ms,
+                         "kernel_share_of_step": light_ms_per_step / ms_per_step if ms_per_step else None,
+                         "shadow_rays_per_frame": shadow_rays, "hits_shaded_per_frame": hits},
+        }
+    if world > 1:
+        dist.barrier()
+    return line
+
+
+def cpu_baseline_leg(args) -> dict:
+    """Rank 0, N=1 only: the unmodified reference on the box's host cores, ~10-30 s of work."""
+    binary = REF_BIN[args.variant]
+    if not binary.exists():
+        return {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "reference", "sample": f"{binary.name} not built"}
+    threads = host_threads()
+    cal = run_reference_frame(binary, 48, SPP, threads, True)
+    px_per_s = 48 * 48 / max(cal["seconds"], 1e-6)
+    size = int(min(200, max(48, (px_per_s * args.cpu_seconds) ** 0.5)))
+    size -= size % 8
+    r = run_reference_frame(binary, size, SPP, threads, True)
+    value = r["rays"] / r["seconds"] / 1e6
+    return {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "reference",
+            "sample": f"{size}x{size} px of the same view, 4x4 CMJ, {r['seconds']:.2f} s", "rays": r["rays"],
+            "frame_ms_800x800": r["seconds"] * (HSIZE * VSIZE) / (size * size) * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="shipped", choices=["shipped", "exact"])
+    ap.add_argument("--size", type=int, default=HSIZE)
+    ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--rows-per-block", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=150.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(reference_arm(args)), flush=True)
+        return 0
+
+    line = cuda_arm(args)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

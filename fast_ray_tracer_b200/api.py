@@ -13,9 +13,10 @@ _PKG = Path(__file__).resolve().parent
 _LIB_PATH = _PKG / "libfrt_b200.so"
 _lib = None
 
-FRT_ABI_VERSION = 3
+FRT_ABI_VERSION = 4
 FRT_FLAG_NO_PRUNE = 1
 FRT_FLAG_COUNT_RAYS = 2
+FRT_FLAG_F64_SHADING = 4
 
 
 class FrtError(RuntimeError):
@@ -107,7 +108,7 @@ class frt_stats(C.Structure):
                 ("rays_primary", C.c_uint64), ("rays_secondary", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("rays_gather", C.c_uint64), ("rays_photon", C.c_uint64), ("hits_shaded", C.c_uint64),
                 ("light_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("shadow_nodes", C.c_uint64),
-                ("overflow", C.c_uint64), ("photons_stored", C.c_uint64 * 3),
+                ("overflow", C.c_uint64), ("photons_stored", C.c_uint64 * 3), ("light_flops", C.c_uint64),
                 ("rows_rendered", C.c_int32), ("pad", C.c_int32)]
 
 
@@ -271,6 +272,7 @@ class RenderStats:
     light_launches: int = 0
     shadow_nodes: int = 0
     overflow: int = 0
+    light_flops: int = 0
     rows_rendered: int = 0
     extra: dict = field(default_factory=dict)
 
@@ -323,7 +325,7 @@ class Scene:
         stats = RenderStats(frame_ms=st.frame_ms, light_ms=st.light_ms, download_ms=st.download_ms,
                             rays_primary=st.rays_primary, rays_secondary=st.rays_secondary, rays_shadow=st.rays_shadow,
                             rays_gather=st.rays_gather, hits_shaded=st.hits_shaded, kernel_launches=st.kernel_launches,
-                            light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow,
+                            light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow, light_flops=st.light_flops,
                             rows_rendered=st.rows_rendered)
         return (out if download else None), stats
 

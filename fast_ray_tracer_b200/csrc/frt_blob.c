@@ -15,6 +15,7 @@
 #include "frt_internal.h"
 
 #define FRT_BLOB_MAGIC 0x4e43535f54524600ULL /* "\0FRT_SCN" */
+#define FRT_BLOB_VERSION 3 /* layout of the scene description sections; independent of the call ABI */
 
 typedef struct frt_blob_header {
     uint64_t magic;
@@ -65,7 +66,7 @@ frt_scene_save(const frt_scene_desc *d, const char *path)
     frt_blob_header h;
     memset(&h, 0, sizeof(h));
     h.magic = FRT_BLOB_MAGIC;
-    h.abi_version = FRT_ABI_VERSION;
+    h.abi_version = FRT_BLOB_VERSION;
     h.n_nodes = d->n_nodes;
     h.n_roots = d->n_roots;
     h.n_xforms = d->n_xforms;
@@ -129,13 +130,13 @@ frt_scene_load(const char *path, frt_scene_desc **out)
     fclose(f);
 
     const frt_blob_header *h = (const frt_blob_header *)(block + head);
-    if (h->magic != FRT_BLOB_MAGIC || h->abi_version != FRT_ABI_VERSION) {
+    if (h->magic != FRT_BLOB_MAGIC || h->abi_version != FRT_BLOB_VERSION) {
         free(block);
-        return frt_set_error(FRT_ERR_IO, "frt_scene_load: %s is not an ABI-%d scene blob", path, FRT_ABI_VERSION);
+        return frt_set_error(FRT_ERR_IO, "frt_scene_load: %s is not a version-%d scene blob", path, FRT_BLOB_VERSION);
     }
     frt_scene_desc *d = (frt_scene_desc *)block;
     memset(d, 0, sizeof(*d));
-    d->abi_version = h->abi_version;
+    d->abi_version = FRT_ABI_VERSION;
     d->n_nodes = h->n_nodes;
     d->n_roots = h->n_roots;
     d->n_xforms = h->n_xforms;

@@ -110,7 +110,7 @@ struct Counters {
     unsigned int n_rays[8];   /* rays queued for level l */
     unsigned int n_hits[8];   /* light records of level l */
     unsigned int overflow_queue, overflow_csg;
-    unsigned long long rays_secondary, rays_shadow, hits_shaded, shadow_nodes;
+    unsigned long long rays_secondary, rays_shadow, hits_shaded, shadow_nodes, light_flops;
 };
 
 struct DCamera {
@@ -575,21 +575,37 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
 /* ------------------------------------------------------------------------------------------------ light */
 
 /*
- * One light, all shaded hits of one level.  G lanes (a power of two <= 32) share a hit and stride over the
- * light's surface samples; partial sums are combined with a fixed-order butterfly, so the result does not
- * depend on scheduling.
+ * Direct illumination of the shaded hits of one level by one light, in three kernels that each stay small enough
+ * to live in the instruction cache (the first, fused version of this stage was 107 KB of SASS and spent half of
+ * its issue slots waiting on instruction fetch; see profiles/):
  *
- *   shadow pass   area_light_intensity_at / point_light_intensity_at  light.c:229-251  -> is_shadowed renderer.c:73
- *   lighting pass lighting_microfacet                                  renderer.c:894-979
+ *   k_light_sum      lighting_microfacet's sums over the light's sample set          renderer.c:894-979
+ *   k_shadow         light->intensity_at: one shadow ray per (hit, surface sample)   light.c:229-251, renderer.c:73
+ *   k_light_resolve  shade_intensity * sums + ambient, weighted into the pixel       renderer.c:904-979, :689-827
  *
- * The reference picks one of cache_len pre-computed sample sets with rand() once per pass (light.c:196); here
- * the pick is a hash of (seed, path id, light, pass).  With cache_len == 1 both passes use set 0 and the result
- * is exactly the reference's.
+ * The reference picks one of cache_len pre-computed sample sets with rand() once per pass (light.c:196); here the
+ * pick is a hash of (seed, path id, light, pass).  With cache_len == 1 both passes use set 0 and the result is
+ * exactly the reference's.
  */
-template <int G>
+struct LightTmp { /* per shaded hit, per light launch */
+    float sum_ndl, sum_b, sum_fb; /* sums over the lighting sample set */
+    int set_a;                    /* sample set of the shadow pass; -1: the hit cannot receive light, skip its shadow rays */
+    int unshadowed;               /* shadow rays that reached the light */
+    int contributes;              /* some lighting term of the hit is non-zero */
+    double dsum_ndl, dsum_b, dsum_fb; /* the same sums in FP64 (FRT_FLAG_F64_SHADING) */
+};
+
+/*
+ * G lanes (a power of two <= 32) share a hit and stride over the samples; partial sums are combined with a
+ * fixed-order butterfly, so the result does not depend on scheduling.  T = float is the production path: the sums
+ * feed an 8-bit pixel through a continuous function, so FP32's 1e-7 relative error sits three orders of magnitude
+ * under one sRGB LSB; T = double (FRT_FLAG_F64_SHADING) keeps the reference's arithmetic type for debugging.
+ * Every geometric DECISION (hit / miss, shadowed / lit) stays in FP64 in k_extend / k_shadow.
+ */
+template <typename T, int G>
 __global__ void __launch_bounds__(256)
-k_light(DScene S, FrameParams F, const LightRec *__restrict__ recs, double *__restrict__ canvas, Counters *cnt,
-        int level, int light_idx)
+k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, const Counters *cnt,
+            int level, int light_idx)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
     const frt_light L = S.lights[light_idx];
@@ -598,8 +614,6 @@ k_light(DScene S, FrameParams F, const LightRec *__restrict__ recs, double *__re
     const unsigned int lane_g = threadIdx.x % G;
     const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     const unsigned int groups = gridDim.x * blockDim.x / G;
-    int overflow = 0;
-    unsigned long long n_shadow = 0, n_nodes = 0;
 
     for (unsigned int hbase = (blockIdx.x * blockDim.x + threadIdx.x) / G;; hbase += groups) {
         /* all lanes of a warp iterate together so that the group shuffles stay converged */
@@ -609,12 +623,11 @@ k_light(DScene S, FrameParams F, const LightRec *__restrict__ recs, double *__re
         }
         const bool live = hbase < n;
         const LightRec *R = recs + (live ? hbase : 0);
-
-        double over[3] = { R->over[0], R->over[1], R->over[2] };
-        double nrm[3] = { R->n[0], R->n[1], R->n[2] };
-        double eye[3] = { R->eye[0], R->eye[1], R->eye[2] };
-        double Ns = R->Ns;
-        unsigned int rng = R->rng;
+        const double over[3] = { R->over[0], R->over[1], R->over[2] };
+        const T nrm[3] = { (T)R->n[0], (T)R->n[1], (T)R->n[2] };
+        const T eye[3] = { (T)R->eye[0], (T)R->eye[1], (T)R->eye[2] };
+        const T Ns = (T)R->Ns;
+        const unsigned int rng = R->rng;
 
         int set_a = 0, set_b = 0;
         if (L.cache_len > 1) {
@@ -623,37 +636,38 @@ k_light(DScene S, FrameParams F, const LightRec *__restrict__ recs, double *__re
             set_b = (int)(mix64(key + 1) % (unsigned long long)L.cache_len);
         }
 
-        /* ---- lighting pass: sums over the sample set, renderer.c:927-968 */
-        double sum_ndl = 0.0, sum_b = 0.0, sum_fb = 0.0;
+        T sum_ndl = 0, sum_b = 0, sum_fb = 0;
         if (live && (F.use_diffuse || F.use_spec_highlight)) {
-            const double ndote = nrm[0] * eye[0] + nrm[1] * eye[1] + nrm[2] * eye[2];
+            const T ndote = nrm[0] * eye[0] + nrm[1] * eye[1] + nrm[2] * eye[2];
             const double *pb = pts + 3 * (size_t)set_b * NS;
             for (int s = lane_g; s < NS; s += G) {
-                double lx = __ldg(pb + 3 * s) - over[0], ly = __ldg(pb + 3 * s + 1) - over[1], lz = __ldg(pb + 3 * s + 2) - over[2];
-                double inv = 1.0 / sqrt(lx * lx + ly * ly + lz * lz);
+                /* the light vector is formed in FP64 (a difference of nearby world points), everything after in T */
+                T lx = (T)(__ldg(pb + 3 * s) - over[0]), ly = (T)(__ldg(pb + 3 * s + 1) - over[1]), lz = (T)(__ldg(pb + 3 * s + 2) - over[2]);
+                T inv = (T)1 / sqrt(lx * lx + ly * ly + lz * lz);
                 lx *= inv;
                 ly *= inv;
                 lz *= inv;
-                double ndl = lx * nrm[0] + ly * nrm[1] + lz * nrm[2];
-                if (ndl >= 0.0) {
+                T ndl = lx * nrm[0] + ly * nrm[1] + lz * nrm[2];
+                if (ndl >= 0) {
                     if (F.use_diffuse) {
                         sum_ndl += ndl;
                     }
                     if (F.use_spec_highlight) {
-                        double hx = lx + eye[0], hy = ly + eye[1], hz = lz + eye[2];
-                        double hinv = 1.0 / sqrt(hx * hx + hy * hy + hz * hz);
+                        T hx = lx + eye[0], hy = ly + eye[1], hz = lz + eye[2];
+                        T hinv = (T)1 / sqrt(hx * hx + hy * hy + hz * hz);
                         hx *= hinv;
                         hy *= hinv;
                         hz *= hinv;
-                        double ndh = fmax(0.0, nrm[0] * hx + nrm[1] * hy + nrm[2] * hz);
-                        double edh_inv = 1.0 / fmax(0.0, eye[0] * hx + eye[1] * hy + eye[2] * hz);
-                        double ldh = lx * hx + ly * hy + lz * hz;
-                        double dist_term = (Ns + 2) * pow(ndh, Ns) * 0.5 * M_1_PI;
-                        double gc = 2.0 * ndh * edh_inv;
-                        double geom = fmin(1.0, fmin(gc * ndote, gc * ndl));
-                        double m1 = 1.0 - ldh;
-                        double factor = pow(m1, 5.0);
-                        double brdf = dist_term * geom / (4.0 * ndl * ndote);
+                        T ndh = max((T)0, nrm[0] * hx + nrm[1] * hy + nrm[2] * hz);
+                        T edh_inv = (T)1 / max((T)0, eye[0] * hx + eye[1] * hy + eye[2] * hz);
+                        T ldh = lx * hx + ly * hy + lz * hz;
+                        T dist_term = (Ns + 2) * pow(ndh, Ns) * (T)(0.5 * M_1_PI);
+                        T gc = 2 * ndh * edh_inv;
+                        T geom = min((T)1, min(gc * ndote, gc * ndl));
+                        T m1 = 1 - ldh;
+                        T m2 = m1 * m1;
+                        T factor = m2 * m2 * m1; /* pow(1 - L.H, 5) */
+                        T brdf = dist_term * geom / (4 * ndl * ndote);
                         sum_b += brdf;
                         sum_fb += factor * brdf;
                     }
@@ -665,48 +679,76 @@ k_light(DScene S, FrameParams F, const LightRec *__restrict__ recs, double *__re
             sum_b += __shfl_xor_sync(gmask, sum_b, o);
             sum_fb += __shfl_xor_sync(gmask, sum_fb, o);
         }
-
-        /* ---- shadow pass.  When every lighting term is exactly zero the visibility fraction cannot matter. */
-        const bool contributes = (sum_ndl != 0.0) || (sum_b != 0.0) || (sum_fb != 0.0);
-        int unshadowed = 0;
-        if (live && (contributes || (F.flags & FRT_FLAG_NO_PRUNE))) {
-            const double *pa = pts + 3 * (size_t)set_a * NS;
-            for (int s = lane_g; s < NS; s += G) {
-                double vx = __ldg(pa + 3 * s) - over[0], vy = __ldg(pa + 3 * s + 1) - over[1], vz = __ldg(pa + 3 * s + 2) - over[2];
-                double dist = sqrt(vx * vx + vy * vy + vz * vz);
-                double inv = 1.0 / dist;
-                Ray sr{ over[0], over[1], over[2], vx * inv, vy * inv, vz * inv };
-                if (!trace_shadow(S, sr, dist, &overflow, &n_nodes)) {
-                    ++unshadowed;
-                }
-                ++n_shadow;
-            }
-        }
-        for (int o = G / 2; o > 0; o >>= 1) {
-            unshadowed += __shfl_xor_sync(gmask, unshadowed, o);
-        }
-
         if (live && lane_g == 0) {
-            double c[3] = { 0.0, 0.0, 0.0 };
-            double intensity = (double)unshadowed / (double)NS;
-            if (!(fabs(intensity) < FRT_EPS) && contributes) { /* equal(shade_intensity, 0.0), renderer.c:904 */
-                double scaling = intensity / (double)NS;
-                for (int k = 0; k < 3; ++k) {
-                    double d = R->Kd[k] * L.intensity[k] * sum_ndl;
-                    double sp = L.intensity[k] * (R->Ks[k] * sum_b + (1.0 - R->Ks[k]) * sum_fb);
-                    c[k] = (d + sp) * scaling;
-                }
-            }
-            if (F.use_ambient) {
-                for (int k = 0; k < 3; ++k) {
-                    c[k] += R->Ka[k] * L.intensity[k];
-                }
-            }
-            double *px = canvas + 4 * (size_t)R->pixel;
-            for (int k = 0; k < 3; ++k) {
-                double v = R->w[k] * c[k];
-                if (v != 0.0) {
-                    atomicAdd(px + k, v);
+            /* when every lighting term is exactly zero the visibility fraction cannot matter: no shadow rays */
+            const bool contributes = (sum_ndl != 0) || (sum_b != 0) || (sum_fb != 0);
+            LightTmp t;
+            t.sum_ndl = (float)sum_ndl;
+            t.sum_b = (float)sum_b;
+            t.sum_fb = (float)sum_fb;
+            t.dsum_ndl = (double)sum_ndl;
+            t.dsum_b = (double)sum_b;
+            t.dsum_fb = (double)sum_fb;
+            t.set_a = (contributes || (F.flags & FRT_FLAG_NO_PRUNE)) ? set_a : -1;
+            t.unshadowed = 0;
+            t.contributes = contributes ? 1 : 0;
+            tmp[hbase] = t;
+        }
+    }
+}
+
+/*
+ * One thread per (hit, surface sample): item = hit * num_samples + sample, so a warp holds 32 consecutive samples
+ * of one hit (or the tail of one and the head of the next) -- rays with a common origin and nearly parallel
+ * directions, which walk the tree together.  The unshadowed count of a hit is reduced inside the warp
+ * (__match_any_sync on the hit index) and added with one integer atomic per (warp, hit): integer sums are
+ * order-independent, so the frame is reproducible.
+ */
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+k_shadow(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
+         int light_idx)
+{
+    const unsigned int n = min(cnt->n_hits[level], F.capacity);
+    const int NS = S.lights[light_idx].num_samples;
+    const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
+    const unsigned long long total = (unsigned long long)n * (unsigned int)NS;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    int overflow = 0;
+    unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0;
+
+    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
+        const unsigned long long item = base + (threadIdx.x & 31);
+        const bool live = item < total;
+        unsigned int h = 0;
+        int s = 0, set_a = -1;
+        if (live) {
+            h = (total <= 0xffffffffull) ? (unsigned int)item / (unsigned int)NS : (unsigned int)(item / (unsigned int)NS);
+            s = (int)(item - (unsigned long long)h * (unsigned int)NS);
+            set_a = tmp[h].set_a;
+        }
+        bool lit = false;
+        if (set_a >= 0) {
+            const LightRec *R = recs + h;
+            const double ox = R->over[0], oy = R->over[1], oz = R->over[2];
+            const double *pa = pts + 3 * ((size_t)set_a * NS + s);
+            double vx = __ldg(pa) - ox, vy = __ldg(pa + 1) - oy, vz = __ldg(pa + 2) - oz;
+            double len2 = vx * vx + vy * vy + vz * vz;
+            double inv = rsqrt_fast(len2);
+            double dist = len2 * inv;
+            Ray sr{ ox, oy, oz, vx * inv, vy * inv, vz * inv };
+            lit = !trace_shadow<COUNT>(S, sr, dist, &overflow, &n_nodes, &n_flops);
+            if (COUNT) ++n_shadow;
+        }
+        /* segmented count: lanes of the same hit are contiguous */
+        const unsigned int active = __ballot_sync(0xffffffffu, set_a >= 0);
+        const unsigned int lit_mask = __ballot_sync(0xffffffffu, lit);
+        if (set_a >= 0) {
+            const unsigned int peers = __match_any_sync(active, h);
+            if ((threadIdx.x & 31) == (unsigned int)(__ffs(peers) - 1)) {
+                int c = __popc(lit_mask & peers);
+                if (c) {
+                    atomicAdd(&tmp[h].unshadowed, c);
                 }
             }
         }
@@ -714,13 +756,58 @@ k_light(DScene S, FrameParams F, const LightRec *__restrict__ recs, double *__re
     if (overflow) {
         atomicOr(&cnt->overflow_csg, 1u);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        n_shadow += __shfl_down_sync(0xffffffffu, n_shadow, o);
-        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, o);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            n_shadow += __shfl_down_sync(0xffffffffu, n_shadow, o);
+            n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, o);
+            n_flops += __shfl_down_sync(0xffffffffu, n_flops, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (n_shadow) atomicAdd(&cnt->rays_shadow, n_shadow);
+            if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
+            if (n_flops) atomicAdd(&cnt->light_flops, n_flops);
+        }
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_shadow) atomicAdd(&cnt->rays_shadow, n_shadow);
-        if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
+}
+
+/* lighting_microfacet's closing arithmetic (renderer.c:904-979) and the weighting into the pixel */
+__global__ void __launch_bounds__(256)
+k_light_resolve(DScene S, FrameParams F, const LightRec *__restrict__ recs, const LightTmp *__restrict__ tmp,
+                double *__restrict__ canvas, const Counters *cnt, int level, int light_idx)
+{
+    const unsigned int n = min(cnt->n_hits[level], F.capacity);
+    const frt_light &L = S.lights[light_idx];
+    const int NS = L.num_samples;
+    const double Li[3] = { L.intensity[0], L.intensity[1], L.intensity[2] };
+    const bool f64 = (F.flags & FRT_FLAG_F64_SHADING) != 0;
+    for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x) {
+        const LightTmp t = tmp[h];
+        const LightRec *R = recs + h;
+        double c[3] = { 0.0, 0.0, 0.0 };
+        double intensity = (double)t.unshadowed / (double)NS;
+        if (!(fabs(intensity) < FRT_EPS) && t.contributes) { /* equal(shade_intensity, 0.0), renderer.c:904 */
+            double scaling = intensity / (double)NS;
+            double sum_ndl = f64 ? t.dsum_ndl : (double)t.sum_ndl;
+            double sum_b = f64 ? t.dsum_b : (double)t.sum_b;
+            double sum_fb = f64 ? t.dsum_fb : (double)t.sum_fb;
+            for (int k = 0; k < 3; ++k) {
+                double d = R->Kd[k] * Li[k] * sum_ndl;
+                double sp = Li[k] * (R->Ks[k] * sum_b + (1.0 - R->Ks[k]) * sum_fb);
+                c[k] = (d + sp) * scaling;
+            }
+        }
+        if (F.use_ambient) {
+            for (int k = 0; k < 3; ++k) {
+                c[k] += R->Ka[k] * Li[k];
+            }
+        }
+        double *px = canvas + 4 * (size_t)R->pixel;
+        for (int k = 0; k < 3; ++k) {
+            double v = R->w[k] * c[k];
+            if (v != 0.0) {
+                atomicAdd(px + k, v);
+            }
+        }
     }
 }
 
@@ -796,9 +883,11 @@ struct frt_scene {
     RayQ q[2]{};
     HitQ hq{};
     LightRec *recs = nullptr;
+    LightTmp *ltmp = nullptr;
     Counters *cnt = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4]{};
+    std::vector<cudaEvent_t> light_ev; /* start/stop pairs around every k_light launch of a frame (no host sync) */
     std::vector<void *> frame_allocs;
 };
 
@@ -913,6 +1002,9 @@ frt_scene_destroy(frt_scene *sc)
     }
     for (auto &e : sc->ev) {
         if (e) cudaEventDestroy(e);
+    }
+    for (auto &e : sc->light_ev) {
+        cudaEventDestroy(e);
     }
     if (sc->stream) {
         cudaStreamDestroy(sc->stream);
@@ -1097,6 +1189,7 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     }
     FA(sc->hq.t); FA(sc->hq.u); FA(sc->hq.v); FA(sc->hq.leaf);
     FA(sc->recs);
+    FA(sc->ltmp);
 #undef FA
     int rc = frame_alloc(sc, &sc->cnt, 1);
     if (rc != FRT_OK) {
@@ -1106,11 +1199,20 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     return FRT_OK;
 }
 
-template <int G>
+template <typename T>
 static void
-launch_light(frt_scene *sc, const FrameParams &F, int blocks, int level, int light)
+launch_light_sum(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g)
 {
-    k_light<G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->canvas, sc->cnt, level, light);
+#define LS(G) k_light_sum<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, light)
+    switch (g) {
+    case 1: LS(1); break;
+    case 2: LS(2); break;
+    case 4: LS(4); break;
+    case 8: LS(8); break;
+    case 16: LS(16); break;
+    default: LS(32); break;
+    }
+#undef LS
 }
 
 static int
@@ -1241,7 +1343,6 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             gw[i] = pick_group_width(hl[i].num_samples);
         }
     }
-    const bool time_light = (cfg->flags & FRT_FLAG_COUNT_RAYS) != 0;
 
     for (unsigned long long first = 0; first < total; first += chunk) {
         unsigned int n = (unsigned int)std::min<unsigned long long>(chunk, total - first);
@@ -1260,25 +1361,29 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             launches += 2;
             if (F.include_direct) {
                 for (int li = 0; li < sc->S.n_lights; ++li) {
-                    if (time_light) CK(cudaEventRecord(sc->ev[2], s));
-                    int blocks = sm_blocks * 8;
-                    switch (gw[li]) {
-                    case 1: launch_light<1>(sc, F, blocks, level, li); break;
-                    case 2: launch_light<2>(sc, F, blocks, level, li); break;
-                    case 4: launch_light<4>(sc, F, blocks, level, li); break;
-                    case 8: launch_light<8>(sc, F, blocks, level, li); break;
-                    case 16: launch_light<16>(sc, F, blocks, level, li); break;
-                    default: launch_light<32>(sc, F, blocks, level, li); break;
+                    if (sc->light_ev.size() < 2 * (size_t)(light_launches + 1)) {
+                        cudaEvent_t a, b;
+                        CK(cudaEventCreate(&a));
+                        CK(cudaEventCreate(&b));
+                        sc->light_ev.push_back(a);
+                        sc->light_ev.push_back(b);
                     }
-                    ++launches;
+                    const int blocks = sm_blocks * 8;
+                    if (F.flags & FRT_FLAG_F64_SHADING) {
+                        launch_light_sum<double>(sc, F, blocks, level, li, gw[li]);
+                    } else {
+                        launch_light_sum<float>(sc, F, blocks, level, li, gw[li]);
+                    }
+                    CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
+                    if (F.flags & FRT_FLAG_COUNT_RAYS) {
+                        k_shadow<true><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li);
+                    } else {
+                        k_shadow<false><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li);
+                    }
+                    CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
+                    k_light_resolve<<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->canvas, sc->cnt, level, li);
+                    launches += 3;
                     ++light_launches;
-                    if (time_light) {
-                        CK(cudaEventRecord(sc->ev[3], s));
-                        CK(cudaEventSynchronize(sc->ev[3]));
-                        float ms = 0.f;
-                        CK(cudaEventElapsedTime(&ms, sc->ev[2], sc->ev[3]));
-                        light_ms += ms;
-                    }
                 }
             }
         }
@@ -1291,6 +1396,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         totals.rays_shadow += hc.rays_shadow;
         totals.hits_shaded += hc.hits_shaded;
         totals.shadow_nodes += hc.shadow_nodes;
+        totals.light_flops += hc.light_flops;
         if (hc.overflow_queue) {
             break;
         }
@@ -1300,6 +1406,11 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     CK(cudaGetLastError());
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, sc->ev[0], sc->ev[1]));
+    for (unsigned long long k = 0; k < light_launches; ++k) {
+        float lms = 0.f;
+        CK(cudaEventElapsedTime(&lms, sc->light_ev[2 * k], sc->light_ev[2 * k + 1]));
+        light_ms += lms;
+    }
 
     if (st != nullptr) {
         st->frame_ms = ms;
@@ -1309,6 +1420,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         st->rays_shadow = totals.rays_shadow;
         st->hits_shaded = totals.hits_shaded;
         st->shadow_nodes = totals.shadow_nodes;
+        st->light_flops = totals.light_flops;
         st->kernel_launches = launches;
         st->light_launches = light_launches;
         st->rows_rendered = F.n_owned_rows;
@@ -1351,7 +1463,7 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
         cudaMemGetInfo(&free_b, &total_b);
         const unsigned long long frame_samples = std::max<unsigned long long>(st.rays_primary, 1);
         const unsigned long long eff_chunk = std::min<unsigned long long>(chunk, frame_samples);
-        const unsigned long long slot_bytes = 2 * 84 + 28 + sizeof(LightRec);
+        const unsigned long long slot_bytes = 2 * 84 + 28 + sizeof(LightRec) + sizeof(LightTmp);
         if (factor < 64 && eff_chunk * factor * 2 * slot_bytes < (free_b + (unsigned long long)sc->capacity * slot_bytes) / 4) {
             factor *= 2;
         } else if (eff_chunk > 4096) {

@@ -469,6 +469,25 @@ prim_intersect(int type, const double *prm, const Ray &r, double t[4], double uv
     }
 }
 
+/* Algorithmic flop per event, the table frozen in BASELINE.md section 4 (used only by the counting build of the
+ * kernels, FRT_FLAG_COUNT_RAYS, to state the roofline numerator). */
+#define FRT_COST_XFORM 33
+#define FRT_COST_BBOX 16
+#define FRT_COST_LIGHT_SAMPLE 100
+__device__ __forceinline__ unsigned int
+prim_cost(int type)
+{
+    switch (type) {
+    case FRT_SPHERE: return 28;
+    case FRT_CUBE: return 16;
+    case FRT_PLANE: return 2;
+    case FRT_CYLINDER: return 42;
+    case FRT_CONE: return 50;
+    case FRT_TOROID: return 200;
+    default: return 45; /* triangles */
+    }
+}
+
 /* ---- CSG: per-ray interval stack ------------------------------------------------------------------- */
 
 struct CsgHit {
@@ -496,8 +515,9 @@ csg_allowed(int op, bool lhit, bool inl, bool inr)
  * reproduced is the shadow early-out of a group nested INSIDE a CSG operand (group.c:105-123).
  * `cur_xf`/`lr` cache the ray in the current node space.  Sets *overflow when the interval stack is too small.
  */
+template <bool COUNT>
 __device__ __noinline__ int
-csg_eval(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow)
+csg_eval_t(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow, unsigned long long *flops)
 {
     struct Frame {
         int node, right, skip, start, mid, op;
@@ -515,7 +535,9 @@ csg_eval(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow)
         if (a.xform != cur_xf) {
             cur_xf = a.xform;
             lr = ray_to_local(S, cur_xf, wr);
+            if (COUNT && cur_xf != 0) *flops += FRT_COST_XFORM;
         }
+        if (COUNT) *flops += (a.type >= FRT_CSG) ? FRT_COST_BBOX : prim_cost(a.type);
         if (a.type == FRT_CSG) {
             if (!bbox_hit(S, i, lr)) {
                 i = a.skip;
@@ -588,6 +610,12 @@ csg_eval(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow)
     return n;
 }
 
+__device__ __forceinline__ int
+csg_eval(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow)
+{
+    return csg_eval_t<false>(S, root, wr, buf, overflow, nullptr);
+}
+
 /* ---- traversal -------------------------------------------------------------------------------------- */
 
 struct Hit {
@@ -653,88 +681,273 @@ trace_closest(const DScene &S, const Ray &wr, int *overflow)
     return best;
 }
 
+/* ---- fast FP64 reciprocal / reciprocal square root: MUFU seed + Newton steps, no slow-path branch.  Results are
+ *      within 1 ulp of the correctly rounded value, which only moves a t value by 1 ulp (never a decision that is
+ *      not already a tie).  Used by the shadow traversal, where every shadow ray would otherwise pay for a dozen
+ *      IEEE divisions per node. */
+__device__ __forceinline__ double
+rcp_fast(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+__device__ __forceinline__ double
+rsqrt_fast(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double h = 0.5 * x;
+    r = r * fma(-h * r, r, 1.5);
+    r = r * fma(-h * r, r, 1.5);
+    return r;
+}
+
+/* 1 / direction per axis for the slab tests; +inf where |direction| < EPSILON, which reproduces the
+ * "numerator * INFINITY" branch of check_axis / bbox_check_axis (cube.c:27-33, bounding_box.c:135-141) */
+struct InvDir {
+    double x, y, z;
+};
+
+__device__ __forceinline__ InvDir
+inv_dir(const Ray &r)
+{
+    InvDir v;
+    v.x = fabs(r.dx) >= FRT_EPS ? rcp_fast(r.dx) : CUDART_INF;
+    v.y = fabs(r.dy) >= FRT_EPS ? rcp_fast(r.dy) : CUDART_INF;
+    v.z = fabs(r.dz) >= FRT_EPS ? rcp_fast(r.dz) : CUDART_INF;
+    return v;
+}
+
+__device__ __forceinline__ void
+slab_axis_inv(double origin, double inv, double lo, double hi, double &t0, double &t1)
+{
+    double a = (lo - origin) * inv;
+    double b = (hi - origin) * inv;
+    if (isnan(a)) a = CUDART_INF; /* 0 * inf */
+    if (isnan(b)) b = CUDART_INF;
+    t0 = fmin(a, b);
+    t1 = fmax(a, b);
+}
+
+__device__ __forceinline__ bool
+bbox_hit_inv(const DScene &S, int node, const Ray &r, const InvDir &inv)
+{
+    const double2 *b = reinterpret_cast<const double2 *>(S.bbox + 6 * node);
+    double2 b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2); /* min.x min.y | min.z max.x | max.y max.z */
+    double x0, x1, y0, y1, z0, z1;
+    slab_axis_inv(r.ox, inv.x, b0.x, b1.y, x0, x1);
+    slab_axis_inv(r.oy, inv.y, b0.y, b2.x, y0, y1);
+    slab_axis_inv(r.oz, inv.z, b1.x, b2.y, z0, z1);
+    return fmax(fmax(x0, y0), z0) <= fmin(fmin(x1, y1), z1);
+}
+
+/*
+ * Shadow-ray summary of one primitive: `stop` = its crossing list holds a t that is not <= 0 (the reference's
+ * search ends here, group.c:105-123), `tmin` = its smallest t > 0.  Sphere and cube -- the two types a Cornell
+ * shadow ray meets -- are answered from their two roots without materialising the list; the other types go
+ * through prim_intersect.
+ */
+__device__ __forceinline__ int
+prim_intersect_inv(int type, const double *prm, const Ray &r, const InvDir &inv, double t[4], double uv[2])
+{
+    if (type == FRT_CUBE) { /* cube_local_intersect, cube.c:56-78 */
+        double x0, x1, y0, y1, z0, z1;
+        slab_axis_inv(r.ox, inv.x, -1.0, 1.0, x0, x1);
+        slab_axis_inv(r.oy, inv.y, -1.0, 1.0, y0, y1);
+        slab_axis_inv(r.oz, inv.z, -1.0, 1.0, z0, z1);
+        double tmin = fmax(fmax(x0, y0), z0);
+        double tmax = fmin(fmin(x1, y1), z1);
+        if (tmin > tmax) {
+            return 0;
+        }
+        t[0] = tmin;
+        t[1] = tmax;
+        return 2;
+    }
+    if (type == FRT_SPHERE) { /* sphere_local_intersect, sphere.c:14-40 */
+        double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
+        double b = 2 * (r.dx * r.ox + r.dy * r.oy + r.dz * r.oz);
+        double c = (r.ox * r.ox + r.oy * r.oy + r.oz * r.oz) - 1.0;
+        double disc = b * b - 4 * a * c;
+        if (disc < 0) {
+            return 0;
+        }
+        disc = disc > 0 ? disc * rsqrt_fast(disc) : 0.0;
+        a = rcp_fast(2 * a);
+        t[0] = (-b - disc) * a;
+        t[1] = (-b + disc) * a;
+        return 2;
+    }
+    return prim_intersect(type, prm, r, t, uv);
+}
+
 /*
  * is_shadowed (renderer.c:73-93) = intersect_world(w, r, true) + hit(xs, true) with the reference's
  * order-dependent early-out (group.c:105-123): walk the divided tree in the reference's child
  * order; the search ENDS at the first leaf (or CSG) whose crossing list holds any t that is not <= 0, whether or
  * not that crossing is nearer than the light or casts a shadow.  The point is shadowed iff that leaf has a
  * positive crossing on a casts_shadow material nearer than `distance`.
+ *
+ * One loop serves plain leaves and CSG subtrees (csg_local_intersect, csg.c:74-125): inside a CSG the leaves'
+ * crossings are pushed on the per-ray interval stack `buf`, and when a CSG node's subtree ends its operands are
+ * merged, sorted and filtered in place (csg_filter_intersections, csg.c:43-71); the outermost CSG is then judged
+ * like a leaf.  Keeping a single primitive-intersection site keeps the kernel's instruction footprint small: the
+ * first version of this stage spent half of its issue slots waiting on instruction fetch (profiles/).
  */
+#define FRT_CSG_DEPTH 8
+template <bool COUNT>
 __device__ __forceinline__ bool
-trace_shadow(const DScene &S, const Ray &wr, double distance, int *overflow, unsigned long long *nodes_visited)
+trace_shadow(const DScene &S, const Ray &wr, double distance, int *overflow, unsigned long long *nodes_visited,
+             unsigned long long *flops)
 {
+    struct Frame {
+        int right, skip, start, mid, op;
+    };
     CsgHit buf[FRT_CSG_CAP];
-    unsigned int visited = 0;
+    Frame st[FRT_CSG_DEPTH];
+    int sp = 0, n = 0;
+    unsigned int visited = 0, cost = 0;
     bool result = false;
+    const InvDir winv = inv_dir(wr);
+
     for (int rt = 0; rt < S.n_roots; ++rt) {
         int i = __ldg(S.roots + rt);
-        int end = load_node_a(S, i).skip;
+        const int end = load_node_a(S, i).skip;
         int cur_xf = 0;
         Ray lr = wr;
+        InvDir inv = winv;
         bool any = false; /* world.c:189-191: stop after the first top-level shape that returned anything */
         bool done = false;
         while (i < end) {
-            NodeA a = load_node_a(S, i);
-            ++visited;
+            const NodeA a = load_node_a(S, i);
+            if (COUNT) ++visited;
             if (a.xform != cur_xf) {
                 cur_xf = a.xform;
-                lr = ray_to_local(S, cur_xf, wr);
+                if (cur_xf == 0) {
+                    lr = wr;
+                    inv = winv;
+                } else {
+                    lr = ray_to_local(S, cur_xf, wr);
+                    inv = inv_dir(lr);
+                    if (COUNT) cost += FRT_COST_XFORM;
+                }
             }
-            if (a.type == FRT_GROUP) {
-                i = bbox_hit(S, i, lr) ? i + 1 : a.skip;
-            } else if (a.type == FRT_CSG) {
-                if (bbox_hit(S, i, lr)) {
-                    int n = csg_eval(S, i, wr, buf, overflow);
+            if (COUNT) cost += (a.type >= FRT_CSG) ? FRT_COST_BBOX : prim_cost(a.type);
+            if (a.type >= FRT_CSG) { /* CSG or group: cull by the node's own bounds */
+                if (!bbox_hit_inv(S, i, lr, inv)) {
+                    i = a.skip;
+                } else {
+                    if (a.type == FRT_CSG) {
+                        if (sp == FRT_CSG_DEPTH) {
+                            *overflow = 1;
+                            return false;
+                        }
+                        const NodeB b = load_node_b(S, i);
+                        st[sp++] = Frame{ b.right, a.skip, n, -1, b.csg_op };
+                    }
+                    i = i + 1;
+                }
+            } else {
+                const NodeB b = load_node_b(S, i);
+                double t[4], uv[2];
+                const int k = prim_intersect_inv(a.type, S.params + (b.param < 0 ? 0 : b.param), lr, inv, t, uv);
+                if (sp == 0) {
                     bool stop = false;
                     double tmin = CUDART_INF;
-                    for (int k = 0; k < n; ++k) {
+                    for (int j = 0; j < k; ++j) {
                         any = true;
-                        if (!(buf[k].t <= 0)) {
-                            stop = true;
-                        }
-                        if (buf[k].t > 0 && buf[k].t < tmin) {
-                            int m = load_node_a(S, buf[k].leaf).material;
-                            if (S.mats[m].casts_shadow) {
-                                tmin = buf[k].t;
-                            }
+                        stop = stop || !(t[j] <= 0);
+                        if (t[j] > 0 && t[j] < tmin) {
+                            tmin = t[j];
                         }
                     }
                     if (stop) {
-                        result = tmin < distance;
+                        result = S.mats[a.material].casts_shadow && tmin < distance;
                         done = true;
                         break;
                     }
-                }
-                i = a.skip;
-            } else {
-                NodeB b = load_node_b(S, i);
-                double t[4], uv[2];
-                int k = prim_intersect(a.type, S.params + (b.param < 0 ? 0 : b.param), lr, t, uv);
-                bool stop = false;
-                double tmin = CUDART_INF;
-                for (int j = 0; j < k; ++j) {
-                    any = true;
-                    if (!(t[j] <= 0)) {
-                        stop = true;
+                } else {
+                    for (int j = 0; j < k; ++j) {
+                        if (n == FRT_CSG_CAP) {
+                            *overflow = 1;
+                            return false;
+                        }
+                        buf[n].t = t[j];
+                        buf[n].leaf = i;
+                        ++n;
                     }
-                    if (t[j] > 0 && t[j] < tmin) {
-                        tmin = t[j];
-                    }
-                }
-                if (stop) {
-                    result = S.mats[a.material].casts_shadow && tmin < distance;
-                    done = true;
-                    break;
                 }
                 i = i + 1;
+            }
+            /* close every CSG whose left / right operand just ended */
+            while (sp > 0) {
+                Frame &f = st[sp - 1];
+                if (f.mid < 0 && i >= f.right) {
+                    f.mid = n;
+                }
+                if (i < f.skip) {
+                    break;
+                }
+                if (f.mid - f.start > 0 && n - f.mid > 0) { /* intersections_sort over both operands */
+                    for (int x = f.start + 1; x < n; ++x) {
+                        CsgHit h = buf[x];
+                        int y = x - 1;
+                        while (y >= f.start && buf[y].t > h.t) {
+                            buf[y + 1] = buf[y];
+                            --y;
+                        }
+                        buf[y + 1] = h;
+                    }
+                }
+                bool inl = false, inr = false;
+                int out = f.start;
+                for (int x = f.start; x < n; ++x) {
+                    const bool lhit = buf[x].leaf < f.right;
+                    if (csg_allowed(f.op, lhit, inl, inr)) {
+                        buf[out++] = buf[x];
+                    }
+                    if (lhit) {
+                        inl = !inl;
+                    } else {
+                        inr = !inr;
+                    }
+                }
+                n = out;
+                --sp;
+                if (sp == 0) { /* the outermost CSG is judged like a leaf */
+                    bool stop = false;
+                    double tmin = CUDART_INF;
+                    for (int x = 0; x < n; ++x) {
+                        any = true;
+                        stop = stop || !(buf[x].t <= 0);
+                        if (buf[x].t > 0 && buf[x].t < tmin && S.mats[load_node_a(S, buf[x].leaf).material].casts_shadow) {
+                            tmin = buf[x].t;
+                        }
+                    }
+                    n = 0;
+                    if (stop) {
+                        result = tmin < distance;
+                        done = true;
+                    }
+                }
+            }
+            if (done) {
+                break;
             }
         }
         if (done || any) {
             break;
         }
     }
-    if (nodes_visited) {
+    if (COUNT) {
         *nodes_visited += visited;
+        *flops += cost;
     }
     return result;
 }

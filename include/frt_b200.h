@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FRT_ABI_VERSION 3
+#define FRT_ABI_VERSION 4
 
 enum frt_status {
     FRT_OK = 0,
@@ -196,7 +196,9 @@ typedef struct frt_scene frt_scene;   /* opaque: device-resident scene */
 enum frt_render_flags {
     FRT_FLAG_NO_PRUNE = 1,   /* also trace branches whose weight is exactly zero, like the reference does
                                 (renderer.c:534-605 on opaque surfaces) -- for ray-count parity only */
-    FRT_FLAG_COUNT_RAYS = 2  /* fill the ray counters in frt_stats */
+    FRT_FLAG_COUNT_RAYS = 2, /* fill the ray counters in frt_stats */
+    FRT_FLAG_F64_SHADING = 4 /* evaluate the lighting sums (lighting_microfacet, renderer.c:894-979) in FP64 like the
+                                reference instead of FP32; geometric decisions are FP64 either way */
 };
 
 typedef struct frt_render_cfg {
@@ -211,7 +213,7 @@ typedef struct frt_render_cfg {
 
 typedef struct frt_stats {
     double frame_ms;         /* device time of the frame, CUDA events on the render stream */
-    double light_ms;         /* summed device time of the shadow+lighting kernel (dominant kernel) */
+    double light_ms;         /* summed device time of the shadow-ray kernel (k_shadow, the dominant kernel) */
     double upload_ms, download_ms;
     uint64_t rays_primary, rays_secondary, rays_shadow, rays_gather, rays_photon;
     uint64_t hits_shaded;
@@ -220,6 +222,8 @@ typedef struct frt_stats {
     uint64_t shadow_nodes;   /* tree nodes visited by shadow rays */
     uint64_t overflow;       /* non-zero: a bounded queue overflowed and the frame was re-run in smaller chunks */
     uint64_t photons_stored[3];
+    uint64_t light_flops;    /* with FRT_FLAG_COUNT_RAYS: algorithmic flop of the dominant kernel, counted event by event
+                                with the cost table of BASELINE.md section 4 (ray transform 33, bbox slab 16, sphere 28, ...) */
     int32_t rows_rendered;
     int32_t pad;
 } frt_stats;
