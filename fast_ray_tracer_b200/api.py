@@ -13,10 +13,12 @@ _PKG = Path(__file__).resolve().parent
 _LIB_PATH = _PKG / "libfrt_b200.so"
 _lib = None
 
-FRT_ABI_VERSION = 4
+FRT_ABI_VERSION = 5
 FRT_FLAG_NO_PRUNE = 1
 FRT_FLAG_COUNT_RAYS = 2
 FRT_FLAG_F64_SHADING = 4
+FRT_FLAG_F64_SHADOW = 8
+FRT_FLAG_VERIFY_F32 = 16
 
 
 class FrtError(RuntimeError):
@@ -109,6 +111,7 @@ class frt_stats(C.Structure):
                 ("rays_gather", C.c_uint64), ("rays_photon", C.c_uint64), ("hits_shaded", C.c_uint64),
                 ("light_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("shadow_nodes", C.c_uint64),
                 ("overflow", C.c_uint64), ("photons_stored", C.c_uint64 * 3), ("light_flops", C.c_uint64),
+                ("shadow_deferred", C.c_uint64), ("shadow_mismatch", C.c_uint64),
                 ("rows_rendered", C.c_int32), ("pad", C.c_int32)]
 
 
@@ -273,6 +276,8 @@ class RenderStats:
     shadow_nodes: int = 0
     overflow: int = 0
     light_flops: int = 0
+    shadow_deferred: int = 0
+    shadow_mismatch: int = 0
     rows_rendered: int = 0
     extra: dict = field(default_factory=dict)
 
@@ -325,7 +330,8 @@ class Scene:
         stats = RenderStats(frame_ms=st.frame_ms, light_ms=st.light_ms, download_ms=st.download_ms,
                             rays_primary=st.rays_primary, rays_secondary=st.rays_secondary, rays_shadow=st.rays_shadow,
                             rays_gather=st.rays_gather, hits_shaded=st.hits_shaded, kernel_launches=st.kernel_launches,
-                            light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow, light_flops=st.light_flops,
+                            light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow, light_flops=st.light_flops, shadow_deferred=st.shadow_deferred,
+                            shadow_mismatch=st.shadow_mismatch,
                             rows_rendered=st.rows_rendered)
         return (out if download else None), stats
 

@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     blob_o = PKG / "csrc" / "frt_blob.o"
     subprocess.run(["gcc", "-O2", "-fPIC", "-std=c11", "-Wall", "-I", str(INCLUDE), "-c", str(CSRC / "frt_blob.c"), "-o", str(blob_o)],
                    check=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-o", str(LIB), str(CSRC / "frt_core.cu"), str(blob_o)]
+    extra = os.environ.get("FRT_NVCC_EXTRA", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", str(INCLUDE), "-o", str(LIB), str(CSRC / "frt_core.cu"), str(blob_o)]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.run(cmd, check=True)

@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +28,7 @@
 #include "frt_internal.h"
 #include "frt_device.cuh"
 #include "frt_patterns.cuh"
+#include "frt_shadow_f32.cuh"
 
 /* ------------------------------------------------------------------------------------------------ errors */
 
@@ -110,7 +112,9 @@ struct Counters {
     unsigned int n_rays[8];   /* rays queued for level l */
     unsigned int n_hits[8];   /* light records of level l */
     unsigned int overflow_queue, overflow_csg;
+    unsigned int n_deferred, pad;  /* shadow rays the FP32 pass left undecided in the current k_shadow_f32 launch */
     unsigned long long rays_secondary, rays_shadow, hits_shaded, shadow_nodes, light_flops;
+    unsigned long long deferred_total, f32_mismatch;
 };
 
 struct DCamera {
@@ -703,46 +707,100 @@ k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
  * directions, which walk the tree together.  The unshadowed count of a hit is reduced inside the warp
  * (__match_any_sync on the hit index) and added with one integer atomic per (warp, hit): integer sums are
  * order-independent, so the frame is reproducible.
+ *
+ * k_shadow_f32 answers every ray the FP32 filtered traversal can decide (frt_shadow_f32.cuh) and appends the rest
+ * to `queue` (one atomic per warp); k_shadow_exact then re-traces the queue in FP64.  MODE: 0 production,
+ * 1 counting (FRT_FLAG_COUNT_RAYS), 2 verifying (FRT_FLAG_VERIFY_F32: every decided ray is also traced in FP64 and
+ * disagreements are counted in Counters::f32_mismatch).
  */
-template <bool COUNT>
-__global__ void __launch_bounds__(256)
-k_shadow(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
-         int light_idx)
+__device__ __forceinline__ void
+shadow_item(const DScene &S, const LightRec *__restrict__ recs, const LightTmp *__restrict__ tmp, const double *pts, int NS,
+            unsigned long long item, bool small, unsigned int &h, int &set_a, Ray &sr, double &dist2)
 {
+    h = small ? (unsigned int)item / (unsigned int)NS : (unsigned int)(item / (unsigned int)NS);
+    const int s = (int)(item - (unsigned long long)h * (unsigned int)NS);
+    set_a = tmp[h].set_a;
+    if (set_a >= 0) {
+        const LightRec *R = recs + h;
+        sr.ox = R->over[0];
+        sr.oy = R->over[1];
+        sr.oz = R->over[2];
+        const double *pa = pts + 3 * ((size_t)set_a * NS + s);
+        sr.dx = __ldg(pa) - sr.ox;
+        sr.dy = __ldg(pa + 1) - sr.oy;
+        sr.dz = __ldg(pa + 2) - sr.oz; /* not normalised yet */
+        dist2 = sr.dx * sr.dx + sr.dy * sr.dy + sr.dz * sr.dz;
+    }
+}
+
+__device__ __forceinline__ double
+normalise_shadow_ray(Ray &sr, double dist2)
+{
+    const double inv = rsqrt_fast(dist2);
+    sr.dx *= inv;
+    sr.dy *= inv;
+    sr.dz *= inv;
+    return dist2 * inv;
+}
+
+#ifndef FRT_SHADOW_MINB
+#define FRT_SHADOW_MINB 2
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
+k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
+             int level, int light_idx, unsigned long long *__restrict__ queue, unsigned int qcap)
+{
+    constexpr bool COUNT = MODE != 0;
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
     const int NS = S.lights[light_idx].num_samples;
     const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
     const unsigned long long total = (unsigned long long)n * (unsigned int)NS;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const bool small = total <= 0xffffffffull;
     int overflow = 0;
-    unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0;
+    unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0, n_mismatch = 0;
 
     for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
         const unsigned long long item = base + (threadIdx.x & 31);
-        const bool live = item < total;
         unsigned int h = 0;
-        int s = 0, set_a = -1;
-        if (live) {
-            h = (total <= 0xffffffffull) ? (unsigned int)item / (unsigned int)NS : (unsigned int)(item / (unsigned int)NS);
-            s = (int)(item - (unsigned long long)h * (unsigned int)NS);
-            set_a = tmp[h].set_a;
+        int set_a = -1;
+        Ray sr{};
+        double dist2 = 1.0;
+        if (item < total) {
+            shadow_item(S, recs, tmp, pts, NS, item, small, h, set_a, sr, dist2);
         }
-        bool lit = false;
+        int res = FRT_SH_SHADOWED;
         if (set_a >= 0) {
-            const LightRec *R = recs + h;
-            const double ox = R->over[0], oy = R->over[1], oz = R->over[2];
-            const double *pa = pts + 3 * ((size_t)set_a * NS + s);
-            double vx = __ldg(pa) - ox, vy = __ldg(pa + 1) - oy, vz = __ldg(pa + 2) - oz;
-            double len2 = vx * vx + vy * vy + vz * vz;
-            double inv = rsqrt_fast(len2);
-            double dist = len2 * inv;
-            Ray sr{ ox, oy, oz, vx * inv, vy * inv, vz * inv };
-            lit = !trace_shadow<COUNT>(S, sr, dist, &overflow, &n_nodes, &n_flops);
+            /* the FP32 ray: FP64 difference of the two world points, rounded, normalised in FP32 */
+            const float vx = (float)sr.dx, vy = (float)sr.dy, vz = (float)sr.dz;
+            const float len2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
+            const float rinv = rsqrtf(len2);
+            const RayF w{ (float)sr.ox, (float)sr.oy, (float)sr.oz, vx * rinv, vy * rinv, vz * rinv };
+            res = trace_shadow_f32<COUNT>(S, SF, sr, w, len2 * rinv, &overflow, &n_nodes, &n_flops);
             if (COUNT) ++n_shadow;
+            if (MODE == 2 && res != FRT_SH_UNDECIDED) {
+                Ray er = sr;
+                const double dist = normalise_shadow_ray(er, dist2);
+                unsigned long long dn = 0, df = 0;
+                const bool sh = trace_shadow<false>(S, er, dist, &overflow, &dn, &df);
+                if (sh != (res == FRT_SH_SHADOWED)) {
+                    ++n_mismatch;
+                    res = sh ? FRT_SH_SHADOWED : FRT_SH_LIT;
+                }
+            }
+        }
+        const unsigned int slot = warp_append(&cnt->n_deferred, res == FRT_SH_UNDECIDED);
+        if (res == FRT_SH_UNDECIDED) {
+            if (slot < qcap) {
+                queue[slot] = item;
+            } else {
+                atomicOr(&cnt->overflow_queue, 1u);
+            }
         }
         /* segmented count: lanes of the same hit are contiguous */
         const unsigned int active = __ballot_sync(0xffffffffu, set_a >= 0);
-        const unsigned int lit_mask = __ballot_sync(0xffffffffu, lit);
+        const unsigned int lit_mask = __ballot_sync(0xffffffffu, res == FRT_SH_LIT);
         if (set_a >= 0) {
             const unsigned int peers = __match_any_sync(active, h);
             if ((threadIdx.x & 31) == (unsigned int)(__ffs(peers) - 1)) {
@@ -761,12 +819,57 @@ k_shadow(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *_
             n_shadow += __shfl_down_sync(0xffffffffu, n_shadow, o);
             n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, o);
             n_flops += __shfl_down_sync(0xffffffffu, n_flops, o);
+            n_mismatch += __shfl_down_sync(0xffffffffu, n_mismatch, o);
         }
         if ((threadIdx.x & 31) == 0) {
             if (n_shadow) atomicAdd(&cnt->rays_shadow, n_shadow);
             if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
             if (n_flops) atomicAdd(&cnt->light_flops, n_flops);
+            if (n_mismatch) atomicAdd(&cnt->f32_mismatch, n_mismatch);
         }
+    }
+}
+
+/* the rays the FP32 pass could not decide, re-traced in FP64 (also the whole shadow pass under FRT_FLAG_F64_SHADOW) */
+template <bool COUNT, bool ALL>
+__global__ void __launch_bounds__(256)
+k_shadow_exact(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
+               int light_idx, const unsigned long long *__restrict__ queue, unsigned int qcap)
+{
+    const unsigned int n = min(cnt->n_hits[level], F.capacity);
+    const int NS = S.lights[light_idx].num_samples;
+    const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
+    const unsigned long long total = ALL ? (unsigned long long)n * (unsigned int)NS : (unsigned long long)min(cnt->n_deferred, qcap);
+    const bool small = (unsigned long long)n * (unsigned int)NS <= 0xffffffffull;
+    int overflow = 0;
+    unsigned long long n_nodes = 0, n_flops = 0, n_shadow = 0;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+         q += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long item = ALL ? q : queue[q];
+        unsigned int h;
+        int set_a;
+        Ray sr;
+        double dist2;
+        shadow_item(S, recs, tmp, pts, NS, item, small, h, set_a, sr, dist2);
+        if (set_a < 0) {
+            continue;
+        }
+        const double dist = normalise_shadow_ray(sr, dist2);
+        if (COUNT && ALL) ++n_shadow;
+        if (!trace_shadow<COUNT>(S, sr, dist, &overflow, &n_nodes, &n_flops)) {
+            atomicAdd(&tmp[h].unshadowed, 1);
+        }
+    }
+    if (overflow) {
+        atomicOr(&cnt->overflow_csg, 1u);
+    }
+    if (COUNT) {
+        if (n_shadow) atomicAdd(&cnt->rays_shadow, n_shadow);
+        if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
+        if (n_flops) atomicAdd(&cnt->light_flops, n_flops);
+    }
+    if (!ALL && blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&cnt->deferred_total, total);
     }
 }
 
@@ -871,6 +974,7 @@ frt_measure_fma_peak(int device, double *fp64_tflops, double *fp32_tflops)
 struct frt_scene {
     int device = 0;
     DScene S{};
+    DSceneF SF{};
     DCamera C{};
     frt_config cfg{};
     std::vector<void *> allocs;
@@ -884,6 +988,8 @@ struct frt_scene {
     HitQ hq{};
     LightRec *recs = nullptr;
     LightTmp *ltmp = nullptr;
+    unsigned long long *dq = nullptr; /* (hit, sample) items the FP32 shadow pass deferred to the FP64 pass */
+    unsigned int dq_cap = 0;
     Counters *cnt = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4]{};
@@ -1067,6 +1173,30 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
     UP(upload(sc, d->lights, (size_t)d->n_lights, &S.lights));
     UP(upload(sc, d->light_points, (size_t)3 * d->n_light_points, &S.lpoints));
     UP(upload(sc, d->roots, (size_t)d->n_roots, &S.roots));
+    {
+        /* FP32 mirror for the filtered shadow traversal (frt_shadow_f32.cuh): matrices rounded to nearest with the
+         * row sums R_k rounded up, bounding boxes rounded outward */
+        std::vector<float4> fx((size_t)4 * d->n_xforms), fb((size_t)2 * d->n_nodes);
+        for (int i = 0; i < d->n_xforms; ++i) {
+            const double *m = d->xforms[i].inv;
+            float R[3];
+            for (int k = 0; k < 3; ++k) {
+                fx[4 * i + k] = make_float4((float)m[4 * k], (float)m[4 * k + 1], (float)m[4 * k + 2], (float)m[4 * k + 3]);
+                double r = fabs(m[4 * k]) + fabs(m[4 * k + 1]) + fabs(m[4 * k + 2]);
+                R[k] = nextafterf((float)(r * (1.0 + 1e-6)), INFINITY);
+            }
+            fx[4 * i + 3] = make_float4(R[0], R[1], R[2], 0.f);
+        }
+        auto down = [](double x) { float f = (float)x; return ((double)f > x) ? nextafterf(f, -INFINITY) : f; };
+        auto up = [](double x) { float f = (float)x; return ((double)f < x) ? nextafterf(f, INFINITY) : f; };
+        for (int i = 0; i < d->n_nodes; ++i) {
+            const frt_node &n = d->nodes[i];
+            fb[2 * i] = make_float4(down(n.bbox_min[0]), down(n.bbox_min[1]), down(n.bbox_min[2]), 0.f);
+            fb[2 * i + 1] = make_float4(up(n.bbox_max[0]), up(n.bbox_max[1]), up(n.bbox_max[2]), 0.f);
+        }
+        UP(upload(sc, fx.data(), fx.size(), &sc->SF.fx));
+        UP(upload(sc, fb.data(), fb.size(), &sc->SF.fbbox));
+    }
     S.n_roots = d->n_roots;
     S.n_nodes = d->n_nodes;
     S.n_lights = d->n_lights;
@@ -1191,6 +1321,14 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     FA(sc->recs);
     FA(sc->ltmp);
 #undef FA
+    {
+        unsigned long long want_q = std::min<unsigned long long>((unsigned long long)capacity * 4ull, 0x7fffffffull);
+        int rc_ = frame_alloc(sc, &sc->dq, (size_t)want_q);
+        if (rc_ != FRT_OK) {
+            return rc_;
+        }
+        sc->dq_cap = (unsigned int)want_q;
+    }
     int rc = frame_alloc(sc, &sc->cnt, 1);
     if (rc != FRT_OK) {
         return rc;
@@ -1375,14 +1513,33 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         launch_light_sum<float>(sc, F, blocks, level, li, gw[li]);
                     }
                     CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
-                    if (F.flags & FRT_FLAG_COUNT_RAYS) {
-                        k_shadow<true><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li);
+                    const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
+                    if (F.flags & FRT_FLAG_F64_SHADOW) {
+                        if (count) {
+                            k_shadow_exact<true, true><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                        } else {
+                            k_shadow_exact<false, true><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                        }
+                        launches += 1;
                     } else {
-                        k_shadow<false><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li);
+                        CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));
+                        if (F.flags & FRT_FLAG_VERIFY_F32) {
+                            k_shadow_f32<2><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                        } else if (count) {
+                            k_shadow_f32<1><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                        } else {
+                            k_shadow_f32<0><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                        }
+                        if (count) {
+                            k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                        } else {
+                            k_shadow_exact<false, false><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                        }
+                        launches += 2;
                     }
                     CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                     k_light_resolve<<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->canvas, sc->cnt, level, li);
-                    launches += 3;
+                    launches += 2;
                     ++light_launches;
                 }
             }
@@ -1397,6 +1554,8 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         totals.hits_shaded += hc.hits_shaded;
         totals.shadow_nodes += hc.shadow_nodes;
         totals.light_flops += hc.light_flops;
+        totals.deferred_total += hc.deferred_total;
+        totals.f32_mismatch += hc.f32_mismatch;
         if (hc.overflow_queue) {
             break;
         }
@@ -1421,6 +1580,8 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         st->hits_shaded = totals.hits_shaded;
         st->shadow_nodes = totals.shadow_nodes;
         st->light_flops = totals.light_flops;
+        st->shadow_deferred = totals.deferred_total;
+        st->shadow_mismatch = totals.f32_mismatch;
         st->kernel_launches = launches;
         st->light_launches = light_launches;
         st->rows_rendered = F.n_owned_rows;
@@ -1463,7 +1624,7 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
         cudaMemGetInfo(&free_b, &total_b);
         const unsigned long long frame_samples = std::max<unsigned long long>(st.rays_primary, 1);
         const unsigned long long eff_chunk = std::min<unsigned long long>(chunk, frame_samples);
-        const unsigned long long slot_bytes = 2 * 84 + 28 + sizeof(LightRec) + sizeof(LightTmp);
+        const unsigned long long slot_bytes = 2 * 84 + 28 + sizeof(LightRec) + sizeof(LightTmp) + 4 * sizeof(unsigned long long);
         if (factor < 64 && eff_chunk * factor * 2 * slot_bytes < (free_b + (unsigned long long)sc->capacity * slot_bytes) / 4) {
             factor *= 2;
         } else if (eff_chunk > 4096) {

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FRT_ABI_VERSION 4
+#define FRT_ABI_VERSION 5
 
 enum frt_status {
     FRT_OK = 0,
@@ -197,6 +197,9 @@ enum frt_render_flags {
     FRT_FLAG_NO_PRUNE = 1,   /* also trace branches whose weight is exactly zero, like the reference does
                                 (renderer.c:534-605 on opaque surfaces) -- for ray-count parity only */
     FRT_FLAG_COUNT_RAYS = 2, /* fill the ray counters in frt_stats */
+    FRT_FLAG_F64_SHADOW = 8, /* trace every shadow ray in FP64 (no FP32 filter pass) */
+    FRT_FLAG_VERIFY_F32 = 16,/* trace every shadow ray the FP32 filter decides in FP64 as well and count disagreements
+                                in frt_stats.shadow_mismatch (must be 0); the frame itself uses the FP64 answers */
     FRT_FLAG_F64_SHADING = 4 /* evaluate the lighting sums (lighting_microfacet, renderer.c:894-979) in FP64 like the
                                 reference instead of FP32; geometric decisions are FP64 either way */
 };
@@ -224,6 +227,8 @@ typedef struct frt_stats {
     uint64_t photons_stored[3];
     uint64_t light_flops;    /* with FRT_FLAG_COUNT_RAYS: algorithmic flop of the dominant kernel, counted event by event
                                 with the cost table of BASELINE.md section 4 (ray transform 33, bbox slab 16, sphere 28, ...) */
+    uint64_t shadow_deferred;/* shadow rays the FP32 filter pass left undecided and the FP64 pass re-traced */
+    uint64_t shadow_mismatch;/* FRT_FLAG_VERIFY_F32: FP32-decided rays whose FP64 answer differs */
     int32_t rows_rendered;
     int32_t pad;
 } frt_stats;

@@ -100,3 +100,31 @@ def test_queue_overflow_retries_in_smaller_chunks(frt, monkeypatch):
     monkeypatch.setenv("FRT_CHUNK_SAMPLES", "20000")
     canvas, st = frt.render_multi(desc)
     assert parity_report(canvas[..., :3], ref)["within_1lsb"] >= GATE_WITHIN_1LSB
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fp32_shadow_filter_never_disagrees_with_fp64(frt, name):
+    """The FP32 filtered shadow traversal may only answer rays whose FP64 answer is the same: with
+    FRT_FLAG_VERIFY_F32 every ray it decides is traced in FP64 as well and disagreements are counted."""
+    from compare import parity_report
+    from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_VERIFY_F32
+
+    ref, _ = load_golden(name)
+    desc = frt.SceneDesc.load(GOLDEN / f"{name}.frt")
+    canvas, st = frt.render_multi(desc, flags=FRT_FLAG_VERIFY_F32 | FRT_FLAG_COUNT_RAYS)
+    assert st.shadow_mismatch == 0, st
+    assert st.shadow_deferred <= st.rays_shadow
+    assert parity_report(canvas[..., :3], ref)["within_1lsb"] >= GATE_WITHIN_1LSB
+
+
+@pytest.mark.parametrize("name", ["cornell_exact_96_1spp", "reflect_refract", "lens_test", "group_test"])
+def test_fp64_shadow_and_shading_flags_give_the_same_frame(frt, name):
+    """FRT_FLAG_F64_SHADOW (no FP32 filter) and the default path must agree bit for bit on the shadow counts, i.e.
+    on the canvas when the shading sums are evaluated the same way."""
+    from fast_ray_tracer_b200.api import FRT_FLAG_F64_SHADING, FRT_FLAG_F64_SHADOW
+
+    desc = frt.SceneDesc.load(GOLDEN / f"{name}.frt")
+    with frt.Scene(desc) as sc:
+        a, _ = sc.render(flags=FRT_FLAG_F64_SHADING)
+        b, _ = sc.render(flags=FRT_FLAG_F64_SHADING | FRT_FLAG_F64_SHADOW)
+    assert np.array_equal(a, b)
