@@ -591,12 +591,14 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
  * pick is a hash of (seed, path id, light, pass).  With cache_len == 1 both passes use set 0 and the result is
  * exactly the reference's.
  */
-struct LightTmp { /* per shaded hit, per light launch */
-    float sum_ndl, sum_b, sum_fb; /* sums over the lighting sample set */
+struct LightTmp { /* per shaded hit, per light launch; the first 16 bytes are all k_shadow_f32 reads per ray */
+    float ox, oy, oz;             /* over_point rounded to FP32 (origin of the hit's shadow rays in the FP32 filter) */
     int set_a;                    /* sample set of the shadow pass; -1: the hit cannot receive light, skip its shadow rays */
+    float sum_ndl, sum_b, sum_fb; /* sums over the lighting sample set */
     int unshadowed;               /* shadow rays that reached the light */
-    int contributes;              /* some lighting term of the hit is non-zero */
     double dsum_ndl, dsum_b, dsum_fb; /* the same sums in FP64 (FRT_FLAG_F64_SHADING) */
+    int contributes;              /* some lighting term of the hit is non-zero */
+    int pad;
 };
 
 /*
@@ -696,6 +698,10 @@ k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
             t.set_a = (contributes || (F.flags & FRT_FLAG_NO_PRUNE)) ? set_a : -1;
             t.unshadowed = 0;
             t.contributes = contributes ? 1 : 0;
+            t.pad = 0;
+            t.ox = (float)over[0];
+            t.oy = (float)over[1];
+            t.oz = (float)over[2];
             tmp[hbase] = t;
         }
     }
@@ -749,38 +755,73 @@ normalise_shadow_ray(Ray &sr, double dist2)
 template <int MODE>
 __global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
 k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
-             int level, int light_idx, unsigned long long *__restrict__ queue, unsigned int qcap)
+             int level, int light_idx, unsigned long long *__restrict__ queue, unsigned int qcap, int nodes_in_smem)
 {
     constexpr bool COUNT = MODE != 0;
+    extern __shared__ float4 s_nodes[];
+    const float4 *fnodes = SF.fnodes;
+    if (nodes_in_smem) { /* small trees (every scene but the OBJ meshes) are walked out of shared memory */
+        for (int k = threadIdx.x; k < 3 * SF.n_nodes; k += blockDim.x) {
+            s_nodes[k] = SF.fnodes[k];
+        }
+        __syncthreads();
+        fnodes = s_nodes;
+    }
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
     const int NS = S.lights[light_idx].num_samples;
+    const float *fpts = SF.lpoints + 3 * S.lights[light_idx].point_offset;
     const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
     const unsigned long long total = (unsigned long long)n * (unsigned int)NS;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const bool small = total <= 0xffffffffull;
+    const int root = __ldg(S.roots);
     int overflow = 0;
     unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0, n_mismatch = 0;
 
     for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
         const unsigned long long item = base + (threadIdx.x & 31);
         unsigned int h = 0;
-        int set_a = -1;
-        Ray sr{};
-        double dist2 = 1.0;
+        int s = 0;
+        float4 head = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         if (item < total) {
-            shadow_item(S, recs, tmp, pts, NS, item, small, h, set_a, sr, dist2);
+            h = small ? (unsigned int)item / (unsigned int)NS : (unsigned int)(item / (unsigned int)NS);
+            s = (int)(item - (unsigned long long)h * (unsigned int)NS);
+            head = *reinterpret_cast<const float4 *>(tmp + h);
         }
+        const int set_a = __float_as_int(head.w);
         int res = FRT_SH_SHADOWED;
         if (set_a >= 0) {
-            /* the FP32 ray: FP64 difference of the two world points, rounded, normalised in FP32 */
-            const float vx = (float)sr.dx, vy = (float)sr.dy, vz = (float)sr.dz;
-            const float len2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
-            const float rinv = rsqrtf(len2);
-            const RayF w{ (float)sr.ox, (float)sr.oy, (float)sr.oz, vx * rinv, vy * rinv, vz * rinv };
-            res = trace_shadow_f32<COUNT>(S, SF, sr, w, len2 * rinv, &overflow, &n_nodes, &n_flops);
+            if (S.n_roots != 1) {
+                res = FRT_SH_UNDECIDED; /* several top-level shapes (world.c:189-191): never generated; FP64 handles it */
+            } else {
+                /* the FP32 ray: both world points rounded to FP32, difference and normalisation in FP32 */
+                const float *pa = fpts + 3 * ((size_t)set_a * NS + s);
+                const float px = __ldg(pa), py = __ldg(pa + 1), pz = __ldg(pa + 2);
+                FrameF w;
+                w.ox = head.x;
+                w.oy = head.y;
+                w.oz = head.z;
+                const float vx = px - w.ox, vy = py - w.oy, vz = pz - w.oz;
+                const float len2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
+                const float rinv = rsqrtf(len2);
+                w.dx = vx * rinv;
+                w.dy = vy * rinv;
+                w.dz = vz * rinv;
+                const float omax = fmaxf(fmaxf(fabsf(w.ox), fabsf(w.oy)), fabsf(w.oz));
+                const float pmax = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
+                const float eo_w = 2.0f * FRT_F32_U * (omax + SF.bmax);
+                const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G);
+                frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
+                const float Df = len2 * rinv;
+                res = trace_shadow_f32<COUNT>(SF, fnodes, root, w, omax, eo_w, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
+            }
             if (COUNT) ++n_shadow;
             if (MODE == 2 && res != FRT_SH_UNDECIDED) {
-                Ray er = sr;
+                unsigned int h2;
+                int sa2;
+                Ray er;
+                double dist2;
+                shadow_item(S, recs, tmp, pts, NS, item, small, h2, sa2, er, dist2);
                 const double dist = normalise_shadow_ray(er, dist2);
                 unsigned long long dn = 0, df = 0;
                 const bool sh = trace_shadow<false>(S, er, dist, &overflow, &dn, &df);
@@ -827,6 +868,14 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
             if (n_flops) atomicAdd(&cnt->light_flops, n_flops);
             if (n_mismatch) atomicAdd(&cnt->f32_mismatch, n_mismatch);
         }
+    }
+}
+
+__global__ void
+k_to_float(const double *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        dst[i] = (float)src[i];
     }
 }
 
@@ -970,6 +1019,15 @@ frt_measure_fma_peak(int device, double *fp64_tflops, double *fp32_tflops)
 }
 
 /* ------------------------------------------------------------------------------------------------ scene */
+
+static inline float
+__int_as_float_host(int v)
+{
+    float f;
+    memcpy(&f, &v, sizeof(f));
+    return f;
+}
+
 
 struct frt_scene {
     int device = 0;
@@ -1118,6 +1176,126 @@ frt_scene_destroy(frt_scene *sc)
     delete sc;
 }
 
+/*
+ * FP32 mirror for the filtered shadow traversal (frt_shadow_f32.cuh).  A node whose composite world->local matrix is
+ * axis-aligned (one significant entry per row: scalings, translations, quarter turns) gets its bounds -- the unit
+ * cube of a cube leaf, the bounding box of a group / CSG -- mapped to WORLD space here, once, in FP64:
+ *      local_k = s_k * world_p(k) + T_k   =>   world_p(k) in [(lo_k - T_k) / s_k, (hi_k - T_k) / s_k]  (sorted)
+ * Leaf bounds are rounded to nearest (their rounding is part of the traversal's error term), cull bounds outward.
+ */
+static int
+build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
+{
+    std::vector<float4> fx((size_t)4 * d->n_xforms), fn((size_t)3 * d->n_nodes);
+    std::vector<int> aligned(d->n_xforms, 0), perm((size_t)3 * d->n_xforms, 0);
+    for (int i = 0; i < d->n_xforms; ++i) {
+        const double *m = d->xforms[i].inv;
+        float R[3];
+        bool ok = true;
+        bool used[3] = { false, false, false };
+        for (int k = 0; k < 3; ++k) {
+            fx[4 * i + k] = make_float4((float)m[4 * k], (float)m[4 * k + 1], (float)m[4 * k + 2], (float)m[4 * k + 3]);
+            double r = fabs(m[4 * k]) + fabs(m[4 * k + 1]) + fabs(m[4 * k + 2]);
+            R[k] = nextafterf((float)(r * (1.0 + 1e-6)), INFINITY);
+            int big = 0;
+            for (int j = 1; j < 3; ++j) {
+                if (fabs(m[4 * k + j]) > fabs(m[4 * k + big])) big = j;
+            }
+            for (int j = 0; j < 3; ++j) {
+                if (j != big && fabs(m[4 * k + j]) > 1e-12 * fabs(m[4 * k + big])) ok = false;
+            }
+            if (m[4 * k + big] == 0.0 || used[big]) ok = false;
+            used[big] = true;
+            perm[3 * i + k] = big;
+        }
+        fx[4 * i + 3] = make_float4(R[0], R[1], R[2], 0.f);
+        aligned[i] = ok ? 1 : 0;
+    }
+    auto down = [](double x) { float f = (float)x; return ((double)f > x) ? nextafterf(f, -INFINITY) : f; };
+    auto up = [](double x) { float f = (float)x; return ((double)f < x) ? nextafterf(f, INFINITY) : f; };
+    double bmax = 0.0;
+    for (int i = 0; i < d->n_nodes; ++i) {
+        const frt_node &n = d->nodes[i];
+        const bool inner = n.type >= FRT_CSG;
+        int flags = n.type;
+        double lo[3], hi[3];
+        if (inner) {
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = n.bbox_min[k];
+                hi[k] = n.bbox_max[k];
+            }
+            if (n.type == FRT_CSG) flags |= (n.csg_op & 3) << FRT_FN_OP_SHIFT;
+        } else {
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = -1.0;
+                hi[k] = 1.0;
+            }
+            if (d->materials[n.material].casts_shadow) flags |= FRT_FN_CASTS;
+            if (n.type == FRT_CUBE || n.type == FRT_SPHERE || n.type == FRT_PLANE) flags |= FRT_FN_FAST;
+        }
+        bool world = n.xform == 0;
+        if (!world && aligned[n.xform] && (inner || n.type == FRT_CUBE)) {
+            const double *m = d->xforms[n.xform].inv;
+            double wlo[3], whi[3];
+            for (int k = 0; k < 3; ++k) {
+                const int p = perm[3 * n.xform + k];
+                const double sk = m[4 * k + p], T = m[4 * k + 3];
+                double a = (lo[k] - T) / sk, b = (hi[k] - T) / sk;
+                wlo[p] = std::min(a, b);
+                whi[p] = std::max(a, b);
+            }
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = wlo[k];
+                hi[k] = whi[k];
+            }
+            world = true;
+        }
+        if (n.type == FRT_GROUP && n.parent < 0) {
+            flags |= FRT_FN_NOCULL; /* shadow rays start inside the world group's box: the test never culls */
+        }
+        if (world) {
+            flags |= FRT_FN_WORLD;
+            if (inner || n.type == FRT_CUBE) {
+                for (int k = 0; k < 3; ++k) {
+                    if (std::isfinite(lo[k])) bmax = std::max(bmax, fabs(lo[k]));
+                    if (std::isfinite(hi[k])) bmax = std::max(bmax, fabs(hi[k]));
+                }
+            }
+        }
+        float4 q0;
+        q0.x = __int_as_float_host(flags);
+        q0.y = __int_as_float_host(n.skip);
+        q0.z = __int_as_float_host(world ? 0 : n.xform);
+        q0.w = __int_as_float_host(n.right);
+        fn[3 * i] = q0;
+        if (inner) {
+            fn[3 * i + 1] = make_float4(down(lo[0]), down(lo[1]), down(lo[2]), 0.f);
+            fn[3 * i + 2] = make_float4(up(hi[0]), up(hi[1]), up(hi[2]), 0.f);
+        } else {
+            fn[3 * i + 1] = make_float4((float)lo[0], (float)lo[1], (float)lo[2], 0.f);
+            fn[3 * i + 2] = make_float4((float)hi[0], (float)hi[1], (float)hi[2], 0.f);
+        }
+    }
+    int rc = upload(sc, fx.data(), fx.size(), &sc->SF.fx);
+    if (rc != FRT_OK) return rc;
+    rc = upload(sc, fn.data(), fn.size(), &sc->SF.fnodes);
+    if (rc != FRT_OK) return rc;
+    sc->SF.bmax = nextafterf((float)(bmax * (1.0 + 1e-6)), INFINITY);
+    sc->SF.n_nodes = d->n_nodes;
+    /* FP32 copy of the light sample points, converted on the device */
+    const size_t np = (size_t)3 * d->n_light_points;
+    float *fp = nullptr;
+    CK(cudaMalloc(&fp, std::max<size_t>(np, 1) * sizeof(float)));
+    sc->allocs.push_back(fp);
+    if (np) {
+        k_to_float<<<148 * 8, 256>>>(sc->S.lpoints, fp, np);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
+    sc->SF.lpoints = fp;
+    return FRT_OK;
+}
+
 extern "C" int
 frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
 {
@@ -1173,30 +1351,7 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
     UP(upload(sc, d->lights, (size_t)d->n_lights, &S.lights));
     UP(upload(sc, d->light_points, (size_t)3 * d->n_light_points, &S.lpoints));
     UP(upload(sc, d->roots, (size_t)d->n_roots, &S.roots));
-    {
-        /* FP32 mirror for the filtered shadow traversal (frt_shadow_f32.cuh): matrices rounded to nearest with the
-         * row sums R_k rounded up, bounding boxes rounded outward */
-        std::vector<float4> fx((size_t)4 * d->n_xforms), fb((size_t)2 * d->n_nodes);
-        for (int i = 0; i < d->n_xforms; ++i) {
-            const double *m = d->xforms[i].inv;
-            float R[3];
-            for (int k = 0; k < 3; ++k) {
-                fx[4 * i + k] = make_float4((float)m[4 * k], (float)m[4 * k + 1], (float)m[4 * k + 2], (float)m[4 * k + 3]);
-                double r = fabs(m[4 * k]) + fabs(m[4 * k + 1]) + fabs(m[4 * k + 2]);
-                R[k] = nextafterf((float)(r * (1.0 + 1e-6)), INFINITY);
-            }
-            fx[4 * i + 3] = make_float4(R[0], R[1], R[2], 0.f);
-        }
-        auto down = [](double x) { float f = (float)x; return ((double)f > x) ? nextafterf(f, -INFINITY) : f; };
-        auto up = [](double x) { float f = (float)x; return ((double)f < x) ? nextafterf(f, INFINITY) : f; };
-        for (int i = 0; i < d->n_nodes; ++i) {
-            const frt_node &n = d->nodes[i];
-            fb[2 * i] = make_float4(down(n.bbox_min[0]), down(n.bbox_min[1]), down(n.bbox_min[2]), 0.f);
-            fb[2 * i + 1] = make_float4(up(n.bbox_max[0]), up(n.bbox_max[1]), up(n.bbox_max[2]), 0.f);
-        }
-        UP(upload(sc, fx.data(), fx.size(), &sc->SF.fx));
-        UP(upload(sc, fb.data(), fb.size(), &sc->SF.fbbox));
-    }
+    UP(build_f32_mirror(sc, d));
     S.n_roots = d->n_roots;
     S.n_nodes = d->n_nodes;
     S.n_lights = d->n_lights;
@@ -1522,13 +1677,14 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         }
                         launches += 1;
                     } else {
+                        const size_t f32_smem = (size_t)sc->S.n_nodes * 48 <= 32768 ? (size_t)sc->S.n_nodes * 48 : 0;
                         CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));
                         if (F.flags & FRT_FLAG_VERIFY_F32) {
-                            k_shadow_f32<2><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_f32<2><<<blocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         } else if (count) {
-                            k_shadow_f32<1><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_f32<1><<<blocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         } else {
-                            k_shadow_f32<0><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_f32<0><<<blocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         }
                         if (count) {
                             k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);

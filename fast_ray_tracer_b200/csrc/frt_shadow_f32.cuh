@@ -4,50 +4,74 @@
  * is_shadowed (renderer.c:73-93) is 98.7 % of the reference's rays on the Cornell scene and
  * its answer is one bit.  That bit is the outcome of a chain of comparisons (slab order, t against 0, t against the
  * light distance, order of CSG crossings).  This file walks the same tree in the same order as the FP64 traversal
- * (trace_shadow in frt_device.cuh) but in FP32, carrying a conservative absolute error bound next to every t value:
+ * (trace_shadow in frt_device.cuh) but in FP32 interval arithmetic: every t value is an interval [lo, hi] that
+ * surely contains the value the FP64 traversal computes.
  *
- *   - a comparison whose operands are further apart than their bounds has the same outcome as in FP64: keep going;
+ *   - a comparison of two disjoint intervals has the same outcome as in FP64: keep going;
  *   - a group / CSG bounding-box test is only a cull, so it is resolved conservatively (when in doubt, descend:
  *     the children are inside the box, so descending where the reference culls changes nothing);
- *   - any other comparison that the bounds cannot decide makes the whole ray UNDECIDED.  The caller appends the
- *     ray to a queue (warp-aggregated) and a second kernel re-traces the queue in FP64.  On the Cornell frame that
- *     is a few percent of the rays (silhouettes, grazing starts, exact CSG ties).
+ *   - anything else -- overlapping intervals, a primitive type or a CSG shape this filter has no fast form for --
+ *     makes the ray UNDECIDED.  The caller appends it to a queue (warp-aggregated) and a second kernel re-traces
+ *     the queue with the general FP64 traversal.  On the Cornell frame that is ~2 % of the rays.
  *
- * The bit that comes out is therefore the FP64 traversal's bit; FRT_FLAG_VERIFY_F32 checks that claim ray by ray on
- * the device (every decided ray is also traced in FP64 and disagreements are counted; tests assert zero).
+ * The filter is therefore free to be narrow: it only has to be right when it answers.  FRT_FLAG_VERIFY_F32 checks
+ * that claim ray by ray on the device (every decided ray is also traced in FP64; tests assert zero disagreements).
  *
- * Error model.  u = 2^-24 is the FP32 unit roundoff.  G = 2^-21 = 8u bounds the rounding of any expression of up
- * to four products / sums relative to the sum of the magnitudes of its terms.  The world ray is the FP64 ray
- * rounded to FP32 (origin: relative u per component; unit direction and distance: a few u after the FP32
- * normalisation, taken as G).  A transform M (rows m_k, translation T_k) maps these to local bounds
- *      eo_k = R_k * (u + G) * |o|max + G * |T_k|,     ed_k = R_k * 2G,          R_k = sum_j |m_kj|
- * and a slab value t = (b - o_k) / d_k with |d_k| >= 2 ed_k carries
- *      E_t = |1/d_k| * (eo_k + 2 |t| ed_k) + G |t|.
+ * What it has fast forms for
+ *   - cube leaves and group / CSG bounds whose composite transform is axis-aligned (scale, translate, quarter
+ *     turns: every wall of the Cornell box): slab test against the WORLD-space box with the world ray -- no
+ *     transform at all.  t is the same parameter in world and local space, so the value is the reference's up to
+ *     FP64 rounding (1e-16), far inside the FP32 intervals;
+ *   - other cubes, spheres, planes: transform to the leaf's frame (FP32 copy of the matrix), then slab / quadratic;
+ *   - CSG (csg_local_intersect + csg_filter_intersections, csg.c:43-125) over operands that each cross the ray as
+ *     ONE interval [enter, exit]: union / intersection / difference of two intervals by the reference's in/out
+ *     toggling rules, worked out per ordering (see csg_combine).  A result that would be two intervals is left to
+ *     FP64.
+ *
+ * Error model.  u = 2^-24 (FP32 unit roundoff), G = 2^-21 = 8u bounds the rounding of an expression of up to four
+ * products / sums relative to the sum of the magnitudes of its terms.  World frame: origin rounded from FP64 and box
+ * bounds rounded to nearest, eo = 2u (|o|max + Bmax); direction normalised in FP32 from the rounded difference of
+ * the two world points, ed = G + 2u (|p|max + |o|max) / |p - o|.  A transform M (rows m_k, translation T_k) maps
+ * these to  eo_k = R_k eo + G (R_k |o|max + |T_k|),  ed_k = R_k (ed + G),  R_k = sum_j |m_kj|.  A slab value
+ * t = (b - o_k) / d_k with |d_k| >= EPSILON + 2 ed_k lies within  |1/d_k| (eo_k + 2 |t| ed_k) + G |t|  of its
+ * FP32 evaluation; axes with a smaller |d_k| (the reference's "* INFINITY" branch, cube.c:27-33) are left open for
+ * culls and make a leaf undecided.
  */
 #pragma once
 
 #include "frt_device.cuh"
 
-#define FRT_F32_G 4.76837158203125e-07f /* 2^-21 */
+#define FRT_F32_G 4.76837158203125e-07f   /* 2^-21 */
 #define FRT_F32_U 5.9604644775390625e-08f /* 2^-24 */
 #define FRT_EPS_F 0.00001f
 
 enum { FRT_SH_LIT = 0, FRT_SH_SHADOWED = 1, FRT_SH_UNDECIDED = 2 };
 
-struct DSceneF { /* FP32 mirror of the tree, built at upload */
-    const float4 *fx;    /* 4 x float4 per xform: rows 0..2 of the world->local matrix, then {R_0, R_1, R_2, 0} */
-    const float4 *fbbox; /* 2 x float4 per node: {min.xyz, 0} {max.xyz, 0}, rounded outward */
+/* FP32 mirror of one tree node, 3 x float4 */
+enum {
+    FRT_FN_TYPE_MASK = 15, /* enum frt_node_type */
+    FRT_FN_WORLD = 16,     /* lo / hi are WORLD-space bounds: test them with the world ray (no transform) */
+    FRT_FN_CASTS = 32,     /* leaf: its material casts shadows */
+    FRT_FN_FAST = 64,      /* leaf: the filter has a fast form for this type (cube, sphere, plane) */
+    FRT_FN_NOCULL = 128,   /* group: descend without testing its bounds (culling is optional; the root's box is always hit) */
+    FRT_FN_OP_SHIFT = 8    /* CSG: enum frt_csg_op in bits 8..9 */
 };
 
-struct RayF {
+struct DSceneF {
+    const float4 *fnodes; /* per node: {flags, skip, xform, right (CSG)} as int bits, {lo.xyz, 0}, {hi.xyz, 0} */
+    const float4 *fx;     /* per xform: rows 0..2 of the world->local matrix, then {R_0, R_1, R_2, 0} */
+    const float *lpoints; /* FP32 copy of the light sample points, 3 per point */
+    float bmax;           /* largest finite |bound| of a WORLD node */
+    int n_nodes;
+};
+
+/* a ray in some frame, ready for slab tests */
+struct FrameF {
     float ox, oy, oz, dx, dy, dz;
-};
-
-struct LocalF {
-    RayF r;
-    float ix, iy, iz;    /* 1 / d_k */
-    float eox, eoy, eoz; /* bounds on the local origin */
-    float edx, edy, edz; /* bounds on the local direction */
+    float ix, iy, iz;    /* 1 / d_k, or 0 on an axis left open */
+    float c1x, c1y, c1z; /* |1/d_k| eo_k, or +inf on an axis left open */
+    float c2x, c2y, c2z; /* 2 |1/d_k| ed_k + G */
+    float eo, ed;        /* max_k eo_k, max_k ed_k (sphere) */
 };
 
 __device__ __forceinline__ float
@@ -59,356 +83,407 @@ rcpf_fast(float x)
 }
 
 __device__ __forceinline__ void
-local_setup(LocalF &L, const DSceneF &SF, int xf, const RayF &w, float omax)
+frame_axis(float d, float eo, float ed, float &inv, float &c1, float &c2)
 {
-    const float c_o = (FRT_F32_U + FRT_F32_G) * omax;
-    if (xf == 0) {
-        L.r = w;
-        L.eox = L.eoy = L.eoz = c_o;
-        L.edx = L.edy = L.edz = FRT_F32_G;
-    } else {
-        const float4 m0 = __ldg(SF.fx + 4 * xf), m1 = __ldg(SF.fx + 4 * xf + 1), m2 = __ldg(SF.fx + 4 * xf + 2);
-        const float4 R = __ldg(SF.fx + 4 * xf + 3);
-        L.r.ox = fmaf(m0.x, w.ox, fmaf(m0.y, w.oy, fmaf(m0.z, w.oz, m0.w)));
-        L.r.oy = fmaf(m1.x, w.ox, fmaf(m1.y, w.oy, fmaf(m1.z, w.oz, m1.w)));
-        L.r.oz = fmaf(m2.x, w.ox, fmaf(m2.y, w.oy, fmaf(m2.z, w.oz, m2.w)));
-        L.r.dx = fmaf(m0.x, w.dx, fmaf(m0.y, w.dy, m0.z * w.dz));
-        L.r.dy = fmaf(m1.x, w.dx, fmaf(m1.y, w.dy, m1.z * w.dz));
-        L.r.dz = fmaf(m2.x, w.dx, fmaf(m2.y, w.dy, m2.z * w.dz));
-        L.eox = fmaf(R.x, c_o, FRT_F32_G * fabsf(m0.w));
-        L.eoy = fmaf(R.y, c_o, FRT_F32_G * fabsf(m1.w));
-        L.eoz = fmaf(R.z, c_o, FRT_F32_G * fabsf(m2.w));
-        L.edx = R.x * (2.0f * FRT_F32_G);
-        L.edy = R.y * (2.0f * FRT_F32_G);
-        L.edz = R.z * (2.0f * FRT_F32_G);
-    }
-    L.ix = rcpf_fast(L.r.dx);
-    L.iy = rcpf_fast(L.r.dy);
-    L.iz = rcpf_fast(L.r.dz);
+    const bool ok = fabsf(d) >= FRT_EPS_F + 2.0f * ed;
+    const float r = rcpf_fast(d);
+    inv = ok ? r : 0.0f;
+    c1 = ok ? fabsf(r) * eo : CUDART_INF_F;
+    c2 = ok ? fmaf(2.0f * fabsf(r), ed, FRT_F32_G) : FRT_F32_G;
 }
 
-/* one slab axis: interval [lo, hi] of t and the bound E on both ends; valid only when |d| >= EPS + 2 ed */
 __device__ __forceinline__ void
-slab_f(float o, float inv, float eo, float ed, float blo, float bhi, float &lo, float &hi, float &E)
+frame_finish(FrameF &f, float eox, float eoy, float eoz, float edx, float edy, float edz)
 {
-    const float a = (blo - o) * inv;
-    const float b = (bhi - o) * inv;
-    lo = fminf(a, b);
-    hi = fmaxf(a, b);
-    const float tabs = fmaxf(fabsf(a), fabsf(b));
-    E = fmaf(fabsf(inv), fmaf(2.0f * tabs, ed, eo), FRT_F32_G * tabs);
+    frame_axis(f.dx, eox, edx, f.ix, f.c1x, f.c2x);
+    frame_axis(f.dy, eoy, edy, f.iy, f.c1y, f.c2y);
+    frame_axis(f.dz, eoz, edz, f.iz, f.c1z, f.c2z);
+    f.eo = fmaxf(fmaxf(eox, eoy), eoz);
+    f.ed = fmaxf(fmaxf(edx, edy), edz);
 }
 
-/* conservative bounding_box_intersects (bounding_box.c:165-175): false only when the FP64 test is surely false */
-__device__ __forceinline__ bool
-bbox_maybe_f(const DSceneF &SF, int node, const LocalF &L)
+/* the world ray in the frame of transform xf (xf != 0) */
+__device__ __forceinline__ void
+frame_local(FrameF &f, const DSceneF &SF, int xf, const FrameF &w, float omax, float eo_w, float ed_w)
 {
-    const float4 bmin = __ldg(SF.fbbox + 2 * node), bmax = __ldg(SF.fbbox + 2 * node + 1);
-    float tn = -CUDART_INF_F, tf = CUDART_INF_F;
-    float lo, hi, E;
-    if (fabsf(L.r.dx) >= FRT_EPS_F + 2.0f * L.edx) {
-        slab_f(L.r.ox, L.ix, L.eox, L.edx, bmin.x, bmax.x, lo, hi, E);
-        tn = fmaxf(tn, lo - E); /* a NaN (unbounded box side) drops out of fmaxf / fminf: the axis stays open */
-        tf = fminf(tf, hi + E);
-    }
-    if (fabsf(L.r.dy) >= FRT_EPS_F + 2.0f * L.edy) {
-        slab_f(L.r.oy, L.iy, L.eoy, L.edy, bmin.y, bmax.y, lo, hi, E);
-        tn = fmaxf(tn, lo - E);
-        tf = fminf(tf, hi + E);
-    }
-    if (fabsf(L.r.dz) >= FRT_EPS_F + 2.0f * L.edz) {
-        slab_f(L.r.oz, L.iz, L.eoz, L.edz, bmin.z, bmax.z, lo, hi, E);
-        tn = fmaxf(tn, lo - E);
-        tf = fminf(tf, hi + E);
-    }
-    return !(tn > tf);
+    const float4 m0 = __ldg(SF.fx + 4 * xf), m1 = __ldg(SF.fx + 4 * xf + 1), m2 = __ldg(SF.fx + 4 * xf + 2);
+    const float4 R = __ldg(SF.fx + 4 * xf + 3);
+    f.ox = fmaf(m0.x, w.ox, fmaf(m0.y, w.oy, fmaf(m0.z, w.oz, m0.w)));
+    f.oy = fmaf(m1.x, w.ox, fmaf(m1.y, w.oy, fmaf(m1.z, w.oz, m1.w)));
+    f.oz = fmaf(m2.x, w.ox, fmaf(m2.y, w.oy, fmaf(m2.z, w.oz, m2.w)));
+    f.dx = fmaf(m0.x, w.dx, fmaf(m0.y, w.dy, m0.z * w.dz));
+    f.dy = fmaf(m1.x, w.dx, fmaf(m1.y, w.dy, m1.z * w.dz));
+    f.dz = fmaf(m2.x, w.dx, fmaf(m2.y, w.dy, m2.z * w.dz));
+    const float go = fmaf(FRT_F32_G, omax, eo_w), gd = ed_w + FRT_F32_G;
+    frame_finish(f, fmaf(R.x, go, FRT_F32_G * fabsf(m0.w)), fmaf(R.y, go, FRT_F32_G * fabsf(m1.w)),
+                 fmaf(R.z, go, FRT_F32_G * fabsf(m2.w)), R.x * gd, R.y * gd, R.z * gd);
 }
 
-/*
- * Crossings of one leaf in FP32 as intervals [tlo_j, thi_j] that surely contain the FP64 values: returns the count
- * (like prim_intersect), -1 when the count itself is undecided.  Cube, sphere and plane are evaluated in FP32;
- * every other type is evaluated in FP64 on the exact ray (`wr`), so its values only carry the final rounding.
- */
-__device__ __forceinline__ int
-prim_f(const DScene &S, int type, int xf, int param, const LocalF &L, const Ray &wr, float tlo[4], float thi[4])
+/* entry / exit of the ray through the box [lo, hi] as intervals: tn in [tn_lo, tn_hi], tf in [tf_lo, tf_hi] */
+__device__ __forceinline__ void
+box_f(const FrameF &f, const float4 lo, const float4 hi, float &tn_lo, float &tn_hi, float &tf_lo, float &tf_hi)
 {
-    if (type == FRT_CUBE) { /* cube_local_intersect, cube.c:56-78 */
-        if (!(fabsf(L.r.dx) >= FRT_EPS_F + 2.0f * L.edx) || !(fabsf(L.r.dy) >= FRT_EPS_F + 2.0f * L.edy) ||
-            !(fabsf(L.r.dz) >= FRT_EPS_F + 2.0f * L.edz)) {
-            return -1; /* an axis-parallel ray takes the reference's INFINITY branch: leave it to FP64 */
-        }
-        float x0, x1, y0, y1, z0, z1, ex, ey, ez;
-        slab_f(L.r.ox, L.ix, L.eox, L.edx, -1.0f, 1.0f, x0, x1, ex);
-        slab_f(L.r.oy, L.iy, L.eoy, L.edy, -1.0f, 1.0f, y0, y1, ey);
-        slab_f(L.r.oz, L.iz, L.eoz, L.edz, -1.0f, 1.0f, z0, z1, ez);
-        /* tmin = max of the entries, tmax = min of the exits, as intervals */
-        const float tn_lo = fmaxf(fmaxf(x0 - ex, y0 - ey), z0 - ez), tn_hi = fmaxf(fmaxf(x0 + ex, y0 + ey), z0 + ez);
-        const float tf_lo = fminf(fminf(x1 - ex, y1 - ey), z1 - ez), tf_hi = fminf(fminf(x1 + ex, y1 + ey), z1 + ez);
-        if (tn_lo > tf_hi) {
-            return 0; /* tmin > tmax for sure */
-        }
-        if (!(tn_hi < tf_lo)) {
-            return -1;
-        }
-        tlo[0] = tn_lo;
-        thi[0] = tn_hi;
-        tlo[1] = tf_lo;
-        thi[1] = tf_hi;
-        return 2;
-    }
-    if (type == FRT_PLANE) { /* plane_local_intersect, plane.c:11-25 */
-        if (fabsf(L.r.dy) + L.edy < FRT_EPS_F) {
-            return 0;
-        }
-        if (!(fabsf(L.r.dy) >= FRT_EPS_F + 2.0f * L.edy)) {
-            return -1;
-        }
-        const float tt = -L.r.oy * L.iy;
-        const float E = fmaf(fabsf(L.iy), fmaf(2.0f * fabsf(tt), L.edy, L.eoy), FRT_F32_G * fabsf(tt));
-        tlo[0] = tt - E;
-        thi[0] = tt + E;
-        return 1;
-    }
-    if (type == FRT_SPHERE) { /* sphere_local_intersect, sphere.c:14-40 */
-        const RayF &r = L.r;
-        const float eo = fmaxf(fmaxf(L.eox, L.eoy), L.eoz), ed = fmaxf(fmaxf(L.edx, L.edy), L.edz);
-        const float So = fabsf(r.ox) + fabsf(r.oy) + fabsf(r.oz), Sd = fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz);
-        const float a = fmaf(r.dx, r.dx, fmaf(r.dy, r.dy, r.dz * r.dz));
-        const float hb = fmaf(r.dx, r.ox, fmaf(r.dy, r.oy, r.dz * r.oz));
-        const float habs = fmaf(fabsf(r.dx), fabsf(r.ox), fmaf(fabsf(r.dy), fabsf(r.oy), fabsf(r.dz * r.oz)));
-        const float oo = fmaf(r.ox, r.ox, fmaf(r.oy, r.oy, r.oz * r.oz));
-        const float b = 2.0f * hb, c = oo - 1.0f;
-        const float da = fmaf(2.0f * Sd + 3.0f * ed, ed, FRT_F32_G * a);
-        const float db = 2.0f * (fmaf(Sd, eo, fmaf(So, ed, 3.0f * eo * ed)) + FRT_F32_G * habs);
-        const float dc = fmaf(2.0f * So + 3.0f * eo, eo, FRT_F32_G * (oo + 1.0f));
-        const float disc = fmaf(b, b, -4.0f * a * c);
-        const float dD = fmaf(2.0f * fabsf(b) + db, db, 4.0f * (fmaf(a, dc, fmaf(fabsf(c), da, da * dc)))) +
-                         FRT_F32_G * fmaf(b, b, 4.0f * a * fabsf(c));
-        if (disc + dD < 0.0f) {
-            return 0;
-        }
-        if (!(disc > 4.0f * dD) || !(a > 4.0f * da)) {
-            return -1;
-        }
-        const float s = sqrtf(disc);
-        const float ds = dD / s + FRT_F32_G * s;
-        const float i2a = rcpf_fast(2.0f * a);
-        const float ra = 2.0f * (da / a) + 2.0f * FRT_F32_G;
-        const float t0 = (-b - s) * i2a, t1 = (-b + s) * i2a;
-        const float E0 = (db + ds) * 2.0f * i2a;
-        const float e0 = fmaf(fabsf(t0), ra, E0), e1 = fmaf(fabsf(t1), ra, E0);
-        tlo[0] = t0 - e0;
-        thi[0] = t0 + e0;
-        tlo[1] = t1 - e1;
-        thi[1] = t1 + e1;
-        return 2;
-    }
-    /* cylinder, cone, torus, triangles: FP64 on the exact ray (`wr` arrives with its direction not yet normalised) */
-    Ray er = wr;
-    {
-        const double inv = rsqrt_fast(er.dx * er.dx + er.dy * er.dy + er.dz * er.dz);
-        er.dx *= inv;
-        er.dy *= inv;
-        er.dz *= inv;
-    }
-    const Ray lr = ray_to_local(S, xf, er);
-    double td[4], uv[2];
-    const int k = prim_intersect(type, S.params + (param < 0 ? 0 : param), lr, td, uv);
-    for (int j = 0; j < k; ++j) {
-        const float tt = (float)td[j];
-        const float E = 2.0f * FRT_F32_U * fabsf(tt) + 1e-37f;
-        tlo[j] = tt - E;
-        thi[j] = tt + E;
-    }
-    return k;
+    float a = (lo.x - f.ox) * f.ix, b = (hi.x - f.ox) * f.ix;
+    float mn = fminf(a, b), mx = fmaxf(a, b);
+    float E = fmaf(fmaxf(fabsf(a), fabsf(b)), f.c2x, f.c1x);
+    tn_lo = mn - E;
+    tn_hi = mn + E;
+    tf_lo = mx - E;
+    tf_hi = mx + E;
+    a = (lo.y - f.oy) * f.iy;
+    b = (hi.y - f.oy) * f.iy;
+    mn = fminf(a, b);
+    mx = fmaxf(a, b);
+    E = fmaf(fmaxf(fabsf(a), fabsf(b)), f.c2y, f.c1y);
+    tn_lo = fmaxf(tn_lo, mn - E);
+    tn_hi = fmaxf(tn_hi, mn + E);
+    tf_lo = fminf(tf_lo, mx - E);
+    tf_hi = fminf(tf_hi, mx + E);
+    a = (lo.z - f.oz) * f.iz;
+    b = (hi.z - f.oz) * f.iz;
+    mn = fminf(a, b);
+    mx = fmaxf(a, b);
+    E = fmaf(fmaxf(fabsf(a), fabsf(b)), f.c2z, f.c1z);
+    tn_lo = fmaxf(tn_lo, mn - E);
+    tn_hi = fmaxf(tn_hi, mn + E);
+    tf_lo = fminf(tf_lo, mx - E);
+    tf_hi = fminf(tf_hi, mx + E);
+    /* an unbounded side gives NaN (inf - inf); fminf / fmaxf drop NaN operands, which leaves that side open */
 }
 
-struct CsgHitF {
-    float lo, hi; /* the crossing's t lies in [lo, hi] */
-    int leaf;
+/* The crossings of one operand (a leaf, or a closed CSG) as ONE interval: enter in [a_lo, a_hi], exit in [b_lo, b_hi],
+ * enter < exit for sure.  flags: 1 = present, 2 / 4 = the enter / exit surface casts shadows. */
+struct SpanF {
+    float a_lo, a_hi, b_lo, b_hi;
+    int flags;
 };
 
 /*
- * FP32 twin of trace_shadow (frt_device.cuh).  `wr` is the exact FP64 ray with an unnormalised direction (only read
- * for the rare FP64 leaf types), `w` / `Df` its normalised FP32 image; returns FRT_SH_LIT, FRT_SH_SHADOWED or FRT_SH_UNDECIDED.
+ * csg_filter_intersections (csg.c:43-71) for two operands that are one interval each.  Walking the merged, sorted
+ * crossings with the reference's inl / inr toggles gives, per ordering of the four ends:
+ *     union         disjoint -> both intervals (2 spans: undecided here)     otherwise -> [first enter, last exit]
+ *     intersection  disjoint -> nothing                                      otherwise -> [later enter, earlier exit]
+ *     difference    disjoint -> L     L inside R -> nothing     R inside L -> 2 spans (undecided)
+ *                   L enters first -> [L enter, R enter]        R enters first -> [R exit, L exit]
+ * Each end keeps the casts_shadow bit of the leaf it came from.  Returns false when an ordering is not decided or the
+ * result is two intervals.
+ */
+__device__ __forceinline__ bool
+csg_combine(int op, const SpanF &L, const SpanF &R, SpanF &out)
+{
+    out.flags = 0;
+    if (!(L.flags & 1)) {
+        if (op == FRT_CSG_UNION) {
+            out = R;
+        }
+        return true; /* intersection, difference: nothing survives without the left operand */
+    }
+    if (!(R.flags & 1)) {
+        if (op != FRT_CSG_INTERSECT) {
+            out = L;
+        }
+        return true;
+    }
+    if (L.b_hi < R.a_lo || R.b_hi < L.a_lo) { /* disjoint for sure */
+        if (op == FRT_CSG_DIFFERENCE) {
+            out = L;
+            return true;
+        }
+        return op == FRT_CSG_INTERSECT; /* intersection: empty; union: two spans */
+    }
+    if (!(L.a_hi < R.b_lo) || !(R.a_hi < L.b_lo)) {
+        return false; /* neither surely disjoint nor surely overlapping */
+    }
+    bool l_enters_first, l_exits_last;
+    if (L.a_hi < R.a_lo) {
+        l_enters_first = true;
+    } else if (R.a_hi < L.a_lo) {
+        l_enters_first = false;
+    } else {
+        return false;
+    }
+    if (R.b_hi < L.b_lo) {
+        l_exits_last = true;
+    } else if (L.b_hi < R.b_lo) {
+        l_exits_last = false;
+    } else {
+        return false;
+    }
+    const SpanF &first = l_enters_first ? L : R, &second = l_enters_first ? R : L;
+    const SpanF &last = l_exits_last ? L : R, &inner = l_exits_last ? R : L;
+    if (op == FRT_CSG_UNION) {
+        out.a_lo = first.a_lo;
+        out.a_hi = first.a_hi;
+        out.b_lo = last.b_lo;
+        out.b_hi = last.b_hi;
+        out.flags = 1 | (first.flags & 2) | (last.flags & 4);
+        return true;
+    }
+    if (op == FRT_CSG_INTERSECT) {
+        out.a_lo = second.a_lo;
+        out.a_hi = second.a_hi;
+        out.b_lo = inner.b_lo;
+        out.b_hi = inner.b_hi;
+        out.flags = 1 | (second.flags & 2) | (inner.flags & 4);
+        return true;
+    }
+    /* difference L - R */
+    if (l_enters_first && l_exits_last) {
+        return false; /* R strictly inside L: two spans */
+    }
+    if (!l_enters_first && !l_exits_last) {
+        return true; /* L inside R: nothing */
+    }
+    if (l_enters_first) { /* [L enter, R enter]: the exit surface is R's entry face */
+        out.a_lo = L.a_lo;
+        out.a_hi = L.a_hi;
+        out.b_lo = R.a_lo;
+        out.b_hi = R.a_hi;
+        out.flags = 1 | (L.flags & 2) | ((R.flags & 2) << 1);
+    } else { /* [R exit, L exit] */
+        out.a_lo = R.b_lo;
+        out.a_hi = R.b_hi;
+        out.b_lo = L.b_lo;
+        out.b_hi = L.b_hi;
+        out.flags = 1 | ((R.flags & 4) >> 1) | (L.flags & 4);
+    }
+    return true;
+}
+
+/*
+ * The reference's verdict on a crossing list that is one span (group.c:105-123, renderer.c:87-90):
+ *   the search stops here iff some t is not <= 0, i.e. iff exit > 0;
+ *   the point is shadowed iff some t > 0 on a casts_shadow surface is < distance.
+ * Returns 0 = does not stop (keep walking), 1 = stops, lit, 2 = stops, shadowed, 3 = undecided.
+ */
+__device__ __forceinline__ int
+judge_span(const SpanF &s, float D_lo, float D_hi)
+{
+    if (s.b_hi <= 0.0f) {
+        return 0;
+    }
+    if (!(s.b_lo > 0.0f)) {
+        return 3;
+    }
+    /* per end: 2 = surely a positive casting crossing nearer than the light, 0 = surely not, 1 = cannot tell */
+    int ea, eb;
+    if (!(s.flags & 2) || s.a_hi <= 0.0f || s.a_lo >= D_hi) {
+        ea = 0;
+    } else {
+        ea = (s.a_lo > 0.0f && s.a_hi < D_lo) ? 2 : 1;
+    }
+    if (!(s.flags & 4) || s.b_lo >= D_hi) {
+        eb = 0;
+    } else {
+        eb = (s.b_hi < D_lo) ? 2 : 1;
+    }
+    if (ea == 2 || eb == 2) {
+        return 2;
+    }
+    return (ea | eb) ? 3 : 1;
+}
+
+/* one cube or sphere leaf as a span; false = undecided */
+__device__ __forceinline__ bool
+leaf_span(int type, const float4 lo, const float4 hi, const FrameF &f, SpanF &s)
+{
+    s.flags = 0;
+    if (type == FRT_CUBE) { /* cube_local_intersect, cube.c:56-78 */
+        box_f(f, lo, hi, s.a_lo, s.a_hi, s.b_lo, s.b_hi);
+        if (s.a_lo > s.b_hi) {
+            return true; /* tmin > tmax for sure: no crossings */
+        }
+        if (!(s.a_hi < s.b_lo)) {
+            return false;
+        }
+        s.flags = 1;
+        return true;
+    }
+    /* sphere_local_intersect, sphere.c:14-40 */
+    const float So = fabsf(f.ox) + fabsf(f.oy) + fabsf(f.oz), Sd = fabsf(f.dx) + fabsf(f.dy) + fabsf(f.dz);
+    const float a = fmaf(f.dx, f.dx, fmaf(f.dy, f.dy, f.dz * f.dz));
+    const float hb = fmaf(f.dx, f.ox, fmaf(f.dy, f.oy, f.dz * f.oz));
+    const float habs = fmaf(fabsf(f.dx), fabsf(f.ox), fmaf(fabsf(f.dy), fabsf(f.oy), fabsf(f.dz * f.oz)));
+    const float oo = fmaf(f.ox, f.ox, fmaf(f.oy, f.oy, f.oz * f.oz));
+    const float b = 2.0f * hb, c = oo - 1.0f;
+    const float da = fmaf(2.0f * Sd + 3.0f * f.ed, f.ed, FRT_F32_G * a);
+    const float db = 2.0f * (fmaf(Sd, f.eo, fmaf(So, f.ed, 3.0f * f.eo * f.ed)) + FRT_F32_G * habs);
+    const float dc = fmaf(2.0f * So + 3.0f * f.eo, f.eo, FRT_F32_G * (oo + 1.0f));
+    const float disc = fmaf(b, b, -4.0f * a * c);
+    const float dD = fmaf(2.0f * fabsf(b) + db, db, 4.0f * (fmaf(a, dc, fmaf(fabsf(c), da, da * dc)))) +
+                     FRT_F32_G * fmaf(b, b, 4.0f * a * fabsf(c));
+    if (disc + dD < 0.0f) {
+        return true;
+    }
+    if (!(disc > 4.0f * dD) || !(a > 4.0f * da)) {
+        return false;
+    }
+    const float sq = sqrtf(disc);
+    const float ds = dD / sq + FRT_F32_G * sq;
+    const float i2a = rcpf_fast(2.0f * a);
+    const float ra = 2.0f * (da / a) + 2.0f * FRT_F32_G;
+    const float t0 = (-b - sq) * i2a, t1 = (-b + sq) * i2a;
+    const float E0 = (db + ds) * 2.0f * i2a;
+    const float e0 = fmaf(fabsf(t0), ra, E0), e1 = fmaf(fabsf(t1), ra, E0);
+    s.a_lo = t0 - e0;
+    s.a_hi = t0 + e0;
+    s.b_lo = t1 - e1;
+    s.b_hi = t1 + e1;
+    if (!(s.a_hi < s.b_lo)) {
+        return false;
+    }
+    s.flags = 1;
+    return true;
+}
+
+/*
+ * FP32 filter twin of trace_shadow (frt_device.cuh).  `w` is the world frame of the ray (frame_finish'ed by the
+ * caller), omax / eo_w / ed_w its error terms, [D_lo, D_hi] the interval of the light distance; `fnodes` is the
+ * node mirror (in shared memory when the tree is small).
+ * Returns FRT_SH_LIT, FRT_SH_SHADOWED or FRT_SH_UNDECIDED.
  */
 template <bool COUNT>
 __device__ __forceinline__ int
-trace_shadow_f32(const DScene &S, const DSceneF &SF, const Ray &wr, const RayF &w, float Df, int *overflow,
-                 unsigned long long *nodes_visited, unsigned long long *flops)
+trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF &w, float omax, float eo_w, float ed_w, float D_lo,
+                 float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
 {
-    struct Frame {
-        int right, skip, start, mid, op;
+    struct Frame { /* an open CSG node: its operator, where its right operand starts and ends, its left result */
+        int op, right, skip, have_left;
+        SpanF left;
     };
-    CsgHitF buf[FRT_CSG_CAP];
     Frame st[FRT_CSG_DEPTH];
-    int sp = 0, n = 0;
+    int sp = 0;
+    SpanF cur; /* result of the operand being evaluated (inside a CSG) */
+    cur.flags = 0;
+    cur.a_lo = cur.a_hi = cur.b_lo = cur.b_hi = 0.0f;
     unsigned int visited = 0, cost = 0;
-    const float omax = fmaxf(fmaxf(fabsf(w.ox), fabsf(w.oy)), fabsf(w.oz));
-    const float D_lo = Df - FRT_F32_G * Df, D_hi = Df + FRT_F32_G * Df; /* the light distance lies in [D_lo, D_hi] */
-    int result = FRT_SH_LIT;
+    int i = root;
+    const int end = __float_as_int(fnodes[3 * i].y);
+    int cur_xf = 0;
+    FrameF cf = w; /* the ray in the frame of transform cur_xf (0 = world) */
+    int verdict = FRT_SH_LIT;
 
-    for (int rt = 0; rt < S.n_roots; ++rt) {
-        int i = __ldg(S.roots + rt);
-        const int end = load_node_a(S, i).skip;
-        int cur_xf = 0;
-        LocalF L;
-        local_setup(L, SF, 0, w, omax);
-        bool any = false, done = false;
-        while (i < end) {
-            const NodeA a = load_node_a(S, i);
-            if (COUNT) ++visited;
-            if (a.xform != cur_xf) {
-                cur_xf = a.xform;
-                local_setup(L, SF, cur_xf, w, omax);
-                if (COUNT && cur_xf != 0) cost += FRT_COST_XFORM;
-            }
-            if (COUNT) cost += (a.type >= FRT_CSG) ? FRT_COST_BBOX : prim_cost(a.type);
-            if (a.type >= FRT_CSG) {
-                if (!bbox_maybe_f(SF, i, L)) {
-                    i = a.skip;
-                } else {
-                    if (a.type == FRT_CSG) {
-                        if (sp == FRT_CSG_DEPTH) {
-                            *overflow = 1;
-                            return FRT_SH_LIT;
-                        }
-                        const NodeB b = load_node_b(S, i);
-                        st[sp++] = Frame{ b.right, a.skip, n, -1, b.csg_op };
-                    }
-                    i = i + 1;
-                }
+    while (i < end) {
+        const float4 q0 = fnodes[3 * i], lo = fnodes[3 * i + 1], hi = fnodes[3 * i + 2];
+        const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y), xf = __float_as_int(q0.z);
+        const int type = flags & FRT_FN_TYPE_MASK;
+        if (COUNT) {
+            ++visited;
+            cost += (type >= FRT_CSG) ? FRT_COST_BBOX : prim_cost(type);
+        }
+        if (xf != cur_xf) { /* WORLD nodes carry xf = 0 */
+            cur_xf = xf;
+            if (xf == 0) {
+                cf = w;
             } else {
-                float tlo[4], thi[4];
-                const int k = prim_f(S, a.type, a.xform, load_node_b(S, i).param, L, wr, tlo, thi);
-                if (k < 0) {
-                    return FRT_SH_UNDECIDED;
-                }
-                if (sp == 0) {
-                    if (k > 0) {
-                        any = true;
-                        /* the search stops here iff some t is not <= 0 (group.c:105-123); shadowed iff the leaf casts
-                         * shadows and its smallest t > 0 is nearer than the light (renderer.c:87-90) */
-                        bool stop = false, amb = false, near_sure = false, far_amb = false;
-                        for (int j = 0; j < k; ++j) {
-                            if (tlo[j] > 0.0f) {
-                                stop = true;
-                                if (thi[j] < D_lo) {
-                                    near_sure = true;
-                                } else if (!(tlo[j] >= D_hi)) {
-                                    far_amb = true;
-                                }
-                            } else if (!(thi[j] <= 0.0f)) {
-                                amb = true; /* sign not decided (or NaN) */
-                            }
-                        }
-                        if (stop) {
-                            if (!S.mats[a.material].casts_shadow) {
-                                result = FRT_SH_LIT;
-                            } else if (near_sure) {
-                                result = FRT_SH_SHADOWED;
-                            } else if (!amb && !far_amb) {
-                                result = FRT_SH_LIT;
-                            } else {
-                                result = FRT_SH_UNDECIDED;
-                            }
-                            done = true;
-                        } else if (amb) {
-                            return FRT_SH_UNDECIDED;
-                        }
+                frame_local(cf, SF, xf, w, omax, eo_w, ed_w);
+                if (COUNT) cost += FRT_COST_XFORM;
+            }
+        }
+        if (type >= FRT_CSG) { /* group or CSG: conservative cull by its bounds */
+            bool miss = false;
+            if (!(flags & FRT_FN_NOCULL)) {
+                float tn_lo, tn_hi, tf_lo, tf_hi;
+                box_f(cf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                miss = tn_lo > tf_hi;
+            }
+            if (miss) {
+                i = skip;
+            } else {
+                if (type == FRT_CSG) {
+                    if (sp == FRT_CSG_DEPTH) {
+                        return FRT_SH_UNDECIDED;
                     }
-                } else {
-                    for (int j = 0; j < k; ++j) {
-                        if (n == FRT_CSG_CAP) {
-                            *overflow = 1;
-                            return FRT_SH_LIT;
-                        }
-                        buf[n].lo = tlo[j];
-                        buf[n].hi = thi[j];
-                        buf[n].leaf = i;
-                        ++n;
-                    }
+                    Frame &f = st[sp++];
+                    f.op = (flags >> FRT_FN_OP_SHIFT) & 3;
+                    f.right = __float_as_int(q0.w);
+                    f.skip = skip;
+                    f.have_left = 0;
+                    f.left = cur;
+                    f.left.flags = 0;
+                    cur.flags = 0;
+                } else if (sp > 0) {
+                    return FRT_SH_UNDECIDED; /* a group inside a CSG operand: several spans */
                 }
                 i = i + 1;
             }
-            /* close every CSG whose left / right operand just ended (csg.c:104-118, :43-71) */
-            while (sp > 0) {
-                Frame &f = st[sp - 1];
-                if (f.mid < 0 && i >= f.right) {
-                    f.mid = n;
+        } else {
+            if (!(flags & FRT_FN_FAST)) {
+                return FRT_SH_UNDECIDED;
+            }
+            SpanF s;
+            bool ok = true;
+            if (type == FRT_PLANE) { /* plane_local_intersect, plane.c:11-25: one crossing; stands alone or undecided */
+                if (sp > 0) {
+                    return FRT_SH_UNDECIDED;
                 }
-                if (i < f.skip) {
-                    break;
-                }
-                if (f.mid - f.start > 0 && n - f.mid > 0) {
-                    for (int x = f.start + 1; x < n; ++x) {
-                        const CsgHitF h = buf[x];
-                        int y = x - 1;
-                        while (y >= f.start) {
-                            if (buf[y].hi < h.lo) {
-                                break; /* surely in order */
-                            }
-                            if (!(buf[y].lo > h.hi)) {
-                                return FRT_SH_UNDECIDED; /* order of two crossings not decided in FP32 */
-                            }
-                            buf[y + 1] = buf[y];
-                            --y;
-                        }
-                        buf[y + 1] = h;
-                    }
-                }
-                bool inl = false, inr = false;
-                int out = f.start;
-                for (int x = f.start; x < n; ++x) {
-                    const bool lhit = buf[x].leaf < f.right;
-                    if (csg_allowed(f.op, lhit, inl, inr)) {
-                        buf[out++] = buf[x];
-                    }
-                    if (lhit) {
-                        inl = !inl;
-                    } else {
-                        inr = !inr;
-                    }
-                }
-                n = out;
-                --sp;
-                if (sp == 0) { /* the outermost CSG is judged like a leaf, with a material per crossing */
-                    bool stop = false, amb = false, near_sure = false, far_amb = false;
-                    for (int x = 0; x < n; ++x) {
-                        any = true;
-                        if (buf[x].lo > 0.0f) {
-                            stop = true;
-                            if (S.mats[load_node_a(S, buf[x].leaf).material].casts_shadow) {
-                                if (buf[x].hi < D_lo) {
-                                    near_sure = true;
-                                } else if (!(buf[x].lo >= D_hi)) {
-                                    far_amb = true;
-                                }
-                            }
-                        } else if (!(buf[x].hi <= 0.0f)) {
-                            amb = true;
-                        }
-                    }
-                    n = 0;
-                    if (stop) {
-                        if (near_sure) {
-                            result = FRT_SH_SHADOWED;
-                        } else if (!amb && !far_amb) {
-                            result = FRT_SH_LIT;
-                        } else {
-                            result = FRT_SH_UNDECIDED;
-                        }
-                        done = true;
-                    } else if (amb) {
+                const float tt = -cf.oy * cf.iy;
+                const float E = fmaf(fabsf(tt), cf.c2y, cf.c1y);
+                s.a_lo = s.b_lo = tt - E;
+                s.a_hi = s.b_hi = tt + E;
+                s.flags = 1;
+            } else {
+                ok = leaf_span(type, lo, hi, cf, s);
+            }
+            if (!ok) {
+                return FRT_SH_UNDECIDED;
+            }
+            if (s.flags && (flags & FRT_FN_CASTS)) {
+                s.flags |= 6;
+            }
+            if (sp == 0) {
+                if (s.flags) {
+                    const int v = judge_span(s, D_lo, D_hi);
+                    if (v == 3) {
                         return FRT_SH_UNDECIDED;
                     }
+                    if (v != 0) {
+                        verdict = (v == 2) ? FRT_SH_SHADOWED : FRT_SH_LIT;
+                        break;
+                    }
                 }
+            } else if (s.flags) {
+                if (cur.flags) {
+                    return FRT_SH_UNDECIDED; /* two spans in one operand */
+                }
+                cur = s;
             }
-            if (done) {
+            i = i + 1;
+        }
+        /* close every CSG whose left / right operand just ended */
+        bool stop = false;
+        while (sp > 0) {
+            Frame &f = st[sp - 1];
+            if (!f.have_left && i >= f.right) {
+                f.left = cur;
+                f.have_left = 1;
+                cur.flags = 0;
+            }
+            if (i < f.skip) {
                 break;
             }
+            SpanF res;
+            res.a_lo = res.a_hi = res.b_lo = res.b_hi = 0.0f;
+            if (!csg_combine(f.op, f.left, cur, res)) {
+                return FRT_SH_UNDECIDED;
+            }
+            --sp;
+            cur = res; /* becomes the enclosing CSG's current operand, or the list to judge */
+            if (sp == 0) { /* the outermost CSG is judged like a leaf */
+                cur.flags = 0;
+                if (res.flags) {
+                    const int v = judge_span(res, D_lo, D_hi);
+                    if (v == 3) {
+                        return FRT_SH_UNDECIDED;
+                    }
+                    if (v != 0) {
+                        verdict = (v == 2) ? FRT_SH_SHADOWED : FRT_SH_LIT;
+                        stop = true;
+                    }
+                }
+            }
         }
-        if (done || any) {
+        if (stop) {
             break;
         }
     }
@@ -416,5 +491,5 @@ trace_shadow_f32(const DScene &S, const DSceneF &SF, const Ray &wr, const RayF &
         *nodes_visited += visited;
         *flops += cost;
     }
-    return result;
+    return verdict;
 }
