@@ -215,11 +215,11 @@ def cuda_arm(args) -> dict:
         _, st_ref = sc.render(rank=rank, world=world, rows_per_block=rpb, flags=FRT_FLAG_NO_PRUNE | FRT_FLAG_COUNT_RAYS,
                               download=False, seed=1)
         _, st_cnt = sc.render(rank=rank, world=world, rows_per_block=rpb, flags=FRT_FLAG_COUNT_RAYS, download=False, seed=1)
-        counts = torch.tensor([st_ref.rays_total, st_cnt.rays_total, st_cnt.rays_shadow, st_cnt.light_flops, st_cnt.hits_shaded],
-                              dtype=torch.float64, device=dev)
+        counts = torch.tensor([st_ref.rays_total, st_cnt.rays_total, st_cnt.rays_shadow, st_cnt.light_flops, st_cnt.hits_shaded,
+                               st_cnt.shadow_deferred], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(counts)
-        ref_rays, traced_rays, shadow_rays, light_flops, hits = (float(x) for x in counts.tolist())
+        ref_rays, traced_rays, shadow_rays, light_flops, hits, deferred = (float(x) for x in counts.tolist())
 
         def step(seed):
             _, st = sc.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=seed)
@@ -303,7 +303,8 @@ def cuda_arm(args) -> dict:
         achieved = (light_flops / world) / (light_ms_per_step * 1e-3) / 1e12 if light_ms_per_step > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 geometry and pixel sums; shadow rays pre-decided by an f32 interval filter, f32 lighting sums",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "variant": args.variant, "hsize": hsize, "vsize": vsize, "spp": args.spp * args.spp,
                        "parallelism": f"rows/{world}" if world > 1 else "single", "rows_per_block": rpb,
@@ -317,14 +318,18 @@ def cuda_arm(args) -> dict:
                     "h2d_bytes_per_step": int(desc.host_bytes) * world, "d2h_bytes_per_step": vsize * hsize * 32,
                     "path": "frt_scene_create(host desc) + frt_render + canvas to pinned host memory, per step"},
             "gpu_launches": total_launches,
-            "roofline": {"bound": "fp64-issue", "kernel": "k_light", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-                         "peak_source": "register-resident FP64 FMA loop measured in this run (frt_measure_fma_peak); "
-                                        "MEASURED_PEAKS.json has no FP64/FP32 SIMT entry",
-                         "fp32_peak_tflops": fp32_peak,
+            "roofline": {"bound": "fp32-issue", "kernel": "k_shadow_f32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                         "peak_source": "register-resident FP32 FMA loop measured in this run (frt_measure_fma_peak); "
+                                        "MEASURED_PEAKS.json holds HBM and bf16-tensor peaks only and this kernel uses neither",
+                         "fp64_peak_tflops": fp64_peak,
                          "flop_per_launch": flops_per_launch, "launch_ms": launch_ms,
                          "kernel_share_of_step": light_ms_per_step / ms_per_step if ms_per_step else None,
-                         "shadow_rays_per_frame": shadow_rays, "hits_shaded_per_frame": hits},
+                         "shadow_rays_per_frame": shadow_rays, "hits_shaded_per_frame": hits,
+                         "shadow_rays_deferred_to_fp64": deferred,
+                         "note": "achieved = algorithmic flop (BASELINE.md section 4 cost table, counted event by event on "
+                                 "the device in an untimed counting frame) / CUDA-event time of the kernel's launches in the "
+                                 "timed frames"},
         }
     if world > 1:
         dist.barrier()

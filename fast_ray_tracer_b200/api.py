@@ -126,7 +126,7 @@ EXPORTS = [
     "frt_abi_version", "frt_abi_sizeof", "frt_last_error", "frt_device_count", "frt_canvas_device_ptr", "frt_scene_create", "frt_scene_destroy",
     "frt_render", "frt_canvas_download", "frt_owned_rows", "frt_photons_emit", "frt_photons_count",
     "frt_photons_export", "frt_photons_import", "frt_photons_finish", "frt_measure_fma_peak",
-    "frt_scene_save", "frt_scene_load", "frt_scene_desc_free",
+    "frt_scene_save", "frt_scene_load", "frt_scene_desc_free", "frt_trim",
 ]
 
 
@@ -148,6 +148,8 @@ def load_library():
     lib.frt_scene_create.argtypes = [C.POINTER(frt_scene_desc), C.c_int, C.POINTER(C.c_void_p)]
     lib.frt_scene_destroy.argtypes = [C.c_void_p]
     lib.frt_scene_destroy.restype = None
+    lib.frt_trim.argtypes = [C.c_int]
+    lib.frt_trim.restype = None
     lib.frt_render.argtypes = [C.c_void_p, C.POINTER(frt_render_cfg), C.c_void_p, C.POINTER(frt_stats)]
     lib.frt_canvas_download.argtypes = [C.c_void_p, C.c_void_p]
     lib.frt_canvas_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]

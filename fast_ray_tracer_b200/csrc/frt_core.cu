@@ -22,6 +22,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "frt_b200.h"
@@ -915,7 +917,7 @@ k_shadow_exact(DScene S, FrameParams F, const LightRec *__restrict__ recs, Light
     if (COUNT) {
         if (n_shadow) atomicAdd(&cnt->rays_shadow, n_shadow);
         if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
-        if (n_flops) atomicAdd(&cnt->light_flops, n_flops);
+        if (n_flops && ALL) atomicAdd(&cnt->light_flops, n_flops); /* light_flops describes the kernel that is timed */
     }
     if (!ALL && blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&cnt->deferred_total, total);
@@ -1055,6 +1057,80 @@ struct frt_scene {
     std::vector<void *> frame_allocs;
 };
 
+/*
+ * Frame buffers (ray queues, hit records, deferred-ray queue) do not depend on the scene, and allocating a few GB of
+ * them costs more than a frame.  When a scene is destroyed its set is parked per device and adopted by the next
+ * scene that needs no more capacity, so render_multi() called once per frame from a host loop pays for them once.
+ * frt_trim() frees the parked set.  (One frame at a time per device, like the reference's render_multi.)
+ */
+struct FrameSet {
+    unsigned int capacity = 0;
+    RayQ q[2]{};
+    HitQ hq{};
+    LightRec *recs = nullptr;
+    LightTmp *ltmp = nullptr;
+    unsigned long long *dq = nullptr;
+    unsigned int dq_cap = 0;
+    Counters *cnt = nullptr;
+    std::vector<void *> allocs;
+};
+static std::mutex g_park_mu;
+static std::map<int, FrameSet> g_parked;
+
+static void
+frameset_free(FrameSet &f)
+{
+    for (void *p : f.allocs) {
+        cudaFree(p);
+    }
+    f = FrameSet{};
+}
+
+static void
+scene_take(frt_scene *sc, FrameSet &f)
+{
+    sc->capacity = f.capacity;
+    sc->q[0] = f.q[0];
+    sc->q[1] = f.q[1];
+    sc->hq = f.hq;
+    sc->recs = f.recs;
+    sc->ltmp = f.ltmp;
+    sc->dq = f.dq;
+    sc->dq_cap = f.dq_cap;
+    sc->cnt = f.cnt;
+    sc->frame_allocs = std::move(f.allocs);
+    f = FrameSet{};
+}
+
+static void
+scene_give(frt_scene *sc, FrameSet &f)
+{
+    f.capacity = sc->capacity;
+    f.q[0] = sc->q[0];
+    f.q[1] = sc->q[1];
+    f.hq = sc->hq;
+    f.recs = sc->recs;
+    f.ltmp = sc->ltmp;
+    f.dq = sc->dq;
+    f.dq_cap = sc->dq_cap;
+    f.cnt = sc->cnt;
+    f.allocs = std::move(sc->frame_allocs);
+    sc->frame_allocs.clear();
+    sc->capacity = 0;
+}
+
+extern "C" void
+frt_trim(int device)
+{
+    std::lock_guard<std::mutex> lk(g_park_mu);
+    auto it = g_parked.find(device);
+    if (it != g_parked.end()) {
+        cudaSetDevice(device);
+        frameset_free(it->second);
+        g_parked.erase(it);
+    }
+}
+
 template <typename T>
 static int
 upload(frt_scene *sc, const T *src, size_t count, const T **dst)
@@ -1161,8 +1237,21 @@ frt_scene_destroy(frt_scene *sc)
     for (void *p : sc->allocs) {
         cudaFree(p);
     }
-    for (void *p : sc->frame_allocs) {
-        cudaFree(p);
+    if (sc->capacity > 0 && !sc->frame_allocs.empty()) {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        FrameSet &slot = g_parked[sc->device];
+        if (slot.capacity >= sc->capacity) {
+            for (void *p : sc->frame_allocs) {
+                cudaFree(p);
+            }
+        } else {
+            frameset_free(slot);
+            scene_give(sc, slot);
+        }
+    } else {
+        for (void *p : sc->frame_allocs) {
+            cudaFree(p);
+        }
     }
     for (auto &e : sc->ev) {
         if (e) cudaEventDestroy(e);
@@ -1466,6 +1555,19 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     }
     sc->frame_allocs.clear();
     sc->capacity = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        auto it = g_parked.find(sc->device);
+        if (it != g_parked.end()) {
+            if (it->second.capacity >= capacity) {
+                scene_take(sc, it->second);
+                g_parked.erase(it);
+                return FRT_OK;
+            }
+            frameset_free(it->second);
+            g_parked.erase(it);
+        }
+    }
 #define FA(p) do { int rc_ = frame_alloc(sc, &(p), capacity); if (rc_ != FRT_OK) return rc_; } while (0)
     for (int k = 0; k < 2; ++k) {
         RayQ &q = sc->q[k];
@@ -1675,6 +1777,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         } else {
                             k_shadow_exact<false, true><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         }
+                        CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         launches += 1;
                     } else {
                         const size_t f32_smem = (size_t)sc->S.n_nodes * 48 <= 32768 ? (size_t)sc->S.n_nodes * 48 : 0;
@@ -1686,6 +1789,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         } else {
                             k_shadow_f32<0><<<blocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         }
+                        CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         if (count) {
                             k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         } else {
@@ -1693,7 +1797,6 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         }
                         launches += 2;
                     }
-                    CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                     k_light_resolve<<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->canvas, sc->cnt, level, li);
                     launches += 2;
                     ++light_launches;

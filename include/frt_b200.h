@@ -216,7 +216,8 @@ typedef struct frt_render_cfg {
 
 typedef struct frt_stats {
     double frame_ms;         /* device time of the frame, CUDA events on the render stream */
-    double light_ms;         /* summed device time of the shadow-ray kernel (k_shadow, the dominant kernel) */
+    double light_ms;         /* summed device time of the FP32 shadow-ray kernel (k_shadow_f32, the dominant kernel;
+                                k_shadow_exact under FRT_FLAG_F64_SHADOW) */
     double upload_ms, download_ms;
     uint64_t rays_primary, rays_secondary, rays_shadow, rays_gather, rays_photon;
     uint64_t hits_shaded;
@@ -252,6 +253,9 @@ int frt_abi_sizeof(const char *struct_name);
 /* Upload a flattened scene (host pointers in desc are read during the call only). */
 int frt_scene_create(const frt_scene_desc *desc, int device, frt_scene **out);
 void frt_scene_destroy(frt_scene *scene);
+/* frt_scene_destroy parks the scene-independent frame buffers (ray queues) for the next scene on the same device;
+ * frt_trim frees them. */
+void frt_trim(int device);
 
 /*
  * Replaces render_multi()/render() (renderer.c:243/:283).  canvas_rgba has the layout of Canvas.arr
