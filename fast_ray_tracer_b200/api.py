@@ -165,6 +165,8 @@ def load_library():
     lib.frt_photons_count.restype = C.c_int64
     lib.frt_photons_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.frt_photons_import.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]
+    lib.frt_photons_emit.restype = C.c_int
+    lib.frt_photons_finish.restype = C.c_int
     lib.frt_photons_finish.argtypes = [C.c_void_p]
     if lib.frt_abi_version() != FRT_ABI_VERSION:
         raise FrtError(f"libfrt_b200.so has ABI {lib.frt_abi_version()}, the Python binding expects {FRT_ABI_VERSION}")
@@ -335,7 +337,61 @@ class Scene:
                             light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow, light_flops=st.light_flops, shadow_deferred=st.shadow_deferred,
                             shadow_mismatch=st.shadow_mismatch,
                             rows_rendered=st.rows_rendered)
+        stats.rays_gather = st.rays_gather
         return (out if download else None), stats
+
+    # ---- photon pass (replaces trace_photons, reference photon_tracer.c:203)
+
+    def photons_emit(self, rank: int = 0, world: int = 1, populate_caustic: bool = False, populate_global: bool = True,
+                     seed: int = 0) -> "RenderStats":
+        """Trace this rank's shard of the photons on the device (photon indices i * world + rank)."""
+        cfg = frt_photon_cfg(device=self.device, rank=rank, world=world, populate_caustic=int(populate_caustic),
+                             populate_global=int(populate_global), seed=seed)
+        st = frt_stats()
+        _check(load_library().frt_photons_emit(self._h, C.byref(cfg), C.byref(st)), "frt_photons_emit")
+        return RenderStats(extra={"rays_photon": int(st.rays_photon), "photons_stored": [int(x) for x in st.photons_stored]})
+
+    def photons_count(self, map_index: int) -> int:
+        return int(load_library().frt_photons_count(self._h, map_index))
+
+    def photons_export(self, map_index: int) -> np.ndarray:
+        """The map's photons as a float32 array [2, count, 4]: {x, y, z, direction bits} and {r, g, b, 0}."""
+        n = self.photons_count(map_index)
+        out = np.zeros((2, n, 4), dtype=np.float32)
+        _check(load_library().frt_photons_export(self._h, map_index, out.ctypes.data_as(C.c_void_p), 0), "frt_photons_export")
+        return out
+
+    def photons_export_tensor(self, map_index: int):
+        """Same, as a torch tensor on this scene's GPU (for NCCL all-gathers)."""
+        import torch
+
+        n = self.photons_count(map_index)
+        out = torch.zeros((2, n, 4), dtype=torch.float32, device=f"cuda:{self.device}")
+        _check(load_library().frt_photons_export(self._h, map_index, C.c_void_p(out.data_ptr()), 1), "frt_photons_export")
+        return out
+
+    def photons_import(self, map_index: int, records):
+        """Replace the map's photons by `records` ([2, count, 4] float32, numpy or a CUDA torch tensor)."""
+        if isinstance(records, np.ndarray):
+            rec = np.ascontiguousarray(records, dtype=np.float32)
+            assert rec.ndim == 3 and rec.shape[0] == 2 and rec.shape[2] == 4
+            _check(load_library().frt_photons_import(self._h, map_index, rec.ctypes.data_as(C.c_void_p), rec.shape[1], 0),
+                   "frt_photons_import")
+        else:
+            rec = records.contiguous()
+            assert rec.dim() == 3 and rec.shape[0] == 2 and rec.shape[2] == 4 and rec.is_cuda
+            _check(load_library().frt_photons_import(self._h, map_index, C.c_void_p(rec.data_ptr()), rec.shape[1], 1),
+                   "frt_photons_import")
+
+    def photons_finish(self):
+        """Scale the photon powers by 1 / photon_count and build the lookup grid (pm_scale_photon_power + pm_balance)."""
+        _check(load_library().frt_photons_finish(self._h), "frt_photons_finish")
+
+    def trace_photons(self, num_maps: int = 3, populate_caustic: bool = False, populate_global: bool = True, seed: int = 0):
+        """Mirror of `trace_photons(w, num_maps, populate_caustic_map, populate_global_map)` (photon_tracer.c:203)."""
+        st = self.photons_emit(0, 1, populate_caustic, populate_global, seed)
+        self.photons_finish()
+        return st
 
     def canvas_tensor(self):
         """The device-resident frame as a torch tensor view [vsize, hsize, 4] float64 (no copy)."""

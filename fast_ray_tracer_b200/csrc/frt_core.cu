@@ -116,7 +116,7 @@ struct Counters {
     unsigned int overflow_queue, overflow_csg;
     unsigned int n_deferred, pad;  /* shadow rays the FP32 pass left undecided in the current k_shadow_f32 launch */
     unsigned long long rays_secondary, rays_shadow, hits_shaded, shadow_nodes, light_flops;
-    unsigned long long deferred_total, f32_mismatch;
+    unsigned long long deferred_total, f32_mismatch, rays_gather;
 };
 
 struct DCamera {
@@ -134,6 +134,7 @@ struct FrameParams {
     int flags;
     int path_length;
     int include_direct, use_ambient, use_diffuse, use_spec_highlight, include_specular;
+    int use_gi; /* shade_hit's global-illumination block is live (renderer.c:737): ambient terms are resolved per hit */
     unsigned long long seed;
     unsigned int capacity; /* ray queue capacity */
 };
@@ -508,7 +509,7 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
             }
 
             /* ---- record for the light stage (direct illumination of this hit, weight = throughput * dissolve) */
-            if (F.include_direct && S.n_lights > 0) {
+            if ((F.include_direct && S.n_lights > 0) || F.use_gi) {
                 want_rec = true;
                 for (int k = 0; k < 3; ++k) {
                     rec.over[k] = over[k];
@@ -927,7 +928,7 @@ k_shadow_exact(DScene S, FrameParams F, const LightRec *__restrict__ recs, Light
 /* lighting_microfacet's closing arithmetic (renderer.c:904-979) and the weighting into the pixel */
 __global__ void __launch_bounds__(256)
 k_light_resolve(DScene S, FrameParams F, const LightRec *__restrict__ recs, const LightTmp *__restrict__ tmp,
-                double *__restrict__ canvas, const Counters *cnt, int level, int light_idx)
+                double *__restrict__ canvas, const Counters *cnt, int level, int light_idx, double *__restrict__ acc_amb)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
     const frt_light &L = S.lights[light_idx];
@@ -952,7 +953,11 @@ k_light_resolve(DScene S, FrameParams F, const LightRec *__restrict__ recs, cons
         }
         if (F.use_ambient) {
             for (int k = 0; k < 3; ++k) {
-                c[k] += R->Ka[k] * Li[k];
+                if (F.use_gi) {
+                    acc_amb[3 * (size_t)h + k] += R->Ka[k] * Li[k]; /* joins the GI terms before the clamp of renderer.c:765 */
+                } else {
+                    c[k] += R->Ka[k] * Li[k];
+                }
             }
         }
         double *px = canvas + 4 * (size_t)R->pixel;
@@ -964,6 +969,8 @@ k_light_resolve(DScene S, FrameParams F, const LightRec *__restrict__ recs, cons
         }
     }
 }
+
+#include "frt_gi.cuh"
 
 /* ------------------------------------------------------------------------------------------------ FMA peak */
 
@@ -1051,6 +1058,22 @@ struct frt_scene {
     unsigned long long *dq = nullptr; /* (hit, sample) items the FP32 shadow pass deferred to the FP64 pass */
     unsigned int dq_cap = 0;
     Counters *cnt = nullptr;
+    /* photon maps (0 = caustic, 1 = global) and the GI work buffers */
+    struct PMap {
+        float4 *ra = nullptr, *rb = nullptr; /* photons as stored / imported */
+        unsigned int cap = 0, count = 0;
+        float4 *sa = nullptr, *sb = nullptr; /* sorted by grid cell */
+        unsigned int *cell_start = nullptr;
+        PMView view{};
+        bool built = false;
+    } pm[2];
+    unsigned int *pm_stored = nullptr; /* device counters, one per map */
+    bool pm_ready = false;
+    GQuery *gq = nullptr;
+    unsigned int gq_cap = 0;
+    unsigned int *gq_n = nullptr;
+    double *acc_amb = nullptr, *acc_fg = nullptr;
+    unsigned int acc_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4]{};
     std::vector<cudaEvent_t> light_ev; /* start/stop pairs around every k_light launch of a frame (no host sync) */
@@ -1227,6 +1250,9 @@ cmj_table_no_jitter(int s0, int s1, std::vector<double> &arr)
     }
 }
 
+static void pm_free(frt_scene *sc);
+static int ensure_gi_buffers(frt_scene *sc);
+
 extern "C" void
 frt_scene_destroy(frt_scene *sc)
 {
@@ -1234,6 +1260,7 @@ frt_scene_destroy(frt_scene *sc)
         return;
     }
     cudaSetDevice(sc->device);
+    pm_free(sc);
     for (void *p : sc->allocs) {
         cudaFree(p);
     }
@@ -1703,6 +1730,34 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     F.use_spec_highlight = g.di_include_specular_highlight;
     F.include_specular = g.di_include_specular;
     F.seed = mix64(cfg->seed);
+    /* shade_hit's GI block (renderer.c:737): use_gi = include_global || visualize_photon_map (renderer.c:62) */
+    F.use_gi = (g.include_global || g.visualize_photon_map) ? 1 : 0;
+    GIParams G{};
+    if (F.use_gi) {
+        if (!sc->pm_ready) {
+            if (g.gi_photon_count <= 0) {
+                F.use_gi = 0; /* the generated main() skips photon tracing when photon_count is 0 (yaml_parser.py:201-215) */
+            } else {
+                return frt_set_error(FRT_ERR_ARG, "the scene asks for global illumination but no photon map was built: "
+                                                  "call frt_photons_emit() and frt_photons_finish() first");
+            }
+        }
+        G.usteps = g.gi_usteps > 0 ? g.gi_usteps : 1;
+        G.vsteps = g.gi_vsteps > 0 ? g.gi_vsteps : 1;
+        G.n_photons = g.gi_irradiance_estimate_num;
+        G.radius = (float)g.gi_irradiance_estimate_radius;
+        G.cone_k = (float)g.gi_irradiance_estimate_cone_filter_k;
+        G.visualize = g.visualize_photon_map;
+        G.use_caustics = g.gi_include_caustics;
+        G.use_final_gather = g.gi_include_final_gather;
+        G.seed = F.seed;
+        if (G.usteps * G.vsteps > FRT_MAX_SPP && G.usteps != G.vsteps) {
+            return frt_set_error(FRT_ERR_ARG, "a non-square final-gather grid supports at most %d cells", FRT_MAX_SPP);
+        }
+        if (G.n_photons <= 0 || G.n_photons > FRT_KNN_CAP / 2) {
+            return frt_set_error(FRT_ERR_ARG, "irradiance-estimate-num %d is outside 1..%d", G.n_photons, FRT_KNN_CAP / 2);
+        }
+    }
 
     const unsigned int spp = (unsigned int)(C.usteps * C.vsteps);
     const unsigned long long total = (unsigned long long)F.n_owned_rows * C.hsize * spp;
@@ -1717,6 +1772,12 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         return rc;
     }
     F.capacity = sc->capacity;
+    if (F.use_gi) {
+        rc = ensure_gi_buffers(sc);
+        if (rc != FRT_OK) {
+            return rc;
+        }
+    }
 
     cudaStream_t s = sc->stream;
     size_t cbytes = (size_t)C.hsize * C.vsize * 4 * sizeof(double);
@@ -1754,6 +1815,10 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, qi, sc->hq, sc->cnt, level, F.capacity);
             k_shade<<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
             launches += 2;
+            if (F.use_gi) {
+                CK(cudaMemsetAsync(sc->acc_amb, 0, sizeof(double) * 3 * (size_t)sc->acc_cap, s));
+                CK(cudaMemsetAsync(sc->acc_fg, 0, sizeof(double) * 3 * (size_t)sc->acc_cap, s));
+            }
             if (F.include_direct) {
                 for (int li = 0; li < sc->S.n_lights; ++li) {
                     if (sc->light_ev.size() < 2 * (size_t)(light_launches + 1)) {
@@ -1797,10 +1862,38 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         }
                         launches += 2;
                     }
-                    k_light_resolve<<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->canvas, sc->cnt, level, li);
+                    k_light_resolve<<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->canvas, sc->cnt, level, li, sc->acc_amb);
                     launches += 2;
                     ++light_launches;
                 }
+            }
+            if (F.use_gi) {
+                /* the GI block of shade_hit for the hits of this level, in batches that fit the request queue */
+                unsigned int n_hits = 0;
+                CK(cudaMemcpyAsync(&n_hits, &sc->cnt->n_hits[level], sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                n_hits = std::min(n_hits, F.capacity);
+                const unsigned int cells = (unsigned int)(G.usteps * G.vsteps);
+                const unsigned int per_hit = (G.use_final_gather ? cells : 0u) + (G.use_caustics ? 1u : 0u) + (G.visualize ? 1u : 0u);
+                const unsigned int batch = per_hit ? std::max(1u, sc->gq_cap / per_hit) : n_hits;
+                for (unsigned int first = 0; first < n_hits && per_hit; first += batch) {
+                    const unsigned int nb = std::min(batch, n_hits - first);
+                    CK(cudaMemsetAsync(sc->gq_n, 0, sizeof(unsigned int), s));
+                    if (G.use_caustics || G.visualize) {
+                        k_gi_points<<<sm_blocks * 4, 256, 0, s>>>(F, G, sc->recs, first, nb, sc->gq, sc->gq_n, sc->gq_cap, sc->cnt,
+                                                                  G.use_caustics, G.visualize);
+                        ++launches;
+                    }
+                    if (G.use_final_gather) {
+                        k_fg_trace<<<sm_blocks * 16, 128, 0, s>>>(sc->S, F, G, sc->recs, first, nb, sc->gq, sc->gq_n, sc->gq_cap, sc->cnt, level);
+                        ++launches;
+                    }
+                    k_knn<<<sm_blocks * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, sc->gq, sc->gq_n, sc->gq_cap,
+                                                                      sc->acc_amb, sc->acc_fg);
+                    ++launches;
+                }
+                k_gi_resolve<<<sm_blocks * 8, 256, 0, s>>>(F, G, sc->recs, sc->acc_amb, sc->acc_fg, sc->canvas, sc->cnt, level);
+                ++launches;
             }
         }
         Counters hc;
@@ -1815,6 +1908,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         totals.light_flops += hc.light_flops;
         totals.deferred_total += hc.deferred_total;
         totals.f32_mismatch += hc.f32_mismatch;
+        totals.rays_gather += hc.rays_gather;
         if (hc.overflow_queue) {
             break;
         }
@@ -1841,6 +1935,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         st->light_flops = totals.light_flops;
         st->shadow_deferred = totals.deferred_total;
         st->shadow_mismatch = totals.f32_mismatch;
+        st->rays_gather = totals.rays_gather;
         st->kernel_launches = launches;
         st->light_launches = light_launches;
         st->rows_rendered = F.n_owned_rows;
@@ -1929,28 +2024,323 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
 
 /* ------------------------------------------------------------------------------------------------ photons */
 
-extern "C" int
-frt_photons_emit(frt_scene *, const frt_photon_cfg *, frt_stats *)
+static double
+lab_lightness(const double rgb[3])
 {
-    return frt_set_error(FRT_ERR_ARG, "photon pass: not built yet in this revision");
+    /* rgb_to_lab's L* (src/color/rgb.c:58, xyz.c:31-56): Y row of the RGB->XYZ matrix over the D65 white's Y = 1 */
+    double y = 0.212671 * rgb[0] + 0.715160 * rgb[1] + 0.072169 * rgb[2];
+    return y > 0.008856 ? 116.0 * cbrt(y) - 16.0 : 903.3 * y;
 }
+
+static int
+pm_reserve(frt_scene *sc, int map, unsigned int cap)
+{
+    frt_scene::PMap &m = sc->pm[map];
+    if (m.cap >= cap) {
+        return FRT_OK;
+    }
+    float4 *na = nullptr, *nb = nullptr;
+    CK(cudaMalloc(&na, sizeof(float4) * (size_t)cap));
+    CK(cudaMalloc(&nb, sizeof(float4) * (size_t)cap));
+    if (m.count) {
+        CK(cudaMemcpy(na, m.ra, sizeof(float4) * (size_t)m.count, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(nb, m.rb, sizeof(float4) * (size_t)m.count, cudaMemcpyDeviceToDevice));
+    }
+    cudaFree(m.ra);
+    cudaFree(m.rb);
+    m.ra = na;
+    m.rb = nb;
+    m.cap = cap;
+    return FRT_OK;
+}
+
+static void
+pm_free(frt_scene *sc)
+{
+    for (auto &m : sc->pm) {
+        cudaFree(m.ra);
+        cudaFree(m.rb);
+        cudaFree(m.sa);
+        cudaFree(m.sb);
+        cudaFree(m.cell_start);
+        m = frt_scene::PMap{};
+    }
+    cudaFree(sc->pm_stored);
+    cudaFree(sc->gq);
+    cudaFree(sc->gq_n);
+    cudaFree(sc->acc_amb);
+    cudaFree(sc->acc_fg);
+    sc->pm_stored = nullptr;
+    sc->gq = nullptr;
+    sc->gq_n = nullptr;
+    sc->acc_amb = sc->acc_fg = nullptr;
+    sc->gq_cap = sc->acc_cap = 0;
+    sc->pm_ready = false;
+}
+
+static int
+ensure_gi_buffers(frt_scene *sc)
+{
+    if (sc->acc_cap < sc->capacity) {
+        cudaFree(sc->acc_amb);
+        cudaFree(sc->acc_fg);
+        sc->acc_amb = sc->acc_fg = nullptr;
+        CK(cudaMalloc(&sc->acc_amb, sizeof(double) * 3 * (size_t)sc->capacity));
+        CK(cudaMalloc(&sc->acc_fg, sizeof(double) * 3 * (size_t)sc->capacity));
+        sc->acc_cap = sc->capacity;
+    }
+    if (sc->gq == nullptr) {
+        unsigned int cap = 32u << 20; /* 32 Mi requests of 40 bytes */
+        const char *env = getenv("FRT_GI_QUEUE");
+        if (env != nullptr && *env) {
+            cap = (unsigned int)std::max(4096L, atol(env));
+        }
+        CK(cudaMalloc(&sc->gq, sizeof(GQuery) * (size_t)cap));
+        CK(cudaMalloc(&sc->gq_n, sizeof(unsigned int)));
+        sc->gq_cap = cap;
+    }
+    return FRT_OK;
+}
+
+/*
+ * trace_photons (photon_tracer.c:203-257) for this rank's shard.  Per light, the reference emits photons until the
+ * light's quota (photon_count * L*(intensity) / sum L*) has been STORED (j += hit, :231-247); here the quota is
+ * divided by `world`, photons are emitted in rounds sized from the measured stores-per-photon, and the rank's photon
+ * indices are i * world + rank so that the shards are disjoint streams.
+ */
+extern "C" int
+frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
+{
+    if (sc == nullptr || cfg == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_photons_emit: null argument");
+    }
+    CK(cudaSetDevice(sc->device));
+    const frt_config &g = sc->cfg;
+    const int world = cfg->world > 0 ? cfg->world : 1;
+    if (cfg->rank < 0 || cfg->rank >= world) {
+        return frt_set_error(FRT_ERR_ARG, "frt_photons_emit: rank %d of world %d", cfg->rank, world);
+    }
+    if (g.gi_photon_count <= 0 || sc->S.n_lights <= 0) {
+        return frt_set_error(FRT_ERR_ARG, "frt_photons_emit: photon_count is %lld and the scene has %d lights",
+                             (long long)g.gi_photon_count, sc->S.n_lights);
+    }
+    if (g.gi_path_length < 0 || g.gi_path_length > 64) {
+        return frt_set_error(FRT_ERR_ARG, "gi.path_length %d is outside 0..64", g.gi_path_length);
+    }
+    std::vector<frt_light> hl(sc->S.n_lights);
+    CK(cudaMemcpy(hl.data(), sc->S.lights, sizeof(frt_light) * hl.size(), cudaMemcpyDeviceToHost));
+    double total_l = 0.0;
+    for (auto &l : hl) {
+        total_l += lab_lightness(l.intensity);
+    }
+    if (sc->pm_stored == nullptr) {
+        CK(cudaMalloc(&sc->pm_stored, 2 * sizeof(unsigned int)));
+    }
+    if (sc->cnt == nullptr) {
+        int rc0 = ensure_frame_buffers(sc, 1024);
+        if (rc0 != FRT_OK) return rc0;
+    }
+    CK(cudaMemset(sc->cnt, 0, sizeof(Counters)));
+    unsigned long long emitted_total = 0;
+    for (int map = 0; map < 2; ++map) {
+        const bool want = map == 0 ? cfg->populate_caustic != 0 : cfg->populate_global != 0;
+        frt_scene::PMap &m = sc->pm[map];
+        m.count = 0;
+        m.built = false;
+        if (!want) {
+            continue;
+        }
+        /* capacity: this rank's share of every light's quota + the overshoot of one path */
+        const unsigned long long share = ((unsigned long long)g.gi_photon_count + world - 1) / world;
+        int rc = pm_reserve(sc, map, (unsigned int)std::min<unsigned long long>(share + 64 + (unsigned long long)g.gi_path_length, 0x7ffffff0ull));
+        if (rc != FRT_OK) {
+            return rc;
+        }
+        CK(cudaMemset(sc->pm_stored + map, 0, sizeof(unsigned int)));
+        unsigned long long target = 0; /* cumulative stored-photon target over the lights */
+        for (int li = 0; li < sc->S.n_lights; ++li) {
+            const unsigned long long quota = (unsigned long long)((double)g.gi_photon_count * lab_lightness(hl[li].intensity) / total_l);
+            target += (quota + world - 1) / world;
+            unsigned long long first = 0, emitted = 0;
+            unsigned int stored = 0, before = 0;
+            CK(cudaMemcpy(&before, sc->pm_stored + map, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+            stored = before;
+            for (int round = 0; round < 256 && stored < target; ++round) {
+                unsigned long long need = target - stored, n;
+                if (emitted == 0) {
+                    n = std::max<unsigned long long>(need / 8, 4096);
+                } else if (stored == before) {
+                    if (emitted > 64ull * (target + 4096)) {
+                        break; /* nothing stores (e.g. a caustic map in a scene without specular surfaces): the reference
+                                  would loop forever here (photon_tracer.c:231-238) */
+                    }
+                    n = emitted * 2;
+                } else {
+                    double yield = (double)(stored - before) / (double)emitted;
+                    n = (unsigned long long)((double)need / yield * 1.02) + 256;
+                }
+                PhotonParams P{};
+                P.light = li;
+                P.map_type = map;
+                P.path_length = g.gi_path_length;
+                P.rank = cfg->rank;
+                P.world = world;
+                P.first = first;
+                P.count = n;
+                P.seed = mix64(cfg->seed ^ 0x70686f746f6e73ull);
+                const int blocks = (int)std::min<unsigned long long>((n + 127) / 128, 148ull * 16);
+                k_photon_trace<<<blocks, 128, 0, sc->stream>>>(sc->S, P, m.ra, m.rb, sc->pm_stored + map, m.cap, sc->cnt);
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(&stored, sc->pm_stored + map, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->stream));
+                CK(cudaStreamSynchronize(sc->stream));
+                first += n;
+                emitted += n;
+            }
+            emitted_total += emitted;
+            /* photons past the cumulative target are dropped (the reference overshoots by less than one path) */
+            unsigned int keep = (unsigned int)std::min<unsigned long long>(std::min<unsigned long long>(stored, target + (unsigned long long)g.gi_path_length), m.cap);
+            CK(cudaMemcpy(sc->pm_stored + map, &keep, sizeof(unsigned int), cudaMemcpyHostToDevice));
+            m.count = keep;
+        }
+    }
+    Counters hc;
+    CK(cudaMemcpy(&hc, sc->cnt, sizeof(Counters), cudaMemcpyDeviceToHost));
+    if (hc.overflow_csg) {
+        return frt_set_error(FRT_ERR_OVERFLOW, "a photon met more than %d CSG crossings", FRT_CSG_CAP);
+    }
+    sc->pm_ready = false;
+    if (stats != nullptr) {
+        stats->rays_photon = emitted_total;
+        stats->photons_stored[0] = sc->pm[0].count;
+        stats->photons_stored[1] = sc->pm[1].count;
+        stats->photons_stored[2] = 0;
+    }
+    return FRT_OK;
+}
+
 extern "C" int64_t
-frt_photons_count(frt_scene *, int)
+frt_photons_count(frt_scene *sc, int map)
 {
-    return 0;
+    if (sc == nullptr || map < 0 || map > 1) {
+        return 0;
+    }
+    return (int64_t)sc->pm[map].count;
 }
+
+/* Layout of an exported map: count records of {x, y, z, dir bits} followed by count records of {r, g, b, 0} (32 B per photon). */
 extern "C" int
-frt_photons_export(frt_scene *, int, void *, int)
+frt_photons_export(frt_scene *sc, int map, void *dst, int dst_is_device)
 {
-    return frt_set_error(FRT_ERR_ARG, "photon pass: not built yet in this revision");
+    if (sc == nullptr || map < 0 || map > 1 || dst == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_photons_export: bad argument");
+    }
+    CK(cudaSetDevice(sc->device));
+    const frt_scene::PMap &m = sc->pm[map];
+    const size_t bytes = sizeof(float4) * (size_t)m.count;
+    const cudaMemcpyKind kind = dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (m.count) {
+        CK(cudaMemcpy(dst, m.ra, bytes, kind));
+        CK(cudaMemcpy((char *)dst + bytes, m.rb, bytes, kind));
+    }
+    return FRT_OK;
 }
+
+/* Replaces the map's photons by `count` records in the export layout (e.g. the all-gathered shards of every rank). */
 extern "C" int
-frt_photons_import(frt_scene *, int, const void *, int64_t, int)
+frt_photons_import(frt_scene *sc, int map, const void *src, int64_t count, int src_is_device)
 {
-    return frt_set_error(FRT_ERR_ARG, "photon pass: not built yet in this revision");
+    if (sc == nullptr || map < 0 || map > 1 || count < 0 || count > 0x7ffffff0ll || (count > 0 && src == nullptr)) {
+        return frt_set_error(FRT_ERR_ARG, "frt_photons_import: bad argument");
+    }
+    CK(cudaSetDevice(sc->device));
+    frt_scene::PMap &m = sc->pm[map];
+    m.count = 0;
+    m.built = false;
+    sc->pm_ready = false;
+    int rc = pm_reserve(sc, map, (unsigned int)std::max<int64_t>(count, 1));
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    const size_t bytes = sizeof(float4) * (size_t)count;
+    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (count) {
+        CK(cudaMemcpy(m.ra, src, bytes, kind));
+        CK(cudaMemcpy(m.rb, (const char *)src + bytes, bytes, kind));
+    }
+    m.count = (unsigned int)count;
+    return FRT_OK;
 }
+
+/* pm_scale_photon_power + pm_balance (photon_tracer.c:251-256): scale by 1 / photon_count, bin into the grid */
 extern "C" int
-frt_photons_finish(frt_scene *)
+frt_photons_finish(frt_scene *sc)
 {
-    return frt_set_error(FRT_ERR_ARG, "photon pass: not built yet in this revision");
+    if (sc == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_photons_finish: null scene");
+    }
+    CK(cudaSetDevice(sc->device));
+    const frt_config &g = sc->cfg;
+    const float scale = (float)(1.0 / (double)std::max<int64_t>(g.gi_photon_count, 1));
+    const float radius = (float)g.gi_irradiance_estimate_radius;
+    if (!(radius > 0.f)) {
+        return frt_set_error(FRT_ERR_ARG, "irradiance-estimate-radius must be positive");
+    }
+    for (int map = 0; map < 2; ++map) {
+        frt_scene::PMap &m = sc->pm[map];
+        cudaFree(m.sa);
+        cudaFree(m.sb);
+        cudaFree(m.cell_start);
+        m.sa = m.sb = nullptr;
+        m.cell_start = nullptr;
+        m.view = PMView{};
+        m.built = true;
+        if (m.count == 0) {
+            continue;
+        }
+        unsigned int hb[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
+        unsigned int *db = nullptr;
+        CK(cudaMalloc(&db, sizeof(hb)));
+        CK(cudaMemcpy(db, hb, sizeof(hb), cudaMemcpyHostToDevice));
+        k_pm_scale_bounds<<<148 * 4, 256, 0, sc->stream>>>(m.ra, m.rb, m.count, scale, db);
+        CK(cudaMemcpyAsync(hb, db, sizeof(hb), cudaMemcpyDeviceToHost, sc->stream));
+        CK(cudaStreamSynchronize(sc->stream));
+        cudaFree(db);
+        float lo[3], hi[3], ext = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = float_unorder(hb[k]);
+            hi[k] = float_unorder(hb[3 + k]);
+            ext = std::max(ext, hi[k] - lo[k]);
+        }
+        const float cell = std::max(radius, ext / 256.0f);
+        PMView V{};
+        V.gx = lo[0];
+        V.gy = lo[1];
+        V.gz = lo[2];
+        V.inv_cell = 1.0f / cell;
+        V.nx = std::max(1, (int)floorf((hi[0] - lo[0]) / cell) + 1);
+        V.ny = std::max(1, (int)floorf((hi[1] - lo[1]) / cell) + 1);
+        V.nz = std::max(1, (int)floorf((hi[2] - lo[2]) / cell) + 1);
+        V.count = m.count;
+        const size_t n_cells = (size_t)V.nx * V.ny * V.nz;
+        unsigned int *counts = nullptr;
+        CK(cudaMalloc(&counts, sizeof(unsigned int) * n_cells));
+        CK(cudaMalloc(&m.cell_start, sizeof(unsigned int) * (n_cells + 1)));
+        CK(cudaMalloc(&m.sa, sizeof(float4) * (size_t)m.count));
+        CK(cudaMalloc(&m.sb, sizeof(float4) * (size_t)m.count));
+        CK(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * n_cells, sc->stream));
+        k_pm_count<<<148 * 4, 256, 0, sc->stream>>>(V, m.ra, m.count, counts);
+        k_pm_scan<<<1, 1024, 0, sc->stream>>>(counts, m.cell_start, (unsigned int)n_cells);
+        /* counts becomes the per-cell write cursor */
+        CK(cudaMemcpyAsync(counts, m.cell_start, sizeof(unsigned int) * n_cells, cudaMemcpyDeviceToDevice, sc->stream));
+        k_pm_scatter<<<148 * 4, 256, 0, sc->stream>>>(V, m.ra, m.rb, m.count, counts, m.sa, m.sb);
+        CK(cudaStreamSynchronize(sc->stream));
+        CK(cudaGetLastError());
+        cudaFree(counts);
+        V.a = m.sa;
+        V.b = m.sb;
+        V.cell_start = m.cell_start;
+        m.view = V;
+    }
+    sc->pm_ready = true;
+    return FRT_OK;
 }

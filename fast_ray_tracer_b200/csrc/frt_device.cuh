@@ -628,8 +628,9 @@ struct Hit {
  * every leaf whose ancestors' bounding boxes the ray meets.  Order of visit is irrelevant for the minimum; ties
  * at equal t (glibc qsort order in the reference) resolve to the first leaf in tree order.
  */
+template <bool CASTERS>
 __device__ __forceinline__ Hit
-trace_closest(const DScene &S, const Ray &wr, int *overflow)
+trace_closest_t(const DScene &S, const Ray &wr, int *overflow)
 {
     Hit best;
     best.t = CUDART_INF;
@@ -653,7 +654,8 @@ trace_closest(const DScene &S, const Ray &wr, int *overflow)
                 if (bbox_hit(S, i, lr)) {
                     int n = csg_eval(S, i, wr, buf, overflow);
                     for (int k = 0; k < n; ++k) {
-                        if (buf[k].t > 0 && buf[k].t < best.t) {
+                        if (buf[k].t > 0 && buf[k].t < best.t &&
+                            (!CASTERS || S.mats[load_node_a(S, buf[k].leaf).material].casts_shadow)) {
                             best.t = buf[k].t;
                             best.leaf = buf[k].leaf;
                             best.u = best.v = -1.0;
@@ -666,6 +668,9 @@ trace_closest(const DScene &S, const Ray &wr, int *overflow)
                 double t[4], uv[2];
                 uv[0] = uv[1] = -1.0;
                 int k = prim_intersect(a.type, S.params + (b.param < 0 ? 0 : b.param), lr, t, uv);
+                if (CASTERS && !S.mats[a.material].casts_shadow) {
+                    k = 0; /* hit(xs, true) skips objects that do not cast shadows (intersection.c:42-54) */
+                }
                 for (int j = 0; j < k; ++j) {
                     if (t[j] > 0 && t[j] < best.t) {
                         best.t = t[j];
@@ -679,6 +684,12 @@ trace_closest(const DScene &S, const Ray &wr, int *overflow)
         }
     }
     return best;
+}
+
+__device__ __forceinline__ Hit
+trace_closest(const DScene &S, const Ray &wr, int *overflow)
+{
+    return trace_closest_t<false>(S, wr, overflow);
 }
 
 /* ---- fast FP64 reciprocal / reciprocal square root: MUFU seed + Newton steps, no slow-path branch.  Results are

@@ -1,0 +1,800 @@
+/*
+ * frt_gi.cuh -- photon pass, photon map and the global-illumination terms of shade_hit.
+ * Included by frt_core.cu after the light stage (uses its RNG, queues and LightRec).
+ *
+ *   k_photon_trace     trace_photons' emission loop + power_at / photon_hit with     photon_tracer.c:114-257,
+ *                      Russian roulette, storing into the caustic / global map        light.c:14-98, pm.c:261
+ *   k_pm_bounds/_count/_scan/_scatter   replace pm_balance (pm.c:329): photons are binned into a uniform grid
+ *                      of cell size >= the estimate radius, sorted by cell
+ *   k_fg_trace         final_gather + color_at_gi: one thread per (hit, CMJ cell)    renderer.c:647, :319
+ *   k_gi_points        lighting_caustics / lighting_gi (visualize) query per hit     renderer.c:829, :862
+ *   k_knn              pm_irradiance_estimate + pm_locate_photons: one WARP per      pm.c:91-252
+ *                      query gathers the photons of the 27 neighbouring cells, selects the n nearest by a
+ *                      bit-wise bisection over the squared distances held in shared memory, and sums them
+ *   k_gi_resolve       the ambient-slot sum and its sqrt(3) clamp                    renderer.c:755-770
+ *
+ * Why a grid and not Jensen's left-balanced kd-tree: the estimate depends only on the SET of the n nearest
+ * photons within max_dist (and the distance of the farthest one), not on the structure that finds it.  With a fixed
+ * search radius a grid of that cell size touches 27 cells; cells are contiguous photon ranges, so a warp streams
+ * them with coalesced 16-byte loads instead of chasing a tree one photon at a time.
+ *
+ * Photon record (32 bytes, two float4): {x, y, z, theta | phi << 8} {power r, g, b, 0} -- theta / phi are Jensen's
+ * 8-bit direction (pm.c:286-300).
+ */
+#pragma once
+
+#define FRT_KNN_WARPS 4
+#define FRT_KNN_CAP 1024
+
+struct PMView { /* one photon map as the kernels see it */
+    const float4 *a, *b;            /* sorted by cell */
+    const unsigned int *cell_start; /* n_cells + 1 */
+    float gx, gy, gz, inv_cell;
+    int nx, ny, nz;
+    unsigned int count;
+};
+
+struct GQuery { /* one radiance-estimate request */
+    float x, y, z;       /* position */
+    float ex, ey, ez;    /* the vector the reference passes as "normal" (the eye vector, renderer.c:842, :875) */
+    float wr, wg, wb;    /* weight applied to the scaled estimate */
+    unsigned int target; /* hit index; bit 31: accumulate into the final-gather sum, else into the ambient sum; bit 30: caustic map */
+};
+
+struct GIParams {
+    int usteps, vsteps;      /* final gather grid */
+    int n_photons;           /* irradiance_estimate_num */
+    float radius, cone_k;
+    int visualize;
+    int use_caustics, use_final_gather;
+    unsigned long long seed;
+};
+
+/* ------------------------------------------------------------------------------------------------ sampling */
+
+/* create_coordinate_system, sampler.c:67-85 */
+__device__ __forceinline__ void
+coordinate_system(const double n[3], double nt[3], double nb[3])
+{
+    double t0, t1, t2;
+    if (fabs(n[0]) > fabs(n[1])) {
+        double s = sqrt(n[0] * n[0] + n[2] * n[2]);
+        t0 = n[2] * s;
+        t1 = 0.0;
+        t2 = -n[0] * s;
+    } else {
+        double s = sqrt(n[1] * n[1] + n[2] * n[2]);
+        t0 = 0.0;
+        t1 = -n[2] * s;
+        t2 = n[1] * s;
+    }
+    double inv = -1.0 / sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+    nt[0] = t0 * inv;
+    nt[1] = t1 * inv;
+    nt[2] = t2 * inv;
+    nb[0] = n[1] * nt[2] - n[2] * nt[1];
+    nb[1] = n[2] * nt[0] - n[0] * nt[2];
+    nb[2] = n[0] * nt[1] - n[1] * nt[0];
+}
+
+/* sampler_hemisphere with cosine weighting (sampler.c:40-64, :88-114) */
+__device__ __forceinline__ void
+cosine_hemisphere(const double n[3], double r1, double r2, double out[3])
+{
+    double nt[3], nb[3];
+    coordinate_system(n, nt, nb);
+    double r = sqrt(r2);
+    double sn, cs;
+    sincospi(2.0 * r1, &sn, &cs);
+    double v0 = r * cs, v2 = r * sn, v1 = sqrt(fmax(0.0, 1.0 - r2));
+    double inv = 1.0 / sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+    v0 *= inv;
+    v1 *= inv;
+    v2 *= inv;
+    double x = v0 * nb[0] + v1 * n[0] + v2 * nt[0];
+    double y = v0 * nb[1] + v1 * n[1] + v2 * nt[1];
+    double z = v0 * nb[2] + v1 * n[2] + v2 * nt[2];
+    inv = 1.0 / sqrt(x * x + y * y + z * z);
+    out[0] = x * inv;
+    out[1] = y * inv;
+    out[2] = z * inv;
+}
+
+/*
+ * Entry [qu, qv] of a jittered s x s correlated-multi-jitter table (sampler_reset_2d, sampler.c:415-470) without
+ * building the table: the two shuffles are row / column permutations, replayed on a packed index array.
+ * Draw numbering follows the reference's order: 2 s^2 canonical jitters, s row picks, s column picks.
+ */
+__device__ __forceinline__ void
+cmj_entry_square(int s, unsigned long long key, int qu, int qv, double &x, double &y)
+{
+    const unsigned int base = 2u * s * s;
+    unsigned long long perm = 0xfedcba9876543210ull; /* nibble v = row now sitting at position v */
+    for (int j = 0; j < s; ++j) {
+        int k = (int)(j + u01(mix64(key + base + j)) * (s - j));
+        unsigned long long a = (perm >> (4 * j)) & 15ull, b = (perm >> (4 * k)) & 15ull;
+        perm &= ~((15ull << (4 * j)) | (15ull << (4 * k)));
+        perm |= (b << (4 * j)) | (a << (4 * k));
+    }
+    const int rp = (int)((perm >> (4 * qv)) & 15ull);
+    perm = 0xfedcba9876543210ull;
+    for (int i = 0; i < s; ++i) {
+        int k = (int)(i + u01(mix64(key + base + s + i)) * (s - i));
+        unsigned long long a = (perm >> (4 * i)) & 15ull, b = (perm >> (4 * k)) & 15ull;
+        perm &= ~((15ull << (4 * i)) | (15ull << (4 * k)));
+        perm |= (b << (4 * i)) | (a << (4 * k));
+    }
+    const int cp = (int)((perm >> (4 * qu)) & 15ull);
+    /* canonical entries: arr[2 (j s + i)] = (i + (j + xi) / s) / s, arr[.. + 1] = (j + (i + xi) / s) / s */
+    const double xi_x = u01(mix64(key + 2u * (rp * s + qu)));
+    const double xi_y = u01(mix64(key + 2u * (qv * s + cp) + 1u));
+    x = (qu + (rp + xi_x) / (double)s) / (double)s;
+    y = (qv + (cp + xi_y) / (double)s) / (double)s;
+}
+
+/* ------------------------------------------------------------------------------------------------ surface */
+
+struct SurfaceG { /* the part of prepare_computations (renderer.c:368-495) the GI paths need */
+    double p[3], n[3], eye[3], over[3], under[3], reflv[3];
+    double Kd[3];
+    int material;
+};
+
+__device__ __forceinline__ void
+surface_at(const DScene &S, const Ray &r, const Hit &h, SurfaceG &g)
+{
+    const NodeA a = load_node_a(S, h.leaf);
+    const NodeB b = load_node_b(S, h.leaf);
+    const frt_material &M = S.mats[a.material];
+    const double *prm = S.params + (b.param < 0 ? 0 : b.param);
+    g.material = a.material;
+    g.p[0] = r.ox + r.dx * h.t;
+    g.p[1] = r.oy + r.dy * h.t;
+    g.p[2] = r.oz + r.dz * h.t;
+    double lp[3], ln[3];
+    point_to_local(S, a.xform, g.p, lp);
+    local_normal(a.type, prm, lp, h.u, h.v, ln);
+    normal_to_world(S, a.xform, ln, g.n);
+    if (M.map_bump >= 0) {
+        double tex[3];
+        pattern_at_shape(S, M.map_bump, h.leaf, g.p, NULL, tex, 0);
+        g.n[0] += 2.0 * tex[0] - 1.0;
+        g.n[1] += 2.0 * tex[1] - 1.0;
+        g.n[2] += 2.0 * tex[2] - 1.0;
+    }
+    double inv = 1.0 / sqrt(g.n[0] * g.n[0] + g.n[1] * g.n[1] + g.n[2] * g.n[2]);
+    g.eye[0] = -r.dx;
+    g.eye[1] = -r.dy;
+    g.eye[2] = -r.dz;
+    double s = (g.n[0] * g.eye[0] + g.n[1] * g.eye[1] + g.n[2] * g.eye[2]) < 0 ? -inv : inv; /* inside flip */
+    double ddot = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        g.n[k] *= s;
+    }
+    ddot = 2 * (r.dx * g.n[0] + r.dy * g.n[1] + r.dz * g.n[2]);
+    g.reflv[0] = r.dx - g.n[0] * ddot;
+    g.reflv[1] = r.dy - g.n[1] * ddot;
+    g.reflv[2] = r.dz - g.n[2] * ddot;
+    for (int k = 0; k < 3; ++k) {
+        g.over[k] = g.p[k] + g.n[k] * FRT_EPS;
+        g.under[k] = g.p[k] - g.n[k] * FRT_EPS;
+    }
+    material_color(S, M.map_Kd, M.Kd, h.leaf, g.over, g.Kd);
+}
+
+/* ------------------------------------------------------------------------------------------------ photon pass */
+
+struct PhotonParams {
+    int light, map_type; /* 0 = caustic, 1 = global */
+    int path_length;
+    int rank, world;
+    unsigned long long first, count; /* this launch traces photon indices first + i, i < count, of the rank's shard */
+    unsigned long long seed;
+};
+
+/* pm_store's direction quantisation, pm.c:286-300 */
+__device__ __forceinline__ unsigned int
+pack_photon_dir(const double d[3])
+{
+    int theta = (int)(acos(d[2]) * (256.0 / M_PI));
+    theta = theta > 255 ? 255 : (theta < 0 ? 0 : theta);
+    int phi = (int)(atan2(d[1], d[0]) * (256.0 / (2.0 * M_PI)));
+    if (phi > 255) {
+        phi = 255;
+    } else if (phi < 0) {
+        phi = (phi + 256) & 255;
+    }
+    return (unsigned int)theta | ((unsigned int)phi << 8);
+}
+
+__global__ void __launch_bounds__(128)
+k_photon_trace(DScene S, PhotonParams P, float4 *__restrict__ pa, float4 *__restrict__ pb, unsigned int *stored, unsigned int cap,
+               Counters *cnt)
+{
+    const frt_light L = S.lights[P.light];
+    int overflow = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.count;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long index = (P.first + i) * (unsigned long long)P.world + (unsigned long long)P.rank;
+        unsigned long long key = mix64(P.seed ^ ((unsigned long long)(P.map_type + 1) << 56) ^ ((unsigned long long)P.light << 44) ^
+                                       (index * 0x9E3779B97F4A7C15ull));
+        unsigned int ctr = 0;
+#define DRAW() u01(mix64(key + (ctr++)))
+        /* ---- emit_photon, light.c:14-98 */
+        Ray r;
+        if (L.type == 3 /* POINT_LIGHT: a direction in the unit ball, NOT normalised (light.c:82-97) */) {
+            double dx, dy, dz;
+            int guard = 0;
+            do {
+                dx = 2 * DRAW() - 1;
+                dy = 2 * DRAW() - 1;
+                dz = 2 * DRAW() - 1;
+            } while (dx * dx + dy * dy + dz * dz > 1 && ++guard < 64);
+            r = Ray{ L.position[0], L.position[1], L.position[2], dx, dy, dz };
+        } else {
+            double o[3] = { L.position[0], L.position[1], L.position[2] };
+            if (L.type == 0 || L.type == 1) { /* area / circle: a random point of a random cached sample set */
+                unsigned long long set = (unsigned long long)(DRAW() * L.cache_len);
+                unsigned long long pt = (unsigned long long)(DRAW() * L.num_samples);
+                set = set >= (unsigned long long)L.cache_len ? L.cache_len - 1 : set;
+                pt = pt >= (unsigned long long)L.num_samples ? L.num_samples - 1 : pt;
+                const double *p = S.lpoints + 3 * (L.point_offset + set * L.num_samples + pt);
+                o[0] = __ldg(p);
+                o[1] = __ldg(p + 1);
+                o[2] = __ldg(p + 2);
+            }
+            const double r1 = DRAW(), r2 = DRAW(); /* sampler_2d(true, 1, 1): two jitters ... */
+            ctr += 2;                              /* ... and two shuffle picks that swap an entry with itself */
+            double d[3];
+            cosine_hemisphere(L.normal, r1, r2, d);
+            r = Ray{ o[0], o[1], o[2], d[0], d[1], d[2] };
+        }
+        double power[3] = { L.intensity[0], L.intensity[1], L.intensity[2] };
+        bool had_diffuse = false, had_specular = false;
+
+        /* ---- power_at / photon_hit, photon_tracer.c:114-201, as a loop */
+        for (int remaining = P.path_length; remaining > 0; --remaining) {
+            const Hit h = trace_closest_t<true>(S, r, &overflow); /* hit(xs, true) */
+            if (h.leaf < 0) {
+                break;
+            }
+            if (power[0] <= 0 && power[1] <= 0 && power[2] <= 0) {
+                break;
+            }
+            SurfaceG g;
+            surface_at(S, r, h, g);
+            const frt_material &M = S.mats[g.material];
+            double refl[3];
+            material_color(S, M.map_refl, M.refl, h.leaf, g.over, refl);
+            const double avg_d = (g.Kd[0] + g.Kd[1] + g.Kd[2]) / 3.0;
+            if (g.Kd[0] > 0 || g.Kd[1] > 0 || g.Kd[2] > 0) {
+                const bool store = (P.map_type == 0) ? had_specular : had_diffuse;
+                if (store) {
+                    const unsigned int slot = atomicAdd(stored, 1u);
+                    if (slot < cap) {
+                        const double dir[3] = { r.dx, r.dy, r.dz };
+                        pa[slot] = make_float4((float)g.p[0], (float)g.p[1], (float)g.p[2], __uint_as_float(pack_photon_dir(dir)));
+                        pb[slot] = make_float4((float)(g.Kd[0] * power[0]), (float)(g.Kd[1] * power[1]), (float)(g.Kd[2] * power[2]), 0.f);
+                    }
+                    if (P.map_type == 0) {
+                        break; /* a caustic photon is stored once */
+                    }
+                }
+            }
+            /* Russian roulette, photon_tracer.c:156-180 */
+            const double rr = DRAW();
+            const double avg_s = (refl[0] + refl[1] + refl[2]) / 3.0;
+            const double avg_t = (M.Tf[0] + M.Tf[1] + M.Tf[2]) / 3.0;
+            int action; /* 0 diffuse, 1 specular, 2 refract, 3 absorbed */
+            if (P.map_type == 1) {
+                const double tot = avg_d + avg_s + avg_t;
+                action = (rr * tot < avg_d) ? 0 : (rr * tot < avg_d + avg_s) ? 1 : (rr * tot < avg_d + avg_s + avg_t) ? 2 : 3;
+            } else {
+                const double tot = avg_s + avg_t;
+                action = (rr * tot < avg_s) ? 1 : (rr * tot < avg_s + avg_t) ? 2 : 3;
+            }
+            if (action == 0) { /* reflect_photon_diffuse :33-62 */
+                for (int k = 0; k < 3; ++k) {
+                    power[k] *= g.Kd[k];
+                }
+                const double r1 = DRAW(), r2 = DRAW();
+                ctr += 2;
+                double d[3];
+                cosine_hemisphere(g.n, r1, r2, d);
+                r = Ray{ g.over[0], g.over[1], g.over[2], d[0], d[1], d[2] };
+                had_diffuse = true;
+            } else if (action == 1) { /* reflect_photon_specular :64-78 */
+                if (!M.reflective) {
+                    break;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    power[k] *= 1.0 / avg_s;
+                }
+                r = Ray{ g.over[0], g.over[1], g.over[2], g.reflv[0], g.reflv[1], g.reflv[2] };
+                had_specular = true;
+            } else if (action == 2) { /* refract_photon :80-112 */
+                if (fabs(M.Tr) < FRT_EPS) {
+                    break;
+                }
+                double n1 = 1.0, n2 = 1.0;
+                trace_containers(S, r, h.leaf, n1, n2, &overflow);
+                const double n_ratio = n1 / n2;
+                const double cos_i = g.eye[0] * g.n[0] + g.eye[1] * g.n[1] + g.eye[2] * g.n[2];
+                const double sin2_t = n_ratio * n_ratio * (1.0 - cos_i * cos_i);
+                if (sin2_t > 1.0) {
+                    break;
+                }
+                const double sc = n_ratio * cos_i - sqrt(1.0 - sin2_t);
+                for (int k = 0; k < 3; ++k) {
+                    power[k] *= 1.0 / avg_t;
+                }
+                r = Ray{ g.under[0], g.under[1], g.under[2], g.n[0] * sc - g.eye[0] * n_ratio, g.n[1] * sc - g.eye[1] * n_ratio,
+                         g.n[2] * sc - g.eye[2] * n_ratio };
+                had_specular = true;
+            } else {
+                break;
+            }
+        }
+#undef DRAW
+    }
+    if (overflow) {
+        atomicOr(&cnt->overflow_csg, 1u);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ grid build */
+
+__device__ __forceinline__ unsigned int
+float_order(float f) /* monotone map float -> uint */
+{
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__host__ __device__ __forceinline__ float
+float_unorder(unsigned int u)
+{
+    unsigned int v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    float f;
+#ifdef __CUDA_ARCH__
+    f = __uint_as_float(v);
+#else
+    memcpy(&f, &v, sizeof(f));
+#endif
+    return f;
+}
+
+__global__ void
+k_pm_scale_bounds(float4 *__restrict__ a, float4 *__restrict__ b, unsigned int n, float scale, unsigned int *bounds /* min xyz, max xyz */)
+{
+    unsigned int mn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, mx[3] = { 0u, 0u, 0u };
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = a[i];
+        float4 w = b[i];
+        w.x *= scale; /* pm_scale_photon_power(map, 1 / photon_count), photon_tracer.c:251-253 */
+        w.y *= scale;
+        w.z *= scale;
+        b[i] = w;
+        const unsigned int o[3] = { float_order(p.x), float_order(p.y), float_order(p.z) };
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = min(mn[k], o[k]);
+            mx[k] = max(mx[k], o[k]);
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
+        mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(bounds + k, mn[k]);
+            atomicMax(bounds + 3 + k, mx[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ int
+pm_cell_of(const PMView &M, float x, float y, float z)
+{
+    int cx = min(max((int)floorf((x - M.gx) * M.inv_cell), 0), M.nx - 1);
+    int cy = min(max((int)floorf((y - M.gy) * M.inv_cell), 0), M.ny - 1);
+    int cz = min(max((int)floorf((z - M.gz) * M.inv_cell), 0), M.nz - 1);
+    return (cz * M.ny + cy) * M.nx + cx;
+}
+
+__global__ void
+k_pm_count(PMView M, const float4 *__restrict__ a, unsigned int n, unsigned int *counts)
+{
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = a[i];
+        atomicAdd(counts + pm_cell_of(M, p.x, p.y, p.z), 1u);
+    }
+}
+
+/* exclusive scan of counts[0..n) into start[0..n], single block */
+__global__ void __launch_bounds__(1024)
+k_pm_scan(const unsigned int *__restrict__ counts, unsigned int *__restrict__ start, unsigned int n)
+{
+    __shared__ unsigned int s_part[1024];
+    const unsigned int per = (n + 1023u) / 1024u;
+    const unsigned int lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    unsigned int sum = 0;
+    for (unsigned int i = lo; i < hi; ++i) {
+        sum += counts[i];
+    }
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int k = 0; k < 1024; ++k) {
+            unsigned int v = s_part[k];
+            s_part[k] = run;
+            run += v;
+        }
+        start[n] = run;
+    }
+    __syncthreads();
+    unsigned int run = s_part[threadIdx.x];
+    for (unsigned int i = lo; i < hi; ++i) {
+        start[i] = run;
+        run += counts[i];
+    }
+}
+
+__global__ void
+k_pm_scatter(PMView M, const float4 *__restrict__ a, const float4 *__restrict__ b, unsigned int n, unsigned int *cursor,
+             float4 *__restrict__ sa, float4 *__restrict__ sb)
+{
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = a[i];
+        const unsigned int slot = atomicAdd(cursor + pm_cell_of(M, p.x, p.y, p.z), 1u);
+        sa[slot] = p;
+        sb[slot] = b[i];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ queries */
+
+/*
+ * final_gather (renderer.c:647-687) + color_at_gi (:319-345): one thread per (hit, CMJ cell).  The gather ray's first
+ * hit, if diffuse, becomes a radiance-estimate request weighted by  pi * Kd * (eye . n) * rands[0]  (shade_hit_gi
+ * :626-645, lighting_gi :862-892, the "scale by theta" of :672).
+ */
+__global__ void __launch_bounds__(128)
+k_fg_trace(DScene S, FrameParams F, GIParams G, const LightRec *__restrict__ recs, unsigned int first_hit, unsigned int n_hits_batch,
+           GQuery *__restrict__ queries, unsigned int *n_queries, unsigned int qcap, Counters *cnt, int level)
+{
+    const unsigned int cells = (unsigned int)(G.usteps * G.vsteps);
+    const unsigned long long total = (unsigned long long)n_hits_batch * cells;
+    int overflow = 0;
+    unsigned long long n_rays = 0;
+    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total;
+         base += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long item = base + (threadIdx.x & 31);
+        bool want = false;
+        GQuery q;
+        if (item < total) {
+            const unsigned int h = first_hit + (unsigned int)(item / cells);
+            const int c = (int)(item % cells);
+            const LightRec *R = recs + h;
+            if (R->Kd[0] > 0 || R->Kd[1] > 0 || R->Kd[2] > 0) { /* renderer.c:739 */
+                const int qu = c % G.usteps, qv = c / G.usteps;
+                const unsigned long long key = mix64(G.seed ^ 0x66676174686572ull ^ ((unsigned long long)R->rng << 24) ^ (unsigned long long)level);
+                double r1, r2;
+                if (G.usteps == G.vsteps && G.usteps <= 16) {
+                    cmj_entry_square(G.usteps, key, qu, qv, r1, r2);
+                } else {
+                    cmj_jittered(G.usteps, G.vsteps, key, qu, qv, r1, r2);
+                }
+                const double n[3] = { R->n[0], R->n[1], R->n[2] };
+                double d[3];
+                cosine_hemisphere(n, r1, r2, d);
+                const Ray r{ R->over[0], R->over[1], R->over[2], d[0], d[1], d[2] };
+                const Hit hit = trace_closest(S, r, &overflow);
+                ++n_rays;
+                if (hit.leaf >= 0) {
+                    /* color_at_gi tests the diffuse colour at the hit point itself (:331-337) ... */
+                    const frt_material &M = S.mats[load_node_a(S, hit.leaf).material];
+                    const double p[3] = { r.ox + r.dx * hit.t, r.oy + r.dy * hit.t, r.oz + r.dz * hit.t };
+                    double kd0[3];
+                    material_color(S, M.map_Kd, M.Kd, hit.leaf, p, kd0);
+                    if (kd0[0] > 0 || kd0[1] > 0 || kd0[2] > 0) {
+                        SurfaceG g; /* ... and lighting_gi uses over_Kd, sampled at over_point (:862-866) */
+                        surface_at(S, r, hit, g);
+                        if (g.Kd[0] > 0.0 || g.Kd[1] > 0.0 || g.Kd[2] > 0.0) {
+                            const double edn = g.eye[0] * g.n[0] + g.eye[1] * g.n[1] + g.eye[2] * g.n[2];
+                            const double base_w = M_PI * r1;
+                            q.x = (float)g.over[0];
+                            q.y = (float)g.over[1];
+                            q.z = (float)g.over[2];
+                            q.ex = (float)g.eye[0];
+                            q.ey = (float)g.eye[1];
+                            q.ez = (float)g.eye[2];
+                            if (G.visualize) {
+                                q.wr = q.wg = q.wb = (float)base_w;
+                            } else {
+                                q.wr = (float)(base_w * g.Kd[0] * edn);
+                                q.wg = (float)(base_w * g.Kd[1] * edn);
+                                q.wb = (float)(base_w * g.Kd[2] * edn);
+                            }
+                            q.target = h | 0x80000000u;
+                            want = true;
+                        }
+                    }
+                }
+            }
+        }
+        const unsigned int slot = warp_append(n_queries, want);
+        if (want) {
+            if (slot < qcap) {
+                queries[slot] = q;
+            } else {
+                atomicOr(&cnt->overflow_queue, 1u);
+            }
+        }
+    }
+    if (overflow) {
+        atomicOr(&cnt->overflow_csg, 1u);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_rays += __shfl_down_sync(0xffffffffu, n_rays, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n_rays) {
+        atomicAdd(&cnt->rays_gather, n_rays);
+    }
+}
+
+/* lighting_caustics (renderer.c:829-860) and the visualize_photon_map call of lighting_gi (:743-751): one request per hit */
+__global__ void __launch_bounds__(256)
+k_gi_points(FrameParams F, GIParams G, const LightRec *__restrict__ recs, unsigned int first_hit, unsigned int n_hits_batch,
+            GQuery *__restrict__ queries, unsigned int *n_queries, unsigned int qcap, Counters *cnt, int want_caustic, int want_global)
+{
+    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_hits_batch; base += gridDim.x * blockDim.x) {
+        const unsigned int i = base + (threadIdx.x & 31);
+        bool live = false;
+        GQuery q;
+        unsigned int h = 0;
+        if (i < n_hits_batch) {
+            h = first_hit + i;
+            const LightRec *R = recs + h;
+            if (R->Kd[0] > 0 || R->Kd[1] > 0 || R->Kd[2] > 0) {
+                live = true;
+                const double edn = R->eye[0] * R->n[0] + R->eye[1] * R->n[1] + R->eye[2] * R->n[2];
+                q.x = (float)R->over[0];
+                q.y = (float)R->over[1];
+                q.z = (float)R->over[2];
+                q.ex = (float)R->eye[0];
+                q.ey = (float)R->eye[1];
+                q.ez = (float)R->eye[2];
+                if (G.visualize) {
+                    q.wr = q.wg = q.wb = 1.0f;
+                } else {
+                    q.wr = (float)(R->Kd[0] * edn);
+                    q.wg = (float)(R->Kd[1] * edn);
+                    q.wb = (float)(R->Kd[2] * edn);
+                }
+            }
+        }
+        if (want_caustic) {
+            const unsigned int slot = warp_append(n_queries, live);
+            if (live) {
+                q.target = h | 0x40000000u;
+                if (slot < qcap) queries[slot] = q; else atomicOr(&cnt->overflow_queue, 1u);
+            }
+        }
+        if (want_global) {
+            const unsigned int slot = warp_append(n_queries, live);
+            if (live) {
+                q.target = h;
+                if (slot < qcap) queries[slot] = q; else atomicOr(&cnt->overflow_queue, 1u);
+            }
+        }
+    }
+}
+
+/*
+ * pm_irradiance_estimate (pm.c:91-156): the n nearest photons within max_dist of the request, cone-filtered sum of
+ * those whose direction faces the "normal", density from the distance of the farthest one; fewer than 8 photons give
+ * nothing (:121).  The callers' rescaling (100 / found for the caustic map, 10 n / found for the global map,
+ * renderer.c:845, :878) and the request's weight are applied here and the result is added to the hit's sum.
+ */
+__global__ void __launch_bounds__(FRT_KNN_WARPS * 32)
+k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, const unsigned int *n_queries, unsigned int qcap,
+      double *__restrict__ acc_amb, double *__restrict__ acc_fg)
+{
+    __shared__ float s_d2[FRT_KNN_WARPS][FRT_KNN_CAP];
+    __shared__ unsigned int s_idx[FRT_KNN_WARPS][FRT_KNN_CAP];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int nq = min(*n_queries, qcap);
+    const unsigned int lt = (1u << lane) - 1u;
+    float *d2 = s_d2[wib];
+    unsigned int *idx = s_idx[wib];
+    const float R2 = G.radius * G.radius;
+    const unsigned int want_n = (unsigned int)G.n_photons;
+
+    for (unsigned int qi = blockIdx.x * FRT_KNN_WARPS + wib; qi < nq; qi += gridDim.x * FRT_KNN_WARPS) {
+        const GQuery q = queries[qi];
+        const bool caustic = (q.target & 0x40000000u) != 0;
+        const PMView &M = caustic ? MC : MG;
+        if (M.count == 0) {
+            continue;
+        }
+        unsigned int count = 0;
+        bool shrunk = false;
+        float r2cur = R2;
+        const int cx = (int)floorf((q.x - M.gx) * M.inv_cell), cy = (int)floorf((q.y - M.gy) * M.inv_cell),
+                  cz = (int)floorf((q.z - M.gz) * M.inv_cell);
+        /* how many cells the radius spans (1 when the cell size is the radius) */
+        const int reach = (int)ceilf(G.radius * M.inv_cell);
+        for (int z = max(cz - reach, 0); z <= min(cz + reach, M.nz - 1); ++z) {
+            for (int y = max(cy - reach, 0); y <= min(cy + reach, M.ny - 1); ++y) {
+                const int x0 = max(cx - reach, 0), x1 = min(cx + reach, M.nx - 1);
+                if (x0 > x1) {
+                    continue;
+                }
+                /* cells of one x-row are contiguous in memory: one range */
+                const unsigned int s = M.cell_start[(z * M.ny + y) * M.nx + x0], e = M.cell_start[(z * M.ny + y) * M.nx + x1 + 1];
+                for (unsigned int p0 = s; p0 < e; p0 += 32) {
+                    const unsigned int p = p0 + lane;
+                    bool hit = false;
+                    float dd = 0.f;
+                    if (p < e) {
+                        const float4 a = __ldg(M.a + p);
+                        const float dx = a.x - q.x, dy = a.y - q.y, dz = a.z - q.z;
+                        dd = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        hit = dd < r2cur;
+                    }
+                    const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const unsigned int pos = count + __popc(mask & lt);
+                        d2[pos] = dd;
+                        idx[pos] = p;
+                    }
+                    count += __popc(mask);
+                    __syncwarp();
+                    if (count > FRT_KNN_CAP - 32) {
+                        /* list nearly full: keep only the want_n nearest seen so far and tighten the radius */
+                        unsigned int T = 0;
+                        for (int bit = 30; bit >= 0; --bit) {
+                            const unsigned int test = T | (1u << bit);
+                            unsigned int c = 0;
+                            for (unsigned int k = lane; k < count; k += 32) {
+                                c += (__float_as_uint(d2[k]) < test) ? 1u : 0u;
+                            }
+                            c = __reduce_add_sync(0xffffffffu, c);
+                            if (c < want_n) {
+                                T = test;
+                            }
+                        }
+                        const float tf = __uint_as_float(T);
+                        unsigned int kept = 0;
+                        for (unsigned int k0 = 0; k0 < count; k0 += 32) {
+                            const unsigned int k = k0 + lane;
+                            const float v = (k < count) ? d2[k] : 0.f;
+                            const unsigned int id = (k < count) ? idx[k] : 0u;
+                            const bool keep = (k < count) && v <= tf;
+                            const unsigned int m2 = __ballot_sync(0xffffffffu, keep);
+                            __syncwarp();
+                            if (keep) {
+                                const unsigned int pos = kept + __popc(m2 & lt);
+                                d2[pos] = v;
+                                idx[pos] = id;
+                            }
+                            kept += __popc(m2);
+                            __syncwarp();
+                        }
+                        count = kept;
+                        r2cur = nextafterf(tf, 3.0e38f); /* candidates must now beat the current n-th distance */
+                        shrunk = true;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        /* the n nearest: threshold T = n-th smallest squared distance */
+        float thr = R2, r2_density = R2;
+        unsigned int found = count;
+        if (count > want_n || shrunk) {
+            if (count > want_n) {
+                unsigned int T = 0;
+                for (int bit = 30; bit >= 0; --bit) {
+                    const unsigned int test = T | (1u << bit);
+                    unsigned int c = 0;
+                    for (unsigned int k = lane; k < count; k += 32) {
+                        c += (__float_as_uint(d2[k]) < test) ? 1u : 0u;
+                    }
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (c < want_n) {
+                        T = test;
+                    }
+                }
+                thr = __uint_as_float(T);
+            } else {
+                float m = 0.f;
+                for (unsigned int k = lane; k < count; k += 32) {
+                    m = fmaxf(m, d2[k]);
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                }
+                thr = m;
+            }
+            r2_density = thr;
+            found = min(count, want_n);
+        }
+        float sr = 0.f, sg = 0.f, sb = 0.f;
+        if (found >= 8) {
+            const float inv_kr = 1.0f / (G.cone_k * G.radius);
+            for (unsigned int k = lane; k < count; k += 32) {
+                const float v = d2[k];
+                if (v <= thr) {
+                    const unsigned int id = idx[k];
+                    const unsigned int bits = __float_as_uint(__ldg(M.a + id).w);
+                    float st, ct, sp, cp;
+                    sincospif((float)(bits & 255u) * (1.0f / 256.0f), &st, &ct);        /* pm.c:60-65 tables */
+                    sincospif((float)((bits >> 8) & 255u) * (2.0f / 256.0f), &sp, &cp);
+                    const float dot = st * cp * q.ex + st * sp * q.ey + ct * q.ez;
+                    if (dot < 0.0f) {
+                        const float4 pw = __ldg(M.b + id);
+                        const float w = 1.0f - sqrtf(v) * inv_kr;
+                        sr = fmaf(pw.x, w, sr);
+                        sg = fmaf(pw.y, w, sg);
+                        sb = fmaf(pw.z, w, sb);
+                    }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                sg += __shfl_xor_sync(0xffffffffu, sg, o);
+                sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            }
+        }
+        if (lane == 0 && found >= 8) {
+            const double density = 1.0 / ((1.0 - 2.0 / (3.0 * (double)G.cone_k)) * (M_PI * (double)r2_density));
+            const double rescale = caustic ? 100.0 / (double)found : 10.0 * (double)G.n_photons / (double)found;
+            const double f = density * rescale;
+            double *acc = ((q.target & 0x80000000u) ? acc_fg : acc_amb) + 3 * (size_t)(q.target & 0x3fffffffu);
+            const double vr = f * (double)sr * (double)q.wr, vg = f * (double)sg * (double)q.wg, vb = f * (double)sb * (double)q.wb;
+            if (vr != 0.0) atomicAdd(acc, vr);
+            if (vg != 0.0) atomicAdd(acc + 1, vg);
+            if (vb != 0.0) atomicAdd(acc + 2, vb);
+        }
+        __syncwarp();
+    }
+}
+
+/* the ambient slot of shade_hit (renderer.c:737-770): direct ambient + indirect + final gather + caustics, clamped to a
+ * sum of sqrt(3) on diffuse surfaces, weighted into the pixel */
+__global__ void __launch_bounds__(256)
+k_gi_resolve(FrameParams F, GIParams G, const LightRec *__restrict__ recs, const double *__restrict__ acc_amb,
+             const double *__restrict__ acc_fg, double *__restrict__ canvas, const Counters *cnt, int level)
+{
+    const unsigned int n = min(cnt->n_hits[level], F.capacity);
+    const double fg_scale = 2.0 * M_PI / (double)(G.usteps * G.vsteps);
+    for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x) {
+        const LightRec *R = recs + h;
+        double amb[3];
+        const bool diffuse = R->Kd[0] > 0 || R->Kd[1] > 0 || R->Kd[2] > 0;
+        for (int k = 0; k < 3; ++k) {
+            amb[k] = acc_amb[3 * (size_t)h + k];
+            if (diffuse && G.use_final_gather) {
+                amb[k] += acc_fg[3 * (size_t)h + k] * fg_scale * R->Kd[k];
+            }
+        }
+        if (diffuse) {
+            const double len = amb[0] + amb[1] + amb[2];
+            if (len > 1.7320508075688772) {
+                for (int k = 0; k < 3; ++k) {
+                    amb[k] = amb[k] * (1.0 / len) * 1.7320508075688772;
+                }
+            }
+        }
+        double *px = canvas + 4 * (size_t)R->pixel;
+        for (int k = 0; k < 3; ++k) {
+            const double v = R->w[k] * amb[k];
+            if (v != 0.0) {
+                atomicAdd(px + k, v);
+            }
+        }
+    }
+}

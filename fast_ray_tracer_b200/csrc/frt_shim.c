@@ -620,6 +620,10 @@ env_long(const char *name, long dflt)
 /* scene kept between trace_photons() and render_multi(): photons live on the device */
 static frt_scene *g_scene;
 static World g_scene_world;
+/* a trace_photons() request waiting for render_multi() (see trace_photons below) */
+static bool g_photons_pending, g_photons_caustic, g_photons_global;
+static World g_photons_world;
+
 
 static Canvas
 render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
@@ -648,6 +652,28 @@ render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
         if (frt_scene_create(&d, device, &scene) != FRT_OK) {
             die("frt_scene_create");
         }
+    }
+
+    if (g_photons_pending && g_photons_world == w) {
+        frt_photon_cfg pc;
+        memset(&pc, 0, sizeof(pc));
+        pc.device = device;
+        pc.rank = 0;
+        pc.world = 1;
+        pc.populate_caustic = g_photons_caustic ? 1 : 0;
+        pc.populate_global = g_photons_global ? 1 : 0;
+        pc.seed = (uint64_t)env_long("FRT_SEED", 0);
+        frt_stats ps;
+        memset(&ps, 0, sizeof(ps));
+        if (frt_photons_emit(scene, &pc, &ps) != FRT_OK) {
+            die("frt_photons_emit");
+        }
+        if (frt_photons_finish(scene) != FRT_OK) {
+            die("frt_photons_finish");
+        }
+        printf("FRT_B200_PHOTONS emitted %llu stored caustic %llu global %llu\n", (unsigned long long)ps.rays_photon,
+               (unsigned long long)ps.photons_stored[0], (unsigned long long)ps.photons_stored[1]);
+        g_photons_pending = false;
     }
 
     frt_render_cfg cfg;
@@ -690,19 +716,17 @@ render(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
     return render_on_device(cam, w, usteps, vsteps, jitter);
 }
 
+/* trace_photons() runs before the camera exists (yaml_parser.py:201-218), so the shim only records the request; the
+ * photons are traced on the device right after the scene has been uploaded in render_multi(). */
+
 void
 trace_photons(const World w, size_t num_maps, bool populate_caustic_map, bool populate_global_map)
 {
     (void)num_maps;
-    if (env_long("FRT_DUMP_ONLY", 0)) {
-        return;
-    }
-    /* The camera is not known yet: flatten with a placeholder camera; render_multi() re-sends the camera. */
-    fprintf(stderr, "frt_shim: trace_photons: device photon pass not wired into the shim yet\n");
-    (void)w;
-    (void)populate_caustic_map;
-    (void)populate_global_map;
-    exit(73);
+    g_photons_pending = true;
+    g_photons_caustic = populate_caustic_map;
+    g_photons_global = populate_global_map;
+    g_photons_world = w;
 }
 
 PhotonMap *

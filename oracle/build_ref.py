@@ -36,7 +36,8 @@ BLOBS = OUT / "blobs"
 LIBDIR = REPO / "fast_ray_tracer_b200"
 
 CFLAGS = ["-std=gnu11", "-O2", "-march=x86-64-v3", "-fPIC", "-w"]
-WRAPS = ["-Wl,--wrap=render_multi", "-Wl,--wrap=intersect_world", "-Wl,--wrap=write_ppm_file", "-Wl,--wrap=write_png"]
+WRAPS = ["-Wl,--wrap=render_multi", "-Wl,--wrap=intersect_world", "-Wl,--wrap=write_ppm_file", "-Wl,--wrap=write_png",
+         "-Wl,--wrap=trace_photons"]
 
 # name -> (yaml relative to the reference root, edit function on the parsed YAML list)
 
@@ -62,6 +63,15 @@ def _cache_size(tree, n):
     return tree
 
 
+def edit_cornell_gi(tree, photons=100000, caustics=False):
+    """C5 at a size the CPU reference renders in seconds: the shipped GI configuration (global map + 8x8 final gather,
+    kNN 200, r 0.1) with fewer photons and a 64-set light cache (small enough to keep as a fixture)."""
+    cfg = _config(tree)
+    cfg["illumination"]["global-illumination"]["photon-count"] = photons
+    cfg["illumination"]["global-illumination"]["include-caustics"] = caustics
+    return _cache_size(tree, 64)
+
+
 def edit_none(tree):
     return tree
 
@@ -82,6 +92,9 @@ SCENES = {
     "cornell_shipped": ("scenes/cornell_box/cornell_box.yml", edit_cornell_shipped),
     # 64 cached sets: small enough to keep as a fixture, pins fast_ray_tracer_b200/lightcache.py bit for bit
     "cornell_cache64": ("scenes/cornell_box/cornell_box.yml", lambda t: _cache_size(_direct_only(t), 64)),
+    # C5: photon-mapped (global map + final gather); and a variant that also fills and queries the caustic map
+    "cornell_gi": ("scenes/cornell_box/cornell_box.yml", edit_cornell_gi),
+    "cornell_gi_caustics": ("scenes/cornell_box/cornell_box.yml", lambda t: edit_cornell_gi(t, 100000, True)),
     # primitive / CSG / group coverage
     "group_test": ("scenes/group_test/group.yml", edit_none),
     "csg_test": ("scenes/test/test.yml", edit_none),

@@ -43,7 +43,12 @@ GOLDEN = {
     "lens_test": ("lens_test", 300, 150, 0, 0),
     "shadow_glamour_shot": ("shadow_glamour_shot", 300, 120, 0, 0),
     "teapot": ("teapot", 200, 200, 0, 0),
+    # photon-mapped: stochastic in the reference too, so two reference renders (seeds 1 and 2) are stored; their RMSE is
+    # the noise floor the CUDA render is held against
+    "cornell_gi_64": ("cornell_gi", 64, 64, 2, 2),
+    "cornell_gi_caustics_48": ("cornell_gi_caustics", 48, 48, 1, 1),
 }
+STOCHASTIC = {"cornell_gi_64", "cornell_gi_caustics_48"}
 
 
 def make(name: str):
@@ -54,18 +59,28 @@ def make(name: str):
     if us:
         env.update(FRT_REF_USTEPS=str(us), FRT_REF_VSTEPS=str(vsteps))
     GOLD.mkdir(parents=True, exist_ok=True)
+    rgb_b = None
     with tempfile.TemporaryDirectory() as td:
         dump = Path(td) / "canvas.bin"
+        if name in STOCHASTIC:
+            env["FRT_REF_SEED"] = "1"
         info = build_ref.run_reference(scene, dump, env)
         rgb = read_canvas_dump(dump)
+        if name in STOCHASTIC:
+            env2 = dict(env, FRT_REF_SEED="2")
+            build_ref.run_reference(scene, dump, env2)
+            rgb_b = read_canvas_dump(dump)
     blob = build_ref.dump_blob(scene, env, suffix=f"__{name}")
     shutil.move(str(blob), GOLD / f"{name}.frt")
     meta = {"scene": scene, "hsize": rgb.shape[1], "vsize": rgb.shape[0],
             "reference_seconds": float(info.get("FRT_RENDER_SECONDS", "nan")),
             "reference_threads": int(info.get("FRT_THREADS", "0")),
             "reference_rays": int(info.get("FRT_RAYS", "0")), "size_line": info.get("FRT_SIZE", "")}
+    if "FRT_PHOTON_SECONDS" in info:
+        meta["reference_photon_seconds"] = float(info["FRT_PHOTON_SECONDS"])
+    extra = {"rgb_b": rgb_b.astype(np.float32)} if rgb_b is not None else {}
     np.savez_compressed(GOLD / f"{name}.npz", rgb=rgb.astype(np.float32), srgb8=to_srgb8(rgb).astype(np.uint8),
-                        meta=json.dumps(meta))
+                        meta=json.dumps(meta), **extra)
     print(name, meta)
 
 

@@ -3,7 +3,7 @@
  *
  * Linked into every binary under oracle/_ref/ with
  *   -Wl,--wrap=render_multi -Wl,--wrap=intersect_world
- *   -Wl,--wrap=write_ppm_file -Wl,--wrap=write_png
+ *   -Wl,--wrap=write_ppm_file -Wl,--wrap=write_png -Wl,--wrap=trace_photons
  * so that the UNMODIFIED reference sources (compiled where they lie under
  * /root/reference) can be timed, ray-counted and dumped without source edits.
  * The same hooks wrap the B200 shim build of a scene, so both arms see the
@@ -18,6 +18,8 @@
  *   FRT_CANVAS_OUT=path    dump Canvas->arr as raw doubles instead of the PPM
  *                          (int64 width, int64 height, then w*h*3 float64 RGB)
  *   FRT_SKIP_PPM=1         do not run the reference's own write_ppm_file
+ *   FRT_REF_SEED=n         srand48(n) / srand(n) before trace_photons() (the reference has no seed control of its own;
+ *                          two seeds give two independent reference renders of a photon-mapped scene)
  * Output lines (stdout): "FRT_RENDER_SECONDS <s>", "FRT_RAYS <n>", "FRT_THREADS <n>".
  */
 #define _GNU_SOURCE
@@ -31,11 +33,13 @@
 #include "src/renderer/camera.h"
 #include "src/renderer/world.h"
 #include "src/renderer/renderer.h"
+#include "src/renderer/photon_tracer.h"
 #include "src/libs/canvas/canvas.h"
 
 Canvas __real_render_multi(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter);
 Intersections __real_intersect_world(const World w, const Ray r, bool stop_after_first_hit);
 int __real_write_ppm_file(Canvas c, const bool use_scaling, const char *file_name);
+void __real_trace_photons(const World w, const size_t num_maps, bool populate_caustic, bool populate_global);
 
 /* intersect_world() calls, counted per thread in cache-line-padded slots so that counting does not serialise the
  * reference's worker threads on one shared atomic */
@@ -83,6 +87,20 @@ __wrap_intersect_world(const World w, const Ray r, bool stop_after_first_hit)
         __atomic_fetch_add(&frt_ray_slots[frt_my_slot].n, 1ULL, __ATOMIC_RELAXED);
     }
     return __real_intersect_world(w, r, stop_after_first_hit);
+}
+
+void
+__wrap_trace_photons(const World w, const size_t num_maps, bool populate_caustic, bool populate_global)
+{
+    long seed = env_long("FRT_REF_SEED", -1);
+    if (seed >= 0) {
+        srand48(seed);
+        srand((unsigned int)seed);
+    }
+    double t0 = now_seconds();
+    __real_trace_photons(w, num_maps, populate_caustic, populate_global);
+    printf("FRT_PHOTON_SECONDS %.6f\n", now_seconds() - t0);
+    fflush(stdout);
 }
 
 Canvas

@@ -22,5 +22,9 @@ def frt():
     return frt
 
 
+STOCHASTIC = ("cornell_gi",)  # photon-mapped fixtures: two reference renders each, compared statistically (test_gpu_gi.py)
+
+
 def golden_names():
-    return sorted(p.stem for p in GOLDEN.glob("*.npz"))
+    """The deterministic fixtures (one reference render each, compared pixel by pixel)."""
+    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(STOCHASTIC))
