@@ -1,0 +1,66 @@
+"""The drop-in itself (-m gpu): the reference's generated main.c + the reference's own host-side scene construction,
+linked with fast_ray_tracer_b200/csrc/frt_shim.c and libfrt_b200.so instead of renderer.c / photon_tracer.c
+(INTEGRATION.md), run as an ordinary program and compared with the unmodified reference's render of the same scene.
+
+The binaries are built by oracle/build_ref.py in the build container (the reference tree does not exist on the GPU
+box) and travel with the snapshot under oracle/_ref/."""
+import json
+import os
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REPO
+
+pytestmark = pytest.mark.gpu
+
+REF = REPO / "oracle" / "_ref"
+
+
+def run_dropin(scene, env_extra):
+    binary = REF / f"{scene}_b200"
+    if not binary.exists():
+        pytest.skip(f"{binary} not built")
+    from compare import read_canvas_dump
+
+    with tempfile.TemporaryDirectory() as td:
+        dump = Path(td) / "canvas.bin"
+        env = dict(os.environ, FRT_CANVAS_OUT=str(dump), FRT_SKIP_PPM="1")
+        env.update(env_extra)
+        r = subprocess.run([str(binary)], env=env, cwd=td, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:]
+        return read_canvas_dump(dump), r.stdout
+
+
+@pytest.mark.parametrize("scene,fixture,env", [
+    ("reflect_refract", "reflect_refract", {}),
+    ("cornell_exact", "cornell_exact_96_1spp", {"FRT_REF_HSIZE": "96", "FRT_REF_VSIZE": "96", "FRT_REF_USTEPS": "1", "FRT_REF_VSTEPS": "1"}),
+    ("csg_test", "csg_test", {"FRT_REF_HSIZE": "200", "FRT_REF_VSIZE": "200"}),
+])
+def test_generated_program_renders_through_the_shim(scene, fixture, env):
+    from compare import parity_report
+
+    canvas, out = run_dropin(scene, env)
+    ref = np.load(GOLDEN / f"{fixture}.npz")["rgb"].astype(np.float64)
+    assert canvas.shape == ref.shape
+    rep = parity_report(canvas, ref)
+    assert rep["within_1lsb"] >= 0.999, rep
+    assert "FRT_B200_FRAME_MS" in out
+
+
+def test_generated_program_with_photon_maps():
+    """C5: main() calls trace_photons() then render_multi(); the shim defers the photon pass to the device."""
+    from compare import to_srgb8
+
+    canvas, out = run_dropin("cornell_gi", {"FRT_REF_HSIZE": "64", "FRT_REF_VSIZE": "64", "FRT_REF_USTEPS": "2", "FRT_REF_VSTEPS": "2"})
+    z = np.load(GOLDEN / "cornell_gi_64.npz")
+    a, b = z["rgb"].astype(np.float64), z["rgb_b"].astype(np.float64)
+
+    def rmse(x, y):
+        return float(np.sqrt(((to_srgb8(x).astype(np.float64) - to_srgb8(y).astype(np.float64)) ** 2).mean()))
+
+    assert "FRT_B200_PHOTONS" in out
+    assert rmse(canvas, a) <= 1.25 * rmse(a, b), (rmse(canvas, a), rmse(a, b))
