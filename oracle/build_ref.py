@@ -72,6 +72,40 @@ def edit_cornell_gi(tree, photons=100000, caustics=False):
     return _cache_size(tree, 64)
 
 
+ASSETS = OUT / "assets"
+MAX_TEXTURE_DIM = 128
+
+
+def edit_images(tree):
+    """Image patterns: the generator shells out to ImageMagick for non-PNG files and the program opens them relative to
+    its working directory.  Neither exists on the GPU box, so every image is converted (Pillow) or copied into
+    oracle/_ref/assets/ and referenced by absolute path (/root/repo is valid on both boxes)."""
+    from PIL import Image
+
+    ASSETS.mkdir(parents=True, exist_ok=True)
+
+    def walk(node):
+        if isinstance(node, dict):
+            if node.get("type") == "image" and "file" in node:
+                src = REF / node["file"]
+                dst = ASSETS / (Path(node["file"]).stem + ".png")
+                if not dst.exists():
+                    im = Image.open(src).convert("RGB")
+                    if max(im.size) > MAX_TEXTURE_DIM:  # keep the scene blobs (texels as doubles) small enough to be fixtures
+                        k = MAX_TEXTURE_DIM / max(im.size)
+                        im = im.resize((max(1, round(im.size[0] * k)), max(1, round(im.size[1] * k))), Image.LANCZOS)
+                    im.save(dst, format="PNG")
+                node["file"] = "/root/repo/oracle/_ref/assets/" + dst.name
+            for v in node.values():
+                walk(v)
+        elif isinstance(node, list):
+            for v in node:
+                walk(v)
+
+    walk(tree)
+    return tree
+
+
 def edit_none(tree):
     return tree
 
@@ -106,6 +140,9 @@ SCENES = {
     "align_check_plane": ("scenes/align_check_plane/align_check_plane.yml", edit_none),
     "lens_test": ("scenes/lens_test/lens_test.yml", edit_none),
     "shadow_glamour_shot": ("scenes/shadow_glamour_shot/shadow_glamour_shot.yml", lambda t: _cache_size(t, 1)),
+    # image textures (Ka / Kd / bump maps through planar and spherical uv maps)
+    "bump_map_test": ("scenes/bump_map_test/bump_map_test.yml", edit_images),
+    "texture_map_test": ("scenes/texture_map_test/texture_map_test.yml", edit_images),
     # C3
     "teapot": ("scenes/teapot/teapot.yml", edit_none),
     "bounding_boxes": ("scenes/bounding_boxes/bounding_boxes.yml", edit_none),
@@ -176,12 +213,12 @@ def build_scene(name: str, force=False):
     all_objs = [str(obj_path(s)) for s in reference_sources()]
     hooks = str(OBJ / "ref_hooks.o")
     ref_bin = OUT / f"{name}_ref"
-    run(["gcc", "-o", str(ref_bin), str(main_o), *all_objs, hooks, *WRAPS, "-lm", "-lpthread"])
+    run(["gcc", "-o", str(ref_bin), str(main_o), *all_objs, hooks, *WRAPS, "-lm", "-lpthread", "-lz"])
     replaced = {"renderer__renderer.o", "renderer__photon_tracer.o"}
     host_objs = [o for o in all_objs if Path(o).name not in replaced]
     b200_bin = OUT / f"{name}_b200"
     run(["gcc", "-o", str(b200_bin), str(main_o), *host_objs, str(OBJ / "frt_shim.o"), hooks, *WRAPS,
-         "-L", str(LIBDIR), "-lfrt_b200", "-Wl,-rpath,$ORIGIN/../../fast_ray_tracer_b200", "-lm", "-lpthread"])
+         "-L", str(LIBDIR), "-lfrt_b200", "-Wl,-rpath,$ORIGIN/../../fast_ray_tracer_b200", "-lm", "-lpthread", "-lz"])
     return ref_bin, b200_bin
 
 

@@ -43,6 +43,8 @@ GOLDEN = {
     "lens_test": ("lens_test", 300, 150, 0, 0),
     "shadow_glamour_shot": ("shadow_glamour_shot", 300, 120, 0, 0),
     "teapot": ("teapot", 200, 200, 0, 0),
+    "bump_map_test": ("bump_map_test", 200, 200, 0, 0),
+    "texture_map_test": ("texture_map_test", 200, 200, 0, 0),
     # photon-mapped: stochastic in the reference too, so two reference renders (seeds 1 and 2) are stored; their RMSE is
     # the noise floor the CUDA render is held against
     "cornell_gi_64": ("cornell_gi", 64, 64, 2, 2),
