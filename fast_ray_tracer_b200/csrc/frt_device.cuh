@@ -140,6 +140,86 @@ bbox_hit(const DScene &S, int node, const Ray &r)
     return tmin <= tmax;
 }
 
+/* ---- fast FP64 reciprocal / reciprocal square root: MUFU seed + Newton steps, no slow-path branch.  Results are
+ *      within 1 ulp of the correctly rounded value, which only moves a t value by 1 ulp (never a decision that is
+ *      not already a tie).  Used by the shadow traversal, where every shadow ray would otherwise pay for a dozen
+ *      IEEE divisions per node. */
+__device__ __forceinline__ double
+rcp_fast(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+__device__ __forceinline__ double
+rsqrt_fast(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double h = 0.5 * x;
+    r = r * fma(-h * r, r, 1.5);
+    r = r * fma(-h * r, r, 1.5);
+    return r;
+}
+
+/* 1 / direction per axis for the slab tests; +inf where |direction| < EPSILON, which reproduces the
+ * "numerator * INFINITY" branch of check_axis / bbox_check_axis (cube.c:27-33, bounding_box.c:135-141) */
+struct InvDir {
+    double x, y, z;
+};
+
+__device__ __forceinline__ InvDir
+inv_dir(const Ray &r)
+{
+    InvDir v;
+    v.x = fabs(r.dx) >= FRT_EPS ? rcp_fast(r.dx) : CUDART_INF;
+    v.y = fabs(r.dy) >= FRT_EPS ? rcp_fast(r.dy) : CUDART_INF;
+    v.z = fabs(r.dz) >= FRT_EPS ? rcp_fast(r.dz) : CUDART_INF;
+    return v;
+}
+
+__device__ __forceinline__ void
+slab_axis_inv(double origin, double inv, double lo, double hi, double &t0, double &t1)
+{
+    double a = (lo - origin) * inv;
+    double b = (hi - origin) * inv;
+    if (isnan(a)) a = CUDART_INF; /* 0 * inf */
+    if (isnan(b)) b = CUDART_INF;
+    t0 = fmin(a, b);
+    t1 = fmax(a, b);
+}
+
+/* the slab interval [tmin, tmax] of the node's box (bounding_box_intersects, bounding_box.c:165-175, hits iff tmin <= tmax) */
+__device__ __forceinline__ void
+bbox_range_inv(const DScene &S, int node, const Ray &r, const InvDir &inv, double &tmin, double &tmax)
+{
+    const double2 *b = reinterpret_cast<const double2 *>(S.bbox + 6 * node);
+    double2 b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2); /* min.x min.y | min.z max.x | max.y max.z */
+    double x0, x1, y0, y1, z0, z1;
+    slab_axis_inv(r.ox, inv.x, b0.x, b1.y, x0, x1);
+    slab_axis_inv(r.oy, inv.y, b0.y, b2.x, y0, y1);
+    slab_axis_inv(r.oz, inv.z, b1.x, b2.y, z0, z1);
+    tmin = fmax(fmax(x0, y0), z0);
+    tmax = fmin(fmin(x1, y1), z1);
+}
+
+__device__ __forceinline__ bool
+bbox_hit_inv(const DScene &S, int node, const Ray &r, const InvDir &inv)
+{
+    const double2 *b = reinterpret_cast<const double2 *>(S.bbox + 6 * node);
+    double2 b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2); /* min.x min.y | min.z max.x | max.y max.z */
+    double x0, x1, y0, y1, z0, z1;
+    slab_axis_inv(r.ox, inv.x, b0.x, b1.y, x0, x1);
+    slab_axis_inv(r.oy, inv.y, b0.y, b2.x, y0, y1);
+    slab_axis_inv(r.oz, inv.z, b1.x, b2.y, z0, z1);
+    return fmax(fmax(x0, y0), z0) <= fmin(fmin(x1, y1), z1);
+}
+
 /* ---- Schwarze's quadric / cubic / quartic solver (Graphics Gems; reference src/libs/quartic/Roots3And4.c) */
 
 #define FRT_EQN_EPS 1e-9
@@ -637,32 +717,48 @@ trace_closest_t(const DScene &S, const Ray &wr, int *overflow)
     best.u = best.v = -1.0;
     best.leaf = -1;
     CsgHit buf[FRT_CSG_CAP];
+    const InvDir winv = inv_dir(wr);
     for (int rt = 0; rt < S.n_roots; ++rt) {
         int i = __ldg(S.roots + rt);
         int end = load_node_a(S, i).skip;
         int cur_xf = 0;
         Ray lr = wr;
+        InvDir inv = winv;
         while (i < end) {
             NodeA a = load_node_a(S, i);
             if (a.xform != cur_xf) {
                 cur_xf = a.xform;
-                lr = ray_to_local(S, cur_xf, wr);
+                if (cur_xf == 0) {
+                    lr = wr;
+                    inv = winv;
+                } else {
+                    lr = ray_to_local(S, cur_xf, wr);
+                    inv = inv_dir(lr);
+                }
             }
-            if (a.type == FRT_GROUP) {
-                i = bbox_hit(S, i, lr) ? i + 1 : a.skip;
-            } else if (a.type == FRT_CSG) {
-                if (bbox_hit(S, i, lr)) {
-                    int n = csg_eval(S, i, wr, buf, overflow);
-                    for (int k = 0; k < n; ++k) {
-                        if (buf[k].t > 0 && buf[k].t < best.t &&
-                            (!CASTERS || S.mats[load_node_a(S, buf[k].leaf).material].casts_shadow)) {
-                            best.t = buf[k].t;
-                            best.leaf = buf[k].leaf;
-                            best.u = best.v = -1.0;
+            if (a.type >= FRT_CSG) {
+                /* The minimum over the leaves does not depend on the order or on which empty subtrees are skipped: besides
+                 * the reference's own cull (tmin > tmax) skip boxes wholly behind the origin (no t > 0 inside) and boxes
+                 * wholly beyond the best hit so far (t is the same parameter in every node's frame). */
+                double tmin, tmax;
+                bbox_range_inv(S, i, lr, inv, tmin, tmax);
+                const bool miss = !(tmin <= tmax) || tmax < 0.0 || tmin > best.t;
+                if (a.type == FRT_GROUP) {
+                    i = miss ? a.skip : i + 1;
+                } else {
+                    if (!miss) {
+                        int n = csg_eval(S, i, wr, buf, overflow);
+                        for (int k = 0; k < n; ++k) {
+                            if (buf[k].t > 0 && buf[k].t < best.t &&
+                                (!CASTERS || S.mats[load_node_a(S, buf[k].leaf).material].casts_shadow)) {
+                                best.t = buf[k].t;
+                                best.leaf = buf[k].leaf;
+                                best.u = best.v = -1.0;
+                            }
                         }
                     }
+                    i = a.skip;
                 }
-                i = a.skip;
             } else {
                 NodeB b = load_node_b(S, i);
                 double t[4], uv[2];
@@ -690,72 +786,6 @@ __device__ __forceinline__ Hit
 trace_closest(const DScene &S, const Ray &wr, int *overflow)
 {
     return trace_closest_t<false>(S, wr, overflow);
-}
-
-/* ---- fast FP64 reciprocal / reciprocal square root: MUFU seed + Newton steps, no slow-path branch.  Results are
- *      within 1 ulp of the correctly rounded value, which only moves a t value by 1 ulp (never a decision that is
- *      not already a tie).  Used by the shadow traversal, where every shadow ray would otherwise pay for a dozen
- *      IEEE divisions per node. */
-__device__ __forceinline__ double
-rcp_fast(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-}
-
-__device__ __forceinline__ double
-rsqrt_fast(double x)
-{
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double h = 0.5 * x;
-    r = r * fma(-h * r, r, 1.5);
-    r = r * fma(-h * r, r, 1.5);
-    return r;
-}
-
-/* 1 / direction per axis for the slab tests; +inf where |direction| < EPSILON, which reproduces the
- * "numerator * INFINITY" branch of check_axis / bbox_check_axis (cube.c:27-33, bounding_box.c:135-141) */
-struct InvDir {
-    double x, y, z;
-};
-
-__device__ __forceinline__ InvDir
-inv_dir(const Ray &r)
-{
-    InvDir v;
-    v.x = fabs(r.dx) >= FRT_EPS ? rcp_fast(r.dx) : CUDART_INF;
-    v.y = fabs(r.dy) >= FRT_EPS ? rcp_fast(r.dy) : CUDART_INF;
-    v.z = fabs(r.dz) >= FRT_EPS ? rcp_fast(r.dz) : CUDART_INF;
-    return v;
-}
-
-__device__ __forceinline__ void
-slab_axis_inv(double origin, double inv, double lo, double hi, double &t0, double &t1)
-{
-    double a = (lo - origin) * inv;
-    double b = (hi - origin) * inv;
-    if (isnan(a)) a = CUDART_INF; /* 0 * inf */
-    if (isnan(b)) b = CUDART_INF;
-    t0 = fmin(a, b);
-    t1 = fmax(a, b);
-}
-
-__device__ __forceinline__ bool
-bbox_hit_inv(const DScene &S, int node, const Ray &r, const InvDir &inv)
-{
-    const double2 *b = reinterpret_cast<const double2 *>(S.bbox + 6 * node);
-    double2 b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2); /* min.x min.y | min.z max.x | max.y max.z */
-    double x0, x1, y0, y1, z0, z1;
-    slab_axis_inv(r.ox, inv.x, b0.x, b1.y, x0, x1);
-    slab_axis_inv(r.oy, inv.y, b0.y, b2.x, y0, y1);
-    slab_axis_inv(r.oz, inv.z, b1.x, b2.y, z0, z1);
-    return fmax(fmax(x0, y0), z0) <= fmin(fmin(x1, y1), z1);
 }
 
 /*
@@ -851,7 +881,12 @@ trace_shadow(const DScene &S, const Ray &wr, double distance, int *overflow, uns
             }
             if (COUNT) cost += (a.type >= FRT_CSG) ? FRT_COST_BBOX : prim_cost(a.type);
             if (a.type >= FRT_CSG) { /* CSG or group: cull by the node's own bounds */
-                if (!bbox_hit_inv(S, i, lr, inv)) {
+                double bt0, bt1;
+                bbox_range_inv(S, i, lr, inv, bt0, bt1);
+                /* the reference's cull (tmin > tmax) plus boxes wholly behind the origin: every crossing inside has
+                 * t <= 0, which neither stops the search nor shadows (group.c:105-123) -- top-level subtrees only, a CSG
+                 * operand's negative crossings still toggle the filter state */
+                if (!(bt0 <= bt1) || (sp == 0 && bt1 < 0.0)) {
                     i = a.skip;
                 } else {
                     if (a.type == FRT_CSG) {

@@ -385,7 +385,8 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
             if (!(flags & FRT_FN_NOCULL)) {
                 float tn_lo, tn_hi, tf_lo, tf_hi;
                 box_f(cf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-                miss = tn_lo > tf_hi;
+                /* surely missed, or (outside a CSG) surely wholly behind the origin: only t <= 0 crossings inside */
+                miss = tn_lo > tf_hi || (sp == 0 && tf_hi < 0.0f);
             }
             if (miss) {
                 i = skip;

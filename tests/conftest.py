@@ -27,4 +27,4 @@ STOCHASTIC = ("cornell_gi",)  # photon-mapped fixtures: two reference renders ea
 
 def golden_names():
     """The deterministic fixtures (one reference render each, compared pixel by pixel)."""
-    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(STOCHASTIC))
+    return sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(STOCHASTIC) and (GOLDEN / f"{p.stem}.frt").exists())

@@ -128,3 +128,22 @@ def test_fp64_shadow_and_shading_flags_give_the_same_frame(frt, name):
         a, _ = sc.render(flags=FRT_FLAG_F64_SHADING)
         b, _ = sc.render(flags=FRT_FLAG_F64_SHADING | FRT_FLAG_F64_SHADOW)
     assert np.allclose(a, b, rtol=0, atol=1e-12)  # pixel sums are FP64 atomics: order may differ in the last bit
+
+
+def test_six_dragons_through_the_divided_group_tree(frt):
+    """BASELINE.json configs[2], bounding_boxes.yml: 6 x dragon.obj (141 K triangles in ~31 K divided groups), glass
+    boxes that do not cast shadows, cylinders, 4 point lights.  The 52 MB scene blob is not a git fixture: it is dumped
+    by oracle/build_ref.py into oracle/_ref/blobs/ and travels to the GPU box with the snapshot."""
+    from compare import parity_report
+    from conftest import REPO
+
+    blob = REPO / "oracle" / "_ref" / "blobs" / "bounding_boxes.frt"
+    if not blob.exists():
+        pytest.skip(f"{blob} not built (python oracle/build_ref.py bounding_boxes)")
+    z = np.load(GOLDEN / "bounding_boxes_600.npz")
+    ref = z["rgb"].astype(np.float64)
+    desc = frt.SceneDesc.load(blob)
+    desc.set_resolution(ref.shape[1], ref.shape[0])
+    canvas, stats = frt.render_multi(desc)
+    rep = parity_report(canvas[..., :3], ref)
+    assert rep["within_1lsb"] >= GATE_WITHIN_1LSB, rep
