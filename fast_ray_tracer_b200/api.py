@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 _LIB_PATH = _PKG / "libfrt_b200.so"
 _lib = None
 
-FRT_ABI_VERSION = 5
+FRT_ABI_VERSION = 6
 FRT_FLAG_NO_PRUNE = 1
 FRT_FLAG_COUNT_RAYS = 2
 FRT_FLAG_F64_SHADING = 4
@@ -111,7 +111,7 @@ class frt_stats(C.Structure):
                 ("rays_gather", C.c_uint64), ("rays_photon", C.c_uint64), ("hits_shaded", C.c_uint64),
                 ("light_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("shadow_nodes", C.c_uint64),
                 ("overflow", C.c_uint64), ("photons_stored", C.c_uint64 * 3), ("light_flops", C.c_uint64),
-                ("shadow_deferred", C.c_uint64), ("shadow_mismatch", C.c_uint64),
+                ("shadow_deferred", C.c_uint64), ("shadow_mismatch", C.c_uint64), ("shadow_reasons", C.c_uint64 * 10),
                 ("rows_rendered", C.c_int32), ("pad", C.c_int32)]
 
 
@@ -338,6 +338,7 @@ class Scene:
                             shadow_mismatch=st.shadow_mismatch,
                             rows_rendered=st.rows_rendered)
         stats.rays_gather = st.rays_gather
+        stats.extra["shadow_reasons"] = [int(x) for x in st.shadow_reasons]
         return (out if download else None), stats
 
     # ---- photon pass (replaces trace_photons, reference photon_tracer.c:203)

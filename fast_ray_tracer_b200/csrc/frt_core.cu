@@ -117,6 +117,8 @@ struct Counters {
     unsigned int n_deferred, pad;  /* shadow rays the FP32 pass left undecided in the current k_shadow_f32 launch */
     unsigned long long rays_secondary, rays_shadow, hits_shaded, shadow_nodes, light_flops;
     unsigned long long deferred_total, f32_mismatch, rays_gather;
+    unsigned long long undecided_node[32]; /* debug: node at which a leaf verdict was undecided */
+    unsigned long long undecided_reason[10]; /* counting build: why the FP32 filter deferred a ray (codes in frt_shadow_f32.cuh) */
 };
 
 struct DCamera {
@@ -614,12 +616,13 @@ struct LightTmp { /* per shaded hit, per light launch; the first 16 bytes are al
 template <typename T, int G>
 __global__ void __launch_bounds__(256)
 k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, const Counters *cnt,
-            int level, int light_idx)
+            int level, int light_idx, const float *__restrict__ flpoints)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
     const frt_light L = S.lights[light_idx];
     const int NS = L.num_samples;
     const double *pts = S.lpoints + 3 * L.point_offset;
+    const float *fpts = flpoints + 3 * L.point_offset;
     const unsigned int lane_g = threadIdx.x % G;
     const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     const unsigned int groups = gridDim.x * blockDim.x / G;
@@ -649,9 +652,19 @@ k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
         if (live && (F.use_diffuse || F.use_spec_highlight)) {
             const T ndote = nrm[0] * eye[0] + nrm[1] * eye[1] + nrm[2] * eye[2];
             const double *pb = pts + 3 * (size_t)set_b * NS;
+            const float *pbf = fpts + 3 * (size_t)set_b * NS;
+            const float ofx = (float)over[0], ofy = (float)over[1], ofz = (float)over[2];
             for (int s = lane_g; s < NS; s += G) {
-                /* the light vector is formed in FP64 (a difference of nearby world points), everything after in T */
-                T lx = (T)(__ldg(pb + 3 * s) - over[0]), ly = (T)(__ldg(pb + 3 * s + 1) - over[1]), lz = (T)(__ldg(pb + 3 * s + 2) - over[2]);
+                T lx, ly, lz;
+                if (sizeof(T) == sizeof(float)) { /* FP32 copy of the sample points: half the bytes of the 157 MB cache */
+                    lx = (T)(__ldg(pbf + 3 * s) - ofx);
+                    ly = (T)(__ldg(pbf + 3 * s + 1) - ofy);
+                    lz = (T)(__ldg(pbf + 3 * s + 2) - ofz);
+                } else {
+                    lx = (T)(__ldg(pb + 3 * s) - over[0]);
+                    ly = (T)(__ldg(pb + 3 * s + 1) - over[1]);
+                    lz = (T)(__ldg(pb + 3 * s + 2) - over[2]);
+                }
                 T inv = (T)1 / sqrt(lx * lx + ly * ly + lz * lz);
                 lx *= inv;
                 ly *= inv;
@@ -753,7 +766,7 @@ normalise_shadow_ray(Ray &sr, double dist2)
 }
 
 #ifndef FRT_SHADOW_MINB
-#define FRT_SHADOW_MINB 2
+#define FRT_SHADOW_MINB 4
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
@@ -812,11 +825,18 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                 w.dz = vz * rinv;
                 const float omax = fmaxf(fmaxf(fabsf(w.ox), fabsf(w.oy)), fabsf(w.oz));
                 const float pmax = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
-                const float eo_w = 2.0f * FRT_F32_U * (omax + SF.bmax);
+                /* origin rounded to FP32: 2u |o|; a WORLD box bound rounded to FP32 adds 2u Bmax to every slab numerator */
+                const float eo_o = 2.0f * FRT_F32_U * omax;
+                const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, eo_o);
                 const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G);
                 frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
                 const float Df = len2 * rinv;
-                res = trace_shadow_f32<COUNT>(SF, fnodes, root, w, omax, eo_w, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
+                res = trace_shadow_f32<COUNT>(SF, fnodes, root, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
+                if (COUNT && (res >> 4)) {
+                    atomicAdd(&cnt->undecided_reason[min((res >> 4) & 15, 9)], 1ull);
+                    atomicAdd(&cnt->undecided_node[(res >> 8) & 31], 1ull);
+                }
+                res &= 15;
             }
             if (COUNT) ++n_shadow;
             if (MODE == 2 && res != FRT_SH_UNDECIDED) {
@@ -1625,7 +1645,7 @@ template <typename T>
 static void
 launch_light_sum(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g)
 {
-#define LS(G) k_light_sum<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, light)
+#define LS(G) k_light_sum<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, light, sc->SF.lpoints)
     switch (g) {
     case 1: LS(1); break;
     case 2: LS(2); break;
@@ -1909,6 +1929,14 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         totals.deferred_total += hc.deferred_total;
         totals.f32_mismatch += hc.f32_mismatch;
         totals.rays_gather += hc.rays_gather;
+        for (int k = 0; k < 10; ++k) {
+            totals.undecided_reason[k] += hc.undecided_reason[k];
+        }
+        if (getenv("FRT_DEBUG_NODES") != nullptr) {
+            for (int k = 0; k < 32; ++k) {
+                if (hc.undecided_node[k]) fprintf(stderr, "undecided at node %d: %llu\n", k, hc.undecided_node[k]);
+            }
+        }
         if (hc.overflow_queue) {
             break;
         }
@@ -1936,6 +1964,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         st->shadow_deferred = totals.deferred_total;
         st->shadow_mismatch = totals.f32_mismatch;
         st->rays_gather = totals.rays_gather;
+        for (int k = 0; k < 10; ++k) {
+            st->shadow_reasons[k] = totals.undecided_reason[k];
+        }
         st->kernel_launches = launches;
         st->light_launches = light_launches;
         st->rows_rendered = F.n_owned_rows;

@@ -320,11 +320,21 @@ leaf_span(int type, const float4 lo, const float4 hi, const FrameF &f, SpanF &s)
     }
     const float sq = sqrtf(disc);
     const float ds = dD / sq + FRT_F32_G * sq;
-    const float i2a = rcpf_fast(2.0f * a);
-    const float ra = 2.0f * (da / a) + 2.0f * FRT_F32_G;
-    const float t0 = (-b - sq) * i2a, t1 = (-b + sq) * i2a;
-    const float E0 = (db + ds) * 2.0f * i2a;
-    const float e0 = fmaf(fabsf(t0), ra, E0), e1 = fmaf(fabsf(t1), ra, E0);
+    /* Cancellation-free roots: q = -(b + sign(b) sqrt(disc)) / 2, roots q / a and c / q.  (-b + sqrt(disc)) loses every
+     * digit for a ray that starts on the sphere (c ~ 1e-5), which is every shadow ray of a hit on the sphere itself. */
+    const float q = -0.5f * (b + copysignf(sq, b));
+    const float dq = 0.5f * (db + ds) + FRT_F32_G * fabsf(q);
+    const float ia = rcpf_fast(a), iq = rcpf_fast(q);
+    const float tb = q * ia, ts = c * iq;                 /* the root far from / near zero */
+    /* first-order bounds, times 1.5 for the second-order terms (a > 4 da and |q| > 4 dq are required) */
+    const float eb = 1.5f * fmaf(fabsf(tb), da * ia + 2.0f * FRT_F32_G, dq * ia);
+    const float es = 1.5f * fmaf(fabsf(ts), dq * fabsf(iq) + 2.0f * FRT_F32_G, dc * fabsf(iq));
+    if (!(fabsf(q) > 4.0f * dq)) {
+        return false;
+    }
+    const bool big_first = tb < ts;
+    const float t0 = big_first ? tb : ts, e0 = big_first ? eb : es;
+    const float t1 = big_first ? ts : tb, e1 = big_first ? es : eb;
     s.a_lo = t0 - e0;
     s.a_hi = t0 + e0;
     s.b_lo = t1 - e1;
@@ -340,7 +350,8 @@ leaf_span(int type, const float4 lo, const float4 hi, const FrameF &f, SpanF &s)
  * FP32 filter twin of trace_shadow (frt_device.cuh).  `w` is the world frame of the ray (frame_finish'ed by the
  * caller), omax / eo_w / ed_w its error terms, [D_lo, D_hi] the interval of the light distance; `fnodes` is the
  * node mirror (in shared memory when the tree is small).
- * Returns FRT_SH_LIT, FRT_SH_SHADOWED or FRT_SH_UNDECIDED.
+ * Returns FRT_SH_LIT, FRT_SH_SHADOWED or FRT_SH_UNDECIDED (the latter with a reason code in bits 4.. for the counting
+ * build's histogram; callers mask with 15).
  */
 template <bool COUNT>
 __device__ __forceinline__ int
@@ -393,7 +404,7 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
             } else {
                 if (type == FRT_CSG) {
                     if (sp == FRT_CSG_DEPTH) {
-                        return FRT_SH_UNDECIDED;
+                        return FRT_SH_UNDECIDED | (1 << 4);
                     }
                     Frame &f = st[sp++];
                     f.op = (flags >> FRT_FN_OP_SHIFT) & 3;
@@ -404,19 +415,19 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
                     f.left.flags = 0;
                     cur.flags = 0;
                 } else if (sp > 0) {
-                    return FRT_SH_UNDECIDED; /* a group inside a CSG operand: several spans */
+                    return FRT_SH_UNDECIDED | (2 << 4); /* a group inside a CSG operand: several spans */
                 }
                 i = i + 1;
             }
         } else {
             if (!(flags & FRT_FN_FAST)) {
-                return FRT_SH_UNDECIDED;
+                return FRT_SH_UNDECIDED | (3 << 4);
             }
             SpanF s;
             bool ok = true;
             if (type == FRT_PLANE) { /* plane_local_intersect, plane.c:11-25: one crossing; stands alone or undecided */
                 if (sp > 0) {
-                    return FRT_SH_UNDECIDED;
+                    return FRT_SH_UNDECIDED | (4 << 4);
                 }
                 const float tt = -cf.oy * cf.iy;
                 const float E = fmaf(fabsf(tt), cf.c2y, cf.c1y);
@@ -427,7 +438,7 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
                 ok = leaf_span(type, lo, hi, cf, s);
             }
             if (!ok) {
-                return FRT_SH_UNDECIDED;
+                return FRT_SH_UNDECIDED | (5 << 4) | (i << 8);
             }
             if (s.flags && (flags & FRT_FN_CASTS)) {
                 s.flags |= 6;
@@ -436,7 +447,7 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
                 if (s.flags) {
                     const int v = judge_span(s, D_lo, D_hi);
                     if (v == 3) {
-                        return FRT_SH_UNDECIDED;
+                        return FRT_SH_UNDECIDED | (6 << 4) | (i << 8);
                     }
                     if (v != 0) {
                         verdict = (v == 2) ? FRT_SH_SHADOWED : FRT_SH_LIT;
@@ -445,7 +456,7 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
                 }
             } else if (s.flags) {
                 if (cur.flags) {
-                    return FRT_SH_UNDECIDED; /* two spans in one operand */
+                    return FRT_SH_UNDECIDED | (7 << 4); /* two spans in one operand */
                 }
                 cur = s;
             }
@@ -466,7 +477,7 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
             SpanF res;
             res.a_lo = res.a_hi = res.b_lo = res.b_hi = 0.0f;
             if (!csg_combine(f.op, f.left, cur, res)) {
-                return FRT_SH_UNDECIDED;
+                return FRT_SH_UNDECIDED | (8 << 4);
             }
             --sp;
             cur = res; /* becomes the enclosing CSG's current operand, or the list to judge */
@@ -475,7 +486,7 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
                 if (res.flags) {
                     const int v = judge_span(res, D_lo, D_hi);
                     if (v == 3) {
-                        return FRT_SH_UNDECIDED;
+                        return FRT_SH_UNDECIDED | (9 << 4);
                     }
                     if (v != 0) {
                         verdict = (v == 2) ? FRT_SH_SHADOWED : FRT_SH_LIT;

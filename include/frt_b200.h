@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FRT_ABI_VERSION 5
+#define FRT_ABI_VERSION 6
 
 enum frt_status {
     FRT_OK = 0,
@@ -230,6 +230,9 @@ typedef struct frt_stats {
                                 with the cost table of BASELINE.md section 4 (ray transform 33, bbox slab 16, sphere 28, ...) */
     uint64_t shadow_deferred;/* shadow rays the FP32 filter pass left undecided and the FP64 pass re-traced */
     uint64_t shadow_mismatch;/* FRT_FLAG_VERIFY_F32: FP32-decided rays whose FP64 answer differs */
+    uint64_t shadow_reasons[10]; /* FRT_FLAG_COUNT_RAYS: deferred rays by reason: 1 CSG depth, 2 group inside a CSG operand,
+                                3 primitive type without a fast form, 4 plane inside a CSG, 5 leaf hit/miss not separable,
+                                6 leaf verdict, 7 two spans in one operand, 8 CSG ordering / two-span result, 9 CSG verdict */
     int32_t rows_rendered;
     int32_t pad;
 } frt_stats;

@@ -27,4 +27,4 @@ with frt.Scene(desc) as sc:
             tot = st.rays_total
             print(f"flags={flags} frame_ms={st.frame_ms:.2f} light_ms={st.light_ms:.2f} wall_ms={wall*1e3:.1f} launches={st.kernel_launches} "
                   f"rays p/s/sh={st.rays_primary}/{st.rays_secondary}/{st.rays_shadow} Mrays/s={tot/st.frame_ms/1e3:.1f} "
-                  f"hits={st.hits_shaded} nodes/shadowray={st.shadow_nodes/max(st.rays_shadow,1):.2f} deferred={st.shadow_deferred} mismatch={st.shadow_mismatch}")
+                  f"hits={st.hits_shaded} nodes/shadowray={st.shadow_nodes/max(st.rays_shadow,1):.2f} deferred={st.shadow_deferred} mismatch={st.shadow_mismatch} reasons={st.extra.get('shadow_reasons')}")
