@@ -182,7 +182,8 @@ def build_objects(force=False):
         run(["gcc", *CFLAGS, "-I", str(REF), "-I", str(REPO / "oracle" / "png_stub"), "-c", str(hsrc), "-o", str(hooks)])
     shim = OBJ / "frt_shim.o"
     ssrc = LIBDIR / "csrc" / "frt_shim.c"
-    if force or not shim.exists() or shim.stat().st_mtime < ssrc.stat().st_mtime:
+    abi = REPO / "include" / "frt_b200.h"  # the shim embeds FRT_ABI_VERSION and the struct layouts
+    if force or not shim.exists() or shim.stat().st_mtime < max(ssrc.stat().st_mtime, abi.stat().st_mtime):
         run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-Wall", "-I", str(REF), "-I", str(REPO / "include"),
              "-I", str(REPO / "oracle" / "png_stub"), "-c", str(ssrc), "-o", str(shim)])
 
