@@ -99,7 +99,7 @@ __wrap_trace_photons(const World w, const size_t num_maps, bool populate_caustic
     }
     double t0 = now_seconds();
     __real_trace_photons(w, num_maps, populate_caustic, populate_global);
-    printf("FRT_PHOTON_SECONDS %.6f\n", now_seconds() - t0);
+    printf("\nFRT_PHOTON_SECONDS %.6f\n", now_seconds() - t0); /* main() printed "Tracing photons..." without a newline */
     fflush(stdout);
 }
 
