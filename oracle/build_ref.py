@@ -106,6 +106,15 @@ def edit_images(tree):
     return tree
 
 
+def edit_dof(tree):
+    for obj in tree:
+        if isinstance(obj, dict) and obj.get("add") == "camera":
+            obj["aperture"] = {"jitter": True, "size": 0.06, "type": ["CIRCULAR_APERTURE", 1.0]}
+            obj["usteps"] = 4
+            obj["vsteps"] = 4
+    return tree
+
+
 def edit_none(tree):
     return tree
 
@@ -140,6 +149,10 @@ SCENES = {
     "align_check_plane": ("scenes/align_check_plane/align_check_plane.yml", edit_none),
     "lens_test": ("scenes/lens_test/lens_test.yml", edit_none),
     "shadow_glamour_shot": ("scenes/shadow_glamour_shot/shadow_glamour_shot.yml", lambda t: _cache_size(t, 1)),
+    # a scene of this repository: Perlin-perturbed / blended / nested / gradient patterns, cone, cylinder, circular area light
+    "patterns_circle_light": (str(REPO / "oracle" / "scenes" / "patterns_circle_light.yml"), edit_none),
+    # focal blur + jittered CMJ (stochastic in the reference: drand48): dof.yml with a circular aperture switched on
+    "dof_blur": ("scenes/dof_test/dof.yml", lambda t: edit_dof(t)),
     # image textures (Ka / Kd / bump maps through planar and spherical uv maps)
     "bump_map_test": ("scenes/bump_map_test/bump_map_test.yml", edit_images),
     "texture_map_test": ("scenes/texture_map_test/texture_map_test.yml", edit_images),

@@ -44,6 +44,8 @@ GOLDEN = {
     "shadow_glamour_shot": ("shadow_glamour_shot", 300, 120, 0, 0),
     "teapot": ("teapot", 200, 200, 0, 0),
     "bump_map_test": ("bump_map_test", 200, 200, 0, 0),
+    "patterns_circle_light": ("patterns_circle_light", 0, 0, 0, 0),
+    "dof_blur_240": ("dof_blur", 240, 120, 0, 0),
     "bounding_boxes_600": ("bounding_boxes", 600, 240, 0, 0),  # C3b: 6 x dragon.obj (141 K triangles, ~31 K groups)
     "texture_map_test": ("texture_map_test", 200, 200, 0, 0),
     # photon-mapped: stochastic in the reference too, so two reference renders (seeds 1 and 2) are stored; their RMSE is
@@ -51,7 +53,7 @@ GOLDEN = {
     "cornell_gi_64": ("cornell_gi", 64, 64, 2, 2),
     "cornell_gi_caustics_48": ("cornell_gi_caustics", 48, 48, 1, 1),
 }
-STOCHASTIC = {"cornell_gi_64", "cornell_gi_caustics_48"}
+STOCHASTIC = {"cornell_gi_64", "cornell_gi_caustics_48", "dof_blur_240"}
 # fixtures whose scene blob is too large to commit (6 dragons = 52 MB): only the reference canvas is stored; the GPU test
 # renders oracle/_ref/blobs/<scene>.frt, which travels to the GPU box with the snapshot
 BLOB_STAYS_IN_REF = {"bounding_boxes_600"}

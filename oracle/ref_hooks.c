@@ -137,6 +137,10 @@ __wrap_render_multi(Camera cam, World w, size_t usteps, size_t vsteps, bool jitt
     }
 
     memset(frt_ray_slots, 0, sizeof(frt_ray_slots));
+    if (env_long("FRT_REF_SEED", -1) >= 0) { /* per-pixel CMJ jitter, aperture sampling and sample-set picks draw from these */
+        srand48(env_long("FRT_REF_SEED", 0) + 17);
+        srand((unsigned int)env_long("FRT_REF_SEED", 0) + 17u);
+    }
     double t0 = now_seconds();
     Canvas c = __real_render_multi(cam, w, usteps, vsteps, jitter);
     double t1 = now_seconds();

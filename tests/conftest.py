@@ -22,7 +22,7 @@ def frt():
     return frt
 
 
-STOCHASTIC = ("cornell_gi",)  # photon-mapped fixtures: two reference renders each, compared statistically (test_gpu_gi.py)
+STOCHASTIC = ("cornell_gi", "dof_blur")  # photon-mapped fixtures: two reference renders each, compared statistically (test_gpu_gi.py)
 
 
 def golden_names():

@@ -109,3 +109,27 @@ def test_gi_without_photon_maps_fails_loudly(frt):
     with frt.Scene(desc) as sc:
         with pytest.raises(frt.FrtError, match="photon map"):
             sc.render()
+
+
+def test_focal_blur_and_jittered_cmj_match_the_reference_statistically(frt):
+    """dof.yml with its circular aperture switched on (size 0.06) and `aperture.jitter: true`: primary rays use a per-pixel
+    jittered CMJ table and rejection-sampled lens points (camera.c:12-90), both drawn from drand48 in the reference and
+    from the counter-based stream here, so the comparison is statistical like the photon-mapped scenes."""
+    z = np.load(GOLDEN / "dof_blur_240.npz")
+    ref_a, ref_b = z["rgb"].astype(np.float64), z["rgb_b"].astype(np.float64)
+    desc = frt.SceneDesc.load(GOLDEN / "dof_blur_240.frt")
+    assert desc.camera.aperture_jitter == 1 and desc.camera.aperture_size > 0
+    canvas, stats = frt.render_multi(desc, seed=5)
+    img = canvas[..., :3]
+    assert rmse_lsb(img, ref_a) <= 1.25 * rmse_lsb(ref_a, ref_b), (rmse_lsb(img, ref_a), rmse_lsb(ref_a, ref_b))
+    # clip before averaging: the scene has emitters of radiance > 100, and clip(mean) != mean(clip)
+    bm = block_means(np.clip(img, 0, 1))
+    br = 0.5 * (block_means(np.clip(ref_a, 0, 1)) + block_means(np.clip(ref_b, 0, 1)))
+    ours_b = float(np.sqrt(((bm - br) ** 2).mean()))
+    noise_b = float(np.sqrt(((block_means(np.clip(ref_a, 0, 1)) - block_means(np.clip(ref_b, 0, 1))) ** 2).mean()))
+    assert ours_b <= 1.25 * noise_b, (ours_b, noise_b)
+    # a different seed gives a different frame (the jitter is live), the same seed the same frame
+    again, _ = frt.render_multi(desc, seed=5)
+    other, _ = frt.render_multi(desc, seed=6)
+    assert np.allclose(again, canvas, rtol=0, atol=1e-12)
+    assert not np.allclose(other, canvas, rtol=0, atol=1e-6)
