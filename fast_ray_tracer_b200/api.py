@@ -19,6 +19,7 @@ FRT_FLAG_COUNT_RAYS = 2
 FRT_FLAG_F64_SHADING = 4
 FRT_FLAG_F64_SHADOW = 8
 FRT_FLAG_VERIFY_F32 = 16
+FRT_FLAG_NO_SHAFT = 32
 
 
 class FrtError(RuntimeError):

@@ -603,7 +603,7 @@ struct LightTmp { /* per shaded hit, per light launch; the first 16 bytes are al
     int unshadowed;               /* shadow rays that reached the light */
     double dsum_ndl, dsum_b, dsum_fb; /* the same sums in FP64 (FRT_FLAG_F64_SHADING) */
     int contributes;              /* some lighting term of the hit is non-zero */
-    int pad;
+    unsigned int relevant;        /* shaft culling: bit i = node i may be crossed at t > 0 by a shadow ray of this hit */
 };
 
 /*
@@ -616,7 +616,7 @@ struct LightTmp { /* per shaded hit, per light launch; the first 16 bytes are al
 template <typename T, int G>
 __global__ void __launch_bounds__(256)
 k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, const Counters *cnt,
-            int level, int light_idx, const float *__restrict__ flpoints)
+            int level, int light_idx, const float *__restrict__ flpoints, DSceneF SF, int shaft_on)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
     const frt_light L = S.lights[light_idx];
@@ -701,6 +701,26 @@ k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
             sum_b += __shfl_xor_sync(gmask, sum_b, o);
             sum_fb += __shfl_xor_sync(gmask, sum_fb, o);
         }
+        /* shaft culling mask of this hit (frt_shadow_f32.cuh): the G lanes share the nodes */
+        unsigned int relevant = 0xffffffffu;
+        if (shaft_on) {
+            relevant = 0u;
+            const float ofx = (float)over[0], ofy = (float)over[1], ofz = (float)over[2];
+            ShaftF sh;
+            shaft_setup(sh, SF.shaft + 4 * light_idx, ofx, ofy, ofz);
+            const int nn = min(SF.n_nodes, 32);
+            for (int k = lane_g; k < nn; k += G) {
+                if (!shaft_misses_box(sh, __ldg(SF.wbox + 2 * k), __ldg(SF.wbox + 2 * k + 1), ofx, ofy, ofz)) {
+                    relevant |= 1u << k;
+                }
+            }
+            for (int o = G / 2; o > 0; o >>= 1) {
+                relevant |= __shfl_xor_sync(gmask, relevant, o);
+            }
+            if (nn < 32) {
+                relevant |= ~((1u << nn) - 1u);
+            }
+        }
         if (live && lane_g == 0) {
             /* when every lighting term is exactly zero the visibility fraction cannot matter: no shadow rays */
             const bool contributes = (sum_ndl != 0) || (sum_b != 0) || (sum_fb != 0);
@@ -714,7 +734,7 @@ k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
             t.set_a = (contributes || (F.flags & FRT_FLAG_NO_PRUNE)) ? set_a : -1;
             t.unshadowed = 0;
             t.contributes = contributes ? 1 : 0;
-            t.pad = 0;
+            t.relevant = relevant;
             t.ox = (float)over[0];
             t.oy = (float)over[1];
             t.oz = (float)over[2];
@@ -805,6 +825,7 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
             head = *reinterpret_cast<const float4 *>(tmp + h);
         }
         const int set_a = __float_as_int(head.w);
+        const unsigned int relevant = set_a >= 0 ? tmp[h].relevant : 0u;
         int res = FRT_SH_SHADOWED;
         if (set_a >= 0) {
             if (S.n_roots != 1) {
@@ -831,7 +852,7 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                 const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G);
                 frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
                 const float Df = len2 * rinv;
-                res = trace_shadow_f32<COUNT>(SF, fnodes, root, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
+                res = trace_shadow_f32<COUNT>(SF, fnodes, root, relevant, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
                 if (COUNT && (res >> 4)) {
                     atomicAdd(&cnt->undecided_reason[min((res >> 4) & 15, 9)], 1ull);
                     atomicAdd(&cnt->undecided_node[(res >> 8) & 31], 1ull);
@@ -1065,6 +1086,7 @@ struct frt_scene {
     DCamera C{};
     frt_config cfg{};
     std::vector<void *> allocs;
+    std::vector<int> light_gw;
     double *canvas = nullptr;     /* hsize*vsize*4 doubles */
     double *samples = nullptr;
     int samples_u = 0, samples_v = 0;
@@ -1271,6 +1293,7 @@ cmj_table_no_jitter(int s0, int s1, std::vector<double> &arr)
 }
 
 static void pm_free(frt_scene *sc);
+static int pick_group_width(int num_samples);
 static int ensure_gi_buffers(frt_scene *sc);
 
 extern "C" void
@@ -1322,7 +1345,8 @@ frt_scene_destroy(frt_scene *sc)
 static int
 build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
 {
-    std::vector<float4> fx((size_t)4 * d->n_xforms), fn((size_t)3 * d->n_nodes);
+    std::vector<float4> fx((size_t)4 * d->n_xforms), fn((size_t)3 * d->n_nodes), wb((size_t)2 * d->n_nodes);
+    std::vector<float4> shaft((size_t)4 * std::max(d->n_lights, 1));
     std::vector<int> aligned(d->n_xforms, 0), perm((size_t)3 * d->n_xforms, 0);
     for (int i = 0; i < d->n_xforms; ++i) {
         const double *m = d->xforms[i].inv;
@@ -1398,6 +1422,92 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
                 }
             }
         }
+        /* world-space box of the node for shaft culling: the node's local bounds (leaf: by type) through the forward matrix */
+        {
+            double blo[3], bhi[3];
+            bool finite = true;
+            if (inner) {
+                for (int k = 0; k < 3; ++k) {
+                    blo[k] = n.bbox_min[k];
+                    bhi[k] = n.bbox_max[k];
+                }
+            } else {
+                const double *prm = d->prim_params + (n.param < 0 ? 0 : n.param);
+                for (int k = 0; k < 3; ++k) {
+                    blo[k] = -1.0;
+                    bhi[k] = 1.0;
+                }
+                switch (n.type) {
+                case FRT_PLANE:
+                    finite = false;
+                    break;
+                case FRT_CYLINDER:
+                    blo[1] = prm[0];
+                    bhi[1] = prm[1];
+                    break;
+                case FRT_CONE: {
+                    blo[1] = prm[0];
+                    bhi[1] = prm[1];
+                    double r = std::max(fabs(prm[0]), fabs(prm[1]));
+                    blo[0] = blo[2] = -r;
+                    bhi[0] = bhi[2] = r;
+                    break;
+                }
+                case FRT_TOROID:
+                    blo[0] = blo[2] = -(fabs(prm[0]) + fabs(prm[1]));
+                    bhi[0] = bhi[2] = fabs(prm[0]) + fabs(prm[1]);
+                    blo[1] = -fabs(prm[1]);
+                    bhi[1] = fabs(prm[1]);
+                    break;
+                case FRT_TRIANGLE:
+                case FRT_SMOOTH_TRIANGLE:
+                    for (int k = 0; k < 3; ++k) {
+                        blo[k] = std::min(prm[k], std::min(prm[3 + k], prm[6 + k]));
+                        bhi[k] = std::max(prm[k], std::max(prm[3 + k], prm[6 + k]));
+                    }
+                    break;
+                default:
+                    break;
+                }
+            }
+            for (int k = 0; k < 3; ++k) {
+                finite = finite && std::isfinite(blo[k]) && std::isfinite(bhi[k]);
+            }
+            double wlo[3] = { -INFINITY, -INFINITY, -INFINITY }, whi[3] = { INFINITY, INFINITY, INFINITY };
+            if (finite) {
+                const double *m = d->xforms[n.xform].inv;
+                double a[9] = { m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10] };
+                double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+                if (std::isfinite(det) && fabs(det) > 1e-300) {
+                    double fi[9] = { (a[4] * a[8] - a[5] * a[7]) / det, (a[2] * a[7] - a[1] * a[8]) / det, (a[1] * a[5] - a[2] * a[4]) / det,
+                                     (a[5] * a[6] - a[3] * a[8]) / det, (a[0] * a[8] - a[2] * a[6]) / det, (a[2] * a[3] - a[0] * a[5]) / det,
+                                     (a[3] * a[7] - a[4] * a[6]) / det, (a[1] * a[6] - a[0] * a[7]) / det, (a[0] * a[4] - a[1] * a[3]) / det };
+                    /* local = M w + T  =>  w = M^-1 (local - T): centre and half extent of the box's image */
+                    double cl[3], hl[3];
+                    for (int k = 0; k < 3; ++k) {
+                        cl[k] = 0.5 * (blo[k] + bhi[k]) - m[4 * k + 3];
+                        hl[k] = 0.5 * (bhi[k] - blo[k]);
+                    }
+                    bool ok = true;
+                    for (int k = 0; k < 3; ++k) {
+                        double c = fi[3 * k] * cl[0] + fi[3 * k + 1] * cl[1] + fi[3 * k + 2] * cl[2];
+                        double e = fabs(fi[3 * k]) * hl[0] + fabs(fi[3 * k + 1]) * hl[1] + fabs(fi[3 * k + 2]) * hl[2];
+                        e = e * (1.0 + 1e-9) + 1e-9 * (fabs(c) + 1.0); /* slack for the FP64 rounding of this inverse */
+                        wlo[k] = c - e;
+                        whi[k] = c + e;
+                        ok = ok && std::isfinite(wlo[k]) && std::isfinite(whi[k]);
+                    }
+                    if (!ok) {
+                        for (int k = 0; k < 3; ++k) {
+                            wlo[k] = -INFINITY;
+                            whi[k] = INFINITY;
+                        }
+                    }
+                }
+            }
+            wb[2 * i] = make_float4(down(wlo[0]), down(wlo[1]), down(wlo[2]), 0.f);
+            wb[2 * i + 1] = make_float4(up(whi[0]), up(whi[1]), up(whi[2]), 0.f);
+        }
         float4 q0;
         q0.x = __int_as_float_host(flags);
         q0.y = __int_as_float_host(n.skip);
@@ -1412,7 +1522,56 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
             fn[3 * i + 2] = make_float4((float)hi[0], (float)hi[1], (float)hi[2], 0.f);
         }
     }
+    /* per light: a parallelogram that contains every surface sample (light.c:100-191), slightly inflated */
+    for (int li = 0; li < d->n_lights; ++li) {
+        const frt_light &L = d->lights[li];
+        double c[4][3];
+        if (L.type == 0) { /* area light: corner + s uvec*usteps + t vvec*vsteps, s, t in [0, 1] */
+            for (int k = 0; k < 3; ++k) {
+                const double U = L.uvec[k] * L.usteps, V = L.vvec[k] * L.vsteps;
+                const double o = L.position[k] - 1e-6 * (U + V);
+                c[0][k] = o;
+                c[1][k] = o + U * (1.0 + 2e-6);
+                c[2][k] = o + (U + V) * (1.0 + 2e-6);
+                c[3][k] = o + V * (1.0 + 2e-6);
+            }
+        } else if (L.type == 1) { /* circle light: the square around the disc, in any basis of its plane */
+            double nrm[3] = { L.normal[0], L.normal[1], L.normal[2] };
+            double len = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+            double t1[3] = { 1, 0, 0 };
+            if (len > 0) {
+                for (int k = 0; k < 3; ++k) nrm[k] /= len;
+            }
+            if (fabs(nrm[0]) > 0.9) {
+                t1[0] = 0;
+                t1[1] = 1;
+            }
+            double dt = t1[0] * nrm[0] + t1[1] * nrm[1] + t1[2] * nrm[2];
+            for (int k = 0; k < 3; ++k) t1[k] -= dt * nrm[k];
+            len = sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+            for (int k = 0; k < 3; ++k) t1[k] /= len;
+            double t2[3] = { nrm[1] * t1[2] - nrm[2] * t1[1], nrm[2] * t1[0] - nrm[0] * t1[2], nrm[0] * t1[1] - nrm[1] * t1[0] };
+            const double r = fabs(L.radius) * (1.0 + 1e-6) * 1.0000001;
+            const double sgn[4][2] = { { -1, -1 }, { 1, -1 }, { 1, 1 }, { -1, 1 } };
+            for (int q = 0; q < 4; ++q) {
+                for (int k = 0; k < 3; ++k) {
+                    c[q][k] = L.position[k] + r * (sgn[q][0] * t1[k] + sgn[q][1] * t2[k]);
+                }
+            }
+        } else { /* point / hemisphere light: a single point */
+            for (int q = 0; q < 4; ++q) {
+                for (int k = 0; k < 3; ++k) c[q][k] = L.position[k];
+            }
+        }
+        for (int q = 0; q < 4; ++q) {
+            shaft[4 * li + q] = make_float4((float)c[q][0], (float)c[q][1], (float)c[q][2], 0.f);
+        }
+    }
     int rc = upload(sc, fx.data(), fx.size(), &sc->SF.fx);
+    if (rc != FRT_OK) return rc;
+    rc = upload(sc, wb.data(), wb.size(), &sc->SF.wbox);
+    if (rc != FRT_OK) return rc;
+    rc = upload(sc, shaft.data(), shaft.size(), &sc->SF.shaft);
     if (rc != FRT_OK) return rc;
     rc = upload(sc, fn.data(), fn.size(), &sc->SF.fnodes);
     if (rc != FRT_OK) return rc;
@@ -1522,6 +1681,10 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
     C.samples = dtab;
 
     sc->cfg = d->config;
+    sc->light_gw.resize(d->n_lights);
+    for (int i = 0; i < d->n_lights; ++i) {
+        sc->light_gw[i] = pick_group_width(d->lights[i].num_samples);
+    }
 
     size_t cbytes = (size_t)c.hsize * c.vsize * 4 * sizeof(double);
     void *cv = nullptr;
@@ -1645,7 +1808,8 @@ template <typename T>
 static void
 launch_light_sum(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g)
 {
-#define LS(G) k_light_sum<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, light, sc->SF.lpoints)
+#define LS(G) k_light_sum<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, light, sc->SF.lpoints, sc->SF, \
+                                                               sc->S.n_roots == 1 && !(F.flags & (FRT_FLAG_F64_SHADOW | FRT_FLAG_NO_SHAFT)))
     switch (g) {
     case 1: LS(1); break;
     case 2: LS(2); break;
@@ -1809,16 +1973,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     CK(cudaEventRecord(sc->ev[0], s));
     CK(cudaMemsetAsync(sc->canvas, 0, cbytes, s));
 
-    std::vector<int> gw(sc->S.n_lights);
-    {
-        std::vector<frt_light> hl(sc->S.n_lights);
-        if (sc->S.n_lights) {
-            CK(cudaMemcpy(hl.data(), sc->S.lights, sizeof(frt_light) * hl.size(), cudaMemcpyDeviceToHost));
-        }
-        for (size_t i = 0; i < hl.size(); ++i) {
-            gw[i] = pick_group_width(hl[i].num_samples);
-        }
-    }
+    const std::vector<int> &gw = sc->light_gw; /* lanes per hit in k_light_sum, chosen per light at upload */
 
     for (unsigned long long first = 0; first < total; first += chunk) {
         unsigned int n = (unsigned int)std::min<unsigned long long>(chunk, total - first);

@@ -61,9 +61,99 @@ struct DSceneF {
     const float4 *fnodes; /* per node: {flags, skip, xform, right (CSG)} as int bits, {lo.xyz, 0}, {hi.xyz, 0} */
     const float4 *fx;     /* per xform: rows 0..2 of the world->local matrix, then {R_0, R_1, R_2, 0} */
     const float *lpoints; /* FP32 copy of the light sample points, 3 per point */
+    const float4 *wbox;   /* per node: WORLD-space bounding box {min.xyz, 0} {max.xyz, 0}, rounded outward (shaft culling) */
+    const float4 *shaft;  /* per light: 4 corners of a parallelogram that contains every surface sample of the light */
     float bmax;           /* largest finite |bound| of a WORLD node */
     int n_nodes;
 };
+
+/*
+ * Shaft culling.  All shadow rays of one hit start at the same point o and aim at points of the light's parallelogram
+ * P, so they lie in the pyramid { o + t (p - o) : p in P, t > 0 }.  A node whose world-space box is separated from
+ * that pyramid by a plane cannot be crossed at t > 0 by any of them, and a subtree without a positive crossing neither
+ * stops the reference's search nor shadows (group.c:105-123): it is skipped for every ray of the hit.  The test is
+ * one-sided (a box that is not provably outside stays), per hit, ~60 flop per node; it runs once per hit in
+ * k_light_sum and leaves a bit mask over the first 32 nodes.  Separating planes tried: the pyramid's four sides, the
+ * plane through o facing the light (when every corner is in front of it), and the box's own six faces.
+ */
+struct ShaftF {
+    float d[4][3]; /* corner - o */
+    float n[4][3]; /* inward side normals: n_i = +-(d_i x d_{i+1}) */
+    float ax[3];   /* sum of the corner directions (the axis) */
+    bool axis_ok;  /* every corner direction has a positive component along the axis */
+    float dmin[3], dmax[3];
+    float scale;   /* magnitude for the tolerance */
+};
+
+__device__ __forceinline__ void
+shaft_setup(ShaftF &s, const float4 *corners, float ox, float oy, float oz)
+{
+    float m = 0.f;
+    for (int i = 0; i < 4; ++i) {
+        const float4 c = __ldg(corners + i);
+        s.d[i][0] = c.x - ox;
+        s.d[i][1] = c.y - oy;
+        s.d[i][2] = c.z - oz;
+        m = fmaxf(m, fmaxf(fabsf(s.d[i][0]), fmaxf(fabsf(s.d[i][1]), fabsf(s.d[i][2]))));
+    }
+    for (int k = 0; k < 3; ++k) {
+        s.ax[k] = s.d[0][k] + s.d[1][k] + s.d[2][k] + s.d[3][k];
+        s.dmin[k] = fminf(fminf(s.d[0][k], s.d[1][k]), fminf(s.d[2][k], s.d[3][k]));
+        s.dmax[k] = fmaxf(fmaxf(s.d[0][k], s.d[1][k]), fmaxf(s.d[2][k], s.d[3][k]));
+    }
+    s.axis_ok = true;
+    for (int i = 0; i < 4; ++i) {
+        const float *a = s.d[i], *b = s.d[(i + 1) & 3];
+        float nx = a[1] * b[2] - a[2] * b[1], ny = a[2] * b[0] - a[0] * b[2], nz = a[0] * b[1] - a[1] * b[0];
+        /* orient towards the inside: the opposite corner lies inside */
+        const float *c = s.d[(i + 2) & 3];
+        const float side = nx * c[0] + ny * c[1] + nz * c[2];
+        /* an origin (almost) in the light's plane leaves the orientation undecided: drop the plane */
+        const float nn = fabsf(nx) + fabsf(ny) + fabsf(nz), cc = fabsf(c[0]) + fabsf(c[1]) + fabsf(c[2]);
+        const float sg = fabsf(side) <= 1e-4f * nn * cc ? 0.f : (side < 0.f ? -1.f : 1.f);
+        s.n[i][0] = nx * sg;
+        s.n[i][1] = ny * sg;
+        s.n[i][2] = nz * sg;
+        s.axis_ok = s.axis_ok && (a[0] * s.ax[0] + a[1] * s.ax[1] + a[2] * s.ax[2] > 0.f);
+    }
+    s.scale = m;
+}
+
+/* true when the box [lo, hi] (world space) is provably outside the pyramid */
+__device__ __forceinline__ bool
+shaft_misses_box(const ShaftF &s, const float4 lo, const float4 hi, float ox, float oy, float oz)
+{
+    const float l[3] = { lo.x - ox, lo.y - oy, lo.z - oz }, h[3] = { hi.x - ox, hi.y - oy, hi.z - oz };
+    float ext = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        ext = fmaxf(ext, fmaxf(fabsf(l[k]), fabsf(h[k])));
+    }
+    if (!(ext < 3.0e38f)) {
+        return false; /* unbounded box */
+    }
+    /* tolerance: FP32 evaluation of products of magnitude scale^2 * ext, and the corners carry the jitter's rounding */
+    const float tol1 = 1e-5f * s.scale * s.scale * ext + 1e-30f;
+    for (int i = 0; i < 4; ++i) { /* farthest box corner along the inward normal still outside? */
+        const float v = fmaxf(s.n[i][0] * l[0], s.n[i][0] * h[0]) + fmaxf(s.n[i][1] * l[1], s.n[i][1] * h[1]) +
+                        fmaxf(s.n[i][2] * l[2], s.n[i][2] * h[2]);
+        if (v < -tol1) {
+            return true;
+        }
+    }
+    if (s.axis_ok) {
+        const float v = fmaxf(s.ax[0] * l[0], s.ax[0] * h[0]) + fmaxf(s.ax[1] * l[1], s.ax[1] * h[1]) + fmaxf(s.ax[2] * l[2], s.ax[2] * h[2]);
+        if (v < -1e-5f * s.scale * ext) {
+            return true; /* wholly behind the origin */
+        }
+    }
+    const float tol2 = 1e-6f * (ext + s.scale);
+    for (int k = 0; k < 3; ++k) { /* the box's own faces: origin beyond a face and no ray heading back towards it */
+        if ((l[k] > tol2 && s.dmax[k] <= 0.f) || (h[k] < -tol2 && s.dmin[k] >= 0.f)) {
+            return true;
+        }
+    }
+    return false;
+}
 
 /* a ray in some frame, ready for slab tests */
 struct FrameF {
@@ -349,14 +439,14 @@ leaf_span(int type, const float4 lo, const float4 hi, const FrameF &f, SpanF &s)
 /*
  * FP32 filter twin of trace_shadow (frt_device.cuh).  `w` is the world frame of the ray (frame_finish'ed by the
  * caller), omax / eo_w / ed_w its error terms, [D_lo, D_hi] the interval of the light distance; `fnodes` is the
- * node mirror (in shared memory when the tree is small).
+ * node mirror (in shared memory when the tree is small), `relevant` the hit's shaft-culling mask over nodes 0..31.
  * Returns FRT_SH_LIT, FRT_SH_SHADOWED or FRT_SH_UNDECIDED (the latter with a reason code in bits 4.. for the counting
  * build's histogram; callers mask with 15).
  */
 template <bool COUNT>
 __device__ __forceinline__ int
-trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF &w, float omax, float eo_w, float ed_w, float D_lo,
-                 float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
+trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int relevant, const FrameF &w, float omax, float eo_w,
+                 float ed_w, float D_lo, float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
 {
     struct Frame { /* an open CSG node: its operator, where its right operand starts and ends, its left result */
         int op, right, skip, have_left;
@@ -375,6 +465,12 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, const FrameF
     int verdict = FRT_SH_LIT;
 
     while (i < end) {
+        if (sp == 0 && i < 32 && !((relevant >> i) & 1u)) {
+            /* shaft culling (see ShaftF): no ray of this hit can cross this subtree at t > 0.  Never inside a CSG, whose
+             * operands' negative crossings still toggle the filter state. */
+            i = __float_as_int(fnodes[3 * i].y);
+            continue;
+        }
         const float4 q0 = fnodes[3 * i], lo = fnodes[3 * i + 1], hi = fnodes[3 * i + 2];
         const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y), xf = __float_as_int(q0.z);
         const int type = flags & FRT_FN_TYPE_MASK;

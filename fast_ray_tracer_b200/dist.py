@@ -20,29 +20,53 @@ def owned_rows(vsize: int, rank: int, world: int, rows_per_block: int = 4) -> np
     return y[(y // rows_per_block) % world == rank].astype(np.int32)
 
 
+_ROW_CACHE = {}
+
+
+def _row_plan(vsize: int, world: int, rows_per_block: int, device):
+    """Per (frame height, world, block size, device): every rank's row count and row-index tensor, built once."""
+    key = (vsize, world, rows_per_block, str(device))
+    plan = _ROW_CACHE.get(key)
+    if plan is None:
+        rows = [owned_rows(vsize, r, world, rows_per_block) for r in range(world)]
+        counts = [len(x) for x in rows]
+        # position of every frame row inside the concatenation of the ranks' padded blocks
+        pad = max(counts)
+        src = np.empty(vsize, dtype=np.int64)
+        for r in range(world):
+            src[rows[r]] = r * pad + np.arange(counts[r])
+        plan = {"counts": counts, "pad": pad, "src": torch.as_tensor(src, device=device)}
+        _ROW_CACHE[key] = plan
+    return plan
+
+
 def gather_rows(local_rows: torch.Tensor, vsize: int, rank: int, world: int, rows_per_block: int = 4,
                 group=None) -> Optional[torch.Tensor]:
-    """Gather every rank's packed rows [n_owned, hsize, 4] to rank 0 and scatter them into a full canvas.
+    """Gather every rank's packed rows [n_owned, hsize, 4] to rank 0 and put them back in frame order.
 
-    Returns the [vsize, hsize, 4] canvas on rank 0, None elsewhere.
+    Returns the [vsize, hsize, 4] canvas on rank 0, None elsewhere.  One collective (gather to rank 0), then one
+    index_select on rank 0; the row bookkeeping is cached.
     """
     hsize = local_rows.shape[1]
-    counts = [len(owned_rows(vsize, r, world, rows_per_block)) for r in range(world)]
-    assert local_rows.shape[0] == counts[rank]
     if world == 1:
         return local_rows
-    pad = max(counts)
-    buf = torch.zeros((pad, hsize, 4), dtype=local_rows.dtype, device=local_rows.device)
-    buf[: counts[rank]] = local_rows
-    parts = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    plan = _row_plan(vsize, world, rows_per_block, local_rows.device)
+    counts, pad = plan["counts"], plan["pad"]
+    assert local_rows.shape[0] == counts[rank]
+    if counts[rank] == pad:
+        buf = local_rows.contiguous()
+    else:
+        buf = torch.zeros((pad, hsize, 4), dtype=local_rows.dtype, device=local_rows.device)
+        buf[: counts[rank]] = local_rows
+    if rank == 0:
+        allbuf = torch.empty((world * pad, hsize, 4), dtype=local_rows.dtype, device=local_rows.device)
+        parts = list(allbuf.view(world, pad, hsize, 4).unbind(0))
+    else:
+        allbuf, parts = None, None
     dist.gather(buf, parts, dst=0, group=group)
     if rank != 0:
         return None
-    canvas = torch.zeros((vsize, hsize, 4), dtype=local_rows.dtype, device=local_rows.device)
-    for r in range(world):
-        rows = torch.as_tensor(owned_rows(vsize, r, world, rows_per_block), device=local_rows.device, dtype=torch.long)
-        canvas[rows] = parts[r][: counts[r]]
-    return canvas
+    return allbuf.index_select(0, plan["src"])
 
 
 def render_distributed(scene, rank: int, world: int, rows_per_block: int = 4, group=None, **render_kw):

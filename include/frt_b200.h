@@ -200,6 +200,7 @@ enum frt_render_flags {
     FRT_FLAG_F64_SHADOW = 8, /* trace every shadow ray in FP64 (no FP32 filter pass) */
     FRT_FLAG_VERIFY_F32 = 16,/* trace every shadow ray the FP32 filter decides in FP64 as well and count disagreements
                                 in frt_stats.shadow_mismatch (must be 0); the frame itself uses the FP64 answers */
+    FRT_FLAG_NO_SHAFT = 32,  /* switch the per-hit shaft culling of the shadow filter off (A/B measurements, tests) */
     FRT_FLAG_F64_SHADING = 4 /* evaluate the lighting sums (lighting_microfacet, renderer.c:894-979) in FP64 like the
                                 reference instead of FP32; geometric decisions are FP64 either way */
 };
