@@ -613,6 +613,15 @@ struct LightTmp { /* per shaded hit, per light launch; the first 16 bytes are al
  * under one sRGB LSB; T = double (FRT_FLAG_F64_SHADING) keeps the reference's arithmetic type for debugging.
  * Every geometric DECISION (hit / miss, shadowed / lit) stays in FP64 in k_extend / k_shadow.
  */
+/* FP32 lighting arithmetic uses the SFU forms (relative error ~1e-6, far below one sRGB-8 LSB after the 100-sample
+ * average); the FP64 instantiation keeps the IEEE forms */
+__device__ __forceinline__ float sh_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double sh_rsqrt(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float sh_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double sh_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ float sh_pow(float x, float y) { return x > 0.f ? exp2f(y * __log2f(x)) : (y == 0.f ? 1.f : 0.f); }
+__device__ __forceinline__ double sh_pow(double x, double y) { return pow(x, y); }
+
 template <typename T, int G>
 __global__ void __launch_bounds__(256)
 k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, const Counters *cnt,
@@ -665,7 +674,7 @@ k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
                     ly = (T)(__ldg(pb + 3 * s + 1) - over[1]);
                     lz = (T)(__ldg(pb + 3 * s + 2) - over[2]);
                 }
-                T inv = (T)1 / sqrt(lx * lx + ly * ly + lz * lz);
+                T inv = sh_rsqrt(lx * lx + ly * ly + lz * lz);
                 lx *= inv;
                 ly *= inv;
                 lz *= inv;
@@ -676,20 +685,20 @@ k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
                     }
                     if (F.use_spec_highlight) {
                         T hx = lx + eye[0], hy = ly + eye[1], hz = lz + eye[2];
-                        T hinv = (T)1 / sqrt(hx * hx + hy * hy + hz * hz);
+                        T hinv = sh_rsqrt(hx * hx + hy * hy + hz * hz);
                         hx *= hinv;
                         hy *= hinv;
                         hz *= hinv;
                         T ndh = max((T)0, nrm[0] * hx + nrm[1] * hy + nrm[2] * hz);
-                        T edh_inv = (T)1 / max((T)0, eye[0] * hx + eye[1] * hy + eye[2] * hz);
+                        T edh_inv = sh_rcp(max((T)0, eye[0] * hx + eye[1] * hy + eye[2] * hz));
                         T ldh = lx * hx + ly * hy + lz * hz;
-                        T dist_term = (Ns + 2) * pow(ndh, Ns) * (T)(0.5 * M_1_PI);
+                        T dist_term = (Ns + 2) * sh_pow(ndh, Ns) * (T)(0.5 * M_1_PI);
                         T gc = 2 * ndh * edh_inv;
                         T geom = min((T)1, min(gc * ndote, gc * ndl));
                         T m1 = 1 - ldh;
                         T m2 = m1 * m1;
                         T factor = m2 * m2 * m1; /* pow(1 - L.H, 5) */
-                        T brdf = dist_term * geom / (4 * ndl * ndote);
+                        T brdf = dist_term * geom * sh_rcp(4 * ndl * ndote);
                         sum_b += brdf;
                         sum_fb += factor * brdf;
                     }
@@ -786,7 +795,7 @@ normalise_shadow_ray(Ray &sr, double dist2)
 }
 
 #ifndef FRT_SHADOW_MINB
-#define FRT_SHADOW_MINB 4
+#define FRT_SHADOW_MINB 3
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
@@ -1076,6 +1085,14 @@ __int_as_float_host(int v)
     float f;
     memcpy(&f, &v, sizeof(f));
     return f;
+}
+
+static inline int
+__float_as_int_host(float f)
+{
+    int v;
+    memcpy(&v, &f, sizeof(v));
+    return v;
 }
 
 
@@ -1522,6 +1539,62 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
             fn[3 * i + 2] = make_float4((float)hi[0], (float)hi[1], (float)hi[2], 0.f);
         }
     }
+    /* postfix programs of the outermost CSG nodes (frt_shadow_f32.cuh): operands first, then the operator */
+    std::vector<int> prog;
+    for (int i = 0; i < d->n_nodes; ++i) {
+        const frt_node &n = d->nodes[i];
+        if (n.type != FRT_CSG) {
+            continue;
+        }
+        bool outermost = true;
+        for (int p = n.parent; p >= 0; p = d->nodes[p].parent) {
+            if (d->nodes[p].type == FRT_CSG) outermost = false;
+        }
+        if (!outermost) {
+            continue;
+        }
+        const int start = (int)prog.size();
+        bool ok = true;
+        int depth = 0, max_depth = 0;
+        /* iterative post-order over the CSG subtree */
+        struct It { int node, stage; };
+        std::vector<It> stk{ { i, 0 } };
+        while (!stk.empty() && ok) {
+            It &t = stk.back();
+            const frt_node &c = d->nodes[t.node];
+            if (c.type == FRT_CSG) {
+                if (t.stage == 0) {
+                    t.stage = 1;
+                    stk.push_back({ t.node + 1, 0 });
+                } else if (t.stage == 1) {
+                    t.stage = 2;
+                    stk.push_back({ c.right, 0 });
+                } else {
+                    prog.push_back(-(c.csg_op + 1));
+                    depth -= 1;
+                    stk.pop_back();
+                }
+            } else if (c.type == FRT_GROUP) {
+                ok = false; /* a group as an operand: several spans */
+            } else {
+                prog.push_back(t.node);
+                depth += 1;
+                max_depth = std::max(max_depth, depth);
+                stk.pop_back();
+            }
+        }
+        if (ok && max_depth <= 3) {
+            int fl = __float_as_int_host(fn[3 * i].x) | FRT_FN_FAST;
+            fn[3 * i].x = __int_as_float_host(fl);
+            fn[3 * i + 1].w = __int_as_float_host(start);
+            fn[3 * i + 2].w = __int_as_float_host((int)prog.size() - start);
+        } else {
+            prog.resize(start);
+        }
+    }
+    if (prog.empty()) {
+        prog.push_back(0);
+    }
     /* per light: a parallelogram that contains every surface sample (light.c:100-191), slightly inflated */
     for (int li = 0; li < d->n_lights; ++li) {
         const frt_light &L = d->lights[li];
@@ -1572,6 +1645,8 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     rc = upload(sc, wb.data(), wb.size(), &sc->SF.wbox);
     if (rc != FRT_OK) return rc;
     rc = upload(sc, shaft.data(), shaft.size(), &sc->SF.shaft);
+    if (rc != FRT_OK) return rc;
+    rc = upload(sc, prog.data(), prog.size(), &sc->SF.csg_prog);
     if (rc != FRT_OK) return rc;
     rc = upload(sc, fn.data(), fn.size(), &sc->SF.fnodes);
     if (rc != FRT_OK) return rc;

@@ -52,17 +52,20 @@ enum {
     FRT_FN_TYPE_MASK = 15, /* enum frt_node_type */
     FRT_FN_WORLD = 16,     /* lo / hi are WORLD-space bounds: test them with the world ray (no transform) */
     FRT_FN_CASTS = 32,     /* leaf: its material casts shadows */
-    FRT_FN_FAST = 64,      /* leaf: the filter has a fast form for this type (cube, sphere, plane) */
+    FRT_FN_FAST = 64,      /* leaf: the filter has a fast form for this type (cube, sphere, plane);
+                              CSG: it has a postfix program that fits the three-register span stack */
     FRT_FN_NOCULL = 128,   /* group: descend without testing its bounds (culling is optional; the root's box is always hit) */
     FRT_FN_OP_SHIFT = 8    /* CSG: enum frt_csg_op in bits 8..9 */
 };
 
 struct DSceneF {
-    const float4 *fnodes; /* per node: {flags, skip, xform, right (CSG)} as int bits, {lo.xyz, 0}, {hi.xyz, 0} */
+    const float4 *fnodes; /* per node: {flags, skip, xform, right (CSG)} as int bits, {lo.xyz, w}, {hi.xyz, w};
+                             outermost CSG nodes: lo.w / hi.w = start / length of the node's postfix program */
     const float4 *fx;     /* per xform: rows 0..2 of the world->local matrix, then {R_0, R_1, R_2, 0} */
     const float *lpoints; /* FP32 copy of the light sample points, 3 per point */
     const float4 *wbox;   /* per node: WORLD-space bounding box {min.xyz, 0} {max.xyz, 0}, rounded outward (shaft culling) */
     const float4 *shaft;  /* per light: 4 corners of a parallelogram that contains every surface sample of the light */
+    const int *csg_prog;  /* postfix programs of the outermost CSG nodes: node index of a leaf, or -(op + 1) */
     float bmax;           /* largest finite |bound| of a WORLD node */
     int n_nodes;
 };
@@ -436,10 +439,54 @@ leaf_span(int type, const float4 lo, const float4 hi, const FrameF &f, SpanF &s)
     return true;
 }
 
+/* one leaf of the tree as a span in its own frame (switching `cf` when the leaf's transform differs); false = undecided */
+template <bool COUNT>
+__device__ __forceinline__ bool
+node_span(const DSceneF &SF, const float4 q0, const float4 lo, const float4 hi, const FrameF &w, FrameF &cf, int &cur_xf, float omax,
+          float eo_w, float ed_w, bool standalone, SpanF &s, unsigned int &cost)
+{
+    const int flags = __float_as_int(q0.x), xf = __float_as_int(q0.z);
+    const int type = flags & FRT_FN_TYPE_MASK;
+    s.flags = 0;
+    if (!(flags & FRT_FN_FAST)) {
+        return false;
+    }
+    if (xf != cur_xf) { /* WORLD nodes carry xf = 0 */
+        cur_xf = xf;
+        if (xf == 0) {
+            cf = w;
+        } else {
+            frame_local(cf, SF, xf, w, omax, eo_w, ed_w);
+            if (COUNT) cost += FRT_COST_XFORM;
+        }
+    }
+    if (type == FRT_PLANE) { /* plane_local_intersect, plane.c:11-25: one crossing; stands alone or undecided */
+        if (!standalone) {
+            return false;
+        }
+        const float tt = -cf.oy * cf.iy;
+        const float E = fmaf(fabsf(tt), cf.c2y, cf.c1y);
+        s.a_lo = s.b_lo = tt - E;
+        s.a_hi = s.b_hi = tt + E;
+        s.flags = 1;
+    } else if (!leaf_span(type, lo, hi, cf, s)) {
+        return false;
+    }
+    if (s.flags && (flags & FRT_FN_CASTS)) {
+        s.flags |= 6;
+    }
+    return true;
+}
+
 /*
  * FP32 filter twin of trace_shadow (frt_device.cuh).  `w` is the world frame of the ray (frame_finish'ed by the
  * caller), omax / eo_w / ed_w its error terms, [D_lo, D_hi] the interval of the light distance; `fnodes` is the
  * node mirror (in shared memory when the tree is small), `relevant` the hit's shaft-culling mask over nodes 0..31.
+ *
+ * An outermost CSG node is evaluated from its postfix program (SF.csg_prog, built at upload: leaf node indices and
+ * operators in evaluation order) on a three-register span stack, so the walk itself never nests: every step is a
+ * group (cull), a CSG (cull, then the program) or a leaf.  The reference's culls of the CSG nodes INSIDE another CSG
+ * (csg.c:82-86) are skipped: a nested CSG whose box is missed contributes no crossings either way.
  * Returns FRT_SH_LIT, FRT_SH_SHADOWED or FRT_SH_UNDECIDED (the latter with a reason code in bits 4.. for the counting
  * build's histogram; callers mask with 15).
  */
@@ -448,15 +495,6 @@ __device__ __forceinline__ int
 trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int relevant, const FrameF &w, float omax, float eo_w,
                  float ed_w, float D_lo, float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
 {
-    struct Frame { /* an open CSG node: its operator, where its right operand starts and ends, its left result */
-        int op, right, skip, have_left;
-        SpanF left;
-    };
-    Frame st[FRT_CSG_DEPTH];
-    int sp = 0;
-    SpanF cur; /* result of the operand being evaluated (inside a CSG) */
-    cur.flags = 0;
-    cur.a_lo = cur.a_hi = cur.b_lo = cur.b_hi = 0.0f;
     unsigned int visited = 0, cost = 0;
     int i = root;
     const int end = __float_as_int(fnodes[3 * i].y);
@@ -465,134 +503,96 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int
     int verdict = FRT_SH_LIT;
 
     while (i < end) {
-        if (sp == 0 && i < 32 && !((relevant >> i) & 1u)) {
-            /* shaft culling (see ShaftF): no ray of this hit can cross this subtree at t > 0.  Never inside a CSG, whose
-             * operands' negative crossings still toggle the filter state. */
+        if (i < 32 && !((relevant >> i) & 1u)) {
+            /* shaft culling (see ShaftF): no ray of this hit can cross this subtree at t > 0 */
             i = __float_as_int(fnodes[3 * i].y);
             continue;
         }
         const float4 q0 = fnodes[3 * i], lo = fnodes[3 * i + 1], hi = fnodes[3 * i + 2];
-        const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y), xf = __float_as_int(q0.z);
+        const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
         const int type = flags & FRT_FN_TYPE_MASK;
         if (COUNT) {
             ++visited;
             cost += (type >= FRT_CSG) ? FRT_COST_BBOX : prim_cost(type);
         }
-        if (xf != cur_xf) { /* WORLD nodes carry xf = 0 */
-            cur_xf = xf;
-            if (xf == 0) {
-                cf = w;
-            } else {
-                frame_local(cf, SF, xf, w, omax, eo_w, ed_w);
-                if (COUNT) cost += FRT_COST_XFORM;
-            }
-        }
+        SpanF s;
         if (type >= FRT_CSG) { /* group or CSG: conservative cull by its bounds */
-            bool miss = false;
             if (!(flags & FRT_FN_NOCULL)) {
+                const int xf = __float_as_int(q0.z);
+                if (xf != cur_xf) {
+                    cur_xf = xf;
+                    if (xf == 0) {
+                        cf = w;
+                    } else {
+                        frame_local(cf, SF, xf, w, omax, eo_w, ed_w);
+                        if (COUNT) cost += FRT_COST_XFORM;
+                    }
+                }
                 float tn_lo, tn_hi, tf_lo, tf_hi;
                 box_f(cf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-                /* surely missed, or (outside a CSG) surely wholly behind the origin: only t <= 0 crossings inside */
-                miss = tn_lo > tf_hi || (sp == 0 && tf_hi < 0.0f);
-            }
-            if (miss) {
-                i = skip;
-            } else {
-                if (type == FRT_CSG) {
-                    if (sp == FRT_CSG_DEPTH) {
-                        return FRT_SH_UNDECIDED | (1 << 4);
-                    }
-                    Frame &f = st[sp++];
-                    f.op = (flags >> FRT_FN_OP_SHIFT) & 3;
-                    f.right = __float_as_int(q0.w);
-                    f.skip = skip;
-                    f.have_left = 0;
-                    f.left = cur;
-                    f.left.flags = 0;
-                    cur.flags = 0;
-                } else if (sp > 0) {
-                    return FRT_SH_UNDECIDED | (2 << 4); /* a group inside a CSG operand: several spans */
+                /* surely missed, or surely wholly behind the origin (only t <= 0 crossings inside) */
+                if (tn_lo > tf_hi || tf_hi < 0.0f) {
+                    i = skip;
+                    continue;
                 }
+            }
+            if (type == FRT_GROUP) {
                 i = i + 1;
+                continue;
             }
-        } else {
+            /* CSG: run its postfix program */
             if (!(flags & FRT_FN_FAST)) {
-                return FRT_SH_UNDECIDED | (3 << 4);
+                return FRT_SH_UNDECIDED | (1 << 4); /* deeper than the span stack, or a group inside an operand */
             }
-            SpanF s;
-            bool ok = true;
-            if (type == FRT_PLANE) { /* plane_local_intersect, plane.c:11-25: one crossing; stands alone or undecided */
-                if (sp > 0) {
-                    return FRT_SH_UNDECIDED | (4 << 4);
-                }
-                const float tt = -cf.oy * cf.iy;
-                const float E = fmaf(fabsf(tt), cf.c2y, cf.c1y);
-                s.a_lo = s.b_lo = tt - E;
-                s.a_hi = s.b_hi = tt + E;
-                s.flags = 1;
-            } else {
-                ok = leaf_span(type, lo, hi, cf, s);
-            }
-            if (!ok) {
-                return FRT_SH_UNDECIDED | (5 << 4) | (i << 8);
-            }
-            if (s.flags && (flags & FRT_FN_CASTS)) {
-                s.flags |= 6;
-            }
-            if (sp == 0) {
-                if (s.flags) {
-                    const int v = judge_span(s, D_lo, D_hi);
-                    if (v == 3) {
-                        return FRT_SH_UNDECIDED | (6 << 4) | (i << 8);
+            const int pc0 = __float_as_int(lo.w), pc1 = pc0 + __float_as_int(hi.w);
+            SpanF X, Y, Z;
+            X.flags = Y.flags = Z.flags = 0;
+            X.a_lo = X.a_hi = X.b_lo = X.b_hi = 0.0f;
+            Y = X;
+            Z = X;
+            for (int pc = pc0; pc < pc1; ++pc) {
+                const int code = __ldg(SF.csg_prog + pc);
+                if (code >= 0) {
+                    const float4 l0 = fnodes[3 * code], l1 = fnodes[3 * code + 1], l2 = fnodes[3 * code + 2];
+                    if (COUNT) {
+                        ++visited;
+                        cost += prim_cost(__float_as_int(l0.x) & FRT_FN_TYPE_MASK);
                     }
-                    if (v != 0) {
-                        verdict = (v == 2) ? FRT_SH_SHADOWED : FRT_SH_LIT;
-                        break;
+                    SpanF t;
+                    if (!node_span<COUNT>(SF, l0, l1, l2, w, cf, cur_xf, omax, eo_w, ed_w, false, t, cost)) {
+                        return FRT_SH_UNDECIDED | (5 << 4) | ((code & 31) << 8);
                     }
+                    Z = Y;
+                    Y = X;
+                    X = t;
+                } else {
+                    SpanF r;
+                    r.a_lo = r.a_hi = r.b_lo = r.b_hi = 0.0f;
+                    if (!csg_combine(-code - 1, Y, X, r)) {
+                        return FRT_SH_UNDECIDED | (8 << 4);
+                    }
+                    X = r;
+                    Y = Z;
+                    Z.flags = 0;
                 }
-            } else if (s.flags) {
-                if (cur.flags) {
-                    return FRT_SH_UNDECIDED | (7 << 4); /* two spans in one operand */
-                }
-                cur = s;
+            }
+            s = X;
+            i = skip;
+        } else {
+            if (!node_span<COUNT>(SF, q0, lo, hi, w, cf, cur_xf, omax, eo_w, ed_w, true, s, cost)) {
+                return FRT_SH_UNDECIDED | (5 << 4) | ((i & 31) << 8);
             }
             i = i + 1;
         }
-        /* close every CSG whose left / right operand just ended */
-        bool stop = false;
-        while (sp > 0) {
-            Frame &f = st[sp - 1];
-            if (!f.have_left && i >= f.right) {
-                f.left = cur;
-                f.have_left = 1;
-                cur.flags = 0;
+        if (s.flags) { /* a leaf's or an outermost CSG's crossing list */
+            const int v = judge_span(s, D_lo, D_hi);
+            if (v == 3) {
+                return FRT_SH_UNDECIDED | (6 << 4) | (((i - 1) & 31) << 8);
             }
-            if (i < f.skip) {
+            if (v != 0) {
+                verdict = (v == 2) ? FRT_SH_SHADOWED : FRT_SH_LIT;
                 break;
             }
-            SpanF res;
-            res.a_lo = res.a_hi = res.b_lo = res.b_hi = 0.0f;
-            if (!csg_combine(f.op, f.left, cur, res)) {
-                return FRT_SH_UNDECIDED | (8 << 4);
-            }
-            --sp;
-            cur = res; /* becomes the enclosing CSG's current operand, or the list to judge */
-            if (sp == 0) { /* the outermost CSG is judged like a leaf */
-                cur.flags = 0;
-                if (res.flags) {
-                    const int v = judge_span(res, D_lo, D_hi);
-                    if (v == 3) {
-                        return FRT_SH_UNDECIDED | (9 << 4);
-                    }
-                    if (v != 0) {
-                        verdict = (v == 2) ? FRT_SH_SHADOWED : FRT_SH_LIT;
-                        stop = true;
-                    }
-                }
-            }
-        }
-        if (stop) {
-            break;
         }
     }
     if (COUNT) {
