@@ -1125,6 +1125,7 @@ struct frt_scene {
         unsigned int *cell_start = nullptr;
         PMView view{};
         bool built = false;
+        bool scaled = false; /* pm_scale_photon_power already applied to ra / rb */
     } pm[2];
     unsigned int *pm_stored = nullptr; /* device counters, one per map */
     bool pm_ready = false;
@@ -2408,6 +2409,7 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
         frt_scene::PMap &m = sc->pm[map];
         m.count = 0;
         m.built = false;
+        m.scaled = false;
         if (!want) {
             continue;
         }
@@ -2517,6 +2519,7 @@ frt_photons_import(frt_scene *sc, int map, const void *src, int64_t count, int s
     frt_scene::PMap &m = sc->pm[map];
     m.count = 0;
     m.built = false;
+    m.scaled = false;
     sc->pm_ready = false;
     int rc = pm_reserve(sc, map, (unsigned int)std::max<int64_t>(count, 1));
     if (rc != FRT_OK) {
@@ -2562,7 +2565,8 @@ frt_photons_finish(frt_scene *sc)
         unsigned int *db = nullptr;
         CK(cudaMalloc(&db, sizeof(hb)));
         CK(cudaMemcpy(db, hb, sizeof(hb), cudaMemcpyHostToDevice));
-        k_pm_scale_bounds<<<148 * 4, 256, 0, sc->stream>>>(m.ra, m.rb, m.count, scale, db);
+        k_pm_scale_bounds<<<148 * 4, 256, 0, sc->stream>>>(m.ra, m.rb, m.count, m.scaled ? 1.0f : scale, db);
+        m.scaled = true;
         CK(cudaMemcpyAsync(hb, db, sizeof(hb), cudaMemcpyDeviceToHost, sc->stream));
         CK(cudaStreamSynchronize(sc->stream));
         cudaFree(db);
@@ -2572,7 +2576,7 @@ frt_photons_finish(frt_scene *sc)
             hi[k] = float_unorder(hb[3 + k]);
             ext = std::max(ext, hi[k] - lo[k]);
         }
-        const float cell = std::max(radius, ext / 256.0f);
+        const float cell = std::max(0.5f * radius, ext / 256.0f); /* half the search radius: 5 x 5 rows, clipped to the sphere */
         PMView V{};
         V.gx = lo[0];
         V.gy = lo[1];

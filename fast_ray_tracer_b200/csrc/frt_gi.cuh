@@ -5,23 +5,25 @@
  *   k_photon_trace     trace_photons' emission loop + power_at / photon_hit with     photon_tracer.c:114-257,
  *                      Russian roulette, storing into the caustic / global map        light.c:14-98, pm.c:261
  *   k_pm_bounds/_count/_scan/_scatter   replace pm_balance (pm.c:329): photons are binned into a uniform grid
- *                      of cell size >= the estimate radius, sorted by cell
+ *                      of cell size = half the estimate radius, sorted by cell
  *   k_fg_trace         final_gather + color_at_gi: one thread per (hit, CMJ cell)    renderer.c:647, :319
  *   k_gi_points        lighting_caustics / lighting_gi (visualize) query per hit     renderer.c:829, :862
  *   k_knn              pm_irradiance_estimate + pm_locate_photons: one WARP per      pm.c:91-252
- *                      query gathers the photons of the 27 neighbouring cells, selects the n nearest by a
- *                      bit-wise bisection over the squared distances held in shared memory, and sums them
+ *                      query gathers the photons of the cell rows its search sphere reaches, selects the n nearest
+ *                      by a three-pass radix select over the squared distances held in shared memory, sums them
  *   k_gi_resolve       the ambient-slot sum and its sqrt(3) clamp                    renderer.c:755-770
  *
  * Why a grid and not Jensen's left-balanced kd-tree: the estimate depends only on the SET of the n nearest
  * photons within max_dist (and the distance of the farthest one), not on the structure that finds it.  With a fixed
- * search radius a grid of that cell size touches 27 cells; cells are contiguous photon ranges, so a warp streams
- * them with coalesced 16-byte loads instead of chasing a tree one photon at a time.
+ * search radius a grid of half that cell size touches at most 5 x 5 rows of cells; a row is one contiguous photon
+ * range, so a warp streams it with coalesced 16-byte loads instead of chasing a tree one photon at a time.
  *
  * Photon record (32 bytes, two float4): {x, y, z, theta | phi << 8} {power r, g, b, 0} -- theta / phi are Jensen's
  * 8-bit direction (pm.c:286-300).
  */
 #pragma once
+
+#include <cuda_fp16.h>
 
 #define FRT_KNN_WARPS 4
 #define FRT_KNN_CAP 1024
@@ -449,7 +451,16 @@ k_pm_scatter(PMView M, const float4 *__restrict__ a, const float4 *__restrict__ 
         const float4 p = a[i];
         const unsigned int slot = atomicAdd(cursor + pm_cell_of(M, p.x, p.y, p.z), 1u);
         sa[slot] = p;
-        sb[slot] = b[i];
+        /* pm_photon_dir (pm.c:80-86) evaluated once here: x, y of the table direction as two halves in power.w; z follows
+         * from them and from theta < 128.  The estimate only tests the SIGN of dir . normal (pm.c:141). */
+        const unsigned int bits = __float_as_uint(p.w);
+        float st, ct, sp, cp;
+        sincospif((float)(bits & 255u) * (1.0f / 256.0f), &st, &ct);
+        sincospif((float)((bits >> 8) & 255u) * (2.0f / 256.0f), &sp, &cp);
+        float4 w = b[i];
+        const __half2 xy = __floats2half2_rn(st * cp, st * sp);
+        w.w = __uint_as_float(*reinterpret_cast<const unsigned int *>(&xy));
+        sb[slot] = w;
     }
 }
 
@@ -593,10 +604,82 @@ k_gi_points(FrameParams F, GIParams G, const LightRec *__restrict__ recs, unsign
 }
 
 /*
+ * Warp-cooperative selection: the 24-bit key of the want-th smallest of d2[0..count) (count > want), keys being
+ * d2 * scale truncated to 24 bits.  Three 8-bit radix passes, each a shared-memory histogram of the candidates that
+ * still match the digits found so far and a warp scan over its 256 bins -- three passes over the list instead of
+ * the 31 of a bit-wise bisection.
+ */
+__device__ __forceinline__ unsigned int
+knn_key(float v, float scale)
+{
+    return min((unsigned int)(v * scale), 0xffffffu);
+}
+
+__device__ __forceinline__ unsigned int
+warp_select_key(const float *d2, unsigned int count, unsigned int want, float scale, unsigned int *hist, int lane)
+{
+    unsigned int prefix = 0, remaining = want; /* remaining: rank of the target among the keys that match `prefix` */
+    for (int shift = 16; shift >= 0; shift -= 8) {
+        for (int b = lane; b < 256; b += 32) {
+            hist[b] = 0;
+        }
+        __syncwarp();
+        const unsigned int hi_mask = shift == 16 ? 0u : (0xffffffu >> (shift + 8)) << (shift + 8);
+        for (unsigned int k = lane; k < count; k += 32) {
+            const unsigned int key = knn_key(d2[k], scale);
+            if ((key & hi_mask) == prefix) {
+                atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+        }
+        __syncwarp();
+        /* lane l owns bins 8l .. 8l+7 */
+        unsigned int mine[8], sum = 0;
+        for (int b = 0; b < 8; ++b) {
+            mine[b] = hist[8 * lane + b];
+            sum += mine[b];
+        }
+        unsigned int incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) {
+                incl += up;
+            }
+        }
+        const unsigned int excl = incl - sum;
+        /* the lane whose range [excl, incl) contains rank `remaining` (1-based) */
+        const bool has = remaining > excl && remaining <= incl;
+        const unsigned int owner_mask = __ballot_sync(0xffffffffu, has);
+        const int owner = __ffs(owner_mask) - 1;
+        unsigned int digit = 0, before = 0;
+        if (lane == owner) {
+            unsigned int run = excl;
+            for (int b = 0; b < 8; ++b) {
+                if (remaining <= run + mine[b]) {
+                    digit = 8 * lane + b;
+                    before = run;
+                    break;
+                }
+                run += mine[b];
+            }
+        }
+        digit = __shfl_sync(0xffffffffu, digit, owner < 0 ? 0 : owner);
+        before = __shfl_sync(0xffffffffu, before, owner < 0 ? 0 : owner);
+        prefix |= digit << shift;
+        remaining -= before;
+        __syncwarp();
+    }
+    return prefix;
+}
+
+/*
  * pm_irradiance_estimate (pm.c:91-156): the n nearest photons within max_dist of the request, cone-filtered sum of
  * those whose direction faces the "normal", density from the distance of the farthest one; fewer than 8 photons give
  * nothing (:121).  The callers' rescaling (100 / found for the caustic map, 10 n / found for the global map,
  * renderer.c:845, :878) and the request's weight are applied here and the result is added to the hit's sum.
+ *
+ * One warp per request.  The grid's cells are half the search radius wide; the warp walks the rows of cells that the
+ * search sphere can reach (a row = cells consecutive in x = one contiguous photon range), clipped to the sphere, and
+ * keeps the squared distances < r^2 with their photon indices in shared memory.
  */
 __global__ void __launch_bounds__(FRT_KNN_WARPS * 32)
 k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, const unsigned int *n_queries, unsigned int qcap,
@@ -604,11 +687,13 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
 {
     __shared__ float s_d2[FRT_KNN_WARPS][FRT_KNN_CAP];
     __shared__ unsigned int s_idx[FRT_KNN_WARPS][FRT_KNN_CAP];
+    __shared__ unsigned int s_hist[FRT_KNN_WARPS][256];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned int nq = min(*n_queries, qcap);
     const unsigned int lt = (1u << lane) - 1u;
     float *d2 = s_d2[wib];
     unsigned int *idx = s_idx[wib];
+    unsigned int *hist = s_hist[wib];
     const float R2 = G.radius * G.radius;
     const unsigned int want_n = (unsigned int)G.n_photons;
 
@@ -620,122 +705,140 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
             continue;
         }
         unsigned int count = 0;
-        bool shrunk = false;
         float r2cur = R2;
-        const int cx = (int)floorf((q.x - M.gx) * M.inv_cell), cy = (int)floorf((q.y - M.gy) * M.inv_cell),
-                  cz = (int)floorf((q.z - M.gz) * M.inv_cell);
-        /* how many cells the radius spans (1 when the cell size is the radius) */
-        const int reach = (int)ceilf(G.radius * M.inv_cell);
-        for (int z = max(cz - reach, 0); z <= min(cz + reach, M.nz - 1); ++z) {
-            for (int y = max(cy - reach, 0); y <= min(cy + reach, M.ny - 1); ++y) {
-                const int x0 = max(cx - reach, 0), x1 = min(cx + reach, M.nx - 1);
-                if (x0 > x1) {
-                    continue;
+        const float cell = 1.0f / M.inv_cell;
+        const float fy = (q.y - M.gy) * M.inv_cell, fz = (q.z - M.gz) * M.inv_cell;
+        const int cy = (int)floorf(fy), cz = (int)floorf(fz);
+        const int reach = (int)ceilf(G.radius * M.inv_cell); /* <= 2: the cells are at least half a radius wide */
+        const int side = 2 * reach + 1;
+        /* lane r owns row r of the (2 reach + 1)^2 rows of cells around the request: clip it to the search sphere and fetch
+         * its photon range -- all rows at once, so the dependent loads (cell_start, then photons) are paid once per request */
+        unsigned int row_s = 0, row_len = 0;
+        if (lane < side * side) {
+            const int z = cz - reach + lane / side, y = cy - reach + lane % side;
+            if (z >= 0 && z < M.nz && y >= 0 && y < M.ny) {
+                const float dzc = fmaxf(fmaxf((float)z - fz, fz - (float)(z + 1)), 0.0f) * cell;
+                const float dyc = fmaxf(fmaxf((float)y - fy, fy - (float)(y + 1)), 0.0f) * cell;
+                const float rem = R2 - dzc * dzc - dyc * dyc;
+                if (rem > 0.0f) {
+                    const float dxm = sqrtf(rem) * 1.0001f + 1e-7f;
+                    const int x0 = max((int)floorf((q.x - dxm - M.gx) * M.inv_cell), 0);
+                    const int x1 = min((int)floorf((q.x + dxm - M.gx) * M.inv_cell), M.nx - 1);
+                    if (x0 <= x1) { /* cells of one x-row are contiguous in memory: one photon range */
+                        const unsigned int base = (unsigned int)((z * M.ny + y) * M.nx);
+                        row_s = __ldg(M.cell_start + base + x0);
+                        row_len = __ldg(M.cell_start + base + x1 + 1) - row_s;
+                    }
                 }
-                /* cells of one x-row are contiguous in memory: one range */
-                const unsigned int s = M.cell_start[(z * M.ny + y) * M.nx + x0], e = M.cell_start[(z * M.ny + y) * M.nx + x1 + 1];
-                for (unsigned int p0 = s; p0 < e; p0 += 32) {
-                    const unsigned int p = p0 + lane;
-                    bool hit = false;
-                    float dd = 0.f;
-                    if (p < e) {
-                        const float4 a = __ldg(M.a + p);
-                        const float dx = a.x - q.x, dy = a.y - q.y, dz = a.z - q.z;
-                        dd = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                        hit = dd < r2cur;
+            }
+        }
+        unsigned int incl = row_len;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) {
+                incl += up;
+            }
+        }
+        const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+        /* four chunks of 32 candidates in flight per step: the photon loads are L2 hits of a few hundred cycles each and the
+         * warp has nothing else to overlap them with */
+        for (unsigned int j0 = 0; j0 < total; j0 += 128) {
+            unsigned int pp[4];
+            float4 aa[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned int j = j0 + 32 * u + lane;
+                /* which row holds candidate j: the first lane whose inclusive prefix exceeds j (binary search by shuffles) */
+                int lo_r = 0;
+                for (int step = 16; step > 0; step >>= 1) {
+                    const unsigned int v = __shfl_sync(0xffffffffu, incl, min(lo_r + step - 1, 31));
+                    if (v <= j) {
+                        lo_r += step;
                     }
-                    const unsigned int mask = __ballot_sync(0xffffffffu, hit);
-                    if (hit) {
-                        const unsigned int pos = count + __popc(mask & lt);
-                        d2[pos] = dd;
-                        idx[pos] = p;
-                    }
-                    count += __popc(mask);
+                }
+                const int r = min(lo_r, 31);
+                const unsigned int r_incl = __shfl_sync(0xffffffffu, incl, r), r_len = __shfl_sync(0xffffffffu, row_len, r);
+                const unsigned int r_s = __shfl_sync(0xffffffffu, row_s, r);
+                pp[u] = r_s + (j - (r_incl - r_len));
+                aa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < total) {
+                    aa[u] = __ldg(M.a + pp[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+            const unsigned int j = j0 + 32 * u + lane;
+            const unsigned int p = pp[u];
+            bool hit = false;
+            float dd = 0.f;
+            if (j < total) {
+                const float dx = aa[u].x - q.x, dy = aa[u].y - q.y, dz = aa[u].z - q.z;
+                dd = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                hit = dd < r2cur;
+            }
+            const unsigned int mask = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const unsigned int pos = count + __popc(mask & lt);
+                d2[pos] = dd;
+                idx[pos] = p;
+            }
+            count += __popc(mask);
+            __syncwarp();
+            if (count > FRT_KNN_CAP - 32) {
+                /* list nearly full: keep only the want_n nearest seen so far and tighten the radius */
+                const float scale = 16777216.0f / r2cur;
+                const unsigned int T = warp_select_key(d2, count, want_n, scale, hist, lane);
+                unsigned int kept = 0;
+                float mx = 0.f;
+                for (unsigned int k0 = 0; k0 < count; k0 += 32) {
+                    const unsigned int k = k0 + lane;
+                    const float v = (k < count) ? d2[k] : 0.f;
+                    const unsigned int id = (k < count) ? idx[k] : 0u;
+                    const bool keep = (k < count) && knn_key(v, scale) <= T;
+                    const unsigned int m2 = __ballot_sync(0xffffffffu, keep);
                     __syncwarp();
-                    if (count > FRT_KNN_CAP - 32) {
-                        /* list nearly full: keep only the want_n nearest seen so far and tighten the radius */
-                        unsigned int T = 0;
-                        for (int bit = 30; bit >= 0; --bit) {
-                            const unsigned int test = T | (1u << bit);
-                            unsigned int c = 0;
-                            for (unsigned int k = lane; k < count; k += 32) {
-                                c += (__float_as_uint(d2[k]) < test) ? 1u : 0u;
-                            }
-                            c = __reduce_add_sync(0xffffffffu, c);
-                            if (c < want_n) {
-                                T = test;
-                            }
-                        }
-                        const float tf = __uint_as_float(T);
-                        unsigned int kept = 0;
-                        for (unsigned int k0 = 0; k0 < count; k0 += 32) {
-                            const unsigned int k = k0 + lane;
-                            const float v = (k < count) ? d2[k] : 0.f;
-                            const unsigned int id = (k < count) ? idx[k] : 0u;
-                            const bool keep = (k < count) && v <= tf;
-                            const unsigned int m2 = __ballot_sync(0xffffffffu, keep);
-                            __syncwarp();
-                            if (keep) {
-                                const unsigned int pos = kept + __popc(m2 & lt);
-                                d2[pos] = v;
-                                idx[pos] = id;
-                            }
-                            kept += __popc(m2);
-                            __syncwarp();
-                        }
-                        count = kept;
-                        r2cur = nextafterf(tf, 3.0e38f); /* candidates must now beat the current n-th distance */
-                        shrunk = true;
+                    if (keep) {
+                        const unsigned int pos = kept + __popc(m2 & lt);
+                        d2[pos] = v;
+                        idx[pos] = id;
+                        mx = fmaxf(mx, v);
                     }
+                    kept += __popc(m2);
+                    __syncwarp();
                 }
+                for (int o = 16; o > 0; o >>= 1) {
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                count = kept;
+                r2cur = nextafterf(mx, 3.0e38f); /* candidates must now beat the current n-th distance */
+            }
             }
         }
         __syncwarp();
-        /* the n nearest: threshold T = n-th smallest squared distance */
-        float thr = R2, r2_density = R2;
+        /* the n nearest: entries whose key is <= the key of the n-th smallest squared distance */
+        const float scale = 16777216.0f / r2cur;
+        unsigned int T = 0xffffffu;
         unsigned int found = count;
-        if (count > want_n || shrunk) {
-            if (count > want_n) {
-                unsigned int T = 0;
-                for (int bit = 30; bit >= 0; --bit) {
-                    const unsigned int test = T | (1u << bit);
-                    unsigned int c = 0;
-                    for (unsigned int k = lane; k < count; k += 32) {
-                        c += (__float_as_uint(d2[k]) < test) ? 1u : 0u;
-                    }
-                    c = __reduce_add_sync(0xffffffffu, c);
-                    if (c < want_n) {
-                        T = test;
-                    }
-                }
-                thr = __uint_as_float(T);
-            } else {
-                float m = 0.f;
-                for (unsigned int k = lane; k < count; k += 32) {
-                    m = fmaxf(m, d2[k]);
-                }
-                for (int o = 16; o > 0; o >>= 1) {
-                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                }
-                thr = m;
-            }
-            r2_density = thr;
-            found = min(count, want_n);
+        const bool select = count > want_n;
+        if (select) {
+            T = warp_select_key(d2, count, want_n, scale, hist, lane);
+            found = want_n;
         }
-        float sr = 0.f, sg = 0.f, sb = 0.f;
+        float sr = 0.f, sg = 0.f, sb = 0.f, far2 = 0.f;
         if (found >= 8) {
             const float inv_kr = 1.0f / (G.cone_k * G.radius);
             for (unsigned int k = lane; k < count; k += 32) {
                 const float v = d2[k];
-                if (v <= thr) {
+                if (knn_key(v, scale) <= T) {
+                    far2 = fmaxf(far2, v);
                     const unsigned int id = idx[k];
-                    const unsigned int bits = __float_as_uint(__ldg(M.a + id).w);
-                    float st, ct, sp, cp;
-                    sincospif((float)(bits & 255u) * (1.0f / 256.0f), &st, &ct);        /* pm.c:60-65 tables */
-                    sincospif((float)((bits >> 8) & 255u) * (2.0f / 256.0f), &sp, &cp);
-                    const float dot = st * cp * q.ex + st * sp * q.ey + ct * q.ez;
+                    const float4 pw = __ldg(M.b + id);
+                    const unsigned int theta = __float_as_uint(__ldg(M.a + id).w) & 255u;
+                    const unsigned int xyb = __float_as_uint(pw.w);
+                    const float2 xy = __half22float2(*reinterpret_cast<const __half2 *>(&xyb));
+                    const float zz = sqrtf(fmaxf(0.0f, 1.0f - xy.x * xy.x - xy.y * xy.y));
+                    const float dot = xy.x * q.ex + xy.y * q.ey + (theta < 128u ? zz : -zz) * q.ez;
                     if (dot < 0.0f) {
-                        const float4 pw = __ldg(M.b + id);
                         const float w = 1.0f - sqrtf(v) * inv_kr;
                         sr = fmaf(pw.x, w, sr);
                         sg = fmaf(pw.y, w, sg);
@@ -747,10 +850,13 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
                 sr += __shfl_xor_sync(0xffffffffu, sr, o);
                 sg += __shfl_xor_sync(0xffffffffu, sg, o);
                 sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                far2 = fmaxf(far2, __shfl_xor_sync(0xffffffffu, far2, o));
             }
         }
         if (lane == 0 && found >= 8) {
-            const double density = 1.0 / ((1.0 - 2.0 / (3.0 * (double)G.cone_k)) * (M_PI * (double)r2_density));
+            /* np.dist2[0] (pm.c:147): the search radius^2 until the heap of n photons is full, then the n-th distance^2 */
+            const double r2_density = (select || r2cur < R2) ? (double)far2 : (double)R2;
+            const double density = 1.0 / ((1.0 - 2.0 / (3.0 * (double)G.cone_k)) * (M_PI * r2_density));
             const double rescale = caustic ? 100.0 / (double)found : 10.0 * (double)G.n_photons / (double)found;
             const double f = density * rescale;
             double *acc = ((q.target & 0x80000000u) ? acc_fg : acc_amb) + 3 * (size_t)(q.target & 0x3fffffffu);
