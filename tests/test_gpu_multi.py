@@ -1,0 +1,78 @@
+"""Two real GPUs, one process each, NCCL (-m gpu; skipped when the box has a single GPU): row-partitioned frame gathered
+to rank 0 equals the single-GPU frame, and the photon pass sharded over the ranks + all-gathered gives the same
+statistical agreement with the reference as the single-GPU pass."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    import fast_ray_tracer_b200 as frt
+    from fast_ray_tracer_b200.dist import render_distributed, trace_photons_distributed
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    out = {}
+    desc = frt.SceneDesc.load(GOLDEN / "cornell_exact_200.frt")
+    with frt.Scene(desc, device=rank) as sc:
+        canvas, _ = render_distributed(sc, rank, world)
+        if rank == 0:
+            out["direct"] = canvas.cpu().numpy()
+    desc = frt.SceneDesc.load(GOLDEN / "cornell_gi_64.frt")
+    with frt.Scene(desc, device=rank) as sc:
+        trace_photons_distributed(sc, rank, world, False, True, seed=7)
+        out_count = sc.photons_count(1)
+        canvas, _ = render_distributed(sc, rank, world, seed=3)
+        if rank == 0:
+            out["gi"] = canvas.cpu().numpy()
+            out["photons"] = out_count
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpus_rows_and_photon_allgather(frt):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from compare import parity_report, to_srgb8
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    ref = np.load(GOLDEN / "cornell_exact_200.npz")["rgb"].astype(np.float64)
+    rep = parity_report(out["direct"][..., :3], ref)
+    assert rep["within_1lsb"] >= 0.999, rep
+    z = np.load(GOLDEN / "cornell_gi_64.npz")
+    a, b = z["rgb"].astype(np.float64), z["rgb_b"].astype(np.float64)
+
+    def rmse(x, y):
+        return float(np.sqrt(((to_srgb8(x).astype(np.float64) - to_srgb8(y).astype(np.float64)) ** 2).mean()))
+
+    assert rmse(out["gi"][..., :3], a) <= 1.25 * rmse(a, b)
+    assert 100000 <= out["photons"] <= 100000 + 2 * 6
