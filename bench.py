@@ -272,10 +272,9 @@ def cuda_arm(args) -> dict:
         #      canvas back in (pinned) host memory, every step.  Multi-GPU: each rank uploads, rank 0 receives the frame.
         pinned = torch.empty((vsize, hsize, 4), dtype=torch.float64).pin_memory()
         out = pinned.numpy()
-        e2e_steps = max(1, min(args.steps, 3))
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
+        e2e_steps = max(1, min(args.steps, 5))
+
+        def e2e_step(k):
             with frt.Scene(desc, device=local) as sc2:
                 if world == 1:
                     sc2.render(out=out, seed=2000 + k)
@@ -285,6 +284,12 @@ def cuda_arm(args) -> dict:
                     if rank == 0:
                         pinned.copy_(full)
                 torch.cuda.synchronize()
+
+        e2e_step(-1)  # warm-up: the first scene of a process allocates the (scene-independent, re-used) ray queues
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e_step(k)
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
