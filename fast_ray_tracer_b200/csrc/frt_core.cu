@@ -819,6 +819,7 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
     const unsigned long long total = (unsigned long long)n * (unsigned int)NS;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const bool small = total <= 0xffffffffull;
+    const unsigned long long ns_magic = NS > 1 ? ~0ull / (unsigned int)NS + 1ull : 0ull; /* ceil(2^64 / NS) */
     const int root = __ldg(S.roots);
     int overflow = 0;
     unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0, n_mismatch = 0;
@@ -829,7 +830,7 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
         int s = 0;
         float4 head = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         if (item < total) {
-            h = small ? (unsigned int)item / (unsigned int)NS : (unsigned int)(item / (unsigned int)NS);
+            h = NS > 1 ? (unsigned int)__umul64hi(item, ns_magic) : (unsigned int)item; /* item / NS, exact while item * NS < 2^64 */
             s = (int)(item - (unsigned long long)h * (unsigned int)NS);
             head = *reinterpret_cast<const float4 *>(tmp + h);
         }
@@ -1584,7 +1585,13 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
                 stk.pop_back();
             }
         }
-        if (ok && max_depth <= 3) {
+        /* left-deep: a leaf, then (leaf, operator) pairs -- one accumulator span evaluates it */
+        const int len = (int)prog.size() - start;
+        ok = ok && len >= 3 && (len % 2) == 1 && prog[start] >= 0;
+        for (int k = start + 1; ok && k < (int)prog.size(); k += 2) {
+            ok = prog[k] >= 0 && prog[k + 1] < 0;
+        }
+        if (ok) {
             int fl = __float_as_int_host(fn[3 * i].x) | FRT_FN_FAST;
             fn[3 * i].x = __int_as_float_host(fl);
             fn[3 * i + 1].w = __int_as_float_host(start);

@@ -439,38 +439,50 @@ leaf_span(int type, const float4 lo, const float4 hi, const FrameF &f, SpanF &s)
     return true;
 }
 
-/* one leaf of the tree as a span in its own frame (switching `cf` when the leaf's transform differs); false = undecided */
+/* plane_local_intersect (plane.c:11-25) as a degenerate span: one crossing */
+__device__ __forceinline__ void
+plane_span(const FrameF &f, SpanF &s)
+{
+    const float tt = -f.oy * f.iy;
+    const float E = fmaf(fabsf(tt), f.c2y, f.c1y);
+    s.a_lo = s.b_lo = tt - E;
+    s.a_hi = s.b_hi = tt + E;
+    s.flags = 1;
+}
+
+/*
+ * One leaf of the tree as a span; false = undecided.  WORLD leaves (xf = 0) are tested with the world frame `w`, the
+ * others with `lf`, the frame of transform cur_xf, which is rebuilt only when the leaf's transform differs from it --
+ * two call sites instead of one frame that is copied back and forth.
+ */
 template <bool COUNT>
 __device__ __forceinline__ bool
-node_span(const DSceneF &SF, const float4 q0, const float4 lo, const float4 hi, const FrameF &w, FrameF &cf, int &cur_xf, float omax,
+node_span(const DSceneF &SF, const float4 q0, const float4 lo, const float4 hi, const FrameF &w, FrameF &lf, int &cur_xf, float omax,
           float eo_w, float ed_w, bool standalone, SpanF &s, unsigned int &cost)
 {
     const int flags = __float_as_int(q0.x), xf = __float_as_int(q0.z);
     const int type = flags & FRT_FN_TYPE_MASK;
     s.flags = 0;
-    if (!(flags & FRT_FN_FAST)) {
-        return false;
+    if (!(flags & FRT_FN_FAST) || (type == FRT_PLANE && !standalone)) {
+        return false; /* no fast form; a plane (one crossing) inside a CSG */
     }
-    if (xf != cur_xf) { /* WORLD nodes carry xf = 0 */
-        cur_xf = xf;
-        if (xf == 0) {
-            cf = w;
-        } else {
-            frame_local(cf, SF, xf, w, omax, eo_w, ed_w);
-            if (COUNT) cost += FRT_COST_XFORM;
-        }
-    }
-    if (type == FRT_PLANE) { /* plane_local_intersect, plane.c:11-25: one crossing; stands alone or undecided */
-        if (!standalone) {
+    if (xf == 0) {
+        if (type == FRT_PLANE) {
+            plane_span(w, s);
+        } else if (!leaf_span(type, lo, hi, w, s)) {
             return false;
         }
-        const float tt = -cf.oy * cf.iy;
-        const float E = fmaf(fabsf(tt), cf.c2y, cf.c1y);
-        s.a_lo = s.b_lo = tt - E;
-        s.a_hi = s.b_hi = tt + E;
-        s.flags = 1;
-    } else if (!leaf_span(type, lo, hi, cf, s)) {
-        return false;
+    } else {
+        if (xf != cur_xf) {
+            cur_xf = xf;
+            frame_local(lf, SF, xf, w, omax, eo_w, ed_w);
+            if (COUNT) cost += FRT_COST_XFORM;
+        }
+        if (type == FRT_PLANE) {
+            plane_span(lf, s);
+        } else if (!leaf_span(type, lo, hi, lf, s)) {
+            return false;
+        }
     }
     if (s.flags && (flags & FRT_FN_CASTS)) {
         s.flags |= 6;
@@ -483,10 +495,12 @@ node_span(const DSceneF &SF, const float4 q0, const float4 lo, const float4 hi, 
  * caller), omax / eo_w / ed_w its error terms, [D_lo, D_hi] the interval of the light distance; `fnodes` is the
  * node mirror (in shared memory when the tree is small), `relevant` the hit's shaft-culling mask over nodes 0..31.
  *
- * An outermost CSG node is evaluated from its postfix program (SF.csg_prog, built at upload: leaf node indices and
- * operators in evaluation order) on a three-register span stack, so the walk itself never nests: every step is a
- * group (cull), a CSG (cull, then the program) or a leaf.  The reference's culls of the CSG nodes INSIDE another CSG
- * (csg.c:82-86) are skipped: a nested CSG whose box is missed contributes no crossings either way.
+ * An outermost CSG node is evaluated from its postfix program (SF.csg_prog, built at upload).  Only LEFT-DEEP trees
+ * have one -- ((A op B) op C) op D ..., which is how the scenes build windows, lenses and gears -- so the program is
+ * "leaf, then (leaf, operator) pairs" and one accumulator span suffices; anything else is left to FP64.  The walk
+ * itself therefore never nests: every step is a group (cull), a CSG (cull, then the program) or a leaf.  The
+ * reference's culls of the CSG nodes INSIDE another CSG (csg.c:82-86) are skipped: a nested CSG whose box is missed
+ * contributes no crossings either way.
  * Returns FRT_SH_LIT, FRT_SH_SHADOWED or FRT_SH_UNDECIDED (the latter with a reason code in bits 4.. for the counting
  * build's histogram; callers mask with 15).
  */
@@ -499,7 +513,7 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int
     int i = root;
     const int end = __float_as_int(fnodes[3 * i].y);
     int cur_xf = 0;
-    FrameF cf = w; /* the ray in the frame of transform cur_xf (0 = world) */
+    FrameF lf = w; /* the ray in the frame of transform cur_xf, once cur_xf != 0 */
     int verdict = FRT_SH_LIT;
 
     while (i < end) {
@@ -519,17 +533,17 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int
         if (type >= FRT_CSG) { /* group or CSG: conservative cull by its bounds */
             if (!(flags & FRT_FN_NOCULL)) {
                 const int xf = __float_as_int(q0.z);
-                if (xf != cur_xf) {
-                    cur_xf = xf;
-                    if (xf == 0) {
-                        cf = w;
-                    } else {
-                        frame_local(cf, SF, xf, w, omax, eo_w, ed_w);
+                float tn_lo, tn_hi, tf_lo, tf_hi;
+                if (xf == 0) {
+                    box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                } else {
+                    if (xf != cur_xf) {
+                        cur_xf = xf;
+                        frame_local(lf, SF, xf, w, omax, eo_w, ed_w);
                         if (COUNT) cost += FRT_COST_XFORM;
                     }
+                    box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
                 }
-                float tn_lo, tn_hi, tf_lo, tf_hi;
-                box_f(cf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
                 /* surely missed, or surely wholly behind the origin (only t <= 0 crossings inside) */
                 if (tn_lo > tf_hi || tf_hi < 0.0f) {
                     i = skip;
@@ -542,44 +556,41 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int
             }
             /* CSG: run its postfix program */
             if (!(flags & FRT_FN_FAST)) {
-                return FRT_SH_UNDECIDED | (1 << 4); /* deeper than the span stack, or a group inside an operand */
+                return FRT_SH_UNDECIDED | (1 << 4); /* not left-deep, or a group inside an operand */
             }
-            const int pc0 = __float_as_int(lo.w), pc1 = pc0 + __float_as_int(hi.w);
-            SpanF X, Y, Z;
-            X.flags = Y.flags = Z.flags = 0;
-            X.a_lo = X.a_hi = X.b_lo = X.b_hi = 0.0f;
-            Y = X;
-            Z = X;
-            for (int pc = pc0; pc < pc1; ++pc) {
+            int pc = __float_as_int(lo.w);
+            const int pc1 = pc + __float_as_int(hi.w);
+            {
                 const int code = __ldg(SF.csg_prog + pc);
-                if (code >= 0) {
-                    const float4 l0 = fnodes[3 * code], l1 = fnodes[3 * code + 1], l2 = fnodes[3 * code + 2];
-                    if (COUNT) {
-                        ++visited;
-                        cost += prim_cost(__float_as_int(l0.x) & FRT_FN_TYPE_MASK);
-                    }
-                    SpanF t;
-                    if (!node_span<COUNT>(SF, l0, l1, l2, w, cf, cur_xf, omax, eo_w, ed_w, false, t, cost)) {
-                        return FRT_SH_UNDECIDED | (5 << 4) | ((code & 31) << 8);
-                    }
-                    Z = Y;
-                    Y = X;
-                    X = t;
-                } else {
-                    SpanF r;
-                    r.a_lo = r.a_hi = r.b_lo = r.b_hi = 0.0f;
-                    if (!csg_combine(-code - 1, Y, X, r)) {
-                        return FRT_SH_UNDECIDED | (8 << 4);
-                    }
-                    X = r;
-                    Y = Z;
-                    Z.flags = 0;
+                if (COUNT) {
+                    ++visited;
+                    cost += prim_cost(__float_as_int(fnodes[3 * code].x) & FRT_FN_TYPE_MASK);
+                }
+                if (!node_span<COUNT>(SF, fnodes[3 * code], fnodes[3 * code + 1], fnodes[3 * code + 2], w, lf, cur_xf, omax, eo_w, ed_w,
+                                      false, s, cost)) {
+                    return FRT_SH_UNDECIDED | (5 << 4) | ((code & 31) << 8);
                 }
             }
-            s = X;
+            for (pc += 1; pc < pc1; pc += 2) {
+                const int code = __ldg(SF.csg_prog + pc), op = -__ldg(SF.csg_prog + pc + 1) - 1;
+                if (COUNT) {
+                    ++visited;
+                    cost += prim_cost(__float_as_int(fnodes[3 * code].x) & FRT_FN_TYPE_MASK);
+                }
+                SpanF t, r;
+                if (!node_span<COUNT>(SF, fnodes[3 * code], fnodes[3 * code + 1], fnodes[3 * code + 2], w, lf, cur_xf, omax, eo_w, ed_w,
+                                      false, t, cost)) {
+                    return FRT_SH_UNDECIDED | (5 << 4) | ((code & 31) << 8);
+                }
+                r.a_lo = r.a_hi = r.b_lo = r.b_hi = 0.0f;
+                if (!csg_combine(op, s, t, r)) {
+                    return FRT_SH_UNDECIDED | (8 << 4);
+                }
+                s = r;
+            }
             i = skip;
         } else {
-            if (!node_span<COUNT>(SF, q0, lo, hi, w, cf, cur_xf, omax, eo_w, ed_w, true, s, cost)) {
+            if (!node_span<COUNT>(SF, q0, lo, hi, w, lf, cur_xf, omax, eo_w, ed_w, true, s, cost)) {
                 return FRT_SH_UNDECIDED | (5 << 4) | ((i & 31) << 8);
             }
             i = i + 1;
