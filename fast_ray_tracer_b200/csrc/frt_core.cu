@@ -588,22 +588,21 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
  * to live in the instruction cache (the first, fused version of this stage was 107 KB of SASS and spent half of
  * its issue slots waiting on instruction fetch; see profiles/):
  *
- *   k_light_sum      lighting_microfacet's sums over the light's sample set          renderer.c:894-979
+ *   k_light_pre      sample-set picks, shaft-culling mask, can-the-light-contribute test per hit
  *   k_shadow         light->intensity_at: one shadow ray per (hit, surface sample)   light.c:229-251, renderer.c:73
- *   k_light_resolve  shade_intensity * sums + ambient, weighted into the pixel       renderer.c:904-979, :689-827
+ *   k_light_final    lighting_microfacet for the hits that received light, weighting into the pixel  renderer.c:894-979
  *
  * The reference picks one of cache_len pre-computed sample sets with rand() once per pass (light.c:196); here the
  * pick is a hash of (seed, path id, light, pass).  With cache_len == 1 both passes use set 0 and the result is
  * exactly the reference's.
  */
-struct LightTmp { /* per shaded hit, per light launch; the first 16 bytes are all k_shadow_f32 reads per ray */
-    float ox, oy, oz;             /* over_point rounded to FP32 (origin of the hit's shadow rays in the FP32 filter) */
-    int set_a;                    /* sample set of the shadow pass; -1: the hit cannot receive light, skip its shadow rays */
-    float sum_ndl, sum_b, sum_fb; /* sums over the lighting sample set */
-    int unshadowed;               /* shadow rays that reached the light */
-    double dsum_ndl, dsum_b, dsum_fb; /* the same sums in FP64 (FRT_FLAG_F64_SHADING) */
-    int contributes;              /* some lighting term of the hit is non-zero */
-    unsigned int relevant;        /* shaft culling: bit i = node i may be crossed at t > 0 by a shadow ray of this hit */
+struct LightTmp { /* per shaded hit, per light launch (32 bytes); the first 16 bytes are what k_shadow_f32 reads per ray */
+    float ox, oy, oz;      /* over_point rounded to FP32 (origin of the hit's shadow rays in the FP32 filter) */
+    int set_a;             /* sample set of the shadow pass; -1: the hit cannot receive light, skip its shadow rays */
+    unsigned int relevant; /* shaft culling: bit i = node i may be crossed at t > 0 by a shadow ray of this hit */
+    int set_b;             /* sample set of the lighting pass */
+    int unshadowed;        /* shadow rays that reached the light */
+    int contributes;       /* the light is not wholly behind the surface: the lighting sums can be non-zero */
 };
 
 /*
@@ -622,99 +621,34 @@ __device__ __forceinline__ double sh_rcp(double x) { return 1.0 / x; }
 __device__ __forceinline__ float sh_pow(float x, float y) { return x > 0.f ? exp2f(y * __log2f(x)) : (y == 0.f ? 1.f : 0.f); }
 __device__ __forceinline__ double sh_pow(double x, double y) { return pow(x, y); }
 
-template <typename T, int G>
+/*
+ * Per hit, before its shadow rays: the two sample-set picks, the shaft-culling mask (frt_shadow_f32.cuh; the G lanes of
+ * a hit share the nodes) and a cheap test whether the light can contribute at all -- if every corner of the light's
+ * parallelogram is behind the surface, every sample has N.L < 0, lighting_microfacet adds nothing (renderer.c:927-968)
+ * and the visibility fraction cannot matter: no shadow rays.
+ */
+template <int G>
 __global__ void __launch_bounds__(256)
-k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, const Counters *cnt,
-            int level, int light_idx, const float *__restrict__ flpoints, DSceneF SF, int shaft_on)
+k_light_pre(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, const Counters *cnt, int level,
+            int light_idx, DSceneF SF, int shaft_on)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
-    const frt_light L = S.lights[light_idx];
-    const int NS = L.num_samples;
-    const double *pts = S.lpoints + 3 * L.point_offset;
-    const float *fpts = flpoints + 3 * L.point_offset;
+    const int cache_len = S.lights[light_idx].cache_len;
     const unsigned int lane_g = threadIdx.x % G;
     const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     const unsigned int groups = gridDim.x * blockDim.x / G;
 
     for (unsigned int hbase = (blockIdx.x * blockDim.x + threadIdx.x) / G;; hbase += groups) {
-        /* all lanes of a warp iterate together so that the group shuffles stay converged */
         unsigned int h0 = __shfl_sync(0xffffffffu, hbase, 0);
         if (h0 >= n) {
             break;
         }
         const bool live = hbase < n;
         const LightRec *R = recs + (live ? hbase : 0);
-        const double over[3] = { R->over[0], R->over[1], R->over[2] };
-        const T nrm[3] = { (T)R->n[0], (T)R->n[1], (T)R->n[2] };
-        const T eye[3] = { (T)R->eye[0], (T)R->eye[1], (T)R->eye[2] };
-        const T Ns = (T)R->Ns;
-        const unsigned int rng = R->rng;
-
-        int set_a = 0, set_b = 0;
-        if (L.cache_len > 1) {
-            unsigned long long key = F.seed ^ ((unsigned long long)rng << 20) ^ ((unsigned long long)light_idx << 4);
-            set_a = (int)(mix64(key) % (unsigned long long)L.cache_len);
-            set_b = (int)(mix64(key + 1) % (unsigned long long)L.cache_len);
-        }
-
-        T sum_ndl = 0, sum_b = 0, sum_fb = 0;
-        if (live && (F.use_diffuse || F.use_spec_highlight)) {
-            const T ndote = nrm[0] * eye[0] + nrm[1] * eye[1] + nrm[2] * eye[2];
-            const double *pb = pts + 3 * (size_t)set_b * NS;
-            const float *pbf = fpts + 3 * (size_t)set_b * NS;
-            const float ofx = (float)over[0], ofy = (float)over[1], ofz = (float)over[2];
-            for (int s = lane_g; s < NS; s += G) {
-                T lx, ly, lz;
-                if (sizeof(T) == sizeof(float)) { /* FP32 copy of the sample points: half the bytes of the 157 MB cache */
-                    lx = (T)(__ldg(pbf + 3 * s) - ofx);
-                    ly = (T)(__ldg(pbf + 3 * s + 1) - ofy);
-                    lz = (T)(__ldg(pbf + 3 * s + 2) - ofz);
-                } else {
-                    lx = (T)(__ldg(pb + 3 * s) - over[0]);
-                    ly = (T)(__ldg(pb + 3 * s + 1) - over[1]);
-                    lz = (T)(__ldg(pb + 3 * s + 2) - over[2]);
-                }
-                T inv = sh_rsqrt(lx * lx + ly * ly + lz * lz);
-                lx *= inv;
-                ly *= inv;
-                lz *= inv;
-                T ndl = lx * nrm[0] + ly * nrm[1] + lz * nrm[2];
-                if (ndl >= 0) {
-                    if (F.use_diffuse) {
-                        sum_ndl += ndl;
-                    }
-                    if (F.use_spec_highlight) {
-                        T hx = lx + eye[0], hy = ly + eye[1], hz = lz + eye[2];
-                        T hinv = sh_rsqrt(hx * hx + hy * hy + hz * hz);
-                        hx *= hinv;
-                        hy *= hinv;
-                        hz *= hinv;
-                        T ndh = max((T)0, nrm[0] * hx + nrm[1] * hy + nrm[2] * hz);
-                        T edh_inv = sh_rcp(max((T)0, eye[0] * hx + eye[1] * hy + eye[2] * hz));
-                        T ldh = lx * hx + ly * hy + lz * hz;
-                        T dist_term = (Ns + 2) * sh_pow(ndh, Ns) * (T)(0.5 * M_1_PI);
-                        T gc = 2 * ndh * edh_inv;
-                        T geom = min((T)1, min(gc * ndote, gc * ndl));
-                        T m1 = 1 - ldh;
-                        T m2 = m1 * m1;
-                        T factor = m2 * m2 * m1; /* pow(1 - L.H, 5) */
-                        T brdf = dist_term * geom * sh_rcp(4 * ndl * ndote);
-                        sum_b += brdf;
-                        sum_fb += factor * brdf;
-                    }
-                }
-            }
-        }
-        for (int o = G / 2; o > 0; o >>= 1) {
-            sum_ndl += __shfl_xor_sync(gmask, sum_ndl, o);
-            sum_b += __shfl_xor_sync(gmask, sum_b, o);
-            sum_fb += __shfl_xor_sync(gmask, sum_fb, o);
-        }
-        /* shaft culling mask of this hit (frt_shadow_f32.cuh): the G lanes share the nodes */
+        const float ofx = (float)R->over[0], ofy = (float)R->over[1], ofz = (float)R->over[2];
         unsigned int relevant = 0xffffffffu;
         if (shaft_on) {
             relevant = 0u;
-            const float ofx = (float)over[0], ofy = (float)over[1], ofz = (float)over[2];
             ShaftF sh;
             shaft_setup(sh, SF.shaft + 4 * light_idx, ofx, ofy, ofz);
             const int nn = min(SF.n_nodes, 32);
@@ -731,22 +665,30 @@ k_light_sum(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
             }
         }
         if (live && lane_g == 0) {
-            /* when every lighting term is exactly zero the visibility fraction cannot matter: no shadow rays */
-            const bool contributes = (sum_ndl != 0) || (sum_b != 0) || (sum_fb != 0);
+            int set_a = 0, set_b = 0;
+            if (cache_len > 1) {
+                unsigned long long key = F.seed ^ ((unsigned long long)R->rng << 20) ^ ((unsigned long long)light_idx << 4);
+                set_a = (int)(mix64(key) % (unsigned long long)cache_len);
+                set_b = (int)(mix64(key + 1) % (unsigned long long)cache_len);
+            }
+            bool contributes = false;
+            if (F.use_diffuse || F.use_spec_highlight) {
+                for (int c = 0; c < 4; ++c) {
+                    const float4 p = __ldg(SF.shaft + 4 * light_idx + c);
+                    const double ndl = R->n[0] * ((double)p.x - R->over[0]) + R->n[1] * ((double)p.y - R->over[1]) +
+                                       R->n[2] * ((double)p.z - R->over[2]);
+                    contributes = contributes || !(ndl < 0.0);
+                }
+            }
             LightTmp t;
-            t.sum_ndl = (float)sum_ndl;
-            t.sum_b = (float)sum_b;
-            t.sum_fb = (float)sum_fb;
-            t.dsum_ndl = (double)sum_ndl;
-            t.dsum_b = (double)sum_b;
-            t.dsum_fb = (double)sum_fb;
+            t.ox = ofx;
+            t.oy = ofy;
+            t.oz = ofz;
             t.set_a = (contributes || (F.flags & FRT_FLAG_NO_PRUNE)) ? set_a : -1;
+            t.relevant = relevant;
+            t.set_b = set_b;
             t.unshadowed = 0;
             t.contributes = contributes ? 1 : 0;
-            t.relevant = relevant;
-            t.ox = (float)over[0];
-            t.oy = (float)over[1];
-            t.oz = (float)over[2];
             tmp[hbase] = t;
         }
     }
@@ -976,46 +918,123 @@ k_shadow_exact(DScene S, FrameParams F, const LightRec *__restrict__ recs, Light
     }
 }
 
-/* lighting_microfacet's closing arithmetic (renderer.c:904-979) and the weighting into the pixel */
+/*
+ * lighting_microfacet (renderer.c:894-979) for the hits that received light, and the weighting into the pixel.
+ * G lanes (a power of two <= 32) share a hit and stride over the sample set; partial sums are combined with a
+ * fixed-order butterfly, so the result does not depend on scheduling.  Hits whose shadow rays were all blocked
+ * (equal(shade_intensity, 0), :904) only add their ambient term -- most of a frame lit through a window.
+ * T = float is the production path: the sums feed an 8-bit pixel through a continuous function, so FP32's 1e-7
+ * relative error sits three orders of magnitude under one sRGB LSB; T = double (FRT_FLAG_F64_SHADING) keeps the
+ * reference's arithmetic type.  Every geometric DECISION (hit / miss, shadowed / lit) stays in FP64 in k_extend /
+ * k_shadow_*.
+ */
+template <typename T, int G>
 __global__ void __launch_bounds__(256)
-k_light_resolve(DScene S, FrameParams F, const LightRec *__restrict__ recs, const LightTmp *__restrict__ tmp,
-                double *__restrict__ canvas, const Counters *cnt, int level, int light_idx, double *__restrict__ acc_amb)
+k_light_final(DScene S, FrameParams F, const LightRec *__restrict__ recs, const LightTmp *__restrict__ tmp, double *__restrict__ canvas,
+              const Counters *cnt, int level, int light_idx, const float *__restrict__ flpoints, double *__restrict__ acc_amb)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
-    const frt_light &L = S.lights[light_idx];
+    const frt_light L = S.lights[light_idx];
     const int NS = L.num_samples;
-    const double Li[3] = { L.intensity[0], L.intensity[1], L.intensity[2] };
-    const bool f64 = (F.flags & FRT_FLAG_F64_SHADING) != 0;
-    for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < n; h += gridDim.x * blockDim.x) {
-        const LightTmp t = tmp[h];
-        const LightRec *R = recs + h;
-        double c[3] = { 0.0, 0.0, 0.0 };
-        double intensity = (double)t.unshadowed / (double)NS;
-        if (!(fabs(intensity) < FRT_EPS) && t.contributes) { /* equal(shade_intensity, 0.0), renderer.c:904 */
-            double scaling = intensity / (double)NS;
-            double sum_ndl = f64 ? t.dsum_ndl : (double)t.sum_ndl;
-            double sum_b = f64 ? t.dsum_b : (double)t.sum_b;
-            double sum_fb = f64 ? t.dsum_fb : (double)t.sum_fb;
-            for (int k = 0; k < 3; ++k) {
-                double d = R->Kd[k] * Li[k] * sum_ndl;
-                double sp = Li[k] * (R->Ks[k] * sum_b + (1.0 - R->Ks[k]) * sum_fb);
-                c[k] = (d + sp) * scaling;
-            }
+    const double *pts = S.lpoints + 3 * L.point_offset;
+    const float *fpts = flpoints + 3 * L.point_offset;
+    const unsigned int lane_g = threadIdx.x % G;
+    const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    const unsigned int groups = gridDim.x * blockDim.x / G;
+
+    for (unsigned int hbase = (blockIdx.x * blockDim.x + threadIdx.x) / G;; hbase += groups) {
+        /* all lanes of a warp iterate together so that the group shuffles stay converged */
+        unsigned int h0 = __shfl_sync(0xffffffffu, hbase, 0);
+        if (h0 >= n) {
+            break;
         }
-        if (F.use_ambient) {
-            for (int k = 0; k < 3; ++k) {
-                if (F.use_gi) {
-                    acc_amb[3 * (size_t)h + k] += R->Ka[k] * Li[k]; /* joins the GI terms before the clamp of renderer.c:765 */
+        const bool live = hbase < n;
+        const LightRec *R = recs + (live ? hbase : 0);
+        const LightTmp t = tmp[live ? hbase : 0];
+        const double intensity = (double)t.unshadowed / (double)NS;
+        const bool lit = live && t.contributes && !(fabs(intensity) < FRT_EPS); /* equal(shade_intensity, 0.0), renderer.c:904 */
+
+        T sum_ndl = 0, sum_b = 0, sum_fb = 0;
+        if (lit) {
+            const double over[3] = { R->over[0], R->over[1], R->over[2] };
+            const T nrm[3] = { (T)R->n[0], (T)R->n[1], (T)R->n[2] };
+            const T eye[3] = { (T)R->eye[0], (T)R->eye[1], (T)R->eye[2] };
+            const T Ns = (T)R->Ns;
+            const T ndote = nrm[0] * eye[0] + nrm[1] * eye[1] + nrm[2] * eye[2];
+            const double *pb = pts + 3 * (size_t)t.set_b * NS;
+            const float *pbf = fpts + 3 * (size_t)t.set_b * NS;
+            for (int s = lane_g; s < NS; s += G) {
+                T lx, ly, lz;
+                if (sizeof(T) == sizeof(float)) { /* FP32 copy of the sample points: half the bytes of the 157 MB cache */
+                    lx = (T)(__ldg(pbf + 3 * s) - t.ox);
+                    ly = (T)(__ldg(pbf + 3 * s + 1) - t.oy);
+                    lz = (T)(__ldg(pbf + 3 * s + 2) - t.oz);
                 } else {
-                    c[k] += R->Ka[k] * Li[k];
+                    lx = (T)(__ldg(pb + 3 * s) - over[0]);
+                    ly = (T)(__ldg(pb + 3 * s + 1) - over[1]);
+                    lz = (T)(__ldg(pb + 3 * s + 2) - over[2]);
+                }
+                T inv = sh_rsqrt(lx * lx + ly * ly + lz * lz);
+                lx *= inv;
+                ly *= inv;
+                lz *= inv;
+                T ndl = lx * nrm[0] + ly * nrm[1] + lz * nrm[2];
+                if (ndl >= 0) {
+                    if (F.use_diffuse) {
+                        sum_ndl += ndl;
+                    }
+                    if (F.use_spec_highlight) {
+                        T hx = lx + eye[0], hy = ly + eye[1], hz = lz + eye[2];
+                        T hinv = sh_rsqrt(hx * hx + hy * hy + hz * hz);
+                        hx *= hinv;
+                        hy *= hinv;
+                        hz *= hinv;
+                        T ndh = max((T)0, nrm[0] * hx + nrm[1] * hy + nrm[2] * hz);
+                        T edh_inv = sh_rcp(max((T)0, eye[0] * hx + eye[1] * hy + eye[2] * hz));
+                        T ldh = lx * hx + ly * hy + lz * hz;
+                        T dist_term = (Ns + 2) * sh_pow(ndh, Ns) * (T)(0.5 * M_1_PI);
+                        T gc = 2 * ndh * edh_inv;
+                        T geom = min((T)1, min(gc * ndote, gc * ndl));
+                        T m1 = 1 - ldh;
+                        T m2 = m1 * m1;
+                        T factor = m2 * m2 * m1; /* pow(1 - L.H, 5) */
+                        T brdf = dist_term * geom * sh_rcp(4 * ndl * ndote);
+                        sum_b += brdf;
+                        sum_fb += factor * brdf;
+                    }
                 }
             }
         }
-        double *px = canvas + 4 * (size_t)R->pixel;
-        for (int k = 0; k < 3; ++k) {
-            double v = R->w[k] * c[k];
-            if (v != 0.0) {
-                atomicAdd(px + k, v);
+        for (int o = G / 2; o > 0; o >>= 1) {
+            sum_ndl += __shfl_xor_sync(gmask, sum_ndl, o);
+            sum_b += __shfl_xor_sync(gmask, sum_b, o);
+            sum_fb += __shfl_xor_sync(gmask, sum_fb, o);
+        }
+        if (live && lane_g == 0) {
+            double c[3] = { 0.0, 0.0, 0.0 };
+            if (lit) {
+                const double scaling = intensity / (double)NS;
+                for (int k = 0; k < 3; ++k) {
+                    double d = R->Kd[k] * L.intensity[k] * (double)sum_ndl;
+                    double sp = L.intensity[k] * (R->Ks[k] * (double)sum_b + (1.0 - R->Ks[k]) * (double)sum_fb);
+                    c[k] = (d + sp) * scaling;
+                }
+            }
+            if (F.use_ambient) {
+                for (int k = 0; k < 3; ++k) {
+                    if (F.use_gi) {
+                        acc_amb[3 * (size_t)hbase + k] += R->Ka[k] * L.intensity[k]; /* joins the GI terms before the clamp of renderer.c:765 */
+                    } else {
+                        c[k] += R->Ka[k] * L.intensity[k];
+                    }
+                }
+            }
+            double *px = canvas + 4 * (size_t)R->pixel;
+            for (int k = 0; k < 3; ++k) {
+                double v = R->w[k] * c[k];
+                if (v != 0.0) {
+                    atomicAdd(px + k, v);
+                }
             }
         }
     }
@@ -1887,21 +1906,36 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     return FRT_OK;
 }
 
+static void
+launch_light_pre(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g)
+{
+    const int shaft_on = sc->S.n_roots == 1 && !(F.flags & (FRT_FLAG_F64_SHADOW | FRT_FLAG_NO_SHAFT));
+#define LP(G) k_light_pre<G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, light, sc->SF, shaft_on)
+    switch (g) {
+    case 1: LP(1); break;
+    case 2: LP(2); break;
+    case 4: LP(4); break;
+    case 8: LP(8); break;
+    case 16: LP(16); break;
+    default: LP(32); break;
+    }
+#undef LP
+}
+
 template <typename T>
 static void
-launch_light_sum(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g)
+launch_light_final(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g)
 {
-#define LS(G) k_light_sum<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, light, sc->SF.lpoints, sc->SF, \
-                                                               sc->S.n_roots == 1 && !(F.flags & (FRT_FLAG_F64_SHADOW | FRT_FLAG_NO_SHAFT)))
+#define LF(G) k_light_final<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->canvas, sc->cnt, level, light, sc->SF.lpoints, sc->acc_amb)
     switch (g) {
-    case 1: LS(1); break;
-    case 2: LS(2); break;
-    case 4: LS(4); break;
-    case 8: LS(8); break;
-    case 16: LS(16); break;
-    default: LS(32); break;
+    case 1: LF(1); break;
+    case 2: LF(2); break;
+    case 4: LF(4); break;
+    case 8: LF(8); break;
+    case 16: LF(16); break;
+    default: LF(32); break;
     }
-#undef LS
+#undef LF
 }
 
 static int
@@ -2056,7 +2090,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     CK(cudaEventRecord(sc->ev[0], s));
     CK(cudaMemsetAsync(sc->canvas, 0, cbytes, s));
 
-    const std::vector<int> &gw = sc->light_gw; /* lanes per hit in k_light_sum, chosen per light at upload */
+    const std::vector<int> &gw = sc->light_gw; /* lanes per hit in k_light_pre / k_light_final, chosen per light at upload */
 
     for (unsigned long long first = 0; first < total; first += chunk) {
         unsigned int n = (unsigned int)std::min<unsigned long long>(chunk, total - first);
@@ -2087,11 +2121,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         sc->light_ev.push_back(b);
                     }
                     const int blocks = sm_blocks * 8;
-                    if (F.flags & FRT_FLAG_F64_SHADING) {
-                        launch_light_sum<double>(sc, F, blocks, level, li, gw[li]);
-                    } else {
-                        launch_light_sum<float>(sc, F, blocks, level, li, gw[li]);
-                    }
+                    launch_light_pre(sc, F, blocks, level, li, gw[li]);
                     CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
                     const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
                     if (F.flags & FRT_FLAG_F64_SHADOW) {
@@ -2120,7 +2150,11 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         }
                         launches += 2;
                     }
-                    k_light_resolve<<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->canvas, sc->cnt, level, li, sc->acc_amb);
+                    if (F.flags & FRT_FLAG_F64_SHADING) {
+                        launch_light_final<double>(sc, F, blocks, level, li, gw[li]);
+                    } else {
+                        launch_light_final<float>(sc, F, blocks, level, li, gw[li]);
+                    }
                     launches += 2;
                     ++light_launches;
                 }

@@ -76,7 +76,7 @@ struct DSceneF {
  * that pyramid by a plane cannot be crossed at t > 0 by any of them, and a subtree without a positive crossing neither
  * stops the reference's search nor shadows (group.c:105-123): it is skipped for every ray of the hit.  The test is
  * one-sided (a box that is not provably outside stays), per hit, ~60 flop per node; it runs once per hit in
- * k_light_sum and leaves a bit mask over the first 32 nodes.  Separating planes tried: the pyramid's four sides, the
+ * k_light_pre and leaves a bit mask over the first 32 nodes.  Separating planes tried: the pyramid's four sides, the
  * plane through o facing the light (when every corner is in front of it), and the box's own six faces.
  */
 struct ShaftF {
