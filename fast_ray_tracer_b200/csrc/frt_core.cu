@@ -2134,13 +2134,15 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         launches += 1;
                     } else {
                         const size_t f32_smem = (size_t)sc->S.n_nodes * 48 <= 32768 ? (size_t)sc->S.n_nodes * 48 : 0;
+                        /* many short grid-stride trips balance the uneven per-ray work better than 8 CTAs per SM (measured: 35.0 -> 33.5 ms) */
+                        const int sblocks = getenv("FRT_SHADOW_BLOCKS") ? atoi(getenv("FRT_SHADOW_BLOCKS")) : sm_blocks * 48;
                         CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));
                         if (F.flags & FRT_FLAG_VERIFY_F32) {
-                            k_shadow_f32<2><<<blocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            k_shadow_f32<2><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         } else if (count) {
-                            k_shadow_f32<1><<<blocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            k_shadow_f32<1><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         } else {
-                            k_shadow_f32<0><<<blocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            k_shadow_f32<0><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         }
                         CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         if (count) {
