@@ -49,56 +49,75 @@ CACHE_SETS = 65535
 
 
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md, the clocks line)."""
+    """SM clock, power and throttle reasons sampled every 20 ms through NVML while the GPU is under load (the clocks line
+    of B200_PROFILING.md; NVML is what nvidia-smi reads).  A frame takes tens of milliseconds, so polling nvidia-smi at
+    its 200 ms granularity would see nothing."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {  # nvmlClocksThrottleReason* bits
+        0x0000000000000008: "hw_slowdown",
+        0x0000000000000040: "hw_thermal_slowdown",
+        0x0000000000000020: "sw_thermal_slowdown",
+        0x0000000000000004: "sw_power_cap",
+    }
 
     def __init__(self, device: int):
         self.device = device
-        self.proc = None
-        self.lines = []
+        self.samples = []
         self.thread = None
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        self.handle = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            idx = self.device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(tok.strip().isdigit() for tok in vis.split(",")):
+                ids = [int(tok) for tok in vis.split(",")]
+                if idx < len(ids):
+                    idx = ids[idx]
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
             return
-        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread = threading.Thread(target=self._poll, daemon=True)
         self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                util = n.nvmlDeviceGetUtilizationRates(self.handle).gpu
+                self.samples.append((sm, smax, power, reasons, util))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower() == "active":
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": []}
+        sm = [x[0] for x in self.samples]
+        reasons = set()
+        for x in self.samples:
+            for bit, name in self.REASONS.items():
+                if x[3] & bit:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(x[1] for x in self.samples),
+                "power_w_max": max(x[2] for x in self.samples), "samples": len(sm), "reasons": sorted(reasons),
+                "how": "NVML every 20 ms from the first warm-up frame to the end of the end-to-end loop"}
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
@@ -230,12 +249,12 @@ def cuda_arm(args) -> dict:
                 canvas = frame
             return st, canvas
 
-        for w in range(args.warmup):
-            step(100 + w)
-            flush.zero_()
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
+        for w in range(args.warmup):
+            step(100 + w)
+            flush.zero_()
         frame_ms, light_ms, launches, light_launches = [], [], 0, 0
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -256,7 +275,6 @@ def cuda_arm(args) -> dict:
             light_launches += st.light_launches
         barrier()
         wall_s = time.perf_counter() - t_wall0
-        clk = clocks.stop() if rank == 0 else None
 
         t = torch.tensor([dev_ms_total, sum(light_ms), float(launches), float(light_launches)], dtype=torch.float64, device=dev)
         tmax = t.clone()
@@ -296,6 +314,7 @@ def cuda_arm(args) -> dict:
         if world > 1:
             dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         e2e_s = float(e2e_t[0])
+        clk = clocks.stop() if rank == 0 else None
 
     fp64_peak, fp32_peak = frt.measure_fma_peak(local)
     line = None
@@ -373,19 +392,22 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(reference_arm(args)), flush=True)
+            print(json.dumps(reference_arm(args)), file=real_stdout, flush=True)
         return 0
 
     line = cuda_arm(args)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         import torch.distributed as dist
 
