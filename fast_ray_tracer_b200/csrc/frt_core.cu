@@ -878,8 +878,8 @@ k_to_float(const double *__restrict__ src, float *__restrict__ dst, size_t n)
 /* the rays the FP32 pass could not decide, re-traced in FP64 (also the whole shadow pass under FRT_FLAG_F64_SHADOW) */
 template <bool COUNT, bool ALL>
 __global__ void __launch_bounds__(256)
-k_shadow_exact(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
-               int light_idx, const unsigned long long *__restrict__ queue, unsigned int qcap)
+k_shadow_exact(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
+               int level, int light_idx, const unsigned long long *__restrict__ queue, unsigned int qcap)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
     const int NS = S.lights[light_idx].num_samples;
@@ -901,7 +901,34 @@ k_shadow_exact(DScene S, FrameParams F, const LightRec *__restrict__ recs, Light
         }
         const double dist = normalise_shadow_ray(sr, dist2);
         if (COUNT && ALL) ++n_shadow;
-        if (!trace_shadow<COUNT>(S, sr, dist, &overflow, &n_nodes, &n_flops)) {
+        bool shadowed;
+        if (ALL || S.n_roots != 1) {
+            shadowed = trace_shadow<COUNT>(S, sr, dist, &overflow, &n_nodes, &n_flops); /* pure FP64 (FRT_FLAG_F64_SHADOW) */
+        } else {
+            /* FP64 leaves and verdicts, FP32 conservative culls (trace_shadow_mixed) */
+            FrameF w;
+            w.ox = (float)sr.ox;
+            w.oy = (float)sr.oy;
+            w.oz = (float)sr.oz;
+            w.dx = (float)sr.dx;
+            w.dy = (float)sr.dy;
+            w.dz = (float)sr.dz;
+            const float omax = fmaxf(fmaxf(fabsf(w.ox), fabsf(w.oy)), fabsf(w.oz));
+            const float eo_o = 2.0f * FRT_F32_U * omax;
+            const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, eo_o);
+            const float ed_w = FRT_F32_G; /* the FP64 unit direction rounded to FP32 */
+            frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
+            shadowed = trace_shadow_mixed<COUNT>(S, SF, sr, dist, w, omax, eo_o, ed_w, &overflow, &n_nodes, &n_flops);
+            if (F.flags & FRT_FLAG_VERIFY_F32) { /* the deferred rays are checked against the pure FP64 walk too */
+                unsigned long long dn = 0, df = 0;
+                const bool ref = trace_shadow<false>(S, sr, dist, &overflow, &dn, &df);
+                if (ref != shadowed) {
+                    atomicAdd(&cnt->f32_mismatch, 1ull);
+                    shadowed = ref;
+                }
+            }
+        }
+        if (!shadowed) {
             atomicAdd(&tmp[h].unshadowed, 1);
         }
     }
@@ -2126,9 +2153,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                     const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
                     if (F.flags & FRT_FLAG_F64_SHADOW) {
                         if (count) {
-                            k_shadow_exact<true, true><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_exact<true, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         } else {
-                            k_shadow_exact<false, true><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_exact<false, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         }
                         CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         launches += 1;
@@ -2146,9 +2173,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         }
                         CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         if (count) {
-                            k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         } else {
-                            k_shadow_exact<false, false><<<blocks, 256, 0, s>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_exact<false, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         }
                         launches += 2;
                     }

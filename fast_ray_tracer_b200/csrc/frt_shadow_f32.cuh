@@ -612,3 +612,173 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int
     }
     return verdict;
 }
+
+/*
+ * The FP64 traversal (trace_shadow, frt_device.cuh) with its CULLS taken from the FP32 mirror: the walk, the group /
+ * CSG box tests and the behind-the-origin test use the conservative FP32 slabs of this file (one 48-byte node record,
+ * three loads issued together, instead of a header load followed by a dependent bounding-box load), every LEAF is still
+ * intersected in FP64 on the exact ray and every verdict is taken in FP64.  Descending where the reference culls
+ * changes nothing (the children lie inside the box), so the answer is trace_shadow's.  This is what re-traces the
+ * rays the filter deferred -- on mesh scenes (triangles have no fast form) that is every shadow ray, and the
+ * reference's divided tree makes them long: the 6-dragon scene visits 357 nodes per shadow ray, the longest rays tens
+ * of thousands, and the kernel's duration is the latency of the longest ray.
+ */
+template <bool COUNT>
+__device__ __forceinline__ bool
+trace_shadow_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, double distance, const FrameF &w, float omax, float eo_w,
+                   float ed_w, int *overflow, unsigned long long *nodes_visited, unsigned long long *flops)
+{
+    struct Frame {
+        int right, skip, start, mid, op;
+    };
+    CsgHit buf[FRT_CSG_CAP];
+    Frame st[FRT_CSG_DEPTH];
+    int sp = 0, n = 0;
+    unsigned int visited = 0, cost = 0;
+    bool result = false;
+    const float4 *fnodes = SF.fnodes;
+    int i = __ldg(S.roots);
+    const int end = __float_as_int(__ldg(fnodes + 3 * i).y);
+    int cur_xf_f = 0, cur_xf_d = 0;
+    FrameF lf = w;
+    Ray lr = wr;
+    InvDir inv = inv_dir(wr);
+
+    while (i < end) {
+        const float4 q0 = __ldg(fnodes + 3 * i), lo = __ldg(fnodes + 3 * i + 1), hi = __ldg(fnodes + 3 * i + 2);
+        const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
+        const int type = flags & FRT_FN_TYPE_MASK;
+        if (COUNT) {
+            ++visited;
+            cost += (type >= FRT_CSG) ? FRT_COST_BBOX : prim_cost(type);
+        }
+        if (type >= FRT_CSG) {
+            bool miss = false;
+            if (!(flags & FRT_FN_NOCULL)) {
+                const int xf = __float_as_int(q0.z);
+                float tn_lo, tn_hi, tf_lo, tf_hi;
+                if (xf == 0) {
+                    box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                } else {
+                    if (xf != cur_xf_f) {
+                        cur_xf_f = xf;
+                        frame_local(lf, SF, xf, w, omax, eo_w, ed_w);
+                    }
+                    box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                }
+                miss = tn_lo > tf_hi || (sp == 0 && tf_hi < 0.0f);
+            }
+            if (miss) {
+                i = skip;
+            } else {
+                if (type == FRT_CSG) {
+                    if (sp == FRT_CSG_DEPTH) {
+                        *overflow = 1;
+                        return false;
+                    }
+                    st[sp++] = Frame{ __float_as_int(q0.w), skip, n, -1, (flags >> FRT_FN_OP_SHIFT) & 3 };
+                }
+                i = i + 1;
+            }
+        } else {
+            const NodeA a = load_node_a(S, i);
+            const NodeB b = load_node_b(S, i);
+            if (a.xform != cur_xf_d) {
+                cur_xf_d = a.xform;
+                if (cur_xf_d == 0) {
+                    lr = wr;
+                } else {
+                    lr = ray_to_local(S, cur_xf_d, wr);
+                    if (COUNT) cost += FRT_COST_XFORM;
+                }
+                inv = inv_dir(lr);
+            }
+            double t[4], uv[2];
+            const int k = prim_intersect_inv(a.type, S.params + (b.param < 0 ? 0 : b.param), lr, inv, t, uv);
+            if (sp == 0) {
+                bool stop = false;
+                double tmin = CUDART_INF;
+                for (int j = 0; j < k; ++j) {
+                    stop = stop || !(t[j] <= 0);
+                    if (t[j] > 0 && t[j] < tmin) {
+                        tmin = t[j];
+                    }
+                }
+                if (stop) {
+                    result = S.mats[a.material].casts_shadow && tmin < distance;
+                    break;
+                }
+            } else {
+                for (int j = 0; j < k; ++j) {
+                    if (n == FRT_CSG_CAP) {
+                        *overflow = 1;
+                        return false;
+                    }
+                    buf[n].t = t[j];
+                    buf[n].leaf = i;
+                    ++n;
+                }
+            }
+            i = i + 1;
+        }
+        bool done = false;
+        while (sp > 0) { /* close every CSG whose left / right operand just ended (csg.c:104-118, :43-71) */
+            Frame &f = st[sp - 1];
+            if (f.mid < 0 && i >= f.right) {
+                f.mid = n;
+            }
+            if (i < f.skip) {
+                break;
+            }
+            if (f.mid - f.start > 0 && n - f.mid > 0) {
+                for (int x = f.start + 1; x < n; ++x) {
+                    CsgHit h = buf[x];
+                    int y = x - 1;
+                    while (y >= f.start && buf[y].t > h.t) {
+                        buf[y + 1] = buf[y];
+                        --y;
+                    }
+                    buf[y + 1] = h;
+                }
+            }
+            bool inl = false, inr = false;
+            int out = f.start;
+            for (int x = f.start; x < n; ++x) {
+                const bool lhit = buf[x].leaf < f.right;
+                if (csg_allowed(f.op, lhit, inl, inr)) {
+                    buf[out++] = buf[x];
+                }
+                if (lhit) {
+                    inl = !inl;
+                } else {
+                    inr = !inr;
+                }
+            }
+            n = out;
+            --sp;
+            if (sp == 0) {
+                bool stop = false;
+                double tmin = CUDART_INF;
+                for (int x = 0; x < n; ++x) {
+                    stop = stop || !(buf[x].t <= 0);
+                    if (buf[x].t > 0 && buf[x].t < tmin && S.mats[load_node_a(S, buf[x].leaf).material].casts_shadow) {
+                        tmin = buf[x].t;
+                    }
+                }
+                n = 0;
+                if (stop) {
+                    result = tmin < distance;
+                    done = true;
+                }
+            }
+        }
+        if (done) {
+            break;
+        }
+    }
+    if (COUNT) {
+        *nodes_visited += visited;
+        *flops += cost;
+    }
+    return result;
+}

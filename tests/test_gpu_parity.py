@@ -147,3 +147,9 @@ def test_six_dragons_through_the_divided_group_tree(frt):
     canvas, stats = frt.render_multi(desc)
     rep = parity_report(canvas[..., :3], ref)
     assert rep["within_1lsb"] >= GATE_WITHIN_1LSB, rep
+    # every shadow ray of a mesh scene is deferred to the FP64 pass with FP32 culls; check it against the pure FP64 walk
+    from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_VERIFY_F32
+
+    desc.set_resolution(300, 120)
+    _, st = frt.render_multi(desc, flags=FRT_FLAG_VERIFY_F32 | FRT_FLAG_COUNT_RAYS)
+    assert st.shadow_mismatch == 0 and st.shadow_deferred > 0, st
