@@ -20,6 +20,7 @@ FRT_FLAG_F64_SHADING = 4
 FRT_FLAG_F64_SHADOW = 8
 FRT_FLAG_VERIFY_F32 = 16
 FRT_FLAG_NO_SHAFT = 32
+FRT_FLAG_NO_BULK = 64
 
 
 class FrtError(RuntimeError):

@@ -114,9 +114,11 @@ struct Counters {
     unsigned int n_rays[8];   /* rays queued for level l */
     unsigned int n_hits[8];   /* light records of level l */
     unsigned int overflow_queue, overflow_csg;
-    unsigned int n_deferred, pad;  /* shadow rays the FP32 pass left undecided in the current k_shadow_f32 launch */
+    unsigned int n_deferred;  /* shadow rays the FP32 pass left undecided in the current k_shadow_f32 launch */
+    unsigned int n_pending;   /* hits whose shadow rays are traced one by one in the current light launch */
     unsigned long long rays_secondary, rays_shadow, hits_shaded, shadow_nodes, light_flops;
     unsigned long long deferred_total, f32_mismatch, rays_gather;
+    unsigned long long rays_bulk; /* shadow rays decided per hit by k_shadow_bulk */
     unsigned long long undecided_node[32]; /* debug: node at which a leaf verdict was undecided */
     unsigned long long undecided_reason[10]; /* counting build: why the FP32 filter deferred a ray (codes in frt_shadow_f32.cuh) */
 };
@@ -602,7 +604,8 @@ struct LightTmp { /* per shaded hit, per light launch (32 bytes); the first 16 b
     unsigned int relevant; /* shaft culling: bit i = node i may be crossed at t > 0 by a shadow ray of this hit */
     int set_b;             /* sample set of the lighting pass */
     int unshadowed;        /* shadow rays that reached the light */
-    int contributes;       /* the light is not wholly behind the surface: the lighting sums can be non-zero */
+    int contributes;       /* bit 0: the light is not wholly behind the surface: the lighting sums can be non-zero;
+                              bit 1: every shadow ray of the hit was decided at once by k_shadow_bulk, bit 2: ... as lit */
 };
 
 /*
@@ -695,6 +698,53 @@ k_light_pre(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
 }
 
 /*
+ * Per hit, after k_light_pre: try to decide ALL shadow rays of the hit at once (trace_shadow_bulk, frt_shadow_f32.cuh)
+ * and compact the hits that still need their rays traced into `pending`.  MODE as in k_shadow_f32: in counting (1) and
+ * verifying (2) frames the bulk-decided hits stay in the list so that k_shadow_f32 can count / re-trace their rays; a
+ * verifying frame takes its visibility counts from those FP64 re-traces, like it does for the per-ray filter.
+ */
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
+              int light_idx, unsigned int *__restrict__ pending, int bulk_on)
+{
+    const unsigned int n = min(cnt->n_hits[level], F.capacity);
+    const int NS = S.lights[light_idx].num_samples;
+    const int root = __ldg(S.roots);
+    unsigned long long n_bulk = 0;
+    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
+        const unsigned int h = base + (threadIdx.x & 31);
+        bool want = false;
+        if (h < n && tmp[h].set_a >= 0) {
+            want = true;
+            if (bulk_on) {
+                ShaftD sh;
+                shaft_d_setup(sh, SF.shaft64 + 12 * light_idx, recs[h].over, SF.bmax, SF.smin, SF.ealign);
+                const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh);
+                if (res != FRT_SH_UNDECIDED) {
+                    tmp[h].contributes |= 2 | (res == FRT_SH_LIT ? 4 : 0);
+                    if (MODE != 2) {
+                        tmp[h].unshadowed = res == FRT_SH_LIT ? NS : 0;
+                    }
+                    n_bulk += (unsigned int)NS;
+                    want = MODE != 0;
+                }
+            }
+        }
+        const unsigned int slot = warp_append(&cnt->n_pending, want);
+        if (want) {
+            pending[slot] = h;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_bulk += __shfl_down_sync(0xffffffffu, n_bulk, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n_bulk) {
+        atomicAdd(&cnt->rays_bulk, n_bulk);
+    }
+}
+
+/*
  * One thread per (hit, surface sample): item = hit * num_samples + sample, so a warp holds 32 consecutive samples
  * of one hit (or the tail of one and the head of the next) -- rays with a common origin and nearly parallel
  * directions, which walk the tree together.  The unshadowed count of a hit is reduced inside the warp
@@ -742,7 +792,8 @@ normalise_shadow_ray(Ray &sr, double dist2)
 template <int MODE>
 __global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
 k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
-             int level, int light_idx, unsigned long long *__restrict__ queue, unsigned int qcap, int nodes_in_smem)
+             const unsigned int *__restrict__ pending, int light_idx, unsigned long long *__restrict__ queue, unsigned int qcap,
+             int nodes_in_smem)
 {
     constexpr bool COUNT = MODE != 0;
     extern __shared__ float4 s_nodes[];
@@ -754,13 +805,12 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
         __syncthreads();
         fnodes = s_nodes;
     }
-    const unsigned int n = min(cnt->n_hits[level], F.capacity);
+    const unsigned int n = min(cnt->n_pending, F.capacity); /* hits k_shadow_bulk left to be traced ray by ray */
     const int NS = S.lights[light_idx].num_samples;
     const float *fpts = SF.lpoints + 3 * S.lights[light_idx].point_offset;
     const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
     const unsigned long long total = (unsigned long long)n * (unsigned int)NS;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const bool small = total <= 0xffffffffull;
     const unsigned long long ns_magic = NS > 1 ? ~0ull / (unsigned int)NS + 1ull : 0ull; /* ceil(2^64 / NS) */
     const int root = __ldg(S.roots);
     int overflow = 0;
@@ -772,15 +822,19 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
         int s = 0;
         float4 head = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         if (item < total) {
-            h = NS > 1 ? (unsigned int)__umul64hi(item, ns_magic) : (unsigned int)item; /* item / NS, exact while item * NS < 2^64 */
-            s = (int)(item - (unsigned long long)h * (unsigned int)NS);
+            const unsigned int idx = NS > 1 ? (unsigned int)__umul64hi(item, ns_magic) : (unsigned int)item; /* item / NS, exact while item * NS < 2^64 */
+            s = (int)(item - (unsigned long long)idx * (unsigned int)NS);
+            h = __ldg(pending + idx);
             head = *reinterpret_cast<const float4 *>(tmp + h);
         }
         const int set_a = __float_as_int(head.w);
         const unsigned int relevant = set_a >= 0 ? tmp[h].relevant : 0u;
+        const int bulk = (MODE != 0 && set_a >= 0) ? (tmp[h].contributes >> 1) & 3 : 0; /* bit 0: decided per hit, bit 1: as lit */
         int res = FRT_SH_SHADOWED;
         if (set_a >= 0) {
-            if (S.n_roots != 1) {
+            if (bulk) {
+                res = MODE == 2 && (bulk & 2) ? FRT_SH_LIT : FRT_SH_SHADOWED; /* counting frame: the hit's count is already set */
+            } else if (S.n_roots != 1) {
                 res = FRT_SH_UNDECIDED; /* several top-level shapes (world.c:189-191): never generated; FP64 handles it */
             } else {
                 /* the FP32 ray: both world points rounded to FP32, difference and normalisation in FP32 */
@@ -800,8 +854,8 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                 const float pmax = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
                 /* origin rounded to FP32: 2u |o|; a WORLD box bound rounded to FP32 adds 2u Bmax to every slab numerator */
                 const float eo_o = 2.0f * FRT_F32_U * omax;
-                const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, eo_o);
-                const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G);
+                const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, fmaf(SF.ealign, omax, eo_o));
+                const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G + SF.ealign);
                 frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
                 const float Df = len2 * rinv;
                 res = trace_shadow_f32<COUNT>(SF, fnodes, root, relevant, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
@@ -817,7 +871,7 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                 int sa2;
                 Ray er;
                 double dist2;
-                shadow_item(S, recs, tmp, pts, NS, item, small, h2, sa2, er, dist2);
+                shadow_item(S, recs, tmp, pts, NS, (unsigned long long)h * (unsigned int)NS + (unsigned int)s, false, h2, sa2, er, dist2);
                 const double dist = normalise_shadow_ray(er, dist2);
                 unsigned long long dn = 0, df = 0;
                 const bool sh = trace_shadow<false>(S, er, dist, &overflow, &dn, &df);
@@ -830,7 +884,7 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
         const unsigned int slot = warp_append(&cnt->n_deferred, res == FRT_SH_UNDECIDED);
         if (res == FRT_SH_UNDECIDED) {
             if (slot < qcap) {
-                queue[slot] = item;
+                queue[slot] = (unsigned long long)h * (unsigned int)NS + (unsigned int)s;
             } else {
                 atomicOr(&cnt->overflow_queue, 1u);
             }
@@ -915,8 +969,8 @@ k_shadow_exact(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
             w.dz = (float)sr.dz;
             const float omax = fmaxf(fmaxf(fabsf(w.ox), fabsf(w.oy)), fabsf(w.oz));
             const float eo_o = 2.0f * FRT_F32_U * omax;
-            const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, eo_o);
-            const float ed_w = FRT_F32_G; /* the FP64 unit direction rounded to FP32 */
+            const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, fmaf(SF.ealign, omax, eo_o));
+            const float ed_w = FRT_F32_G + SF.ealign; /* the FP64 unit direction rounded to FP32 */
             frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
             shadowed = trace_shadow_mixed<COUNT>(S, SF, sr, dist, w, omax, eo_o, ed_w, &overflow, &n_nodes, &n_flops);
             if (F.flags & FRT_FLAG_VERIFY_F32) { /* the deferred rays are checked against the pure FP64 walk too */
@@ -979,7 +1033,7 @@ k_light_final(DScene S, FrameParams F, const LightRec *__restrict__ recs, const 
         const LightRec *R = recs + (live ? hbase : 0);
         const LightTmp t = tmp[live ? hbase : 0];
         const double intensity = (double)t.unshadowed / (double)NS;
-        const bool lit = live && t.contributes && !(fabs(intensity) < FRT_EPS); /* equal(shade_intensity, 0.0), renderer.c:904 */
+        const bool lit = live && (t.contributes & 1) && !(fabs(intensity) < FRT_EPS); /* equal(shade_intensity, 0.0), renderer.c:904 */
 
         T sum_ndl = 0, sum_b = 0, sum_fb = 0;
         if (lit) {
@@ -1150,7 +1204,7 @@ struct frt_scene {
     DCamera C{};
     frt_config cfg{};
     std::vector<void *> allocs;
-    std::vector<int> light_gw;
+    std::vector<int> light_gw, light_ns;
     double *canvas = nullptr;     /* hsize*vsize*4 doubles */
     double *samples = nullptr;
     int samples_u = 0, samples_v = 0;
@@ -1161,6 +1215,7 @@ struct frt_scene {
     HitQ hq{};
     LightRec *recs = nullptr;
     LightTmp *ltmp = nullptr;
+    unsigned int *pending = nullptr;  /* hits whose shadow rays k_shadow_bulk left to the per-ray kernels */
     unsigned long long *dq = nullptr; /* (hit, sample) items the FP32 shadow pass deferred to the FP64 pass */
     unsigned int dq_cap = 0;
     Counters *cnt = nullptr;
@@ -1199,6 +1254,7 @@ struct FrameSet {
     HitQ hq{};
     LightRec *recs = nullptr;
     LightTmp *ltmp = nullptr;
+    unsigned int *pending = nullptr;
     unsigned long long *dq = nullptr;
     unsigned int dq_cap = 0;
     Counters *cnt = nullptr;
@@ -1225,6 +1281,7 @@ scene_take(frt_scene *sc, FrameSet &f)
     sc->hq = f.hq;
     sc->recs = f.recs;
     sc->ltmp = f.ltmp;
+    sc->pending = f.pending;
     sc->dq = f.dq;
     sc->dq_cap = f.dq_cap;
     sc->cnt = f.cnt;
@@ -1241,6 +1298,7 @@ scene_give(frt_scene *sc, FrameSet &f)
     f.hq = sc->hq;
     f.recs = sc->recs;
     f.ltmp = sc->ltmp;
+    f.pending = sc->pending;
     f.dq = sc->dq;
     f.dq_cap = sc->dq_cap;
     f.cnt = sc->cnt;
@@ -1412,10 +1470,13 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
 {
     std::vector<float4> fx((size_t)4 * d->n_xforms), fn((size_t)3 * d->n_nodes), wb((size_t)2 * d->n_nodes);
     std::vector<float4> shaft((size_t)4 * std::max(d->n_lights, 1));
+    std::vector<double> shaft64((size_t)12 * std::max(d->n_lights, 1), 0.0);
+    double smin = 1.0, tilt = 0.0;
     std::vector<int> aligned(d->n_xforms, 0), perm((size_t)3 * d->n_xforms, 0);
     for (int i = 0; i < d->n_xforms; ++i) {
         const double *m = d->xforms[i].inv;
         float R[3];
+        double row_tilt[3] = { 0.0, 0.0, 0.0 };
         bool ok = true;
         bool used[3] = { false, false, false };
         for (int k = 0; k < 3; ++k) {
@@ -1426,15 +1487,24 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
             for (int j = 1; j < 3; ++j) {
                 if (fabs(m[4 * k + j]) > fabs(m[4 * k + big])) big = j;
             }
+            double off = 0.0;
             for (int j = 0; j < 3; ++j) {
-                if (j != big && fabs(m[4 * k + j]) > 1e-12 * fabs(m[4 * k + big])) ok = false;
+                if (j != big) off += fabs(m[4 * k + j]);
             }
+            /* quarter turns built from a rounded pi leave off-axis entries of ~5e-12 (every wall of the Cornell box):
+             * still axis-aligned for the filter, the tilt goes into its error terms (DSceneF::ealign) */
+            if (off > 1e-9 * fabs(m[4 * k + big])) ok = false;
+            row_tilt[k] = off / std::max(fabs(m[4 * k + big]), 1e-300);
             if (m[4 * k + big] == 0.0 || used[big]) ok = false;
             used[big] = true;
             perm[3 * i + k] = big;
         }
         fx[4 * i + 3] = make_float4(R[0], R[1], R[2], 0.f);
         aligned[i] = ok ? 1 : 0;
+        for (int k = 0; ok && k < 3; ++k) {
+            smin = std::min(smin, fabs(m[4 * k + perm[3 * i + k]]));
+            tilt = std::max(tilt, row_tilt[k]);
+        }
     }
     auto down = [](double x) { float f = (float)x; return ((double)f > x) ? nextafterf(f, -INFINITY) : f; };
     auto up = [](double x) { float f = (float)x; return ((double)f < x) ? nextafterf(f, INFINITY) : f; };
@@ -1692,6 +1762,9 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
         }
         for (int q = 0; q < 4; ++q) {
             shaft[4 * li + q] = make_float4((float)c[q][0], (float)c[q][1], (float)c[q][2], 0.f);
+            for (int k = 0; k < 3; ++k) {
+                shaft64[12 * li + 3 * q + k] = c[q][k];
+            }
         }
     }
     int rc = upload(sc, fx.data(), fx.size(), &sc->SF.fx);
@@ -1702,6 +1775,10 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     if (rc != FRT_OK) return rc;
     rc = upload(sc, prog.data(), prog.size(), &sc->SF.csg_prog);
     if (rc != FRT_OK) return rc;
+    rc = upload(sc, shaft64.data(), shaft64.size(), &sc->SF.shaft64);
+    if (rc != FRT_OK) return rc;
+    sc->SF.smin = (float)(smin * (1.0 - 1e-6));
+    sc->SF.ealign = (float)(2.0 * tilt * (1.0 + 1e-6));
     rc = upload(sc, fn.data(), fn.size(), &sc->SF.fnodes);
     if (rc != FRT_OK) return rc;
     sc->SF.bmax = nextafterf((float)(bmax * (1.0 + 1e-6)), INFINITY);
@@ -1813,6 +1890,7 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
     sc->light_gw.resize(d->n_lights);
     for (int i = 0; i < d->n_lights; ++i) {
         sc->light_gw[i] = pick_group_width(d->lights[i].num_samples);
+        sc->light_ns.push_back(d->lights[i].num_samples);
     }
 
     size_t cbytes = (size_t)c.hsize * c.vsize * 4 * sizeof(double);
@@ -1916,6 +1994,7 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     FA(sc->hq.t); FA(sc->hq.u); FA(sc->hq.v); FA(sc->hq.leaf);
     FA(sc->recs);
     FA(sc->ltmp);
+    FA(sc->pending);
 #undef FA
     {
         unsigned long long want_q = std::min<unsigned long long>((unsigned long long)capacity * 4ull, 0x7fffffffull);
@@ -2163,13 +2242,19 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         const size_t f32_smem = (size_t)sc->S.n_nodes * 48 <= 32768 ? (size_t)sc->S.n_nodes * 48 : 0;
                         /* many short grid-stride trips balance the uneven per-ray work better than 8 CTAs per SM (measured: 35.0 -> 33.5 ms) */
                         const int sblocks = getenv("FRT_SHADOW_BLOCKS") ? atoi(getenv("FRT_SHADOW_BLOCKS")) : sm_blocks * 48;
-                        CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));
+                        CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, 2 * sizeof(unsigned int), s)); /* n_deferred, n_pending */
+                        /* per hit: every shadow ray at once where the shaft's intervals separate (small trees, area lights) */
+                        const int bulk_on = sc->S.n_roots == 1 && sc->S.n_nodes <= 32 && sc->light_ns[li] >= 4 &&
+                                            !(F.flags & (FRT_FLAG_NO_SHAFT | FRT_FLAG_NO_BULK));
                         if (F.flags & FRT_FLAG_VERIFY_F32) {
-                            k_shadow_f32<2><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            k_shadow_bulk<2><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, bulk_on);
+                            k_shadow_f32<2><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         } else if (count) {
-                            k_shadow_f32<1><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            k_shadow_bulk<1><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, bulk_on);
+                            k_shadow_f32<1><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         } else {
-                            k_shadow_f32<0><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            k_shadow_bulk<0><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, bulk_on);
+                            k_shadow_f32<0><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, li, sc->dq, sc->dq_cap, f32_smem != 0);
                         }
                         CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         if (count) {
@@ -2177,7 +2262,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         } else {
                             k_shadow_exact<false, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         }
-                        launches += 2;
+                        launches += 3;
                     }
                     if (F.flags & FRT_FLAG_F64_SHADING) {
                         launch_light_final<double>(sc, F, blocks, level, li, gw[li]);
@@ -2230,6 +2315,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         totals.deferred_total += hc.deferred_total;
         totals.f32_mismatch += hc.f32_mismatch;
         totals.rays_gather += hc.rays_gather;
+        totals.rays_bulk += hc.rays_bulk;
         for (int k = 0; k < 10; ++k) {
             totals.undecided_reason[k] += hc.undecided_reason[k];
         }
@@ -2268,6 +2354,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         for (int k = 0; k < 10; ++k) {
             st->shadow_reasons[k] = totals.undecided_reason[k];
         }
+        st->shadow_reasons[0] = totals.rays_bulk; /* slot 0 is no deferral reason: shadow rays decided per hit (k_shadow_bulk) */
         st->kernel_launches = launches;
         st->light_launches = light_launches;
         st->rows_rendered = F.n_owned_rows;

@@ -66,7 +66,11 @@ struct DSceneF {
     const float4 *wbox;   /* per node: WORLD-space bounding box {min.xyz, 0} {max.xyz, 0}, rounded outward (shaft culling) */
     const float4 *shaft;  /* per light: 4 corners of a parallelogram that contains every surface sample of the light */
     const int *csg_prog;  /* postfix programs of the outermost CSG nodes: node index of a leaf, or -(op + 1) */
+    const double *shaft64;/* per light: the same 4 corners in FP64, 12 doubles (trace_shadow_bulk) */
     float bmax;           /* largest finite |bound| of a WORLD node */
+    float smin;           /* smallest |axis scale| of an axis-aligned world->local transform (<= 1) */
+    float ealign;         /* 2 x the largest off-axis / on-axis ratio of a transform treated as axis-aligned (<= 2e-9):
+                             a WORLD box test sees the world point up to ealign |o|max, the direction up to ealign, off */
     int n_nodes;
 };
 
@@ -246,10 +250,13 @@ box_f(const FrameF &f, const float4 lo, const float4 hi, float &tn_lo, float &tn
 
 /* The crossings of one operand (a leaf, or a closed CSG) as ONE interval: enter in [a_lo, a_hi], exit in [b_lo, b_hi],
  * enter < exit for sure.  flags: 1 = present, 2 / 4 = the enter / exit surface casts shadows. */
-struct SpanF {
-    float a_lo, a_hi, b_lo, b_hi;
+template <typename T>
+struct SpanT {
+    T a_lo, a_hi, b_lo, b_hi;
     int flags;
 };
+typedef SpanT<float> SpanF;   /* one ray, FP32 rounding intervals */
+typedef SpanT<double> SpanD;  /* every shadow ray of a hit at once (trace_shadow_bulk) */
 
 /*
  * csg_filter_intersections (csg.c:43-71) for two operands that are one interval each.  Walking the merged, sorted
@@ -261,8 +268,9 @@ struct SpanF {
  * Each end keeps the casts_shadow bit of the leaf it came from.  Returns false when an ordering is not decided or the
  * result is two intervals.
  */
+template <typename SP>
 __device__ __forceinline__ bool
-csg_combine(int op, const SpanF &L, const SpanF &R, SpanF &out)
+csg_combine(int op, const SP &L, const SP &R, SP &out)
 {
     out.flags = 0;
     if (!(L.flags & 1)) {
@@ -302,8 +310,8 @@ csg_combine(int op, const SpanF &L, const SpanF &R, SpanF &out)
     } else {
         return false;
     }
-    const SpanF &first = l_enters_first ? L : R, &second = l_enters_first ? R : L;
-    const SpanF &last = l_exits_last ? L : R, &inner = l_exits_last ? R : L;
+    const SP &first = l_enters_first ? L : R, &second = l_enters_first ? R : L;
+    const SP &last = l_exits_last ? L : R, &inner = l_exits_last ? R : L;
     if (op == FRT_CSG_UNION) {
         out.a_lo = first.a_lo;
         out.a_hi = first.a_hi;
@@ -349,21 +357,22 @@ csg_combine(int op, const SpanF &L, const SpanF &R, SpanF &out)
  *   the point is shadowed iff some t > 0 on a casts_shadow surface is < distance.
  * Returns 0 = does not stop (keep walking), 1 = stops, lit, 2 = stops, shadowed, 3 = undecided.
  */
+template <typename T>
 __device__ __forceinline__ int
-judge_span(const SpanF &s, float D_lo, float D_hi)
+judge_span(const SpanT<T> &s, T D_lo, T D_hi)
 {
-    if (s.b_hi <= 0.0f) {
+    if (s.b_hi <= (T)0) {
         return 0;
     }
-    if (!(s.b_lo > 0.0f)) {
+    if (!(s.b_lo > (T)0)) {
         return 3;
     }
     /* per end: 2 = surely a positive casting crossing nearer than the light, 0 = surely not, 1 = cannot tell */
     int ea, eb;
-    if (!(s.flags & 2) || s.a_hi <= 0.0f || s.a_lo >= D_hi) {
+    if (!(s.flags & 2) || s.a_hi <= (T)0 || s.a_lo >= D_hi) {
         ea = 0;
     } else {
-        ea = (s.a_lo > 0.0f && s.a_hi < D_lo) ? 2 : 1;
+        ea = (s.a_lo > (T)0 && s.a_hi < D_lo) ? 2 : 1;
     }
     if (!(s.flags & 4) || s.b_lo >= D_hi) {
         eb = 0;
@@ -611,6 +620,206 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int
         *flops += cost;
     }
     return verdict;
+}
+
+/*
+ * All shadow rays of ONE hit at once.  They share the origin o and aim at points of the light's parallelogram, so in
+ * the parametrisation  o + t (p - o)  (t = 1 is the light; t against 0, t against the light distance and the order of
+ * two crossings are invariant under the per-ray scale |p - o|) every direction component d_k lies in
+ * [min, max] over the four corners.  The slab values of a WORLD-space box are then intervals over the whole family:
+ *   d_k of one sign on every ray:   (b - o_k) / d_k is monotone in d_k, the ends are attained at the interval's ends;
+ *   d_k changes sign (or gets small enough for the reference's "* INFINITY" branch, cube.c:27-33) and the origin is
+ *   strictly inside the slab:       near_k <= max(lo/d+, hi/d-) < 0  and  far_k >= min(hi/d+, lo/d-) > 0;
+ *   otherwise the axis says nothing.
+ * The same walk as trace_shadow_f32 is done ONCE with these intervals; when every comparison on the way separates,
+ * all rays of the hit take the same branches and get the same verdict (csg_combine / judge_span are shared with the
+ * per-ray filter), and none of them has to be traced: on the Cornell frame that is every hit in the umbra of the
+ * window wall, four fifths of the frame.  Anything else -- a sphere, a local frame, an overlap -- leaves the hit to
+ * the per-ray kernels.  Arithmetic is FP64 on the FP64 over-point; the only error of note is the FP32 rounding of the
+ * mirror's box bounds (en), the rest is covered by relative slacks far above FP64 rounding and far below any feature.
+ * Checked like the per-ray filter: FRT_FLAG_VERIFY_F32 traces every ray of a bulk-decided hit in FP64 as well.
+ */
+struct ShaftD {
+    double o[3], dlo[3], dhi[3];
+    int sgn[3]; /* +1 / -1: d_k has that sign on every ray and the reference divides; 0: see above */
+    double en;  /* bound on the error of a slab numerator (b - o_k) */
+};
+
+__device__ __forceinline__ void
+shaft_d_setup(ShaftD &s, const double *corners, const double *over, float bmax, float smin, float ealign)
+{
+    double cmax = 0.0, len2max = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        s.o[k] = over[k];
+        s.dlo[k] = CUDART_INF;
+        s.dhi[k] = -CUDART_INF;
+        cmax = fmax(cmax, fabs(over[k]));
+    }
+    for (int q = 0; q < 4; ++q) {
+        double l2 = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            const double c = __ldg(corners + 3 * q + k), d = c - over[k];
+            cmax = fmax(cmax, fabs(c));
+            s.dlo[k] = fmin(s.dlo[k], d);
+            s.dhi[k] = fmax(s.dhi[k], d);
+            l2 += d * d;
+        }
+        len2max = fmax(len2max, l2);
+    }
+    const double sd = (1e-12 + (double)ealign) * 2.0 * cmax + 1e-300;
+    /* the reference divides by the LOCAL normalised component when it is >= EPSILON: local = scale * world */
+    const double thr = 2.0 * FRT_EPS * sqrt(len2max) / (double)smin;
+    for (int k = 0; k < 3; ++k) {
+        s.dlo[k] -= sd;
+        s.dhi[k] += sd;
+        s.sgn[k] = s.dlo[k] > thr ? 1 : (s.dhi[k] < -thr ? -1 : 0);
+    }
+    s.en = 2.4e-7 * (double)bmax + (1e-12 + (double)ealign) * cmax + 1e-300; /* bounds rounded to FP32: 2^-22 Bmax */
+}
+
+/* quotient range of n in [n_lo, n_hi] over e in [e_lo, e_hi], e_lo > 0 */
+__device__ __forceinline__ void
+shaft_div(double n_lo, double n_hi, double e_lo, double e_hi, double &q_lo, double &q_hi)
+{
+    q_lo = n_lo / (n_lo >= 0.0 ? e_hi : e_lo);
+    q_hi = n_hi / (n_hi >= 0.0 ? e_lo : e_hi);
+}
+
+/* entry / exit of every ray of the shaft through the world box [lo, hi], as intervals */
+__device__ __forceinline__ void
+shaft_box_d(const ShaftD &s, const float4 lo, const float4 hi, double &tn_lo, double &tn_hi, double &tf_lo, double &tf_hi)
+{
+    const float l[3] = { lo.x, lo.y, lo.z }, h[3] = { hi.x, hi.y, hi.z };
+    tn_lo = tn_hi = -CUDART_INF;
+    tf_lo = tf_hi = CUDART_INF;
+    for (int k = 0; k < 3; ++k) {
+        const double nl = (double)l[k] - s.o[k], nh = (double)h[k] - s.o[k];
+        double a_lo = -CUDART_INF, a_hi = CUDART_INF, b_lo = -CUDART_INF, b_hi = CUDART_INF;
+        if (s.sgn[k] > 0) {
+            shaft_div(nl - s.en, nl + s.en, s.dlo[k], s.dhi[k], a_lo, a_hi);
+            shaft_div(nh - s.en, nh + s.en, s.dlo[k], s.dhi[k], b_lo, b_hi);
+        } else if (s.sgn[k] < 0) { /* near = hi / d = (-hi) / (-d) */
+            shaft_div(-nh - s.en, -nh + s.en, -s.dhi[k], -s.dlo[k], a_lo, a_hi);
+            shaft_div(-nl - s.en, -nl + s.en, -s.dhi[k], -s.dlo[k], b_lo, b_hi);
+        } else if (nl + s.en < 0.0 && nh - s.en > 0.0) {
+            const double dp = fmax(s.dhi[k], 1e-300), dn = fmin(s.dlo[k], -1e-300);
+            a_hi = fmax((nl + s.en) / dp, (nh - s.en) / dn);
+            b_lo = fmin((nh - s.en) / dp, (nl + s.en) / dn);
+        }
+        tn_lo = fmax(tn_lo, a_lo);
+        tn_hi = fmax(tn_hi, a_hi);
+        tf_lo = fmin(tf_lo, b_lo);
+        tf_hi = fmin(tf_hi, b_hi);
+    }
+    /* the reference evaluates the same quotients in the leaf's frame: FP64 rounding of either side */
+    tn_lo -= 1e-12 * fabs(tn_lo);
+    tn_hi += 1e-12 * fabs(tn_hi);
+    tf_lo -= 1e-12 * fabs(tf_lo);
+    tf_hi += 1e-12 * fabs(tf_hi);
+}
+
+/* a WORLD cube leaf over the shaft; false = undecided */
+__device__ __forceinline__ bool
+shaft_leaf_span(const ShaftD &sh, const float4 q0, const float4 lo, const float4 hi, SpanD &s)
+{
+    const int flags = __float_as_int(q0.x);
+    s.flags = 0;
+    s.a_lo = s.a_hi = s.b_lo = s.b_hi = 0.0;
+    if ((flags & FRT_FN_TYPE_MASK) != FRT_CUBE || !(flags & FRT_FN_FAST) || !(flags & FRT_FN_WORLD) || __float_as_int(q0.z) != 0) {
+        return false;
+    }
+    shaft_box_d(sh, lo, hi, s.a_lo, s.a_hi, s.b_lo, s.b_hi);
+    if (s.a_lo > s.b_hi) {
+        return true; /* missed by every ray */
+    }
+    if (!(s.a_hi < s.b_lo)) {
+        return false;
+    }
+    s.flags = 1 | ((flags & FRT_FN_CASTS) ? 6 : 0);
+    return true;
+}
+
+/* FRT_SH_LIT / FRT_SH_SHADOWED: the verdict of every shadow ray of the hit; FRT_SH_UNDECIDED: trace them one by one.
+ * Trees of more than 32 nodes are not tried (`relevant` covers nodes 0..31). */
+__device__ __forceinline__ int
+trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const ShaftD &sh)
+{
+    const float4 *fnodes = SF.fnodes;
+    int i = root;
+    const int end = __float_as_int(__ldg(fnodes + 3 * i).y);
+    const double D_lo = 1.0 - 1e-9, D_hi = 1.0 + 1e-9;
+    while (i < end) {
+        const float4 q0 = __ldg(fnodes + 3 * i);
+        const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
+        if (!((relevant >> i) & 1u)) {
+            i = skip;
+            continue;
+        }
+        const float4 lo = __ldg(fnodes + 3 * i + 1), hi = __ldg(fnodes + 3 * i + 2);
+        const int type = flags & FRT_FN_TYPE_MASK;
+        SpanD s;
+        if (type >= FRT_CSG) {
+            if (!(flags & FRT_FN_NOCULL) && (flags & FRT_FN_WORLD) && __float_as_int(q0.z) == 0) {
+                double tn_lo, tn_hi, tf_lo, tf_hi;
+                shaft_box_d(sh, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                if (tn_lo > tf_hi || tf_hi < 0.0) {
+                    i = skip;
+                    continue;
+                }
+            }
+            if (type == FRT_GROUP) {
+                i = i + 1;
+                continue;
+            }
+            if (!(flags & FRT_FN_FAST)) {
+                return FRT_SH_UNDECIDED;
+            }
+            int pc = __float_as_int(lo.w);
+            const int pc1 = pc + __float_as_int(hi.w);
+            s.flags = 0;
+            s.a_lo = s.a_hi = s.b_lo = s.b_hi = 0.0;
+            for (bool first = true; pc < pc1; first = false) {
+                const int code = __ldg(SF.csg_prog + pc);
+                SpanD t;
+                t.flags = 0;
+                t.a_lo = t.a_hi = t.b_lo = t.b_hi = 0.0;
+                /* an operand outside the shaft has no crossing at t > 0: for the crossings at t > 0 it is absent */
+                if (((relevant >> code) & 1u) &&
+                    !shaft_leaf_span(sh, __ldg(fnodes + 3 * code), __ldg(fnodes + 3 * code + 1), __ldg(fnodes + 3 * code + 2), t)) {
+                    return FRT_SH_UNDECIDED;
+                }
+                if (first) {
+                    s = t;
+                    pc += 1;
+                } else {
+                    const int op = -__ldg(SF.csg_prog + pc + 1) - 1;
+                    SpanD r;
+                    r.a_lo = r.a_hi = r.b_lo = r.b_hi = 0.0;
+                    if (!csg_combine(op, s, t, r)) {
+                        return FRT_SH_UNDECIDED;
+                    }
+                    s = r;
+                    pc += 2;
+                }
+            }
+            i = skip;
+        } else {
+            if (!shaft_leaf_span(sh, q0, lo, hi, s)) {
+                return FRT_SH_UNDECIDED;
+            }
+            i = i + 1;
+        }
+        if (s.flags) {
+            const int v = judge_span(s, D_lo, D_hi);
+            if (v == 3) {
+                return FRT_SH_UNDECIDED;
+            }
+            if (v != 0) {
+                return v == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
+            }
+        }
+    }
+    return FRT_SH_LIT;
 }
 
 /*

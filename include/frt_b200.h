@@ -201,6 +201,7 @@ enum frt_render_flags {
     FRT_FLAG_VERIFY_F32 = 16,/* trace every shadow ray the FP32 filter decides in FP64 as well and count disagreements
                                 in frt_stats.shadow_mismatch (must be 0); the frame itself uses the FP64 answers */
     FRT_FLAG_NO_SHAFT = 32,  /* switch the per-hit shaft culling of the shadow filter off (A/B measurements, tests) */
+    FRT_FLAG_NO_BULK = 64,   /* switch the per-hit decision of all shadow rays at once (k_shadow_bulk) off */
     FRT_FLAG_F64_SHADING = 4 /* evaluate the lighting sums (lighting_microfacet, renderer.c:894-979) in FP64 like the
                                 reference instead of FP32; geometric decisions are FP64 either way */
 };
@@ -231,7 +232,8 @@ typedef struct frt_stats {
                                 with the cost table of BASELINE.md section 4 (ray transform 33, bbox slab 16, sphere 28, ...) */
     uint64_t shadow_deferred;/* shadow rays the FP32 filter pass left undecided and the FP64 pass re-traced */
     uint64_t shadow_mismatch;/* FRT_FLAG_VERIFY_F32: FP32-decided rays whose FP64 answer differs */
-    uint64_t shadow_reasons[10]; /* FRT_FLAG_COUNT_RAYS: deferred rays by reason: 1 CSG depth, 2 group inside a CSG operand,
+    uint64_t shadow_reasons[10]; /* [0]: shadow rays decided per hit, all at once, by the shaft-interval pass (never traced).
+                                FRT_FLAG_COUNT_RAYS: deferred rays by reason: 1 CSG depth, 2 group inside a CSG operand,
                                 3 primitive type without a fast form, 4 plane inside a CSG, 5 leaf hit/miss not separable,
                                 6 leaf verdict, 7 two spans in one operand, 8 CSG ordering / two-span result, 9 CSG verdict */
     int32_t rows_rendered;

@@ -130,6 +130,24 @@ def test_fp64_shadow_and_shading_flags_give_the_same_frame(frt, name):
     assert np.allclose(a, b, rtol=0, atol=1e-12)  # pixel sums are FP64 atomics: order may differ in the last bit
 
 
+def test_per_hit_shadow_decision_matches_the_per_ray_kernels(frt):
+    """k_shadow_bulk decides all shadow rays of a hit at once where the shaft's intervals separate (the umbra of the
+    Cornell window wall).  It must fire on that scene, and the frame must be the one the per-ray kernels produce."""
+    from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_F64_SHADING, FRT_FLAG_NO_BULK, FRT_FLAG_VERIFY_F32
+
+    desc = frt.SceneDesc.load(GOLDEN / "cornell_exact_200.frt")
+    with frt.Scene(desc) as sc:
+        a, sa = sc.render(flags=FRT_FLAG_F64_SHADING | FRT_FLAG_COUNT_RAYS)
+        b, sb = sc.render(flags=FRT_FLAG_F64_SHADING | FRT_FLAG_COUNT_RAYS | FRT_FLAG_NO_BULK)
+        _, sv = sc.render(flags=FRT_FLAG_VERIFY_F32 | FRT_FLAG_COUNT_RAYS)
+    bulk = sa.extra["shadow_reasons"][0]
+    assert bulk > 0.3 * sa.rays_shadow, (bulk, sa.rays_shadow)
+    assert sb.extra["shadow_reasons"][0] == 0
+    assert sa.rays_shadow == sb.rays_shadow  # bulk-decided rays still count as shadow rays of the frame
+    assert sv.shadow_mismatch == 0 and sv.extra["shadow_reasons"][0] == bulk
+    assert np.allclose(a, b, rtol=0, atol=1e-12)
+
+
 def test_six_dragons_through_the_divided_group_tree(frt):
     """BASELINE.json configs[2], bounding_boxes.yml: 6 x dragon.obj (141 K triangles in ~31 K divided groups), glass
     boxes that do not cast shadows, cylinders, 4 point lights.  The 52 MB scene blob is not a git fixture: it is dumped
