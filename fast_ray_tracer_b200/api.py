@@ -128,7 +128,7 @@ EXPORTS = [
     "frt_abi_version", "frt_abi_sizeof", "frt_last_error", "frt_device_count", "frt_canvas_device_ptr", "frt_scene_create", "frt_scene_destroy",
     "frt_render", "frt_canvas_download", "frt_owned_rows", "frt_photons_emit", "frt_photons_count",
     "frt_photons_export", "frt_photons_import", "frt_photons_finish", "frt_measure_fma_peak",
-    "frt_scene_save", "frt_scene_load", "frt_scene_desc_free", "frt_trim",
+    "frt_scene_save", "frt_scene_load", "frt_scene_desc_free", "frt_trim", "frt_host_register", "frt_host_unregister",
 ]
 
 
@@ -152,6 +152,8 @@ def load_library():
     lib.frt_scene_destroy.restype = None
     lib.frt_trim.argtypes = [C.c_int]
     lib.frt_trim.restype = None
+    lib.frt_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.frt_host_unregister.argtypes = [C.c_void_p]
     lib.frt_render.argtypes = [C.c_void_p, C.POINTER(frt_render_cfg), C.c_void_p, C.POINTER(frt_stats)]
     lib.frt_canvas_download.argtypes = [C.c_void_p, C.c_void_p]
     lib.frt_canvas_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -251,6 +253,23 @@ class SceneDesc:
         self.c.n_pixel_samples = 0
         self.c.pixel_samples = C.POINTER(C.c_double)()
 
+    def pin(self):
+        """Page-lock the light sample-set cache (the only large host buffer of a scene) so that every Scene built from
+        this description uploads it at PCIe speed (frt_host_register).  Undone by unpin() / when the object dies."""
+        d = self.c
+        if getattr(self, "_pinned", None) or d.n_light_points <= 0:
+            return self
+        addr = C.cast(d.light_points, C.c_void_p).value
+        _check(load_library().frt_host_register(addr, d.n_light_points * 24), "frt_host_register")
+        self._pinned = addr
+        return self
+
+    def unpin(self):
+        addr = getattr(self, "_pinned", None)
+        if addr:
+            self._pinned = None
+            _check(load_library().frt_host_unregister(addr), "frt_host_unregister")
+
     def owned_rows(self, rank: int, world: int, rows_per_block: int = 4) -> np.ndarray:
         cfg = frt_render_cfg(rank=rank, world=world, rows_per_block=rows_per_block)
         n = load_library().frt_owned_rows(self._ptr, C.byref(cfg), None, 0)
@@ -259,6 +278,10 @@ class SceneDesc:
         return np.frombuffer(rows, dtype=np.int32, count=n).copy()
 
     def __del__(self):
+        try:
+            self.unpin()
+        except Exception:
+            pass
         if getattr(self, "_owned", False) and self._ptr:
             try:
                 load_library().frt_scene_desc_free(self._ptr)

@@ -1204,6 +1204,7 @@ struct frt_scene {
     DCamera C{};
     frt_config cfg{};
     std::vector<void *> allocs;
+    std::vector<size_t> alloc_bytes; /* parallel to allocs */
     std::vector<int> light_gw, light_ns;
     double *canvas = nullptr;     /* hsize*vsize*4 doubles */
     double *samples = nullptr;
@@ -1307,15 +1308,100 @@ scene_give(frt_scene *sc, FrameSet &f)
     sc->capacity = 0;
 }
 
+/*
+ * The large scene buffers (the 157 MB light-sample cache of the shipped Cornell scene, its FP32 copy, the canvas) are
+ * kept by size when a scene is destroyed, up to FRT_BLOCK_CACHE_MAX per device, and handed to the next scene that asks
+ * for the same size: a host loop that builds a scene per frame then makes no cudaMalloc / cudaFree driver call per
+ * frame at all (each is a device-wide synchronisation point and takes the driver lock).  frt_trim() frees them.
+ */
+#define FRT_BLOCK_CACHE_MIN ((size_t)1 << 20)
+#define FRT_BLOCK_CACHE_MAX ((size_t)2 << 30)
+struct BlockCache {
+    std::multimap<size_t, void *> blocks;
+    size_t bytes = 0;
+};
+static std::map<int, BlockCache> g_blocks; /* under g_park_mu */
+
+static cudaError_t
+scene_alloc(frt_scene *sc, void **p, size_t bytes)
+{
+    bytes = std::max<size_t>(bytes, 1);
+    *p = nullptr;
+    if (bytes >= FRT_BLOCK_CACHE_MIN) {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        BlockCache &c = g_blocks[sc->device];
+        auto it = c.blocks.find(bytes);
+        if (it != c.blocks.end()) {
+            *p = it->second;
+            c.bytes -= bytes;
+            c.blocks.erase(it);
+        }
+    }
+    if (*p == nullptr) {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) {
+            return e;
+        }
+    }
+    sc->allocs.push_back(*p);
+    sc->alloc_bytes.push_back(bytes);
+    return cudaSuccess;
+}
+
+static void
+scene_release_allocs(frt_scene *sc)
+{
+    std::lock_guard<std::mutex> lk(g_park_mu);
+    BlockCache &c = g_blocks[sc->device];
+    for (size_t i = 0; i < sc->allocs.size(); ++i) {
+        const size_t bytes = i < sc->alloc_bytes.size() ? sc->alloc_bytes[i] : 0;
+        if (bytes >= FRT_BLOCK_CACHE_MIN && c.bytes + bytes <= FRT_BLOCK_CACHE_MAX) {
+            c.blocks.emplace(bytes, sc->allocs[i]);
+            c.bytes += bytes;
+        } else {
+            cudaFree(sc->allocs[i]);
+        }
+    }
+    sc->allocs.clear();
+    sc->alloc_bytes.clear();
+}
+
+extern "C" int
+frt_host_register(void *ptr, size_t bytes)
+{
+    if (ptr == nullptr || bytes == 0) {
+        return frt_set_error(FRT_ERR_ARG, "frt_host_register: empty buffer");
+    }
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return FRT_OK;
+}
+
+extern "C" int
+frt_host_unregister(void *ptr)
+{
+    if (ptr == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_host_unregister: null pointer");
+    }
+    CK(cudaHostUnregister(ptr));
+    return FRT_OK;
+}
+
 extern "C" void
 frt_trim(int device)
 {
     std::lock_guard<std::mutex> lk(g_park_mu);
+    cudaSetDevice(device);
     auto it = g_parked.find(device);
     if (it != g_parked.end()) {
-        cudaSetDevice(device);
         frameset_free(it->second);
         g_parked.erase(it);
+    }
+    auto bt = g_blocks.find(device);
+    if (bt != g_blocks.end()) {
+        for (auto &b : bt->second.blocks) {
+            cudaFree(b.second);
+        }
+        g_blocks.erase(bt);
     }
 }
 
@@ -1325,8 +1411,7 @@ upload(frt_scene *sc, const T *src, size_t count, const T **dst)
 {
     T *d = nullptr;
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    CK(cudaMalloc(&d, bytes));
-    sc->allocs.push_back(d);
+    CK(scene_alloc(sc, (void **)&d, bytes));
     if (count) {
         CK(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
     } else {
@@ -1427,9 +1512,7 @@ frt_scene_destroy(frt_scene *sc)
     }
     cudaSetDevice(sc->device);
     pm_free(sc);
-    for (void *p : sc->allocs) {
-        cudaFree(p);
-    }
+    scene_release_allocs(sc);
     if (sc->capacity > 0 && !sc->frame_allocs.empty()) {
         std::lock_guard<std::mutex> lk(g_park_mu);
         FrameSet &slot = g_parked[sc->device];
@@ -1786,8 +1869,7 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     /* FP32 copy of the light sample points, converted on the device */
     const size_t np = (size_t)3 * d->n_light_points;
     float *fp = nullptr;
-    CK(cudaMalloc(&fp, std::max<size_t>(np, 1) * sizeof(float)));
-    sc->allocs.push_back(fp);
+    CK(scene_alloc(sc, (void **)&fp, std::max<size_t>(np, 1) * sizeof(float)));
     if (np) {
         k_to_float<<<148 * 8, 256>>>(sc->S.lpoints, fp, np);
         CK(cudaGetLastError());
@@ -1895,11 +1977,10 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
 
     size_t cbytes = (size_t)c.hsize * c.vsize * 4 * sizeof(double);
     void *cv = nullptr;
-    if (cudaMalloc(&cv, cbytes) != cudaSuccess) {
+    if (scene_alloc(sc, &cv, cbytes) != cudaSuccess) {
         frt_scene_destroy(sc);
         return frt_set_error(FRT_ERR_CUDA, "cudaMalloc of the canvas failed");
     }
-    sc->allocs.push_back(cv);
     sc->canvas = (double *)cv;
     if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) {
         frt_scene_destroy(sc);
@@ -2103,8 +2184,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             std::vector<double> table;
             cmj_table_no_jitter(cfg->usteps, cfg->vsteps, table);
             double *dtab = nullptr;
-            CK(cudaMalloc(&dtab, table.size() * sizeof(double)));
-            sc->allocs.push_back(dtab);
+            CK(scene_alloc(sc, (void **)&dtab, table.size() * sizeof(double)));
             CK(cudaMemcpy(dtab, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
             sc->samples = dtab;
             sc->samples_u = cfg->usteps;

@@ -259,9 +259,14 @@ int frt_abi_sizeof(const char *struct_name);
 /* Upload a flattened scene (host pointers in desc are read during the call only). */
 int frt_scene_create(const frt_scene_desc *desc, int device, frt_scene **out);
 void frt_scene_destroy(frt_scene *scene);
-/* frt_scene_destroy parks the scene-independent frame buffers (ray queues) for the next scene on the same device;
- * frt_trim frees them. */
+/* frt_scene_destroy parks the scene-independent frame buffers (ray queues) and the large scene buffers (by size) for
+ * the next scene on the same device; frt_trim frees them. */
 void frt_trim(int device);
+/* Page-lock / release a caller-owned host buffer a scene description points at (typically light_points, the 157 MB
+ * sample-set cache the reference builds in light.c:100-191): frt_scene_create then uploads it at PCIe speed.  Worth
+ * it for a host loop that creates a scene per frame; a one-shot program need not call it. */
+int frt_host_register(void *ptr, size_t bytes);
+int frt_host_unregister(void *ptr);
 
 /*
  * Replaces render_multi()/render() (renderer.c:243/:283).  canvas_rgba has the layout of Canvas.arr
