@@ -21,6 +21,7 @@ FRT_FLAG_F64_SHADOW = 8
 FRT_FLAG_VERIFY_F32 = 16
 FRT_FLAG_NO_SHAFT = 32
 FRT_FLAG_NO_BULK = 64
+FRT_FLAG_NO_SPLIT = 128
 
 
 class FrtError(RuntimeError):

@@ -604,8 +604,7 @@ struct LightTmp { /* per shaded hit, per light launch (32 bytes); the first 16 b
     unsigned int relevant; /* shaft culling: bit i = node i may be crossed at t > 0 by a shadow ray of this hit */
     int set_b;             /* sample set of the lighting pass */
     int unshadowed;        /* shadow rays that reached the light */
-    int contributes;       /* bit 0: the light is not wholly behind the surface: the lighting sums can be non-zero;
-                              bit 1: every shadow ray of the hit was decided at once by k_shadow_bulk, bit 2: ... as lit */
+    int contributes;       /* the light is not wholly behind the surface: the lighting sums can be non-zero */
 };
 
 /*
@@ -698,42 +697,73 @@ k_light_pre(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
 }
 
 /*
- * Per hit, after k_light_pre: try to decide ALL shadow rays of the hit at once (trace_shadow_bulk, frt_shadow_f32.cuh)
- * and compact the hits that still need their rays traced into `pending`.  MODE as in k_shadow_f32: in counting (1) and
- * verifying (2) frames the bulk-decided hits stay in the list so that k_shadow_f32 can count / re-trace their rays; a
- * verifying frame takes its visibility counts from those FP64 re-traces, like it does for the per-ray filter.
+ * Sample index of item k of quadrant q of the light's sample grid (the cache stores sample (u, v) at v * usteps + u,
+ * light.c:172-186): quadrant q covers u in [(q & 1) hu, ...+hu), v in [(q >> 1) hv, ...+hv).  hu == 0: no split.
+ */
+__device__ __forceinline__ int
+quadrant_sample(int4 lq, int q, int k)
+{
+    if (lq.y == 0) {
+        return k;
+    }
+    const int lv = k / lq.y, lu = k - lv * lq.y;
+    return ((q >> 1) * lq.z + lv) * lq.w + (q & 1) * lq.y + lu;
+}
+
+/* pending entry: hit in bits 0..27, quadrant in bits 28..29, bit 30 = decided by k_shadow_bulk, bit 31 = ... as lit */
+#define FRT_PEND_HIT_MASK 0x0fffffffu
+#define FRT_PEND_BULK 0x40000000u
+#define FRT_PEND_LIT 0x80000000u
+
+/*
+ * Per hit, after k_light_pre: try to decide ALL shadow rays of the hit at once (trace_shadow_bulk, frt_shadow_f32.cuh);
+ * when the whole light is undecided (a penumbra hit) and the light's sample grid splits into quadrants, try each
+ * quadrant of samples on its own -- an occluder's edge seldom crosses all four.  What is left is compacted into
+ * `pending`, one entry per (hit, quadrant) whose rays the per-ray kernels must trace.  MODE as in k_shadow_f32: in
+ * counting (1) and verifying (2) frames the decided entries stay in the list, flagged, so that k_shadow_f32 can count /
+ * re-trace their rays; a verifying frame takes its visibility counts from those FP64 re-traces, like it does for the
+ * per-ray filter.
  */
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
-              int light_idx, unsigned int *__restrict__ pending, int bulk_on)
+              int light_idx, unsigned int *__restrict__ pending, unsigned int *__restrict__ retry, int bulk_on, int split_on)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
-    const int NS = S.lights[light_idx].num_samples;
+    const int4 lq = split_on ? __ldg(SF.lquad + light_idx) : make_int4(S.lights[light_idx].num_samples, 0, 0, 0);
+    const int nq = lq.y ? 4 : 1;
     const int root = __ldg(S.roots);
     unsigned long long n_bulk = 0;
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
         const unsigned int h = base + (threadIdx.x & 31);
-        bool want = false;
+        /* 0 = nothing to do, 1 = undecided, 2 / 3 = decided shadowed / lit */
+        int state = 0;
         if (h < n && tmp[h].set_a >= 0) {
-            want = true;
+            state = 1;
             if (bulk_on) {
                 ShaftD sh;
-                shaft_d_setup(sh, SF.shaft64 + 12 * light_idx, recs[h].over, SF.bmax, SF.smin, SF.ealign);
+                shaft_d_setup(sh, SF.lbox + 30 * light_idx, recs[h].over, SF.bmax, SF.smin, SF.ealign);
                 const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh);
                 if (res != FRT_SH_UNDECIDED) {
-                    tmp[h].contributes |= 2 | (res == FRT_SH_LIT ? 4 : 0);
-                    if (MODE != 2) {
-                        tmp[h].unshadowed = res == FRT_SH_LIT ? NS : 0;
+                    state = res == FRT_SH_LIT ? 3 : 2;
+                    n_bulk += (unsigned int)(nq * lq.x);
+                    if (MODE != 2 && res == FRT_SH_LIT) {
+                        tmp[h].unshadowed = nq * lq.x; /* k_light_pre left 0 */
                     }
-                    n_bulk += (unsigned int)NS;
-                    want = MODE != 0;
                 }
             }
         }
-        const unsigned int slot = warp_append(&cnt->n_pending, want);
-        if (want) {
-            pending[slot] = h;
+        /* undecided and the light's sample grid splits: k_shadow_quad tries the quadrants one by one */
+        const unsigned int r = warp_append(&cnt->n_deferred, state == 1 && nq > 1);
+        if (state == 1 && nq > 1) {
+            retry[r] = h;
+        }
+        const bool keep = (state == 1 && nq == 1) || (MODE != 0 && state >= 2);
+        for (int q = 0; q < nq; ++q) {
+            const unsigned int slot = warp_append(&cnt->n_pending, keep);
+            if (keep) {
+                pending[slot] = h | ((unsigned int)q << 28) | (state >= 2 ? FRT_PEND_BULK : 0u) | (state == 3 ? FRT_PEND_LIT : 0u);
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -741,6 +771,88 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
     }
     if ((threadIdx.x & 31) == 0 && n_bulk) {
         atomicAdd(&cnt->rays_bulk, n_bulk);
+    }
+}
+
+/* one thread per (undecided hit, quadrant of the light's sample grid): the same walk against the quadrant's bounds */
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int light_idx,
+              unsigned int *__restrict__ pending, const unsigned int *__restrict__ retry)
+{
+    const unsigned int n = min(cnt->n_deferred, F.capacity);
+    const int4 lq = __ldg(SF.lquad + light_idx);
+    const int root = __ldg(S.roots);
+    unsigned long long n_bulk = 0;
+    const unsigned int total = 4u * n; /* n <= 2^28 */
+    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += gridDim.x * blockDim.x) {
+        const unsigned int item = base + (threadIdx.x & 31);
+        int state = 0;
+        unsigned int h = 0;
+        const int q = (int)(item & 3u);
+        if (item < total) {
+            h = __ldg(retry + (item >> 2));
+            ShaftD sh;
+            shaft_d_setup(sh, SF.lbox + 30 * light_idx + 6 * (q + 1), recs[h].over, SF.bmax, SF.smin, SF.ealign);
+            const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh);
+            state = res == FRT_SH_UNDECIDED ? 1 : (res == FRT_SH_LIT ? 3 : 2);
+            if (state >= 2) {
+                n_bulk += (unsigned int)lq.x;
+                if (MODE != 2 && state == 3) {
+                    atomicAdd(&tmp[h].unshadowed, lq.x);
+                }
+            }
+        }
+        const bool keep = state == 1 || (MODE != 0 && state >= 2);
+        const unsigned int slot = warp_append(&cnt->n_pending, keep);
+        if (keep) {
+            pending[slot] = h | ((unsigned int)q << 28) | (state >= 2 ? FRT_PEND_BULK : 0u) | (state == 3 ? FRT_PEND_LIT : 0u);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_bulk += __shfl_down_sync(0xffffffffu, n_bulk, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n_bulk) {
+        atomicAdd(&cnt->rays_bulk, n_bulk);
+    }
+}
+
+/* axis-aligned bounds of the light points of quadrant blockIdx.y over the sample sets blockIdx.x, +gridDim.x, ... */
+__global__ void __launch_bounds__(256)
+k_light_boxes(const double *__restrict__ pts, int cache_len, int NS, int4 lq, double *__restrict__ partial)
+{
+    const int q = blockIdx.y;
+    double lo[3] = { CUDART_INF, CUDART_INF, CUDART_INF }, hi[3] = { -CUDART_INF, -CUDART_INF, -CUDART_INF };
+    for (int set = blockIdx.x; set < cache_len; set += gridDim.x) {
+        for (int k = threadIdx.x; k < lq.x; k += blockDim.x) {
+            const double *p = pts + 3 * ((size_t)set * NS + quadrant_sample(lq, q, k));
+            for (int c = 0; c < 3; ++c) {
+                const double v = __ldg(p + c);
+                lo[c] = fmin(lo[c], v);
+                hi[c] = fmax(hi[c], v);
+            }
+        }
+    }
+    __shared__ double sm[8][6];
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_down_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_down_sync(0xffffffffu, hi[c], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int c = 0; c < 3; ++c) {
+            sm[threadIdx.x >> 5][c] = lo[c];
+            sm[threadIdx.x >> 5][3 + c] = hi[c];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = sm[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) {
+            v = threadIdx.x < 3 ? fmin(v, sm[w][threadIdx.x]) : fmax(v, sm[w][threadIdx.x]);
+        }
+        partial[((size_t)q * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = v;
     }
 }
 
@@ -792,8 +904,8 @@ normalise_shadow_ray(Ray &sr, double dist2)
 template <int MODE>
 __global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
 k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
-             const unsigned int *__restrict__ pending, int light_idx, unsigned long long *__restrict__ queue, unsigned int qcap,
-             int nodes_in_smem)
+             const unsigned int *__restrict__ pending, unsigned int pend_cap, int split_on, int light_idx,
+             unsigned long long *__restrict__ queue, unsigned int qcap, int nodes_in_smem)
 {
     constexpr bool COUNT = MODE != 0;
     extern __shared__ float4 s_nodes[];
@@ -805,13 +917,15 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
         __syncthreads();
         fnodes = s_nodes;
     }
-    const unsigned int n = min(cnt->n_pending, F.capacity); /* hits k_shadow_bulk left to be traced ray by ray */
+    const unsigned int n = min(cnt->n_pending, pend_cap); /* (hit, quadrant) entries k_shadow_bulk left to be traced ray by ray */
     const int NS = S.lights[light_idx].num_samples;
+    const int4 lq = split_on ? __ldg(SF.lquad + light_idx) : make_int4(NS, 0, 0, 0);
+    const int NSQ = lq.x; /* samples per entry */
     const float *fpts = SF.lpoints + 3 * S.lights[light_idx].point_offset;
     const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
-    const unsigned long long total = (unsigned long long)n * (unsigned int)NS;
+    const unsigned long long total = (unsigned long long)n * (unsigned int)NSQ;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long ns_magic = NS > 1 ? ~0ull / (unsigned int)NS + 1ull : 0ull; /* ceil(2^64 / NS) */
+    const unsigned long long ns_magic = NSQ > 1 ? ~0ull / (unsigned int)NSQ + 1ull : 0ull; /* ceil(2^64 / NSQ) */
     const int root = __ldg(S.roots);
     int overflow = 0;
     unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0, n_mismatch = 0;
@@ -821,15 +935,17 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
         unsigned int h = 0;
         int s = 0;
         float4 head = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        unsigned int entry = 0;
         if (item < total) {
-            const unsigned int idx = NS > 1 ? (unsigned int)__umul64hi(item, ns_magic) : (unsigned int)item; /* item / NS, exact while item * NS < 2^64 */
-            s = (int)(item - (unsigned long long)idx * (unsigned int)NS);
-            h = __ldg(pending + idx);
+            const unsigned int idx = NSQ > 1 ? (unsigned int)__umul64hi(item, ns_magic) : (unsigned int)item; /* item / NSQ, exact while item * NSQ < 2^64 */
+            entry = __ldg(pending + idx);
+            s = quadrant_sample(lq, (entry >> 28) & 3, (int)(item - (unsigned long long)idx * (unsigned int)NSQ));
+            h = entry & FRT_PEND_HIT_MASK;
             head = *reinterpret_cast<const float4 *>(tmp + h);
         }
         const int set_a = __float_as_int(head.w);
         const unsigned int relevant = set_a >= 0 ? tmp[h].relevant : 0u;
-        const int bulk = (MODE != 0 && set_a >= 0) ? (tmp[h].contributes >> 1) & 3 : 0; /* bit 0: decided per hit, bit 1: as lit */
+        const int bulk = (MODE != 0 && set_a >= 0) ? (int)(entry >> 30) : 0; /* bit 0: decided by k_shadow_bulk, bit 1: as lit */
         int res = FRT_SH_SHADOWED;
         if (set_a >= 0) {
             if (bulk) {
@@ -1033,7 +1149,7 @@ k_light_final(DScene S, FrameParams F, const LightRec *__restrict__ recs, const 
         const LightRec *R = recs + (live ? hbase : 0);
         const LightTmp t = tmp[live ? hbase : 0];
         const double intensity = (double)t.unshadowed / (double)NS;
-        const bool lit = live && (t.contributes & 1) && !(fabs(intensity) < FRT_EPS); /* equal(shade_intensity, 0.0), renderer.c:904 */
+        const bool lit = live && t.contributes && !(fabs(intensity) < FRT_EPS); /* equal(shade_intensity, 0.0), renderer.c:904 */
 
         T sum_ndl = 0, sum_b = 0, sum_fb = 0;
         if (lit) {
@@ -1553,7 +1669,6 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
 {
     std::vector<float4> fx((size_t)4 * d->n_xforms), fn((size_t)3 * d->n_nodes), wb((size_t)2 * d->n_nodes);
     std::vector<float4> shaft((size_t)4 * std::max(d->n_lights, 1));
-    std::vector<double> shaft64((size_t)12 * std::max(d->n_lights, 1), 0.0);
     double smin = 1.0, tilt = 0.0;
     std::vector<int> aligned(d->n_xforms, 0), perm((size_t)3 * d->n_xforms, 0);
     for (int i = 0; i < d->n_xforms; ++i) {
@@ -1845,9 +1960,6 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
         }
         for (int q = 0; q < 4; ++q) {
             shaft[4 * li + q] = make_float4((float)c[q][0], (float)c[q][1], (float)c[q][2], 0.f);
-            for (int k = 0; k < 3; ++k) {
-                shaft64[12 * li + 3 * q + k] = c[q][k];
-            }
         }
     }
     int rc = upload(sc, fx.data(), fx.size(), &sc->SF.fx);
@@ -1857,8 +1969,6 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     rc = upload(sc, shaft.data(), shaft.size(), &sc->SF.shaft);
     if (rc != FRT_OK) return rc;
     rc = upload(sc, prog.data(), prog.size(), &sc->SF.csg_prog);
-    if (rc != FRT_OK) return rc;
-    rc = upload(sc, shaft64.data(), shaft64.size(), &sc->SF.shaft64);
     if (rc != FRT_OK) return rc;
     sc->SF.smin = (float)(smin * (1.0 - 1e-6));
     sc->SF.ealign = (float)(2.0 * tilt * (1.0 + 1e-6));
@@ -1876,6 +1986,65 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
         CK(cudaDeviceSynchronize());
     }
     sc->SF.lpoints = fp;
+
+    /* per light: bounds of its sample points (all of them, and per quadrant of the sample grid) over every cached set,
+     * reduced on the device from the points as uploaded -- no assumption about where the sampler puts sample (u, v) */
+    std::vector<double> lbox((size_t)30 * std::max(d->n_lights, 1), 0.0);
+    std::vector<int4> lquad(std::max(d->n_lights, 1), make_int4(1, 0, 0, 0));
+    const int chunks = 64;
+    double *partial = nullptr;
+    CK(cudaMalloc(&partial, sizeof(double) * 6 * 4 * chunks));
+    std::vector<double> hp((size_t)6 * 4 * chunks);
+    for (int li = 0; li < d->n_lights; ++li) {
+        const frt_light &L = d->lights[li];
+        const int NS = L.num_samples;
+        int4 lq = make_int4(NS, 0, 0, 0);
+        if (NS >= 16 && L.usteps > 0 && L.vsteps > 0 && L.usteps % 2 == 0 && L.vsteps % 2 == 0 && L.usteps * L.vsteps == NS) {
+            lq = make_int4(NS / 4, L.usteps / 2, L.vsteps / 2, L.usteps);
+        }
+        lquad[li] = lq;
+        const int nq = lq.y ? 4 : 1;
+        const int nb = std::max(1, std::min(chunks, L.cache_len));
+        k_light_boxes<<<dim3(nb, nq), 256>>>(sc->S.lpoints + 3 * L.point_offset, L.cache_len, NS, lq, partial);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(hp.data(), partial, sizeof(double) * 6 * nq * nb, cudaMemcpyDeviceToHost));
+        double *all = &lbox[(size_t)30 * li];
+        for (int k = 0; k < 3; ++k) {
+            all[k] = INFINITY;
+            all[3 + k] = -INFINITY;
+        }
+        for (int q = 0; q < nq; ++q) {
+            double *b = &lbox[(size_t)30 * li + 6 * (q + 1)];
+            for (int k = 0; k < 3; ++k) {
+                b[k] = INFINITY;
+                b[3 + k] = -INFINITY;
+            }
+            for (int c = 0; c < nb; ++c) {
+                const double *pp = &hp[((size_t)q * nb + c) * 6];
+                for (int k = 0; k < 3; ++k) {
+                    b[k] = std::min(b[k], pp[k]);
+                    b[3 + k] = std::max(b[3 + k], pp[3 + k]);
+                }
+            }
+            for (int k = 0; k < 3; ++k) { /* inflate: the points are exact, the slack covers nothing but habit */
+                const double m = 1e-12 * (std::max(fabs(b[k]), fabs(b[3 + k])) + 1.0);
+                b[k] -= m;
+                b[3 + k] += m;
+                all[k] = std::min(all[k], b[k]);
+                all[3 + k] = std::max(all[3 + k], b[3 + k]);
+            }
+        }
+        if (nq == 1) {
+            for (int q = 1; q < 4; ++q) {
+                std::copy(all, all + 6, &lbox[(size_t)30 * li + 6 * (q + 1)]);
+            }
+        }
+    }
+    cudaFree(partial);
+    rc = upload(sc, lbox.data(), lbox.size(), &sc->SF.lbox);
+    if (rc != FRT_OK) return rc;
+    rc = upload(sc, lquad.data(), lquad.size(), &sc->SF.lquad);
+    if (rc != FRT_OK) return rc;
     return FRT_OK;
 }
 
@@ -2075,8 +2244,13 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     FA(sc->hq.t); FA(sc->hq.u); FA(sc->hq.v); FA(sc->hq.leaf);
     FA(sc->recs);
     FA(sc->ltmp);
-    FA(sc->pending);
 #undef FA
+    {
+        int rc_ = frame_alloc(sc, &sc->pending, (size_t)capacity * 4); /* one entry per (hit, quadrant of the light's sample grid) */
+        if (rc_ != FRT_OK) {
+            return rc_;
+        }
+    }
     {
         unsigned long long want_q = std::min<unsigned long long>((unsigned long long)capacity * 4ull, 0x7fffffffull);
         int rc_ = frame_alloc(sc, &sc->dq, (size_t)want_q);
@@ -2253,7 +2427,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     }
     unsigned int chunk = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(total, 1), chunk_samples);
     unsigned long long want = (unsigned long long)chunk * cap_factor;
-    unsigned int capacity = (unsigned int)std::min<unsigned long long>(want, 0x7fffffffULL);
+    unsigned int capacity = (unsigned int)std::min<unsigned long long>(want, (unsigned long long)FRT_PEND_HIT_MASK + 1ull); /* hit ids share a word with flags */
     int rc = ensure_frame_buffers(sc, capacity);
     if (rc != FRT_OK) {
         return rc;
@@ -2326,16 +2500,28 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         /* per hit: every shadow ray at once where the shaft's intervals separate (small trees, area lights) */
                         const int bulk_on = sc->S.n_roots == 1 && sc->S.n_nodes <= 32 && sc->light_ns[li] >= 4 &&
                                             !(F.flags & (FRT_FLAG_NO_SHAFT | FRT_FLAG_NO_BULK));
+                        const int split_on = bulk_on && !(F.flags & FRT_FLAG_NO_SPLIT);
+                        const unsigned int pend_cap = sc->capacity * 4u;
+                        unsigned int *retry = reinterpret_cast<unsigned int *>(sc->dq); /* free until k_shadow_f32 defers rays */
+#define FRT_SHADOW_STAGE(M)                                                                                                                       \
+    do {                                                                                                                                          \
+        k_shadow_bulk<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, retry, bulk_on, split_on);  \
+        if (split_on) {                                                                                                                           \
+            k_shadow_quad<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, retry);                        \
+            CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));                                                                \
+            launches += 1;                                                                                                                        \
+        }                                                                                                                                         \
+        k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pend_cap, split_on, li, sc->dq, \
+                                                       sc->dq_cap, f32_smem != 0);                                                                \
+    } while (0)
                         if (F.flags & FRT_FLAG_VERIFY_F32) {
-                            k_shadow_bulk<2><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, bulk_on);
-                            k_shadow_f32<2><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            FRT_SHADOW_STAGE(2);
                         } else if (count) {
-                            k_shadow_bulk<1><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, bulk_on);
-                            k_shadow_f32<1><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            FRT_SHADOW_STAGE(1);
                         } else {
-                            k_shadow_bulk<0><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, bulk_on);
-                            k_shadow_f32<0><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, li, sc->dq, sc->dq_cap, f32_smem != 0);
+                            FRT_SHADOW_STAGE(0);
                         }
+#undef FRT_SHADOW_STAGE
                         CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         if (count) {
                             k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);

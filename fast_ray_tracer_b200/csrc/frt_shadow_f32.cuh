@@ -66,7 +66,9 @@ struct DSceneF {
     const float4 *wbox;   /* per node: WORLD-space bounding box {min.xyz, 0} {max.xyz, 0}, rounded outward (shaft culling) */
     const float4 *shaft;  /* per light: 4 corners of a parallelogram that contains every surface sample of the light */
     const int *csg_prog;  /* postfix programs of the outermost CSG nodes: node index of a leaf, or -(op + 1) */
-    const double *shaft64;/* per light: the same 4 corners in FP64, 12 doubles (trace_shadow_bulk) */
+    const double *lbox;   /* per light: 5 axis-aligned boxes {min xyz, max xyz} of its sample points over every cached set,
+                             box 0 = all samples, boxes 1..4 = the quadrants of the sample grid (trace_shadow_bulk) */
+    const int4 *lquad;    /* per light: {samples per pending entry, half usteps (0: the grid is not split), half vsteps, usteps} */
     float bmax;           /* largest finite |bound| of a WORLD node */
     float smin;           /* smallest |axis scale| of an axis-aligned world->local transform (<= 1) */
     float ealign;         /* 2 x the largest off-axis / on-axis ratio of a transform treated as axis-aligned (<= 2e-9):
@@ -640,49 +642,55 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int
  * Checked like the per-ray filter: FRT_FLAG_VERIFY_F32 traces every ray of a bulk-decided hit in FP64 as well.
  */
 struct ShaftD {
-    double o[3], dlo[3], dhi[3];
+    double o[3];
+    double ia[3], ib[3]; /* sgn != 0: 1 / min |d_k|, 1 / max |d_k|;  sgn == 0: 1 / max(d_k, tiny), 1 / min(d_k, -tiny) */
     int sgn[3]; /* +1 / -1: d_k has that sign on every ray and the reference divides; 0: see above */
     double en;  /* bound on the error of a slab numerator (b - o_k) */
 };
 
 __device__ __forceinline__ void
-shaft_d_setup(ShaftD &s, const double *corners, const double *over, float bmax, float smin, float ealign)
+shaft_d_setup(ShaftD &s, const double *box, const double *over, float bmax, float smin, float ealign)
 {
-    double cmax = 0.0, len2max = 0.0;
+    /* box: axis-aligned bounds {min xyz, max xyz} of the light points the rays aim at (the whole light, or one quadrant
+     * of its sample grid), measured over every cached sample set at upload and inflated there */
+    double cmax = 0.0, len2max = 0.0, dlo[3], dhi[3];
     for (int k = 0; k < 3; ++k) {
+        const double lo = __ldg(box + k), hi = __ldg(box + 3 + k);
         s.o[k] = over[k];
-        s.dlo[k] = CUDART_INF;
-        s.dhi[k] = -CUDART_INF;
-        cmax = fmax(cmax, fabs(over[k]));
-    }
-    for (int q = 0; q < 4; ++q) {
-        double l2 = 0.0;
-        for (int k = 0; k < 3; ++k) {
-            const double c = __ldg(corners + 3 * q + k), d = c - over[k];
-            cmax = fmax(cmax, fabs(c));
-            s.dlo[k] = fmin(s.dlo[k], d);
-            s.dhi[k] = fmax(s.dhi[k], d);
-            l2 += d * d;
-        }
-        len2max = fmax(len2max, l2);
+        dlo[k] = lo - over[k];
+        dhi[k] = hi - over[k];
+        cmax = fmax(cmax, fmax(fabs(over[k]), fmax(fabs(lo), fabs(hi))));
+        const double m = fmax(fabs(dlo[k]), fabs(dhi[k]));
+        len2max += m * m;
     }
     const double sd = (1e-12 + (double)ealign) * 2.0 * cmax + 1e-300;
     /* the reference divides by the LOCAL normalised component when it is >= EPSILON: local = scale * world */
     const double thr = 2.0 * FRT_EPS * sqrt(len2max) / (double)smin;
     for (int k = 0; k < 3; ++k) {
-        s.dlo[k] -= sd;
-        s.dhi[k] += sd;
-        s.sgn[k] = s.dlo[k] > thr ? 1 : (s.dhi[k] < -thr ? -1 : 0);
+        dlo[k] -= sd;
+        dhi[k] += sd;
+        s.sgn[k] = dlo[k] > thr ? 1 : (dhi[k] < -thr ? -1 : 0);
+        /* the slab quotients become products with these reciprocals (their rounding, 2^-52, sits in shaft_box_d's 1e-12) */
+        if (s.sgn[k] > 0) {
+            s.ia[k] = 1.0 / dlo[k];
+            s.ib[k] = 1.0 / dhi[k];
+        } else if (s.sgn[k] < 0) {
+            s.ia[k] = -1.0 / dhi[k];
+            s.ib[k] = -1.0 / dlo[k];
+        } else {
+            s.ia[k] = 1.0 / fmax(dhi[k], 1e-300);
+            s.ib[k] = 1.0 / fmin(dlo[k], -1e-300);
+        }
     }
     s.en = 2.4e-7 * (double)bmax + (1e-12 + (double)ealign) * cmax + 1e-300; /* bounds rounded to FP32: 2^-22 Bmax */
 }
 
-/* quotient range of n in [n_lo, n_hi] over e in [e_lo, e_hi], e_lo > 0 */
+/* quotient range of n in [n_lo, n_hi] over e in [e_lo, e_hi], e_lo > 0, given ia = 1 / e_lo and ib = 1 / e_hi */
 __device__ __forceinline__ void
-shaft_div(double n_lo, double n_hi, double e_lo, double e_hi, double &q_lo, double &q_hi)
+shaft_div(double n_lo, double n_hi, double ia, double ib, double &q_lo, double &q_hi)
 {
-    q_lo = n_lo / (n_lo >= 0.0 ? e_hi : e_lo);
-    q_hi = n_hi / (n_hi >= 0.0 ? e_lo : e_hi);
+    q_lo = n_lo * (n_lo >= 0.0 ? ib : ia);
+    q_hi = n_hi * (n_hi >= 0.0 ? ia : ib);
 }
 
 /* entry / exit of every ray of the shaft through the world box [lo, hi], as intervals */
@@ -696,15 +704,14 @@ shaft_box_d(const ShaftD &s, const float4 lo, const float4 hi, double &tn_lo, do
         const double nl = (double)l[k] - s.o[k], nh = (double)h[k] - s.o[k];
         double a_lo = -CUDART_INF, a_hi = CUDART_INF, b_lo = -CUDART_INF, b_hi = CUDART_INF;
         if (s.sgn[k] > 0) {
-            shaft_div(nl - s.en, nl + s.en, s.dlo[k], s.dhi[k], a_lo, a_hi);
-            shaft_div(nh - s.en, nh + s.en, s.dlo[k], s.dhi[k], b_lo, b_hi);
+            shaft_div(nl - s.en, nl + s.en, s.ia[k], s.ib[k], a_lo, a_hi);
+            shaft_div(nh - s.en, nh + s.en, s.ia[k], s.ib[k], b_lo, b_hi);
         } else if (s.sgn[k] < 0) { /* near = hi / d = (-hi) / (-d) */
-            shaft_div(-nh - s.en, -nh + s.en, -s.dhi[k], -s.dlo[k], a_lo, a_hi);
-            shaft_div(-nl - s.en, -nl + s.en, -s.dhi[k], -s.dlo[k], b_lo, b_hi);
-        } else if (nl + s.en < 0.0 && nh - s.en > 0.0) {
-            const double dp = fmax(s.dhi[k], 1e-300), dn = fmin(s.dlo[k], -1e-300);
-            a_hi = fmax((nl + s.en) / dp, (nh - s.en) / dn);
-            b_lo = fmin((nh - s.en) / dp, (nl + s.en) / dn);
+            shaft_div(-nh - s.en, -nh + s.en, s.ia[k], s.ib[k], a_lo, a_hi);
+            shaft_div(-nl - s.en, -nl + s.en, s.ia[k], s.ib[k], b_lo, b_hi);
+        } else if (nl + s.en < 0.0 && nh - s.en > 0.0) { /* ia = 1 / (largest positive d), ib = 1 / (most negative d) */
+            a_hi = fmax((nl + s.en) * s.ia[k], (nh - s.en) * s.ib[k]);
+            b_lo = fmin((nh - s.en) * s.ia[k], (nl + s.en) * s.ib[k]);
         }
         tn_lo = fmax(tn_lo, a_lo);
         tn_hi = fmax(tn_hi, a_hi);

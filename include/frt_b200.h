@@ -202,6 +202,7 @@ enum frt_render_flags {
                                 in frt_stats.shadow_mismatch (must be 0); the frame itself uses the FP64 answers */
     FRT_FLAG_NO_SHAFT = 32,  /* switch the per-hit shaft culling of the shadow filter off (A/B measurements, tests) */
     FRT_FLAG_NO_BULK = 64,   /* switch the per-hit decision of all shadow rays at once (k_shadow_bulk) off */
+    FRT_FLAG_NO_SPLIT = 128, /* ... keep it, but do not retry undecided hits per quadrant of the light's sample grid */
     FRT_FLAG_F64_SHADING = 4 /* evaluate the lighting sums (lighting_microfacet, renderer.c:894-979) in FP64 like the
                                 reference instead of FP32; geometric decisions are FP64 either way */
 };

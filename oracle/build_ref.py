@@ -119,6 +119,15 @@ def edit_none(tree):
     return tree
 
 
+def edit_sibenik_surrogate(tree):
+    """C4 stand-in: write the synthetic textured OBJ mesh + MTL + texture copies into oracle/_ref/assets/ first."""
+    sys.path.insert(0, str(REPO / "oracle" / "scenes"))
+    import make_sibenik_surrogate
+
+    make_sibenik_surrogate.main(int(os.environ.get("FRT_SIBENIK_DETAIL", "3")))
+    return tree
+
+
 def edit_cornell_exact(tree):
     return _cache_size(_direct_only(tree), 1)
 
@@ -156,6 +165,8 @@ SCENES = {
     # image textures (Ka / Kd / bump maps through planar and spherical uv maps)
     "bump_map_test": ("scenes/bump_map_test/bump_map_test.yml", edit_images),
     "texture_map_test": ("scenes/texture_map_test/texture_map_test.yml", edit_images),
+    # C4 stand-in (sibenik.obj is not in the reference tree): textured + bump-mapped OBJ triangles under an area light
+    "sibenik_surrogate": (str(REPO / "oracle" / "scenes" / "sibenik_surrogate.yml"), edit_sibenik_surrogate),
     # C3
     "teapot": ("scenes/teapot/teapot.yml", edit_none),
     "bounding_boxes": ("scenes/bounding_boxes/bounding_boxes.yml", edit_none),

@@ -48,6 +48,8 @@ GOLDEN = {
     "dof_blur_240": ("dof_blur", 240, 120, 0, 0),
     "bounding_boxes_600": ("bounding_boxes", 600, 240, 0, 0),  # C3b: 6 x dragon.obj (141 K triangles, ~31 K groups)
     "texture_map_test": ("texture_map_test", 200, 200, 0, 0),
+    # C4 stand-in: 86 K textured / bump-mapped OBJ triangles (smooth columns, glass windows), 10x10 area light, 2x2 CMJ
+    "sibenik_surrogate_160": ("sibenik_surrogate", 160, 200, 2, 2),
     # photon-mapped: stochastic in the reference too, so two reference renders (seeds 1 and 2) are stored; their RMSE is
     # the noise floor the CUDA render is held against
     "cornell_gi_64": ("cornell_gi", 64, 64, 2, 2),
@@ -56,7 +58,7 @@ GOLDEN = {
 STOCHASTIC = {"cornell_gi_64", "cornell_gi_caustics_48", "dof_blur_240"}
 # fixtures whose scene blob is too large to commit (6 dragons = 52 MB): only the reference canvas is stored; the GPU test
 # renders oracle/_ref/blobs/<scene>.frt, which travels to the GPU box with the snapshot
-BLOB_STAYS_IN_REF = {"bounding_boxes_600"}
+BLOB_STAYS_IN_REF = {"bounding_boxes_600", "sibenik_surrogate_160"}
 
 
 def make(name: str):
