@@ -119,6 +119,7 @@ struct Counters {
     unsigned long long rays_secondary, rays_shadow, hits_shaded, shadow_nodes, light_flops;
     unsigned long long deferred_total, f32_mismatch, rays_gather;
     unsigned long long rays_bulk; /* shadow rays decided per hit by k_shadow_bulk */
+    unsigned long long mesh_next; /* k_shadow_mesh: next (hit, sample) item to hand out */
     unsigned long long undecided_node[32]; /* debug: node at which a leaf verdict was undecided */
     unsigned long long undecided_reason[10]; /* counting build: why the FP32 filter deferred a ray (codes in frt_shadow_f32.cuh) */
 };
@@ -1116,6 +1117,287 @@ k_shadow_exact(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
 }
 
 /*
+ * Shadow rays of MESH scenes (most leaves are triangles, which the FP32 filter has no fast form for, so every ray
+ * would be deferred): all rays go straight to the mixed walk of trace_shadow_mixed -- FP32 conservative culls out of
+ * the 48-byte node mirror, FP64 leaves and verdicts, the reference's order (H1) -- but run by PERSISTENT warps whose
+ * lanes are REFILLED: the reference's divided tree makes ray lengths wildly uneven (100 to 10 000s of nodes), and
+ * ncu on the queue version showed 14 of 32 lanes active and 30 % issue utilisation, the kernel's duration being the
+ * latency of its longest rays.  Here a lane that finishes its ray takes the next (hit, sample) item from a global
+ * counter as soon as FRT_MESH_REFILL lanes of its warp are idle; items are handed out in order, so the rays a warp
+ * picks up together still share an origin.  The walk is "while-while": each lane first walks inner nodes (culls)
+ * until it stands on a leaf, then the warp intersects its leaves together, and a leaf's mirror record carries the
+ * parameter offset, transform and casts-shadow bit, so a leaf costs one dependent load (its FP64 vertices), not three.
+ * C4 stand-in 800x1000, 61 M rays: 163 ms (deferred queue + one ray per thread) -> 100 ms.
+ */
+#define FRT_MESH_REFILL 24 /* idle lanes of a warp before it takes new items (measured: 4 -> 140 ms, 24 -> 104 ms, 32 = never -> 110 ms on the C4 stand-in) */
+#define FRT_MESH_INNER 32 /* inner nodes a lane may walk before the warp looks at its leaves */
+#ifndef FRT_MESH_MINB
+#define FRT_MESH_MINB 6
+#endif
+template <bool COUNT>
+__global__ void __launch_bounds__(128, FRT_MESH_MINB)
+k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
+              int light_idx, int inner_budget, int refill_min)
+{
+    struct Frame {
+        int right, skip, start, mid, op;
+    };
+    const unsigned int nh = min(cnt->n_hits[level], F.capacity);
+    const int NS = S.lights[light_idx].num_samples;
+    const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
+    const unsigned long long total = (unsigned long long)nh * (unsigned int)NS;
+    const bool small = total <= 0xffffffffull;
+    const float4 *fnodes = SF.fnodes;
+    const int root = __ldg(S.roots);
+    const int end = __float_as_int(__ldg(fnodes + 3 * root).y);
+    const unsigned int lane = threadIdx.x & 31;
+    const bool verify = (F.flags & FRT_FLAG_VERIFY_F32) != 0;
+
+    bool active = false, exhausted = false;
+    unsigned int h = 0;
+    Ray wr{}, lr{};
+    InvDir inv{};
+    FrameF w{}, lf{};
+    double dist = 0.0;
+    float omax = 0.f, eo_o = 0.f, ed_w = 0.f;
+    int cur_xf_f = 0, cur_xf_d = 0, i = 0, sp = 0, n = 0;
+    CsgHit buf[FRT_CSG_CAP];
+    Frame st[FRT_CSG_DEPTH];
+    int overflow = 0;
+    unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0, n_mismatch = 0;
+
+    for (;;) {
+        const unsigned int idle = __ballot_sync(0xffffffffu, !active);
+        if (idle == 0xffffffffu && exhausted) {
+            break;
+        }
+        if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= refill_min)) {
+            const int want = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) {
+                base = atomicAdd(&cnt->mesh_next, (unsigned long long)want);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + (unsigned long long)want >= total;
+            const unsigned long long item = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
+            if (!active && item < total) {
+                int set_a;
+                double dist2;
+                shadow_item(S, recs, tmp, pts, NS, item, small, h, set_a, wr, dist2);
+                if (set_a >= 0) {
+                    dist = normalise_shadow_ray(wr, dist2);
+                    w.ox = (float)wr.ox;
+                    w.oy = (float)wr.oy;
+                    w.oz = (float)wr.oz;
+                    w.dx = (float)wr.dx;
+                    w.dy = (float)wr.dy;
+                    w.dz = (float)wr.dz;
+                    omax = fmaxf(fmaxf(fabsf(w.ox), fabsf(w.oy)), fabsf(w.oz));
+                    eo_o = 2.0f * FRT_F32_U * omax;
+                    const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, fmaf(SF.ealign, omax, eo_o));
+                    ed_w = FRT_F32_G + SF.ealign; /* the FP64 unit direction rounded to FP32 */
+                    frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
+                    lf = w;
+                    lr = wr;
+                    inv = inv_dir(wr);
+                    cur_xf_f = cur_xf_d = 0;
+                    i = root;
+                    sp = 0;
+                    n = 0;
+                    active = true;
+                    if (COUNT) ++n_shadow;
+                }
+            }
+        }
+        if (!active) {
+            continue;
+        }
+        bool done = false, result = false;
+        /* close every CSG whose left / right operand just ended (csg.c:104-118, :43-71) */
+        auto close_frames = [&]() {
+            while (sp > 0 && !done) {
+                Frame &f = st[sp - 1];
+                if (f.mid < 0 && i >= f.right) {
+                    f.mid = n;
+                }
+                if (i < f.skip) {
+                    break;
+                }
+                if (f.mid - f.start > 0 && n - f.mid > 0) {
+                    for (int x = f.start + 1; x < n; ++x) {
+                        CsgHit hh = buf[x];
+                        int y = x - 1;
+                        while (y >= f.start && buf[y].t > hh.t) {
+                            buf[y + 1] = buf[y];
+                            --y;
+                        }
+                        buf[y + 1] = hh;
+                    }
+                }
+                bool inl = false, inr = false;
+                int out = f.start;
+                for (int x = f.start; x < n; ++x) {
+                    const bool lhit = buf[x].leaf < f.right;
+                    if (csg_allowed(f.op, lhit, inl, inr)) {
+                        buf[out++] = buf[x];
+                    }
+                    if (lhit) {
+                        inl = !inl;
+                    } else {
+                        inr = !inr;
+                    }
+                }
+                n = out;
+                --sp;
+                if (sp == 0) {
+                    bool stop = false;
+                    double tmin = CUDART_INF;
+                    for (int x = 0; x < n; ++x) {
+                        stop = stop || !(buf[x].t <= 0);
+                        if (buf[x].t > 0 && buf[x].t < tmin && S.mats[load_node_a(S, buf[x].leaf).material].casts_shadow) {
+                            tmin = buf[x].t;
+                        }
+                    }
+                    n = 0;
+                    if (stop) {
+                        result = tmin < dist;
+                        done = true;
+                    }
+                }
+            }
+        };
+        /* while-while: every lane first walks inner nodes (culls) until it stands on a leaf, then the lanes that do
+         * intersect their leaves together -- the two code paths are not interleaved lane by lane */
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), lo = q0, hi = q0;
+        bool at_leaf = false;
+        for (int budget = inner_budget; budget > 0 && !done; --budget) {
+            if (i >= end) {
+                done = true;
+                break;
+            }
+            q0 = __ldg(fnodes + 3 * i);
+            lo = __ldg(fnodes + 3 * i + 1);
+            const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
+            const int type = flags & FRT_FN_TYPE_MASK;
+            if (type < FRT_CSG) {
+                at_leaf = true;
+                break;
+            }
+            hi = __ldg(fnodes + 3 * i + 2);
+            if (COUNT) {
+                ++n_nodes;
+                n_flops += FRT_COST_BBOX;
+            }
+            bool miss = false;
+            if (!(flags & FRT_FN_NOCULL)) {
+                const int xf = __float_as_int(q0.z);
+                float tn_lo, tn_hi, tf_lo, tf_hi;
+                if (xf == 0) {
+                    box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                } else {
+                    if (xf != cur_xf_f) {
+                        cur_xf_f = xf;
+                        frame_local(lf, SF, xf, w, omax, eo_o, ed_w);
+                    }
+                    box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                }
+                miss = tn_lo > tf_hi || (sp == 0 && tf_hi < 0.0f);
+            }
+            if (miss) {
+                i = skip;
+            } else {
+                if (type == FRT_CSG) {
+                    if (sp == FRT_CSG_DEPTH) {
+                        overflow = 1;
+                        done = true;
+                    } else {
+                        st[sp++] = Frame{ __float_as_int(q0.w), skip, n, -1, (flags >> FRT_FN_OP_SHIFT) & 3 };
+                    }
+                }
+                i = i + 1;
+            }
+            if (sp > 0) {
+                close_frames();
+            }
+        }
+        if (at_leaf && !done) {
+            /* leaves carry what the walk needs in their mirror record: {flags (type, casts), skip, -, param} {-, -, -, xform} */
+            const int flags = __float_as_int(q0.x);
+            const int type = flags & FRT_FN_TYPE_MASK, param = __float_as_int(q0.w), xform = __float_as_int(lo.w);
+            if (COUNT) {
+                ++n_nodes;
+                n_flops += prim_cost(type);
+            }
+            if (xform != cur_xf_d) {
+                cur_xf_d = xform;
+                if (cur_xf_d == 0) {
+                    lr = wr;
+                } else {
+                    lr = ray_to_local(S, cur_xf_d, wr);
+                    if (COUNT) n_flops += FRT_COST_XFORM;
+                }
+                inv = inv_dir(lr);
+            }
+            double t[4], uv[2];
+            const int k = prim_intersect_inv(type, S.params + (param < 0 ? 0 : param), lr, inv, t, uv);
+            if (sp == 0) {
+                bool stop = false;
+                double tmin = CUDART_INF;
+                for (int j = 0; j < k; ++j) {
+                    stop = stop || !(t[j] <= 0);
+                    if (t[j] > 0 && t[j] < tmin) {
+                        tmin = t[j];
+                    }
+                }
+                if (stop) {
+                    result = (flags & FRT_FN_CASTS) && tmin < dist;
+                    done = true;
+                }
+            } else {
+                for (int j = 0; j < k; ++j) {
+                    if (n == FRT_CSG_CAP) {
+                        overflow = 1;
+                        done = true;
+                        break;
+                    }
+                    buf[n].t = t[j];
+                    buf[n].leaf = i;
+                    ++n;
+                }
+            }
+            i = i + 1;
+            if (sp > 0) {
+                close_frames();
+            }
+        }
+        if (done) {
+            if (verify) { /* the mixed walk is checked against the pure FP64 walk ray by ray */
+                unsigned long long dn = 0, df = 0;
+                const bool ref = trace_shadow<false>(S, wr, dist, &overflow, &dn, &df);
+                if (ref != result) {
+                    ++n_mismatch;
+                    result = ref;
+                }
+            }
+            if (!result) {
+                atomicAdd(&tmp[h].unshadowed, 1);
+            }
+            active = false;
+        }
+    }
+    if (overflow) {
+        atomicOr(&cnt->overflow_csg, 1u);
+    }
+    if (COUNT) {
+        if (n_shadow) atomicAdd(&cnt->rays_shadow, n_shadow);
+        if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
+        if (n_flops) atomicAdd(&cnt->light_flops, n_flops);
+        if (n_shadow) atomicAdd(&cnt->deferred_total, n_shadow); /* every ray of a mesh scene takes the FP64-leaf walk */
+    }
+    if (n_mismatch) atomicAdd(&cnt->f32_mismatch, n_mismatch);
+}
+
+/*
  * lighting_microfacet (renderer.c:894-979) for the hits that received light, and the weighting into the pixel.
  * G lanes (a power of two <= 32) share a hit and stride over the sample set; partial sums are combined with a
  * fixed-order butterfly, so the result does not depend on scheduling.  Hits whose shadow rays were all blocked
@@ -1322,6 +1604,7 @@ struct frt_scene {
     std::vector<void *> allocs;
     std::vector<size_t> alloc_bytes; /* parallel to allocs */
     std::vector<int> light_gw, light_ns;
+    bool mesh_mode = false; /* most leaves have no FP32 fast form (OBJ meshes): shadow rays go straight to k_shadow_mesh */
     double *canvas = nullptr;     /* hsize*vsize*4 doubles */
     double *samples = nullptr;
     int samples_u = 0, samples_v = 0;
@@ -1845,14 +2128,14 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
         q0.x = __int_as_float_host(flags);
         q0.y = __int_as_float_host(n.skip);
         q0.z = __int_as_float_host(world ? 0 : n.xform);
-        q0.w = __int_as_float_host(n.right);
+        q0.w = __int_as_float_host(inner ? n.right : n.param); /* leaves: what the FP64 leaf test needs, without a second record */
         fn[3 * i] = q0;
         if (inner) {
             fn[3 * i + 1] = make_float4(down(lo[0]), down(lo[1]), down(lo[2]), 0.f);
             fn[3 * i + 2] = make_float4(up(hi[0]), up(hi[1]), up(hi[2]), 0.f);
         } else {
-            fn[3 * i + 1] = make_float4((float)lo[0], (float)lo[1], (float)lo[2], 0.f);
-            fn[3 * i + 2] = make_float4((float)hi[0], (float)hi[1], (float)hi[2], 0.f);
+            fn[3 * i + 1] = make_float4((float)lo[0], (float)lo[1], (float)lo[2], __int_as_float_host(n.xform));
+            fn[3 * i + 2] = make_float4((float)hi[0], (float)hi[1], (float)hi[2], __int_as_float_host(n.material));
         }
     }
     /* postfix programs of the outermost CSG nodes (frt_shadow_f32.cuh): operands first, then the operator */
@@ -2138,6 +2421,21 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
     C.samples = dtab;
 
     sc->cfg = d->config;
+    {
+        long leaves = 0, slow = 0;
+        for (int i = 0; i < d->n_nodes; ++i) {
+            const int t = d->nodes[i].type;
+            if (t < FRT_CSG) {
+                ++leaves;
+                slow += !(t == FRT_CUBE || t == FRT_SPHERE || t == FRT_PLANE);
+            }
+        }
+        sc->mesh_mode = slow * 2 > leaves && d->n_nodes > 64;
+        const char *env = getenv("FRT_MESH_MODE");
+        if (env != nullptr && *env) {
+            sc->mesh_mode = atoi(env) != 0;
+        }
+    }
     sc->light_gw.resize(d->n_lights);
     for (int i = 0; i < d->n_lights; ++i) {
         sc->light_gw[i] = pick_group_width(d->lights[i].num_samples);
@@ -2489,6 +2787,18 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                             k_shadow_exact<true, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         } else {
                             k_shadow_exact<false, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                        }
+                        CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
+                        launches += 1;
+                    } else if (sc->mesh_mode && sc->S.n_roots == 1) {
+                        CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
+                        const int mblocks = getenv("FRT_MESH_BLOCKS") ? atoi(getenv("FRT_MESH_BLOCKS")) : sm_blocks * 8;
+                        const int m_inner = getenv("FRT_MESH_INNER_STEPS") ? atoi(getenv("FRT_MESH_INNER_STEPS")) : FRT_MESH_INNER;
+                        const int m_refill = getenv("FRT_MESH_REFILL_MIN") ? atoi(getenv("FRT_MESH_REFILL_MIN")) : FRT_MESH_REFILL;
+                        if (count) {
+                            k_shadow_mesh<true><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, m_inner, m_refill);
+                        } else {
+                            k_shadow_mesh<false><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, m_inner, m_refill);
                         }
                         CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         launches += 1;
