@@ -335,13 +335,13 @@ k_raygen(DCamera C, FrameParams F, RayQ q, Counters *cnt, unsigned int first_sam
 /* ------------------------------------------------------------------------------------------------ extend */
 
 __global__ void __launch_bounds__(256)
-k_extend(DScene S, RayQ q, HitQ h, Counters *cnt, int level, unsigned int capacity)
+k_extend(DScene S, DSceneF SF, RayQ q, HitQ h, Counters *cnt, int level, unsigned int capacity)
 {
     const unsigned int n = min(cnt->n_rays[level], capacity); /* an overflowed level is clamped; the frame is re-run */
     int overflow = 0;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Ray r{ q.ox[i], q.oy[i], q.oz[i], q.dx[i], q.dy[i], q.dz[i] };
-        Hit best = trace_closest(S, r, &overflow);
+        Hit best = trace_closest_mixed<false>(S, SF, r, &overflow);
         h.t[i] = best.t;
         h.u[i] = best.u;
         h.v[i] = best.v;
@@ -2762,7 +2762,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             /* level 0 has n rays; deeper levels read their count on the device: size the grid for the worst case
              * the level can hold, but never more than a few waves */
             int ex_blocks = sm_blocks * 8;
-            k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, qi, sc->hq, sc->cnt, level, F.capacity);
+            k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, sc->SF, qi, sc->hq, sc->cnt, level, F.capacity);
             k_shade<<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
             launches += 2;
             if (F.use_gi) {
@@ -2867,7 +2867,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         ++launches;
                     }
                     if (G.use_final_gather) {
-                        k_fg_trace<<<sm_blocks * 16, 128, 0, s>>>(sc->S, F, G, sc->recs, first, nb, sc->gq, sc->gq_n, sc->gq_cap, sc->cnt, level);
+                        k_fg_trace<<<sm_blocks * 16, 128, 0, s>>>(sc->S, sc->SF, F, G, sc->recs, first, nb, sc->gq, sc->gq_n, sc->gq_cap, sc->cnt, level);
                         ++launches;
                     }
                     k_knn<<<sm_blocks * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, sc->gq, sc->gq_n, sc->gq_cap,
@@ -3185,7 +3185,7 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
                 P.count = n;
                 P.seed = mix64(cfg->seed ^ 0x70686f746f6e73ull);
                 const int blocks = (int)std::min<unsigned long long>((n + 127) / 128, 148ull * 16);
-                k_photon_trace<<<blocks, 128, 0, sc->stream>>>(sc->S, P, m.ra, m.rb, sc->pm_stored + map, m.cap, sc->cnt);
+                k_photon_trace<<<blocks, 128, 0, sc->stream>>>(sc->S, sc->SF, P, m.ra, m.rb, sc->pm_stored + map, m.cap, sc->cnt);
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(&stored, sc->pm_stored + map, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->stream));
                 CK(cudaStreamSynchronize(sc->stream));

@@ -1019,19 +1019,26 @@ trace_containers(const DScene &S, const Ray &wr, int hit_leaf, double &n1, doubl
         int end = load_node_a(S, i).skip;
         int cur_xf = 0;
         Ray lr = wr;
+        InvDir inv = inv_dir(wr);
         while (i < end) {
             NodeA a = load_node_a(S, i);
             if (a.xform != cur_xf) {
                 cur_xf = a.xform;
                 lr = ray_to_local(S, cur_xf, wr);
-            }
-            if (a.type == FRT_GROUP) {
-                i = bbox_hit(S, i, lr) ? i + 1 : a.skip;
-                continue;
+                inv = inv_dir(lr);
             }
             int n = 0;
-            if (a.type == FRT_CSG) {
-                if (bbox_hit(S, i, lr)) {
+            if (a.type >= FRT_CSG) {
+                /* only crossings at t <= 0 count (see above): a box the ray enters at t > 0 holds none of them.  A primary
+                 * ray has the whole scene in front of it, so this walk ends at the first level of groups. */
+                double tmin, tmax;
+                bbox_range_inv(S, i, lr, inv, tmin, tmax);
+                const bool miss = !(tmin <= tmax) || tmin > 0.0;
+                if (a.type == FRT_GROUP) {
+                    i = miss ? a.skip : i + 1;
+                    continue;
+                }
+                if (!miss) {
                     n = csg_eval(S, i, wr, buf, overflow);
                 }
                 i = a.skip;

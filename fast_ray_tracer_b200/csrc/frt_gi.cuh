@@ -210,7 +210,7 @@ pack_photon_dir(const double d[3])
 }
 
 __global__ void __launch_bounds__(128)
-k_photon_trace(DScene S, PhotonParams P, float4 *__restrict__ pa, float4 *__restrict__ pb, unsigned int *stored, unsigned int cap,
+k_photon_trace(DScene S, DSceneF SF, PhotonParams P, float4 *__restrict__ pa, float4 *__restrict__ pb, unsigned int *stored, unsigned int cap,
                Counters *cnt)
 {
     const frt_light L = S.lights[P.light];
@@ -256,7 +256,7 @@ k_photon_trace(DScene S, PhotonParams P, float4 *__restrict__ pa, float4 *__rest
 
         /* ---- power_at / photon_hit, photon_tracer.c:114-201, as a loop */
         for (int remaining = P.path_length; remaining > 0; --remaining) {
-            const Hit h = trace_closest_t<true>(S, r, &overflow); /* hit(xs, true) */
+            const Hit h = trace_closest_mixed<true>(S, SF, r, &overflow); /* hit(xs, true) */
             if (h.leaf < 0) {
                 break;
             }
@@ -472,7 +472,7 @@ k_pm_scatter(PMView M, const float4 *__restrict__ a, const float4 *__restrict__ 
  * :626-645, lighting_gi :862-892, the "scale by theta" of :672).
  */
 __global__ void __launch_bounds__(128)
-k_fg_trace(DScene S, FrameParams F, GIParams G, const LightRec *__restrict__ recs, unsigned int first_hit, unsigned int n_hits_batch,
+k_fg_trace(DScene S, DSceneF SF, FrameParams F, GIParams G, const LightRec *__restrict__ recs, unsigned int first_hit, unsigned int n_hits_batch,
            GQuery *__restrict__ queries, unsigned int *n_queries, unsigned int qcap, Counters *cnt, int level)
 {
     const unsigned int cells = (unsigned int)(G.usteps * G.vsteps);
@@ -501,7 +501,7 @@ k_fg_trace(DScene S, FrameParams F, GIParams G, const LightRec *__restrict__ rec
                 double d[3];
                 cosine_hemisphere(n, r1, r2, d);
                 const Ray r{ R->over[0], R->over[1], R->over[2], d[0], d[1], d[2] };
-                const Hit hit = trace_closest(S, r, &overflow);
+                const Hit hit = trace_closest_mixed<false>(S, SF, r, &overflow);
                 ++n_rays;
                 if (hit.leaf >= 0) {
                     /* color_at_gi tests the diffuse colour at the hit point itself (:331-337) ... */

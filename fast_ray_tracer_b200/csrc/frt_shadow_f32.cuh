@@ -998,3 +998,107 @@ trace_shadow_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, double dis
     }
     return result;
 }
+
+/*
+ * trace_closest_t (frt_device.cuh) with its CULLS taken from the FP32 mirror, like trace_shadow_mixed: one 48-byte
+ * record per node instead of a header plus a dependent FP64 box, conservative FP32 slabs (a box is skipped only when it
+ * is surely missed, surely behind the origin, or surely beyond the best hit so far), every leaf intersected in FP64 on
+ * the exact ray, and the leaf's parameter offset / transform / casts-shadow bit read from its mirror record.  The
+ * minimum over the leaves does not depend on which empty subtrees are skipped.
+ */
+template <bool CASTERS>
+__device__ __forceinline__ Hit
+trace_closest_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, int *overflow)
+{
+    Hit best;
+    best.t = CUDART_INF;
+    best.u = best.v = -1.0;
+    best.leaf = -1;
+    CsgHit buf[FRT_CSG_CAP];
+    const float4 *fnodes = SF.fnodes;
+    FrameF w;
+    w.ox = (float)wr.ox;
+    w.oy = (float)wr.oy;
+    w.oz = (float)wr.oz;
+    w.dx = (float)wr.dx;
+    w.dy = (float)wr.dy;
+    w.dz = (float)wr.dz;
+    const float omax = fmaxf(fmaxf(fabsf(w.ox), fabsf(w.oy)), fabsf(w.oz));
+    const float dmax = fmaxf(1.0f, fmaxf(fmaxf(fabsf(w.dx), fabsf(w.dy)), fabsf(w.dz))); /* refracted rays are not renormalised */
+    const float eo_o = 2.0f * FRT_F32_U * omax;
+    const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, fmaf(SF.ealign, omax, eo_o));
+    const float ed_w = (FRT_F32_G + SF.ealign) * dmax;
+    frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
+    const InvDir winv = inv_dir(wr);
+    for (int rt = 0; rt < S.n_roots; ++rt) {
+        int i = __ldg(S.roots + rt);
+        const int end = __float_as_int(__ldg(fnodes + 3 * i).y);
+        int cur_xf_f = 0, cur_xf_d = 0;
+        FrameF lf = w;
+        Ray lr = wr;
+        InvDir inv = winv;
+        while (i < end) {
+            const float4 q0 = __ldg(fnodes + 3 * i), lo = __ldg(fnodes + 3 * i + 1);
+            const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
+            const int type = flags & FRT_FN_TYPE_MASK;
+            if (type >= FRT_CSG) {
+                const float4 hi = __ldg(fnodes + 3 * i + 2);
+                const int xf = __float_as_int(q0.z);
+                float tn_lo, tn_hi, tf_lo, tf_hi;
+                if (xf == 0) {
+                    box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                } else {
+                    if (xf != cur_xf_f) {
+                        cur_xf_f = xf;
+                        frame_local(lf, SF, xf, w, omax, eo_o, ed_w);
+                    }
+                    box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+                }
+                const bool miss = tn_lo > tf_hi || tf_hi < 0.0f || (double)tn_lo > best.t;
+                if (type == FRT_GROUP) {
+                    i = miss ? skip : i + 1;
+                } else {
+                    if (!miss) {
+                        const int n = csg_eval(S, i, wr, buf, overflow);
+                        for (int k = 0; k < n; ++k) {
+                            if (buf[k].t > 0 && buf[k].t < best.t &&
+                                (!CASTERS || (__float_as_int(__ldg(fnodes + 3 * buf[k].leaf).x) & FRT_FN_CASTS))) {
+                                best.t = buf[k].t;
+                                best.leaf = buf[k].leaf;
+                                best.u = best.v = -1.0;
+                            }
+                        }
+                    }
+                    i = skip;
+                }
+            } else {
+                const int xform = __float_as_int(lo.w), param = __float_as_int(q0.w);
+                if (xform != cur_xf_d) {
+                    cur_xf_d = xform;
+                    if (xform == 0) {
+                        lr = wr;
+                        inv = winv;
+                    } else {
+                        lr = ray_to_local(S, xform, wr);
+                        inv = inv_dir(lr);
+                    }
+                }
+                if (!CASTERS || (flags & FRT_FN_CASTS)) { /* hit(xs, true) skips objects that do not cast shadows */
+                    double t[4], uv[2];
+                    uv[0] = uv[1] = -1.0;
+                    const int k = prim_intersect(type, S.params + (param < 0 ? 0 : param), lr, t, uv);
+                    for (int j = 0; j < k; ++j) {
+                        if (t[j] > 0 && t[j] < best.t) {
+                            best.t = t[j];
+                            best.leaf = i;
+                            best.u = uv[0];
+                            best.v = uv[1];
+                        }
+                    }
+                }
+                i = i + 1;
+            }
+        }
+    }
+    return best;
+}
