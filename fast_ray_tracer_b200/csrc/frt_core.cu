@@ -1131,22 +1131,28 @@ k_shadow_exact(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
  */
 #define FRT_MESH_REFILL 24 /* idle lanes of a warp before it takes new items (measured: 4 -> 140 ms, 24 -> 104 ms, 32 = never -> 110 ms on the C4 stand-in) */
 #define FRT_MESH_INNER 32 /* inner nodes a lane may walk before the warp looks at its leaves */
+#define FRT_MESH_LIGHTS 8 /* lights whose shadow rays share one launch (point lights: few, long rays per launch otherwise) */
 #ifndef FRT_MESH_MINB
 #define FRT_MESH_MINB 6
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(128, FRT_MESH_MINB)
-k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
-              int light_idx, int inner_budget, int refill_min)
+k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp_base, size_t tmp_stride,
+              Counters *cnt, int level, int first_light, int n_lights, int inner_budget, int refill_min)
 {
     struct Frame {
         int right, skip, start, mid, op;
     };
+    /* the lights first_light .. first_light + n_lights - 1 (<= FRT_MESH_LIGHTS) share the launch: items are light-major,
+     * light k's (hit, sample) pairs follow light k - 1's; its per-hit records are tmp_base + k * tmp_stride */
     const unsigned int nh = min(cnt->n_hits[level], F.capacity);
-    const int NS = S.lights[light_idx].num_samples;
-    const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
-    const unsigned long long total = (unsigned long long)nh * (unsigned int)NS;
-    const bool small = total <= 0xffffffffull;
+    unsigned long long cum[FRT_MESH_LIGHTS + 1];
+    cum[0] = 0;
+    for (int k = 0; k < FRT_MESH_LIGHTS; ++k) {
+        cum[k + 1] = cum[k] + (k < n_lights ? (unsigned long long)nh * (unsigned int)S.lights[first_light + k].num_samples : 0ull);
+    }
+    const unsigned long long total = cum[FRT_MESH_LIGHTS];
+    LightTmp *tmp = tmp_base;
     const float4 *fnodes = SF.fnodes;
     const int root = __ldg(S.roots);
     const int end = __float_as_int(__ldg(fnodes + 3 * root).y);
@@ -1181,9 +1187,15 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             exhausted = base + (unsigned long long)want >= total;
             const unsigned long long item = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
             if (!active && item < total) {
-                int set_a;
+                int set_a, lk = 0;
+#pragma unroll
+                for (int k = 1; k < FRT_MESH_LIGHTS; ++k) {
+                    lk += item >= cum[k] ? 1 : 0;
+                }
+                const frt_light &L = S.lights[first_light + lk];
+                tmp = tmp_base + (size_t)lk * tmp_stride;
                 double dist2;
-                shadow_item(S, recs, tmp, pts, NS, item, small, h, set_a, wr, dist2);
+                shadow_item(S, recs, tmp, S.lpoints + 3 * L.point_offset, L.num_samples, item - cum[lk], false, h, set_a, wr, dist2);
                 if (set_a >= 0) {
                     dist = normalise_shadow_ray(wr, dist2);
                     w.ox = (float)wr.ox;
@@ -1604,6 +1616,8 @@ struct frt_scene {
     std::vector<void *> allocs;
     std::vector<size_t> alloc_bytes; /* parallel to allocs */
     std::vector<int> light_gw, light_ns;
+    LightTmp *ltmp_multi = nullptr; /* mesh mode with several lights: one LightTmp array per light of a shared launch */
+    size_t ltmp_multi_cap = 0;
     bool mesh_mode = false; /* most leaves have no FP32 fast form (OBJ meshes): shadow rays go straight to k_shadow_mesh */
     double *canvas = nullptr;     /* hsize*vsize*4 doubles */
     double *samples = nullptr;
@@ -2566,10 +2580,10 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
 }
 
 static void
-launch_light_pre(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g)
+launch_light_pre(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g, LightTmp *tmp)
 {
     const int shaft_on = sc->S.n_roots == 1 && !(F.flags & (FRT_FLAG_F64_SHADOW | FRT_FLAG_NO_SHAFT));
-#define LP(G) k_light_pre<G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->cnt, level, light, sc->SF, shaft_on)
+#define LP(G) k_light_pre<G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, tmp, sc->cnt, level, light, sc->SF, shaft_on)
     switch (g) {
     case 1: LP(1); break;
     case 2: LP(2); break;
@@ -2583,9 +2597,9 @@ launch_light_pre(frt_scene *sc, const FrameParams &F, int blocks, int level, int
 
 template <typename T>
 static void
-launch_light_final(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g)
+launch_light_final(frt_scene *sc, const FrameParams &F, int blocks, int level, int light, int g, const LightTmp *tmp)
 {
-#define LF(G) k_light_final<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, sc->ltmp, sc->canvas, sc->cnt, level, light, sc->SF.lpoints, sc->acc_amb)
+#define LF(G) k_light_final<T, G><<<blocks, 256, 0, sc->stream>>>(sc->S, F, sc->recs, tmp, sc->canvas, sc->cnt, level, light, sc->SF.lpoints, sc->acc_amb)
     switch (g) {
     case 1: LF(1); break;
     case 2: LF(2); break;
@@ -2769,7 +2783,51 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                 CK(cudaMemsetAsync(sc->acc_amb, 0, sizeof(double) * 3 * (size_t)sc->acc_cap, s));
                 CK(cudaMemsetAsync(sc->acc_fg, 0, sizeof(double) * 3 * (size_t)sc->acc_cap, s));
             }
-            if (F.include_direct) {
+            if (F.include_direct && sc->mesh_mode && sc->S.n_roots == 1 && sc->S.n_lights > 1 && !(F.flags & FRT_FLAG_F64_SHADOW)) {
+                /* mesh scene, several lights: their shadow rays share launches of k_shadow_mesh (FRT_MESH_LIGHTS at a time) */
+                const size_t need = (size_t)sc->capacity * std::min(sc->S.n_lights, FRT_MESH_LIGHTS);
+                if (sc->ltmp_multi_cap < need) {
+                    void *p = nullptr;
+                    CK(scene_alloc(sc, &p, need * sizeof(LightTmp)));
+                    sc->ltmp_multi = (LightTmp *)p;
+                    sc->ltmp_multi_cap = need;
+                }
+                const int blocks = sm_blocks * 8;
+                const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
+                for (int l0 = 0; l0 < sc->S.n_lights; l0 += FRT_MESH_LIGHTS) {
+                    const int nl = std::min(FRT_MESH_LIGHTS, sc->S.n_lights - l0);
+                    if (sc->light_ev.size() < 2 * (size_t)(light_launches + 1)) {
+                        cudaEvent_t a, b;
+                        CK(cudaEventCreate(&a));
+                        CK(cudaEventCreate(&b));
+                        sc->light_ev.push_back(a);
+                        sc->light_ev.push_back(b);
+                    }
+                    for (int k = 0; k < nl; ++k) {
+                        launch_light_pre(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
+                    }
+                    CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
+                    CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
+                    const int mblocks = getenv("FRT_MESH_BLOCKS") ? atoi(getenv("FRT_MESH_BLOCKS")) : sm_blocks * 8;
+                    const int m_inner = getenv("FRT_MESH_INNER_STEPS") ? atoi(getenv("FRT_MESH_INNER_STEPS")) : FRT_MESH_INNER;
+                    const int m_refill = getenv("FRT_MESH_REFILL_MIN") ? atoi(getenv("FRT_MESH_REFILL_MIN")) : FRT_MESH_REFILL;
+                    if (count) {
+                        k_shadow_mesh<true><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp_multi, sc->capacity, sc->cnt, level, l0, nl, m_inner, m_refill);
+                    } else {
+                        k_shadow_mesh<false><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp_multi, sc->capacity, sc->cnt, level, l0, nl, m_inner, m_refill);
+                    }
+                    CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
+                    for (int k = 0; k < nl; ++k) {
+                        if (F.flags & FRT_FLAG_F64_SHADING) {
+                            launch_light_final<double>(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
+                        } else {
+                            launch_light_final<float>(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
+                        }
+                    }
+                    launches += 1 + 2 * nl;
+                    ++light_launches;
+                }
+            } else if (F.include_direct) {
                 for (int li = 0; li < sc->S.n_lights; ++li) {
                     if (sc->light_ev.size() < 2 * (size_t)(light_launches + 1)) {
                         cudaEvent_t a, b;
@@ -2779,7 +2837,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         sc->light_ev.push_back(b);
                     }
                     const int blocks = sm_blocks * 8;
-                    launch_light_pre(sc, F, blocks, level, li, gw[li]);
+                    launch_light_pre(sc, F, blocks, level, li, gw[li], sc->ltmp);
                     CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
                     const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
                     if (F.flags & FRT_FLAG_F64_SHADOW) {
@@ -2796,9 +2854,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         const int m_inner = getenv("FRT_MESH_INNER_STEPS") ? atoi(getenv("FRT_MESH_INNER_STEPS")) : FRT_MESH_INNER;
                         const int m_refill = getenv("FRT_MESH_REFILL_MIN") ? atoi(getenv("FRT_MESH_REFILL_MIN")) : FRT_MESH_REFILL;
                         if (count) {
-                            k_shadow_mesh<true><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, m_inner, m_refill);
+                            k_shadow_mesh<true><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, 0, sc->cnt, level, li, 1, m_inner, m_refill);
                         } else {
-                            k_shadow_mesh<false><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, m_inner, m_refill);
+                            k_shadow_mesh<false><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, 0, sc->cnt, level, li, 1, m_inner, m_refill);
                         }
                         CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
                         launches += 1;
@@ -2841,9 +2899,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         launches += 3;
                     }
                     if (F.flags & FRT_FLAG_F64_SHADING) {
-                        launch_light_final<double>(sc, F, blocks, level, li, gw[li]);
+                        launch_light_final<double>(sc, F, blocks, level, li, gw[li], sc->ltmp);
                     } else {
-                        launch_light_final<float>(sc, F, blocks, level, li, gw[li]);
+                        launch_light_final<float>(sc, F, blocks, level, li, gw[li], sc->ltmp);
                     }
                     launches += 2;
                     ++light_launches;
