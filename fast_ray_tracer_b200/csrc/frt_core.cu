@@ -707,7 +707,8 @@ quadrant_sample(int4 lq, int q, int k)
     if (lq.y == 0) {
         return k;
     }
-    const int lv = k / lq.y, lu = k - lv * lq.y;
+    const int lv = (int)(((float)k + 0.5f) * __frcp_rn((float)lq.y)); /* k / hu, exact for the few hundred samples of a light */
+    const int lu = k - lv * lq.y;
     return ((q >> 1) * lq.z + lv) * lq.w + (q & 1) * lq.y + lu;
 }
 

@@ -50,7 +50,8 @@ def gpu(desc, reps=3, photons=None):
     out = {"frame_ms": min(ms), "rays_traced": cnt.rays_total, "rays_shadow": cnt.rays_shadow, "rays_gather": cnt.rays_gather,
            "hits_shaded": cnt.hits_shaded, "shadow_nodes_per_ray": cnt.shadow_nodes / max(cnt.rays_shadow, 1),
            "algorithmic_flop_per_shadow_ray": cnt.light_flops / max(cnt.rays_shadow - cnt.shadow_deferred, 1),
-           "deferred_fraction": cnt.shadow_deferred / max(cnt.rays_shadow, 1), "launches": cnt.kernel_launches}
+           "deferred_fraction": cnt.shadow_deferred / max(cnt.rays_shadow, 1), "launches": cnt.kernel_launches,
+           "shadow_rays_decided_per_hit_or_quadrant": cnt.extra["shadow_reasons"][0] / max(cnt.rays_shadow, 1)}
     if ref is not None:
         out["rays_reference_counted"] = ref.rays_total
     if pm:
@@ -80,6 +81,15 @@ blob = REF / "blobs" / "bounding_boxes.frt"
 if blob.exists():
     d = frt.SceneDesc.load(blob)
     rows["C3b bounding_boxes 1200x480 1spp (6 dragons)"] = gpu(d)
+
+blob = REF / "blobs" / "sibenik_surrogate.frt"
+if blob.exists():
+    d = frt.SceneDesc.load(blob)  # 800 x 1000, 4 x 4 CMJ, 10 x 10 area light (one cached set), 85 K textured triangles
+    key = "C4 stand-in (sibenik.obj is not in the reference tree) 800x1000 4x4, 10x10 area light"
+    rows[key] = gpu(d, reps=2)
+    r = ref_run("sibenik_surrogate_ref", {"FRT_REF_HSIZE": "80", "FRT_REF_VSIZE": "100", "FRT_REF_USTEPS": "2", "FRT_REF_VSTEPS": "2"})
+    if r:
+        rows[key]["reference_frame_s_scaled_from_80x100_2x2"] = 400 * float(r["FRT_RENDER_SECONDS"])
 
 d = frt.SceneDesc.load(G / "cornell_gi_64.frt")
 d.set_resolution(800, 800)
