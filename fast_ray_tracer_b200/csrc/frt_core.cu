@@ -1617,6 +1617,8 @@ struct frt_scene {
     std::vector<void *> allocs;
     std::vector<size_t> alloc_bytes; /* parallel to allocs */
     std::vector<int> light_gw, light_ns;
+    unsigned int *h_nrays = nullptr; /* pinned: the next level's ray count, read back behind k_shade without stalling the stream */
+    cudaEvent_t nrays_ev = nullptr;
     LightTmp *ltmp_multi = nullptr; /* mesh mode with several lights: one LightTmp array per light of a shared launch */
     size_t ltmp_multi_cap = 0;
     bool mesh_mode = false; /* most leaves have no FP32 fast form (OBJ meshes): shadow rays go straight to k_shadow_mesh */
@@ -1946,6 +1948,7 @@ frt_scene_destroy(frt_scene *sc)
     for (auto &e : sc->ev) {
         if (e) cudaEventDestroy(e);
     }
+    if (sc->nrays_ev) cudaEventDestroy(sc->nrays_ev);
     for (auto &e : sc->light_ev) {
         cudaEventDestroy(e);
     }
@@ -2474,6 +2477,21 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
             return frt_set_error(FRT_ERR_CUDA, "cudaEventCreate failed");
         }
     }
+    {
+        /* one pinned word per device for the whole process (one frame at a time per device, like the parked buffers) */
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        static std::map<int, unsigned int *> pinned;
+        auto it = pinned.find(device);
+        if (it == pinned.end()) {
+            unsigned int *p = nullptr;
+            if (cudaHostAlloc((void **)&p, 64, cudaHostAllocPortable) == cudaSuccess) {
+                it = pinned.emplace(device, p).first;
+            }
+        }
+        if (it != pinned.end() && cudaEventCreateWithFlags(&sc->nrays_ev, cudaEventDisableTiming) == cudaSuccess) {
+            sc->h_nrays = it->second;
+        }
+    }
 #undef UP
     *out = sc;
     return FRT_OK;
@@ -2772,6 +2790,15 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         k_raygen<<<rg_blocks, 256, 0, s>>>(C, F, sc->q[0], sc->cnt, (unsigned int)first, n);
         ++launches;
         for (int level = 0; level <= F.path_length; ++level) {
+            if (level > 0 && sc->h_nrays != nullptr) {
+                /* the count was copied right behind the previous k_shade; the stream is still busy with that level's light
+                 * stage, so this wait costs nothing -- and the empty tail of the recursion (Cornell: levels 2..5, ~9 launches
+                 * of full grids each) is never enqueued */
+                CK(cudaEventSynchronize(sc->nrays_ev));
+                if (sc->h_nrays[0] == 0) {
+                    break;
+                }
+            }
             RayQ &qi = sc->q[level & 1];
             RayQ &qo = sc->q[(level + 1) & 1];
             /* level 0 has n rays; deeper levels read their count on the device: size the grid for the worst case
@@ -2780,6 +2807,10 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, sc->SF, qi, sc->hq, sc->cnt, level, F.capacity);
             k_shade<<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
             launches += 2;
+            if (sc->h_nrays != nullptr && level < F.path_length) {
+                CK(cudaMemcpyAsync(sc->h_nrays, &sc->cnt->n_rays[level + 1], sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+                CK(cudaEventRecord(sc->nrays_ev, s));
+            }
             if (F.use_gi) {
                 CK(cudaMemsetAsync(sc->acc_amb, 0, sizeof(double) * 3 * (size_t)sc->acc_cap, s));
                 CK(cudaMemsetAsync(sc->acc_fg, 0, sizeof(double) * 3 * (size_t)sc->acc_cap, s));
