@@ -372,7 +372,8 @@ def cuda_arm(args) -> dict:
             "clocks": clk,
             "e2e": {"value": ref_rays / e2e_s / 1e6, "unit": "Mrays/s", "frame_ms": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(desc.host_bytes) * world, "d2h_bytes_per_step": vsize * hsize * 32,
-                    "path": "frt_scene_create(host desc, light-sample cache page-locked) + frt_render + canvas to pinned host memory + frt_scene_destroy, per step"},
+                    "path": "frt_scene_create(host desc; the page-locked light-sample cache is copied asynchronously and the frame waits "
+                            "for it where its light stage begins) + frt_render + canvas to pinned host memory + frt_scene_destroy, per step"},
             "gpu_launches": total_launches,
             "roofline": {"bound": "fp32-issue", "kernel": "k_shadow_f32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic_per_launch(args),

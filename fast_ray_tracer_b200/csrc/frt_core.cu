@@ -713,6 +713,7 @@ quadrant_sample(int4 lq, int q, int k)
 }
 
 /* pending entry: hit in bits 0..27, quadrant in bits 28..29, bit 30 = decided by k_shadow_bulk, bit 31 = ... as lit */
+#define FRT_BOX_CHUNKS 64
 #define FRT_PEND_HIT_MASK 0x0fffffffu
 #define FRT_PEND_BULK 0x40000000u
 #define FRT_PEND_LIT 0x80000000u
@@ -821,7 +822,7 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
 
 /* axis-aligned bounds of the light points of quadrant blockIdx.y over the sample sets blockIdx.x, +gridDim.x, ... */
 __global__ void __launch_bounds__(256)
-k_light_boxes(const double *__restrict__ pts, int cache_len, int NS, int4 lq, double *__restrict__ partial)
+k_light_boxes(const double *__restrict__ pts, int cache_len, int NS, int4 lq, double *__restrict__ partial, int chunk_stride)
 {
     const int q = blockIdx.y;
     double lo[3] = { CUDART_INF, CUDART_INF, CUDART_INF }, hi[3] = { -CUDART_INF, -CUDART_INF, -CUDART_INF };
@@ -854,7 +855,50 @@ k_light_boxes(const double *__restrict__ pts, int cache_len, int NS, int4 lq, do
         for (int w = 1; w < 8; ++w) {
             v = threadIdx.x < 3 ? fmin(v, sm[w][threadIdx.x]) : fmax(v, sm[w][threadIdx.x]);
         }
-        partial[((size_t)q * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = v;
+        partial[((size_t)q * chunk_stride + blockIdx.x) * 6 + threadIdx.x] = v;
+    }
+}
+
+/* second stage of k_light_boxes, one block per light: reduce the chunks, inflate, write {all, quadrant 0..3} */
+__global__ void
+k_light_boxes_finish(const double *__restrict__ partial, const int4 *__restrict__ lquad, const int *__restrict__ chunks, double *__restrict__ lbox)
+{
+    const int li = blockIdx.x, q = threadIdx.x;
+    const int nq = lquad[li].y ? 4 : 1, nb = chunks[li];
+    __shared__ double box[4][6];
+    if (q < 4) {
+        double b[6] = { CUDART_INF, CUDART_INF, CUDART_INF, -CUDART_INF, -CUDART_INF, -CUDART_INF };
+        if (q < nq) {
+            const double *pp = partial + ((size_t)li * 4 + q) * FRT_BOX_CHUNKS * 6;
+            for (int c = 0; c < nb; ++c) {
+                for (int k = 0; k < 3; ++k) {
+                    b[k] = fmin(b[k], pp[6 * c + k]);
+                    b[3 + k] = fmax(b[3 + k], pp[6 * c + 3 + k]);
+                }
+            }
+            for (int k = 0; k < 3; ++k) { /* inflate: the points are exact, the slack covers nothing but habit */
+                const double m = 1e-12 * (fmax(fabs(b[k]), fabs(b[3 + k])) + 1.0);
+                b[k] -= m;
+                b[3 + k] += m;
+            }
+        }
+        for (int k = 0; k < 6; ++k) {
+            box[q][k] = b[k];
+        }
+    }
+    __syncthreads();
+    if (q < 4) {
+        double *out = lbox + (size_t)30 * li;
+        for (int k = 0; k < 6; ++k) {
+            double all = box[0][k];
+            for (int j = 1; j < nq; ++j) {
+                all = k < 3 ? fmin(all, box[j][k]) : fmax(all, box[j][k]);
+            }
+            if (q == 0) {
+                out[k] = all;
+            }
+            out[6 * (q + 1) + k] = q < nq ? box[q][k] : all;
+        }
     }
 }
 
@@ -1617,6 +1661,9 @@ struct frt_scene {
     std::vector<void *> allocs;
     std::vector<size_t> alloc_bytes; /* parallel to allocs */
     std::vector<int> light_gw, light_ns;
+    cudaStream_t upload_stream = nullptr; /* the light-sample cache and what is derived from it travel here */
+    cudaEvent_t upload_ev = nullptr;
+    bool upload_pending = false;          /* the render stream has not waited for upload_ev yet */
     unsigned int *h_nrays = nullptr; /* pinned: the next level's ray count, read back behind k_shade without stalling the stream */
     cudaEvent_t nrays_ev = nullptr;
     LightTmp *ltmp_multi = nullptr; /* mesh mode with several lights: one LightTmp array per light of a shared launch */
@@ -1782,6 +1829,21 @@ scene_release_allocs(frt_scene *sc)
     sc->alloc_bytes.clear();
 }
 
+static std::map<const char *, size_t> g_registered; /* page-locked caller buffers (frt_host_register), under g_park_mu */
+
+static bool
+host_range_registered(const void *ptr, size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_park_mu);
+    const char *p = (const char *)ptr;
+    for (const auto &r : g_registered) {
+        if (p >= r.first && p + bytes <= r.first + r.second) {
+            return true;
+        }
+    }
+    return false;
+}
+
 extern "C" int
 frt_host_register(void *ptr, size_t bytes)
 {
@@ -1789,6 +1851,8 @@ frt_host_register(void *ptr, size_t bytes)
         return frt_set_error(FRT_ERR_ARG, "frt_host_register: empty buffer");
     }
     CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    std::lock_guard<std::mutex> lk(g_park_mu);
+    g_registered[(const char *)ptr] = bytes;
     return FRT_OK;
 }
 
@@ -1797,6 +1861,10 @@ frt_host_unregister(void *ptr)
 {
     if (ptr == nullptr) {
         return frt_set_error(FRT_ERR_ARG, "frt_host_unregister: null pointer");
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        g_registered.erase((const char *)ptr);
     }
     CK(cudaHostUnregister(ptr));
     return FRT_OK;
@@ -1927,6 +1995,12 @@ frt_scene_destroy(frt_scene *sc)
         return;
     }
     cudaSetDevice(sc->device);
+    if (sc->upload_stream) {
+        cudaStreamSynchronize(sc->upload_stream); /* the caller's page-locked buffer may go away after this call */
+    }
+    if (sc->stream) {
+        cudaStreamSynchronize(sc->stream);
+    }
     pm_free(sc);
     scene_release_allocs(sc);
     if (sc->capacity > 0 && !sc->frame_allocs.empty()) {
@@ -1949,6 +2023,8 @@ frt_scene_destroy(frt_scene *sc)
         if (e) cudaEventDestroy(e);
     }
     if (sc->nrays_ev) cudaEventDestroy(sc->nrays_ev);
+    if (sc->upload_ev) cudaEventDestroy(sc->upload_ev);
+    if (sc->upload_stream) cudaStreamDestroy(sc->upload_stream);
     for (auto &e : sc->light_ev) {
         cudaEventDestroy(e);
     }
@@ -2277,25 +2353,26 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     if (rc != FRT_OK) return rc;
     sc->SF.bmax = nextafterf((float)(bmax * (1.0 + 1e-6)), INFINITY);
     sc->SF.n_nodes = d->n_nodes;
-    /* FP32 copy of the light sample points, converted on the device */
+    /* FP32 copy of the light sample points, converted on the device; then, per light, the bounds of its sample points
+     * (all of them, and per quadrant of the sample grid) over every cached set, reduced on the device from the points as
+     * uploaded -- no assumption about where the sampler puts sample (u, v).  All of it runs on the upload stream behind
+     * the copy of the points (frt_scene_create), so none of it needs the host. */
+    cudaStream_t us = sc->upload_stream;
     const size_t np = (size_t)3 * d->n_light_points;
     float *fp = nullptr;
     CK(scene_alloc(sc, (void **)&fp, std::max<size_t>(np, 1) * sizeof(float)));
     if (np) {
-        k_to_float<<<148 * 8, 256>>>(sc->S.lpoints, fp, np);
+        k_to_float<<<148 * 8, 256, 0, us>>>(sc->S.lpoints, fp, np);
         CK(cudaGetLastError());
-        CK(cudaDeviceSynchronize());
     }
     sc->SF.lpoints = fp;
 
-    /* per light: bounds of its sample points (all of them, and per quadrant of the sample grid) over every cached set,
-     * reduced on the device from the points as uploaded -- no assumption about where the sampler puts sample (u, v) */
-    std::vector<double> lbox((size_t)30 * std::max(d->n_lights, 1), 0.0);
-    std::vector<int4> lquad(std::max(d->n_lights, 1), make_int4(1, 0, 0, 0));
-    const int chunks = 64;
-    double *partial = nullptr;
-    CK(cudaMalloc(&partial, sizeof(double) * 6 * 4 * chunks));
-    std::vector<double> hp((size_t)6 * 4 * chunks);
+    const int nl = std::max(d->n_lights, 1);
+    std::vector<int4> lquad(nl, make_int4(1, 0, 0, 0));
+    std::vector<int> chunks(nl, 1);
+    double *partial = nullptr, *lbox = nullptr;
+    CK(scene_alloc(sc, (void **)&partial, sizeof(double) * 6 * 4 * FRT_BOX_CHUNKS * nl));
+    CK(scene_alloc(sc, (void **)&lbox, sizeof(double) * 30 * nl));
     for (int li = 0; li < d->n_lights; ++li) {
         const frt_light &L = d->lights[li];
         const int NS = L.num_samples;
@@ -2304,48 +2381,25 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
             lq = make_int4(NS / 4, L.usteps / 2, L.vsteps / 2, L.usteps);
         }
         lquad[li] = lq;
-        const int nq = lq.y ? 4 : 1;
-        const int nb = std::max(1, std::min(chunks, L.cache_len));
-        k_light_boxes<<<dim3(nb, nq), 256>>>(sc->S.lpoints + 3 * L.point_offset, L.cache_len, NS, lq, partial);
-        CK(cudaGetLastError());
-        CK(cudaMemcpy(hp.data(), partial, sizeof(double) * 6 * nq * nb, cudaMemcpyDeviceToHost));
-        double *all = &lbox[(size_t)30 * li];
-        for (int k = 0; k < 3; ++k) {
-            all[k] = INFINITY;
-            all[3 + k] = -INFINITY;
-        }
-        for (int q = 0; q < nq; ++q) {
-            double *b = &lbox[(size_t)30 * li + 6 * (q + 1)];
-            for (int k = 0; k < 3; ++k) {
-                b[k] = INFINITY;
-                b[3 + k] = -INFINITY;
-            }
-            for (int c = 0; c < nb; ++c) {
-                const double *pp = &hp[((size_t)q * nb + c) * 6];
-                for (int k = 0; k < 3; ++k) {
-                    b[k] = std::min(b[k], pp[k]);
-                    b[3 + k] = std::max(b[3 + k], pp[3 + k]);
-                }
-            }
-            for (int k = 0; k < 3; ++k) { /* inflate: the points are exact, the slack covers nothing but habit */
-                const double m = 1e-12 * (std::max(fabs(b[k]), fabs(b[3 + k])) + 1.0);
-                b[k] -= m;
-                b[3 + k] += m;
-                all[k] = std::min(all[k], b[k]);
-                all[3 + k] = std::max(all[3 + k], b[3 + k]);
-            }
-        }
-        if (nq == 1) {
-            for (int q = 1; q < 4; ++q) {
-                std::copy(all, all + 6, &lbox[(size_t)30 * li + 6 * (q + 1)]);
-            }
-        }
+        chunks[li] = std::max(1, std::min(FRT_BOX_CHUNKS, L.cache_len));
     }
-    cudaFree(partial);
-    rc = upload(sc, lbox.data(), lbox.size(), &sc->SF.lbox);
-    if (rc != FRT_OK) return rc;
     rc = upload(sc, lquad.data(), lquad.size(), &sc->SF.lquad);
     if (rc != FRT_OK) return rc;
+    const int *dchunks = nullptr;
+    rc = upload(sc, chunks.data(), chunks.size(), &dchunks);
+    if (rc != FRT_OK) return rc;
+    for (int li = 0; li < d->n_lights; ++li) {
+        const frt_light &L = d->lights[li];
+        const int nq = lquad[li].y ? 4 : 1;
+        k_light_boxes<<<dim3(chunks[li], nq), 256, 0, us>>>(sc->S.lpoints + 3 * L.point_offset, L.cache_len, L.num_samples, lquad[li],
+                                                          partial + (size_t)li * 4 * FRT_BOX_CHUNKS * 6, FRT_BOX_CHUNKS);
+        CK(cudaGetLastError());
+    }
+    if (d->n_lights > 0) {
+        k_light_boxes_finish<<<d->n_lights, 32, 0, us>>>(partial, sc->SF.lquad, dchunks, lbox);
+        CK(cudaGetLastError());
+    }
+    sc->SF.lbox = lbox;
     return FRT_OK;
 }
 
@@ -2402,9 +2456,39 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
     UP(upload(sc, d->textures, (size_t)d->n_textures, &S.texs));
     UP(upload(sc, d->texels, (size_t)3 * d->n_texels, &S.texels));
     UP(upload(sc, d->lights, (size_t)d->n_lights, &S.lights));
-    UP(upload(sc, d->light_points, (size_t)3 * d->n_light_points, &S.lpoints));
+    if (cudaStreamCreateWithFlags(&sc->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sc->upload_ev, cudaEventDisableTiming) != cudaSuccess) {
+        frt_scene_destroy(sc);
+        return frt_set_error(FRT_ERR_CUDA, "cudaStreamCreate (upload) failed");
+    }
+    /* The light-sample cache is the one large buffer of a scene (157 MB for the shipped Cornell box).  When the caller
+     * page-locked it (frt_host_register) it is copied asynchronously on the upload stream and the first frame only waits
+     * for it where its light stage begins -- ray generation, the primary rays and their shading run meanwhile.  The
+     * buffer must then stay valid until the first frt_render (or frt_scene_destroy) returns; an unregistered buffer is
+     * copied before this call returns, as ever. */
+    const size_t lp_bytes = (size_t)3 * d->n_light_points * sizeof(double);
+    const bool async_points = lp_bytes >= ((size_t)1 << 20) && host_range_registered(d->light_points, lp_bytes);
+    if (async_points) {
+        double *dp = nullptr;
+        if (scene_alloc(sc, (void **)&dp, lp_bytes) != cudaSuccess ||
+            cudaMemcpyAsync(dp, d->light_points, lp_bytes, cudaMemcpyHostToDevice, sc->upload_stream) != cudaSuccess) {
+            frt_scene_destroy(sc);
+            return frt_set_error(FRT_ERR_CUDA, "asynchronous upload of the light points failed");
+        }
+        S.lpoints = dp;
+    } else {
+        UP(upload(sc, d->light_points, (size_t)3 * d->n_light_points, &S.lpoints));
+    }
     UP(upload(sc, d->roots, (size_t)d->n_roots, &S.roots));
     UP(build_f32_mirror(sc, d));
+    if (cudaEventRecord(sc->upload_ev, sc->upload_stream) != cudaSuccess) {
+        frt_scene_destroy(sc);
+        return frt_set_error(FRT_ERR_CUDA, "cudaEventRecord (upload) failed");
+    }
+    sc->upload_pending = true;
+    if (!async_points) {
+        cudaStreamSynchronize(sc->upload_stream); /* nothing of the caller's is read after this call returns */
+    }
     S.n_roots = d->n_roots;
     S.n_nodes = d->n_nodes;
     S.n_lights = d->n_lights;
@@ -2595,6 +2679,17 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
         return rc;
     }
     sc->capacity = capacity;
+    return FRT_OK;
+}
+
+/* the light stage is the first consumer of the light points and of what the upload stream derives from them */
+static int
+wait_for_upload(frt_scene *sc, cudaStream_t s)
+{
+    if (sc->upload_pending) {
+        CK(cudaStreamWaitEvent(s, sc->upload_ev, 0));
+        sc->upload_pending = false;
+    }
     return FRT_OK;
 }
 
@@ -2838,6 +2933,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                     for (int k = 0; k < nl; ++k) {
                         launch_light_pre(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
                     }
+                    if (wait_for_upload(sc, s) != FRT_OK) return FRT_ERR_CUDA;
                     CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
                     CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
                     const int mblocks = getenv("FRT_MESH_BLOCKS") ? atoi(getenv("FRT_MESH_BLOCKS")) : sm_blocks * 8;
@@ -2870,6 +2966,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                     }
                     const int blocks = sm_blocks * 8;
                     launch_light_pre(sc, F, blocks, level, li, gw[li], sc->ltmp);
+                    if (wait_for_upload(sc, s) != FRT_OK) return FRT_ERR_CUDA;
                     CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
                     const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
                     if (F.flags & FRT_FLAG_F64_SHADOW) {
@@ -3200,6 +3297,10 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
         return frt_set_error(FRT_ERR_ARG, "frt_photons_emit: null argument");
     }
     CK(cudaSetDevice(sc->device));
+    if (sc->upload_pending) { /* the emitters read the lights; be conservative about what the upload stream still writes */
+        CK(cudaStreamSynchronize(sc->upload_stream));
+        sc->upload_pending = false;
+    }
     const frt_config &g = sc->cfg;
     const int world = cfg->world > 0 ? cfg->world : 1;
     if (cfg->rank < 0 || cfg->rank >= world) {

@@ -257,15 +257,20 @@ int frt_device_count(void);
 /* layout check for foreign-language bindings: sizeof of a named ABI struct ("frt_node", "frt_light", ...), or -1 */
 int frt_abi_sizeof(const char *struct_name);
 
-/* Upload a flattened scene (host pointers in desc are read during the call only). */
+/* Upload a flattened scene (host pointers in desc are read during the call only; the one exception is a light_points
+ * buffer registered with frt_host_register, see there). */
 int frt_scene_create(const frt_scene_desc *desc, int device, frt_scene **out);
 void frt_scene_destroy(frt_scene *scene);
 /* frt_scene_destroy parks the scene-independent frame buffers (ray queues) and the large scene buffers (by size) for
  * the next scene on the same device; frt_trim frees them. */
 void frt_trim(int device);
 /* Page-lock / release a caller-owned host buffer a scene description points at (typically light_points, the 157 MB
- * sample-set cache the reference builds in light.c:100-191): frt_scene_create then uploads it at PCIe speed.  Worth
- * it for a host loop that creates a scene per frame; a one-shot program need not call it. */
+ * sample-set cache the reference builds in light.c:100-191): frt_scene_create then uploads it at PCIe speed and
+ * ASYNCHRONOUSLY -- the first frame waits for it only where its light stage begins, so the copy hides behind ray
+ * generation, the primary rays and their shading.  A registered light_points buffer must therefore stay valid and
+ * unmodified until the first frt_render of the scene (or frt_scene_destroy) has returned; every other buffer, and an
+ * unregistered light_points, is read during frt_scene_create only.  Worth it for a host loop that creates a scene per
+ * frame; a one-shot program need not call it. */
 int frt_host_register(void *ptr, size_t bytes);
 int frt_host_unregister(void *ptr);
 

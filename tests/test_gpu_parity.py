@@ -133,19 +133,26 @@ def test_fp64_shadow_and_shading_flags_give_the_same_frame(frt, name):
 def test_per_hit_shadow_decision_matches_the_per_ray_kernels(frt):
     """k_shadow_bulk decides all shadow rays of a hit at once where the shaft's intervals separate (the umbra of the
     Cornell window wall).  It must fire on that scene, and the frame must be the one the per-ray kernels produce."""
-    from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_F64_SHADING, FRT_FLAG_NO_BULK, FRT_FLAG_VERIFY_F32
+    from fast_ray_tracer_b200.api import (FRT_FLAG_COUNT_RAYS, FRT_FLAG_F64_SHADING, FRT_FLAG_NO_BULK, FRT_FLAG_NO_SPLIT,
+                                          FRT_FLAG_VERIFY_F32)
 
     desc = frt.SceneDesc.load(GOLDEN / "cornell_exact_200.frt")
     with frt.Scene(desc) as sc:
         a, sa = sc.render(flags=FRT_FLAG_F64_SHADING | FRT_FLAG_COUNT_RAYS)
         b, sb = sc.render(flags=FRT_FLAG_F64_SHADING | FRT_FLAG_COUNT_RAYS | FRT_FLAG_NO_BULK)
+        c, sn = sc.render(flags=FRT_FLAG_F64_SHADING | FRT_FLAG_COUNT_RAYS | FRT_FLAG_NO_SPLIT)
         _, sv = sc.render(flags=FRT_FLAG_VERIFY_F32 | FRT_FLAG_COUNT_RAYS)
+        p, _ = sc.render(flags=FRT_FLAG_F64_SHADING)  # the production kernels (no counting build)
     bulk = sa.extra["shadow_reasons"][0]
-    assert bulk > 0.3 * sa.rays_shadow, (bulk, sa.rays_shadow)
+    whole = sn.extra["shadow_reasons"][0]  # decided for the whole light only, no retry per quadrant of the sample grid
+    assert whole > 0.3 * sa.rays_shadow, (whole, sa.rays_shadow)
+    assert bulk > whole, (bulk, whole)
     assert sb.extra["shadow_reasons"][0] == 0
-    assert sa.rays_shadow == sb.rays_shadow  # bulk-decided rays still count as shadow rays of the frame
+    assert sa.rays_shadow == sb.rays_shadow == sn.rays_shadow  # rays decided at once still count as shadow rays of the frame
     assert sv.shadow_mismatch == 0 and sv.extra["shadow_reasons"][0] == bulk
     assert np.allclose(a, b, rtol=0, atol=1e-12)
+    assert np.allclose(a, c, rtol=0, atol=1e-12)
+    assert np.allclose(a, p, rtol=0, atol=1e-12)
 
 
 def test_six_dragons_through_the_divided_group_tree(frt):
