@@ -200,3 +200,9 @@ def test_sibenik_surrogate_textured_mesh_under_an_area_light(frt):
     canvas, stats = frt.render_multi(desc)
     rep = parity_report(canvas[..., :3], ref)
     assert rep["within_1lsb"] >= GATE_WITHIN_1LSB, rep
+    # the per-hit candidate lists (k_mesh_shaft / k_mesh_rays) and the tree walk of k_shadow_mesh against the pure FP64 walk
+    from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_VERIFY_F32
+
+    desc.set_resolution(64, 80)
+    _, st = frt.render_multi(desc, flags=FRT_FLAG_VERIFY_F32 | FRT_FLAG_COUNT_RAYS)
+    assert st.shadow_mismatch == 0 and st.rays_shadow > 0, st
