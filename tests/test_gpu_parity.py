@@ -206,3 +206,26 @@ def test_sibenik_surrogate_textured_mesh_under_an_area_light(frt):
     desc.set_resolution(64, 80)
     _, st = frt.render_multi(desc, flags=FRT_FLAG_VERIFY_F32 | FRT_FLAG_COUNT_RAYS)
     assert st.shadow_mismatch == 0 and st.rays_shadow > 0, st
+
+
+def test_page_locked_light_cache_is_uploaded_asynchronously_with_the_same_frame(frt):
+    """frt_host_register: a page-locked light-sample cache is copied on the upload stream and the frame waits for it
+    where its light stage begins.  Same scene, same seed, pinned or not: the same frame; and the scene buffers of a
+    destroyed scene are handed to the next one (no stale contents)."""
+    from fast_ray_tracer_b200.lightcache import expand_area_light_caches
+
+    def build():
+        d = frt.SceneDesc.load(GOLDEN / "cornell_cache64.frt")
+        d.set_resolution(120, 120)
+        expand_area_light_caches(d, 2000)  # 4.8 MB of light points: above the 1 MB threshold of the asynchronous path
+        return d
+
+    plain, pinned = build(), build().pin()
+    frames = []
+    for d in (plain, pinned, pinned, plain):
+        with frt.Scene(d) as sc:
+            c, st = sc.render(seed=5)
+            frames.append(c.copy())
+    for f in frames[1:]:
+        assert np.allclose(frames[0], f, rtol=0, atol=1e-12)
+    pinned.unpin()
