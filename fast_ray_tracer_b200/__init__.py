@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     Scene,
     SceneDesc,
     device_count,
+    encode_ppm16,
     library_path,
     load_library,
     measure_fma_peak,
@@ -22,6 +23,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "FrtError", "RenderStats", "Scene", "SceneDesc", "device_count", "library_path", "load_library",
+    "FrtError", "RenderStats", "Scene", "SceneDesc", "device_count", "encode_ppm16", "library_path", "load_library",
     "measure_fma_peak", "render", "render_multi",
 ]

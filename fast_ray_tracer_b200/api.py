@@ -130,6 +130,7 @@ EXPORTS = [
     "frt_render", "frt_canvas_download", "frt_owned_rows", "frt_photons_emit", "frt_photons_count",
     "frt_photons_export", "frt_photons_import", "frt_photons_finish", "frt_measure_fma_peak",
     "frt_scene_save", "frt_scene_load", "frt_scene_desc_free", "frt_trim", "frt_host_register", "frt_host_unregister",
+    "frt_ppm16_size", "frt_canvas_encode_ppm16", "frt_encode_ppm16",
 ]
 
 
@@ -153,6 +154,11 @@ def load_library():
     lib.frt_scene_destroy.restype = None
     lib.frt_trim.argtypes = [C.c_int]
     lib.frt_trim.restype = None
+    lib.frt_ppm16_size.argtypes = [C.c_int, C.c_int]
+    lib.frt_ppm16_size.restype = C.c_size_t
+    lib.frt_canvas_encode_ppm16.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
+    lib.frt_encode_ppm16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_double)]
     lib.frt_host_register.argtypes = [C.c_void_p, C.c_size_t]
     lib.frt_host_unregister.argtypes = [C.c_void_p]
     lib.frt_render.argtypes = [C.c_void_p, C.POINTER(frt_render_cfg), C.c_void_p, C.POINTER(frt_stats)]
@@ -194,6 +200,22 @@ def measure_fma_peak(device: int = 0):
     a, b = C.c_double(), C.c_double()
     _check(lib.frt_measure_fma_peak(device, C.byref(a), C.byref(b)), "frt_measure_fma_peak")
     return a.value, b.value
+
+
+def encode_ppm16(canvas: np.ndarray, use_scaling: bool = True, device: int = 0, return_ms: bool = False):
+    """write_ppm_file's file contents (16-bit P6, reference canvas.c:150-328) for a host canvas [h, w, 3 or 4] float64,
+    produced on the device (frt_encode_ppm16)."""
+    lib = load_library()
+    h, w = canvas.shape[:2]
+    rgba = np.zeros((h, w, 4), dtype=np.float64)
+    rgba[..., : min(canvas.shape[2], 4)] = canvas[..., :4]
+    n = lib.frt_ppm16_size(w, h)
+    out = np.empty(n, dtype=np.uint8)
+    got, ms = C.c_size_t(0), C.c_double(0.0)
+    _check(lib.frt_encode_ppm16(rgba.ctypes.data, w, h, int(use_scaling), device, out.ctypes.data, n, C.byref(got), C.byref(ms)),
+           "frt_encode_ppm16")
+    data = out[: got.value].tobytes()
+    return (data, ms.value) if return_ms else data
 
 
 # ---------------------------------------------------------------------------------------------- scenes
@@ -419,6 +441,19 @@ class Scene:
         st = self.photons_emit(0, 1, populate_caustic, populate_global, seed)
         self.photons_finish()
         return st
+
+    def encode_ppm16(self, use_scaling: bool = True, return_ms: bool = False):
+        """The file contents write_ppm_file would produce for the last frame (reference canvas.c:150-328), encoded on the
+        device from the device-resident canvas (frt_canvas_encode_ppm16)."""
+        lib = load_library()
+        cam = self.desc.camera
+        n = lib.frt_ppm16_size(cam.hsize, cam.vsize)
+        out = np.empty(n, dtype=np.uint8)
+        got, ms = C.c_size_t(0), C.c_double(0.0)
+        _check(lib.frt_canvas_encode_ppm16(self._h, int(use_scaling), out.ctypes.data, n, C.byref(got), C.byref(ms)),
+               "frt_canvas_encode_ppm16")
+        data = out[: got.value].tobytes()
+        return (data, ms.value) if return_ms else data
 
     def canvas_tensor(self):
         """The device-resident frame as a torch tensor view [vsize, hsize, 4] float64 (no copy)."""

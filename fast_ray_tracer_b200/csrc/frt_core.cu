@@ -1582,6 +1582,7 @@ k_light_final(DScene S, FrameParams F, const LightRec *__restrict__ recs, const 
 }
 
 #include "frt_gi.cuh"
+#include "frt_encode.cuh"
 
 /* ------------------------------------------------------------------------------------------------ FMA peak */
 
@@ -2777,6 +2778,104 @@ frt_canvas_device_ptr(frt_scene *sc, void **device_ptr)
     }
     *device_ptr = sc->canvas;
     return FRT_OK;
+}
+
+/* ---- output encode: write_ppm_file / construct_ppm (canvas.c:150-328) on the device ------------------------------ */
+
+static size_t
+ppm16_header(char *buf, size_t cap, int width, int height)
+{
+    return (size_t)snprintf(buf, cap, "P6\n%zu %zu\n65535\n", (size_t)width, (size_t)height); /* canvas.c:167 */
+}
+
+extern "C" size_t
+frt_ppm16_size(int width, int height)
+{
+    char hdr[32];
+    if (width <= 0 || height <= 0) {
+        return 0;
+    }
+    return ppm16_header(hdr, sizeof(hdr), width, height) + (size_t)width * height * 6 + 1;
+}
+
+/* dev_canvas: width * height * 4 doubles on the current device; out: host buffer of frt_ppm16_size bytes */
+static int
+encode_ppm16(const double *dev_canvas, int width, int height, int use_scaling, cudaStream_t s, unsigned char *out, size_t out_cap,
+             size_t *out_len, double *encode_ms)
+{
+    const size_t need = frt_ppm16_size(width, height);
+    if (out == nullptr || out_cap < need || need == 0) {
+        return frt_set_error(FRT_ERR_ARG, "PPM buffer of %zu bytes, %zu needed", out_cap, need);
+    }
+    const size_t n = (size_t)width * height;
+    double *maxes = nullptr;
+    unsigned char *data = nullptr;
+    CK(cudaMalloc(&maxes, 6 * sizeof(double)));
+    if (cudaMalloc(&data, n * 6) != cudaSuccess) {
+        cudaFree(maxes);
+        return frt_set_error(FRT_ERR_CUDA, "cudaMalloc of the PPM samples failed");
+    }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    CK(cudaEventRecord(e0, s));
+    CK(cudaMemsetAsync(maxes, 0, 6 * sizeof(double), s));
+    k_ppm_rgb_max<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes);
+    k_ppm_srgb_max<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes);
+    k_ppm_encode<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes, use_scaling, data);
+    CK(cudaEventRecord(e1, s));
+    char hdr[32];
+    const size_t hl = ppm16_header(hdr, sizeof(hdr), width, height);
+    memcpy(out, hdr, hl);
+    cudaError_t e = cudaMemcpyAsync(out + hl, data, n * 6, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    out[hl + n * 6] = '\n'; /* canvas.c:298 */
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(maxes);
+    cudaFree(data);
+    if (e != cudaSuccess) {
+        return frt_set_error(FRT_ERR_CUDA, "PPM encode: %s", cudaGetErrorString(e));
+    }
+    if (out_len) *out_len = need;
+    if (encode_ms) *encode_ms = ms;
+    return FRT_OK;
+}
+
+extern "C" int
+frt_canvas_encode_ppm16(frt_scene *sc, int use_scaling, unsigned char *out, size_t out_cap, size_t *out_len, double *encode_ms)
+{
+    if (sc == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_canvas_encode_ppm16: null scene");
+    }
+    CK(cudaSetDevice(sc->device));
+    return encode_ppm16(sc->canvas, sc->C.hsize, sc->C.vsize, use_scaling, sc->stream, out, out_cap, out_len, encode_ms);
+}
+
+extern "C" int
+frt_encode_ppm16(const double *canvas_rgba, int width, int height, int use_scaling, int device, unsigned char *out, size_t out_cap,
+                 size_t *out_len, double *encode_ms)
+{
+    if (canvas_rgba == nullptr || width <= 0 || height <= 0) {
+        return frt_set_error(FRT_ERR_ARG, "frt_encode_ppm16: empty canvas");
+    }
+    CK(cudaSetDevice(device));
+    double *dev = nullptr;
+    const size_t bytes = (size_t)width * height * 4 * sizeof(double);
+    CK(cudaMalloc(&dev, bytes));
+    cudaError_t e = cudaMemcpy(dev, canvas_rgba, bytes, cudaMemcpyHostToDevice);
+    int rc = FRT_OK;
+    if (e != cudaSuccess) {
+        rc = frt_set_error(FRT_ERR_CUDA, "frt_encode_ppm16: %s", cudaGetErrorString(e));
+    } else {
+        rc = encode_ppm16(dev, width, height, use_scaling, 0, out, out_cap, out_len, encode_ms);
+    }
+    cudaFree(dev);
+    return rc;
 }
 
 static int

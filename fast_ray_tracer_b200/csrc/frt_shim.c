@@ -617,6 +617,21 @@ env_long(const char *name, long dflt)
     return (s == NULL || *s == '\0') ? dflt : strtol(s, NULL, 10);
 }
 
+/* the scene and the Canvas of the last frame: its pixels are still on the device when main() asks for the PPM file */
+static frt_scene *g_last_scene;
+static Canvas g_last_image;
+static bool g_last_full_frame;
+
+static void
+drop_last_scene(void)
+{
+    if (g_last_scene != NULL) {
+        frt_scene_destroy(g_last_scene);
+        g_last_scene = NULL;
+        g_last_image = NULL;
+    }
+}
+
 /* scene kept between trace_photons() and render_multi(): photons live on the device */
 static frt_scene *g_scene;
 static World g_scene_world;
@@ -697,11 +712,61 @@ render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
            (unsigned long long)st.rays_shadow, (unsigned long long)st.rays_gather);
     fflush(stdout);
 
-    frt_scene_destroy(scene);
+    /* keep the frame on the device until the next one (or exit): frt_shim_write_ppm_file encodes it there */
+    static bool registered;
+    drop_last_scene();
+    g_last_scene = scene;
+    g_last_image = image;
+    g_last_full_frame = cfg.world <= 1;
+    if (!registered) {
+        atexit(drop_last_scene);
+        registered = true;
+    }
     g_scene = NULL;
     g_scene_world = NULL;
     flat_free(&f);
     return image;
+}
+
+/*
+ * write_ppm_file (src/libs/canvas/canvas.c:305-328) for the Canvas render_multi() just returned: construct_ppm's three
+ * host passes (two pow() per channel and pixel, 0.2 s for 800 x 800 on one thread) become three kernels over the frame
+ * that is still on the device (frt_canvas_encode_ppm16); the host writes the same bytes to <file_path>.ppm.  Returns 0
+ * when it wrote the file, -1 when `c` is not that canvas (the caller then runs the reference's own write_ppm_file).
+ * The generated main() reaches it through a three-line change in canvas.c or `-Wl,--wrap=write_ppm_file`, see
+ * INTEGRATION.md.
+ */
+int
+frt_shim_write_ppm_file(Canvas c, const bool use_scaling, const char *file_path)
+{
+    if (c == NULL || c != g_last_image || g_last_scene == NULL || !g_last_full_frame || file_path == NULL) {
+        return -1;
+    }
+    size_t cap = frt_ppm16_size((int)c->width, (int)c->height), len = 0;
+    unsigned char *buf = (unsigned char *)malloc(cap);
+    double ms = 0.0;
+    if (buf == NULL || frt_canvas_encode_ppm16(g_last_scene, use_scaling ? 1 : 0, buf, cap, &len, &ms) != FRT_OK) {
+        free(buf);
+        die("frt_canvas_encode_ppm16");
+    }
+    size_t n = strlen(file_path);
+    char *full = (char *)malloc(n + 5);
+    if (full == NULL) {
+        die("out of memory");
+    }
+    memcpy(full, file_path, n);
+    memcpy(full + n, ".ppm", 5);
+    FILE *fp = fopen(full, "wb");
+    if (fp == NULL) {
+        fprintf(stderr, "frt_shim: cannot open %s\n", full);
+        exit(3);
+    }
+    fwrite(buf, 1, len, fp);
+    fclose(fp);
+    printf("FRT_B200_PPM_MS %.3f\n", ms);
+    free(full);
+    free(buf);
+    return 0;
 }
 
 Canvas

@@ -264,6 +264,19 @@ void frt_scene_destroy(frt_scene *scene);
 /* frt_scene_destroy parks the scene-independent frame buffers (ray queues) and the large scene buffers (by size) for
  * the next scene on the same device; frt_trim frees them. */
 void frt_trim(int device);
+/*
+ * Output encode: write_ppm_file -> construct_ppm (src/libs/canvas/canvas.c:150-328), the 16-bit P6 file
+ * the generated main() writes after render_multi (yaml_parser/yaml_parser.py:220), produced on the device -- byte for
+ * byte the reference's file contents for the same canvas.  frt_ppm16_size: bytes of the file for a frame size.
+ * frt_canvas_encode_ppm16 encodes the device-resident canvas of the scene's last frt_render (the canvas never crosses
+ * PCIe as doubles); frt_encode_ppm16 takes a host canvas in the Canvas.arr layout (width * height * 4 doubles).
+ * encode_ms (optional): device time of the three kernels.
+ */
+size_t frt_ppm16_size(int width, int height);
+int frt_canvas_encode_ppm16(frt_scene *scene, int use_scaling, unsigned char *out, size_t out_cap, size_t *out_len, double *encode_ms);
+int frt_encode_ppm16(const double *canvas_rgba, int width, int height, int use_scaling, int device, unsigned char *out, size_t out_cap,
+                     size_t *out_len, double *encode_ms);
+
 /* Page-lock / release a caller-owned host buffer a scene description points at (typically light_points, the 157 MB
  * sample-set cache the reference builds in light.c:100-191): frt_scene_create then uploads it at PCIe speed and
  * ASYNCHRONOUSLY -- the first frame waits for it only where its light stage begins, so the copy hides behind ray

@@ -95,6 +95,38 @@ def make(name: str):
     print(name, meta)
 
 
+# PPM encoder fixtures: a float64 canvas the reference rendered and the bytes its own
+# write_ppm_file (canvas.c:150-328) produced from that very canvas in the same run.
+PPM_GOLDEN = {
+    "ppm_cornell_exact_64": ("cornell_exact", 64, 64, 1, 1),           # dark frame: every channel maximum below 1
+    "ppm_reflect_refract_100": ("reflect_refract", 100, 50, 0, 0),     # bright frame: the sum > sqrt(3) rescale is taken
+    "ppm_checkered_sphere_64": ("checkered_sphere", 64, 64, 0, 0),
+}
+
+
+def make_ppm(name: str):
+    scene, hs, vs, us, vsteps = PPM_GOLDEN[name]
+    env = {"FRT_REF_HSIZE": str(hs), "FRT_REF_VSIZE": str(vs), "FRT_SKIP_PPM": "0"}
+    if us:
+        env.update(FRT_REF_USTEPS=str(us), FRT_REF_VSTEPS=str(vsteps))
+    # output.file of the scene (the reference appends .ppm); yaml_parser/config.py:66-67 defaults it to /tmp/ray_tracer_out
+    outs = [Path("/tmp/out_file.ppm"), Path("/tmp/ray_tracer_out.ppm")]
+    for o in outs:
+        if o.exists():
+            o.unlink()
+    with tempfile.TemporaryDirectory() as td:
+        dump = Path(td) / "canvas.bin"
+        build_ref.run_reference(scene, dump, env)
+        raw = np.fromfile(dump, dtype=np.float64, offset=16)
+        w, h = (int(x) for x in np.fromfile(dump, dtype=np.int64, count=2))
+    rgb = raw.reshape(h, w, 3)
+    out = next(o for o in outs if o.exists())
+    ppm = np.frombuffer(out.read_bytes(), dtype=np.uint8)
+    np.savez_compressed(GOLD / f"{name}.npz", rgb64=rgb, ppm=ppm, meta=json.dumps({"scene": scene, "hsize": w, "vsize": h, "use_scaling": True}))
+    print(name, rgb.shape, len(ppm), "bytes, max rgb", rgb.reshape(-1, 3).max(axis=0))
+
+
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or list(GOLDEN)):
-        make(n)
+    args = sys.argv[1:] or list(GOLDEN) + list(PPM_GOLDEN)
+    for n in args:
+        make_ppm(n) if n in PPM_GOLDEN else make(n)

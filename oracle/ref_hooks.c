@@ -18,6 +18,7 @@
  *   FRT_CANVAS_OUT=path    dump Canvas->arr as raw doubles instead of the PPM
  *                          (int64 width, int64 height, then w*h*3 float64 RGB)
  *   FRT_SKIP_PPM=1         do not run the reference's own write_ppm_file
+ *   FRT_DEVICE_PPM=0       B200 drop-in build: run the reference's host write_ppm_file instead of the device encoder
  *   FRT_REF_SEED=n         srand48(n) / srand(n) before trace_photons() (the reference has no seed control of its own;
  *                          two seeds give two independent reference renders of a photon-mapped scene)
  * Output lines (stdout): "FRT_RENDER_SECONDS <s>", "FRT_RAYS <n>", "FRT_THREADS <n>".
@@ -39,6 +40,8 @@
 Canvas __real_render_multi(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter);
 Intersections __real_intersect_world(const World w, const Ray r, bool stop_after_first_hit);
 int __real_write_ppm_file(Canvas c, const bool use_scaling, const char *file_name);
+/* present in the B200 drop-in build only (fast_ray_tracer_b200/csrc/frt_shim.c): the PPM encoded on the device */
+int frt_shim_write_ppm_file(Canvas c, const bool use_scaling, const char *file_name) __attribute__((weak));
 void __real_trace_photons(const World w, const size_t num_maps, bool populate_caustic, bool populate_global);
 
 /* intersect_world() calls, counted per thread in cache-line-padded slots so that counting does not serialise the
@@ -177,7 +180,17 @@ __wrap_write_ppm_file(Canvas c, const bool use_scaling, const char *file_name)
     if (env_long("FRT_SKIP_PPM", 0)) {
         return 0;
     }
-    return __real_write_ppm_file(c, use_scaling, file_name);
+    double t0 = now_seconds();
+    int rc = -1;
+    if (frt_shim_write_ppm_file != NULL && env_long("FRT_DEVICE_PPM", 1)) {
+        rc = frt_shim_write_ppm_file(c, use_scaling, file_name);
+    }
+    if (rc != 0) {
+        rc = __real_write_ppm_file(c, use_scaling, file_name);
+    }
+    printf("FRT_PPM_SECONDS %.6f\n", now_seconds() - t0); /* encode + file write, either arm */
+    fflush(stdout);
+    return rc;
 }
 
 int

@@ -64,3 +64,23 @@ def test_generated_program_with_photon_maps():
 
     assert "FRT_B200_PHOTONS" in out
     assert rmse(canvas, a) <= 1.25 * rmse(a, b), (rmse(canvas, a), rmse(a, b))
+
+
+def test_generated_program_writes_its_ppm_from_the_device():
+    """SURVEY 8f, output encode: main() calls write_ppm_file(c, true, path) after render_multi (yaml_parser.py:220); in
+    the drop-in build the file is encoded on the device from the frame that is still there (frt_shim_write_ppm_file ->
+    frt_canvas_encode_ppm16).  Its bytes must be what the reference's construct_ppm makes of the same canvas
+    (oracle/ppm16.py, pinned to files the reference wrote)."""
+    from ppm16 import construct_ppm
+
+    out_file = Path("/tmp/out_file.ppm")  # output.file of cornell_box.yml + ".ppm"
+    if out_file.exists():
+        out_file.unlink()
+    env = {"FRT_REF_HSIZE": "96", "FRT_REF_VSIZE": "96", "FRT_REF_USTEPS": "1", "FRT_REF_VSTEPS": "1", "FRT_SKIP_PPM": "0"}
+    canvas, out = run_dropin("cornell_exact", env)
+    assert "FRT_B200_PPM_MS" in out, out[-1500:]
+    assert out_file.read_bytes() == construct_ppm(canvas, True)
+    # and the host path of the same program (the reference's own write_ppm_file) writes the same file
+    canvas2, out2 = run_dropin("cornell_exact", dict(env, FRT_DEVICE_PPM="0"))
+    assert "FRT_B200_PPM_MS" not in out2
+    assert out_file.read_bytes() == construct_ppm(canvas2, True)
