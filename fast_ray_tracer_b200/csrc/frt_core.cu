@@ -768,7 +768,8 @@ quadrant_sample(int4 lq, int q, int k)
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
-              int light_idx, unsigned int *__restrict__ pending, unsigned int *__restrict__ retry, int bulk_on, int split_on)
+              int light_idx, unsigned int *__restrict__ pending, unsigned char *__restrict__ pstart, unsigned int *__restrict__ retry,
+              int bulk_on, int split_on)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
     const int4 lq = split_on ? __ldg(SF.lquad + light_idx) : make_int4(S.lights[light_idx].num_samples, 0, 0, 0);
@@ -778,13 +779,13 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
         const unsigned int h = base + (threadIdx.x & 31);
         /* 0 = nothing to do, 1 = undecided, 2 / 3 = decided shadowed / lit */
-        int state = 0;
+        int state = 0, resume = root;
         if (h < n && tmp[h].set_a >= 0) {
             state = 1;
             if (bulk_on) {
                 ShaftD sh;
                 shaft_d_setup(sh, SF.lbox + 30 * light_idx, recs[h].over, SF.bmax, SF.smin, SF.ealign);
-                const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh);
+                const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh, &resume);
                 if (res != FRT_SH_UNDECIDED) {
                     state = res == FRT_SH_LIT ? 3 : 2;
                     n_bulk += (unsigned int)(nq * lq.x);
@@ -804,6 +805,7 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             const unsigned int slot = warp_append(&cnt->n_pending, keep);
             if (keep) {
                 pending[slot] = h | ((unsigned int)q << 28) | (state >= 2 ? FRT_PEND_BULK : 0u) | (state == 3 ? FRT_PEND_LIT : 0u);
+                pstart[slot] = (unsigned char)(state == 1 ? resume : root);
             }
         }
     }
@@ -819,7 +821,7 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int light_idx,
-              unsigned int *__restrict__ pending, const unsigned int *__restrict__ retry)
+              unsigned int *__restrict__ pending, unsigned char *__restrict__ pstart, const unsigned int *__restrict__ retry)
 {
     const unsigned int n = min(cnt->n_deferred, F.capacity);
     const int4 lq = __ldg(SF.lquad + light_idx);
@@ -828,14 +830,14 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
     const unsigned int total = 4u * n; /* n <= 2^28 */
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += gridDim.x * blockDim.x) {
         const unsigned int item = base + (threadIdx.x & 31);
-        int state = 0;
+        int state = 0, resume = root;
         unsigned int h = 0;
         const int q = (int)(item & 3u);
         if (item < total) {
             h = __ldg(retry + (item >> 2));
             ShaftD sh;
             shaft_d_setup(sh, SF.lbox + 30 * light_idx + 6 * (q + 1), recs[h].over, SF.bmax, SF.smin, SF.ealign);
-            const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh);
+            const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh, &resume);
             state = res == FRT_SH_UNDECIDED ? 1 : (res == FRT_SH_LIT ? 3 : 2);
             if (state >= 2) {
                 n_bulk += (unsigned int)lq.x;
@@ -848,6 +850,7 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         const unsigned int slot = warp_append(&cnt->n_pending, keep);
         if (keep) {
             pending[slot] = h | ((unsigned int)q << 28) | (state >= 2 ? FRT_PEND_BULK : 0u) | (state == 3 ? FRT_PEND_LIT : 0u);
+            pstart[slot] = (unsigned char)(state == 1 ? resume : root);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -988,7 +991,7 @@ normalise_shadow_ray(Ray &sr, double dist2)
 template <int MODE>
 __global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
 k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
-             const unsigned int *__restrict__ pending, unsigned int pend_cap, int split_on, int light_idx,
+             const unsigned int *__restrict__ pending, const unsigned char *__restrict__ pstart, unsigned int pend_cap, int split_on, int light_idx,
              unsigned long long *__restrict__ queue, unsigned int qcap, int nodes_in_smem)
 {
     constexpr bool COUNT = MODE != 0;
@@ -1020,9 +1023,11 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
         int s = 0;
         float4 head = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         unsigned int entry = 0;
+        int start = root;
         if (item < total) {
             const unsigned int idx = NSQ > 1 ? (unsigned int)__umul64hi(item, ns_magic) : (unsigned int)item; /* item / NSQ, exact while item * NSQ < 2^64 */
             entry = __ldg(pending + idx);
+            start = (int)__ldg(pstart + idx);
             s = quadrant_sample(lq, (entry >> 28) & 3, (int)(item - (unsigned long long)idx * (unsigned int)NSQ));
             h = entry & FRT_PEND_HIT_MASK;
             head = *reinterpret_cast<const float4 *>(tmp + h);
@@ -1058,7 +1063,7 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                 const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G + SF.ealign);
                 frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
                 const float Df = len2 * rinv;
-                res = trace_shadow_f32<COUNT>(SF, fnodes, root, relevant, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
+                res = trace_shadow_f32<COUNT>(SF, fnodes, root, start, relevant, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
                 if (COUNT && (res >> 4)) {
                     atomicAdd(&cnt->undecided_reason[min((res >> 4) & 15, 9)], 1ull);
                     atomicAdd(&cnt->undecided_node[(res >> 8) & 31], 1ull);
@@ -2700,7 +2705,8 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     FA(sc->ltmp);
 #undef FA
     {
-        int rc_ = frame_alloc(sc, &sc->pending, (size_t)capacity * 4); /* one entry per (hit, quadrant of the light's sample grid) */
+        /* one entry per (hit, quadrant of the light's sample grid), then one byte per entry: the node its rays start at */
+        int rc_ = frame_alloc(sc, &sc->pending, (size_t)capacity * 5);
         if (rc_ != FRT_OK) {
             return rc_;
         }
@@ -3137,15 +3143,16 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         const int split_on = bulk_on && !(F.flags & FRT_FLAG_NO_SPLIT);
                         const unsigned int pend_cap = sc->capacity * 4u;
                         unsigned int *retry = reinterpret_cast<unsigned int *>(sc->dq); /* free until k_shadow_f32 defers rays */
+                        unsigned char *pstart = reinterpret_cast<unsigned char *>(sc->pending + (size_t)sc->capacity * 4);
 #define FRT_SHADOW_STAGE(M)                                                                                                                       \
     do {                                                                                                                                          \
-        k_shadow_bulk<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, retry, bulk_on, split_on);  \
+        k_shadow_bulk<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pstart, retry, bulk_on, split_on);  \
         if (split_on) {                                                                                                                           \
-            k_shadow_quad<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, retry);                        \
+            k_shadow_quad<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, pstart, retry);                        \
             CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));                                                                \
             launches += 1;                                                                                                                        \
         }                                                                                                                                         \
-        k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pend_cap, split_on, li, sc->dq, \
+        k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, pend_cap, split_on, li, sc->dq, \
                                                        sc->dq_cap, f32_smem != 0);                                                                \
     } while (0)
                         if (F.flags & FRT_FLAG_VERIFY_F32) {

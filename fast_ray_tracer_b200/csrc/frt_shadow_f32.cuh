@@ -517,12 +517,12 @@ node_span(const DSceneF &SF, const float4 q0, const float4 lo, const float4 hi, 
  */
 template <bool COUNT>
 __device__ __forceinline__ int
-trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, unsigned int relevant, const FrameF &w, float omax, float eo_w,
+trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, int start, unsigned int relevant, const FrameF &w, float omax, float eo_w,
                  float ed_w, float D_lo, float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
 {
     unsigned int visited = 0, cost = 0;
-    int i = root;
-    const int end = __float_as_int(fnodes[3 * i].y);
+    int i = start; /* the root, or the node at which the shaft walk of this hit / quadrant got stuck (trace_shadow_bulk) */
+    const int end = __float_as_int(fnodes[3 * root].y);
     int cur_xf = 0;
     FrameF lf = w; /* the ray in the frame of transform cur_xf, once cur_xf != 0 */
     int verdict = FRT_SH_LIT;
@@ -749,13 +749,16 @@ shaft_leaf_span(const ShaftD &sh, const float4 q0, const float4 lo, const float4
 /* FRT_SH_LIT / FRT_SH_SHADOWED: the verdict of every shadow ray of the hit; FRT_SH_UNDECIDED: trace them one by one.
  * Trees of more than 32 nodes are not tried (`relevant` covers nodes 0..31). */
 __device__ __forceinline__ int
-trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const ShaftD &sh)
+trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const ShaftD &sh, int *resume)
 {
+    /* *resume: when the answer is FRT_SH_UNDECIDED, the top-level node at which the walk got stuck.  Every node before it
+     * was passed with a decided "does not end the search" for every ray of the shaft, so the per-ray walk may start there. */
     const float4 *fnodes = SF.fnodes;
     int i = root;
     const int end = __float_as_int(__ldg(fnodes + 3 * i).y);
     const double D_lo = 1.0 - 1e-9, D_hi = 1.0 + 1e-9;
     while (i < end) {
+        const int cur = i;
         const float4 q0 = __ldg(fnodes + 3 * i);
         const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
         if (!((relevant >> i) & 1u)) {
@@ -779,7 +782,10 @@ trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const Shaf
                 continue;
             }
             if (!(flags & FRT_FN_FAST)) {
+                {
+                *resume = cur;
                 return FRT_SH_UNDECIDED;
+            }
             }
             int pc = __float_as_int(lo.w);
             const int pc1 = pc + __float_as_int(hi.w);
@@ -793,7 +799,10 @@ trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const Shaf
                 /* an operand outside the shaft has no crossing at t > 0: for the crossings at t > 0 it is absent */
                 if (((relevant >> code) & 1u) &&
                     !shaft_leaf_span(sh, __ldg(fnodes + 3 * code), __ldg(fnodes + 3 * code + 1), __ldg(fnodes + 3 * code + 2), t)) {
-                    return FRT_SH_UNDECIDED;
+                    {
+                *resume = cur;
+                return FRT_SH_UNDECIDED;
+            }
                 }
                 if (first) {
                     s = t;
@@ -803,7 +812,10 @@ trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const Shaf
                     SpanD r;
                     r.a_lo = r.a_hi = r.b_lo = r.b_hi = 0.0;
                     if (!csg_combine(op, s, t, r)) {
-                        return FRT_SH_UNDECIDED;
+                        {
+                *resume = cur;
+                return FRT_SH_UNDECIDED;
+            }
                     }
                     s = r;
                     pc += 2;
@@ -812,14 +824,20 @@ trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const Shaf
             i = skip;
         } else {
             if (!shaft_leaf_span(sh, q0, lo, hi, s)) {
+                {
+                *resume = cur;
                 return FRT_SH_UNDECIDED;
+            }
             }
             i = i + 1;
         }
         if (s.flags) {
             const int v = judge_span(s, D_lo, D_hi);
             if (v == 3) {
+                {
+                *resume = cur;
                 return FRT_SH_UNDECIDED;
+            }
             }
             if (v != 0) {
                 return v == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
