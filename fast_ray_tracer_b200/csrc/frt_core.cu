@@ -991,7 +991,8 @@ normalise_shadow_ray(Ray &sr, double dist2)
 template <int MODE>
 __global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
 k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
-             const unsigned int *__restrict__ pending, const unsigned char *__restrict__ pstart, unsigned int pend_cap, int split_on, int light_idx,
+             const unsigned int *__restrict__ pending, const unsigned char *__restrict__ pstart, int use_start, unsigned int pend_cap,
+             int split_on, int light_idx,
              unsigned long long *__restrict__ queue, unsigned int qcap, int nodes_in_smem)
 {
     constexpr bool COUNT = MODE != 0;
@@ -1063,7 +1064,8 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                 const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G + SF.ealign);
                 frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
                 const float Df = len2 * rinv;
-                res = trace_shadow_f32<COUNT>(SF, fnodes, root, start, relevant, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
+                res = trace_shadow_f32<COUNT>(SF, fnodes, root, use_start ? (start & FRT_RESUME_NODE_MASK) : root,
+                                            use_start ? (start >> FRT_RESUME_TAIL_SHIFT) : 0, relevant, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
                 if (COUNT && (res >> 4)) {
                     atomicAdd(&cnt->undecided_reason[min((res >> 4) & 15, 9)], 1ull);
                     atomicAdd(&cnt->undecided_node[(res >> 8) & 31], 1ull);
@@ -3152,7 +3154,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));                                                                \
             launches += 1;                                                                                                                        \
         }                                                                                                                                         \
-        k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, pend_cap, split_on, li, sc->dq, \
+        k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, bulk_on, pend_cap, split_on, li, sc->dq, \
                                                        sc->dq_cap, f32_smem != 0);                                                                \
     } while (0)
                         if (F.flags & FRT_FLAG_VERIFY_F32) {

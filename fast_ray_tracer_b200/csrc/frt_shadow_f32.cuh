@@ -517,11 +517,14 @@ node_span(const DSceneF &SF, const float4 q0, const float4 lo, const float4 hi, 
  */
 template <bool COUNT>
 __device__ __forceinline__ int
-trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, int start, unsigned int relevant, const FrameF &w, float omax, float eo_w,
+trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, int start, int tail, unsigned int relevant, const FrameF &w, float omax,
+                 float eo_w,
                  float ed_w, float D_lo, float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
 {
     unsigned int visited = 0, cost = 0;
-    int i = start; /* the root, or the node at which the shaft walk of this hit / quadrant got stuck (trace_shadow_bulk) */
+    /* start: the root, or the node X at which the shaft walk of this hit / quadrant got stuck; tail: what that walk found
+     * for the rays X does not stop (trace_shadow_bulk): 0 nothing, 1 lit, 2 shadowed */
+    int i = start;
     const int end = __float_as_int(fnodes[3 * root].y);
     int cur_xf = 0;
     FrameF lf = w; /* the ray in the frame of transform cur_xf, once cur_xf != 0 */
@@ -536,6 +539,7 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, int start, u
         const float4 q0 = fnodes[3 * i], lo = fnodes[3 * i + 1], hi = fnodes[3 * i + 2];
         const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
         const int type = flags & FRT_FN_TYPE_MASK;
+        const bool at_start = i == start;
         if (COUNT) {
             ++visited;
             cost += (type >= FRT_CSG) ? FRT_COST_BBOX : prim_cost(type);
@@ -557,6 +561,10 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, int start, u
                 }
                 /* surely missed, or surely wholly behind the origin (only t <= 0 crossings inside) */
                 if (tn_lo > tf_hi || tf_hi < 0.0f) {
+                    if (tail && i == start) {
+                        verdict = tail == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
+                        break;
+                    }
                     i = skip;
                     continue;
                 }
@@ -615,6 +623,10 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, int start, u
                 verdict = (v == 2) ? FRT_SH_SHADOWED : FRT_SH_LIT;
                 break;
             }
+        }
+        if (tail && at_start) { /* X did not stop this ray: the shaft walk knows the rest */
+            verdict = tail == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
+            break;
         }
     }
     if (COUNT) {
@@ -746,105 +758,127 @@ shaft_leaf_span(const ShaftD &sh, const float4 q0, const float4 lo, const float4
     return true;
 }
 
-/* FRT_SH_LIT / FRT_SH_SHADOWED: the verdict of every shadow ray of the hit; FRT_SH_UNDECIDED: trace them one by one.
- * Trees of more than 32 nodes are not tried (`relevant` covers nodes 0..31). */
+/*
+ * One node of the shaft walk.  Returns 0 = no ray of the shaft ends its search here (go on at *next), 1 / 2 = every ray
+ * ends it here, lit / shadowed, 3 = cannot tell (a leaf or a CSG node; *next is the node after it).
+ */
+__device__ __forceinline__ int
+shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const ShaftD &sh, int i, int *next)
+{
+    const double D_lo = 1.0 - 1e-9, D_hi = 1.0 + 1e-9;
+    const float4 q0 = __ldg(fnodes + 3 * i);
+    const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
+    if (!((relevant >> i) & 1u)) {
+        *next = skip;
+        return 0;
+    }
+    const float4 lo = __ldg(fnodes + 3 * i + 1), hi = __ldg(fnodes + 3 * i + 2);
+    const int type = flags & FRT_FN_TYPE_MASK;
+    SpanD s;
+    if (type >= FRT_CSG) {
+        *next = skip;
+        if (!(flags & FRT_FN_NOCULL) && (flags & FRT_FN_WORLD) && __float_as_int(q0.z) == 0) {
+            double tn_lo, tn_hi, tf_lo, tf_hi;
+            shaft_box_d(sh, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+            if (tn_lo > tf_hi || tf_hi < 0.0) {
+                return 0;
+            }
+        }
+        if (type == FRT_GROUP) {
+            *next = i + 1;
+            return 0;
+        }
+        if (!(flags & FRT_FN_FAST)) {
+            return 3;
+        }
+        int pc = __float_as_int(lo.w);
+        const int pc1 = pc + __float_as_int(hi.w);
+        s.flags = 0;
+        s.a_lo = s.a_hi = s.b_lo = s.b_hi = 0.0;
+        for (bool first = true; pc < pc1; first = false) {
+            const int code = __ldg(SF.csg_prog + pc);
+            SpanD t;
+            t.flags = 0;
+            t.a_lo = t.a_hi = t.b_lo = t.b_hi = 0.0;
+            /* an operand outside the shaft has no crossing at t > 0: for the crossings at t > 0 it is absent */
+            if (((relevant >> code) & 1u) &&
+                !shaft_leaf_span(sh, __ldg(fnodes + 3 * code), __ldg(fnodes + 3 * code + 1), __ldg(fnodes + 3 * code + 2), t)) {
+                return 3;
+            }
+            if (first) {
+                s = t;
+                pc += 1;
+            } else {
+                const int op = -__ldg(SF.csg_prog + pc + 1) - 1;
+                SpanD r;
+                r.a_lo = r.a_hi = r.b_lo = r.b_hi = 0.0;
+                if (!csg_combine(op, s, t, r)) {
+                    return 3;
+                }
+                s = r;
+                pc += 2;
+            }
+        }
+    } else {
+        *next = i + 1;
+        if (!shaft_leaf_span(sh, q0, lo, hi, s)) {
+            return 3;
+        }
+    }
+    if (s.flags) {
+        const int v = judge_span(s, D_lo, D_hi);
+        if (v == 3) {
+            return 3;
+        }
+        if (v != 0) {
+            return v == 2 ? 2 : 1;
+        }
+    }
+    return 0;
+}
+
+/*
+ * FRT_SH_LIT / FRT_SH_SHADOWED: the verdict of every shadow ray of the hit; FRT_SH_UNDECIDED: trace them one by one.
+ * Trees of more than 32 nodes are not tried (`relevant` covers nodes 0..31).
+ *
+ * When the walk gets stuck at a node X it does not give up: *resume = X, and it walks on AS IF X ended no search.  If
+ * the rest is decided for the whole shaft -- a later node ends every search with one verdict, or the tree ends (lit) --
+ * that verdict is the answer of every ray X does not stop, and it goes into bits 5..6 of *resume (1 lit, 2 shadowed,
+ * 0 = stuck a second time).  The per-ray walk then starts at X (every node before it was passed with a decided "ends no
+ * search" for every ray) and, with a tail verdict, ends right after it: a ray of a Cornell penumbra hit evaluates the
+ * window wall's CSG program and nothing else.
+ */
+#define FRT_RESUME_NODE_MASK 31
+#define FRT_RESUME_TAIL_SHIFT 5
 __device__ __forceinline__ int
 trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const ShaftD &sh, int *resume)
 {
-    /* *resume: when the answer is FRT_SH_UNDECIDED, the top-level node at which the walk got stuck.  Every node before it
-     * was passed with a decided "does not end the search" for every ray of the shaft, so the per-ray walk may start there. */
     const float4 *fnodes = SF.fnodes;
-    int i = root;
+    int i = root, stuck = -1;
     const int end = __float_as_int(__ldg(fnodes + 3 * i).y);
-    const double D_lo = 1.0 - 1e-9, D_hi = 1.0 + 1e-9;
     while (i < end) {
-        const int cur = i;
-        const float4 q0 = __ldg(fnodes + 3 * i);
-        const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
-        if (!((relevant >> i) & 1u)) {
-            i = skip;
-            continue;
+        int next = i + 1;
+        const int code = shaft_node(SF, fnodes, relevant, sh, i, &next);
+        if (code == 3) {
+            if (stuck >= 0) {
+                *resume = stuck;
+                return FRT_SH_UNDECIDED;
+            }
+            stuck = i;
+        } else if (code != 0) {
+            if (stuck < 0) {
+                return code == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
+            }
+            *resume = stuck | (code << FRT_RESUME_TAIL_SHIFT);
+            return FRT_SH_UNDECIDED;
         }
-        const float4 lo = __ldg(fnodes + 3 * i + 1), hi = __ldg(fnodes + 3 * i + 2);
-        const int type = flags & FRT_FN_TYPE_MASK;
-        SpanD s;
-        if (type >= FRT_CSG) {
-            if (!(flags & FRT_FN_NOCULL) && (flags & FRT_FN_WORLD) && __float_as_int(q0.z) == 0) {
-                double tn_lo, tn_hi, tf_lo, tf_hi;
-                shaft_box_d(sh, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-                if (tn_lo > tf_hi || tf_hi < 0.0) {
-                    i = skip;
-                    continue;
-                }
-            }
-            if (type == FRT_GROUP) {
-                i = i + 1;
-                continue;
-            }
-            if (!(flags & FRT_FN_FAST)) {
-                {
-                *resume = cur;
-                return FRT_SH_UNDECIDED;
-            }
-            }
-            int pc = __float_as_int(lo.w);
-            const int pc1 = pc + __float_as_int(hi.w);
-            s.flags = 0;
-            s.a_lo = s.a_hi = s.b_lo = s.b_hi = 0.0;
-            for (bool first = true; pc < pc1; first = false) {
-                const int code = __ldg(SF.csg_prog + pc);
-                SpanD t;
-                t.flags = 0;
-                t.a_lo = t.a_hi = t.b_lo = t.b_hi = 0.0;
-                /* an operand outside the shaft has no crossing at t > 0: for the crossings at t > 0 it is absent */
-                if (((relevant >> code) & 1u) &&
-                    !shaft_leaf_span(sh, __ldg(fnodes + 3 * code), __ldg(fnodes + 3 * code + 1), __ldg(fnodes + 3 * code + 2), t)) {
-                    {
-                *resume = cur;
-                return FRT_SH_UNDECIDED;
-            }
-                }
-                if (first) {
-                    s = t;
-                    pc += 1;
-                } else {
-                    const int op = -__ldg(SF.csg_prog + pc + 1) - 1;
-                    SpanD r;
-                    r.a_lo = r.a_hi = r.b_lo = r.b_hi = 0.0;
-                    if (!csg_combine(op, s, t, r)) {
-                        {
-                *resume = cur;
-                return FRT_SH_UNDECIDED;
-            }
-                    }
-                    s = r;
-                    pc += 2;
-                }
-            }
-            i = skip;
-        } else {
-            if (!shaft_leaf_span(sh, q0, lo, hi, s)) {
-                {
-                *resume = cur;
-                return FRT_SH_UNDECIDED;
-            }
-            }
-            i = i + 1;
-        }
-        if (s.flags) {
-            const int v = judge_span(s, D_lo, D_hi);
-            if (v == 3) {
-                {
-                *resume = cur;
-                return FRT_SH_UNDECIDED;
-            }
-            }
-            if (v != 0) {
-                return v == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
-            }
-        }
+        i = next;
     }
-    return FRT_SH_LIT;
+    if (stuck < 0) {
+        return FRT_SH_LIT;
+    }
+    *resume = stuck | (1 << FRT_RESUME_TAIL_SHIFT);
+    return FRT_SH_UNDECIDED;
 }
 
 /*
