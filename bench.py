@@ -186,7 +186,7 @@ def reference_arm(args) -> dict:
 # ---------------------------------------------------------------------------------------------- CUDA arm
 
 
-TRAFFIC_FILE = REPO / "profiles" / "r1m_traffic_k_shadow_f32.json"
+TRAFFIC_FILE = REPO / "profiles" / "r1n_traffic_k_shadow_f32.json"
 
 
 def traffic_per_launch(args):
