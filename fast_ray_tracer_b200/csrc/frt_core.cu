@@ -780,12 +780,18 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         const unsigned int h = base + (threadIdx.x & 31);
         /* 0 = nothing to do, 1 = undecided, 2 / 3 = decided shadowed / lit */
         int state = 0, resume = root;
-        if (h < n && tmp[h].set_a >= 0) {
+        LightTmp t;
+        t.set_a = -1;
+        if (h < n) {
+            t = tmp[h];
+        }
+        if (t.set_a >= 0) {
             state = 1;
             if (bulk_on) {
                 ShaftD sh;
-                shaft_d_setup(sh, SF.lbox + 30 * light_idx, recs[h].over, SF.bmax, SF.smin, SF.ealign);
-                const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh, &resume);
+                const double over[3] = { (double)t.ox, (double)t.oy, (double)t.oz }; /* FP32 over-point: within 2^-24 |o| of the FP64 one */
+                shaft_d_setup(sh, SF.lbox + 30 * light_idx, over, 1.2e-7, SF.bmax, SF.smin, SF.ealign);
+                const int res = trace_shadow_bulk(SF, root, t.relevant, sh, &resume);
                 if (res != FRT_SH_UNDECIDED) {
                     state = res == FRT_SH_LIT ? 3 : 2;
                     n_bulk += (unsigned int)(nq * lq.x);
@@ -836,8 +842,10 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         if (item < total) {
             h = __ldg(retry + (item >> 2));
             ShaftD sh;
-            shaft_d_setup(sh, SF.lbox + 30 * light_idx + 6 * (q + 1), recs[h].over, SF.bmax, SF.smin, SF.ealign);
-            const int res = trace_shadow_bulk(SF, root, tmp[h].relevant, sh, &resume);
+            const LightTmp t = tmp[h];
+            const double over[3] = { (double)t.ox, (double)t.oy, (double)t.oz };
+            shaft_d_setup(sh, SF.lbox + 30 * light_idx + 6 * (q + 1), over, 1.2e-7, SF.bmax, SF.smin, SF.ealign);
+            const int res = trace_shadow_bulk(SF, root, t.relevant, sh, &resume);
             state = res == FRT_SH_UNDECIDED ? 1 : (res == FRT_SH_LIT ? 3 : 2);
             if (state >= 2) {
                 n_bulk += (unsigned int)lq.x;

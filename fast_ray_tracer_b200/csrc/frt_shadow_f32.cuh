@@ -661,8 +661,10 @@ struct ShaftD {
 };
 
 __device__ __forceinline__ void
-shaft_d_setup(ShaftD &s, const double *box, const double *over, float bmax, float smin, float ealign)
+shaft_d_setup(ShaftD &s, const double *box, const double *over, double orel, float bmax, float smin, float ealign)
 {
+    /* over: the rays' common origin, known up to orel * |over| per component (the FP32 copy of the over-point in LightTmp:
+     * 2^-24; reading it instead of the FP64 record saves the per-hit kernels a 152-byte-strided load) */
     /* box: axis-aligned bounds {min xyz, max xyz} of the light points the rays aim at (the whole light, or one quadrant
      * of its sample grid), measured over every cached sample set at upload and inflated there */
     double cmax = 0.0, len2max = 0.0, dlo[3], dhi[3];
@@ -675,7 +677,7 @@ shaft_d_setup(ShaftD &s, const double *box, const double *over, float bmax, floa
         const double m = fmax(fabs(dlo[k]), fabs(dhi[k]));
         len2max += m * m;
     }
-    const double sd = (1e-12 + (double)ealign) * 2.0 * cmax + 1e-300;
+    const double sd = (1e-12 + (double)ealign + orel) * 2.0 * cmax + 1e-300;
     /* the reference divides by the LOCAL normalised component when it is >= EPSILON: local = scale * world */
     const double thr = 2.0 * FRT_EPS * sqrt(len2max) / (double)smin;
     for (int k = 0; k < 3; ++k) {
@@ -694,7 +696,7 @@ shaft_d_setup(ShaftD &s, const double *box, const double *over, float bmax, floa
             s.ib[k] = 1.0 / fmin(dlo[k], -1e-300);
         }
     }
-    s.en = 2.4e-7 * (double)bmax + (1e-12 + (double)ealign) * cmax + 1e-300; /* bounds rounded to FP32: 2^-22 Bmax */
+    s.en = 2.4e-7 * (double)bmax + (1e-12 + (double)ealign + orel) * cmax + 1e-300; /* bounds rounded to FP32: 2^-22 Bmax */
 }
 
 /* quotient range of n in [n_lo, n_hi] over e in [e_lo, e_hi], e_lo > 0, given ia = 1 / e_lo and ib = 1 / e_hi */
