@@ -952,9 +952,12 @@ k_light_boxes_finish(const double *__restrict__ partial, const int4 *__restrict_
 }
 
 /*
- * One thread per (hit, surface sample): item = hit * num_samples + sample, so a warp holds 32 consecutive samples
- * of one hit (or the tail of one and the head of the next) -- rays with a common origin and nearly parallel
- * directions, which walk the tree together.  The unshadowed count of a hit is reduced inside the warp
+ * One thread per (pending entry, sample): k_shadow_bulk / k_shadow_quad leave a list of (hit, quadrant of the light's
+ * sample grid) entries whose rays still have to be traced; item = entry * samples-per-entry + k, so a warp holds
+ * consecutive samples of one hit (or the tail of one entry and the head of the next) -- rays with a common origin and
+ * nearly parallel directions, which walk the tree together.  Each entry also says at which node its rays start and,
+ * when the shaft walk could tell, what becomes of the rays that node does not stop (trace_shadow_bulk).  Deferred
+ * items keep the absolute encoding hit * num_samples + sample.  The unshadowed count of a hit is reduced inside the warp
  * (__match_any_sync on the hit index) and added with one integer atomic per (warp, hit): integer sums are
  * order-independent, so the frame is reproducible.
  *
