@@ -22,6 +22,8 @@ FRT_FLAG_VERIFY_F32 = 16
 FRT_FLAG_NO_SHAFT = 32
 FRT_FLAG_NO_BULK = 64
 FRT_FLAG_NO_SPLIT = 128
+FRT_FLAG_STAGE_TIMES = 256
+STAGES = ["raygen", "extend", "shade", "light_pre", "shadow_shaft", "shadow_ray", "shadow_exact", "light_final", "gi_trace", "knn", "gi_resolve", "other"]
 
 
 class FrtError(RuntimeError):
@@ -115,7 +117,16 @@ class frt_stats(C.Structure):
                 ("light_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("shadow_nodes", C.c_uint64),
                 ("overflow", C.c_uint64), ("photons_stored", C.c_uint64 * 3), ("light_flops", C.c_uint64),
                 ("shadow_deferred", C.c_uint64), ("shadow_mismatch", C.c_uint64), ("shadow_reasons", C.c_uint64 * 10),
-                ("rows_rendered", C.c_int32), ("pad", C.c_int32)]
+                ("rows_rendered", C.c_int32), ("pad", C.c_int32), ("stage_ms", C.c_double * 12),
+                ("shadow_ray_launches", C.c_uint64), ("shadow_rays_traced", C.c_uint64)]
+
+
+FRT_GEN_VERIFY_MAX = 8
+
+
+class frt_light_gen(C.Structure):
+    _fields_ = [("light", C.c_int32), ("n_verify", C.c_int32), ("drand48_state", C.c_uint64),
+                ("verify_set", C.c_int32 * FRT_GEN_VERIFY_MAX), ("verify_points", C.POINTER(C.c_double) * FRT_GEN_VERIFY_MAX)]
 
 
 class frt_photon_cfg(C.Structure):
@@ -131,6 +142,9 @@ EXPORTS = [
     "frt_photons_export", "frt_photons_import", "frt_photons_finish", "frt_measure_fma_peak",
     "frt_scene_save", "frt_scene_load", "frt_scene_desc_free", "frt_trim", "frt_host_register", "frt_host_unregister",
     "frt_ppm16_size", "frt_canvas_encode_ppm16", "frt_encode_ppm16",
+    "frt_scene_create_gen", "frt_drand48_advance", "frt_light_points_checksum", "frt_light_points_checksum_host",
+    "frt_photons_estimate", "frt_multi_create", "frt_multi_destroy", "frt_multi_device_count", "frt_multi_scene",
+    "frt_multi_render", "frt_multi_photons",
 ]
 
 
@@ -150,6 +164,22 @@ def load_library():
     lib.frt_last_error.restype = C.c_char_p
     lib.frt_device_count.restype = C.c_int
     lib.frt_scene_create.argtypes = [C.POINTER(frt_scene_desc), C.c_int, C.POINTER(C.c_void_p)]
+    lib.frt_scene_create_gen.argtypes = [C.POINTER(frt_scene_desc), C.c_int, C.POINTER(frt_light_gen), C.c_int, C.POINTER(C.c_void_p)]
+    lib.frt_drand48_advance.argtypes = [C.c_uint64, C.c_uint64]
+    lib.frt_drand48_advance.restype = C.c_uint64
+    lib.frt_light_points_checksum.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]
+    lib.frt_light_points_checksum_host.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+    lib.frt_light_points_checksum_host.restype = C.c_uint64
+    lib.frt_photons_estimate.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.frt_multi_create.argtypes = [C.POINTER(frt_scene_desc), C.POINTER(C.c_int32), C.c_int, C.POINTER(frt_light_gen), C.c_int,
+                                     C.POINTER(C.c_void_p)]
+    lib.frt_multi_destroy.argtypes = [C.c_void_p]
+    lib.frt_multi_destroy.restype = None
+    lib.frt_multi_device_count.argtypes = [C.c_void_p]
+    lib.frt_multi_scene.argtypes = [C.c_void_p, C.c_int]
+    lib.frt_multi_scene.restype = C.c_void_p
+    lib.frt_multi_render.argtypes = [C.c_void_p, C.POINTER(frt_render_cfg), C.c_void_p, C.POINTER(frt_stats)]
+    lib.frt_multi_photons.argtypes = [C.c_void_p, C.POINTER(frt_photon_cfg), C.POINTER(frt_stats)]
     lib.frt_scene_destroy.argtypes = [C.c_void_p]
     lib.frt_scene_destroy.restype = None
     lib.frt_trim.argtypes = [C.c_int]
@@ -338,6 +368,96 @@ class RenderStats:
         return self.rays_primary + self.rays_secondary + self.rays_shadow + self.rays_gather
 
 
+def _stats_from(st: frt_stats) -> RenderStats:
+    stats = RenderStats(frame_ms=st.frame_ms, light_ms=st.light_ms, download_ms=st.download_ms,
+                        rays_primary=st.rays_primary, rays_secondary=st.rays_secondary, rays_shadow=st.rays_shadow,
+                        rays_gather=st.rays_gather, hits_shaded=st.hits_shaded, kernel_launches=st.kernel_launches,
+                        light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow,
+                        light_flops=st.light_flops, shadow_deferred=st.shadow_deferred, shadow_mismatch=st.shadow_mismatch,
+                        rows_rendered=st.rows_rendered)
+    stats.extra["shadow_reasons"] = [int(x) for x in st.shadow_reasons]
+    stats.extra["stage_ms"] = dict(zip(STAGES, (float(x) for x in st.stage_ms)))
+    stats.extra["shadow_ray_launches"] = int(st.shadow_ray_launches)
+    stats.extra["shadow_rays_traced"] = int(st.shadow_rays_traced)
+    return stats
+
+
+def _light_gens(desc: SceneDesc):
+    """(frt_light_gen array or None, objects to keep alive) from desc.light_gens = [{light, state, verify: [(set, points)]}]."""
+    spec = getattr(desc, "light_gens", None)
+    if not spec:
+        return None, None
+    arr = (frt_light_gen * len(spec))()
+    keep = []
+    for g, item in zip(arr, spec):
+        g.light = int(item["light"])
+        g.drand48_state = int(item["state"])
+        ver = item.get("verify") or []
+        assert len(ver) <= FRT_GEN_VERIFY_MAX
+        g.n_verify = len(ver)
+        for k, (set_index, pts) in enumerate(ver):
+            pts = np.ascontiguousarray(pts, dtype=np.float64)
+            keep.append(pts)
+            g.verify_set[k] = int(set_index)
+            g.verify_points[k] = pts.ctypes.data_as(C.POINTER(C.c_double))
+    return arr, keep
+
+
+class MultiScene:
+    """One scene replicated on several GPUs of this process (frt_multi): device k renders the row blocks b % n == k and
+    writes them straight into the caller's canvas -- the C twin of the reference's row fan-out, no collective."""
+
+    def __init__(self, desc: SceneDesc, devices=None):
+        lib = load_library()
+        self.desc = desc
+        self._h = C.c_void_p()
+        gens, _keep = _light_gens(desc)
+        dev = None
+        n = 0
+        if devices is not None:
+            n = len(devices)
+            dev = (C.c_int32 * n)(*devices)
+        _check(lib.frt_multi_create(desc._ptr, dev, n, gens, 0 if gens is None else len(gens), C.byref(self._h)), "frt_multi_create")
+        self.n_devices = int(lib.frt_multi_device_count(self._h))
+
+    def scene(self, k: int) -> "Scene":
+        return Scene._adopt(self.desc, k, load_library().frt_multi_scene(self._h, k))
+
+    def close(self):
+        if self._h:
+            load_library().frt_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, rows_per_block: int = 4, usteps: int = 0, vsteps: int = 0, jitter: int = -1, seed: int = 0, flags: int = 0,
+               out: Optional[np.ndarray] = None):
+        cam = self.desc.camera
+        cfg = frt_render_cfg(rows_per_block=rows_per_block, usteps=usteps, vsteps=vsteps, jitter=jitter, flags=flags, seed=seed)
+        st = frt_stats()
+        if out is None:
+            out = np.zeros((cam.vsize, cam.hsize, 4), dtype=np.float64)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (cam.vsize, cam.hsize, 4)
+        _check(load_library().frt_multi_render(self._h, C.byref(cfg), out.ctypes.data_as(C.c_void_p), C.byref(st)), "frt_multi_render")
+        return out, _stats_from(st)
+
+    def trace_photons(self, populate_caustic: bool = False, populate_global: bool = True, seed: int = 0):
+        cfg = frt_photon_cfg(populate_caustic=int(populate_caustic), populate_global=int(populate_global), seed=seed)
+        st = frt_stats()
+        _check(load_library().frt_multi_photons(self._h, C.byref(cfg), C.byref(st)), "frt_multi_photons")
+        return RenderStats(extra={"rays_photon": int(st.rays_photon), "photons_stored": [int(x) for x in st.photons_stored]})
+
+
 class Scene:
     """A scene resident in HBM on one GPU (frt_scene)."""
 
@@ -345,12 +465,44 @@ class Scene:
         self.desc = desc
         self.device = device
         self._h = C.c_void_p()
-        _check(load_library().frt_scene_create(desc._ptr, device, C.byref(self._h)), "frt_scene_create")
+        gens, _keep = _light_gens(desc)
+        if gens is None:
+            _check(load_library().frt_scene_create(desc._ptr, device, C.byref(self._h)), "frt_scene_create")
+        else:
+            # area-light sample caches rebuilt on the device (lightcache.generate_area_light_caches)
+            _check(load_library().frt_scene_create_gen(desc._ptr, device, gens, len(gens), C.byref(self._h)), "frt_scene_create_gen")
+
+    @classmethod
+    def _adopt(cls, desc: SceneDesc, device: int, handle) -> "Scene":
+        """A scene owned by someone else (a MultiScene): same methods, close() does nothing."""
+        self = cls.__new__(cls)
+        self.desc, self.device, self._h, self._borrowed = desc, device, C.c_void_p(handle), True
+        return self
+
+    def light_points_checksum(self, first_point: int = 0, n_points: Optional[int] = None) -> int:
+        """Checksum of the FP64 light-point pool as it is on the device (frt_light_points_checksum)."""
+        if n_points is None:
+            n_points = self.desc.c.n_light_points - first_point
+        out = C.c_uint64(0)
+        _check(load_library().frt_light_points_checksum(self._h, first_point, n_points, C.byref(out)), "frt_light_points_checksum")
+        return int(out.value)
+
+    def photons_estimate(self, map_index: int, pos: np.ndarray, normal: np.ndarray):
+        """pm_irradiance_estimate (reference pm.c:91) for every row of pos / normal ([n, 3] float64) against the device
+        photon map: returns (irradiance [n, 3] float64, photons used [n] int32)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        normal = np.ascontiguousarray(normal, dtype=np.float64)
+        n = pos.shape[0]
+        irr = np.zeros((n, 3), dtype=np.float64)
+        found = np.zeros(n, dtype=np.int32)
+        _check(load_library().frt_photons_estimate(self._h, map_index, n, pos.ctypes.data, normal.ctypes.data, irr.ctypes.data,
+                                                   found.ctypes.data), "frt_photons_estimate")
+        return irr, found
 
     def close(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):
             load_library().frt_scene_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __enter__(self):
         return self
@@ -379,15 +531,7 @@ class Scene:
             assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (cam.vsize, cam.hsize, 4)
             ptr = out.ctypes.data_as(C.c_void_p)
         _check(load_library().frt_render(self._h, C.byref(cfg), ptr, C.byref(st)), "frt_render")
-        stats = RenderStats(frame_ms=st.frame_ms, light_ms=st.light_ms, download_ms=st.download_ms,
-                            rays_primary=st.rays_primary, rays_secondary=st.rays_secondary, rays_shadow=st.rays_shadow,
-                            rays_gather=st.rays_gather, hits_shaded=st.hits_shaded, kernel_launches=st.kernel_launches,
-                            light_launches=st.light_launches, shadow_nodes=st.shadow_nodes, overflow=st.overflow, light_flops=st.light_flops, shadow_deferred=st.shadow_deferred,
-                            shadow_mismatch=st.shadow_mismatch,
-                            rows_rendered=st.rows_rendered)
-        stats.rays_gather = st.rays_gather
-        stats.extra["shadow_reasons"] = [int(x) for x in st.shadow_reasons]
-        return (out if download else None), stats
+        return (out if download else None), _stats_from(st)
 
     # ---- photon pass (replaces trace_photons, reference photon_tracer.c:203)
 

@@ -151,6 +151,15 @@ frt_scene_load(const char *path, frt_scene_desc **out)
     d->camera = h->camera;
     d->config = h->config;
 
+    /* counts come from the file: negative or absurd ones must not wrap the offsets below */
+    const long long lim = (long long)size;
+    if (d->n_nodes < 0 || d->n_roots < 0 || d->n_xforms < 0 || d->n_materials < 0 || d->n_patterns < 0 || d->n_textures < 0 ||
+        d->n_lights < 0 || d->n_prim_params < 0 || d->n_texels < 0 || d->n_light_points < 0 || d->n_pixel_samples < 0 ||
+        d->n_nodes > lim || d->n_roots > lim || d->n_xforms > lim || d->n_materials > lim || d->n_patterns > lim || d->n_textures > lim ||
+        d->n_lights > lim || d->n_prim_params > lim || d->n_texels > lim || d->n_light_points > lim || d->n_pixel_samples > lim) {
+        free(block);
+        return frt_set_error(FRT_ERR_IO, "frt_scene_load: %s has a negative or impossible section count", path);
+    }
     struct section s[11];
     sections_of(d, s); /* sizes only; pointers are filled below */
     size_t off = head + pad8(sizeof(frt_blob_header));
@@ -158,6 +167,10 @@ frt_scene_load(const char *path, frt_scene_desc **out)
     s[10].bytes = (size_t)d->n_pixel_samples * sizeof(double);
     for (int i = 0; i < 11; ++i) {
         ptrs[i] = s[i].bytes ? block + off : NULL;
+        if (s[i].bytes > (size_t)size || off > head + (size_t)size) { /* every count is <= size, so no product above wraps */
+            off = (size_t)-1;
+            break;
+        }
         off += pad8(s[i].bytes);
     }
     if (off > head + (size_t)size) {

@@ -24,6 +24,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "frt_b200.h"
@@ -31,6 +33,7 @@
 #include "frt_device.cuh"
 #include "frt_patterns.cuh"
 #include "frt_shadow_f32.cuh"
+#include "frt_lightgen.cuh"
 
 /* ------------------------------------------------------------------------------------------------ errors */
 
@@ -120,6 +123,7 @@ struct Counters {
     unsigned long long deferred_total, f32_mismatch, rays_gather;
     unsigned long long rays_bulk; /* shadow rays decided per hit by k_shadow_bulk */
     unsigned long long mesh_next; /* k_shadow_mesh: next (hit, sample) item to hand out */
+    unsigned long long rays_per_ray; /* rays handed to the per-ray shadow kernel (k_shadow_f32 / k_shadow_mesh / k_shadow_exact<ALL>) */
     unsigned long long undecided_node[32]; /* debug: node at which a leaf verdict was undecided */
     unsigned long long undecided_reason[10]; /* counting build: why the FP32 filter deferred a ray (codes in frt_shadow_f32.cuh) */
 };
@@ -153,6 +157,17 @@ mix64(unsigned long long z)
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
+}
+
+__host__ __device__ __forceinline__ unsigned int
+hash32(unsigned int x)
+{
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
 }
 
 __host__ __device__ __forceinline__ double
@@ -307,7 +322,10 @@ k_raygen(DCamera C, FrameParams F, RayQ q, Counters *cnt, unsigned int first_sam
             pxl[k] = C.inv[4 * k] * wx + C.inv[4 * k + 1] * wy + C.inv[4 * k + 2] * wz + C.inv[4 * k + 3];
         }
         double ax, ay;
-        aperture_sample(C, mix64(F.seed ^ (0x7f4a7c15ULL * (s + 1))), ax, ay);
+        /* every random stream of a path is keyed on the sample's GLOBAL id (pixel, sub-sample), never on its position in
+         * this rank's queue: the frame does not depend on how its rows are partitioned */
+        const unsigned int gid = pixel * (unsigned int)spp + (unsigned int)sub;
+        aperture_sample(C, mix64(F.seed ^ (0x7f4a7c15ULL * ((unsigned long long)gid + 1ull))), ax, ay);
         ax = (ax - 0.5) * C.aperture_size;
         ay = (ay - 0.5) * C.aperture_size;
         for (int k = 0; k < 3; ++k) {
@@ -325,7 +343,7 @@ k_raygen(DCamera C, FrameParams F, RayQ q, Counters *cnt, unsigned int first_sam
         q.wg[i] = w0;
         q.wb[i] = w0;
         q.pixel[i] = (int)pixel;
-        q.rng[i] = s * 2654435761u + 1u;
+        q.rng[i] = hash32(gid);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         cnt->n_rays[0] = n_samples;
@@ -583,7 +601,7 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
                 qn.dx[s1] = rfl.dx; qn.dy[s1] = rfl.dy; qn.dz[s1] = rfl.dz;
                 qn.wr[s1] = w_refl[0]; qn.wg[s1] = w_refl[1]; qn.wb[s1] = w_refl[2];
                 qn.pixel[s1] = pixel;
-                qn.rng[s1] = rng * 2u + 1u;
+                qn.rng[s1] = hash32(rng + 0x9e3779b9u); /* child ids are hashed: no arithmetic relation between paths */
                 ++n_secondary;
             } else {
                 atomicOr(&cnt->overflow_queue, 1u);
@@ -596,7 +614,7 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
                 qn.dx[s2] = rfr.dx; qn.dy[s2] = rfr.dy; qn.dz[s2] = rfr.dz;
                 qn.wr[s2] = w_refr[0]; qn.wg[s2] = w_refr[1]; qn.wb[s2] = w_refr[2];
                 qn.pixel[s2] = pixel;
-                qn.rng[s2] = rng * 2u + 2u;
+                qn.rng[s2] = hash32(rng + 0x3c6ef372u);
                 ++n_secondary;
             } else {
                 atomicOr(&cnt->overflow_queue, 1u);
@@ -1028,6 +1046,9 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
     const int root = __ldg(S.roots);
     int overflow = 0;
     unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0, n_mismatch = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&cnt->rays_per_ray, total);
+    }
 
     for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
         const unsigned long long item = base + (threadIdx.x & 31);
@@ -1212,8 +1233,8 @@ k_shadow_exact(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
         if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
         if (n_flops && ALL) atomicAdd(&cnt->light_flops, n_flops); /* light_flops describes the kernel that is timed */
     }
-    if (!ALL && blockIdx.x == 0 && threadIdx.x == 0) {
-        atomicAdd(&cnt->deferred_total, total);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(ALL ? &cnt->rays_per_ray : &cnt->deferred_total, total);
     }
 }
 
@@ -1253,6 +1274,9 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         cum[k + 1] = cum[k] + (k < n_lights ? (unsigned long long)nh * (unsigned int)S.lights[first_light + k].num_samples : 0ull);
     }
     const unsigned long long total = cum[FRT_MESH_LIGHTS];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&cnt->rays_per_ray, total);
+    }
     LightTmp *tmp = tmp_base;
     const float4 *fnodes = SF.fnodes;
     const int root = __ldg(S.roots);
@@ -1654,7 +1678,10 @@ template <typename T>
 static int
 measure_fma(double *tflops)
 {
-    const int blocks = 148 * 8, threads = 256, iters = 1 << 15;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    const int blocks = sms * 8, threads = 256, iters = 1 << 15;
     T *out = nullptr;
     CK(cudaMalloc(&out, sizeof(T) * blocks * threads));
     cudaEvent_t e0, e1;
@@ -1719,7 +1746,8 @@ struct frt_scene {
     std::vector<size_t> alloc_bytes; /* parallel to allocs */
     std::vector<int> light_gw, light_ns;
     cudaStream_t upload_stream = nullptr; /* the light-sample cache and what is derived from it travel here */
-    cudaEvent_t upload_ev = nullptr;
+    cudaEvent_t upload_ev = nullptr, ready_ev = nullptr;
+    int sm_count = 148;
     bool upload_pending = false;          /* the render stream has not waited for upload_ev yet */
     unsigned int *h_nrays = nullptr; /* pinned: the next level's ray count, read back behind k_shade without stalling the stream */
     cudaEvent_t nrays_ev = nullptr;
@@ -1751,6 +1779,7 @@ struct frt_scene {
         bool scaled = false; /* pm_scale_photon_power already applied to ra / rb */
     } pm[2];
     unsigned int *pm_stored = nullptr; /* device counters, one per map */
+    float4 *pm_merged[2] = { nullptr, nullptr }; /* frt_multi_photons: every device's shard, gathered here before the import */
     bool pm_ready = false;
     GQuery *gq = nullptr;
     unsigned int gq_cap = 0;
@@ -1886,6 +1915,38 @@ scene_release_allocs(frt_scene *sc)
     sc->alloc_bytes.clear();
 }
 
+/* 64-byte page-locked slots, one per live scene (so that two scenes rendered from two threads on one device never share
+ * the word the frame loop polls), recycled because cudaHostAlloc costs more than a small frame */
+static std::vector<unsigned int *> g_pinned_free; /* under g_park_mu */
+
+static unsigned int *
+pinned_slot_take()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        if (!g_pinned_free.empty()) {
+            unsigned int *p = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return p;
+        }
+    }
+    unsigned int *p = nullptr;
+    if (cudaHostAlloc((void **)&p, 64, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+static void
+pinned_slot_give(unsigned int *p)
+{
+    if (p != nullptr) {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        g_pinned_free.push_back(p);
+    }
+}
+
 static std::map<const char *, size_t> g_registered; /* page-locked caller buffers (frt_host_register), under g_park_mu */
 
 static bool
@@ -1950,13 +2011,16 @@ template <typename T>
 static int
 upload(frt_scene *sc, const T *src, size_t count, const T **dst)
 {
+    /* Every copy travels on the scene's upload stream, the stream whose kernels (FP32 conversion, light bounds) read the
+     * data; the render stream waits for an event recorded behind them (frt_scene_create).  A copy from pageable memory
+     * returns once the source has been staged, so the caller's buffer may go away afterwards. */
     T *d = nullptr;
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     CK(scene_alloc(sc, (void **)&d, bytes));
     if (count) {
-        CK(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, sc->upload_stream));
     } else {
-        CK(cudaMemset(d, 0, bytes));
+        CK(cudaMemsetAsync(d, 0, bytes, sc->upload_stream));
     }
     *dst = d;
     return FRT_OK;
@@ -1974,6 +2038,56 @@ validate_desc(const frt_scene_desc *d)
     if (d->n_nodes <= 0 || d->n_roots <= 0 || d->n_xforms <= 0 || d->nodes == nullptr || d->roots == nullptr || d->xforms == nullptr) {
         return frt_set_error(FRT_ERR_ARG, "scene has no nodes / roots / transforms");
     }
+    if (d->n_materials < 0 || d->n_patterns < 0 || d->n_textures < 0 || d->n_lights < 0 || d->n_prim_params < 0 || d->n_texels < 0 ||
+        d->n_light_points < 0 || d->n_pixel_samples < 0) {
+        return frt_set_error(FRT_ERR_ARG, "scene description has a negative count");
+    }
+    if ((d->n_materials > 0 && d->materials == nullptr) || (d->n_patterns > 0 && d->patterns == nullptr) ||
+        (d->n_textures > 0 && d->textures == nullptr) || (d->n_lights > 0 && d->lights == nullptr) ||
+        (d->n_prim_params > 0 && d->prim_params == nullptr) || (d->n_texels > 0 && d->texels == nullptr)) {
+        return frt_set_error(FRT_ERR_ARG, "scene description has a positive count with a null array");
+    }
+    /* every index and offset the kernels dereference */
+    for (int i = 0; i < d->n_materials; ++i) {
+        const frt_material &m = d->materials[i];
+        const int maps[7] = { m.map_Ka, m.map_Kd, m.map_Ks, m.map_Ns, m.map_d, m.map_bump, m.map_refl };
+        for (int k = 0; k < 7; ++k) {
+            if (maps[k] < -1 || maps[k] >= d->n_patterns) {
+                return frt_set_error(FRT_ERR_ARG, "material %d: map %d is pattern %d of %d", i, k, maps[k], d->n_patterns);
+            }
+        }
+    }
+    for (int i = 0; i < d->n_textures; ++i) {
+        const frt_texture &t = d->textures[i];
+        if (t.width <= 0 || t.height <= 0 || t.texel_offset < 0 || t.texel_offset + (int64_t)t.width * t.height > d->n_texels) {
+            return frt_set_error(FRT_ERR_ARG, "texture %d (%d x %d at %lld) does not fit the %lld texels", i, t.width, t.height,
+                                 (long long)t.texel_offset, (long long)d->n_texels);
+        }
+    }
+    for (int i = 0; i < d->n_patterns; ++i) {
+        const frt_pattern &p = d->patterns[i];
+        bool ok = p.type >= 0 && p.type <= FRT_PAT_TEXTURE_MAP;
+        auto child = [&](int idx) { return idx >= 0 && idx < d->n_patterns && idx != i; };
+        if (ok) {
+            switch (p.type) {
+            case FRT_PAT_UV_TEXTURE: ok = p.i[0] >= 0 && p.i[0] < d->n_textures; break;
+            case FRT_PAT_BLENDED: ok = child(p.i[0]) && child(p.i[1]); break;
+            case FRT_PAT_NESTED: ok = child(p.i[0]) && child(p.i[1]) && child(p.i[2]); break;
+            case FRT_PAT_PERTURBED: ok = child(p.i[0]); break;
+            case FRT_PAT_CUBE_MAP:
+            case FRT_PAT_CYLINDER_MAP:
+            case FRT_PAT_TEXTURE_MAP: {
+                const int faces = p.i[0] == FRT_UV_CUBE ? 6 : (p.i[0] == FRT_UV_CYLINDER ? 3 : 1);
+                ok = p.i[0] >= 0 && p.i[0] <= FRT_UV_TRIANGLE && p.i[1] >= 0 && p.i[1] + faces <= d->n_patterns;
+                break;
+            }
+            default: break;
+            }
+        }
+        if (!ok) {
+            return frt_set_error(FRT_ERR_ARG, "pattern %d (type %d) refers outside the pattern / texture tables", i, p.type);
+        }
+    }
     for (int i = 0; i < d->n_nodes; ++i) {
         const frt_node &n = d->nodes[i];
         if (n.type < 0 || n.type > FRT_GROUP || n.skip <= i || n.skip > d->n_nodes || n.xform < 0 || n.xform >= d->n_xforms) {
@@ -1986,7 +2100,8 @@ validate_desc(const frt_scene_desc *d)
             return frt_set_error(FRT_ERR_ARG, "CSG node %d has right child %d outside (%d, %d)", i, n.right, i + 1, n.skip);
         }
         bool needs_param = n.type == FRT_CONE || n.type == FRT_CYLINDER || n.type == FRT_TOROID || n.type == FRT_TRIANGLE || n.type == FRT_SMOOTH_TRIANGLE;
-        if (needs_param && (n.param < 0 || n.param >= d->n_prim_params)) {
+        const int64_t param_len = (n.type == FRT_TRIANGLE || n.type == FRT_SMOOTH_TRIANGLE) ? FRT_TRI_PARAMS : (n.type == FRT_TOROID ? 2 : 3);
+        if (needs_param && (n.param < 0 || (int64_t)n.param + param_len > d->n_prim_params)) {
             return frt_set_error(FRT_ERR_ARG, "leaf node %d has parameter offset %d of %lld", i, n.param, (long long)d->n_prim_params);
         }
     }
@@ -1997,7 +2112,7 @@ validate_desc(const frt_scene_desc *d)
     }
     for (int i = 0; i < d->n_lights; ++i) {
         const frt_light &l = d->lights[i];
-        if (l.num_samples <= 0 || l.cache_len <= 0 || l.point_offset < 0 ||
+        if (l.num_samples <= 0 || l.cache_len <= 0 || l.point_offset < 0 || l.type < 0 || l.type > 3 ||
             l.point_offset + (int64_t)l.num_samples * l.cache_len > d->n_light_points) {
             return frt_set_error(FRT_ERR_ARG, "light %d has an inconsistent sample cache", i);
         }
@@ -2080,7 +2195,9 @@ frt_scene_destroy(frt_scene *sc)
         if (e) cudaEventDestroy(e);
     }
     if (sc->nrays_ev) cudaEventDestroy(sc->nrays_ev);
+    pinned_slot_give(sc->h_nrays);
     if (sc->upload_ev) cudaEventDestroy(sc->upload_ev);
+    if (sc->ready_ev) cudaEventDestroy(sc->ready_ev);
     if (sc->upload_stream) cudaStreamDestroy(sc->upload_stream);
     for (auto &e : sc->light_ev) {
         cudaEventDestroy(e);
@@ -2410,20 +2527,33 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     if (rc != FRT_OK) return rc;
     sc->SF.bmax = nextafterf((float)(bmax * (1.0 + 1e-6)), INFINITY);
     sc->SF.n_nodes = d->n_nodes;
-    /* FP32 copy of the light sample points, converted on the device; then, per light, the bounds of its sample points
-     * (all of them, and per quadrant of the sample grid) over every cached set, reduced on the device from the points as
-     * uploaded -- no assumption about where the sampler puts sample (u, v).  All of it runs on the upload stream behind
-     * the copy of the points (frt_scene_create), so none of it needs the host. */
-    cudaStream_t us = sc->upload_stream;
-    const size_t np = (size_t)3 * d->n_light_points;
-    float *fp = nullptr;
-    CK(scene_alloc(sc, (void **)&fp, std::max<size_t>(np, 1) * sizeof(float)));
-    if (np) {
-        k_to_float<<<148 * 8, 256, 0, us>>>(sc->S.lpoints, fp, np);
-        CK(cudaGetLastError());
-    }
-    sc->SF.lpoints = fp;
+    return FRT_OK;
+}
 
+/*
+ * What the upload stream derives from the light points once they are on the device (copied, or rebuilt by k_light_gen):
+ * their FP32 copy (only for the lights that were copied -- k_light_gen writes both precisions) and, per light, the
+ * bounds of its sample points (all of them, and per quadrant of the sample grid) over every cached set, reduced on the
+ * device from the points as they are -- no assumption about where the sampler puts sample (u, v).  All of it runs on the
+ * upload stream behind the copy / the generator, so none of it needs the host.
+ */
+static int
+build_light_bounds(frt_scene *sc, const frt_scene_desc *d, const std::vector<int> &generated)
+{
+    cudaStream_t us = sc->upload_stream;
+    float *fp = const_cast<float *>(sc->SF.lpoints);
+    for (int li = 0; li < d->n_lights; ++li) {
+        if (generated[li]) {
+            continue;
+        }
+        const frt_light &L = d->lights[li];
+        const size_t np = (size_t)3 * L.num_samples * L.cache_len;
+        if (np) {
+            const int blocks = (int)std::min<size_t>((np + 255) / 256, (size_t)sc->sm_count * 8);
+            k_to_float<<<blocks, 256, 0, us>>>(sc->S.lpoints + 3 * L.point_offset, fp + 3 * L.point_offset, np);
+            CK(cudaGetLastError());
+        }
+    }
     const int nl = std::max(d->n_lights, 1);
     std::vector<int4> lquad(nl, make_int4(1, 0, 0, 0));
     std::vector<int> chunks(nl, 1);
@@ -2440,7 +2570,7 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
         lquad[li] = lq;
         chunks[li] = std::max(1, std::min(FRT_BOX_CHUNKS, L.cache_len));
     }
-    rc = upload(sc, lquad.data(), lquad.size(), &sc->SF.lquad);
+    int rc = upload(sc, lquad.data(), lquad.size(), &sc->SF.lquad);
     if (rc != FRT_OK) return rc;
     const int *dchunks = nullptr;
     rc = upload(sc, chunks.data(), chunks.size(), &dchunks);
@@ -2460,8 +2590,139 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     return FRT_OK;
 }
 
+/* k_light_gen for one listed light, then the bit-for-bit comparison of the caller's sets; *d_mismatch accumulates */
+static int
+generate_light_cache(frt_scene *sc, const frt_scene_desc *d, const frt_light_gen &g, double *pool64, float *pool32, unsigned int *d_mismatch)
+{
+    const frt_light &L = d->lights[g.light];
+    LightGenParams P{};
+    for (int k = 0; k < 3; ++k) {
+        P.corner[k] = L.position[k];
+        P.uvec[k] = L.uvec[k];
+        P.vvec[k] = L.vvec[k];
+    }
+    P.usteps = L.usteps;
+    P.vsteps = L.vsteps;
+    P.cache_len = L.cache_len;
+    P.x0 = g.drand48_state & FRT_LCG_MASK;
+    const unsigned long long per_set = 2ull * L.usteps * L.vsteps + L.usteps + L.vsteps;
+    LcgJump j = lcg_jump(per_set);
+    for (int b = 0; b < 32; ++b) {
+        P.pow2[b] = j;
+        const unsigned long long a = j.a;
+        j.a = (a * a) & FRT_LCG_MASK;
+        j.c = (a * j.c + j.c) & FRT_LCG_MASK;
+    }
+    const size_t smem = (size_t)FRT_LGEN_WARPS * (per_set + 2ull * L.num_samples) * sizeof(double);
+    if (smem > 48 * 1024) {
+        CK(cudaFuncSetAttribute(k_light_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int blocks = (L.cache_len + FRT_LGEN_WARPS - 1) / FRT_LGEN_WARPS;
+    cudaStream_t us = sc->upload_stream;
+    k_light_gen<<<blocks, FRT_LGEN_WARPS * 32, smem, us>>>(P, pool64 + 3 * L.point_offset, pool32 + 3 * L.point_offset);
+    CK(cudaGetLastError());
+    const int words = 3 * L.num_samples;
+    for (int k = 0; k < g.n_verify; ++k) {
+        double *expect = nullptr;
+        CK(scene_alloc(sc, (void **)&expect, sizeof(double) * words));
+        CK(cudaMemcpyAsync(expect, g.verify_points[k], sizeof(double) * words, cudaMemcpyHostToDevice, us));
+        k_light_gen_verify<<<1, 256, 0, us>>>(pool64 + 3 * (L.point_offset + (size_t)g.verify_set[k] * L.num_samples), expect, words, d_mismatch);
+        CK(cudaGetLastError());
+    }
+    return FRT_OK;
+}
+
+static int
+validate_gens(const frt_scene_desc *d, const frt_light_gen *gens, int n_gens, std::vector<int> &generated)
+{
+    generated.assign(std::max(d->n_lights, 1), 0);
+    if (n_gens < 0 || (n_gens > 0 && gens == nullptr)) {
+        return frt_set_error(FRT_ERR_ARG, "frt_scene_create_gen: %d generators, null list", n_gens);
+    }
+    for (int k = 0; k < n_gens; ++k) {
+        const frt_light_gen &g = gens[k];
+        if (g.light < 0 || g.light >= d->n_lights || generated[g.light]) {
+            return frt_set_error(FRT_ERR_ARG, "light generator %d names light %d of %d (or names it twice)", k, g.light, d->n_lights);
+        }
+        const frt_light &L = d->lights[g.light];
+        if (L.type != 0 || !L.jitter || L.usteps <= 0 || L.vsteps <= 0 || L.usteps > FRT_LGEN_MAX_STEPS || L.vsteps > FRT_LGEN_MAX_STEPS ||
+            L.usteps * L.vsteps != L.num_samples) {
+            return frt_set_error(FRT_ERR_ARG, "light %d is not a jittered rectangular area light with at most %d x %d steps", g.light,
+                                 FRT_LGEN_MAX_STEPS, FRT_LGEN_MAX_STEPS);
+        }
+        if (g.n_verify < 0 || g.n_verify > FRT_GEN_VERIFY_MAX) {
+            return frt_set_error(FRT_ERR_ARG, "light generator %d: n_verify %d is outside 0..%d", k, g.n_verify, FRT_GEN_VERIFY_MAX);
+        }
+        for (int v = 0; v < g.n_verify; ++v) {
+            if (g.verify_points[v] == nullptr || g.verify_set[v] < 0 || g.verify_set[v] >= L.cache_len) {
+                return frt_set_error(FRT_ERR_ARG, "light generator %d: verify set %d is null or outside the cache", k, v);
+            }
+        }
+        generated[g.light] = 1;
+    }
+    for (int li = 0; li < d->n_lights; ++li) {
+        if (!generated[li] && d->light_points == nullptr && d->n_light_points > 0) {
+            return frt_set_error(FRT_ERR_ARG, "light %d has no generator and the description carries no light points", li);
+        }
+    }
+    return FRT_OK;
+}
+
+extern "C" uint64_t
+frt_drand48_advance(uint64_t x, uint64_t draws)
+{
+    const LcgJump j = lcg_jump(draws);
+    return (j.a * (x & FRT_LCG_MASK) + j.c) & FRT_LCG_MASK;
+}
+
+/* wrapping sum over the words of bits(word) * (2 * index + 1): order- and position-sensitive, associative */
+__global__ void
+k_points_checksum(const double *__restrict__ pts, unsigned long long first_word, unsigned long long n_words, unsigned long long *sum)
+{
+    unsigned long long acc = 0;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_words; k += (unsigned long long)gridDim.x * blockDim.x) {
+        acc += (unsigned long long)__double_as_longlong(pts[first_word + k]) * (2ull * k + 1ull);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_down_sync(0xffffffffu, acc, o);
+    }
+    if ((threadIdx.x & 31) == 0 && acc) {
+        atomicAdd(sum, acc);
+    }
+}
+
+extern "C" uint64_t
+frt_light_points_checksum_host(const double *points, int64_t first_point, int64_t n_points)
+{
+    uint64_t acc = 0;
+    if (points == nullptr || first_point < 0 || n_points <= 0) {
+        return 0;
+    }
+    const double *p = points + 3 * first_point;
+    for (uint64_t k = 0; k < (uint64_t)n_points * 3u; ++k) {
+        uint64_t bits;
+        memcpy(&bits, p + k, sizeof(bits));
+        acc += bits * (2u * k + 1u);
+    }
+    return acc;
+}
+
+static int scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int n_gens, frt_scene **out);
+
 extern "C" int
 frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
+{
+    return scene_create(d, device, nullptr, 0, out);
+}
+
+extern "C" int
+frt_scene_create_gen(const frt_scene_desc *d, int device, const frt_light_gen *gens, int n_gens, frt_scene **out)
+{
+    return scene_create(d, device, gens, n_gens, out);
+}
+
+static int
+scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int n_gens, frt_scene **out)
 {
     if (out == nullptr) {
         return frt_set_error(FRT_ERR_ARG, "frt_scene_create: null out pointer");
@@ -2479,9 +2740,18 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
         return frt_set_error(FRT_ERR_ARG, "device %d of %d", device, ndev);
     }
     CK(cudaSetDevice(device));
+    std::vector<int> generated;
+    rc = validate_gens(d, gens, n_gens, generated);
+    if (rc != FRT_OK) {
+        return rc;
+    }
 
     frt_scene *sc = new frt_scene();
     sc->device = device;
+    {
+        cudaDeviceProp prop;
+        sc->sm_count = cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    }
 #define UP(expr)                     \
     do {                             \
         int rc_ = (expr);            \
@@ -2490,6 +2760,16 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
             return rc_;              \
         }                            \
     } while (0)
+    /* two streams: everything the host hands over travels on the upload stream, the frame runs on the render stream.
+     * The render stream waits for `ready_ev` (the small buffers: tree, materials, mirror) before its first kernel and
+     * for `upload_ev` (the light points and what is derived from them) where its first light stage begins. */
+    if (cudaStreamCreateWithFlags(&sc->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sc->upload_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sc->ready_ev, cudaEventDisableTiming) != cudaSuccess) {
+        frt_scene_destroy(sc);
+        return frt_set_error(FRT_ERR_CUDA, "cudaStreamCreate failed");
+    }
 
     /* nodes -> 2 x int4, bounding boxes -> 6 doubles */
     std::vector<int4> nodes((size_t)2 * d->n_nodes);
@@ -2513,44 +2793,99 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
     UP(upload(sc, d->textures, (size_t)d->n_textures, &S.texs));
     UP(upload(sc, d->texels, (size_t)3 * d->n_texels, &S.texels));
     UP(upload(sc, d->lights, (size_t)d->n_lights, &S.lights));
-    if (cudaStreamCreateWithFlags(&sc->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&sc->upload_ev, cudaEventDisableTiming) != cudaSuccess) {
-        frt_scene_destroy(sc);
-        return frt_set_error(FRT_ERR_CUDA, "cudaStreamCreate (upload) failed");
-    }
-    /* The light-sample cache is the one large buffer of a scene (157 MB for the shipped Cornell box).  When the caller
-     * page-locked it (frt_host_register) it is copied asynchronously on the upload stream and the first frame only waits
-     * for it where its light stage begins -- ray generation, the primary rays and their shading run meanwhile.  The
-     * buffer must then stay valid until the first frt_render (or frt_scene_destroy) returns; an unregistered buffer is
-     * copied before this call returns, as ever. */
-    const size_t lp_bytes = (size_t)3 * d->n_light_points * sizeof(double);
-    const bool async_points = lp_bytes >= ((size_t)1 << 20) && host_range_registered(d->light_points, lp_bytes);
-    if (async_points) {
-        double *dp = nullptr;
-        if (scene_alloc(sc, (void **)&dp, lp_bytes) != cudaSuccess ||
-            cudaMemcpyAsync(dp, d->light_points, lp_bytes, cudaMemcpyHostToDevice, sc->upload_stream) != cudaSuccess) {
-            frt_scene_destroy(sc);
-            return frt_set_error(FRT_ERR_CUDA, "asynchronous upload of the light points failed");
-        }
-        S.lpoints = dp;
-    } else {
-        UP(upload(sc, d->light_points, (size_t)3 * d->n_light_points, &S.lpoints));
-    }
     UP(upload(sc, d->roots, (size_t)d->n_roots, &S.roots));
     UP(build_f32_mirror(sc, d));
+    const frt_camera &c = d->camera;
+    {
+        std::vector<double> table;
+        if (d->pixel_samples != nullptr && d->n_pixel_samples == (int64_t)2 * c.usteps * c.vsteps) {
+            table.assign(d->pixel_samples, d->pixel_samples + d->n_pixel_samples);
+        } else {
+            cmj_table_no_jitter(c.usteps, c.vsteps, table);
+        }
+        const double *dtab = nullptr;
+        UP(upload(sc, table.data(), table.size(), &dtab));
+        sc->samples = const_cast<double *>(dtab);
+        sc->samples_u = c.usteps;
+        sc->samples_v = c.vsteps;
+        sc->C.samples = dtab;
+    }
+    if (cudaEventRecord(sc->ready_ev, sc->upload_stream) != cudaSuccess || cudaStreamWaitEvent(sc->stream, sc->ready_ev, 0) != cudaSuccess) {
+        frt_scene_destroy(sc);
+        return frt_set_error(FRT_ERR_CUDA, "cudaEventRecord (ready) failed");
+    }
+
+    /* The light-sample cache is the one large buffer of a scene (157 MB for the shipped Cornell box).  A light listed in
+     * `gens` has its cache rebuilt on the device (frt_lightgen.cuh); the others are copied -- asynchronously when the
+     * caller page-locked the pool (frt_host_register): the first frame then only waits for it where its light stage
+     * begins, and the buffer must stay valid until the first frt_render (or frt_scene_destroy) returns; an unregistered
+     * buffer is staged before this call returns, as ever. */
+    const size_t lp_count = (size_t)3 * d->n_light_points;
+    const size_t lp_bytes = lp_count * sizeof(double);
+    double *pool64 = nullptr;
+    float *pool32 = nullptr;
+    if (scene_alloc(sc, (void **)&pool64, std::max<size_t>(lp_bytes, 8)) != cudaSuccess ||
+        scene_alloc(sc, (void **)&pool32, std::max<size_t>(lp_count, 1) * sizeof(float)) != cudaSuccess) {
+        frt_scene_destroy(sc);
+        return frt_set_error(FRT_ERR_CUDA, "cudaMalloc of the light points failed");
+    }
+    S.lpoints = pool64;
+    sc->SF.lpoints = pool32;
+    bool async_points = false;
+    unsigned int *d_mismatch = nullptr;
+    if (n_gens == 0) {
+        async_points = lp_bytes >= ((size_t)1 << 20) && host_range_registered(d->light_points, lp_bytes);
+        if (lp_bytes && cudaMemcpyAsync(pool64, d->light_points, lp_bytes, cudaMemcpyHostToDevice, sc->upload_stream) != cudaSuccess) {
+            frt_scene_destroy(sc);
+            return frt_set_error(FRT_ERR_CUDA, "upload of the light points failed");
+        }
+    } else {
+        if (scene_alloc(sc, (void **)&d_mismatch, sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemsetAsync(d_mismatch, 0, sizeof(unsigned int), sc->upload_stream) != cudaSuccess) {
+            frt_scene_destroy(sc);
+            return frt_set_error(FRT_ERR_CUDA, "cudaMalloc (light generator) failed");
+        }
+        for (int li = 0; li < d->n_lights; ++li) {
+            if (generated[li]) {
+                continue;
+            }
+            const frt_light &L = d->lights[li];
+            const size_t n = (size_t)3 * L.num_samples * L.cache_len;
+            if (n && cudaMemcpyAsync(pool64 + 3 * L.point_offset, d->light_points + 3 * L.point_offset, n * sizeof(double),
+                                     cudaMemcpyHostToDevice, sc->upload_stream) != cudaSuccess) {
+                frt_scene_destroy(sc);
+                return frt_set_error(FRT_ERR_CUDA, "upload of the light points failed");
+            }
+        }
+        for (int k = 0; k < n_gens; ++k) {
+            UP(generate_light_cache(sc, d, gens[k], pool64, pool32, d_mismatch));
+        }
+    }
+    UP(build_light_bounds(sc, d, generated));
     if (cudaEventRecord(sc->upload_ev, sc->upload_stream) != cudaSuccess) {
         frt_scene_destroy(sc);
         return frt_set_error(FRT_ERR_CUDA, "cudaEventRecord (upload) failed");
     }
     sc->upload_pending = true;
-    if (!async_points) {
+    if (d_mismatch != nullptr) {
+        unsigned int bad = 0;
+        if (cudaMemcpyAsync(&bad, d_mismatch, sizeof(bad), cudaMemcpyDeviceToHost, sc->upload_stream) != cudaSuccess ||
+            cudaStreamSynchronize(sc->upload_stream) != cudaSuccess) {
+            frt_scene_destroy(sc);
+            return frt_set_error(FRT_ERR_CUDA, "light generator: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (bad) {
+            frt_scene_destroy(sc);
+            return frt_set_error(FRT_ERR_MISMATCH, "a light-sample set rebuilt on the device differs from the caller's in %u words "
+                                                   "(another drand48 state, or another sampler): upload the host cache instead", bad);
+        }
+    } else if (!async_points) {
         cudaStreamSynchronize(sc->upload_stream); /* nothing of the caller's is read after this call returns */
     }
     S.n_roots = d->n_roots;
     S.n_nodes = d->n_nodes;
     S.n_lights = d->n_lights;
 
-    const frt_camera &c = d->camera;
     DCamera &C = sc->C;
     C.hsize = c.hsize;
     C.vsize = c.vsize;
@@ -2565,19 +2900,6 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
     C.jitter = c.aperture_jitter;
     C.aperture_size = c.aperture_size;
     memcpy(C.aperture_args, c.aperture_args, sizeof(C.aperture_args));
-
-    std::vector<double> table;
-    if (d->pixel_samples != nullptr && d->n_pixel_samples == (int64_t)2 * c.usteps * c.vsteps) {
-        table.assign(d->pixel_samples, d->pixel_samples + d->n_pixel_samples);
-    } else {
-        cmj_table_no_jitter(c.usteps, c.vsteps, table);
-    }
-    const double *dtab = nullptr;
-    UP(upload(sc, table.data(), table.size(), &dtab));
-    sc->samples = const_cast<double *>(dtab);
-    sc->samples_u = c.usteps;
-    sc->samples_v = c.vsteps;
-    C.samples = dtab;
 
     sc->cfg = d->config;
     {
@@ -2608,30 +2930,15 @@ frt_scene_create(const frt_scene_desc *d, int device, frt_scene **out)
         return frt_set_error(FRT_ERR_CUDA, "cudaMalloc of the canvas failed");
     }
     sc->canvas = (double *)cv;
-    if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        frt_scene_destroy(sc);
-        return frt_set_error(FRT_ERR_CUDA, "cudaStreamCreate failed");
-    }
     for (auto &e : sc->ev) {
         if (cudaEventCreate(&e) != cudaSuccess) {
             frt_scene_destroy(sc);
             return frt_set_error(FRT_ERR_CUDA, "cudaEventCreate failed");
         }
     }
-    {
-        /* one pinned word per device for the whole process (one frame at a time per device, like the parked buffers) */
-        std::lock_guard<std::mutex> lk(g_park_mu);
-        static std::map<int, unsigned int *> pinned;
-        auto it = pinned.find(device);
-        if (it == pinned.end()) {
-            unsigned int *p = nullptr;
-            if (cudaHostAlloc((void **)&p, 64, cudaHostAllocPortable) == cudaSuccess) {
-                it = pinned.emplace(device, p).first;
-            }
-        }
-        if (it != pinned.end() && cudaEventCreateWithFlags(&sc->nrays_ev, cudaEventDisableTiming) == cudaSuccess) {
-            sc->h_nrays = it->second;
-        }
+    /* one pinned slot per scene (recycled through a per-process free list): the next level's ray count lands here */
+    if (cudaEventCreateWithFlags(&sc->nrays_ev, cudaEventDisableTiming) == cudaSuccess) {
+        sc->h_nrays = pinned_slot_take();
     }
 #undef UP
     *out = sc;
@@ -2832,6 +3139,31 @@ frt_canvas_device_ptr(frt_scene *sc, void **device_ptr)
     return FRT_OK;
 }
 
+extern "C" int
+frt_light_points_checksum(frt_scene *sc, int64_t first_point, int64_t n_points, uint64_t *sum)
+{
+    if (sc == nullptr || sum == nullptr || first_point < 0 || n_points < 0) {
+        return frt_set_error(FRT_ERR_ARG, "frt_light_points_checksum: bad argument");
+    }
+    CK(cudaSetDevice(sc->device));
+    CK(cudaStreamSynchronize(sc->upload_stream));
+    unsigned long long *d = nullptr, h = 0;
+    CK(cudaMalloc(&d, sizeof(h)));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(h), sc->stream);
+    if (e == cudaSuccess && n_points) {
+        k_points_checksum<<<sc->sm_count * 8, 256, 0, sc->stream>>>(sc->S.lpoints, 3ull * (unsigned long long)first_point, 3ull * (unsigned long long)n_points, d);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, sc->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sc->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        return frt_set_error(FRT_ERR_CUDA, "frt_light_points_checksum: %s", cudaGetErrorString(e));
+    }
+    *sum = h;
+    return FRT_OK;
+}
+
 /* ---- output encode: write_ppm_file / construct_ppm (canvas.c:150-328) on the device ------------------------------ */
 
 static size_t
@@ -2862,32 +3194,39 @@ encode_ppm16(const double *dev_canvas, int width, int height, int use_scaling, c
     const size_t n = (size_t)width * height;
     double *maxes = nullptr;
     unsigned char *data = nullptr;
-    CK(cudaMalloc(&maxes, 6 * sizeof(double)));
-    if (cudaMalloc(&data, n * 6) != cudaSuccess) {
-        cudaFree(maxes);
-        return frt_set_error(FRT_ERR_CUDA, "cudaMalloc of the PPM samples failed");
-    }
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
-    CK(cudaEventRecord(e0, s));
-    CK(cudaMemsetAsync(maxes, 0, 6 * sizeof(double), s));
-    k_ppm_rgb_max<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes);
-    k_ppm_srgb_max<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes);
-    k_ppm_encode<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes, use_scaling, data);
-    CK(cudaEventRecord(e1, s));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0.f;
     char hdr[32];
     const size_t hl = ppm16_header(hdr, sizeof(hdr), width, height);
-    memcpy(out, hdr, hl);
-    cudaError_t e = cudaMemcpyAsync(out + hl, data, n * 6, cudaMemcpyDeviceToHost, s);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)sms * 8);
+    cudaError_t e = cudaMalloc(&maxes, 6 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&data, n * 6);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(maxes, 0, 6 * sizeof(double), s);
+    if (e == cudaSuccess) {
+        k_ppm_rgb_max<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes);
+        k_ppm_srgb_max<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes);
+        k_ppm_encode<<<blocks, 256, 0, s>>>(dev_canvas, n, maxes, use_scaling, data);
+        e = cudaEventRecord(e1, s);
+    }
+    if (e == cudaSuccess) {
+        memcpy(out, hdr, hl);
+        e = cudaMemcpyAsync(out + hl, data, n * 6, cudaMemcpyDeviceToHost, s);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
-    out[hl + n * 6] = '\n'; /* canvas.c:298 */
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    if (e == cudaSuccess) {
+        out[hl + n * 6] = '\n'; /* canvas.c:298 */
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    /* every path releases what it took */
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
     cudaFree(maxes);
     cudaFree(data);
     if (e != cudaSuccess) {
@@ -2941,7 +3280,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             cmj_table_no_jitter(cfg->usteps, cfg->vsteps, table);
             double *dtab = nullptr;
             CK(scene_alloc(sc, (void **)&dtab, table.size() * sizeof(double)));
-            CK(cudaMemcpy(dtab, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
+            CK(cudaMemcpyAsync(dtab, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice, sc->stream)); /* pageable: staged before the call returns */
             sc->samples = dtab;
             sc->samples_u = cfg->usteps;
             sc->samples_v = cfg->vsteps;
@@ -3024,21 +3363,55 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
 
     cudaStream_t s = sc->stream;
     size_t cbytes = (size_t)C.hsize * C.vsize * 4 * sizeof(double);
-    const int sm_blocks = 148;
+    const int sm_blocks = sc->sm_count;
     unsigned long long launches = 0, light_launches = 0;
     Counters totals{};
-    float light_ms = 0.f;
+    /* Per-stage device times: every launch of the dominant shadow-ray kernel (FRT_ST_SHADOW_RAY) and of the per-hit shaft
+     * kernels is bracketed by a pair of events on the render stream, the other stages too under FRT_FLAG_STAGE_TIMES; the
+     * pairs are read after the frame's last event -- nothing here waits for the device. */
+    std::vector<int> span_stage;
+    const bool all_stages = (F.flags & FRT_FLAG_STAGE_TIMES) != 0;
+    bool tick_failed = false;
+    auto tick = [&](int stage) -> int {
+        if (!all_stages && stage != FRT_ST_SHADOW_RAY && stage != FRT_ST_SHADOW_SHAFT) {
+            return -1;
+        }
+        const size_t i = span_stage.size();
+        while (sc->light_ev.size() < 2 * (i + 1)) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) {
+                tick_failed = true;
+                return -1;
+            }
+            sc->light_ev.push_back(e);
+        }
+        span_stage.push_back(stage);
+        if (cudaEventRecord(sc->light_ev[2 * i], s) != cudaSuccess) tick_failed = true;
+        return (int)i;
+    };
+    auto tock = [&](int i) {
+        if (i >= 0 && cudaEventRecord(sc->light_ev[2 * (size_t)i + 1], s) != cudaSuccess) tick_failed = true;
+    };
 
     CK(cudaEventRecord(sc->ev[0], s));
     CK(cudaMemsetAsync(sc->canvas, 0, cbytes, s));
 
     const std::vector<int> &gw = sc->light_gw; /* lanes per hit in k_light_pre / k_light_final, chosen per light at upload */
+    /* launch-shape overrides for experiments, read once per frame */
+    auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return (v != nullptr && *v) ? atoi(v) : dflt; };
+    const int mblocks = env_int("FRT_MESH_BLOCKS", sm_blocks * 8);
+    const int m_inner = env_int("FRT_MESH_INNER_STEPS", FRT_MESH_INNER);
+    const int m_refill = env_int("FRT_MESH_REFILL_MIN", FRT_MESH_REFILL);
+    const int sblocks = env_int("FRT_SHADOW_BLOCKS", sm_blocks * 48);
+    const bool debug_nodes = getenv("FRT_DEBUG_NODES") != nullptr;
 
     for (unsigned long long first = 0; first < total; first += chunk) {
         unsigned int n = (unsigned int)std::min<unsigned long long>(chunk, total - first);
         CK(cudaMemsetAsync(sc->cnt, 0, sizeof(Counters), s));
         int rg_blocks = (int)std::min<unsigned int>((n + 255) / 256, sm_blocks * 16);
+        int tk = tick(FRT_ST_RAYGEN);
         k_raygen<<<rg_blocks, 256, 0, s>>>(C, F, sc->q[0], sc->cnt, (unsigned int)first, n);
+        tock(tk);
         ++launches;
         for (int level = 0; level <= F.path_length; ++level) {
             if (level > 0 && sc->h_nrays != nullptr) {
@@ -3055,8 +3428,12 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             /* level 0 has n rays; deeper levels read their count on the device: size the grid for the worst case
              * the level can hold, but never more than a few waves */
             int ex_blocks = sm_blocks * 8;
+            tk = tick(FRT_ST_EXTEND);
             k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, sc->SF, qi, sc->hq, sc->cnt, level, F.capacity);
+            tock(tk);
+            tk = tick(FRT_ST_SHADE);
             k_shade<<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+            tock(tk);
             launches += 2;
             if (sc->h_nrays != nullptr && level < F.path_length) {
                 CK(cudaMemcpyAsync(sc->h_nrays, &sc->cnt->n_rays[level + 1], sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -3079,28 +3456,21 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                 const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
                 for (int l0 = 0; l0 < sc->S.n_lights; l0 += FRT_MESH_LIGHTS) {
                     const int nl = std::min(FRT_MESH_LIGHTS, sc->S.n_lights - l0);
-                    if (sc->light_ev.size() < 2 * (size_t)(light_launches + 1)) {
-                        cudaEvent_t a, b;
-                        CK(cudaEventCreate(&a));
-                        CK(cudaEventCreate(&b));
-                        sc->light_ev.push_back(a);
-                        sc->light_ev.push_back(b);
-                    }
+                    tk = tick(FRT_ST_LIGHT_PRE);
                     for (int k = 0; k < nl; ++k) {
                         launch_light_pre(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
                     }
+                    tock(tk);
                     if (wait_for_upload(sc, s) != FRT_OK) return FRT_ERR_CUDA;
-                    CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
                     CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
-                    const int mblocks = getenv("FRT_MESH_BLOCKS") ? atoi(getenv("FRT_MESH_BLOCKS")) : sm_blocks * 8;
-                    const int m_inner = getenv("FRT_MESH_INNER_STEPS") ? atoi(getenv("FRT_MESH_INNER_STEPS")) : FRT_MESH_INNER;
-                    const int m_refill = getenv("FRT_MESH_REFILL_MIN") ? atoi(getenv("FRT_MESH_REFILL_MIN")) : FRT_MESH_REFILL;
+                    tk = tick(FRT_ST_SHADOW_RAY);
                     if (count) {
                         k_shadow_mesh<true><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp_multi, sc->capacity, sc->cnt, level, l0, nl, m_inner, m_refill);
                     } else {
                         k_shadow_mesh<false><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp_multi, sc->capacity, sc->cnt, level, l0, nl, m_inner, m_refill);
                     }
-                    CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
+                    tock(tk);
+                    tk = tick(FRT_ST_LIGHT_FINAL);
                     for (int k = 0; k < nl; ++k) {
                         if (F.flags & FRT_FLAG_F64_SHADING) {
                             launch_light_final<double>(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
@@ -3108,47 +3478,40 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                             launch_light_final<float>(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
                         }
                     }
+                    tock(tk);
                     launches += 1 + 2 * nl;
                     ++light_launches;
                 }
             } else if (F.include_direct) {
                 for (int li = 0; li < sc->S.n_lights; ++li) {
-                    if (sc->light_ev.size() < 2 * (size_t)(light_launches + 1)) {
-                        cudaEvent_t a, b;
-                        CK(cudaEventCreate(&a));
-                        CK(cudaEventCreate(&b));
-                        sc->light_ev.push_back(a);
-                        sc->light_ev.push_back(b);
-                    }
                     const int blocks = sm_blocks * 8;
+                    tk = tick(FRT_ST_LIGHT_PRE);
                     launch_light_pre(sc, F, blocks, level, li, gw[li], sc->ltmp);
+                    tock(tk);
                     if (wait_for_upload(sc, s) != FRT_OK) return FRT_ERR_CUDA;
-                    CK(cudaEventRecord(sc->light_ev[2 * light_launches], s));
                     const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
                     if (F.flags & FRT_FLAG_F64_SHADOW) {
+                        tk = tick(FRT_ST_SHADOW_RAY);
                         if (count) {
                             k_shadow_exact<true, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         } else {
                             k_shadow_exact<false, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         }
-                        CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
+                        tock(tk);
                         launches += 1;
                     } else if (sc->mesh_mode && sc->S.n_roots == 1) {
                         CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
-                        const int mblocks = getenv("FRT_MESH_BLOCKS") ? atoi(getenv("FRT_MESH_BLOCKS")) : sm_blocks * 8;
-                        const int m_inner = getenv("FRT_MESH_INNER_STEPS") ? atoi(getenv("FRT_MESH_INNER_STEPS")) : FRT_MESH_INNER;
-                        const int m_refill = getenv("FRT_MESH_REFILL_MIN") ? atoi(getenv("FRT_MESH_REFILL_MIN")) : FRT_MESH_REFILL;
+                        tk = tick(FRT_ST_SHADOW_RAY);
                         if (count) {
                             k_shadow_mesh<true><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, 0, sc->cnt, level, li, 1, m_inner, m_refill);
                         } else {
                             k_shadow_mesh<false><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, 0, sc->cnt, level, li, 1, m_inner, m_refill);
                         }
-                        CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
+                        tock(tk);
                         launches += 1;
                     } else {
                         const size_t f32_smem = (size_t)sc->S.n_nodes * 48 <= 32768 ? (size_t)sc->S.n_nodes * 48 : 0;
                         /* many short grid-stride trips balance the uneven per-ray work better than 8 CTAs per SM (measured: 35.0 -> 33.5 ms) */
-                        const int sblocks = getenv("FRT_SHADOW_BLOCKS") ? atoi(getenv("FRT_SHADOW_BLOCKS")) : sm_blocks * 48;
                         CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, 2 * sizeof(unsigned int), s)); /* n_deferred, n_pending */
                         /* per hit: every shadow ray at once where the shaft's intervals separate (small trees, area lights) */
                         const int bulk_on = sc->S.n_roots == 1 && sc->S.n_nodes <= 32 && sc->light_ns[li] >= 4 &&
@@ -3159,14 +3522,18 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         unsigned char *pstart = reinterpret_cast<unsigned char *>(sc->pending + (size_t)sc->capacity * 4);
 #define FRT_SHADOW_STAGE(M)                                                                                                                       \
     do {                                                                                                                                          \
+        tk = tick(FRT_ST_SHADOW_SHAFT);                                                                                                           \
         k_shadow_bulk<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pstart, retry, bulk_on, split_on);  \
         if (split_on) {                                                                                                                           \
             k_shadow_quad<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, pstart, retry);                        \
             CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));                                                                \
             launches += 1;                                                                                                                        \
         }                                                                                                                                         \
+        tock(tk);                                                                                                                                 \
+        tk = tick(FRT_ST_SHADOW_RAY);                                                                                                             \
         k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, bulk_on, pend_cap, split_on, li, sc->dq, \
                                                        sc->dq_cap, f32_smem != 0);                                                                \
+        tock(tk);                                                                                                                                 \
     } while (0)
                         if (F.flags & FRT_FLAG_VERIFY_F32) {
                             FRT_SHADOW_STAGE(2);
@@ -3176,19 +3543,22 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                             FRT_SHADOW_STAGE(0);
                         }
 #undef FRT_SHADOW_STAGE
-                        CK(cudaEventRecord(sc->light_ev[2 * light_launches + 1], s));
+                        tk = tick(FRT_ST_SHADOW_EXACT);
                         if (count) {
                             k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         } else {
                             k_shadow_exact<false, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
                         }
+                        tock(tk);
                         launches += 3;
                     }
+                    tk = tick(FRT_ST_LIGHT_FINAL);
                     if (F.flags & FRT_FLAG_F64_SHADING) {
                         launch_light_final<double>(sc, F, blocks, level, li, gw[li], sc->ltmp);
                     } else {
                         launch_light_final<float>(sc, F, blocks, level, li, gw[li], sc->ltmp);
                     }
+                    tock(tk);
                     launches += 2;
                     ++light_launches;
                 }
@@ -3205,6 +3575,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                 for (unsigned int first = 0; first < n_hits && per_hit; first += batch) {
                     const unsigned int nb = std::min(batch, n_hits - first);
                     CK(cudaMemsetAsync(sc->gq_n, 0, sizeof(unsigned int), s));
+                    tk = tick(FRT_ST_GI_TRACE);
                     if (G.use_caustics || G.visualize) {
                         k_gi_points<<<sm_blocks * 4, 256, 0, s>>>(F, G, sc->recs, first, nb, sc->gq, sc->gq_n, sc->gq_cap, sc->cnt,
                                                                   G.use_caustics, G.visualize);
@@ -3214,11 +3585,16 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         k_fg_trace<<<sm_blocks * 16, 128, 0, s>>>(sc->S, sc->SF, F, G, sc->recs, first, nb, sc->gq, sc->gq_n, sc->gq_cap, sc->cnt, level);
                         ++launches;
                     }
+                    tock(tk);
+                    tk = tick(FRT_ST_KNN);
                     k_knn<<<sm_blocks * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, sc->gq, sc->gq_n, sc->gq_cap,
-                                                                      sc->acc_amb, sc->acc_fg);
+                                                                      sc->acc_amb, sc->acc_fg, nullptr);
+                    tock(tk);
                     ++launches;
                 }
+                tk = tick(FRT_ST_GI_RESOLVE);
                 k_gi_resolve<<<sm_blocks * 8, 256, 0, s>>>(F, G, sc->recs, sc->acc_amb, sc->acc_fg, sc->canvas, sc->cnt, level);
+                tock(tk);
                 ++launches;
             }
         }
@@ -3236,10 +3612,11 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         totals.f32_mismatch += hc.f32_mismatch;
         totals.rays_gather += hc.rays_gather;
         totals.rays_bulk += hc.rays_bulk;
+        totals.rays_per_ray += hc.rays_per_ray;
         for (int k = 0; k < 10; ++k) {
             totals.undecided_reason[k] += hc.undecided_reason[k];
         }
-        if (getenv("FRT_DEBUG_NODES") != nullptr) {
+        if (debug_nodes) {
             for (int k = 0; k < 32; ++k) {
                 if (hc.undecided_node[k]) fprintf(stderr, "undecided at node %d: %llu\n", k, hc.undecided_node[k]);
             }
@@ -3253,15 +3630,26 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     CK(cudaGetLastError());
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, sc->ev[0], sc->ev[1]));
-    for (unsigned long long k = 0; k < light_launches; ++k) {
+    if (tick_failed) {
+        return frt_set_error(FRT_ERR_CUDA, "cudaEventCreate / cudaEventRecord of a stage timer failed");
+    }
+    double stage_ms[FRT_ST_COUNT] = { 0 };
+    unsigned long long stage_launches[FRT_ST_COUNT] = { 0 };
+    for (size_t k = 0; k < span_stage.size(); ++k) {
         float lms = 0.f;
         CK(cudaEventElapsedTime(&lms, sc->light_ev[2 * k], sc->light_ev[2 * k + 1]));
-        light_ms += lms;
+        stage_ms[span_stage[k]] += lms;
+        stage_launches[span_stage[k]] += 1;
     }
 
     if (st != nullptr) {
         st->frame_ms = ms;
-        st->light_ms = light_ms;
+        st->light_ms = stage_ms[FRT_ST_SHADOW_RAY];
+        for (int k = 0; k < FRT_ST_COUNT; ++k) {
+            st->stage_ms[k] = stage_ms[k];
+        }
+        st->shadow_ray_launches = stage_launches[FRT_ST_SHADOW_RAY];
+        st->shadow_rays_traced = totals.rays_per_ray;
         st->rays_primary = total;
         st->rays_secondary = totals.rays_secondary;
         st->rays_shadow = totals.rays_shadow;
@@ -3382,8 +3770,9 @@ pm_reserve(frt_scene *sc, int map, unsigned int cap)
     CK(cudaMalloc(&na, sizeof(float4) * (size_t)cap));
     CK(cudaMalloc(&nb, sizeof(float4) * (size_t)cap));
     if (m.count) {
-        CK(cudaMemcpy(na, m.ra, sizeof(float4) * (size_t)m.count, cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(nb, m.rb, sizeof(float4) * (size_t)m.count, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpyAsync(na, m.ra, sizeof(float4) * (size_t)m.count, cudaMemcpyDeviceToDevice, sc->stream));
+        CK(cudaMemcpyAsync(nb, m.rb, sizeof(float4) * (size_t)m.count, cudaMemcpyDeviceToDevice, sc->stream));
+        CK(cudaStreamSynchronize(sc->stream));
     }
     cudaFree(m.ra);
     cudaFree(m.rb);
@@ -3471,7 +3860,8 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
         return frt_set_error(FRT_ERR_ARG, "gi.path_length %d is outside 0..64", g.gi_path_length);
     }
     std::vector<frt_light> hl(sc->S.n_lights);
-    CK(cudaMemcpy(hl.data(), sc->S.lights, sizeof(frt_light) * hl.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(hl.data(), sc->S.lights, sizeof(frt_light) * hl.size(), cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaStreamSynchronize(sc->stream));
     double total_l = 0.0;
     for (auto &l : hl) {
         total_l += lab_lightness(l.intensity);
@@ -3483,7 +3873,7 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
         int rc0 = ensure_frame_buffers(sc, 1024);
         if (rc0 != FRT_OK) return rc0;
     }
-    CK(cudaMemset(sc->cnt, 0, sizeof(Counters)));
+    CK(cudaMemsetAsync(sc->cnt, 0, sizeof(Counters), sc->stream));
     unsigned long long emitted_total = 0;
     for (int map = 0; map < 2; ++map) {
         const bool want = map == 0 ? cfg->populate_caustic != 0 : cfg->populate_global != 0;
@@ -3500,14 +3890,15 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
         if (rc != FRT_OK) {
             return rc;
         }
-        CK(cudaMemset(sc->pm_stored + map, 0, sizeof(unsigned int)));
+        CK(cudaMemsetAsync(sc->pm_stored + map, 0, sizeof(unsigned int), sc->stream));
         unsigned long long target = 0; /* cumulative stored-photon target over the lights */
         for (int li = 0; li < sc->S.n_lights; ++li) {
             const unsigned long long quota = (unsigned long long)((double)g.gi_photon_count * lab_lightness(hl[li].intensity) / total_l);
             target += (quota + world - 1) / world;
             unsigned long long first = 0, emitted = 0;
             unsigned int stored = 0, before = 0;
-            CK(cudaMemcpy(&before, sc->pm_stored + map, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpyAsync(&before, sc->pm_stored + map, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->stream));
+            CK(cudaStreamSynchronize(sc->stream));
             stored = before;
             for (int round = 0; round < 256 && stored < target; ++round) {
                 unsigned long long need = target - stored, n;
@@ -3532,7 +3923,7 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
                 P.first = first;
                 P.count = n;
                 P.seed = mix64(cfg->seed ^ 0x70686f746f6e73ull);
-                const int blocks = (int)std::min<unsigned long long>((n + 127) / 128, 148ull * 16);
+                const int blocks = (int)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)sc->sm_count * 16);
                 k_photon_trace<<<blocks, 128, 0, sc->stream>>>(sc->S, sc->SF, P, m.ra, m.rb, sc->pm_stored + map, m.cap, sc->cnt);
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(&stored, sc->pm_stored + map, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->stream));
@@ -3543,12 +3934,13 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
             emitted_total += emitted;
             /* photons past the cumulative target are dropped (the reference overshoots by less than one path) */
             unsigned int keep = (unsigned int)std::min<unsigned long long>(std::min<unsigned long long>(stored, target + (unsigned long long)g.gi_path_length), m.cap);
-            CK(cudaMemcpy(sc->pm_stored + map, &keep, sizeof(unsigned int), cudaMemcpyHostToDevice));
+            CK(cudaMemcpyAsync(sc->pm_stored + map, &keep, sizeof(unsigned int), cudaMemcpyHostToDevice, sc->stream)); /* pageable: staged before the call returns */
             m.count = keep;
         }
     }
     Counters hc;
-    CK(cudaMemcpy(&hc, sc->cnt, sizeof(Counters), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(&hc, sc->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaStreamSynchronize(sc->stream));
     if (hc.overflow_csg) {
         return frt_set_error(FRT_ERR_OVERFLOW, "a photon met more than %d CSG crossings", FRT_CSG_CAP);
     }
@@ -3583,8 +3975,9 @@ frt_photons_export(frt_scene *sc, int map, void *dst, int dst_is_device)
     const size_t bytes = sizeof(float4) * (size_t)m.count;
     const cudaMemcpyKind kind = dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (m.count) {
-        CK(cudaMemcpy(dst, m.ra, bytes, kind));
-        CK(cudaMemcpy((char *)dst + bytes, m.rb, bytes, kind));
+        CK(cudaMemcpyAsync(dst, m.ra, bytes, kind, sc->stream));
+        CK(cudaMemcpyAsync((char *)dst + bytes, m.rb, bytes, kind, sc->stream));
+        CK(cudaStreamSynchronize(sc->stream));
     }
     return FRT_OK;
 }
@@ -3609,8 +4002,9 @@ frt_photons_import(frt_scene *sc, int map, const void *src, int64_t count, int s
     const size_t bytes = sizeof(float4) * (size_t)count;
     const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (count) {
-        CK(cudaMemcpy(m.ra, src, bytes, kind));
-        CK(cudaMemcpy(m.rb, (const char *)src + bytes, bytes, kind));
+        CK(cudaMemcpyAsync(m.ra, src, bytes, kind, sc->stream));
+        CK(cudaMemcpyAsync(m.rb, (const char *)src + bytes, bytes, kind, sc->stream));
+        CK(cudaStreamSynchronize(sc->stream)); /* the caller's buffer may go away (and a device source may be reused) after this call */
     }
     m.count = (unsigned int)count;
     return FRT_OK;
@@ -3645,8 +4039,8 @@ frt_photons_finish(frt_scene *sc)
         unsigned int hb[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
         unsigned int *db = nullptr;
         CK(cudaMalloc(&db, sizeof(hb)));
-        CK(cudaMemcpy(db, hb, sizeof(hb), cudaMemcpyHostToDevice));
-        k_pm_scale_bounds<<<148 * 4, 256, 0, sc->stream>>>(m.ra, m.rb, m.count, m.scaled ? 1.0f : scale, db);
+        CK(cudaMemcpyAsync(db, hb, sizeof(hb), cudaMemcpyHostToDevice, sc->stream)); /* pageable: staged before the call returns */
+        k_pm_scale_bounds<<<sc->sm_count * 4, 256, 0, sc->stream>>>(m.ra, m.rb, m.count, m.scaled ? 1.0f : scale, db);
         m.scaled = true;
         CK(cudaMemcpyAsync(hb, db, sizeof(hb), cudaMemcpyDeviceToHost, sc->stream));
         CK(cudaStreamSynchronize(sc->stream));
@@ -3674,11 +4068,11 @@ frt_photons_finish(frt_scene *sc)
         CK(cudaMalloc(&m.sa, sizeof(float4) * (size_t)m.count));
         CK(cudaMalloc(&m.sb, sizeof(float4) * (size_t)m.count));
         CK(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * n_cells, sc->stream));
-        k_pm_count<<<148 * 4, 256, 0, sc->stream>>>(V, m.ra, m.count, counts);
+        k_pm_count<<<sc->sm_count * 4, 256, 0, sc->stream>>>(V, m.ra, m.count, counts);
         k_pm_scan<<<1, 1024, 0, sc->stream>>>(counts, m.cell_start, (unsigned int)n_cells);
         /* counts becomes the per-cell write cursor */
         CK(cudaMemcpyAsync(counts, m.cell_start, sizeof(unsigned int) * n_cells, cudaMemcpyDeviceToDevice, sc->stream));
-        k_pm_scatter<<<148 * 4, 256, 0, sc->stream>>>(V, m.ra, m.rb, m.count, counts, m.sa, m.sb);
+        k_pm_scatter<<<sc->sm_count * 4, 256, 0, sc->stream>>>(V, m.ra, m.rb, m.count, counts, m.sa, m.sb);
         CK(cudaStreamSynchronize(sc->stream));
         CK(cudaGetLastError());
         cudaFree(counts);
@@ -3688,5 +4082,321 @@ frt_photons_finish(frt_scene *sc)
         m.view = V;
     }
     sc->pm_ready = true;
+    return FRT_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ several GPUs, one process */
+
+/*
+ * render_multi()'s row fan-out (renderer.c:244-281: a pthread pool, one job per image row, every thread on its own deep
+ * copy of the World) across the GPUs of one node, behind the same call: the scene is replicated -- uploaded, or its
+ * light cache rebuilt, once per device, concurrently -- device k renders the row blocks b with b % n == k on its own
+ * host thread and stream, and writes them straight into the caller's Canvas.arr (a block of 4 rows is one contiguous
+ * run of the canvas, so the rows need no packing, no collective and no reorder).  The photon pass shards the emission
+ * the same way and exchanges the stored photons device to device (cudaMemcpyPeerAsync over NVLink) before every device
+ * bins the full set.  One process per GPU over NCCL (fast_ray_tracer_b200/dist.py) remains the launch shape of bench.py.
+ */
+struct frt_multi {
+    std::vector<int> devices;
+    std::vector<frt_scene *> scenes;
+};
+
+template <typename Fn>
+static int
+multi_for_each(frt_multi *m, Fn fn)
+{
+    const int n = (int)m->devices.size();
+    std::vector<int> rc(n, FRT_OK);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (int k = 0; k < n; ++k) {
+        th.emplace_back([&, k]() {
+            rc[k] = fn(k);
+            if (rc[k] != FRT_OK) {
+                msg[k] = frt_last_error(); /* the worker's thread-local message */
+            }
+        });
+    }
+    for (auto &t : th) {
+        t.join();
+    }
+    for (int k = 0; k < n; ++k) {
+        if (rc[k] != FRT_OK) {
+            return frt_set_error(rc[k], "device %d: %s", m->devices[k], msg[k].c_str());
+        }
+    }
+    return FRT_OK;
+}
+
+extern "C" void
+frt_multi_destroy(frt_multi *m)
+{
+    if (m == nullptr) {
+        return;
+    }
+    for (frt_scene *s : m->scenes) {
+        frt_scene_destroy(s);
+    }
+    delete m;
+}
+
+extern "C" int
+frt_multi_create(const frt_scene_desc *desc, const int32_t *devices, int n_devices, const frt_light_gen *gens, int n_gens, frt_multi **out)
+{
+    if (out == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_multi_create: null out pointer");
+    }
+    *out = nullptr;
+    int ndev = frt_device_count();
+    if (ndev <= 0) {
+        return frt_set_error(FRT_ERR_CUDA, "no CUDA device is visible: the B200 core has no CPU fallback");
+    }
+    frt_multi *m = new frt_multi();
+    if (devices == nullptr || n_devices <= 0) { /* all of them */
+        for (int k = 0; k < ndev; ++k) {
+            m->devices.push_back(k);
+        }
+    } else {
+        for (int k = 0; k < n_devices; ++k) {
+            if (devices[k] < 0 || devices[k] >= ndev || std::count(m->devices.begin(), m->devices.end(), devices[k])) {
+                delete m;
+                return frt_set_error(FRT_ERR_ARG, "frt_multi_create: device %d of %d (or listed twice)", devices[k], ndev);
+            }
+            m->devices.push_back(devices[k]);
+        }
+    }
+    m->scenes.assign(m->devices.size(), nullptr);
+    for (int a : m->devices) { /* photon shards travel device to device; without peer access the copies stage through the host */
+        for (int b : m->devices) {
+            int can = 0;
+            if (a != b && cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can && cudaSetDevice(a) == cudaSuccess) {
+                if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) {
+                    cudaGetLastError(); /* already enabled */
+                }
+            }
+        }
+    }
+    int rc = multi_for_each(m, [&](int k) { return scene_create(desc, m->devices[k], gens, n_gens, &m->scenes[k]); });
+    if (rc != FRT_OK) {
+        frt_multi_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return FRT_OK;
+}
+
+extern "C" int
+frt_multi_device_count(const frt_multi *m)
+{
+    return m == nullptr ? 0 : (int)m->devices.size();
+}
+
+extern "C" frt_scene *
+frt_multi_scene(frt_multi *m, int k)
+{
+    return (m == nullptr || k < 0 || k >= (int)m->scenes.size()) ? nullptr : m->scenes[k];
+}
+
+extern "C" int
+frt_multi_render(frt_multi *m, const frt_render_cfg *cfg, double *canvas_rgba, frt_stats *stats)
+{
+    if (m == nullptr || cfg == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_multi_render: null argument");
+    }
+    const int n = (int)m->devices.size();
+    std::vector<frt_stats> st(n);
+    int rc = multi_for_each(m, [&](int k) {
+        frt_render_cfg c = *cfg;
+        c.device = m->devices[k];
+        c.rank = k;
+        c.world = n;
+        return frt_render(m->scenes[k], &c, canvas_rgba, &st[k]);
+    });
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    if (stats != nullptr) {
+        frt_stats t = st[0];
+        for (int k = 1; k < n; ++k) {
+            const frt_stats &s = st[k];
+            t.frame_ms = std::max(t.frame_ms, s.frame_ms); /* the devices run side by side */
+            t.light_ms = std::max(t.light_ms, s.light_ms);
+            t.download_ms = std::max(t.download_ms, s.download_ms);
+            t.rays_primary += s.rays_primary;
+            t.rays_secondary += s.rays_secondary;
+            t.rays_shadow += s.rays_shadow;
+            t.rays_gather += s.rays_gather;
+            t.hits_shaded += s.hits_shaded;
+            t.light_launches += s.light_launches;
+            t.kernel_launches += s.kernel_launches;
+            t.shadow_nodes += s.shadow_nodes;
+            t.overflow += s.overflow;
+            t.light_flops += s.light_flops;
+            t.shadow_deferred += s.shadow_deferred;
+            t.shadow_mismatch += s.shadow_mismatch;
+            for (int j = 0; j < 10; ++j) {
+                t.shadow_reasons[j] += s.shadow_reasons[j];
+            }
+            t.rows_rendered += s.rows_rendered;
+        }
+        *stats = t;
+    }
+    return FRT_OK;
+}
+
+/* trace_photons (photon_tracer.c:203) on every device: shard k of n is emitted on device k, then every device receives
+ * the other shards (peer copies) and builds the same lookup grid from the full set. */
+extern "C" int
+frt_multi_photons(frt_multi *m, const frt_photon_cfg *cfg, frt_stats *stats)
+{
+    if (m == nullptr || cfg == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_multi_photons: null argument");
+    }
+    const int n = (int)m->devices.size();
+    std::vector<frt_stats> st(n);
+    int rc = multi_for_each(m, [&](int k) {
+        frt_photon_cfg c = *cfg;
+        c.device = m->devices[k];
+        c.rank = k;
+        c.world = n;
+        memset(&st[k], 0, sizeof(frt_stats));
+        return frt_photons_emit(m->scenes[k], &c, &st[k]);
+    });
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    if (n > 1) {
+        for (int map = 0; map < 2; ++map) {
+            std::vector<size_t> cnt(n), off(n + 1, 0);
+            for (int k = 0; k < n; ++k) {
+                cnt[k] = m->scenes[k]->pm[map].count;
+                off[k + 1] = off[k] + cnt[k];
+            }
+            const size_t total = off[n];
+            if (total == 0) {
+                continue;
+            }
+            rc = multi_for_each(m, [&](int d) {
+                frt_scene *sc = m->scenes[d];
+                CK(cudaSetDevice(sc->device));
+                float4 *merged = nullptr;
+                CK(cudaMalloc(&merged, sizeof(float4) * 2 * total));
+                cudaError_t e = cudaSuccess;
+                for (int k = 0; k < n && e == cudaSuccess; ++k) {
+                    const frt_scene::PMap &src = m->scenes[k]->pm[map];
+                    if (cnt[k] == 0) continue;
+                    e = cudaMemcpyPeerAsync(merged + off[k], sc->device, src.ra, m->devices[k], sizeof(float4) * cnt[k], sc->stream);
+                    if (e == cudaSuccess) {
+                        e = cudaMemcpyPeerAsync(merged + total + off[k], sc->device, src.rb, m->devices[k], sizeof(float4) * cnt[k], sc->stream);
+                    }
+                }
+                if (e == cudaSuccess) e = cudaStreamSynchronize(sc->stream);
+                int r = FRT_OK;
+                if (e != cudaSuccess) {
+                    r = frt_set_error(FRT_ERR_CUDA, "photon exchange: %s", cudaGetErrorString(e));
+                }
+                sc->pm_merged[map] = merged;
+                return r;
+            });
+            /* every device has read every shard: only now may the shards be replaced */
+            int rc2 = multi_for_each(m, [&](int d) {
+                frt_scene *sc = m->scenes[d];
+                CK(cudaSetDevice(sc->device));
+                int r = FRT_OK;
+                if (rc == FRT_OK && sc->pm_merged[map] != nullptr) {
+                    r = frt_photons_import(sc, map, sc->pm_merged[map], (int64_t)total, 1);
+                }
+                cudaFree(sc->pm_merged[map]);
+                sc->pm_merged[map] = nullptr;
+                return r;
+            });
+            if (rc != FRT_OK) return rc;
+            if (rc2 != FRT_OK) return rc2;
+        }
+    }
+    rc = multi_for_each(m, [&](int k) { return frt_photons_finish(m->scenes[k]); });
+    if (rc != FRT_OK) {
+        return rc;
+    }
+    if (stats != nullptr) {
+        memset(stats, 0, sizeof(*stats));
+        for (int k = 0; k < n; ++k) {
+            stats->rays_photon += st[k].rays_photon;
+        }
+        stats->photons_stored[0] = m->scenes[0]->pm[0].count;
+        stats->photons_stored[1] = m->scenes[0]->pm[1].count;
+    }
+    return FRT_OK;
+}
+
+/*
+ * pm_irradiance_estimate (pm.c:91-156) for n positions against the scene's photon map `map` (0 caustic, 1 global), with
+ * the radius / photon count / cone filter of the scene's configuration: the unit-level twin of what k_knn does inside a
+ * frame, without the callers' rescaling (renderer.c:845, :878).  pos / normal: n x 3 doubles (positions are rounded to
+ * FP32 like every request of a frame); irrad: n x 3 doubles; found: n ints, the function's return value per position.
+ */
+extern "C" int
+frt_photons_estimate(frt_scene *sc, int map, int64_t n, const double *pos, const double *normal, double *irrad, int32_t *found)
+{
+    if (sc == nullptr || map < 0 || map > 1 || n < 0 || n > 0x3fffffff || (n > 0 && (pos == nullptr || normal == nullptr || irrad == nullptr))) {
+        return frt_set_error(FRT_ERR_ARG, "frt_photons_estimate: bad argument");
+    }
+    if (!sc->pm_ready) {
+        return frt_set_error(FRT_ERR_ARG, "frt_photons_estimate: no photon map was built (frt_photons_emit / _import, then frt_photons_finish)");
+    }
+    if (n == 0) {
+        return FRT_OK;
+    }
+    CK(cudaSetDevice(sc->device));
+    const frt_config &g = sc->cfg;
+    GIParams G{};
+    G.usteps = G.vsteps = 1;
+    G.n_photons = g.gi_irradiance_estimate_num;
+    G.radius = (float)g.gi_irradiance_estimate_radius;
+    G.cone_k = (float)g.gi_irradiance_estimate_cone_filter_k;
+    if (G.n_photons <= 0 || G.n_photons > FRT_KNN_CAP / 2) {
+        return frt_set_error(FRT_ERR_ARG, "irradiance-estimate-num %d is outside 1..%d", G.n_photons, FRT_KNN_CAP / 2);
+    }
+    std::vector<GQuery> hq((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        GQuery &q = hq[(size_t)i];
+        q.x = (float)pos[3 * i];
+        q.y = (float)pos[3 * i + 1];
+        q.z = (float)pos[3 * i + 2];
+        q.ex = (float)normal[3 * i];
+        q.ey = (float)normal[3 * i + 1];
+        q.ez = (float)normal[3 * i + 2];
+        q.wr = q.wg = q.wb = 1.0f;
+        q.target = (unsigned int)i | (map == 0 ? 0x40000000u : 0u);
+    }
+    GQuery *dq = nullptr;
+    unsigned int *dn = nullptr;
+    double *dacc = nullptr;
+    int *dfound = nullptr;
+    const unsigned int un = (unsigned int)n;
+    cudaError_t e = cudaMalloc(&dq, sizeof(GQuery) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&dn, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&dacc, sizeof(double) * 3 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc(&dfound, sizeof(int) * (size_t)n);
+    cudaStream_t s = sc->stream;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dq, hq.data(), sizeof(GQuery) * (size_t)n, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dn, &un, sizeof(un), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dacc, 0, sizeof(double) * 3 * (size_t)n, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dfound, 0, sizeof(int) * (size_t)n, s);
+    if (e == cudaSuccess) {
+        k_knn<<<sc->sm_count * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, dq, dn, un, dacc, dacc, dfound);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(irrad, dacc, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && found != nullptr) e = cudaMemcpyAsync(found, dfound, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(dq);
+    cudaFree(dn);
+    cudaFree(dacc);
+    cudaFree(dfound);
+    if (e != cudaSuccess) {
+        return frt_set_error(FRT_ERR_CUDA, "frt_photons_estimate: %s", cudaGetErrorString(e));
+    }
     return FRT_OK;
 }

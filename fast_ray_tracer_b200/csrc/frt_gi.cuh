@@ -616,7 +616,8 @@ knn_key(float v, float scale)
 }
 
 __device__ __forceinline__ unsigned int
-warp_select_key(const float *d2, unsigned int count, unsigned int want, float scale, unsigned int *hist, int lane)
+warp_select_key(const float *d2, unsigned int count, unsigned int want, float scale, unsigned int *hist, int lane,
+                unsigned int *take_from_bin = nullptr, unsigned int *bin_size = nullptr)
 {
     unsigned int prefix = 0, remaining = want; /* remaining: rank of the target among the keys that match `prefix` */
     for (int shift = 16; shift >= 0; shift -= 8) {
@@ -666,9 +667,31 @@ warp_select_key(const float *d2, unsigned int count, unsigned int want, float sc
         before = __shfl_sync(0xffffffffu, before, owner < 0 ? 0 : owner);
         prefix |= digit << shift;
         remaining -= before;
+        if (shift == 0 && bin_size != nullptr) {
+            *bin_size = hist[digit]; /* candidates that share the selected 24-bit key */
+        }
         __syncwarp();
     }
+    if (take_from_bin != nullptr) {
+        *take_from_bin = remaining; /* how many of them belong to the `want` smallest */
+    }
     return prefix;
+}
+
+/* Exact membership among the candidates that share the selected key (a few, and rarely more than are wanted): candidate k
+ * belongs to the n nearest iff fewer than `take` of them precede it in (distance, list position) order. */
+__device__ __forceinline__ bool
+knn_tie_kept(const float *d2, unsigned int count, unsigned int k, unsigned int T, float scale, unsigned int take)
+{
+    const float v = d2[k];
+    unsigned int rank = 0;
+    for (unsigned int j = 0; j < count; ++j) {
+        const float u = d2[j];
+        if (knn_key(u, scale) == T && (u < v || (u == v && j < k))) {
+            ++rank;
+        }
+    }
+    return rank < take;
 }
 
 /*
@@ -683,7 +706,7 @@ warp_select_key(const float *d2, unsigned int count, unsigned int want, float sc
  */
 __global__ void __launch_bounds__(FRT_KNN_WARPS * 32)
 k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, const unsigned int *n_queries, unsigned int qcap,
-      double *__restrict__ acc_amb, double *__restrict__ acc_fg)
+      double *__restrict__ acc_amb, double *__restrict__ acc_fg, int *__restrict__ found_out)
 {
     __shared__ float s_d2[FRT_KNN_WARPS][FRT_KNN_CAP];
     __shared__ unsigned int s_idx[FRT_KNN_WARPS][FRT_KNN_CAP];
@@ -820,16 +843,19 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
         unsigned int T = 0xffffffu;
         unsigned int found = count;
         const bool select = count > want_n;
+        unsigned int take = 0, bin = 0;
         if (select) {
-            T = warp_select_key(d2, count, want_n, scale, hist, lane);
+            T = warp_select_key(d2, count, want_n, scale, hist, lane, &take, &bin);
             found = want_n;
         }
+        const bool ties = select && bin > take; /* more candidates share the n-th key than fit: order them exactly */
         float sr = 0.f, sg = 0.f, sb = 0.f, far2 = 0.f;
         if (found >= 8) {
             const float inv_kr = 1.0f / (G.cone_k * G.radius);
             for (unsigned int k = lane; k < count; k += 32) {
                 const float v = d2[k];
-                if (knn_key(v, scale) <= T) {
+                const unsigned int key = knn_key(v, scale);
+                if (key < T || (key == T && (!ties || knn_tie_kept(d2, count, k, T, scale, take)))) {
                     far2 = fmaxf(far2, v);
                     const unsigned int id = idx[k];
                     const float4 pw = __ldg(M.b + id);
@@ -853,11 +879,15 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
                 far2 = fmaxf(far2, __shfl_xor_sync(0xffffffffu, far2, o));
             }
         }
+        if (lane == 0 && found_out != nullptr) {
+            found_out[q.target & 0x3fffffffu] = (int)found; /* frt_photons_estimate: pm_irradiance_estimate's return value */
+        }
         if (lane == 0 && found >= 8) {
             /* np.dist2[0] (pm.c:147): the search radius^2 until the heap of n photons is full, then the n-th distance^2 */
             const double r2_density = (select || r2cur < R2) ? (double)far2 : (double)R2;
             const double density = 1.0 / ((1.0 - 2.0 / (3.0 * (double)G.cone_k)) * (M_PI * r2_density));
-            const double rescale = caustic ? 100.0 / (double)found : 10.0 * (double)G.n_photons / (double)found;
+            /* the callers' rescale (renderer.c:845, :878); frt_photons_estimate returns the estimate as pm.c does */
+            const double rescale = found_out != nullptr ? 1.0 : (caustic ? 100.0 / (double)found : 10.0 * (double)G.n_photons / (double)found);
             const double f = density * rescale;
             double *acc = ((q.target & 0x80000000u) ? acc_fg : acc_amb) + 3 * (size_t)(q.target & 0x3fffffffu);
             const double vr = f * (double)sr * (double)q.wr, vg = f * (double)sg * (double)q.wg, vb = f * (double)sb * (double)q.wb;

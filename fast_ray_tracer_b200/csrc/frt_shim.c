@@ -143,6 +143,16 @@ struct flat {
     VEC(double) light_points;
     VEC(double) pixel_samples;
     struct ptrmap mat_map, pat_map, tex_map;
+    /* area lights whose sample cache is to be rebuilt on the device (frt_scene_create_gen): their region of light_points
+     * is reserved but not written unless the rebuilt sets turn out to differ from the reference's */
+    struct lazy_light {
+        int32_t light;
+        Light l;
+        uint64_t drand48_state;
+    } lazy[16];
+    int n_lazy;
+    uint64_t draws; /* drand48 draws the light constructors seen so far have made (light.c:100-191, sampler.c:510-523) */
+    bool gen_enabled;
 };
 
 static void
@@ -510,11 +520,6 @@ flatten_light(struct flat *f, Light l)
     q.point_offset = (int64_t)(f->light_points.n / 3);
     /* the whole cache at once (157 MB for the shipped Cornell light): one reservation, no per-value growth check */
     const size_t total = 3 * (size_t)l->surface_points_cache_len * (size_t)l->num_samples;
-    if (f->light_points.n + total > f->light_points.cap) {
-        f->light_points.cap = f->light_points.n + total;
-        f->light_points.p = (double *)xrealloc(f->light_points.p, f->light_points.cap * sizeof(double));
-    }
-    double *dst = f->light_points.p + f->light_points.n;
     for (size_t s = 0; s < l->surface_points_cache_len; ++s) {
         if (l->surface_points_cache[s].points_num != l->num_samples) {
             fprintf(stderr, "frt_shim: light sample set %zu has %zu points, expected %zu\n", s, l->surface_points_cache[s].points_num,
@@ -522,19 +527,74 @@ flatten_light(struct flat *f, Light l)
             exit(72);
         }
     }
-    /* 65 535 separately allocated sets of 32-byte points -> one array of 24-byte points.  (Measured here: 125 ms for the
-     * shipped Cornell light, of which 110 ms are first-touch page faults of the fresh 157 MB array in this VM -- 8 copy
-     * threads changed nothing; streaming the sets through a warm page-locked staging buffer is the next step, DESIGN.md.) */
-    struct copy_job job = { l, dst, 0, l->surface_points_cache_len };
-    copy_light_sets(&job);
+    /* The constructors of jittered area / circle lights are the program's drand48 consumers before render_multi()
+     * (sampler_2d draws one table when it is created, then one per cached set: light.c:166-171, sampler.c:510-523), in
+     * world order.  An area light's cache is a pure function of the generator state in front of its first set, so the
+     * core rebuilds it on the device and compares a few sets with the reference's bit for bit (frt_scene_create_gen);
+     * the 157 MB of the shipped Cornell light are then neither repacked here (115 ms) nor copied over PCIe. */
+    bool lazy = false;
+    if ((l->type == AREA_LIGHT && l->u.area.jitter) || (l->type == CIRCLE_LIGHT && l->u.circle.jitter)) {
+        const uint64_t per_set = 2 * (uint64_t)q.usteps * q.vsteps + q.usteps + q.vsteps;
+        if (l->type == AREA_LIGHT && f->gen_enabled && f->n_lazy < 16 && q.cache_len >= 8 && q.usteps <= 64 && q.vsteps <= 64 &&
+            (size_t)q.usteps * q.vsteps == l->num_samples) {
+            lazy = true;
+            f->lazy[f->n_lazy].light = (int32_t)f->lights.n;
+            f->lazy[f->n_lazy].l = l;
+            f->lazy[f->n_lazy].drand48_state = frt_drand48_advance(0, f->draws + per_set);
+            f->n_lazy += 1;
+        }
+        f->draws += per_set * ((uint64_t)q.cache_len + 1);
+    }
+    if (f->light_points.n + total > f->light_points.cap) {
+        /* calloc: a large block comes straight from mmap, so the pages of a region that is never written (a lazy light's)
+         * are never touched */
+        double *np = (double *)calloc(f->light_points.n + total, sizeof(double));
+        if (np == NULL) {
+            fprintf(stderr, "frt_shim: out of memory\n");
+            exit(70);
+        }
+        if (f->light_points.n) {
+            memcpy(np, f->light_points.p, f->light_points.n * sizeof(double));
+        }
+        free(f->light_points.p);
+        f->light_points.p = np;
+        f->light_points.cap = f->light_points.n + total;
+    }
+    if (!lazy) {
+        /* separately allocated sets of 32-byte points -> one array of 24-byte points */
+        struct copy_job job = { l, f->light_points.p + f->light_points.n, 0, l->surface_points_cache_len };
+        copy_light_sets(&job);
+    }
     f->light_points.n += total;
     *VEC_PUSH(f->lights, frt_light) = q;
+}
+
+/* a lazy light's sets after all: the rebuilt cache differed from the reference's (FRT_ERR_MISMATCH) */
+static void
+materialize_lazy_lights(struct flat *f)
+{
+    for (int k = 0; k < f->n_lazy; ++k) {
+        Light l = f->lazy[k].l;
+        struct copy_job job = { l, f->light_points.p + 3 * (size_t)f->lights.p[f->lazy[k].light].point_offset, 0, l->surface_points_cache_len };
+        copy_light_sets(&job);
+    }
+    f->n_lazy = 0;
 }
 
 static void
 flatten_world(struct flat *f, Camera cam, World w, size_t usteps, size_t vsteps, bool jitter, frt_scene_desc *d)
 {
     memset(f, 0, sizeof(*f));
+    {
+        const char *e = getenv("FRT_LIGHT_GEN");
+        f->gen_enabled = !(e != NULL && e[0] == '0') && !(getenv("FRT_DUMP_SCENE") != NULL && *getenv("FRT_DUMP_SCENE"));
+    }
+    /* the generated main() builds the camera before the lights (yaml_parser.py:182-186); a jittered aperture's sampler
+     * has drawn one table by then (camera.c:170-175) */
+    if (cam->aperture.jitter && cam->aperture.sampler.steps_by_dimension != NULL) {
+        const uint64_t au = cam->aperture.sampler.steps_by_dimension[0], av = cam->aperture.sampler.steps_by_dimension[1];
+        f->draws = 2 * au * av + au + av;
+    }
     frt_xform *ident = VEC_PUSH(f->xforms, frt_xform);
     rows3x4(ident->inv, MATRIX_IDENTITY);
 
@@ -651,44 +711,101 @@ env_long(const char *name, long dflt)
     return (s == NULL || *s == '\0') ? dflt : strtol(s, NULL, 10);
 }
 
-/* the scene and the Canvas of the last frame: its pixels are still on the device when main() asks for the PPM file */
-static frt_scene *g_last_scene;
+/* the scene(s) and the Canvas of the last frame: with one device its pixels are still there when main() asks for the PPM */
+static frt_multi *g_last_multi;
 static Canvas g_last_image;
-static bool g_last_full_frame;
+static uint64_t g_last_digest;
 
 static void
 drop_last_scene(void)
 {
-    if (g_last_scene != NULL) {
-        frt_scene_destroy(g_last_scene);
-        g_last_scene = NULL;
+    if (g_last_multi != NULL) {
+        frt_multi_destroy(g_last_multi);
+        g_last_multi = NULL;
         g_last_image = NULL;
     }
 }
 
-/* scene kept between trace_photons() and render_multi(): photons live on the device */
-static frt_scene *g_scene;
-static World g_scene_world;
+/* sampled digest of a canvas (every 16th pixel): frt_shim_write_ppm_file only encodes the device copy of the frame when
+ * the host Canvas still holds what render_multi() returned */
+static uint64_t
+canvas_digest(Canvas c)
+{
+    uint64_t acc = 0x9E3779B97F4A7C15ULL;
+    const size_t n = c->width * c->height;
+    for (size_t i = 0; i < n; i += 16) {
+        for (int k = 0; k < 3; ++k) {
+            uint64_t bits;
+            memcpy(&bits, &c->arr[i][k], sizeof(bits));
+            acc = (acc ^ bits) * 0x100000001B3ULL + i;
+        }
+    }
+    return acc;
+}
+
 /* a trace_photons() request waiting for render_multi() (see trace_photons below) */
 static bool g_photons_pending, g_photons_caustic, g_photons_global;
 static World g_photons_world;
 
+static double
+ms_since(const struct timespec *t0)
+{
+    struct timespec t1;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return 1e3 * (double)(t1.tv_sec - t0->tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0->tv_nsec);
+}
+
+/* FRT_DEVICES: "all" (default), a count ("4"), or a list of ordinals ("0,2,3"); FRT_DEVICE=n is the one-device spelling */
+static int
+pick_devices(int32_t *out, int cap)
+{
+    const int visible = frt_device_count();
+    const char *e = getenv("FRT_DEVICES");
+    int n = 0;
+    if (e == NULL || *e == '\0') {
+        const char *one = getenv("FRT_DEVICE");
+        if (one != NULL && *one != '\0') {
+            out[0] = (int32_t)strtol(one, NULL, 10);
+            return 1;
+        }
+        e = "all";
+    }
+    if (strcmp(e, "all") == 0) {
+        for (n = 0; n < visible && n < cap; ++n) out[n] = n;
+    } else if (strchr(e, ',') != NULL) {
+        const char *p = e;
+        while (*p != '\0' && n < cap) {
+            char *end;
+            long v = strtol(p, &end, 10);
+            if (end == p) break;
+            out[n++] = (int32_t)v;
+            p = (*end == ',') ? end + 1 : end;
+        }
+    } else {
+        long want = strtol(e, NULL, 10);
+        for (n = 0; n < want && n < visible && n < cap; ++n) out[n] = n;
+    }
+    if (n == 0) {
+        out[0] = 0;
+        n = 1;
+    }
+    return n;
+}
 
 static Canvas
 render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
 {
     struct flat f;
     frt_scene_desc d;
-    struct timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
+    struct timespec t0, t_all;
+    clock_gettime(CLOCK_MONOTONIC, &t_all);
+    t0 = t_all;
     flatten_world(&f, cam, w, usteps, vsteps, jitter, &d);
-    clock_gettime(CLOCK_MONOTONIC, &t1);
     /* the one walk over the finished World that replaces world_copy x threads */
-    printf("FRT_B200_FLATTEN_MS %.3f (%d nodes, %lld light points)\n",
-           1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec), (int)d.n_nodes, (long long)d.n_light_points);
+    printf("FRT_B200_FLATTEN_MS %.3f (%d nodes, %lld light points, %d light caches left to the device)\n", ms_since(&t0), (int)d.n_nodes,
+           (long long)d.n_light_points, f.n_lazy);
 
     Canvas image = canvas_alloc(cam->hsize, cam->vsize, false, NULL); /* renderer.c:250 */
-    memset(image->arr, 0, cam->hsize * cam->vsize * sizeof(Color));
 
     const char *dump = getenv("FRT_DUMP_SCENE");
     if (dump != NULL && *dump != '\0') {
@@ -697,74 +814,109 @@ render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
         }
     }
     if (env_long("FRT_DUMP_ONLY", 0)) {
+        memset(image->arr, 0, cam->hsize * cam->vsize * sizeof(Color));
         flat_free(&f);
         return image;
     }
 
-    int device = (int)env_long("FRT_DEVICE", 0);
-    frt_scene *scene = g_scene;
-    if (scene == NULL || g_scene_world != w) {
-        if (frt_scene_create(&d, device, &scene) != FRT_OK) {
-            die("frt_scene_create");
+    int32_t devices[64];
+    const int n_dev = pick_devices(devices, 64);
+
+    /* light caches rebuilt on the device, checked against a few of the sets the reference built (first, last, spread) */
+    frt_light_gen gens[16];
+    double *verify_buf = NULL;
+    if (f.n_lazy > 0) {
+        size_t words = 0;
+        for (int k = 0; k < f.n_lazy; ++k) {
+            words += (size_t)FRT_GEN_VERIFY_MAX * 3 * f.lazy[k].l->num_samples;
+        }
+        verify_buf = (double *)xrealloc(NULL, words * sizeof(double));
+        double *vb = verify_buf;
+        for (int k = 0; k < f.n_lazy; ++k) {
+            Light l = f.lazy[k].l;
+            frt_light_gen *g = &gens[k];
+            memset(g, 0, sizeof(*g));
+            g->light = f.lazy[k].light;
+            g->drand48_state = f.lazy[k].drand48_state;
+            const size_t len = l->surface_points_cache_len;
+            g->n_verify = (int32_t)(len < FRT_GEN_VERIFY_MAX ? len : FRT_GEN_VERIFY_MAX);
+            for (int v = 0; v < g->n_verify; ++v) {
+                const size_t set = g->n_verify == 1 ? 0 : (size_t)v * (len - 1) / (size_t)(g->n_verify - 1);
+                struct copy_job job = { l, vb - set * 3 * l->num_samples, set, set + 1 };
+                copy_light_sets(&job);
+                g->verify_set[v] = (int32_t)set;
+                g->verify_points[v] = vb;
+                vb += 3 * l->num_samples;
+            }
         }
     }
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    frt_multi *multi = NULL;
+    int rc = frt_multi_create(&d, devices, n_dev, f.n_lazy ? gens : NULL, f.n_lazy, &multi);
+    if (rc == FRT_ERR_MISMATCH) {
+        /* another generator state than the constructors' order implies (or another sampler): take the reference's sets */
+        printf("FRT_B200_LIGHT_GEN mismatch (%s): uploading the host caches\n", frt_last_error());
+        materialize_lazy_lights(&f);
+        rc = frt_multi_create(&d, devices, n_dev, NULL, 0, &multi);
+    } else if (f.n_lazy > 0 && rc == FRT_OK) {
+        printf("FRT_B200_LIGHT_GEN %d light caches rebuilt on the device, %d sets each compared bit for bit\n", f.n_lazy, (int)gens[0].n_verify);
+    }
+    free(verify_buf);
+    if (rc != FRT_OK) {
+        die("frt_multi_create");
+    }
+    printf("FRT_B200_CREATE_MS %.3f (%d devices)\n", ms_since(&t0), frt_multi_device_count(multi));
 
     if (g_photons_pending && g_photons_world == w) {
         frt_photon_cfg pc;
         memset(&pc, 0, sizeof(pc));
-        pc.device = device;
-        pc.rank = 0;
-        pc.world = 1;
         pc.populate_caustic = g_photons_caustic ? 1 : 0;
         pc.populate_global = g_photons_global ? 1 : 0;
         pc.seed = (uint64_t)env_long("FRT_SEED", 0);
         frt_stats ps;
         memset(&ps, 0, sizeof(ps));
-        if (frt_photons_emit(scene, &pc, &ps) != FRT_OK) {
-            die("frt_photons_emit");
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        if (frt_multi_photons(multi, &pc, &ps) != FRT_OK) {
+            die("frt_multi_photons");
         }
-        if (frt_photons_finish(scene) != FRT_OK) {
-            die("frt_photons_finish");
-        }
-        printf("FRT_B200_PHOTONS emitted %llu stored caustic %llu global %llu\n", (unsigned long long)ps.rays_photon,
-               (unsigned long long)ps.photons_stored[0], (unsigned long long)ps.photons_stored[1]);
+        printf("FRT_B200_PHOTONS emitted %llu stored caustic %llu global %llu in %.3f ms\n", (unsigned long long)ps.rays_photon,
+               (unsigned long long)ps.photons_stored[0], (unsigned long long)ps.photons_stored[1], ms_since(&t0));
         g_photons_pending = false;
     }
 
     frt_render_cfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.device = device;
-    cfg.rank = (int32_t)env_long("FRT_RANK", 0);
-    cfg.world = (int32_t)env_long("FRT_WORLD", 1);
     cfg.usteps = (int32_t)usteps;
     cfg.vsteps = (int32_t)vsteps;
     cfg.jitter = jitter ? 1 : 0;
     cfg.seed = (uint64_t)env_long("FRT_SEED", 0);
-    cfg.flags = FRT_FLAG_COUNT_RAYS | (env_long("FRT_NO_PRUNE", 0) ? FRT_FLAG_NO_PRUNE : 0);
+    cfg.flags = (env_long("FRT_COUNT_RAYS", 0) ? FRT_FLAG_COUNT_RAYS : 0) | (env_long("FRT_NO_PRUNE", 0) ? FRT_FLAG_NO_PRUNE : 0);
 
     frt_stats st;
-    if (frt_render(scene, &cfg, (double *)image->arr, &st) != FRT_OK) {
-        die("frt_render");
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (frt_multi_render(multi, &cfg, (double *)image->arr, &st) != FRT_OK) {
+        die("frt_multi_render");
     }
-    printf("FRT_B200_FRAME_MS %.3f\n", st.frame_ms);
-    printf("FRT_B200_RAYS primary %llu secondary %llu shadow %llu gather %llu\n",
-           (unsigned long long)st.rays_primary, (unsigned long long)st.rays_secondary,
-           (unsigned long long)st.rays_shadow, (unsigned long long)st.rays_gather);
-    fflush(stdout);
+    printf("FRT_B200_FRAME_MS %.3f (render call %.3f ms, canvas download %.3f ms)\n", st.frame_ms, ms_since(&t0), st.download_ms);
+    if (cfg.flags & FRT_FLAG_COUNT_RAYS) {
+        printf("FRT_B200_RAYS primary %llu secondary %llu shadow %llu gather %llu\n",
+               (unsigned long long)st.rays_primary, (unsigned long long)st.rays_secondary,
+               (unsigned long long)st.rays_shadow, (unsigned long long)st.rays_gather);
+    }
 
     /* keep the frame on the device until the next one (or exit): frt_shim_write_ppm_file encodes it there */
     static bool registered;
     drop_last_scene();
-    g_last_scene = scene;
+    g_last_multi = multi;
     g_last_image = image;
-    g_last_full_frame = cfg.world <= 1;
+    g_last_digest = canvas_digest(image);
     if (!registered) {
         atexit(drop_last_scene);
         registered = true;
     }
-    g_scene = NULL;
-    g_scene_world = NULL;
     flat_free(&f);
+    printf("FRT_B200_RENDER_MULTI_MS %.3f\n", ms_since(&t_all));
+    fflush(stdout);
     return image;
 }
 
@@ -779,13 +931,22 @@ render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
 int
 frt_shim_write_ppm_file(Canvas c, const bool use_scaling, const char *file_path)
 {
-    if (c == NULL || c != g_last_image || g_last_scene == NULL || !g_last_full_frame || file_path == NULL) {
-        return -1;
+    if (c == NULL || c != g_last_image || g_last_multi == NULL || file_path == NULL || canvas_digest(c) != g_last_digest) {
+        return -1; /* not the frame render_multi() returned, or the caller changed it since */
     }
     size_t cap = frt_ppm16_size((int)c->width, (int)c->height), len = 0;
     unsigned char *buf = (unsigned char *)malloc(cap);
     double ms = 0.0;
-    if (buf == NULL || frt_canvas_encode_ppm16(g_last_scene, use_scaling ? 1 : 0, buf, cap, &len, &ms) != FRT_OK) {
+    int rc;
+    if (buf == NULL) {
+        die("out of memory");
+    }
+    if (frt_multi_device_count(g_last_multi) == 1) {
+        rc = frt_canvas_encode_ppm16(frt_multi_scene(g_last_multi, 0), use_scaling ? 1 : 0, buf, cap, &len, &ms);
+    } else { /* every device holds its own rows only: encode the assembled host canvas on device 0 */
+        rc = frt_encode_ppm16((const double *)c->arr, (int)c->width, (int)c->height, use_scaling ? 1 : 0, 0, buf, cap, &len, &ms);
+    }
+    if (rc != FRT_OK) {
         free(buf);
         die("frt_canvas_encode_ppm16");
     }

@@ -25,8 +25,12 @@ AREA_LIGHT = 0
 def _jump(n: int):
     """(A_n, C_n) with X_{k+n} = A_n * X_k + C_n (mod 2^48)."""
     a, c = 1, 0
-    for _ in range(n):
-        a, c = (a * _A) & _MASK, (c * _A + _C) & _MASK
+    pa, pc = _A, _C  # the map of 2^b steps
+    while n:
+        if n & 1:
+            a, c = (pa * a) & _MASK, (pa * c + pc) & _MASK
+        pa, pc = (pa * pa) & _MASK, (pa * pc + pc) & _MASK
+        n >>= 1
     return a, c
 
 
@@ -133,3 +137,55 @@ def expand_area_light_caches(desc: SceneDesc, cache_size: int) -> int:
     d.light_points = pool.ctypes.data_as(C.POINTER(C.c_double))
     d.n_light_points = pool.shape[0]
     return pool.nbytes
+
+
+def drand48_state_after(draws: int) -> int:
+    """The generator's 48-bit state after `draws` draws from glibc's start state (X = 0 when srand48 was never called)."""
+    a, c = _jump(draws)
+    return (a * _X0 + c) & _MASK
+
+
+def generate_area_light_caches(desc: SceneDesc, cache_size: int, verify_sets=(), keep_host_points: bool = False) -> int:
+    """Like expand_area_light_caches, but the sets are REBUILT ON THE DEVICE (frt_scene_create_gen, csrc/frt_lightgen.cuh):
+    the description only records, per jittered area light, the drand48 state in front of its first set.  Nothing of the
+    157 MB of the shipped Cornell light exists on the host or crosses PCIe.
+
+    verify_sets: set indices whose points are also built here (numpy) and handed to the core, which compares them bit for
+    bit with what it generated (a mismatch fails scene creation).  Lights that are not jittered area lights keep their
+    host points.  Returns the number of bytes of the device point pool.
+    """
+    d = desc.c
+    old = np.ctypeslib.as_array(d.light_points, (max(d.n_light_points, 1), 3)) if d.n_light_points else np.zeros((0, 3))
+    kept, gens, offset, skip = [], [], 0, 0
+    for li in range(d.n_lights):
+        L = d.lights[li]
+        if L.type == AREA_LIGHT and L.jitter:
+            per_set = 2 * L.usteps * L.vsteps + L.usteps + L.vsteps
+            state = drand48_state_after(skip + per_set)  # sampler_2d() drew one table when the sampler was created
+            verify = []
+            for s in verify_sets:
+                s = s % cache_size
+                pts = area_light_points(L.position[:], L.uvec[:], L.vvec[:], L.usteps, L.vsteps, 1, True, skip + s * per_set)
+                verify.append((s, pts.reshape(-1, 3)))
+            gens.append({"light": li, "state": state, "verify": verify})
+            skip += (cache_size + 1) * per_set
+            L.cache_len = cache_size
+            n = cache_size * L.num_samples
+        else:
+            n = L.num_samples * L.cache_len
+            kept.append((offset, old[L.point_offset: L.point_offset + n].copy()))
+        L.point_offset = offset
+        offset += n
+    if kept or keep_host_points:
+        # untouched pages of a calloc'ed pool cost nothing: only the regions of the lights that are copied get written
+        pool = np.zeros((offset, 3), dtype=np.float64)
+        for off, block in kept:
+            pool[off: off + block.shape[0]] = block
+        desc._light_pool = pool
+        d.light_points = pool.ctypes.data_as(C.POINTER(C.c_double))
+    else:
+        desc._light_pool = None
+        d.light_points = C.POINTER(C.c_double)()
+    d.n_light_points = offset
+    desc.light_gens = gens
+    return offset * 24

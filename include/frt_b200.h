@@ -25,14 +25,16 @@
 extern "C" {
 #endif
 
-#define FRT_ABI_VERSION 6
+#define FRT_ABI_VERSION 6 /* struct layouts (scene blobs carry it); entry points added since: see FRT_API_LEVEL */
+#define FRT_API_LEVEL 2   /* 2: frt_scene_create_gen, frt_render_multi, frt_photons_estimate, frt_light_cache_checksum */
 
 enum frt_status {
     FRT_OK = 0,
     FRT_ERR_ARG = 1,      /* malformed scene description / bad argument */
     FRT_ERR_CUDA = 2,     /* CUDA runtime error or no usable device */
     FRT_ERR_IO = 3,       /* scene blob read/write */
-    FRT_ERR_OVERFLOW = 4  /* a per-ray bounded stack (CSG interval list) overflowed */
+    FRT_ERR_OVERFLOW = 4, /* a per-ray bounded stack (CSG interval list) overflowed */
+    FRT_ERR_MISMATCH = 5  /* frt_scene_create_gen: a light-sample set rebuilt on the device differs from the caller's */
 };
 
 /* Same numbering as the reference's enum shape_enum (src/shapes/shapes.h:16-27). */
@@ -203,6 +205,8 @@ enum frt_render_flags {
     FRT_FLAG_NO_SHAFT = 32,  /* switch the per-hit shaft culling of the shadow filter off (A/B measurements, tests) */
     FRT_FLAG_NO_BULK = 64,   /* switch the per-hit decision of all shadow rays at once (k_shadow_bulk) off */
     FRT_FLAG_NO_SPLIT = 128, /* ... keep it, but do not retry undecided hits per quadrant of the light's sample grid */
+    FRT_FLAG_STAGE_TIMES = 256, /* bracket every kernel of the frame with events and fill frt_stats.stage_ms completely (the
+                                shadow-ray and shaft stages are always timed) */
     FRT_FLAG_F64_SHADING = 4 /* evaluate the lighting sums (lighting_microfacet, renderer.c:894-979) in FP64 like the
                                 reference instead of FP32; geometric decisions are FP64 either way */
 };
@@ -217,10 +221,19 @@ typedef struct frt_render_cfg {
     uint64_t seed;           /* counter-based RNG seed (sample-set picks, jitter, aperture, photons) */
 } frt_render_cfg;
 
+/* stages of a frame, index into frt_stats.stage_ms */
+enum frt_stage {
+    FRT_ST_RAYGEN = 0, FRT_ST_EXTEND = 1, FRT_ST_SHADE = 2, FRT_ST_LIGHT_PRE = 3,
+    FRT_ST_SHADOW_SHAFT = 4,  /* k_shadow_bulk + k_shadow_quad: all shadow rays of a hit / a quadrant of the light at once */
+    FRT_ST_SHADOW_RAY = 5,    /* the per-ray kernel: k_shadow_f32 (k_shadow_mesh on mesh scenes, k_shadow_exact under F64_SHADOW) */
+    FRT_ST_SHADOW_EXACT = 6,  /* FP64 re-trace of the rays the FP32 filter deferred */
+    FRT_ST_LIGHT_FINAL = 7, FRT_ST_GI_TRACE = 8, FRT_ST_KNN = 9, FRT_ST_GI_RESOLVE = 10, FRT_ST_COUNT = 12
+};
+
 typedef struct frt_stats {
     double frame_ms;         /* device time of the frame, CUDA events on the render stream */
-    double light_ms;         /* summed device time of the FP32 shadow-ray kernel (k_shadow_f32, the dominant kernel;
-                                k_shadow_exact under FRT_FLAG_F64_SHADOW) */
+    double light_ms;         /* summed device time of the launches of the dominant kernel alone (= stage_ms[FRT_ST_SHADOW_RAY]):
+                                k_shadow_f32; k_shadow_mesh on mesh scenes; k_shadow_exact under FRT_FLAG_F64_SHADOW */
     double upload_ms, download_ms;
     uint64_t rays_primary, rays_secondary, rays_shadow, rays_gather, rays_photon;
     uint64_t hits_shaded;
@@ -239,6 +252,9 @@ typedef struct frt_stats {
                                 6 leaf verdict, 7 two spans in one operand, 8 CSG ordering / two-span result, 9 CSG verdict */
     int32_t rows_rendered;
     int32_t pad;
+    double stage_ms[12];     /* summed device time per stage (enum frt_stage); [4] and [5] always, the rest under FRT_FLAG_STAGE_TIMES */
+    uint64_t shadow_ray_launches; /* launches behind stage_ms[FRT_ST_SHADOW_RAY] */
+    uint64_t shadow_rays_traced;  /* FRT_FLAG_COUNT_RAYS: rays the per-ray kernel was handed (pending entries x samples) */
 } frt_stats;
 
 typedef struct frt_photon_cfg {
@@ -260,6 +276,36 @@ int frt_abi_sizeof(const char *struct_name);
 /* Upload a flattened scene (host pointers in desc are read during the call only; the one exception is a light_points
  * buffer registered with frt_host_register, see there). */
 int frt_scene_create(const frt_scene_desc *desc, int device, frt_scene **out);
+/*
+ * The same, with the sample caches of jittered rectangular area lights REBUILT ON THE DEVICE instead of uploaded.
+ * construct_area_light_surface_points_cache (src/light/light.c:155-191) is a pure function of the light's corner /
+ * uvec / vvec / steps, cache_size and the state of the process's drand48 generator before the constructor's first draw
+ * of set 0 (i.e. after the sampler_2d() call at :166 consumed one table of draws); the shipped Cornell light's cache is
+ * 157 MB flattened, and rebuilding it costs less than copying it once.  For every entry of `gens`:
+ *   - desc->lights[gen.light] must be a jittered area light (type 0) with usteps * vsteps == num_samples;
+ *   - the light's region of desc->light_points is NOT read (desc->light_points may be NULL when every light is listed);
+ *   - gen.verify_points[k] (k < gen.n_verify <= FRT_GEN_VERIFY_MAX): set gen.verify_set[k] as the reference built it,
+ *     num_samples * 3 doubles; each is compared bit for bit with the rebuilt set on the device.
+ * Returns FRT_ERR_MISMATCH (no scene) when a compared set differs -- the caller then flattens the host cache and calls
+ * frt_scene_create; FRT_OK means every listed light was rebuilt and every compared set is identical.
+ */
+#define FRT_GEN_VERIFY_MAX 8
+typedef struct frt_light_gen {
+    int32_t light;                 /* index into desc->lights */
+    int32_t n_verify;
+    uint64_t drand48_state;        /* the 48-bit state X before the first draw of set 0 */
+    int32_t verify_set[FRT_GEN_VERIFY_MAX];
+    const double *verify_points[FRT_GEN_VERIFY_MAX];
+} frt_light_gen;
+int frt_scene_create_gen(const frt_scene_desc *desc, int device, const frt_light_gen *gens, int n_gens, frt_scene **out);
+/* drand48 state after `draws` draws from state `x` (X' = 0x5DEECE66D X + 0xB mod 2^48; glibc starts from X = 0 when
+ * srand48 was never called): what a caller needs to fill frt_light_gen.drand48_state. */
+uint64_t frt_drand48_advance(uint64_t x, uint64_t draws);
+/* 64-bit checksum (wrapping sum of the words' bit patterns, each multiplied by an odd function of its index) of the
+ * scene's FP64 light-point pool on the device, points [first, first + count): lets a caller compare a whole rebuilt
+ * cache with the host's without moving either. frt_light_points_checksum_host computes the same over host points. */
+int frt_light_points_checksum(frt_scene *scene, int64_t first_point, int64_t n_points, uint64_t *sum);
+uint64_t frt_light_points_checksum_host(const double *points, int64_t first_point, int64_t n_points);
 void frt_scene_destroy(frt_scene *scene);
 /* frt_scene_destroy parks the scene-independent frame buffers (ray queues) and the large scene buffers (by size) for
  * the next scene on the same device; frt_trim frees them. */
@@ -310,6 +356,40 @@ int64_t frt_photons_count(frt_scene *scene, int map);
 int frt_photons_export(frt_scene *scene, int map, void *host_or_device_dst, int dst_is_device);
 int frt_photons_import(frt_scene *scene, int map, const void *src, int64_t count, int src_is_device);
 int frt_photons_finish(frt_scene *scene);
+
+/*
+ * pm_irradiance_estimate (src/libs/photon_map/pm.c:91-156) for n positions against photon map `map` (0 caustic,
+ * 1 global) with the scene's irradiance-estimate radius / num / cone-filter-k: the estimate as pm.c returns it (no
+ * caller rescale) and, per position, the function's return value (photons used).  pos_xyz / normal_xyz: n x 3 doubles
+ * (positions are rounded to FP32, as every request inside a frame is); irrad_rgb: n x 3 doubles; found: n ints or NULL.
+ */
+int frt_photons_estimate(frt_scene *scene, int map, int64_t n, const double *pos_xyz, const double *normal_xyz, double *irrad_rgb,
+                         int32_t *found);
+
+/*
+ * Several GPUs in ONE process: replaces render_multi()'s pthread row pool (src/renderer/renderer.c:244-281) at node
+ * scale.  frt_multi_create replicates the scene on every listed device (devices == NULL: all visible ones), each on its
+ * own host thread; frt_multi_render lets device k render the row blocks b with b % n == k and write them straight into
+ * canvas_rgba (the Canvas.arr layout; a block of rows is one contiguous run, so there is no packing, no collective and
+ * no reorder); frt_multi_photons shards the photon emission the same way (photon_tracer.c:203) and exchanges the
+ * stored photons device to device before every device bins the full set.  cfg->device / rank / world are ignored
+ * (filled per device).  stats: counters summed over the devices, times = the slowest device's.
+ */
+typedef struct frt_multi frt_multi;
+int frt_multi_create(const frt_scene_desc *desc, const int32_t *devices, int n_devices, const frt_light_gen *gens, int n_gens,
+                     frt_multi **out);
+void frt_multi_destroy(frt_multi *multi);
+int frt_multi_device_count(const frt_multi *multi);
+frt_scene *frt_multi_scene(frt_multi *multi, int k);
+int frt_multi_render(frt_multi *multi, const frt_render_cfg *cfg, double *canvas_rgba, frt_stats *stats);
+int frt_multi_photons(frt_multi *multi, const frt_photon_cfg *cfg, frt_stats *stats);
+
+/*
+ * Threading contract.  Every entry point may be called from any host thread; frt_last_error() is per thread.  One
+ * frt_scene (and one frt_multi) is used by one thread at a time.  Different scenes may be rendered concurrently from
+ * different threads, also on the same device (each scene has its own streams, frame buffers and page-locked slot; the
+ * buffers parked by frt_scene_destroy are handed out under a lock).
+ */
 
 /* Peak FP64/FP32 FMA issue rate of the device, measured by a register-resident FMA loop (TFLOP/s). */
 int frt_measure_fma_peak(int device, double *fp64_tflops, double *fp32_tflops);

@@ -212,6 +212,16 @@ def build_objects(force=False):
              "-I", str(REPO / "oracle" / "png_stub"), "-c", str(ssrc), "-o", str(shim)])
 
 
+def build_pm_oracle():
+    """oracle/_ref/libpm_ref.so: the reference's photon map (pm.c, unmodified) behind oracle/pm_oracle.c."""
+    lib = OUT / "libpm_ref.so"
+    src = REPO / "oracle" / "pm_oracle.c"
+    pm = REF / "src" / "libs" / "photon_map" / "pm.c"
+    if not lib.exists() or lib.stat().st_mtime < max(src.stat().st_mtime, pm.stat().st_mtime):
+        run(["gcc", *CFLAGS, "-shared", "-I", str(REF), "-o", str(lib), str(src), str(pm), "-lm"])
+    return lib
+
+
 def generate_main(name: str) -> Path:
     import yaml
 
@@ -283,6 +293,7 @@ def main():
         raise SystemExit("build fast_ray_tracer_b200/libfrt_b200.so first (python -m fast_ray_tracer_b200.build)")
     names = args.scenes or list(SCENES)
     build_objects(force=args.force)
+    build_pm_oracle()
     for name in names:
         build_scene(name, force=args.force)
         if not args.no_blobs and name not in NO_BLOB:

@@ -54,8 +54,11 @@ GOLDEN = {
     # the noise floor the CUDA render is held against
     "cornell_gi_64": ("cornell_gi", 64, 64, 2, 2),
     "cornell_gi_caustics_48": ("cornell_gi_caustics", 48, 48, 1, 1),
+    # C2 as benched, at a fixture-sized cache: every hit picks one of 64 cached sample sets with rand() twice
+    # (light.c:194-198, renderer.c:915) -- stochastic in the reference itself, so two seeded renders are stored
+    "cornell_cache64_200": ("cornell_cache64", 200, 200, 4, 4),
 }
-STOCHASTIC = {"cornell_gi_64", "cornell_gi_caustics_48", "dof_blur_240"}
+STOCHASTIC = {"cornell_gi_64", "cornell_gi_caustics_48", "dof_blur_240", "cornell_cache64_200"}
 # fixtures whose scene blob is too large to commit (6 dragons = 52 MB): only the reference canvas is stored; the GPU test
 # renders oracle/_ref/blobs/<scene>.frt, which travels to the GPU box with the snapshot
 BLOB_STAYS_IN_REF = {"bounding_boxes_600", "sibenik_surrogate_160"}

@@ -22,7 +22,9 @@ def frt():
     return frt
 
 
-STOCHASTIC = ("cornell_gi", "dof_blur")  # photon-mapped fixtures: two reference renders each, compared statistically (test_gpu_gi.py)
+# fixtures the reference itself renders differently from run to run (photon maps, jittered lens, rand() picks among
+# several cached light-sample sets): two seeded reference renders each, compared statistically
+STOCHASTIC = ("cornell_gi", "dof_blur", "cornell_cache64")
 
 
 def golden_names():

@@ -95,3 +95,54 @@ def test_set_resolution_follows_the_reference_camera(frt):
     assert cam.half_width == hw and abs(cam.pixel_size - ps / 2) < 1e-15
     desc.set_resolution(200, 400)  # portrait: camera.c:127-130
     assert abs(cam.half_height - hw) < 1e-15 and abs(cam.half_width - hw * 0.5) < 1e-15
+
+
+def test_malformed_descriptions_are_rejected_before_any_device_work(frt):
+    """validate_desc bounds-checks every index the kernels dereference (FRT_ERR_ARG, also on a host without a GPU)."""
+    import pytest
+
+    def load():
+        return frt.SceneDesc.load(GOLDEN / "texture_map_test.frt")
+
+    d = load()
+    d.c.materials[0].map_Kd = d.c.n_patterns
+    with pytest.raises(frt.FrtError, match="material 0"):
+        frt.Scene(d)
+    d = load()
+    d.c.textures[0].texel_offset = d.c.n_texels
+    with pytest.raises(frt.FrtError, match="texture 0"):
+        frt.Scene(d)
+    d = load()
+    for i in range(d.c.n_patterns):
+        if d.c.patterns[i].type == 9:  # uv texture
+            d.c.patterns[i].i[0] = d.c.n_textures + 3
+            break
+    with pytest.raises(frt.FrtError, match="pattern"):
+        frt.Scene(d)
+    d = load()
+    d.c.n_materials = -1
+    with pytest.raises(frt.FrtError, match="negative"):
+        frt.Scene(d)
+    d = frt.SceneDesc.load(GOLDEN / "teapot.frt")
+    for i in range(d.c.n_nodes):
+        if d.c.nodes[i].type in (4, 7):  # a triangle whose parameters would run past the pool
+            d.c.nodes[i].param = d.c.n_prim_params - 5
+            break
+    with pytest.raises(frt.FrtError, match="parameter offset"):
+        frt.Scene(d)
+
+
+def test_blob_with_a_negative_count_is_refused(frt, tmp_path):
+    import struct
+
+    import pytest
+
+    raw = bytearray((GOLDEN / "csg_test.frt").read_bytes())
+    # header: uint64 magic, int32 version, then the int32 counts (n_nodes first), then four int64 counts
+    for offset, fmt, value in ((12, "<i", -5), (12 + 7 * 4 + 4 + 16, "<q", -(1 << 40)), (12 + 7 * 4 + 4 + 8, "<q", 1 << 60)):
+        bad_raw = bytearray(raw)
+        struct.pack_into(fmt, bad_raw, offset, value)
+        bad = tmp_path / "bad.frt"
+        bad.write_bytes(bytes(bad_raw))
+        with pytest.raises(frt.FrtError, match="negative or impossible|truncated"):
+            frt.SceneDesc.load(bad)

@@ -1,0 +1,50 @@
+"""Unit parity of the device radiance estimate (k_knn on the uniform grid) with the reference's pm_irradiance_estimate
+through its own left-balanced kd-tree (pm.c:91-252), on IDENTICAL photons and queries (-m gpu).  The photons are the
+device's own (traced on the Cornell GI fixture, exported after the 1 / photon_count scaling), handed to the unmodified
+pm.c behind oracle/_ref/libpm_ref.so."""
+import numpy as np
+import pytest
+
+import pm_ref
+from conftest import GOLDEN
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not pm_ref.available(), reason="oracle/_ref/libpm_ref.so not built")]
+
+
+@pytest.mark.parametrize("which", ["global", "caustic"])
+def test_device_estimate_equals_pm_irradiance_estimate(frt, which):
+    name = "cornell_gi_64" if which == "global" else "cornell_gi_caustics_48"
+    m = 1 if which == "global" else 0
+    desc = frt.SceneDesc.load(GOLDEN / f"{name}.frt")
+    cfg = desc.config
+    rng = np.random.default_rng(11)
+    with frt.Scene(desc) as sc:
+        sc.trace_photons(3, which == "caustic", True, seed=5)
+        rec = sc.photons_export(m)  # after frt_photons_finish: powers carry the 1 / photon_count scale
+        n = rec.shape[1]
+        assert n > 1000
+        pos, power = rec[0, :, :3], rec[1, :, :3]
+        bits = np.ascontiguousarray(rec[0, :, 3]).view(np.uint32)
+        theta, phi = (bits & 255).astype(np.uint8), ((bits >> 8) & 255).astype(np.uint8)
+        # queries: on the surfaces (photon positions, nudged) and in the volume; FP32-representable like a frame's requests
+        pick = rng.integers(0, n, 3000)
+        q1 = pos[pick].astype(np.float64) + rng.normal(0, 0.01, (3000, 3))
+        q2 = rng.uniform(-1.5, 1.5, (1000, 3))
+        qpos = np.concatenate([q1, q2]).astype(np.float32).astype(np.float64)
+        qn = rng.standard_normal(qpos.shape)
+        qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+        qn = qn.astype(np.float32).astype(np.float64)
+        irr, found = sc.photons_estimate(m, qpos, qn)
+    ref, rfound = pm_ref.estimate(pos, power, theta, phi, qpos, qn, cfg.gi_irradiance_estimate_radius, cfg.gi_irradiance_estimate_num,
+                                  cfg.gi_irradiance_estimate_cone_filter_k)
+    assert np.array_equal(found, rfound.astype(np.int32))
+    used = rfound >= 8
+    assert used.sum() > 500 and (rfound == cfg.gi_irradiance_estimate_num).sum() > (100 if which == "global" else 0)
+    assert np.all(irr[~used] == 0.0)
+    scale = np.abs(ref[used]).max(axis=1, keepdims=True)
+    rel = np.abs(irr[used] - ref[used]) / scale
+    worst = rel.max(axis=1)
+    # FP32 sums of <= 200 weighted powers against FP64: 1e-5.  A request may swap its n-th and (n+1)-th photon when their
+    # distances agree to FP32 rounding (one photon of n differs): allowed on at most 0.5 % of the requests, and bounded.
+    assert (worst <= 1e-5).mean() >= 0.995, (worst > 1e-5).sum()
+    assert worst.max() <= 0.03

@@ -1,0 +1,52 @@
+"""The photon-map oracle (oracle/_ref/libpm_ref.so = the reference's pm.c behind oracle/pm_oracle.c) against a brute-force
+numpy restatement of pm_irradiance_estimate (pm.c:91-156): pins the harness the GPU kNN test relies on (no GPU)."""
+import numpy as np
+import pytest
+
+import pm_ref
+
+pytestmark = pytest.mark.skipif(not pm_ref.available(), reason="oracle/_ref/libpm_ref.so not built (python oracle/build_ref.py)")
+
+
+def brute_force(pos, power, theta, phi, qpos, qn, radius, n, k):
+    ang = np.arange(256) * (np.pi / 256.0)
+    dirs = np.stack([np.sin(ang)[theta] * np.cos(2 * ang)[phi], np.sin(ang)[theta] * np.sin(2 * ang)[phi], np.cos(ang)[theta]], axis=1)
+    out = np.zeros((qpos.shape[0], 3))
+    found = np.zeros(qpos.shape[0], dtype=np.int64)
+    p64, w64 = pos.astype(np.float64), power.astype(np.float64)
+    for i, (q, nr) in enumerate(zip(qpos, qn)):
+        d = p64 - q
+        d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+        idx = np.nonzero(d2 < radius * radius)[0]
+        r2 = radius * radius
+        if idx.size > n:
+            order = np.argsort(d2[idx], kind="stable")[:n]
+            idx = idx[order]
+            r2 = d2[idx].max()
+        found[i] = idx.size
+        if idx.size < 8:
+            continue
+        w = 1.0 - np.sqrt(d2[idx]) / (k * radius)
+        facing = dirs[idx] @ nr < 0.0
+        out[i] = (w64[idx] * (w * facing)[:, None]).sum(axis=0) / ((1.0 - 2.0 / (3.0 * k)) * np.pi * r2)
+    return out, found
+
+
+def test_oracle_equals_brute_force():
+    rng = np.random.default_rng(5)
+    n = 20000
+    pos = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    pos[:, 1] = np.where(rng.random(n) < 0.5, -1.0, pos[:, 1])  # half of them on a floor, like a real map
+    power = rng.uniform(0, 1e-4, (n, 3)).astype(np.float32)
+    theta = rng.integers(0, 256, n).astype(np.uint8)
+    phi = rng.integers(0, 256, n).astype(np.uint8)
+    qpos = rng.uniform(-1, 1, (300, 3)).astype(np.float32).astype(np.float64)
+    qpos[:150, 1] = -1.0
+    qn = rng.standard_normal((300, 3))
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    for radius, nn in ((0.1, 50), (0.3, 200)):
+        irr, found = pm_ref.estimate(pos, power, theta, phi, qpos, qn, radius, nn, 1.1)
+        want, wfound = brute_force(pos, power, theta, phi, qpos, qn, radius, nn, 1.1)
+        assert np.array_equal(found, wfound)
+        assert found.max() == nn and (found < 8).any() or radius > 0.2
+        assert np.allclose(irr, want, rtol=1e-9, atol=1e-15)
