@@ -8,8 +8,8 @@ jittered 10x10 rectangular area light), on N B200s of one node, next to the refe
 A step is one frame.  The workload is the reference's own scenes/cornell_box/cornell_box.yml with direct
 illumination only (include-global false, photon-count 0, area-light cache of 65 535 CMJ
 sample sets picked per hit), flattened by the drop-in shim into tests/golden/cornell_exact_200.frt; the camera is
-re-derived for 800x800 and the 65 535-set light cache is rebuilt on the host bit for bit
-(fast_ray_tracer_b200/lightcache.py).
+re-derived for 800x800 and the 65 535-set light cache is rebuilt on the device, bit for bit, at every scene creation
+(csrc/frt_lightgen.cuh; six sets built here by fast_ray_tracer_b200/lightcache.py are compared with it each time).
 
 Unit of work, identical on both arms: *reference-counted rays* = calls of the reference's intersect_world()
 (world.c:164) for the frame -- camera, reflection/refraction and shadow rays exactly as the reference spawns them
@@ -19,7 +19,10 @@ timed frames it skips rays whose weight is exactly zero, and the JSON line carri
 (`rays_traced_per_frame`).  value = reference-counted rays of the frame / frame time.
 
 Multi-GPU (torchrun, one process per GPU): the frame's row blocks are partitioned over the ranks, the scene is
-replicated, rank 0 gathers the rows over NCCL inside the timed region; "scaling" is strong (one frame, N GPUs).
+replicated, rank 0 gathers the rows over NCCL inside the timed region; "scaling" is strong (one frame, N GPUs).  After
+the timed loop the exact variant of the scene goes through the same rows/gather path and is compared with the reference's
+own 800x800 frame (`parity` in the JSON line); the end-to-end steps write each rank's rows straight into one page-locked
+host canvas (shared memory at N > 1).
 """
 from __future__ import annotations
 
@@ -186,30 +189,72 @@ def reference_arm(args) -> dict:
 # ---------------------------------------------------------------------------------------------- CUDA arm
 
 
-TRAFFIC_FILE = REPO / "profiles" / "r1n_traffic_k_shadow_f32.json"
+TRAFFIC_FILES = [REPO / "profiles" / "r2_traffic_k_shadow_f32.json", REPO / "profiles" / "r1n_traffic_k_shadow_f32.json"]
+FP32_PEAK_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FP32 lanes x FMA x 1.965 GHz = 74.4 TFLOP/s
 
 
 def traffic_per_launch(args):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very command (null when the
     workload differs from the one that was captured)."""
     if args.variant != "shipped" or args.size != HSIZE or args.spp != SPP or int(os.environ.get("WORLD_SIZE", "1")) != 1:
-        return None
-    try:
-        return json.loads(TRAFFIC_FILE.read_text())["dram_bytes_per_launch_mean"]
-    except Exception:
-        return None
+        return None, None
+    for f in TRAFFIC_FILES:
+        try:
+            return json.loads(f.read_text())["dram_bytes_per_launch_mean"], f.name
+        except Exception:
+            continue
+    return None, None
 
 
 def load_workload(frt, variant: str, size: int, spp: int):
-    from fast_ray_tracer_b200.lightcache import expand_area_light_caches
+    """The flattened Cornell scene at the benchmark size.  `shipped`: the area light carries 65 535 cached sample sets like
+    the reference's YAML (cache-size 65535); they are rebuilt on the device per scene (frt_scene_create_gen) from the
+    light's geometry and the drand48 state in front of the constructor's first draw -- the description holds six sets
+    built here in numpy (the reference's arithmetic, pinned by tests/test_lightcache.py) which the core compares bit for
+    bit with what it generated at every scene creation."""
+    from fast_ray_tracer_b200.lightcache import generate_area_light_caches
 
     desc = frt.SceneDesc.load(BLOB)
     desc.set_resolution(size, size)
     desc.set_samples(spp, spp)
     if variant == "shipped":
-        expand_area_light_caches(desc, CACHE_SETS)
-    desc.pin()  # the light-sample cache (157 MB of the description) is page-locked once: the e2e steps copy from pinned memory
+        generate_area_light_caches(desc, CACHE_SETS, verify_sets=(0, 1, 4097, 32768, 65533, 65534))
     return desc
+
+
+class SharedCanvas:
+    """The caller's host canvas of a multi-process run: one page-locked buffer in POSIX shared memory that every rank
+    maps; rank r's frt_render copies the rows it owns straight into it (a block of rows is one contiguous run of
+    Canvas.arr), so the frame reaches the host without a collective, a packing kernel or a reorder."""
+
+    def __init__(self, frt, name: str, shape, rank: int, barrier):
+        import numpy as np
+
+        self.path = Path("/dev/shm") / name
+        nbytes = int(np.prod(shape)) * 8
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        barrier()
+        self.arr = np.memmap(self.path, dtype=np.float64, mode="r+", shape=tuple(shape))
+        if rank == 0:
+            self.arr[...] = 0.0  # touch the pages before they are page-locked
+        barrier()
+        self.frt, self.nbytes, self.rank = frt, nbytes, rank
+        rc = frt.load_library().frt_host_register(self.arr.ctypes.data, nbytes)
+        if rc != 0:
+            raise SystemExit("bench.py: frt_host_register of the shared canvas failed")
+        barrier()
+
+    def close(self, barrier):
+        self.frt.load_library().frt_host_unregister(self.arr.ctypes.data)
+        barrier()
+        del self.arr
+        if self.rank == 0:
+            try:
+                self.path.unlink()
+            except OSError:
+                pass
 
 
 def cuda_arm(args) -> dict:
@@ -218,8 +263,11 @@ def cuda_arm(args) -> dict:
     import torch.distributed as dist
 
     import fast_ray_tracer_b200 as frt
-    from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_NO_PRUNE
+    from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_NO_PRUNE, FRT_FLAG_STAGE_TIMES
     from fast_ray_tracer_b200.dist import gather_rows, owned_rows
+
+    sys.path.insert(0, str(REPO / "oracle"))
+    from compare import parity_report  # the checker of the parity block below; nothing of oracle/ is on the timed path
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,26 +293,28 @@ def cuda_arm(args) -> dict:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def frame_step(sc, seed):
+        """One frame of this rank's rows on the device, then (N > 1) the NCCL gather of the rows to rank 0."""
+        _, st = sc.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=seed)
+        frame = sc.canvas_tensor()
+        if world > 1:
+            canvas = gather_rows(frame.index_select(0, rows_idx), vsize, rank, world, rpb)
+        else:
+            canvas = frame
+        return st, canvas
+
     with frt.Scene(desc, device=local) as sc:
         # ---- counting frames (untimed): the reference's ray count for this frame and this kernel's event flop
         _, st_ref = sc.render(rank=rank, world=world, rows_per_block=rpb, flags=FRT_FLAG_NO_PRUNE | FRT_FLAG_COUNT_RAYS,
                               download=False, seed=1)
         _, st_cnt = sc.render(rank=rank, world=world, rows_per_block=rpb, flags=FRT_FLAG_COUNT_RAYS, download=False, seed=1)
+        _, st_stage = sc.render(rank=rank, world=world, rows_per_block=rpb, flags=FRT_FLAG_STAGE_TIMES, download=False, seed=1)
         counts = torch.tensor([st_ref.rays_total, st_cnt.rays_total, st_cnt.rays_shadow, st_cnt.light_flops, st_cnt.hits_shaded,
                                st_cnt.shadow_deferred, st_cnt.extra["shadow_reasons"][0]], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(counts)
         ref_rays, traced_rays, shadow_rays, light_flops, hits, deferred, bulk_rays = (float(x) for x in counts.tolist())
         traced_rays -= bulk_rays  # rays_total counts every shadow ray of the frame; the ones decided per hit are not traced
-
-        def step(seed):
-            _, st = sc.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=seed)
-            frame = sc.canvas_tensor()
-            if world > 1:
-                canvas = gather_rows(frame.index_select(0, rows_idx), vsize, rank, world, rpb)
-            else:
-                canvas = frame
-            return st, canvas
 
         clocks = ClockSampler(local)
         if rank == 0 and not os.environ.get("FRT_BENCH_NO_NVML"):
@@ -273,9 +323,10 @@ def cuda_arm(args) -> dict:
         for w in range(args.warmup):
             # keep the previous frame alive across the next step, exactly like the timed loop does: the gathered canvas of
             # rank 0 then needs its second 20 MB block from the caching allocator here, not in a timed step
-            st, canvas = step(100 + w)
+            st, canvas = frame_step(sc, 100 + w)
             flush.zero_()
-        frame_ms, light_ms, launches, light_launches = [], [], 0, 0
+        frame_ms, launches = [], 0
+        kern_ms = kern_launches = kern_rays = shaft_ms = 0.0
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t_wall0 = time.perf_counter()
@@ -285,7 +336,7 @@ def cuda_arm(args) -> dict:
             torch.cuda.synchronize()
             ev0.record()
             tk = time.perf_counter()
-            st, canvas = step(1000 + k)
+            st, canvas = frame_step(sc, 1000 + k)
             ev1.record()
             torch.cuda.synchronize()
             if os.environ.get("FRT_BENCH_DEBUG"):
@@ -294,67 +345,108 @@ def cuda_arm(args) -> dict:
             # the core times its own stream with CUDA events (frame_ms); the torch events bracket the NCCL gather too
             dev_ms_total += max(st.frame_ms, ev0.elapsed_time(ev1))
             frame_ms.append(st.frame_ms)
-            light_ms.append(st.light_ms)
             launches += st.kernel_launches
-            light_launches += st.light_launches
+            # the dominant kernel ALONE: CUDA events around each of its launches on the render stream, this very frame
+            kern_ms += st.light_ms
+            kern_launches += st.extra["shadow_ray_launches"]
+            kern_rays += st.extra["shadow_rays_traced"]
+            shaft_ms += st.extra["stage_ms"]["shadow_shaft"]
         barrier()
         wall_s = time.perf_counter() - t_wall0
 
-        t = torch.tensor([dev_ms_total, sum(light_ms), float(launches), float(light_launches)], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms_total, kern_ms, float(launches), kern_launches, kern_rays, shaft_ms], dtype=torch.float64, device=dev)
         tmax = t.clone()
         if world > 1:
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms_per_step = float(tmax[0]) / args.steps
-        light_ms_per_step = float(tmax[1]) / args.steps
+        kern_ms_per_step = float(tmax[1]) / args.steps          # the slowest rank's
+        shaft_ms_per_step = float(tmax[5]) / args.steps
         total_launches = int(t[2])
-        light_launches_per_rank_step = float(t[3]) / world / args.steps
+        kern_launches_per_rank_step = float(t[3]) / world / args.steps
+        kern_rays_per_step = float(t[4]) / args.steps            # all ranks
+        last_frame = canvas.cpu().numpy() if (rank == 0 and canvas is not None) else None  # the scene's buffers are recycled below
 
-        # ---- e2e: the reference-facing call with HOST buffers: flattened scene in host memory -> upload -> frame ->
-        #      canvas back in (pinned) host memory, every step.  Multi-GPU: each rank uploads, rank 0 receives the frame.
+    # ---- parity of the very path that was timed (untimed): the exact variant (one cached sample set: deterministic in the
+    #      reference) through the same frame_step() -- rows per rank, NCCL gather -- against the committed reference frame
+    parity = None
+    gold = REPO / "tests" / "golden" / f"cornell_exact_{args.size}.npz"
+    if args.spp == SPP and gold.exists():
+        exact = frt.SceneDesc.load(BLOB)
+        exact.set_resolution(args.size, args.size)
+        exact.set_samples(args.spp, args.spp)
+        with frt.Scene(exact, device=local) as sc_exact:
+            _, full = frame_step(sc_exact, 1)
+            if rank == 0:
+                rep = parity_report(full.cpu().numpy()[..., :3], np.load(gold)["rgb"].astype(np.float64))
+                parity = {"fixture": gold.name, "variant": "exact (cache-size 1), same rows/gather path as the timed frames",
+                          "within_1lsb": rep["within_1lsb"], "max_lsb": rep["max_lsb"], "exact": rep["exact"], "pixels": rep["pixels"]}
+        barrier()
+
+    # ---- e2e: the reference-facing call with HOST buffers, every step: frt_scene_create_gen(host description) -> the light
+    #      cache rebuilt + verified on the device -> frt_render -> this rank's rows copied straight into the caller's
+    #      page-locked host canvas -> frt_scene_destroy.  N > 1: the canvas lives in shared memory, every rank writes its rows.
+    shared = None
+    if world > 1:
+        shared = SharedCanvas(frt, f"frt_bench_canvas_{os.environ.get('MASTER_PORT', '0')}", (vsize, hsize, 4), rank, barrier)
+        out = shared.arr
+    else:
         pinned = torch.empty((vsize, hsize, 4), dtype=torch.float64).pin_memory()
         out = pinned.numpy()
-        e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 5))
 
-        def e2e_step(k):
-            with frt.Scene(desc, device=local) as sc2:
-                if world == 1:
-                    sc2.render(out=out, seed=2000 + k)
-                else:
-                    sc2.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=2000 + k)
-                    full = gather_rows(sc2.canvas_tensor().index_select(0, rows_idx), vsize, rank, world, rpb)
-                    if rank == 0:
-                        pinned.copy_(full)
-                torch.cuda.synchronize()
+    def e2e_step(k):
+        with frt.Scene(desc, device=local) as sc2:
+            sc2.render(rank=rank, world=world, rows_per_block=rpb, out=out, seed=2000 + k)
 
-        e2e_step(-1)  # warm-up: the first scene of a process allocates the (scene-independent, re-used) ray queues
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
-            tk = time.perf_counter()
-            e2e_step(k)
-            if rank == 0:
-                print(f"[bench] e2e step {k}: {1e3 * (time.perf_counter() - tk):.1f} ms", file=sys.stderr)
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_step(-1)  # warm-up: the first scene of a process allocates the (scene-independent, re-used) ray queues
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        tk = time.perf_counter()
+        e2e_step(k)
         if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_s = float(e2e_t[0])
-        clk = clocks.stop() if rank == 0 else None
+            dist.barrier()  # the frame is complete on the host when every rank's rows have landed
+        if rank == 0:
+            print(f"[bench] e2e step {k}: {1e3 * (time.perf_counter() - tk):.1f} ms", file=sys.stderr)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t[0])
+    e2e_parity = None
+    if rank == 0 and last_frame is not None:
+        # the host canvas of the last e2e step against the device-timed frame of the same workload (other seed: the
+        # set picks differ like two runs of the reference do) -- a torn / missing row block would show as a large error
+        rep = parity_report(np.asarray(out)[..., :3], last_frame[..., :3])
+        e2e_parity = {"against": "device-timed frame, other seed", "within_1lsb": rep["within_1lsb"], "rmse_lsb": rep["rmse_lsb"], "max_lsb": rep["max_lsb"]}
+    if shared is not None:
+        shared.close(barrier)
+    clk = clocks.stop() if rank == 0 else None
 
     fp64_peak, fp32_peak = frt.measure_fma_peak(local)
+    # bytes a scene creation copies host -> device: the flattened description; a rebuilt light cache contributes only the
+    # sets that are sent along for the bit-for-bit comparison
+    gens = getattr(desc, "light_gens", None) or []
+    h2d_per_rank = int(desc.host_bytes)
+    if gens:
+        h2d_per_rank -= int(desc.c.n_light_points) * 24
+        h2d_per_rank += sum(24 * int(desc.c.lights[g["light"]].num_samples) * len(g["verify"]) for g in gens)
     line = None
     if rank == 0:
         value = ref_rays / (ms_per_step * 1e-3) / 1e6
-        # roofline of the dominant kernel (k_light: shadow rays + microfacet lighting): algorithmic flop per launch,
-        # counted event by event with the BASELINE.md cost table, over the CUDA-event duration of its launches
-        # numerator: BASELINE.md section 4's frozen per-unit figure (algorithmic flop per shadow ray in the REFERENCE's
-        # traversal order, counted once with shaft culling off) x the shadow rays the launches processed
-        algo_flops = F_SHADOW_RAY * shadow_rays
-        flops_per_launch = algo_flops / max(light_launches_per_rank_step * world, 1)
-        launch_ms = light_ms_per_step / max(light_launches_per_rank_step, 1)
-        achieved = (algo_flops / world) / (light_ms_per_step * 1e-3) / 1e12 if light_ms_per_step > 0 else 0.0
+        # Roofline of the dominant kernel, k_shadow_f32, ALONE.  Unit: one shadow ray handed to the kernel (pending entry
+        # x light sample); algorithmic flop per unit: BASELINE.md section 4's frozen figure (events one shadow ray costs in
+        # the REFERENCE's traversal order, counted once with every per-hit cull off).  achieved = that x the units per
+        # launch / the launch's duration (CUDA events around each launch on the render stream, timed frames).
+        launch_ms = kern_ms_per_step / max(kern_launches_per_rank_step, 1)
+        units_per_launch = kern_rays_per_step / world / max(kern_launches_per_rank_step, 1)
+        achieved = F_SHADOW_RAY * units_per_launch / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+        stage_ms = (shaft_ms_per_step + kern_ms_per_step)
+        stage_achieved = (F_SHADOW_RAY * shadow_rays / world) / (stage_ms * 1e-3) / 1e12 if stage_ms > 0 else 0.0
+        executed = light_flops / max(shadow_rays - bulk_rays, 1)
+        traffic, traffic_file = traffic_per_launch(args)
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -370,31 +462,42 @@ def cuda_arm(args) -> dict:
             "mrays_s_traced": traced_rays / (ms_per_step * 1e-3) / 1e6,
             "wall_s_timed_region": wall_s,
             "clocks": clk,
+            "parity": parity,
             "e2e": {"value": ref_rays / e2e_s / 1e6, "unit": "Mrays/s", "frame_ms": e2e_s * 1e3,
-                    "h2d_bytes_per_step": int(desc.host_bytes) * world, "d2h_bytes_per_step": vsize * hsize * 32,
-                    "path": "frt_scene_create(host desc; the page-locked light-sample cache is copied asynchronously and the frame waits "
-                            "for it where its light stage begins) + frt_render + canvas to pinned host memory + frt_scene_destroy, per step"},
+                    "h2d_bytes_per_step": h2d_per_rank * world,
+                    "d2h_bytes_per_step": vsize * hsize * 32,
+                    "parity": e2e_parity,
+                    "path": "per step and rank: frt_scene_create_gen(host description; the 65 535-set light cache is rebuilt on the device and "
+                            "six sets are compared bit for bit with host-built ones) + frt_render(rank, world) with the rank's row blocks "
+                            "copied straight into the caller's page-locked host canvas (N > 1: one canvas in shared memory, no "
+                            "collective) + frt_scene_destroy"},
             "gpu_launches": total_launches,
             "roofline": {"bound": "fp32-issue", "kernel": "k_shadow_f32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic_per_launch(args),
+                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
                          "peak_source": "register-resident FP32 FMA loop measured in this run (frt_measure_fma_peak); "
                                         "MEASURED_PEAKS.json holds HBM and bf16-tensor peaks only and this kernel uses neither",
+                         "fp32_peak_nominal": FP32_PEAK_NOMINAL, "frac_of_nominal": achieved / FP32_PEAK_NOMINAL,
                          "fp64_peak_tflops": fp64_peak,
-                         "flop_per_launch": flops_per_launch, "launch_ms": launch_ms,
-                         "kernel_share_of_step": light_ms_per_step / ms_per_step if ms_per_step else None,
-                         "shadow_rays_per_frame": shadow_rays, "hits_shaded_per_frame": hits,
-                         "shadow_rays_deferred_to_fp64": deferred,
-                         "flop_per_shadow_ray_frozen": F_SHADOW_RAY,
-                         "flop_per_shadow_ray_after_shaft_culling": light_flops / max(shadow_rays - deferred, 1),
-                         "shadow_rays_decided_per_hit_or_quadrant": bulk_rays,
-                         "traffic_unit": "bytes of DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the "
-                                         "kernel's 6 launches of one frame), ncu capture of this command: " + TRAFFIC_FILE.name,
-                         "note": "achieved = shadow rays of the frame (device counter, untimed counting frame) x the frozen "
-                                 "algorithmic flop per shadow ray of BASELINE.md section 4 / CUDA-event time of the shadow stage "
-                                 "(k_shadow_bulk + k_shadow_quad + k_shadow_f32) in the timed frames; two thirds of the rays are "
-                                 "decided per hit or per quadrant of the light by interval arithmetic over the whole shaft and "
-                                 "never traced; k_shadow_f32 itself is instruction-issue bound (ncu: 73 % issue utilisation), "
-                                 "not arithmetic or HBM bound, see DESIGN.md 4.3"},
+                         "launch_ms": launch_ms, "launches_per_frame": kern_launches_per_rank_step, "units_per_launch": units_per_launch,
+                         "unit_name": "shadow ray handed to k_shadow_f32 (pending (hit, quadrant) entry x light sample)",
+                         "flop_per_unit": F_SHADOW_RAY, "flop_per_launch": F_SHADOW_RAY * units_per_launch,
+                         "kernel_share_of_step": kern_ms_per_step / ms_per_step if ms_per_step else None,
+                         "flop_per_unit_executed": executed,
+                         "frac_executed": (executed * units_per_launch / (launch_ms * 1e-3) / 1e12) / fp32_peak if launch_ms > 0 and fp32_peak else None,
+                         "shadow_stage": {"kernels": "k_shadow_bulk + k_shadow_quad + k_shadow_f32", "ms_per_frame": stage_ms,
+                                          "shadow_rays_per_frame": shadow_rays, "decided_per_hit_or_quadrant": bulk_rays,
+                                          "deferred_to_fp64": deferred, "achieved_reference_equivalent": stage_achieved,
+                                          "frac_reference_equivalent": stage_achieved / fp32_peak if fp32_peak else None,
+                                          "note": "all shadow rays of the frame x the frozen flop per ray / the time of the three kernels: "
+                                                  "rays decided per hit or per quadrant of the light are never traced and raise this figure"},
+                         "stage_ms_profile_frame": st_stage.extra["stage_ms"],
+                         "hits_shaded_per_frame": hits,
+                         "traffic_unit": "bytes of DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the kernel's "
+                                         "launches of one frame), ncu capture of this command: " + str(traffic_file),
+                         "note": "achieved = flop_per_unit x units_per_launch / launch_ms: the frozen algorithmic flop per shadow ray of "
+                                 "BASELINE.md section 4 x the rays one launch of k_shadow_f32 is handed (device counter, timed frames) / "
+                                 "the mean duration of its launches (CUDA events around each launch, timed frames).  The kernel is "
+                                 "instruction-issue bound, not HBM bound (DRAM traffic ~1 % of peak), see DESIGN.md 4.3"},
         }
     if world > 1:
         dist.barrier()

@@ -84,3 +84,38 @@ def test_generated_program_writes_its_ppm_from_the_device():
     canvas2, out2 = run_dropin("cornell_exact", dict(env, FRT_DEVICE_PPM="0"))
     assert "FRT_B200_PPM_MS" not in out2
     assert out_file.read_bytes() == construct_ppm(canvas2, True)
+
+
+def test_generated_program_rebuilds_the_light_cache_on_the_device():
+    """A jittered area light with several cached sample sets: the reference's constructor built them on the host
+    (light.c:155-191); the shim leaves them there, the core rebuilds them from the drand48 state the constructors' order
+    implies and compares eight sets bit for bit with the reference's (frt_scene_create_gen).  Same seed, cache rebuilt or
+    uploaded: the same frame; and that frame agrees statistically with the reference's renders of the scene."""
+    from compare import to_srgb8
+
+    env = {"FRT_REF_HSIZE": "200", "FRT_REF_VSIZE": "200", "FRT_REF_USTEPS": "4", "FRT_REF_VSTEPS": "4", "FRT_SEED": "3"}
+    canvas, out = run_dropin("cornell_cache64", env)
+    assert "1 light caches rebuilt on the device" in out, out[-1500:]
+    canvas2, out2 = run_dropin("cornell_cache64", dict(env, FRT_LIGHT_GEN="0"))
+    assert "rebuilt on the device" not in out2
+    assert np.array_equal(canvas, canvas2)
+    z = np.load(GOLDEN / "cornell_cache64_200.npz")
+    a, b = z["rgb"].astype(np.float64), z["rgb_b"].astype(np.float64)
+
+    def rmse(x, y):
+        return float(np.sqrt(((to_srgb8(x).astype(np.float64) - to_srgb8(y).astype(np.float64)) ** 2).mean()))
+
+    assert rmse(canvas, a) <= 1.25 * rmse(a, b), (rmse(canvas, a), rmse(a, b))
+
+
+def test_generated_program_uses_every_gpu_of_the_box():
+    """FRT_DEVICES (default: all visible GPUs): render_multi() splits the row blocks over them inside the library and
+    every device writes its rows into the returned Canvas; one device or all, a deterministic scene gives one frame."""
+    import torch
+
+    env = {"FRT_REF_HSIZE": "200", "FRT_REF_VSIZE": "200"}
+    one, out1 = run_dropin("csg_test", dict(env, FRT_DEVICES="1"))
+    assert "(1 devices)" in out1
+    every, outn = run_dropin("csg_test", dict(env, FRT_DEVICES="all"))
+    assert f"({torch.cuda.device_count()} devices)" in outn
+    assert np.array_equal(one, every)
