@@ -126,6 +126,8 @@ struct Counters {
     unsigned long long rays_per_ray; /* rays handed to the per-ray shadow kernel (k_shadow_f32 / k_shadow_mesh / k_shadow_exact<ALL>) */
     unsigned long long undecided_node[32]; /* debug: node at which a leaf verdict was undecided */
     unsigned long long undecided_reason[10]; /* counting build: why the FP32 filter deferred a ray (codes in frt_shadow_f32.cuh) */
+    unsigned long long entry_node[3][32];    /* counting build: pending entries by class (0 straight-line, 1 tail verdict but general walk,
+                                                2 no tail verdict) and start node */
 };
 
 struct DCamera {
@@ -719,7 +721,12 @@ k_light_pre(DScene S, FrameParams F, const LightRec *__restrict__ recs, LightTmp
                 shaft_setup(sh, SF.shaft + 4 * light_idx, ofx, ofy, ofz);
                 const int nn = min(SF.n_nodes, 32);
                 for (int k = lane_g; k < nn; k += G) {
-                    if (!shaft_misses_box(sh, __ldg(SF.wbox + 2 * k), __ldg(SF.wbox + 2 * k + 1), ofx, ofy, ofz)) {
+                    bool miss = shaft_misses_box(sh, __ldg(SF.wbox + 2 * k), __ldg(SF.wbox + 2 * k + 1), ofx, ofy, ofz);
+                    if (!miss) { /* a ball fills half of its box: test the ball itself */
+                        const float4 sp = __ldg(SF.wsphere + k);
+                        miss = sp.w > 0.f && shaft_misses_sphere(sh, sp, ofx, ofy, ofz);
+                    }
+                    if (!miss) {
                         relevant |= 1u << k;
                     }
                 }
@@ -1139,6 +1146,181 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                     atomicAdd(&tmp[h].unshadowed, c);
                 }
             }
+        }
+    }
+    if (overflow) {
+        atomicOr(&cnt->overflow_csg, 1u);
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            n_shadow += __shfl_down_sync(0xffffffffu, n_shadow, o);
+            n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, o);
+            n_flops += __shfl_down_sync(0xffffffffu, n_flops, o);
+            n_mismatch += __shfl_down_sync(0xffffffffu, n_mismatch, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (n_shadow) atomicAdd(&cnt->rays_shadow, n_shadow);
+            if (n_nodes) atomicAdd(&cnt->shadow_nodes, n_nodes);
+            if (n_flops) atomicAdd(&cnt->light_flops, n_flops);
+            if (n_mismatch) atomicAdd(&cnt->f32_mismatch, n_mismatch);
+        }
+    }
+}
+
+/*
+ * The same job with ONE WARP PER PENDING ENTRY: lanes are the samples of the entry's quadrant (25 of a 10 x 10 light;
+ * larger entries take several passes).  Everything an entry carries -- hit, origin, sample set, start node, tail verdict,
+ * shaft mask -- is the same in every lane, so the warp takes every branch of the walk together; what differs from lane to
+ * lane is arithmetic (slab values, orderings), and in the common case (trace_entry_fast: the shaft walk left one WORLD
+ * cube / CSG-of-cubes node and a tail verdict) it is straight-line code with selects.  The count of lit rays is one ballot
+ * and one atomic per entry (no __match_any_sync), deferred rays are appended with one atomic per warp.  ncu on
+ * k_shadow_f32 (profiles/r2a_k_shadow_f32_lines.txt): 1 030 warp-instructions per 32 rays at 23.3 active lanes, box tests
+ * at 19.7 and the CSG combination at 15 lanes -- the warps there hold the tail of one entry and the head of the next.
+ */
+/* the general walk as a call: k_shadow_entry's registers are sized for the straight-line path */
+template <bool COUNT>
+__device__ __noinline__ int
+trace_shadow_f32_call(const DSceneF &SF, const float4 *fnodes, int root, int start, int tail, unsigned int relevant, const FrameF &w, float omax,
+                      float eo_o, float ed_w, float D_lo, float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
+{
+    return trace_shadow_f32<COUNT>(SF, fnodes, root, start, tail, relevant, w, omax, eo_o, ed_w, D_lo, D_hi, nodes_visited, flops);
+}
+
+#ifndef FRT_ENTRY_MINB
+#define FRT_ENTRY_MINB 6
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(128, FRT_ENTRY_MINB)
+k_shadow_entry(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
+               const unsigned int *__restrict__ pending, const unsigned char *__restrict__ pstart, int use_start, unsigned int pend_cap,
+               int split_on, int light_idx, unsigned long long *__restrict__ queue, unsigned int qcap, int nodes_in_smem)
+{
+    constexpr bool COUNT = MODE != 0;
+    extern __shared__ float4 s_nodes[];
+    const float4 *fnodes = SF.fnodes;
+    if (nodes_in_smem) {
+        for (int k = threadIdx.x; k < 3 * SF.n_nodes; k += blockDim.x) {
+            s_nodes[k] = SF.fnodes[k];
+        }
+        __syncthreads();
+        fnodes = s_nodes;
+    }
+    const unsigned int n = min(cnt->n_pending, pend_cap);
+    const int NS = S.lights[light_idx].num_samples;
+    const int4 lq = split_on ? __ldg(SF.lquad + light_idx) : make_int4(NS, 0, 0, 0);
+    const int NSQ = lq.x;
+    const float *fpts = SF.lpoints + 3 * S.lights[light_idx].point_offset;
+    const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
+    const int root = __ldg(S.roots);
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int warps = gridDim.x * (blockDim.x >> 5), wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int overflow = 0;
+    unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0, n_mismatch = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&cnt->rays_per_ray, (unsigned long long)n * (unsigned int)NSQ);
+    }
+    const float bmax_term = 2.0f * FRT_F32_U * SF.bmax;
+
+    for (unsigned int e = wid; e < n; e += warps) {
+        const unsigned int entry = __ldg(pending + e);
+        const int start = (int)__ldg(pstart + e);
+        const unsigned int h = entry & FRT_PEND_HIT_MASK;
+        const int q = (int)((entry >> 28) & 3u);
+        const float4 head = *reinterpret_cast<const float4 *>(tmp + h);
+        const int set_a = __float_as_int(head.w);
+        if (set_a < 0) {
+            continue; /* the whole warp */
+        }
+        const unsigned int relevant = tmp[h].relevant;
+        const int bulk = MODE != 0 ? (int)(entry >> 30) : 0; /* bit 0: decided by k_shadow_bulk, bit 1: as lit */
+        const int node = use_start ? (start & FRT_RESUME_NODE_MASK) : root;
+        const int tail = use_start ? (start >> FRT_RESUME_TAIL_SHIFT) : 0;
+        const bool fast = tail != 0 && node < 32 && ((SF.entry_fast >> node) & 1u) && S.n_roots == 1;
+        /* per entry: the origin's error terms */
+        const float omax = fmaxf(fmaxf(fabsf(head.x), fabsf(head.y)), fabsf(head.z));
+        const float eo_o = 2.0f * FRT_F32_U * omax;
+        const float eo_w = bmax_term + fmaf(SF.ealign, omax, eo_o);
+        const float *set_pts = fpts + 3 * (size_t)set_a * NS;
+        if (COUNT && lane == 0 && !bulk) {
+            atomicAdd(&cnt->entry_node[fast ? 0 : (tail != 0 ? 1 : 2)][node & 31], 1ull);
+        }
+        int lit = 0;
+        for (int k0 = 0; k0 < NSQ; k0 += 32) {
+            const int k = k0 + (int)lane;
+            const bool active = k < NSQ;
+            const int s = active ? quadrant_sample(lq, q, k) : 0;
+            int res = FRT_SH_SHADOWED;
+            if (active) {
+                if (bulk) {
+                    res = MODE == 2 && (bulk & 2) ? FRT_SH_LIT : FRT_SH_SHADOWED; /* counting frame: the hit's count is already set */
+                } else if (S.n_roots != 1) {
+                    res = FRT_SH_UNDECIDED; /* several top-level shapes (world.c:189-191): never generated; FP64 handles it */
+                } else {
+                    /* the FP32 ray: both world points rounded to FP32, difference and normalisation in FP32 */
+                    const float px = __ldg(set_pts + 3 * s), py = __ldg(set_pts + 3 * s + 1), pz = __ldg(set_pts + 3 * s + 2);
+                    FrameF w;
+                    w.ox = head.x;
+                    w.oy = head.y;
+                    w.oz = head.z;
+                    const float vx = px - w.ox, vy = py - w.oy, vz = pz - w.oz;
+                    const float len2 = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
+                    const float rinv = rsqrtf(len2);
+                    w.dx = vx * rinv;
+                    w.dy = vy * rinv;
+                    w.dz = vz * rinv;
+                    const float pmax = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
+                    const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G + SF.ealign);
+                    frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
+                    const float Df = len2 * rinv;
+                    const float D_lo = Df - Df * ed_w, D_hi = Df + Df * ed_w;
+                    if (fast) {
+                        res = trace_entry_fast<COUNT>(SF, fnodes, node, tail, w, D_lo, D_hi, &n_nodes, &n_flops);
+                    } else {
+                        res = trace_shadow_f32_call<COUNT>(SF, fnodes, root, node, tail, relevant, w, omax, eo_o, ed_w, D_lo, D_hi, &n_nodes, &n_flops);
+                    }
+                    if (COUNT && (res >> 4)) {
+                        atomicAdd(&cnt->undecided_reason[min((res >> 4) & 15, 9)], 1ull);
+                        atomicAdd(&cnt->undecided_node[(res >> 8) & 31], 1ull);
+                    }
+                    res &= 15;
+                }
+                if (COUNT) ++n_shadow;
+                if (MODE == 2 && res != FRT_SH_UNDECIDED) {
+                    unsigned int h2;
+                    int sa2;
+                    Ray er;
+                    double dist2;
+                    shadow_item(S, recs, tmp, pts, NS, (unsigned long long)h * (unsigned int)NS + (unsigned int)s, false, h2, sa2, er, dist2);
+                    const double dist = normalise_shadow_ray(er, dist2);
+                    unsigned long long dn = 0, df = 0;
+                    const bool sh = trace_shadow<false>(S, er, dist, &overflow, &dn, &df);
+                    if (sh != (res == FRT_SH_SHADOWED)) {
+                        ++n_mismatch;
+                        res = sh ? FRT_SH_SHADOWED : FRT_SH_LIT;
+                    }
+                }
+            }
+            const bool defer = active && res == FRT_SH_UNDECIDED;
+            const unsigned int dmask = __ballot_sync(0xffffffffu, defer);
+            if (dmask) {
+                unsigned int base = 0;
+                if (lane == 0) {
+                    base = atomicAdd(&cnt->n_deferred, (unsigned int)__popc(dmask));
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (defer) {
+                    const unsigned int slot = base + __popc(dmask & ((1u << lane) - 1u));
+                    if (slot < qcap) {
+                        queue[slot] = (unsigned long long)h * (unsigned int)NS + (unsigned int)s;
+                    } else {
+                        atomicOr(&cnt->overflow_queue, 1u);
+                    }
+                }
+            }
+            lit += __popc(__ballot_sync(0xffffffffu, active && res == FRT_SH_LIT));
+        }
+        if (lane == 0 && lit) {
+            atomicAdd(&tmp[h].unshadowed, lit); /* integer sums: order-independent, the frame stays reproducible */
         }
     }
     if (overflow) {
@@ -2468,6 +2650,46 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     if (prog.empty()) {
         prog.push_back(0);
     }
+    /* sphere leaves whose composite transform is a similarity (uniform scale, rotation, translation): balls in WORLD space */
+    std::vector<float4> wsph(32, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int i = 0; i < std::min(d->n_nodes, 32); ++i) {
+        const frt_node &n = d->nodes[i];
+        if (n.type != FRT_SPHERE) {
+            continue;
+        }
+        const double *m = d->xforms[n.xform].inv; /* local = A w + T */
+        double rows[3], dots[3];
+        for (int k = 0; k < 3; ++k) {
+            rows[k] = sqrt(m[4 * k] * m[4 * k] + m[4 * k + 1] * m[4 * k + 1] + m[4 * k + 2] * m[4 * k + 2]);
+        }
+        dots[0] = m[0] * m[4] + m[1] * m[5] + m[2] * m[6];
+        dots[1] = m[0] * m[8] + m[1] * m[9] + m[2] * m[10];
+        dots[2] = m[4] * m[8] + m[5] * m[9] + m[6] * m[10];
+        const double s0 = rows[0];
+        bool ok = std::isfinite(s0) && s0 > 1e-12;
+        for (int k = 0; ok && k < 3; ++k) {
+            ok = fabs(rows[k] - s0) <= 1e-12 * s0 && fabs(dots[k]) <= 1e-12 * s0 * s0;
+        }
+        if (!ok) {
+            continue;
+        }
+        /* A = s0 Q with Q orthogonal: w = A^-1 (local - T) = Q^T (local - T) / s0; the centre is the image of local 0 */
+        double c[3];
+        for (int k = 0; k < 3; ++k) {
+            c[k] = -(m[k] * m[3] + m[4 + k] * m[7] + m[8 + k] * m[11]) / (s0 * s0);
+        }
+        wsph[i] = make_float4((float)c[0], (float)c[1], (float)c[2], (float)(1.0 / s0));
+    }
+    {
+        const int rc_ = upload(sc, wsph.data(), wsph.size(), &sc->SF.wsphere);
+        if (rc_ != FRT_OK) return rc_;
+    }
+    sc->SF.entry_fast = 0u;
+    for (int i = 0; i < std::min(d->n_nodes, 32); ++i) {
+        if (node_is_entry_fast(fn.data(), prog.data(), i)) {
+            sc->SF.entry_fast |= 1u << i;
+        }
+    }
     /* per light: a parallelogram that contains every surface sample (light.c:100-191), slightly inflated */
     for (int li = 0; li < d->n_lights; ++li) {
         const frt_light &L = d->lights[li];
@@ -3403,6 +3625,8 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     const int m_inner = env_int("FRT_MESH_INNER_STEPS", FRT_MESH_INNER);
     const int m_refill = env_int("FRT_MESH_REFILL_MIN", FRT_MESH_REFILL);
     const int sblocks = env_int("FRT_SHADOW_BLOCKS", sm_blocks * 48);
+    const int eblocks = env_int("FRT_ENTRY_BLOCKS", sm_blocks * 64);
+    const int entry_kernel = env_int("FRT_ENTRY_KERNEL", 0); /* 1: one warp per pending entry (k_shadow_entry, A/B measurements: 6.5 vs 5.9 ms) */
     const bool debug_nodes = getenv("FRT_DEBUG_NODES") != nullptr;
 
     for (unsigned long long first = 0; first < total; first += chunk) {
@@ -3531,8 +3755,13 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         }                                                                                                                                         \
         tock(tk);                                                                                                                                 \
         tk = tick(FRT_ST_SHADOW_RAY);                                                                                                             \
-        k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, bulk_on, pend_cap, split_on, li, sc->dq, \
-                                                       sc->dq_cap, f32_smem != 0);                                                                \
+        if (entry_kernel) {                                                                                                                       \
+            k_shadow_entry<M><<<eblocks, 128, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, bulk_on, pend_cap, split_on, li, \
+                                                             sc->dq, sc->dq_cap, f32_smem != 0);                                                  \
+        } else {                                                                                                                                  \
+            k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, bulk_on, pend_cap, split_on, li, sc->dq, \
+                                                           sc->dq_cap, f32_smem != 0);                                                            \
+        }                                                                                                                                         \
         tock(tk);                                                                                                                                 \
     } while (0)
                         if (F.flags & FRT_FLAG_VERIFY_F32) {
@@ -3619,6 +3848,12 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         if (debug_nodes) {
             for (int k = 0; k < 32; ++k) {
                 if (hc.undecided_node[k]) fprintf(stderr, "undecided at node %d: %llu\n", k, hc.undecided_node[k]);
+            }
+            const char *cls[3] = { "straight-line", "tail, general walk", "no tail" };
+            for (int c = 0; c < 3; ++c) {
+                for (int k = 0; k < 32; ++k) {
+                    if (hc.entry_node[c][k]) fprintf(stderr, "pending entries (%s) starting at node %d: %llu\n", cls[c], k, hc.entry_node[c][k]);
+                }
             }
         }
         if (hc.overflow_queue) {

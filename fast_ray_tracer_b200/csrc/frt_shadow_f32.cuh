@@ -64,6 +64,8 @@ struct DSceneF {
     const float4 *fx;     /* per xform: rows 0..2 of the world->local matrix, then {R_0, R_1, R_2, 0} */
     const float *lpoints; /* FP32 copy of the light sample points, 3 per point */
     const float4 *wbox;   /* per node: WORLD-space bounding box {min.xyz, 0} {max.xyz, 0}, rounded outward (shaft culling) */
+    const float4 *wsphere;/* per node (first 32): {centre xyz, radius} of a sphere leaf whose transform is a similarity (a ball in
+                             WORLD space), radius 0 otherwise -- the shaft tests of k_light_pre / trace_shadow_bulk */
     const float4 *shaft;  /* per light: 4 corners of a parallelogram that contains every surface sample of the light */
     const int *csg_prog;  /* postfix programs of the outermost CSG nodes: node index of a leaf, or -(op + 1) */
     const double *lbox;   /* per light: 5 axis-aligned boxes {min xyz, max xyz} of its sample points over every cached set,
@@ -74,6 +76,7 @@ struct DSceneF {
     float ealign;         /* 2 x the largest off-axis / on-axis ratio of a transform treated as axis-aligned (<= 2e-9):
                              a WORLD box test sees the world point up to ealign |o|max, the direction up to ealign, off */
     int n_nodes;
+    unsigned int entry_fast; /* bit i: node i (< 32) is a WORLD cube leaf or a CSG over WORLD cube leaves (trace_entry_fast) */
 };
 
 /*
@@ -158,6 +161,34 @@ shaft_misses_box(const ShaftF &s, const float4 lo, const float4 hi, float ox, fl
     const float tol2 = 1e-6f * (ext + s.scale);
     for (int k = 0; k < 3; ++k) { /* the box's own faces: origin beyond a face and no ray heading back towards it */
         if ((l[k] > tol2 && s.dmax[k] <= 0.f) || (h[k] < -tol2 && s.dmin[k] >= 0.f)) {
+            return true;
+        }
+    }
+    return false;
+}
+
+/* true when the WORLD-space ball sp = {centre, radius} is provably outside the pyramid: its centre lies farther than the
+ * (inflated) radius beyond one of the pyramid's sides, or beyond the plane through o that every ray leaves */
+__device__ __forceinline__ bool
+shaft_misses_sphere(const ShaftF &s, const float4 sp, float ox, float oy, float oz)
+{
+    const float mx = sp.x - ox, my = sp.y - oy, mz = sp.z - oz;
+    const float mm = fmaxf(fabsf(mx), fmaxf(fabsf(my), fabsf(mz)));
+    /* FP32 cross products of corner directions of magnitude `scale`: the plane distances carry ~1e-6 |m| / sin(light's
+     * angular size); the inflation is two orders above that for any light wider than a few milliradians */
+    const float r = fmaf(sp.w, 1.001f, 1e-4f * (mm + s.scale));
+    const float r2 = r * r;
+    for (int i = 0; i < 4; ++i) {
+        const float dist = s.n[i][0] * mx + s.n[i][1] * my + s.n[i][2] * mz;
+        const float nn = s.n[i][0] * s.n[i][0] + s.n[i][1] * s.n[i][1] + s.n[i][2] * s.n[i][2];
+        if (dist < 0.f && dist * dist > r2 * nn * 1.0001f) { /* a dropped plane has n = 0: never true */
+            return true;
+        }
+    }
+    if (s.axis_ok) {
+        const float dist = s.ax[0] * mx + s.ax[1] * my + s.ax[2] * mz;
+        const float aa = s.ax[0] * s.ax[0] + s.ax[1] * s.ax[1] + s.ax[2] * s.ax[2];
+        if (dist < 0.f && dist * dist > r2 * aa * 1.0001f) {
             return true;
         }
     }
@@ -637,6 +668,156 @@ trace_shadow_f32(const DSceneF &SF, const float4 *fnodes, int root, int start, i
 }
 
 /*
+ * csg_combine without a data-dependent branch: inside k_shadow_entry every lane of a warp evaluates the SAME operand pair
+ * of the same CSG program for a different ray, so the operator is warp-uniform and only the orderings differ from lane
+ * to lane -- they become selects.  Same case analysis, same results as csg_combine (the templates are compared on every
+ * fixture through FRT_FLAG_VERIFY_F32).
+ */
+__device__ __forceinline__ bool
+csg_combine_sel(int op, const SpanF &L, const SpanF &R, SpanF &out)
+{
+    const bool hasL = (L.flags & 1) != 0, hasR = (R.flags & 1) != 0;
+    const bool disj = L.b_hi < R.a_lo || R.b_hi < L.a_lo;         /* disjoint for sure */
+    const bool over = L.a_hi < R.b_lo && R.a_hi < L.b_lo;         /* overlapping for sure */
+    const bool lf = L.a_hi < R.a_lo, rf = R.a_hi < L.a_lo;        /* who enters first */
+    const bool ll = R.b_hi < L.b_lo, rl = L.b_hi < R.b_lo;        /* who exits last */
+    const bool ordered = over && (lf || rf) && (ll || rl);
+    bool ok;
+    /* the result's ends: enter from span `ea` end `ea_b` (false: its a-end, true: its b-end), likewise the exit */
+    bool present, a_from_L, a_is_b, b_from_L, b_is_a;
+    if (op == FRT_CSG_UNION) {
+        /* both: [first enter, last exit]; one absent: the other */
+        ok = !(hasL && hasR) || (!disj && ordered);
+        present = hasL || hasR;
+        a_from_L = hasL && (!hasR || lf);
+        b_from_L = hasL && (!hasR || ll);
+        a_is_b = false;
+        b_is_a = false;
+    } else if (op == FRT_CSG_INTERSECT) {
+        /* both and overlapping: [later enter, earlier exit]; anything else: nothing */
+        ok = !(hasL && hasR) || disj || ordered;
+        present = hasL && hasR && !disj;
+        a_from_L = !lf;
+        b_from_L = !ll;
+        a_is_b = false;
+        b_is_a = false;
+    } else { /* difference L - R */
+        const bool both = hasL && hasR && !disj;
+        ok = !both || (ordered && !(lf && ll));                    /* R strictly inside L: two spans */
+        present = hasL && !(both && rf && rl);                     /* L inside R: nothing */
+        /* L alone, or disjoint: L.  L enters first: [L enter, R enter].  R enters first: [R exit, L exit]. */
+        a_from_L = !both || lf;
+        a_is_b = both && !lf;      /* R's exit */
+        b_from_L = !both || !lf;
+        b_is_a = both && lf;       /* R's entry */
+    }
+    const SpanF &A = a_from_L ? L : R, &B = b_from_L ? L : R;
+    out.a_lo = a_is_b ? A.b_lo : A.a_lo;
+    out.a_hi = a_is_b ? A.b_hi : A.a_hi;
+    out.b_lo = b_is_a ? B.a_lo : B.b_lo;
+    out.b_hi = b_is_a ? B.a_hi : B.b_hi;
+    const int fa = a_is_b ? ((A.flags & 4) >> 1) : (A.flags & 2);
+    const int fb = b_is_a ? ((B.flags & 2) << 1) : (B.flags & 4);
+    out.flags = present ? (1 | fa | fb) : 0;
+    return ok;
+}
+
+/*
+ * The common case of a pending entry, straight-line: the shaft walk of the (hit, quadrant) got stuck at node X and
+ * decided everything after it (tail verdict), and X is a WORLD-space cube leaf or an outermost CSG whose program runs
+ * over WORLD-space cube leaves only -- every wall, box and window of the Cornell scene.  The ray evaluates X's operands
+ * against the world frame (no transform, no tree walk, no cull: X's own bounds are not tested -- a ray that misses them
+ * misses every operand inside), combines them and judges the span; a ray X does not stop takes the tail verdict.
+ * `fast` is warp-uniform (k_shadow_entry decides it per entry).  Returns FRT_SH_* like trace_shadow_f32.
+ */
+template <bool COUNT>
+__device__ __forceinline__ int
+trace_entry_fast(const DSceneF &SF, const float4 *fnodes, int node, int tail, const FrameF &w, float D_lo, float D_hi,
+                 unsigned long long *nodes_visited, unsigned long long *flops)
+{
+    const float4 q0 = fnodes[3 * node];
+    const int flags = __float_as_int(q0.x);
+    SpanF s;
+    bool ok = true;
+    if ((flags & FRT_FN_TYPE_MASK) == FRT_CSG) {
+        int pc = __float_as_int(fnodes[3 * node + 1].w);
+        const int pc1 = pc + __float_as_int(fnodes[3 * node + 2].w);
+        {
+            const int code = __ldg(SF.csg_prog + pc);
+            const int lf = __float_as_int(fnodes[3 * code].x);
+            box_f(w, fnodes[3 * code + 1], fnodes[3 * code + 2], s.a_lo, s.a_hi, s.b_lo, s.b_hi);
+            const bool miss = s.a_lo > s.b_hi;
+            ok = ok && (miss || s.a_hi < s.b_lo);
+            s.flags = miss ? 0 : ((lf & FRT_FN_CASTS) ? 7 : 1);
+        }
+        for (pc += 1; pc < pc1; pc += 2) {
+            const int code = __ldg(SF.csg_prog + pc), op = -__ldg(SF.csg_prog + pc + 1) - 1;
+            const int lf = __float_as_int(fnodes[3 * code].x);
+            SpanF t, r;
+            box_f(w, fnodes[3 * code + 1], fnodes[3 * code + 2], t.a_lo, t.a_hi, t.b_lo, t.b_hi);
+            const bool miss = t.a_lo > t.b_hi;
+            ok = ok && (miss || t.a_hi < t.b_lo);
+            t.flags = miss ? 0 : ((lf & FRT_FN_CASTS) ? 7 : 1);
+            ok = csg_combine_sel(op, s, t, r) && ok;
+            s = r;
+        }
+        if (COUNT) {
+            const int n_ops = (pc1 - __float_as_int(fnodes[3 * node + 1].w) + 1) / 2;
+            *nodes_visited += 1 + n_ops;
+            *flops += FRT_COST_BBOX + n_ops * prim_cost(FRT_CUBE);
+        }
+    } else {
+        box_f(w, fnodes[3 * node + 1], fnodes[3 * node + 2], s.a_lo, s.a_hi, s.b_lo, s.b_hi);
+        const bool miss = s.a_lo > s.b_hi;
+        ok = miss || s.a_hi < s.b_lo;
+        s.flags = miss ? 0 : ((flags & FRT_FN_CASTS) ? 7 : 1);
+        if (COUNT) {
+            *nodes_visited += 1;
+            *flops += prim_cost(FRT_CUBE);
+        }
+    }
+    if (!ok) {
+        return FRT_SH_UNDECIDED | (5 << 4) | ((node & 31) << 8);
+    }
+    int v = 0;
+    if (s.flags) {
+        v = judge_span(s, D_lo, D_hi);
+        if (v == 3) {
+            return FRT_SH_UNDECIDED | (6 << 4) | ((node & 31) << 8);
+        }
+    }
+    if (v == 0) {
+        v = tail; /* X did not stop this ray: the shaft walk knows the rest (1 lit, 2 shadowed) */
+    }
+    return v == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
+}
+
+/* can node `i` be evaluated by trace_entry_fast?  (decided once per scene on the host: bit i of the mask) */
+static inline bool
+node_is_entry_fast(const float4 *fn, const int *prog, int i)
+{
+    auto as_int = [](float f) { int v; memcpy(&v, &f, sizeof(v)); return v; };
+    const int flags = as_int(fn[3 * i].x), type = flags & FRT_FN_TYPE_MASK;
+    auto world_cube = [&](int k) {
+        const int f = as_int(fn[3 * k].x);
+        return (f & FRT_FN_TYPE_MASK) == FRT_CUBE && (f & FRT_FN_FAST) && (f & FRT_FN_WORLD) && as_int(fn[3 * k].z) == 0;
+    };
+    if (type == FRT_CUBE) {
+        return world_cube(i);
+    }
+    if (type != FRT_CSG || !(flags & FRT_FN_FAST)) {
+        return false;
+    }
+    const int pc = as_int(fn[3 * i + 1].w), len = as_int(fn[3 * i + 2].w);
+    for (int k = pc; k < pc + len; ++k) {
+        if (prog[k] >= 0 && !world_cube(prog[k])) {
+            return false;
+        }
+    }
+    return true;
+}
+
+/*
  * All shadow rays of ONE hit at once.  They share the origin o and aim at points of the light's parallelogram, so in
  * the parametrisation  o + t (p - o)  (t = 1 is the light; t against 0, t against the light distance and the order of
  * two crossings are invariant under the per-ray scale |p - o|) every direction component d_k lies in
@@ -658,6 +839,7 @@ struct ShaftD {
     double ia[3], ib[3]; /* sgn != 0: 1 / min |d_k|, 1 / max |d_k|;  sgn == 0: 1 / max(d_k, tiny), 1 / min(d_k, -tiny) */
     int sgn[3]; /* +1 / -1: d_k has that sign on every ray and the reference divides; 0: see above */
     double en;  /* bound on the error of a slab numerator (b - o_k) */
+    float dl[3], dh[3]; /* the box of (unnormalised) ray directions p - o, slack included (shaft_sphere) */
 };
 
 __device__ __forceinline__ void
@@ -683,6 +865,8 @@ shaft_d_setup(ShaftD &s, const double *box, const double *over, double orel, flo
     for (int k = 0; k < 3; ++k) {
         dlo[k] -= sd;
         dhi[k] += sd;
+        s.dl[k] = (float)dlo[k];
+        s.dh[k] = (float)dhi[k];
         s.sgn[k] = dlo[k] > thr ? 1 : (dhi[k] < -thr ? -1 : 0);
         /* the slab quotients become products with these reciprocals (their rounding, 2^-52, sits in shaft_box_d's 1e-12) */
         if (s.sgn[k] > 0) {
@@ -761,6 +945,72 @@ shaft_leaf_span(const ShaftD &sh, const float4 q0, const float4 lo, const float4
 }
 
 /*
+ * A WORLD-space ball over the shaft (sphere_local_intersect, sphere.c:14-40, for every ray o + t (p - o), p in the box of
+ * light points).  Returns 0 = no ray has a crossing at t > 0, 1 / 2 = every ray ends its search here, lit / shadowed,
+ * 3 = cannot tell.  FP32 with margins of 2e-5 on every cosine: the quantities are O(1) geometry, FP32 evaluation and the
+ * FP32 over-point move them by ~1e-6, the reference's FP64 evaluation by 1e-15.
+ *   (B) the origin is outside the ball and every direction points away from the centre ((p - o) . (o - c) > 0): the
+ *       quadratic has b > 0, c > 0 -- no positive root.  Every shadow ray of a hit ON the ball.
+ *   (C) every corner direction of the box lies inside the ball's tangent cone (the set of hitting directions is a convex
+ *       cone, the box's directions are in the conical hull of its corners) and the far side of the ball is nearer than
+ *       the nearest light point: every ray has a positive crossing nearer than the light.
+ *   (A) a circular cone around the box's axis that contains every corner direction (hence every direction: (u . w) / |w|
+ *       is quasi-concave where positive) lies outside the tangent cone: angle(axis, centre) > cone angle + tangent angle.
+ */
+__device__ __forceinline__ int
+shaft_sphere(const ShaftD &sh, const float4 sp, bool casts)
+{
+    const float r = sp.w;
+    const float mx = sp.x - (float)sh.o[0], my = sp.y - (float)sh.o[1], mz = sp.z - (float)sh.o[2];
+    const float L2 = fmaf(mx, mx, fmaf(my, my, mz * mz)), r2 = r * r;
+    const float wm_max = fmaxf(sh.dl[0] * mx, sh.dh[0] * mx) + fmaxf(sh.dl[1] * my, sh.dh[1] * my) + fmaxf(sh.dl[2] * mz, sh.dh[2] * mz);
+    float w2max = 0.f, w2min = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        const float a = fabsf(sh.dl[k]), b = fabsf(sh.dh[k]);
+        w2max = fmaf(fmaxf(a, b), fmaxf(a, b), w2max);
+        const float lo = (sh.dl[k] > 0.f || sh.dh[k] < 0.f) ? fminf(a, b) : 0.f;
+        w2min = fmaf(lo, lo, w2min);
+    }
+    if (L2 > r2 * (1.0f + 8e-6f) && wm_max < -2e-5f * sqrtf(w2max * L2)) {
+        return 0; /* (B) */
+    }
+    if (!(L2 > 1.1025f * r2)) {
+        return 3; /* origin within 5 % of the surface: the tangent angle is ill-conditioned */
+    }
+    const float invL = rsqrtf(L2);
+    const float sina = r * invL, cosa = sqrtf(fmaxf(1.0f - sina * sina, 0.f));
+    float ux = 0.5f * (sh.dl[0] + sh.dh[0]), uy = 0.5f * (sh.dl[1] + sh.dh[1]), uz = 0.5f * (sh.dl[2] + sh.dh[2]);
+    const float u2 = fmaf(ux, ux, fmaf(uy, uy, uz * uz));
+    if (!(u2 > 1e-20f)) {
+        return 3;
+    }
+    const float iu = rsqrtf(u2);
+    ux *= iu;
+    uy *= iu;
+    uz *= iu;
+    float cmin_u = 1.0f, cmin_m = 1.0f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float wx = (c & 1) ? sh.dh[0] : sh.dl[0], wy = (c & 2) ? sh.dh[1] : sh.dl[1], wz = (c & 4) ? sh.dh[2] : sh.dl[2];
+        const float iw = rsqrtf(fmaxf(fmaf(wx, wx, fmaf(wy, wy, wz * wz)), 1e-30f));
+        cmin_u = fminf(cmin_u, fmaf(ux, wx, fmaf(uy, wy, uz * wz)) * iw);
+        cmin_m = fminf(cmin_m, fmaf(mx, wx, fmaf(my, wy, mz * wz)) * iw * invL);
+    }
+    if (cmin_m > cosa + 2e-5f && (sqrtf(L2) + r) * 1.00002f < sqrtf(w2min)) {
+        return casts ? 2 : 1; /* (C) */
+    }
+    if (!(cmin_u > 0.1f)) {
+        return 3;
+    }
+    const float sint = sqrtf(fmaxf(1.0f - cmin_u * cmin_u, 0.f));
+    const float cphi = fmaf(ux, mx, fmaf(uy, my, uz * mz)) * invL;
+    if (cphi < fmaf(cmin_u, cosa, -sint * sina) - 2e-5f) {
+        return 0; /* (A) */
+    }
+    return 3;
+}
+
+/*
  * One node of the shaft walk.  Returns 0 = no ray of the shaft ends its search here (go on at *next), 1 / 2 = every ray
  * ends it here, lit / shadowed, 3 = cannot tell (a leaf or a CSG node; *next is the node after it).
  */
@@ -823,6 +1073,10 @@ shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const
         }
     } else {
         *next = i + 1;
+        if (type == FRT_SPHERE) {
+            const float4 sp = __ldg(SF.wsphere + i);
+            return sp.w > 0.f ? shaft_sphere(sh, sp, (flags & FRT_FN_CASTS) != 0) : 3;
+        }
         if (!shaft_leaf_span(sh, q0, lo, hi, s)) {
             return 3;
         }
