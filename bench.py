@@ -171,16 +171,30 @@ def reference_arm(args) -> dict:
     counted = run_reference_frame(binary, size, SPP, threads, True) if size <= 200 else None
     rays_sample = counted["rays"] if counted else rays_per_px * size * size
     mean_s = sum(times) / len(times)
-    value = rays_sample / mean_s / 1e6
-    frame_ms = mean_s * (HSIZE * VSIZE) / (size * size) * 1e3
+    sampled_value = rays_sample / mean_s / 1e6
+    sampled_frame_ms = mean_s * (HSIZE * VSIZE) / (size * size) * 1e3
     sample = f"{size}x{size} px of the same view at 4x4 CMJ per step ({size * size / (HSIZE * VSIZE):.4f} of the frame); frame time scaled by pixel count"
+    # one frame of the workload itself (800x800, 4x4: about 80 s on 16 threads) beside the sampled steps: the line's value and
+    # ms_per_step are THIS frame's -- the same configuration as the CUDA arm -- and the sample -> frame scale factor is measured
+    full = None
+    if not args.no_ref_full:
+        f = run_reference_frame(binary, HSIZE, SPP, threads, True)  # counted: one relaxed add per ray on a per-thread cache line
+        full = {"frame_ms": f["seconds"] * 1e3, "rays": f["rays"],
+                "scale_factor_measured": f["seconds"] / mean_s, "scale_factor_by_pixel_count": (HSIZE * VSIZE) / (size * size)}
+    frame_ms = full["frame_ms"] if full else sampled_frame_ms
+    value = (full["rays"] / (full["frame_ms"] * 1e-3) / 1e6) if full else sampled_value
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "variant": args.variant, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "reference", "sample": sample,
-                         "frame_ms_800x800": frame_ms},
+        "config": {"workload": WORKLOAD, "variant": args.variant, "hsize": HSIZE, "vsize": VSIZE, "spp": SPP * SPP},
+        "measured_on": "one full 800x800 frame of the workload" if full else "sampled steps, scaled by pixel count",
+        "full_frame": full,
+        "sampled_steps": {"sample": sample, "value": sampled_value, "frame_ms_scaled": sampled_frame_ms, "step_seconds": times},
+        "build": "gcc -O2 -march=x86-64-v3 (the binary is built where the reference tree is mounted and travels to this box: -march=native "
+                 "of the build host could fault here)",
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "reference",
+                         "sample": "the full 800x800 frame" if full else sample, "frame_ms_800x800": frame_ms},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -499,9 +513,110 @@ def cuda_arm(args) -> dict:
                                  "the mean duration of its launches (CUDA events around each launch, timed frames).  The kernel is "
                                  "instruction-issue bound, not HBM bound (DRAM traffic ~1 % of peak), see DESIGN.md 4.3"},
         }
+    if not args.no_configs:
+        rows = configs_leg(args, frt, rank, world, local, dev, rpb)
+        if line is not None:
+            line["configs"] = rows
     if world > 1:
         dist.barrier()
     return line
+
+
+def configs_leg(args, frt, rank, world, local, dev, rpb) -> dict:
+    """The other BASELINE.json configs (C1, C3a, C3b, the C4 stand-in, C5), a few frames each after the headline loop, through
+    the same rows / NCCL-gather path: frame time = the slowest rank's device time, parity = the gathered frame at the
+    fixture's size against the reference's own render of that scene (deterministic scenes: share of sRGB-8 pixels within
+    1 LSB; C5: RMSE in LSB against reference render A next to the reference-vs-reference RMSE).  At N > 1 the C5 photon
+    pass is sharded over the ranks and all-gathered over NCCL (fast_ray_tracer_b200/dist.py)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from compare import parity_report, to_srgb8
+    from fast_ray_tracer_b200.dist import gather_rows, owned_rows, trace_photons_distributed
+
+    gold = REPO / "tests" / "golden"
+    blobs = REPO / "oracle" / "_ref" / "blobs"
+
+    def frame(sc, vsize, seed=0):
+        _, st = sc.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=seed)
+        full = sc.canvas_tensor()
+        if world > 1:
+            rows = torch.as_tensor(owned_rows(vsize, rank, world, rpb), device=dev, dtype=torch.long)
+            full = gather_rows(full.index_select(0, rows), vsize, rank, world, rpb)
+        return st, full
+
+    def slowest(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def run(name, blob, fixture, size, spp, reps, fixture_size=None, fixture_spp=None, photons=0):
+        if not blob.exists():
+            return {"unavailable": f"{blob.name} not built"}
+        out = {}
+        # ---- parity at the fixture's size
+        z = np.load(gold / f"{fixture}.npz") if (gold / f"{fixture}.npz").exists() else None
+        if z is not None:
+            d = frt.SceneDesc.load(blob)
+            if fixture_size:
+                d.set_resolution(*fixture_size)
+            if fixture_spp:
+                d.set_samples(*fixture_spp)
+            with frt.Scene(d, device=local) as sc:
+                if d.config.include_global and d.config.gi_photon_count > 0:
+                    trace_photons_distributed(sc, rank, world, bool(d.config.gi_include_caustics), True, seed=7)
+                _, full = frame(sc, d.camera.vsize, seed=3)
+                if rank == 0:
+                    img = full.cpu().numpy()[..., :3]
+                    ref = z["rgb"].astype(np.float64)
+                    if "rgb_b" in z.files:
+                        a8, b8, i8 = (to_srgb8(x).astype(np.float64) for x in (ref, z["rgb_b"].astype(np.float64), img))
+                        out["parity"] = {"fixture": fixture, "rmse_lsb_vs_reference": float(np.sqrt(((i8 - a8) ** 2).mean())),
+                                         "rmse_lsb_reference_vs_reference": float(np.sqrt(((a8 - b8) ** 2).mean()))}
+                    else:
+                        rep = parity_report(img, ref)
+                        out["parity"] = {"fixture": fixture, "within_1lsb": rep["within_1lsb"], "max_lsb": rep["max_lsb"]}
+        # ---- frame time at the BASELINE size
+        d = frt.SceneDesc.load(blob)
+        if size:
+            d.set_resolution(*size)
+        if spp:
+            d.set_samples(*spp)
+        if photons:
+            d.config.gi_photon_count = photons
+        with frt.Scene(d, device=local) as sc:
+            if d.config.include_global and d.config.gi_photon_count > 0:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                pst = trace_photons_distributed(sc, rank, world, bool(d.config.gi_include_caustics), True, seed=7)
+                torch.cuda.synchronize()
+                out["photon_pass_ms"] = slowest(1e3 * (time.perf_counter() - t0))
+                out["photons_stored_global"] = sc.photons_count(1)
+                out["photon_allgather_bytes"] = 32 * sc.photons_count(1) * (world - 1)  # every rank receives the other ranks' shards
+            frame(sc, d.camera.vsize, seed=11)  # warm-up (first-use buffers)
+            ms = []
+            for k in range(reps):
+                st, _ = frame(sc, d.camera.vsize, seed=20 + k)
+                ms.append(slowest(st.frame_ms))
+            out.update({"frame_ms": min(ms), "frames": reps, "hsize": d.camera.hsize, "vsize": d.camera.vsize,
+                        "spp": d.camera.usteps * d.camera.vsteps})
+        return out
+
+    rows = {
+        "C1 reflect_refract 400x200 1spp": run("C1", gold / "reflect_refract.frt", "reflect_refract", None, None, 3),
+        "C3a teapot_low 400x400 1spp": run("C3a", gold / "teapot.frt", "teapot", (400, 400), None, 3),
+        "C3b bounding_boxes 1200x480 1spp (6 dragons, 141 K triangles)": run("C3b", blobs / "bounding_boxes.frt", "bounding_boxes_600", None, None, 3,
+                                                                           fixture_size=(600, 240)),
+        "C4 stand-in 800x1000 4x4 (sibenik.obj is not in the reference tree: 85 K textured triangles, 10x10 area light)":
+            run("C4", blobs / "sibenik_surrogate.frt", "sibenik_surrogate_160", None, None, 2, fixture_size=(160, 200), fixture_spp=(2, 2)),
+        "C5 cornell GI 800x800 4x4, 1 M photons, 8x8 final gather": run("C5", gold / "cornell_gi_64.frt", "cornell_gi_64", (800, 800), (4, 4), 1,
+                                                                       photons=1000000),
+    }
+    return rows
 
 
 def cpu_baseline_leg(args) -> dict:
@@ -532,8 +647,10 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--rows-per-block", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--ref-seconds", type=float, default=150.0)
+    ap.add_argument("--ref-seconds", type=float, default=90.0)
+    ap.add_argument("--no-ref-full", action="store_true", help="reference arm: skip the one full-size frame (about 80 s on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (C1, C3, C4 stand-in, C5) after the headline loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr

@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -776,7 +777,7 @@ quadrant_sample(int4 lq, int q, int k)
 }
 
 /* pending entry: hit in bits 0..27, quadrant in bits 28..29, bit 30 = decided by k_shadow_bulk, bit 31 = ... as lit */
-#define FRT_BOX_CHUNKS 64
+#define FRT_BOX_CHUNKS 512
 #define FRT_PEND_HIT_MASK 0x0fffffffu
 #define FRT_PEND_BULK 0x40000000u
 #define FRT_PEND_LIT 0x80000000u
@@ -1961,6 +1962,7 @@ struct frt_scene {
         bool scaled = false; /* pm_scale_photon_power already applied to ra / rb */
     } pm[2];
     unsigned int *pm_stored = nullptr; /* device counters, one per map */
+    float *pm_dir_tab = nullptr;       /* the photon maps' direction tables (pm.c:54-60), 4 x 256 floats */
     float4 *pm_merged[2] = { nullptr, nullptr }; /* frt_multi_photons: every device's shard, gathered here before the import */
     bool pm_ready = false;
     GQuery *gq = nullptr;
@@ -2970,10 +2972,21 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
 
     frt_scene *sc = new frt_scene();
     sc->device = device;
+    const bool timing = getenv("FRT_DEBUG_TIMING") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (timing) {
+            auto t = std::chrono::steady_clock::now();
+            fprintf(stderr, "[frt] scene_create %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_start).count());
+            t_start = t;
+        }
+    };
     {
-        cudaDeviceProp prop;
-        sc->sm_count = cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+        /* cudaGetDeviceProperties takes milliseconds; the attribute query does not */
+        int sms = 0;
+        sc->sm_count = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0 ? sms : 148;
     }
+    lap("device attribute");
 #define UP(expr)                     \
     do {                             \
         int rc_ = (expr);            \
@@ -3016,7 +3029,9 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     UP(upload(sc, d->texels, (size_t)3 * d->n_texels, &S.texels));
     UP(upload(sc, d->lights, (size_t)d->n_lights, &S.lights));
     UP(upload(sc, d->roots, (size_t)d->n_roots, &S.roots));
+    lap("scene buffers");
     UP(build_f32_mirror(sc, d));
+    lap("fp32 mirror");
     const frt_camera &c = d->camera;
     {
         std::vector<double> table;
@@ -3053,6 +3068,7 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     }
     S.lpoints = pool64;
     sc->SF.lpoints = pool32;
+    lap("light pool allocation");
     bool async_points = false;
     unsigned int *d_mismatch = nullptr;
     if (n_gens == 0) {
@@ -3083,7 +3099,9 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
             UP(generate_light_cache(sc, d, gens[k], pool64, pool32, d_mismatch));
         }
     }
+    lap("light points enqueued");
     UP(build_light_bounds(sc, d, generated));
+    lap("light bounds enqueued");
     if (cudaEventRecord(sc->upload_ev, sc->upload_stream) != cudaSuccess) {
         frt_scene_destroy(sc);
         return frt_set_error(FRT_ERR_CUDA, "cudaEventRecord (upload) failed");
@@ -3104,6 +3122,7 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     } else if (!async_points) {
         cudaStreamSynchronize(sc->upload_stream); /* nothing of the caller's is read after this call returns */
     }
+    lap("upload stream drained");
     S.n_roots = d->n_roots;
     S.n_nodes = d->n_nodes;
     S.n_lights = d->n_lights;
@@ -3163,6 +3182,7 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
         sc->h_nrays = pinned_slot_take();
     }
 #undef UP
+    lap("canvas, events");
     *out = sc;
     return FRT_OK;
 }
@@ -4029,6 +4049,8 @@ pm_free(frt_scene *sc)
         m = frt_scene::PMap{};
     }
     cudaFree(sc->pm_stored);
+    cudaFree(sc->pm_dir_tab);
+    sc->pm_dir_tab = nullptr;
     cudaFree(sc->gq);
     cudaFree(sc->gq_n);
     cudaFree(sc->acc_amb);
@@ -4259,6 +4281,20 @@ frt_photons_finish(frt_scene *sc)
     if (!(radius > 0.f)) {
         return frt_set_error(FRT_ERR_ARG, "irradiance-estimate-radius must be positive");
     }
+    if (sc->pm_dir_tab == nullptr) {
+        /* init_Photon_map's direction tables (pm.c:54-60), evaluated in FP64 like there, stored as FP32 */
+        std::vector<float> tab(1024);
+        for (int i = 0; i < 256; ++i) {
+            const double angle = (double)i * (1.0 / 256.0) * M_PI;
+            tab[i] = (float)sin(angle);
+            tab[256 + i] = (float)cos(angle);
+            tab[512 + i] = (float)cos(2.0 * angle);
+            tab[768 + i] = (float)sin(2.0 * angle);
+        }
+        CK(cudaMalloc(&sc->pm_dir_tab, sizeof(float) * 1024));
+        CK(cudaMemcpyAsync(sc->pm_dir_tab, tab.data(), sizeof(float) * 1024, cudaMemcpyHostToDevice, sc->stream));
+        CK(cudaStreamSynchronize(sc->stream));
+    }
     for (int map = 0; map < 2; ++map) {
         frt_scene::PMap &m = sc->pm[map];
         cudaFree(m.sa);
@@ -4267,6 +4303,7 @@ frt_photons_finish(frt_scene *sc)
         m.sa = m.sb = nullptr;
         m.cell_start = nullptr;
         m.view = PMView{};
+        m.view.dir_tab = sc->pm_dir_tab;
         m.built = true;
         if (m.count == 0) {
             continue;
@@ -4296,6 +4333,7 @@ frt_photons_finish(frt_scene *sc)
         V.ny = std::max(1, (int)floorf((hi[1] - lo[1]) / cell) + 1);
         V.nz = std::max(1, (int)floorf((hi[2] - lo[2]) / cell) + 1);
         V.count = m.count;
+        V.dir_tab = sc->pm_dir_tab;
         const size_t n_cells = (size_t)V.nx * V.ny * V.nz;
         unsigned int *counts = nullptr;
         CK(cudaMalloc(&counts, sizeof(unsigned int) * n_cells));

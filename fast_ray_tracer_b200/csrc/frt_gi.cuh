@@ -34,6 +34,7 @@ struct PMView { /* one photon map as the kernels see it */
     float gx, gy, gz, inv_cell;
     int nx, ny, nz;
     unsigned int count;
+    const float *dir_tab;           /* sintheta[256] costheta[256] cosphi[256] sinphi[256]: init_Photon_map's tables (pm.c:54-60) */
 };
 
 struct GQuery { /* one radiance-estimate request */
@@ -451,16 +452,7 @@ k_pm_scatter(PMView M, const float4 *__restrict__ a, const float4 *__restrict__ 
         const float4 p = a[i];
         const unsigned int slot = atomicAdd(cursor + pm_cell_of(M, p.x, p.y, p.z), 1u);
         sa[slot] = p;
-        /* pm_photon_dir (pm.c:80-86) evaluated once here: x, y of the table direction as two halves in power.w; z follows
-         * from them and from theta < 128.  The estimate only tests the SIGN of dir . normal (pm.c:141). */
-        const unsigned int bits = __float_as_uint(p.w);
-        float st, ct, sp, cp;
-        sincospif((float)(bits & 255u) * (1.0f / 256.0f), &st, &ct);
-        sincospif((float)((bits >> 8) & 255u) * (2.0f / 256.0f), &sp, &cp);
-        float4 w = b[i];
-        const __half2 xy = __floats2half2_rn(st * cp, st * sp);
-        w.w = __uint_as_float(*reinterpret_cast<const unsigned int *>(&xy));
-        sb[slot] = w;
+        sb[slot] = b[i]; /* the 8-bit direction stays in sa[slot].w; k_knn looks it up in the reference's tables */
     }
 }
 
@@ -711,6 +703,14 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
     __shared__ float s_d2[FRT_KNN_WARPS][FRT_KNN_CAP];
     __shared__ unsigned int s_idx[FRT_KNN_WARPS][FRT_KNN_CAP];
     __shared__ unsigned int s_hist[FRT_KNN_WARPS][256];
+    __shared__ float s_dir[1024]; /* pm_photon_dir's tables (pm.c:80-86): the facing test must flip where the reference's does */
+    {
+        const float *tab = MG.dir_tab != nullptr ? MG.dir_tab : MC.dir_tab;
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
+            s_dir[k] = tab != nullptr ? __ldg(tab + k) : 0.f;
+        }
+        __syncthreads();
+    }
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned int nq = min(*n_queries, qcap);
     const unsigned int lt = (1u << lane) - 1u;
@@ -859,11 +859,10 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
                     far2 = fmaxf(far2, v);
                     const unsigned int id = idx[k];
                     const float4 pw = __ldg(M.b + id);
-                    const unsigned int theta = __float_as_uint(__ldg(M.a + id).w) & 255u;
-                    const unsigned int xyb = __float_as_uint(pw.w);
-                    const float2 xy = __half22float2(*reinterpret_cast<const __half2 *>(&xyb));
-                    const float zz = sqrtf(fmaxf(0.0f, 1.0f - xy.x * xy.x - xy.y * xy.y));
-                    const float dot = xy.x * q.ex + xy.y * q.ey + (theta < 128u ? zz : -zz) * q.ez;
+                    const unsigned int dbits = __float_as_uint(__ldg(M.a + id).w);
+                    const unsigned int theta = dbits & 255u, phi = (dbits >> 8) & 255u;
+                    const float st = s_dir[theta];
+                    const float dot = fmaf(st * s_dir[512 + phi], q.ex, fmaf(st * s_dir[768 + phi], q.ey, s_dir[256 + theta] * q.ez));
                     if (dot < 0.0f) {
                         const float w = 1.0f - sqrtf(v) * inv_kr;
                         sr = fmaf(pw.x, w, sr);

@@ -15,7 +15,7 @@
 int
 pm_oracle_estimate(long n_photons, const float *pos, const float *power, const unsigned char *theta, const unsigned char *phi,
                    long n_queries, const double *qpos, const double *qnormal, double radius, int nphotons, double cone_k,
-                   double *irrad, long *found)
+                   double *irrad, long *found, float *lost_pos, int *n_lost)
 {
     PhotonMap pm;
     init_Photon_map(n_photons, &pm);
@@ -33,6 +33,21 @@ pm_oracle_estimate(long n_photons, const float *pos, const float *power, const u
     }
     pm.stored_photons = n_photons;
     pm_balance(&pm);
+    /* pm_locate_photons only descends from nodes with index < half_stored_photons = stored / 2 - 1 (pm.c:173, :372), so the
+     * children of the last one or two inner nodes -- heap slots 2 * half_stored_photons .. stored, three or four photons --
+     * are never looked at by any query.  Report them (up to 4 positions) so that a caller can tell which queries they touch. */
+    if (n_lost != NULL) {
+        int k = 0;
+        for (long i = 2 * pm.half_stored_photons; i <= pm.stored_photons && lost_pos != NULL; ++i) {
+            if (i >= 1 && i / 2 >= pm.half_stored_photons && k < 4) {
+                lost_pos[3 * k] = (float)pm.photons[i].pos[0];
+                lost_pos[3 * k + 1] = (float)pm.photons[i].pos[1];
+                lost_pos[3 * k + 2] = (float)pm.photons[i].pos[2];
+                ++k;
+            }
+        }
+        *n_lost = k;
+    }
     for (long q = 0; q < n_queries; ++q) {
         double p[3] = { qpos[3 * q], qpos[3 * q + 1], qpos[3 * q + 2] };
         double n[3] = { qnormal[3 * q], qnormal[3 * q + 1], qnormal[3 * q + 2] };

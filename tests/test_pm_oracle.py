@@ -45,8 +45,16 @@ def test_oracle_equals_brute_force():
     qn = rng.standard_normal((300, 3))
     qn /= np.linalg.norm(qn, axis=1, keepdims=True)
     for radius, nn in ((0.1, 50), (0.3, 200)):
-        irr, found = pm_ref.estimate(pos, power, theta, phi, qpos, qn, radius, nn, 1.1)
-        want, wfound = brute_force(pos, power, theta, phi, qpos, qn, radius, nn, 1.1)
+        irr, found, lost = pm_ref.estimate(pos, power, theta, phi, qpos, qn, radius, nn, 1.1, return_lost=True)
+        # Parity hazard H15: the kd-tree search never visits heap slots 2 * (stored / 2 - 1) .. stored (pm.c:173, :372), so the
+        # reference ignores three or four photons of every map; brute force over the remaining photons is what it computes
+        assert lost.shape[0] in (3, 4)
+        keep = np.ones(n, dtype=bool)
+        for p in lost:
+            hit = np.nonzero((pos.astype(np.float64) == p).all(axis=1))[0]
+            assert hit.size == 1
+            keep[hit[0]] = False
+        want, wfound = brute_force(pos[keep], power[keep], theta[keep], phi[keep], qpos, qn, radius, nn, 1.1)
         assert np.array_equal(found, wfound)
         assert found.max() == nn and (found < 8).any() or radius > 0.2
         assert np.allclose(irr, want, rtol=1e-9, atol=1e-15)
