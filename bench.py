@@ -410,7 +410,8 @@ def cuda_arm(args) -> dict:
     e2e_steps = max(1, min(args.steps, 5))
 
     def e2e_step(k):
-        with frt.Scene(desc, device=local) as sc2:
+        # check_generated=False: the comparison of the rebuilt sample sets is read with the frame (a mismatch raises there)
+        with frt.Scene(desc, device=local, check_generated=False) as sc2:
             sc2.render(rank=rank, world=world, rows_per_block=rpb, out=out, seed=2000 + k)
 
     e2e_step(-1)  # warm-up: the first scene of a process allocates the (scene-independent, re-used) ray queues

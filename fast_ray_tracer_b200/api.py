@@ -142,7 +142,7 @@ EXPORTS = [
     "frt_photons_export", "frt_photons_import", "frt_photons_finish", "frt_measure_fma_peak",
     "frt_scene_save", "frt_scene_load", "frt_scene_desc_free", "frt_trim", "frt_host_register", "frt_host_unregister",
     "frt_ppm16_size", "frt_canvas_encode_ppm16", "frt_encode_ppm16",
-    "frt_scene_create_gen", "frt_drand48_advance", "frt_light_points_checksum", "frt_light_points_checksum_host",
+    "frt_scene_create_gen", "frt_scene_gen_status", "frt_drand48_advance", "frt_light_points_checksum", "frt_light_points_checksum_host",
     "frt_photons_estimate", "frt_multi_create", "frt_multi_destroy", "frt_multi_device_count", "frt_multi_scene",
     "frt_multi_render", "frt_multi_photons",
 ]
@@ -165,6 +165,7 @@ def load_library():
     lib.frt_device_count.restype = C.c_int
     lib.frt_scene_create.argtypes = [C.POINTER(frt_scene_desc), C.c_int, C.POINTER(C.c_void_p)]
     lib.frt_scene_create_gen.argtypes = [C.POINTER(frt_scene_desc), C.c_int, C.POINTER(frt_light_gen), C.c_int, C.POINTER(C.c_void_p)]
+    lib.frt_scene_gen_status.argtypes = [C.c_void_p]
     lib.frt_drand48_advance.argtypes = [C.c_uint64, C.c_uint64]
     lib.frt_drand48_advance.restype = C.c_uint64
     lib.frt_light_points_checksum.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]
@@ -461,7 +462,9 @@ class MultiScene:
 class Scene:
     """A scene resident in HBM on one GPU (frt_scene)."""
 
-    def __init__(self, desc: SceneDesc, device: int = 0):
+    def __init__(self, desc: SceneDesc, device: int = 0, check_generated: bool = True):
+        """check_generated: wait for the bit-for-bit comparison of rebuilt light-sample sets here (frt_scene_gen_status);
+        False leaves it to the first render(), which then raises on a mismatch -- what a per-frame host loop wants."""
         self.desc = desc
         self.device = device
         self._h = C.c_void_p()
@@ -471,6 +474,11 @@ class Scene:
         else:
             # area-light sample caches rebuilt on the device (lightcache.generate_area_light_caches)
             _check(load_library().frt_scene_create_gen(desc._ptr, device, gens, len(gens), C.byref(self._h)), "frt_scene_create_gen")
+            if check_generated:
+                rc = load_library().frt_scene_gen_status(self._h)
+                if rc != 0:
+                    self.close()
+                    _check(rc, "frt_scene_gen_status")
 
     @classmethod
     def _adopt(cls, desc: SceneDesc, device: int, handle) -> "Scene":

@@ -794,7 +794,7 @@ quadrant_sample(int4 lq, int q, int k)
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
-              int light_idx, unsigned int *__restrict__ pending, unsigned char *__restrict__ pstart, unsigned int *__restrict__ retry,
+              int light_idx, unsigned int *__restrict__ pending, unsigned int *__restrict__ pprog, unsigned int *__restrict__ retry,
               int bulk_on, int split_on)
 {
     const unsigned int n = min(cnt->n_hits[level], F.capacity);
@@ -805,7 +805,8 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += gridDim.x * blockDim.x) {
         const unsigned int h = base + (threadIdx.x & 31);
         /* 0 = nothing to do, 1 = undecided, 2 / 3 = decided shadowed / lit */
-        int state = 0, resume = root;
+        int state = 0;
+        unsigned int prog = FRT_PROG_ROOT(root);
         LightTmp t;
         t.set_a = -1;
         if (h < n) {
@@ -817,7 +818,7 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
                 ShaftD sh;
                 const double over[3] = { (double)t.ox, (double)t.oy, (double)t.oz }; /* FP32 over-point: within 2^-24 |o| of the FP64 one */
                 shaft_d_setup(sh, SF.lbox + 30 * light_idx, over, 1.2e-7, SF.bmax, SF.smin, SF.ealign);
-                const int res = trace_shadow_bulk(SF, root, t.relevant, sh, &resume);
+                const int res = trace_shadow_bulk(SF, root, t.relevant, sh, &prog);
                 if (res != FRT_SH_UNDECIDED) {
                     state = res == FRT_SH_LIT ? 3 : 2;
                     n_bulk += (unsigned int)(nq * lq.x);
@@ -837,7 +838,7 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             const unsigned int slot = warp_append(&cnt->n_pending, keep);
             if (keep) {
                 pending[slot] = h | ((unsigned int)q << 28) | (state >= 2 ? FRT_PEND_BULK : 0u) | (state == 3 ? FRT_PEND_LIT : 0u);
-                pstart[slot] = (unsigned char)(state == 1 ? resume : root);
+                pprog[slot] = state == 1 ? prog : FRT_PROG_ROOT(root);
             }
         }
     }
@@ -853,7 +854,7 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int light_idx,
-              unsigned int *__restrict__ pending, unsigned char *__restrict__ pstart, const unsigned int *__restrict__ retry)
+              unsigned int *__restrict__ pending, unsigned int *__restrict__ pprog, const unsigned int *__restrict__ retry)
 {
     const unsigned int n = min(cnt->n_deferred, F.capacity);
     const int4 lq = __ldg(SF.lquad + light_idx);
@@ -862,7 +863,8 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
     const unsigned int total = 4u * n; /* n <= 2^28 */
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += gridDim.x * blockDim.x) {
         const unsigned int item = base + (threadIdx.x & 31);
-        int state = 0, resume = root;
+        int state = 0;
+        unsigned int prog = FRT_PROG_ROOT(root);
         unsigned int h = 0;
         const int q = (int)(item & 3u);
         if (item < total) {
@@ -871,7 +873,7 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             const LightTmp t = tmp[h];
             const double over[3] = { (double)t.ox, (double)t.oy, (double)t.oz };
             shaft_d_setup(sh, SF.lbox + 30 * light_idx + 6 * (q + 1), over, 1.2e-7, SF.bmax, SF.smin, SF.ealign);
-            const int res = trace_shadow_bulk(SF, root, t.relevant, sh, &resume);
+            const int res = trace_shadow_bulk(SF, root, t.relevant, sh, &prog);
             state = res == FRT_SH_UNDECIDED ? 1 : (res == FRT_SH_LIT ? 3 : 2);
             if (state >= 2) {
                 n_bulk += (unsigned int)lq.x;
@@ -884,7 +886,7 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         const unsigned int slot = warp_append(&cnt->n_pending, keep);
         if (keep) {
             pending[slot] = h | ((unsigned int)q << 28) | (state >= 2 ? FRT_PEND_BULK : 0u) | (state == 3 ? FRT_PEND_LIT : 0u);
-            pstart[slot] = (unsigned char)(state == 1 ? resume : root);
+            pprog[slot] = state == 1 ? prog : FRT_PROG_ROOT(root);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -1022,13 +1024,22 @@ normalise_shadow_ray(Ray &sr, double dist2)
     return dist2 * inv;
 }
 
+/* the general walk as a call: the per-ray kernels' registers are sized for the straight-line path */
+template <bool COUNT>
+__device__ __noinline__ int
+trace_shadow_f32_call(const DSceneF &SF, const float4 *fnodes, int root, int start, int tail, unsigned int relevant, const FrameF &w, float omax,
+                      float eo_o, float ed_w, float D_lo, float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
+{
+    return trace_shadow_f32<COUNT>(SF, fnodes, root, start, tail, relevant, w, omax, eo_o, ed_w, D_lo, D_hi, nodes_visited, flops);
+}
+
 #ifndef FRT_SHADOW_MINB
 #define FRT_SHADOW_MINB 3
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, FRT_SHADOW_MINB)
 k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
-             const unsigned int *__restrict__ pending, const unsigned char *__restrict__ pstart, int use_start, unsigned int pend_cap,
+             const unsigned int *__restrict__ pending, const unsigned int *__restrict__ pprog, int use_start, unsigned int pend_cap,
              int split_on, int light_idx,
              unsigned long long *__restrict__ queue, unsigned int qcap, int nodes_in_smem)
 {
@@ -1064,11 +1075,11 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
         int s = 0;
         float4 head = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         unsigned int entry = 0;
-        int start = root;
+        unsigned int prog = FRT_PROG_ROOT(root);
         if (item < total) {
             const unsigned int idx = NSQ > 1 ? (unsigned int)__umul64hi(item, ns_magic) : (unsigned int)item; /* item / NSQ, exact while item * NSQ < 2^64 */
             entry = __ldg(pending + idx);
-            start = (int)__ldg(pstart + idx);
+            prog = __ldg(pprog + idx);
             s = quadrant_sample(lq, (entry >> 28) & 3, (int)(item - (unsigned long long)idx * (unsigned int)NSQ));
             h = entry & FRT_PEND_HIT_MASK;
             head = *reinterpret_cast<const float4 *>(tmp + h);
@@ -1104,8 +1115,15 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                 const float ed_w = fmaf(2.0f * FRT_F32_U * (pmax + omax), rinv, FRT_F32_G + SF.ealign);
                 frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
                 const float Df = len2 * rinv;
-                res = trace_shadow_f32<COUNT>(SF, fnodes, root, use_start ? (start & FRT_RESUME_NODE_MASK) : root,
-                                            use_start ? (start >> FRT_RESUME_TAIL_SHIFT) : 0, relevant, w, omax, eo_o, ed_w, Df - Df * ed_w, Df + Df * ed_w, &n_nodes, &n_flops);
+                const float D_lo = Df - Df * ed_w, D_hi = Df + Df * ed_w;
+                if (use_start && entry_program_is_fast(prog, SF.entry_fast)) {
+                    res = trace_entry_program<COUNT>(SF, fnodes, prog, w, omax, eo_o, D_lo, D_hi, &n_nodes, &n_flops);
+                } else {
+                    /* the general walk from X1; a single-node program's tail verdict still ends it right after X1 */
+                    const int tail = (use_start && FRT_PROG_COUNT(prog) == 1) ? FRT_PROG_TAIL(prog) : 0;
+                    res = trace_shadow_f32_call<COUNT>(SF, fnodes, root, use_start ? FRT_PROG_NODE(prog, 0) : root, tail, relevant, w, omax, eo_o, ed_w,
+                                                     D_lo, D_hi, &n_nodes, &n_flops);
+                }
                 if (COUNT && (res >> 4)) {
                     atomicAdd(&cnt->undecided_reason[min((res >> 4) & 15, 9)], 1ull);
                     atomicAdd(&cnt->undecided_node[(res >> 8) & 31], 1ull);
@@ -1178,22 +1196,13 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
  * k_shadow_f32 (profiles/r2a_k_shadow_f32_lines.txt): 1 030 warp-instructions per 32 rays at 23.3 active lanes, box tests
  * at 19.7 and the CSG combination at 15 lanes -- the warps there hold the tail of one entry and the head of the next.
  */
-/* the general walk as a call: k_shadow_entry's registers are sized for the straight-line path */
-template <bool COUNT>
-__device__ __noinline__ int
-trace_shadow_f32_call(const DSceneF &SF, const float4 *fnodes, int root, int start, int tail, unsigned int relevant, const FrameF &w, float omax,
-                      float eo_o, float ed_w, float D_lo, float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
-{
-    return trace_shadow_f32<COUNT>(SF, fnodes, root, start, tail, relevant, w, omax, eo_o, ed_w, D_lo, D_hi, nodes_visited, flops);
-}
-
 #ifndef FRT_ENTRY_MINB
 #define FRT_ENTRY_MINB 6
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(128, FRT_ENTRY_MINB)
 k_shadow_entry(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt,
-               const unsigned int *__restrict__ pending, const unsigned char *__restrict__ pstart, int use_start, unsigned int pend_cap,
+               const unsigned int *__restrict__ pending, const unsigned int *__restrict__ pprog, int use_start, unsigned int pend_cap,
                int split_on, int light_idx, unsigned long long *__restrict__ queue, unsigned int qcap, int nodes_in_smem)
 {
     constexpr bool COUNT = MODE != 0;
@@ -1224,7 +1233,7 @@ k_shadow_entry(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
 
     for (unsigned int e = wid; e < n; e += warps) {
         const unsigned int entry = __ldg(pending + e);
-        const int start = (int)__ldg(pstart + e);
+        const unsigned int prog = use_start ? __ldg(pprog + e) : FRT_PROG_ROOT(root);
         const unsigned int h = entry & FRT_PEND_HIT_MASK;
         const int q = (int)((entry >> 28) & 3u);
         const float4 head = *reinterpret_cast<const float4 *>(tmp + h);
@@ -1234,16 +1243,16 @@ k_shadow_entry(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
         }
         const unsigned int relevant = tmp[h].relevant;
         const int bulk = MODE != 0 ? (int)(entry >> 30) : 0; /* bit 0: decided by k_shadow_bulk, bit 1: as lit */
-        const int node = use_start ? (start & FRT_RESUME_NODE_MASK) : root;
-        const int tail = use_start ? (start >> FRT_RESUME_TAIL_SHIFT) : 0;
-        const bool fast = tail != 0 && node < 32 && ((SF.entry_fast >> node) & 1u) && S.n_roots == 1;
+        const int node = FRT_PROG_NODE(prog, 0);
+        const int tail = FRT_PROG_COUNT(prog) == 1 ? FRT_PROG_TAIL(prog) : 0; /* for the general walk from X1 */
+        const bool fast = use_start && S.n_roots == 1 && entry_program_is_fast(prog, SF.entry_fast);
         /* per entry: the origin's error terms */
         const float omax = fmaxf(fmaxf(fabsf(head.x), fabsf(head.y)), fabsf(head.z));
         const float eo_o = 2.0f * FRT_F32_U * omax;
         const float eo_w = bmax_term + fmaf(SF.ealign, omax, eo_o);
         const float *set_pts = fpts + 3 * (size_t)set_a * NS;
         if (COUNT && lane == 0 && !bulk) {
-            atomicAdd(&cnt->entry_node[fast ? 0 : (tail != 0 ? 1 : 2)][node & 31], 1ull);
+            atomicAdd(&cnt->entry_node[fast ? 0 : (FRT_PROG_TAIL(prog) != 0 ? 1 : 2)][(FRT_PROG_COUNT(prog) - 1) * 8 + min(node, 7)], 1ull);
         }
         int lit = 0;
         for (int k0 = 0; k0 < NSQ; k0 += 32) {
@@ -1275,7 +1284,7 @@ k_shadow_entry(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
                     const float Df = len2 * rinv;
                     const float D_lo = Df - Df * ed_w, D_hi = Df + Df * ed_w;
                     if (fast) {
-                        res = trace_entry_fast<COUNT>(SF, fnodes, node, tail, w, D_lo, D_hi, &n_nodes, &n_flops);
+                        res = trace_entry_program<COUNT>(SF, fnodes, prog, w, omax, eo_o, D_lo, D_hi, &n_nodes, &n_flops);
                     } else {
                         res = trace_shadow_f32_call<COUNT>(SF, fnodes, root, node, tail, relevant, w, omax, eo_o, ed_w, D_lo, D_hi, &n_nodes, &n_flops);
                     }
@@ -1932,6 +1941,9 @@ struct frt_scene {
     cudaEvent_t upload_ev = nullptr, ready_ev = nullptr;
     int sm_count = 148;
     bool upload_pending = false;          /* the render stream has not waited for upload_ev yet */
+    unsigned int *gen_mismatch = nullptr; /* device word: words in which a rebuilt light-sample set differs from the caller's */
+    bool gen_check_pending = false;       /* nobody has looked at it yet */
+    bool gen_failed = false;
     unsigned int *h_nrays = nullptr; /* pinned: the next level's ray count, read back behind k_shade without stalling the stream */
     cudaEvent_t nrays_ev = nullptr;
     LightTmp *ltmp_multi = nullptr; /* mesh mode with several lights: one LightTmp array per light of a shared launch */
@@ -2059,8 +2071,15 @@ static cudaError_t
 scene_alloc(frt_scene *sc, void **p, size_t bytes)
 {
     bytes = std::max<size_t>(bytes, 1);
+    if (bytes < FRT_BLOCK_CACHE_MIN) { /* small buffers (tree, materials, tables) share a few power-of-two sizes */
+        size_t r = 512;
+        while (r < bytes) {
+            r <<= 1;
+        }
+        bytes = r;
+    }
     *p = nullptr;
-    if (bytes >= FRT_BLOCK_CACHE_MIN) {
+    {
         std::lock_guard<std::mutex> lk(g_park_mu);
         BlockCache &c = g_blocks[sc->device];
         auto it = c.blocks.find(bytes);
@@ -2088,7 +2107,7 @@ scene_release_allocs(frt_scene *sc)
     BlockCache &c = g_blocks[sc->device];
     for (size_t i = 0; i < sc->allocs.size(); ++i) {
         const size_t bytes = i < sc->alloc_bytes.size() ? sc->alloc_bytes[i] : 0;
-        if (bytes >= FRT_BLOCK_CACHE_MIN && c.bytes + bytes <= FRT_BLOCK_CACHE_MAX) {
+        if (bytes > 0 && c.bytes + bytes <= FRT_BLOCK_CACHE_MAX) {
             c.blocks.emplace(bytes, sc->allocs[i]);
             c.bytes += bytes;
         } else {
@@ -2128,6 +2147,63 @@ pinned_slot_give(unsigned int *p)
     if (p != nullptr) {
         std::lock_guard<std::mutex> lk(g_park_mu);
         g_pinned_free.push_back(p);
+    }
+}
+
+/* streams and events of destroyed scenes, per device (creating two streams and a dozen events costs a small frame) */
+struct HandlePool {
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> timed, untimed;
+};
+static std::map<int, HandlePool> g_handles; /* under g_park_mu */
+
+static cudaError_t
+pool_stream(int device, cudaStream_t *out)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        HandlePool &h = g_handles[device];
+        if (!h.streams.empty()) {
+            *out = h.streams.back();
+            h.streams.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+
+static cudaError_t
+pool_event(int device, bool timed, cudaEvent_t *out)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        HandlePool &h = g_handles[device];
+        std::vector<cudaEvent_t> &v = timed ? h.timed : h.untimed;
+        if (!v.empty()) {
+            *out = v.back();
+            v.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return timed ? cudaEventCreate(out) : cudaEventCreateWithFlags(out, cudaEventDisableTiming);
+}
+
+static void
+pool_give(int device, cudaStream_t s)
+{
+    if (s != nullptr) {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        g_handles[device].streams.push_back(s);
+    }
+}
+
+static void
+pool_give(int device, bool timed, cudaEvent_t e)
+{
+    if (e != nullptr) {
+        std::lock_guard<std::mutex> lk(g_park_mu);
+        HandlePool &h = g_handles[device];
+        (timed ? h.timed : h.untimed).push_back(e);
     }
 }
 
@@ -2181,6 +2257,13 @@ frt_trim(int device)
     if (it != g_parked.end()) {
         frameset_free(it->second);
         g_parked.erase(it);
+    }
+    auto ht = g_handles.find(device);
+    if (ht != g_handles.end()) {
+        for (cudaStream_t st : ht->second.streams) cudaStreamDestroy(st);
+        for (cudaEvent_t e : ht->second.timed) cudaEventDestroy(e);
+        for (cudaEvent_t e : ht->second.untimed) cudaEventDestroy(e);
+        g_handles.erase(ht);
     }
     auto bt = g_blocks.find(device);
     if (bt != g_blocks.end()) {
@@ -2375,20 +2458,19 @@ frt_scene_destroy(frt_scene *sc)
             cudaFree(p);
         }
     }
+    /* both streams are idle here (synchronised above): they and the events go back to the device's pool */
     for (auto &e : sc->ev) {
-        if (e) cudaEventDestroy(e);
+        pool_give(sc->device, true, e);
     }
-    if (sc->nrays_ev) cudaEventDestroy(sc->nrays_ev);
+    pool_give(sc->device, false, sc->nrays_ev);
     pinned_slot_give(sc->h_nrays);
-    if (sc->upload_ev) cudaEventDestroy(sc->upload_ev);
-    if (sc->ready_ev) cudaEventDestroy(sc->ready_ev);
-    if (sc->upload_stream) cudaStreamDestroy(sc->upload_stream);
+    pool_give(sc->device, false, sc->upload_ev);
+    pool_give(sc->device, false, sc->ready_ev);
+    pool_give(sc->device, sc->upload_stream);
     for (auto &e : sc->light_ev) {
-        cudaEventDestroy(e);
+        pool_give(sc->device, true, e);
     }
-    if (sc->stream) {
-        cudaStreamDestroy(sc->stream);
-    }
+    pool_give(sc->device, sc->stream);
     delete sc;
 }
 
@@ -2688,7 +2770,7 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     }
     sc->SF.entry_fast = 0u;
     for (int i = 0; i < std::min(d->n_nodes, 32); ++i) {
-        if (node_is_entry_fast(fn.data(), prog.data(), i)) {
+        if (node_is_entry_fast(fn.data(), prog.data(), wsph.data(), i)) {
             sc->SF.entry_fast |= 1u << i;
         }
     }
@@ -2998,10 +3080,8 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     /* two streams: everything the host hands over travels on the upload stream, the frame runs on the render stream.
      * The render stream waits for `ready_ev` (the small buffers: tree, materials, mirror) before its first kernel and
      * for `upload_ev` (the light points and what is derived from them) where its first light stage begins. */
-    if (cudaStreamCreateWithFlags(&sc->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&sc->upload_ev, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&sc->ready_ev, cudaEventDisableTiming) != cudaSuccess) {
+    if (pool_stream(device, &sc->upload_stream) != cudaSuccess || pool_stream(device, &sc->stream) != cudaSuccess ||
+        pool_event(device, false, &sc->upload_ev) != cudaSuccess || pool_event(device, false, &sc->ready_ev) != cudaSuccess) {
         frt_scene_destroy(sc);
         return frt_set_error(FRT_ERR_CUDA, "cudaStreamCreate failed");
     }
@@ -3108,17 +3188,9 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     }
     sc->upload_pending = true;
     if (d_mismatch != nullptr) {
-        unsigned int bad = 0;
-        if (cudaMemcpyAsync(&bad, d_mismatch, sizeof(bad), cudaMemcpyDeviceToHost, sc->upload_stream) != cudaSuccess ||
-            cudaStreamSynchronize(sc->upload_stream) != cudaSuccess) {
-            frt_scene_destroy(sc);
-            return frt_set_error(FRT_ERR_CUDA, "light generator: %s", cudaGetErrorString(cudaGetLastError()));
-        }
-        if (bad) {
-            frt_scene_destroy(sc);
-            return frt_set_error(FRT_ERR_MISMATCH, "a light-sample set rebuilt on the device differs from the caller's in %u words "
-                                                   "(another drand48 state, or another sampler): upload the host cache instead", bad);
-        }
+        /* the comparison runs behind this call: frt_scene_gen_status waits for it; frt_render reads it with its first frame */
+        sc->gen_mismatch = d_mismatch;
+        sc->gen_check_pending = true;
     } else if (!async_points) {
         cudaStreamSynchronize(sc->upload_stream); /* nothing of the caller's is read after this call returns */
     }
@@ -3172,13 +3244,13 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     }
     sc->canvas = (double *)cv;
     for (auto &e : sc->ev) {
-        if (cudaEventCreate(&e) != cudaSuccess) {
+        if (pool_event(device, true, &e) != cudaSuccess) {
             frt_scene_destroy(sc);
             return frt_set_error(FRT_ERR_CUDA, "cudaEventCreate failed");
         }
     }
     /* one pinned slot per scene (recycled through a per-process free list): the next level's ray count lands here */
-    if (cudaEventCreateWithFlags(&sc->nrays_ev, cudaEventDisableTiming) == cudaSuccess) {
+    if (pool_event(device, false, &sc->nrays_ev) == cudaSuccess) {
         sc->h_nrays = pinned_slot_take();
     }
 #undef UP
@@ -3267,8 +3339,8 @@ ensure_frame_buffers(frt_scene *sc, unsigned int capacity)
     FA(sc->ltmp);
 #undef FA
     {
-        /* one entry per (hit, quadrant of the light's sample grid), then one byte per entry: the node its rays start at */
-        int rc_ = frame_alloc(sc, &sc->pending, (size_t)capacity * 5);
+        /* one entry per (hit, quadrant of the light's sample grid), then one word per entry: its program (frt_shadow_f32.cuh) */
+        int rc_ = frame_alloc(sc, &sc->pending, (size_t)capacity * 8);
         if (rc_ != FRT_OK) {
             return rc_;
         }
@@ -3621,7 +3693,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         const size_t i = span_stage.size();
         while (sc->light_ev.size() < 2 * (i + 1)) {
             cudaEvent_t e = nullptr;
-            if (cudaEventCreate(&e) != cudaSuccess) {
+            if (pool_event(sc->device, true, &e) != cudaSuccess) {
                 tick_failed = true;
                 return -1;
             }
@@ -3763,23 +3835,23 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         const int split_on = bulk_on && !(F.flags & FRT_FLAG_NO_SPLIT);
                         const unsigned int pend_cap = sc->capacity * 4u;
                         unsigned int *retry = reinterpret_cast<unsigned int *>(sc->dq); /* free until k_shadow_f32 defers rays */
-                        unsigned char *pstart = reinterpret_cast<unsigned char *>(sc->pending + (size_t)sc->capacity * 4);
+                        unsigned int *pprog = sc->pending + (size_t)sc->capacity * 4; /* one program word per pending entry */
 #define FRT_SHADOW_STAGE(M)                                                                                                                       \
     do {                                                                                                                                          \
         tk = tick(FRT_ST_SHADOW_SHAFT);                                                                                                           \
-        k_shadow_bulk<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pstart, retry, bulk_on, split_on);  \
+        k_shadow_bulk<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pprog, retry, bulk_on, split_on);  \
         if (split_on) {                                                                                                                           \
-            k_shadow_quad<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, pstart, retry);                        \
+            k_shadow_quad<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, pprog, retry);                        \
             CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));                                                                \
             launches += 1;                                                                                                                        \
         }                                                                                                                                         \
         tock(tk);                                                                                                                                 \
         tk = tick(FRT_ST_SHADOW_RAY);                                                                                                             \
         if (entry_kernel) {                                                                                                                       \
-            k_shadow_entry<M><<<eblocks, 128, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, bulk_on, pend_cap, split_on, li, \
+            k_shadow_entry<M><<<eblocks, 128, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pprog, bulk_on, pend_cap, split_on, li, \
                                                              sc->dq, sc->dq_cap, f32_smem != 0);                                                  \
         } else {                                                                                                                                  \
-            k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pstart, bulk_on, pend_cap, split_on, li, sc->dq, \
+            k_shadow_f32<M><<<sblocks, 256, f32_smem, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, sc->pending, pprog, bulk_on, pend_cap, split_on, li, sc->dq, \
                                                            sc->dq_cap, f32_smem != 0);                                                            \
         }                                                                                                                                         \
         tock(tk);                                                                                                                                 \
@@ -3931,6 +4003,37 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     return FRT_OK;
 }
 
+static int
+gen_check(frt_scene *sc, cudaStream_t s)
+{
+    if (!sc->gen_check_pending) {
+        return FRT_OK;
+    }
+    unsigned int bad = 0;
+    CK(cudaMemcpyAsync(&bad, sc->gen_mismatch, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    sc->gen_check_pending = false;
+    sc->gen_failed = bad != 0;
+    if (bad) {
+        return frt_set_error(FRT_ERR_MISMATCH, "a light-sample set rebuilt on the device differs from the caller's in %u words "
+                                               "(another drand48 state, or another sampler): upload the host cache instead", bad);
+    }
+    return FRT_OK;
+}
+
+extern "C" int
+frt_scene_gen_status(frt_scene *sc)
+{
+    if (sc == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_scene_gen_status: null scene");
+    }
+    CK(cudaSetDevice(sc->device));
+    if (sc->gen_failed) {
+        return frt_set_error(FRT_ERR_MISMATCH, "a light-sample set rebuilt on the device differs from the caller's");
+    }
+    return gen_check(sc, sc->upload_stream);
+}
+
 extern "C" int
 frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_stats *stats)
 {
@@ -3938,6 +4041,9 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
         return frt_set_error(FRT_ERR_ARG, "frt_render: null argument");
     }
     CK(cudaSetDevice(sc->device));
+    if (sc->gen_failed) {
+        return frt_set_error(FRT_ERR_MISMATCH, "a light-sample set rebuilt on the device differs from the caller's");
+    }
     frt_stats st;
     memset(&st, 0, sizeof(st));
 
@@ -3975,6 +4081,12 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
     }
     if (rc != FRT_OK) {
         return rc;
+    }
+    if (sc->gen_check_pending) { /* the frame is done: the comparison (upload stream) finished long ago */
+        rc = gen_check(sc, sc->upload_stream);
+        if (rc != FRT_OK) {
+            return rc;
+        }
     }
     if (canvas_rgba != nullptr) {
         cudaEvent_t e0 = sc->ev[2], e1 = sc->ev[3];

@@ -76,7 +76,7 @@ struct DSceneF {
     float ealign;         /* 2 x the largest off-axis / on-axis ratio of a transform treated as axis-aligned (<= 2e-9):
                              a WORLD box test sees the world point up to ealign |o|max, the direction up to ealign, off */
     int n_nodes;
-    unsigned int entry_fast; /* bit i: node i (< 32) is a WORLD cube leaf or a CSG over WORLD cube leaves (trace_entry_fast) */
+    unsigned int entry_fast; /* bit i: node i (< 32) is a WORLD cube leaf, a CSG over WORLD cube leaves or a WORLD ball (entry_node_span) */
 };
 
 /*
@@ -418,6 +418,8 @@ judge_span(const SpanT<T> &s, T D_lo, T D_hi)
     return (ea | eb) ? 3 : 1;
 }
 
+__device__ __forceinline__ bool sphere_span(const FrameF &f, float r2, float dr2, SpanF &s);
+
 /* one cube or sphere leaf as a span; false = undecided */
 __device__ __forceinline__ bool
 leaf_span(int type, const float4 lo, const float4 hi, const FrameF &f, SpanF &s)
@@ -434,16 +436,27 @@ leaf_span(int type, const float4 lo, const float4 hi, const FrameF &f, SpanF &s)
         s.flags = 1;
         return true;
     }
-    /* sphere_local_intersect, sphere.c:14-40 */
+    return sphere_span(f, 1.0f, 0.0f, s);
+}
+
+/*
+ * sphere_local_intersect (sphere.c:14-40) for the ray of frame f against the ball |x|^2 = r2 (r2 known up to dr2): the unit
+ * sphere of a leaf's own frame (r2 = 1), or a WORLD-space ball with f = the world ray moved to its centre -- a similarity
+ * transform scales a, b and c of the quadratic alike, the roots are the reference's.  false = undecided.
+ */
+__device__ __forceinline__ bool
+sphere_span(const FrameF &f, float r2, float dr2, SpanF &s)
+{
+    s.flags = 0;
     const float So = fabsf(f.ox) + fabsf(f.oy) + fabsf(f.oz), Sd = fabsf(f.dx) + fabsf(f.dy) + fabsf(f.dz);
     const float a = fmaf(f.dx, f.dx, fmaf(f.dy, f.dy, f.dz * f.dz));
     const float hb = fmaf(f.dx, f.ox, fmaf(f.dy, f.oy, f.dz * f.oz));
     const float habs = fmaf(fabsf(f.dx), fabsf(f.ox), fmaf(fabsf(f.dy), fabsf(f.oy), fabsf(f.dz * f.oz)));
     const float oo = fmaf(f.ox, f.ox, fmaf(f.oy, f.oy, f.oz * f.oz));
-    const float b = 2.0f * hb, c = oo - 1.0f;
+    const float b = 2.0f * hb, c = oo - r2;
     const float da = fmaf(2.0f * Sd + 3.0f * f.ed, f.ed, FRT_F32_G * a);
     const float db = 2.0f * (fmaf(Sd, f.eo, fmaf(So, f.ed, 3.0f * f.eo * f.ed)) + FRT_F32_G * habs);
-    const float dc = fmaf(2.0f * So + 3.0f * f.eo, f.eo, FRT_F32_G * (oo + 1.0f));
+    const float dc = fmaf(2.0f * So + 3.0f * f.eo, f.eo, FRT_F32_G * (oo + r2)) + dr2;
     const float disc = fmaf(b, b, -4.0f * a * c);
     const float dD = fmaf(2.0f * fabsf(b) + db, db, 4.0f * (fmaf(a, dc, fmaf(fabsf(c), da, da * dc)))) +
                      FRT_F32_G * fmaf(b, b, 4.0f * a * fabsf(c));
@@ -723,23 +736,33 @@ csg_combine_sel(int op, const SpanF &L, const SpanF &R, SpanF &out)
 }
 
 /*
- * The common case of a pending entry, straight-line: the shaft walk of the (hit, quadrant) got stuck at node X and
- * decided everything after it (tail verdict), and X is a WORLD-space cube leaf or an outermost CSG whose program runs
- * over WORLD-space cube leaves only -- every wall, box and window of the Cornell scene.  The ray evaluates X's operands
- * against the world frame (no transform, no tree walk, no cull: X's own bounds are not tested -- a ray that misses them
- * misses every operand inside), combines them and judges the span; a ray X does not stop takes the tail verdict.
- * `fast` is warp-uniform (k_shadow_entry decides it per entry).  Returns FRT_SH_* like trace_shadow_f32.
+ * What the shaft walk of a (hit, quadrant) leaves to its rays: a PROGRAM of up to FRT_PROG_MAX nodes X1 < X2 < X3 at which
+ * the walk could not tell (in the reference's order; every node between and before them was passed with a decided "ends
+ * no search" for every ray of the shaft) and the verdict the walk reached for the rays none of them stops (trace_shadow_bulk):
+ *     bits 0..1  tail: 1 lit, 2 shadowed, 0 = the walk got stuck more often than the program holds (general walk from X1)
+ *     bits 2..3  number of nodes (1..3)
+ *     bits 4..8, 9..13, 14..18  X1, X2, X3
+ * A ray evaluates X1, X2, ... in turn and takes the first one's verdict that stops it, else the tail (trace_entry_program).
+ * Nodes it can evaluate without the tree walk (DSceneF::entry_fast): WORLD-space cube leaves, outermost CSGs whose program
+ * runs over WORLD-space cube leaves (every wall, box and window of the Cornell scene: X's own bounds are not tested -- a
+ * ray that misses them misses every operand inside) and WORLD-space balls (DSceneF::wsphere).
  */
+#define FRT_PROG_MAX 3
+#define FRT_PROG_ROOT(root) ((1u << 2) | ((unsigned int)(root) << 4)) /* one node, no tail: the general walk from `root` */
+#define FRT_PROG_TAIL(p) ((int)((p) & 3u))
+#define FRT_PROG_COUNT(p) ((int)(((p) >> 2) & 3u))
+#define FRT_PROG_NODE(p, k) ((int)(((p) >> (4 + 5 * (k))) & 31u))
+
+/* one program node as a span (flags 0: the ray does not cross it); false = undecided */
 template <bool COUNT>
-__device__ __forceinline__ int
-trace_entry_fast(const DSceneF &SF, const float4 *fnodes, int node, int tail, const FrameF &w, float D_lo, float D_hi,
-                 unsigned long long *nodes_visited, unsigned long long *flops)
+__device__ __forceinline__ bool
+entry_node_span(const DSceneF &SF, const float4 *fnodes, int node, const FrameF &w, float omax, float eo_o, SpanF &s,
+                unsigned int &visited, unsigned int &cost)
 {
     const float4 q0 = fnodes[3 * node];
-    const int flags = __float_as_int(q0.x);
-    SpanF s;
+    const int flags = __float_as_int(q0.x), type = flags & FRT_FN_TYPE_MASK;
     bool ok = true;
-    if ((flags & FRT_FN_TYPE_MASK) == FRT_CSG) {
+    if (type == FRT_CSG) {
         int pc = __float_as_int(fnodes[3 * node + 1].w);
         const int pc1 = pc + __float_as_int(fnodes[3 * node + 2].w);
         {
@@ -747,7 +770,7 @@ trace_entry_fast(const DSceneF &SF, const float4 *fnodes, int node, int tail, co
             const int lf = __float_as_int(fnodes[3 * code].x);
             box_f(w, fnodes[3 * code + 1], fnodes[3 * code + 2], s.a_lo, s.a_hi, s.b_lo, s.b_hi);
             const bool miss = s.a_lo > s.b_hi;
-            ok = ok && (miss || s.a_hi < s.b_lo);
+            ok = miss || s.a_hi < s.b_lo;
             s.flags = miss ? 0 : ((lf & FRT_FN_CASTS) ? 7 : 1);
         }
         for (pc += 1; pc < pc1; pc += 2) {
@@ -763,8 +786,30 @@ trace_entry_fast(const DSceneF &SF, const float4 *fnodes, int node, int tail, co
         }
         if (COUNT) {
             const int n_ops = (pc1 - __float_as_int(fnodes[3 * node + 1].w) + 1) / 2;
-            *nodes_visited += 1 + n_ops;
-            *flops += FRT_COST_BBOX + n_ops * prim_cost(FRT_CUBE);
+            visited += 1 + n_ops;
+            cost += FRT_COST_BBOX + n_ops * prim_cost(FRT_CUBE);
+        }
+    } else if (type == FRT_SPHERE) {
+        /* the world ray moved to the ball's centre: o - c carries the rounding of o (eo_o), of c (u |c|) and of the difference */
+        const float4 sp = __ldg(SF.wsphere + node);
+        FrameF f;
+        f.ox = w.ox - sp.x;
+        f.oy = w.oy - sp.y;
+        f.oz = w.oz - sp.z;
+        f.dx = w.dx;
+        f.dy = w.dy;
+        f.dz = w.dz;
+        const float cmax = fmaxf(fmaxf(fabsf(sp.x), fabsf(sp.y)), fabsf(sp.z));
+        f.eo = eo_o + 2.0f * FRT_F32_U * (omax + cmax);
+        f.ed = w.ed;
+        const float r2 = sp.w * sp.w;
+        ok = sphere_span(f, r2, 4.0f * FRT_F32_U * r2, s);
+        if (s.flags && (flags & FRT_FN_CASTS)) {
+            s.flags |= 6;
+        }
+        if (COUNT) {
+            visited += 1;
+            cost += prim_cost(FRT_SPHERE);
         }
     } else {
         box_f(w, fnodes[3 * node + 1], fnodes[3 * node + 2], s.a_lo, s.a_hi, s.b_lo, s.b_hi);
@@ -772,29 +817,64 @@ trace_entry_fast(const DSceneF &SF, const float4 *fnodes, int node, int tail, co
         ok = miss || s.a_hi < s.b_lo;
         s.flags = miss ? 0 : ((flags & FRT_FN_CASTS) ? 7 : 1);
         if (COUNT) {
-            *nodes_visited += 1;
-            *flops += prim_cost(FRT_CUBE);
+            visited += 1;
+            cost += prim_cost(FRT_CUBE);
         }
     }
-    if (!ok) {
-        return FRT_SH_UNDECIDED | (5 << 4) | ((node & 31) << 8);
-    }
-    int v = 0;
-    if (s.flags) {
-        v = judge_span(s, D_lo, D_hi);
-        if (v == 3) {
-            return FRT_SH_UNDECIDED | (6 << 4) | ((node & 31) << 8);
-        }
-    }
-    if (v == 0) {
-        v = tail; /* X did not stop this ray: the shaft walk knows the rest (1 lit, 2 shadowed) */
-    }
-    return v == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
+    return ok;
 }
 
-/* can node `i` be evaluated by trace_entry_fast?  (decided once per scene on the host: bit i of the mask) */
+/* the program of a pending entry for one ray; the caller checked that every node is in DSceneF::entry_fast and tail != 0.
+ * Returns FRT_SH_* like trace_shadow_f32 (reason / node of an undecided ray in bits 4.. for the counting build). */
+template <bool COUNT>
+__device__ __forceinline__ int
+trace_entry_program(const DSceneF &SF, const float4 *fnodes, unsigned int prog, const FrameF &w, float omax, float eo_o, float D_lo,
+                    float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
+{
+    const int n = FRT_PROG_COUNT(prog);
+    unsigned int visited = 0, cost = 0;
+    int res = FRT_PROG_TAIL(prog) == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT; /* the rays no node stops */
+    for (int k = 0; k < n; ++k) {
+        const int node = FRT_PROG_NODE(prog, k);
+        SpanF s;
+        if (!entry_node_span<COUNT>(SF, fnodes, node, w, omax, eo_o, s, visited, cost)) {
+            res = FRT_SH_UNDECIDED | (5 << 4) | ((node & 31) << 8);
+            break;
+        }
+        if (s.flags) {
+            const int v = judge_span(s, D_lo, D_hi);
+            if (v == 3) {
+                res = FRT_SH_UNDECIDED | (6 << 4) | ((node & 31) << 8);
+                break;
+            }
+            if (v != 0) {
+                res = v == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
+                break;
+            }
+        }
+    }
+    if (COUNT) {
+        *nodes_visited += visited;
+        *flops += cost;
+    }
+    return res;
+}
+
+/* are all nodes of the program evaluable by entry_node_span, and does it carry a tail verdict? */
+__device__ __forceinline__ bool
+entry_program_is_fast(unsigned int prog, unsigned int entry_fast)
+{
+    const int n = FRT_PROG_COUNT(prog);
+    bool ok = FRT_PROG_TAIL(prog) != 0 && n >= 1;
+    for (int k = 0; k < FRT_PROG_MAX; ++k) {
+        ok = ok && (k >= n || ((entry_fast >> FRT_PROG_NODE(prog, k)) & 1u));
+    }
+    return ok;
+}
+
+/* can node `i` be evaluated by entry_node_span?  (decided once per scene on the host: bit i of DSceneF::entry_fast) */
 static inline bool
-node_is_entry_fast(const float4 *fn, const int *prog, int i)
+node_is_entry_fast(const float4 *fn, const int *prog, const float4 *wsph, int i)
 {
     auto as_int = [](float f) { int v; memcpy(&v, &f, sizeof(v)); return v; };
     const int flags = as_int(fn[3 * i].x), type = flags & FRT_FN_TYPE_MASK;
@@ -804,6 +884,9 @@ node_is_entry_fast(const float4 *fn, const int *prog, int i)
     };
     if (type == FRT_CUBE) {
         return world_cube(i);
+    }
+    if (type == FRT_SPHERE) {
+        return wsph[i].w > 0.f;
     }
     if (type != FRT_CSG || !(flags & FRT_FN_FAST)) {
         return false;
@@ -1097,43 +1180,43 @@ shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const
  * FRT_SH_LIT / FRT_SH_SHADOWED: the verdict of every shadow ray of the hit; FRT_SH_UNDECIDED: trace them one by one.
  * Trees of more than 32 nodes are not tried (`relevant` covers nodes 0..31).
  *
- * When the walk gets stuck at a node X it does not give up: *resume = X, and it walks on AS IF X ended no search.  If
- * the rest is decided for the whole shaft -- a later node ends every search with one verdict, or the tree ends (lit) --
- * that verdict is the answer of every ray X does not stop, and it goes into bits 5..6 of *resume (1 lit, 2 shadowed,
- * 0 = stuck a second time).  The per-ray walk then starts at X (every node before it was passed with a decided "ends no
- * search" for every ray) and, with a tail verdict, ends right after it: a ray of a Cornell penumbra hit evaluates the
- * window wall's CSG program and nothing else.
+ * When the walk gets stuck at a node X it does not give up: X goes into the entry's program and the walk goes on AS IF X
+ * ended no search.  When the rest is decided for the whole shaft -- a later node ends every search with one verdict, or
+ * the tree ends (lit) -- that verdict is the answer of every ray the program's nodes do not stop: *prog (layout above
+ * trace_entry_program).  A ray of a Cornell penumbra hit then evaluates the window wall's CSG program and nothing else.
+ * Stuck more than FRT_PROG_MAX times: tail 0, the rays walk the tree from X1 on.
  */
 #define FRT_RESUME_NODE_MASK 31
-#define FRT_RESUME_TAIL_SHIFT 5
 __device__ __forceinline__ int
-trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const ShaftD &sh, int *resume)
+trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const ShaftD &sh, unsigned int *prog)
 {
     const float4 *fnodes = SF.fnodes;
-    int i = root, stuck = -1;
+    int i = root, n_stuck = 0;
+    unsigned int list = 0u;
     const int end = __float_as_int(__ldg(fnodes + 3 * i).y);
     while (i < end) {
         int next = i + 1;
         const int code = shaft_node(SF, fnodes, relevant, sh, i, &next);
         if (code == 3) {
-            if (stuck >= 0) {
-                *resume = stuck;
+            if (n_stuck == FRT_PROG_MAX) {
+                *prog = list | ((unsigned int)n_stuck << 2);
                 return FRT_SH_UNDECIDED;
             }
-            stuck = i;
+            list |= (unsigned int)i << (4 + 5 * n_stuck);
+            ++n_stuck;
         } else if (code != 0) {
-            if (stuck < 0) {
+            if (n_stuck == 0) {
                 return code == 2 ? FRT_SH_SHADOWED : FRT_SH_LIT;
             }
-            *resume = stuck | (code << FRT_RESUME_TAIL_SHIFT);
+            *prog = list | ((unsigned int)n_stuck << 2) | (unsigned int)code;
             return FRT_SH_UNDECIDED;
         }
         i = next;
     }
-    if (stuck < 0) {
+    if (n_stuck == 0) {
         return FRT_SH_LIT;
     }
-    *resume = stuck | (1 << FRT_RESUME_TAIL_SHIFT);
+    *prog = list | ((unsigned int)n_stuck << 2) | 1u;
     return FRT_SH_UNDECIDED;
 }
 

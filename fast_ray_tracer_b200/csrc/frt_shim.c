@@ -853,7 +853,12 @@ render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
     clock_gettime(CLOCK_MONOTONIC, &t0);
     frt_multi *multi = NULL;
     int rc = frt_multi_create(&d, devices, n_dev, f.n_lazy ? gens : NULL, f.n_lazy, &multi);
+    for (int k = 0; rc == FRT_OK && f.n_lazy > 0 && k < frt_multi_device_count(multi); ++k) {
+        rc = frt_scene_gen_status(frt_multi_scene(multi, k)); /* waits for the comparison on that device */
+    }
     if (rc == FRT_ERR_MISMATCH) {
+        frt_multi_destroy(multi);
+        multi = NULL;
         /* another generator state than the constructors' order implies (or another sampler): take the reference's sets */
         printf("FRT_B200_LIGHT_GEN mismatch (%s): uploading the host caches\n", frt_last_error());
         materialize_lazy_lights(&f);

@@ -286,8 +286,10 @@ int frt_scene_create(const frt_scene_desc *desc, int device, frt_scene **out);
  *   - the light's region of desc->light_points is NOT read (desc->light_points may be NULL when every light is listed);
  *   - gen.verify_points[k] (k < gen.n_verify <= FRT_GEN_VERIFY_MAX): set gen.verify_set[k] as the reference built it,
  *     num_samples * 3 doubles; each is compared bit for bit with the rebuilt set on the device.
- * Returns FRT_ERR_MISMATCH (no scene) when a compared set differs -- the caller then flattens the host cache and calls
- * frt_scene_create; FRT_OK means every listed light was rebuilt and every compared set is identical.
+ * The comparison runs on the device BEHIND this call (which only fails for malformed arguments): frt_scene_gen_status
+ * waits for it and returns FRT_OK or FRT_ERR_MISMATCH; a caller that does not ask gets the same answer from the scene's
+ * first frt_render (FRT_ERR_MISMATCH, nothing written to the canvas; every later call on the scene fails the same way).
+ * On a mismatch the caller destroys the scene, flattens the host cache and calls frt_scene_create.
  */
 #define FRT_GEN_VERIFY_MAX 8
 typedef struct frt_light_gen {
@@ -298,6 +300,7 @@ typedef struct frt_light_gen {
     const double *verify_points[FRT_GEN_VERIFY_MAX];
 } frt_light_gen;
 int frt_scene_create_gen(const frt_scene_desc *desc, int device, const frt_light_gen *gens, int n_gens, frt_scene **out);
+int frt_scene_gen_status(frt_scene *scene);
 /* drand48 state after `draws` draws from state `x` (X' = 0x5DEECE66D X + 0xB mod 2^48; glibc starts from X = 0 when
  * srand48 was never called): what a caller needs to fill frt_light_gen.drand48_state. */
 uint64_t frt_drand48_advance(uint64_t x, uint64_t draws);
