@@ -144,7 +144,7 @@ EXPORTS = [
     "frt_ppm16_size", "frt_canvas_encode_ppm16", "frt_encode_ppm16",
     "frt_scene_create_gen", "frt_scene_gen_status", "frt_drand48_advance", "frt_light_points_checksum", "frt_light_points_checksum_host",
     "frt_photons_estimate", "frt_multi_create", "frt_multi_destroy", "frt_multi_device_count", "frt_multi_scene",
-    "frt_multi_render", "frt_multi_photons",
+    "frt_multi_render", "frt_multi_photons", "frt_texture_ingest",
 ]
 
 
@@ -166,6 +166,7 @@ def load_library():
     lib.frt_scene_create.argtypes = [C.POINTER(frt_scene_desc), C.c_int, C.POINTER(C.c_void_p)]
     lib.frt_scene_create_gen.argtypes = [C.POINTER(frt_scene_desc), C.c_int, C.POINTER(frt_light_gen), C.c_int, C.POINTER(C.c_void_p)]
     lib.frt_scene_gen_status.argtypes = [C.c_void_p]
+    lib.frt_texture_ingest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.frt_drand48_advance.argtypes = [C.c_uint64, C.c_uint64]
     lib.frt_drand48_advance.restype = C.c_uint64
     lib.frt_light_points_checksum.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]
@@ -247,6 +248,17 @@ def encode_ppm16(canvas: np.ndarray, use_scaling: bool = True, device: int = 0, 
            "frt_encode_ppm16")
     data = out[: got.value].tobytes()
     return (data, ms.value) if return_ms else data
+
+
+def texture_ingest(raw_rgb: np.ndarray, super_sample: bool = False, srgb: bool = True, device: int = 0) -> np.ndarray:
+    """What the device keeps of an image (frt_texture_ingest): raw_rgb [h, w, 3] float64 as read_png leaves it ->
+    [h, w, 4] float32 linear RGB, per texel what canvas_pixel_at (reference canvas.c:115-148) returns."""
+    raw = np.ascontiguousarray(raw_rgb, dtype=np.float64)
+    h, w = raw.shape[:2]
+    out = np.zeros((h, w, 4), dtype=np.float32)
+    _check(load_library().frt_texture_ingest(raw.ctypes.data, w, h, int(super_sample), 1 if srgb else 0, device, out.ctypes.data),
+           "frt_texture_ingest")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- scenes

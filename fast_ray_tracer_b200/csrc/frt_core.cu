@@ -3106,7 +3106,28 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     UP(upload(sc, d->materials, (size_t)d->n_materials, &S.mats));
     UP(upload(sc, d->patterns, (size_t)d->n_patterns, &S.pats));
     UP(upload(sc, d->textures, (size_t)d->n_textures, &S.texs));
-    UP(upload(sc, d->texels, (size_t)3 * d->n_texels, &S.texels));
+    {
+        /* textures: the raw FP64 texels travel once, k_texture_ingest turns them into what a fetch returns */
+        const double *raw = nullptr;
+        UP(upload(sc, d->texels, (size_t)3 * d->n_texels, &raw));
+        float4 *tex = nullptr;
+        if (scene_alloc(sc, (void **)&tex, std::max<size_t>((size_t)d->n_texels, 1) * sizeof(float4)) != cudaSuccess) {
+            frt_scene_destroy(sc);
+            return frt_set_error(FRT_ERR_CUDA, "cudaMalloc of the textures failed");
+        }
+        for (int i = 0; i < d->n_textures; ++i) {
+            const frt_texture &t = d->textures[i];
+            const size_t n = (size_t)t.width * t.height;
+            const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)sc->sm_count * 8);
+            k_texture_ingest<<<blocks, 256, 0, sc->upload_stream>>>(raw + 3 * t.texel_offset, t.width, t.height, t.super_sample, t.color_fn,
+                                                                   tex + t.texel_offset);
+        }
+        if (cudaGetLastError() != cudaSuccess) {
+            frt_scene_destroy(sc);
+            return frt_set_error(FRT_ERR_CUDA, "texture ingest failed");
+        }
+        S.texels = tex;
+    }
     UP(upload(sc, d->lights, (size_t)d->n_lights, &S.lights));
     UP(upload(sc, d->roots, (size_t)d->n_roots, &S.roots));
     lap("scene buffers");
@@ -4782,6 +4803,39 @@ frt_photons_estimate(frt_scene *sc, int map, int64_t n, const double *pos, const
     cudaFree(dfound);
     if (e != cudaSuccess) {
         return frt_set_error(FRT_ERR_CUDA, "frt_photons_estimate: %s", cudaGetErrorString(e));
+    }
+    return FRT_OK;
+}
+
+/*
+ * Texture ingest on its own: what frt_scene_create does to every image of a scene.  raw_rgb: the
+ * Canvas.arr of an image as the reference's read_png / read_ppm leave it (width * height * 3 doubles, row-major); out:
+ * width * height * 4 floats, linear RGB + 0 -- per texel what canvas_pixel_at (canvas.c:115-148) returns, rounded to FP32.
+ */
+extern "C" int
+frt_texture_ingest(const double *raw_rgb, int width, int height, int super_sample, int color_fn, int device, float *out_rgba)
+{
+    if (raw_rgb == nullptr || out_rgba == nullptr || width <= 0 || height <= 0 || (color_fn != FRT_COLOR_RGB && color_fn != FRT_COLOR_SRGB_TO_RGB)) {
+        return frt_set_error(FRT_ERR_ARG, "frt_texture_ingest: bad argument");
+    }
+    CK(cudaSetDevice(device));
+    const size_t n = (size_t)width * height;
+    double *raw = nullptr;
+    float4 *tex = nullptr;
+    cudaError_t e = cudaMalloc(&raw, n * 3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&tex, n * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemcpy(raw, raw_rgb, n * 3 * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        k_texture_ingest<<<(int)std::min<size_t>((n + 255) / 256, (size_t)sms * 8), 256>>>(raw, width, height, super_sample ? 1 : 0, color_fn, tex);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_rgba, tex, n * sizeof(float4), cudaMemcpyDeviceToHost);
+    cudaFree(raw);
+    cudaFree(tex);
+    if (e != cudaSuccess) {
+        return frt_set_error(FRT_ERR_CUDA, "frt_texture_ingest: %s", cudaGetErrorString(e));
     }
     return FRT_OK;
 }

@@ -28,7 +28,7 @@ struct DScene {
     const frt_material *mats;
     const frt_pattern *pats;
     const frt_texture *texs;
-    const double *texels;
+    const float4 *texels;     /* one per texel: canvas_pixel_at evaluated at upload, linear FP32 RGB (frt_patterns.cuh) */
     const frt_light *lights;
     const double *lpoints;
     const int *roots;

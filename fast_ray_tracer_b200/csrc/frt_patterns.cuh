@@ -80,45 +80,63 @@ srgb_to_linear(double c)
     return c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4);
 }
 
-/* canvas_pixel_at, canvas.c:115-148 (3x3 wrap-around box when super_sample; colour_space_fn at every fetch) */
-__device__ __noinline__ void
+/*
+ * Texture ingest.  The reference keeps an image as a Canvas of FP64 RGB (32 B per texel on the host)
+ * and evaluates canvas_pixel_at (canvas.c:115-148) at EVERY fetch: a 3 x 3 wrap-around box average when the canvas is
+ * super-sampled, then color_space_fn -- two pow() per channel for sRGB sources.  Both depend on the texel only, so the
+ * upload evaluates them once per texel, in FP64 and in the reference's order of operations, and stores linear FP32 RGBA
+ * (16 B per texel, one 128-bit load through the read-only path per fetch); a fetch returns exactly what canvas_pixel_at
+ * returns, rounded to FP32 (6e-8 relative, four orders below one sRGB-8 LSB; bump maps perturb the normal by the same).
+ */
+__global__ void
+k_texture_ingest(const double *__restrict__ raw, int width, int height, int super_sample, int color_fn, float4 *__restrict__ out)
+{
+    const long n = (long)width * height;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+        const long row = t / width, col = t - row * width;
+        double c[3] = { 0.0, 0.0, 0.0 };
+        if (super_sample) {
+            for (int j = -1; j <= 1; ++j) { /* columns outside, rows inside: the reference's order of accumulation */
+                const long cc = (col + j + width) % width;
+                for (int i = -1; i <= 1; ++i) {
+                    const long rr = (row + i + height) % height;
+                    const double *p = raw + 3 * (rr * width + cc);
+                    c[0] += p[0];
+                    c[1] += p[1];
+                    c[2] += p[2];
+                }
+            }
+            c[0] *= 1.0 / 9.0;
+            c[1] *= 1.0 / 9.0;
+            c[2] *= 1.0 / 9.0;
+        } else {
+            const double *p = raw + 3 * t;
+            c[0] = p[0];
+            c[1] = p[1];
+            c[2] = p[2];
+        }
+        if (color_fn == FRT_COLOR_SRGB_TO_RGB) {
+            c[0] = srgb_to_linear(c[0]);
+            c[1] = srgb_to_linear(c[1]);
+            c[2] = srgb_to_linear(c[2]);
+        }
+        out[t] = make_float4((float)c[0], (float)c[1], (float)c[2], 0.f);
+    }
+}
+
+/* canvas_pixel_at (canvas.c:115-148) of the ingested texture: one texel, already filtered and in linear RGB */
+__device__ __forceinline__ void
 texture_fetch(const DScene &S, int tex, long col, long row, double out[3])
 {
     const frt_texture T = S.texs[tex];
-    const double *base = S.texels + 3 * T.texel_offset;
-    double c[3] = { 0.0, 0.0, 0.0 };
     if (col < 0) col = 0;
     if (row < 0) row = 0;
     if (col >= T.width) col = T.width - 1;
     if (row >= T.height) row = T.height - 1;
-    if (T.super_sample) {
-        for (int j = -1; j <= 1; ++j) {
-            long cc = (col + j + T.width) % T.width;
-            for (int i = -1; i <= 1; ++i) {
-                long rr = (row + i + T.height) % T.height;
-                const double *p = base + 3 * (rr * T.width + cc);
-                c[0] += __ldg(p + 0);
-                c[1] += __ldg(p + 1);
-                c[2] += __ldg(p + 2);
-            }
-        }
-        c[0] *= 1.0 / 9.0;
-        c[1] *= 1.0 / 9.0;
-        c[2] *= 1.0 / 9.0;
-    } else {
-        const double *p = base + 3 * (row * T.width + col);
-        c[0] = __ldg(p + 0);
-        c[1] = __ldg(p + 1);
-        c[2] = __ldg(p + 2);
-    }
-    if (T.color_fn == FRT_COLOR_SRGB_TO_RGB) {
-        c[0] = srgb_to_linear(c[0]);
-        c[1] = srgb_to_linear(c[1]);
-        c[2] = srgb_to_linear(c[2]);
-    }
-    out[0] = c[0];
-    out[1] = c[1];
-    out[2] = c[2];
+    const float4 t = __ldg(S.texels + T.texel_offset + row * T.width + col);
+    out[0] = (double)t.x;
+    out[1] = (double)t.y;
+    out[2] = (double)t.z;
 }
 
 /* ---- uv maps, pattern.c:310-488 ---------------------------------------------------------------------- */

@@ -123,8 +123,9 @@ typedef struct frt_pattern {
     int32_t i[4];
 } frt_pattern;
 
-/* Texture = struct canvas used as an image (canvas.h:10-17); texels are RAW, colour_fn is applied at fetch
- * exactly like canvas_pixel_at (canvas.c:115-148). */
+/* Texture = struct canvas used as an image (canvas.h:10-17).  The description carries the texels RAW, as read_png left
+ * them; frt_scene_create evaluates canvas_pixel_at (canvas.c:115-148: the 3x3 wrap-around box of a super-sampled canvas,
+ * then colour_fn) once per texel and keeps linear FP32 RGBA on the device (texture ingest). */
 enum frt_color_fn { FRT_COLOR_RGB = 0, FRT_COLOR_SRGB_TO_RGB = 1 };
 typedef struct frt_texture {
     int32_t width, height;
@@ -325,6 +326,10 @@ size_t frt_ppm16_size(int width, int height);
 int frt_canvas_encode_ppm16(frt_scene *scene, int use_scaling, unsigned char *out, size_t out_cap, size_t *out_len, double *encode_ms);
 int frt_encode_ppm16(const double *canvas_rgba, int width, int height, int use_scaling, int device, unsigned char *out, size_t out_cap,
                      size_t *out_len, double *encode_ms);
+
+/* Texture ingest on its own: raw_rgb = width * height * 3 doubles (an image's Canvas.arr without the 4th lane), out_rgba =
+ * width * height * 4 floats: per texel what canvas_pixel_at returns for it, rounded to FP32. */
+int frt_texture_ingest(const double *raw_rgb, int width, int height, int super_sample, int color_fn, int device, float *out_rgba);
 
 /* Page-lock / release a caller-owned host buffer a scene description points at (typically light_points, the 157 MB
  * sample-set cache the reference builds in light.c:100-191): frt_scene_create then uploads it at PCIe speed and

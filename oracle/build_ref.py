@@ -222,6 +222,17 @@ def build_pm_oracle():
     return lib
 
 
+def build_canvas_oracle():
+    """oracle/_ref/libcanvas_ref.so: the reference's canvas_pixel_at (canvas.c, unmodified, with its colour helpers)."""
+    lib = OUT / "libcanvas_ref.so"
+    src = REPO / "oracle" / "canvas_oracle.c"
+    deps = [REF / "src" / "libs" / "canvas" / "canvas.c"] + sorted((REF / "src" / "color").glob("*.c")) + [REF / "src" / "libs" / "linalg" / "linalg.c"]
+    deps = [p for p in deps if p.exists()]
+    if not lib.exists() or lib.stat().st_mtime < max(p.stat().st_mtime for p in [src, *deps]):
+        run(["gcc", *CFLAGS, "-shared", "-I", str(REF), "-I", str(REPO / "oracle" / "png_stub"), "-o", str(lib), str(src), *map(str, deps), "-lm", "-lz"])
+    return lib
+
+
 def generate_main(name: str) -> Path:
     import yaml
 
@@ -294,6 +305,7 @@ def main():
     names = args.scenes or list(SCENES)
     build_objects(force=args.force)
     build_pm_oracle()
+    build_canvas_oracle()
     for name in names:
         build_scene(name, force=args.force)
         if not args.no_blobs and name not in NO_BLOB:
