@@ -1977,7 +1977,9 @@ struct frt_scene {
     float *pm_dir_tab = nullptr;       /* the photon maps' direction tables (pm.c:54-60), 4 x 256 floats */
     float4 *pm_merged[2] = { nullptr, nullptr }; /* frt_multi_photons: every device's shard, gathered here before the import */
     bool pm_ready = false;
-    GQuery *gq = nullptr;
+    GQuery *gq = nullptr, *gq2 = nullptr;     /* radiance-estimate requests of a batch, as queued / sorted by grid cell */
+    unsigned int *gq_counts = nullptr, *gq_starts = nullptr;
+    size_t gq_cells = 0;
     unsigned int gq_cap = 0;
     unsigned int *gq_n = nullptr;
     double *acc_amb = nullptr, *acc_fg = nullptr;
@@ -3741,6 +3743,8 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     const int eblocks = env_int("FRT_ENTRY_BLOCKS", sm_blocks * 64);
     const int entry_kernel = env_int("FRT_ENTRY_KERNEL", 0); /* 1: one warp per pending entry (k_shadow_entry, A/B measurements: 6.5 vs 5.9 ms) */
     const bool debug_nodes = getenv("FRT_DEBUG_NODES") != nullptr;
+    const int sort_queries = env_int("FRT_KNN_SORT", 0); /* measured: 840 -> 900 ms on the 400 x 400 C5 frame (the requests are not L2-latency bound) */
+    const int knn_list = env_int("FRT_KNN_LIST", 0);     /* 1: the candidate-list kernel k_knn_list (A/B measurements) */
 
     for (unsigned long long first = 0; first < total; first += chunk) {
         unsigned int n = (unsigned int)std::min<unsigned long long>(chunk, total - first);
@@ -3929,8 +3933,37 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                     }
                     tock(tk);
                     tk = tick(FRT_ST_KNN);
-                    k_knn<<<sm_blocks * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, sc->gq, sc->gq_n, sc->gq_cap,
-                                                                      sc->acc_amb, sc->acc_fg, nullptr);
+                    const GQuery *gq_in = sc->gq;
+                    if (sort_queries) { /* counting sort of the batch by photon-grid cell (frt_gi.cuh) */
+                        const PMView &M = sc->pm[1].view.count ? sc->pm[1].view : sc->pm[0].view;
+                        const size_t n_cells = (size_t)M.nx * M.ny * M.nz;
+                        if (M.count && n_cells > 0) {
+                            if (sc->gq_cells < n_cells + 1) {
+                                cudaFree(sc->gq_counts);
+                                cudaFree(sc->gq_starts);
+                                sc->gq_counts = sc->gq_starts = nullptr;
+                                CK(cudaMalloc(&sc->gq_counts, sizeof(unsigned int) * (n_cells + 1)));
+                                CK(cudaMalloc(&sc->gq_starts, sizeof(unsigned int) * (n_cells + 1)));
+                                sc->gq_cells = n_cells + 1;
+                            }
+                            if (sc->gq2 == nullptr) {
+                                CK(cudaMalloc(&sc->gq2, sizeof(GQuery) * (size_t)sc->gq_cap));
+                            }
+                            CK(cudaMemsetAsync(sc->gq_counts, 0, sizeof(unsigned int) * n_cells, s));
+                            k_gq_count<<<sm_blocks * 8, 256, 0, s>>>(M, sc->gq, sc->gq_n, sc->gq_cap, sc->gq_counts);
+                            k_pm_scan<<<1, 1024, 0, s>>>(sc->gq_counts, sc->gq_starts, (unsigned int)n_cells);
+                            k_gq_scatter<<<sm_blocks * 8, 256, 0, s>>>(M, sc->gq, sc->gq_n, sc->gq_cap, sc->gq_starts, sc->gq2);
+                            launches += 3;
+                            gq_in = sc->gq2;
+                        }
+                    }
+                    if (knn_list) {
+                        k_knn_list<<<sm_blocks * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, gq_in, sc->gq_n, sc->gq_cap,
+                                                                               sc->acc_amb, sc->acc_fg, nullptr);
+                    } else {
+                        k_knn<<<sm_blocks * 16, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, gq_in, sc->gq_n, sc->gq_cap,
+                                                                           sc->acc_amb, sc->acc_fg, nullptr);
+                    }
                     tock(tk);
                     ++launches;
                 }
@@ -4185,6 +4218,12 @@ pm_free(frt_scene *sc)
     cudaFree(sc->pm_dir_tab);
     sc->pm_dir_tab = nullptr;
     cudaFree(sc->gq);
+    cudaFree(sc->gq2);
+    cudaFree(sc->gq_counts);
+    cudaFree(sc->gq_starts);
+    sc->gq2 = nullptr;
+    sc->gq_counts = sc->gq_starts = nullptr;
+    sc->gq_cells = 0;
     cudaFree(sc->gq_n);
     cudaFree(sc->acc_amb);
     cudaFree(sc->acc_fg);
@@ -4456,7 +4495,17 @@ frt_photons_finish(frt_scene *sc)
             hi[k] = float_unorder(hb[3 + k]);
             ext = std::max(ext, hi[k] - lo[k]);
         }
-        const float cell = std::max(0.5f * radius, ext / 256.0f); /* half the search radius: 5 x 5 rows, clipped to the sphere */
+        /* half the search radius: 5 x 5 rows of cells, each clipped to the sphere.  Coarser cells only when the grid would
+         * not fit (a few photons that left the box through the window make the Cornell map 20 units wide: at ext / 256 the
+         * cells were 0.078 instead of 0.05 and a request looked at 2.4 x the photons) */
+        float cell = std::max(0.5f * radius, ext / 2048.0f);
+        for (;;) {
+            const double cells = (floor((hi[0] - lo[0]) / cell) + 1.0) * (floor((hi[1] - lo[1]) / cell) + 1.0) * (floor((hi[2] - lo[2]) / cell) + 1.0);
+            if (cells <= (double)(1u << 26)) {
+                break;
+            }
+            cell *= 1.25f;
+        }
         PMView V{};
         V.gx = lo[0];
         V.gy = lo[1];
@@ -4791,7 +4840,11 @@ frt_photons_estimate(frt_scene *sc, int map, int64_t n, const double *pos, const
     if (e == cudaSuccess) e = cudaMemsetAsync(dacc, 0, sizeof(double) * 3 * (size_t)n, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(dfound, 0, sizeof(int) * (size_t)n, s);
     if (e == cudaSuccess) {
-        k_knn<<<sc->sm_count * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, dq, dn, un, dacc, dacc, dfound);
+        if (getenv("FRT_KNN_LIST") != nullptr && atoi(getenv("FRT_KNN_LIST")) != 0) {
+            k_knn_list<<<sc->sm_count * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, dq, dn, un, dacc, dacc, dfound);
+        } else {
+            k_knn<<<sc->sm_count * 16, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, dq, dn, un, dacc, dacc, dfound);
+        }
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(irrad, dacc, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, s);

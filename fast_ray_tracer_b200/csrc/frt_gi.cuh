@@ -596,6 +596,33 @@ k_gi_points(FrameParams F, GIParams G, const LightRec *__restrict__ recs, unsign
 }
 
 /*
+ * Requests sorted by grid cell before k_knn.  The gather rays of a hit scatter over the whole scene, so consecutive
+ * requests of the queue land in unrelated cells and every warp of k_knn pulls its candidate photons from L2 on its own
+ * (ncu: L1 hit rate 4 %, long_scoreboard 4.4 warps per issue).  A counting sort by the cell of the request's position
+ * (the photon grid's own cells, x fastest) makes neighbours in the queue neighbours in space: the four warps of a block
+ * and the blocks of an SM then read the same rows of cells.  Cost: two passes over 40-byte records.
+ */
+__global__ void
+k_gq_count(PMView M, const GQuery *__restrict__ q, const unsigned int *n_queries, unsigned int qcap, unsigned int *__restrict__ counts)
+{
+    const unsigned int n = min(*n_queries, qcap);
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        atomicAdd(counts + pm_cell_of(M, q[i].x, q[i].y, q[i].z), 1u);
+    }
+}
+
+__global__ void
+k_gq_scatter(PMView M, const GQuery *__restrict__ q, const unsigned int *n_queries, unsigned int qcap, unsigned int *__restrict__ cursor,
+             GQuery *__restrict__ out)
+{
+    const unsigned int n = min(*n_queries, qcap);
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const GQuery g = q[i];
+        out[atomicAdd(cursor + pm_cell_of(M, g.x, g.y, g.z), 1u)] = g;
+    }
+}
+
+/*
  * Warp-cooperative selection: the 24-bit key of the want-th smallest of d2[0..count) (count > want), keys being
  * d2 * scale truncated to 24 bits.  Three 8-bit radix passes, each a shared-memory histogram of the candidates that
  * still match the digits found so far and a warp scan over its 256 bins -- three passes over the list instead of
@@ -697,7 +724,7 @@ knn_tie_kept(const float *d2, unsigned int count, unsigned int k, unsigned int T
  * keeps the squared distances < r^2 with their photon indices in shared memory.
  */
 __global__ void __launch_bounds__(FRT_KNN_WARPS * 32)
-k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, const unsigned int *n_queries, unsigned int qcap,
+k_knn_list(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, const unsigned int *n_queries, unsigned int qcap,
       double *__restrict__ acc_amb, double *__restrict__ acc_fg, int *__restrict__ found_out)
 {
     __shared__ float s_d2[FRT_KNN_WARPS][FRT_KNN_CAP];
@@ -884,6 +911,314 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
         if (lane == 0 && found >= 8) {
             /* np.dist2[0] (pm.c:147): the search radius^2 until the heap of n photons is full, then the n-th distance^2 */
             const double r2_density = (select || r2cur < R2) ? (double)far2 : (double)R2;
+            const double density = 1.0 / ((1.0 - 2.0 / (3.0 * (double)G.cone_k)) * (M_PI * r2_density));
+            /* the callers' rescale (renderer.c:845, :878); frt_photons_estimate returns the estimate as pm.c does */
+            const double rescale = found_out != nullptr ? 1.0 : (caustic ? 100.0 / (double)found : 10.0 * (double)G.n_photons / (double)found);
+            const double f = density * rescale;
+            double *acc = ((q.target & 0x80000000u) ? acc_fg : acc_amb) + 3 * (size_t)(q.target & 0x3fffffffu);
+            const double vr = f * (double)sr * (double)q.wr, vg = f * (double)sg * (double)q.wg, vb = f * (double)sb * (double)q.wb;
+            if (vr != 0.0) atomicAdd(acc, vr);
+            if (vg != 0.0) atomicAdd(acc + 1, vg);
+            if (vb != 0.0) atomicAdd(acc + 2, vb);
+        }
+        __syncwarp();
+    }
+}
+
+/*
+ * The same estimate WITHOUT a candidate list.  k_knn_list keeps every photon inside the search sphere (distance and index,
+ * 8 KB of shared memory per warp: 24 resident warps per SM) and then radix-selects the n nearest in three passes over that
+ * list; ncu (profiles/r1b_k_knn_radix.txt): 41 % issue utilisation at 27 % occupancy, ~2 100 warp-instructions per request.
+ * Here the candidates are STREAMED twice from the photon grid (the second time out of L1 / L2):
+ *   pass 1   histogram of the squared distances over 256 equal bins of [0, r^2)           (1 KB per warp)
+ *            -> the bin B that holds the n-th nearest photon, and how many of its photons belong to the n nearest;
+ *            a bin with more than FRT_KNN_TIES photons is split once more into 256 sub-bins by a second histogram pass
+ *   pass 2   photons in bins below B are summed on the fly; those of bin B go to a short list, from which the missing
+ *            ones are taken in exact (distance, position) order -- the result is the set pm_locate_photons keeps.
+ * 2 KB of shared memory per warp, so residency is bounded by registers, not shared memory.
+ */
+#define FRT_KNN_TIES 128
+
+/* which candidates the n nearest are: key16 < t_lo taken, t_lo <= key16 <= t_hi tie class, above: not */
+__device__ __forceinline__ unsigned int
+knn_key16(float dd, float kscale)
+{
+    return min((unsigned int)(dd * kscale), 65535u);
+}
+
+/* the bin of hist[0..256) in which the cumulative count reaches `want` (1-based), the count before it and its own count */
+__device__ __forceinline__ void
+knn_find_bin(const unsigned int *hist, unsigned int want, int lane, unsigned int &bin, unsigned int &before, unsigned int &inside,
+             unsigned int &total)
+{
+    unsigned int mine[8], sum = 0;
+    for (int b = 0; b < 8; ++b) {
+        mine[b] = hist[8 * lane + b];
+        sum += mine[b];
+    }
+    unsigned int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) {
+            incl += up;
+        }
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned int excl = incl - sum;
+    const bool has = want > excl && want <= incl;
+    const int owner = __ffs(__ballot_sync(0xffffffffu, has)) - 1;
+    unsigned int b_ = 255u, bef = 0u, ins = 0u;
+    if (lane == owner) {
+        unsigned int run = excl;
+        for (int b = 0; b < 8; ++b) {
+            if (want <= run + mine[b]) {
+                b_ = 8u * lane + b;
+                bef = run;
+                ins = mine[b];
+                break;
+            }
+            run += mine[b];
+        }
+    }
+    const int src = owner < 0 ? 0 : owner;
+    bin = __shfl_sync(0xffffffffu, b_, src);
+    before = __shfl_sync(0xffffffffu, bef, src);
+    inside = __shfl_sync(0xffffffffu, ins, src);
+}
+
+#ifndef FRT_KNN_MINB
+#define FRT_KNN_MINB 8
+#endif
+__global__ void __launch_bounds__(FRT_KNN_WARPS * 32, FRT_KNN_MINB)
+k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, const unsigned int *n_queries, unsigned int qcap,
+      double *__restrict__ acc_amb, double *__restrict__ acc_fg, int *__restrict__ found_out)
+{
+    __shared__ unsigned int s_hist[FRT_KNN_WARPS][256];
+    __shared__ float s_td2[FRT_KNN_WARPS][FRT_KNN_TIES];
+    __shared__ unsigned int s_tid[FRT_KNN_WARPS][FRT_KNN_TIES];
+    __shared__ float s_dir[1024]; /* pm_photon_dir's tables (pm.c:80-86): the facing test must flip where the reference's does */
+    {
+        const float *tab = MG.dir_tab != nullptr ? MG.dir_tab : MC.dir_tab;
+        for (int k = threadIdx.x; k < 1024; k += blockDim.x) {
+            s_dir[k] = tab != nullptr ? __ldg(tab + k) : 0.f;
+        }
+        __syncthreads();
+    }
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int nq = min(*n_queries, qcap);
+    const unsigned int lt = (1u << lane) - 1u;
+    unsigned int *hist = s_hist[wib];
+    float *td2 = s_td2[wib];
+    unsigned int *tid = s_tid[wib];
+    const float R2 = G.radius * G.radius;
+    const float kscale = 65536.0f / R2;
+    const unsigned int want_n = (unsigned int)G.n_photons;
+    const float inv_kr = 1.0f / (G.cone_k * G.radius);
+
+    for (unsigned int qi = blockIdx.x * FRT_KNN_WARPS + wib; qi < nq; qi += gridDim.x * FRT_KNN_WARPS) {
+        const GQuery q = queries[qi];
+        const bool caustic = (q.target & 0x40000000u) != 0;
+        const PMView &M = caustic ? MC : MG;
+        if (M.count == 0) {
+            continue;
+        }
+        const float cell = 1.0f / M.inv_cell;
+        const float fy = (q.y - M.gy) * M.inv_cell, fz = (q.z - M.gz) * M.inv_cell;
+        const int cy = (int)floorf(fy), cz = (int)floorf(fz);
+        const int reach = (int)ceilf(G.radius * M.inv_cell); /* <= 2: the cells are at least half a radius wide */
+        const int side = 2 * reach + 1;
+        /* lane r owns row r of the (2 reach + 1)^2 rows of cells around the request, clipped to the search sphere */
+        unsigned int row_s = 0, row_len = 0;
+        if (lane < side * side) {
+            const int z = cz - reach + lane / side, y = cy - reach + lane % side;
+            if (z >= 0 && z < M.nz && y >= 0 && y < M.ny) {
+                const float dzc = fmaxf(fmaxf((float)z - fz, fz - (float)(z + 1)), 0.0f) * cell;
+                const float dyc = fmaxf(fmaxf((float)y - fy, fy - (float)(y + 1)), 0.0f) * cell;
+                const float rem = R2 - dzc * dzc - dyc * dyc;
+                if (rem > 0.0f) {
+                    const float dxm = sqrtf(rem) * 1.0001f + 1e-7f;
+                    const int x0 = max((int)floorf((q.x - dxm - M.gx) * M.inv_cell), 0);
+                    const int x1 = min((int)floorf((q.x + dxm - M.gx) * M.inv_cell), M.nx - 1);
+                    if (x0 <= x1) {
+                        const unsigned int base = (unsigned int)((z * M.ny + y) * M.nx);
+                        row_s = __ldg(M.cell_start + base + x0);
+                        row_len = __ldg(M.cell_start + base + x1 + 1) - row_s;
+                    }
+                }
+            }
+        }
+        unsigned int incl = row_len;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) {
+                incl += up;
+            }
+        }
+        const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned int rows_mask = __ballot_sync(0xffffffffu, row_len > 0u);
+        if (total == 0u) {
+            if (found_out != nullptr && lane == 0) {
+                found_out[q.target & 0x3fffffffu] = 0;
+            }
+            continue;
+        }
+
+        /* mode 0: histogram of the high key byte; mode 1: of the low byte inside bin B (only when B is crowded);
+         * mode 2: sum the photons below the tie class, list the tie class */
+        unsigned int t_lo = 65536u, t_hi = 65536u; /* tie class in key16 space; everything below t_lo is taken */
+        unsigned int need = 0, found = 0, n_ties = 0, B = 0;
+        bool select = false;
+        float sr = 0.f, sg = 0.f, sb = 0.f, far2 = 0.f;
+        for (int mode = 0; mode < 3; ++mode) {
+            if (mode < 2) {
+                for (int b = lane; b < 256; b += 32) {
+                    hist[b] = 0;
+                }
+                __syncwarp();
+            }
+            /* four rows of cells at a time: lane k takes photon k of each (a row is one contiguous photon range, ~25 photons
+             * at 1 M photons), so four independent loads are in flight and nobody searches for the row of a candidate --
+             * the flattened candidate list this replaces spent 30 % of the kernel's instructions on that search */
+            for (unsigned int rm = rows_mask; rm != 0u;) {
+                unsigned int rs[4], rl[4], lmax = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rm ? __ffs(rm) - 1 : 0;
+                    const bool live = rm != 0u;
+                    rm &= rm - 1u;
+                    rs[u] = __shfl_sync(0xffffffffu, row_s, r);
+                    rl[u] = live ? __shfl_sync(0xffffffffu, row_len, r) : 0u;
+                    lmax = max(lmax, rl[u]);
+                }
+                for (unsigned int k0 = 0; k0 < lmax; k0 += 32) {
+                unsigned int pp[4];
+                float4 aa[4];
+                bool valid[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned int k = k0 + lane;
+                    valid[u] = k < rl[u];
+                    pp[u] = rs[u] + k;
+                    aa[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid[u]) {
+                        aa[u] = __ldg(M.a + pp[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float dx = aa[u].x - q.x, dy = aa[u].y - q.y, dz = aa[u].z - q.z;
+                    const float dd = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    const bool in = valid[u] && dd < R2;
+                    const unsigned int key = knn_key16(dd, kscale);
+                    if (mode == 0) {
+                        if (in) {
+                            atomicAdd(&hist[key >> 8], 1u);
+                        }
+                    } else if (mode == 1) {
+                        if (in && (key >> 8) == B) {
+                            atomicAdd(&hist[key & 255u], 1u);
+                        }
+                    } else {
+                        const bool take = in && key < t_lo;
+                        const bool tie = in && key >= t_lo && key <= t_hi;
+                        if (take) {
+                            far2 = fmaxf(far2, dd);
+                            const float4 pw = __ldg(M.b + pp[u]);
+                            const unsigned int dbits = __float_as_uint(aa[u].w);
+                            const unsigned int theta = dbits & 255u, phi = (dbits >> 8) & 255u;
+                            const float st = s_dir[theta];
+                            const float dot = fmaf(st * s_dir[512 + phi], q.ex, fmaf(st * s_dir[768 + phi], q.ey, s_dir[256 + theta] * q.ez));
+                            if (dot < 0.0f) {
+                                const float w = 1.0f - sqrtf(dd) * inv_kr;
+                                sr = fmaf(pw.x, w, sr);
+                                sg = fmaf(pw.y, w, sg);
+                                sb = fmaf(pw.z, w, sb);
+                            }
+                        }
+                        const unsigned int tm = __ballot_sync(0xffffffffu, tie);
+                        if (tie) {
+                            const unsigned int pos = n_ties + __popc(tm & lt);
+                            if (pos < FRT_KNN_TIES) {
+                                td2[pos] = dd;
+                                tid[pos] = pp[u];
+                            }
+                        }
+                        n_ties += __popc(tm);
+                    }
+                }
+                }
+            }
+            __syncwarp();
+            if (mode == 0) {
+                unsigned int before, inside, count;
+                knn_find_bin(hist, want_n, lane, B, before, inside, count);
+                found = min(count, want_n);
+                select = count > want_n;
+                if (found < 8) {
+                    break; /* pm.c:121: fewer than 8 photons give nothing */
+                }
+                if (!select) {
+                    mode = 1; /* every photon inside the sphere is taken: straight to the sums */
+                    continue;
+                }
+                need = want_n - before;
+                t_lo = B << 8;
+                t_hi = (B << 8) | 255u;
+                if (inside <= FRT_KNN_TIES) {
+                    mode = 1; /* the tie class fits the list */
+                    continue;
+                }
+            } else if (mode == 1) {
+                unsigned int B2, before2, inside2, count2;
+                knn_find_bin(hist, need, lane, B2, before2, inside2, count2);
+                need -= before2;
+                t_lo = (B << 8) | B2;
+                t_hi = t_lo;
+            }
+        }
+        if (found_out != nullptr && lane == 0) {
+            found_out[q.target & 0x3fffffffu] = (int)found;
+        }
+        if (found < 8) {
+            continue;
+        }
+        if (select) {
+            /* the tie class: `need` of its n_ties photons belong to the n nearest, in (distance, position) order.  (More than
+             * FRT_KNN_TIES photons within r^2 / 65536 of one another: the first ones in stream order stand for the class.) */
+            const unsigned int m = min(n_ties, (unsigned int)FRT_KNN_TIES);
+            for (unsigned int k = lane; k < m; k += 32) {
+                const float v = td2[k];
+                unsigned int rank = 0;
+                for (unsigned int j = 0; j < m; ++j) {
+                    const float u = td2[j];
+                    rank += (u < v || (u == v && j < k)) ? 1u : 0u;
+                }
+                if (rank < need) {
+                    far2 = fmaxf(far2, v);
+                    const unsigned int id = tid[k];
+                    const float4 pw = __ldg(M.b + id);
+                    const unsigned int dbits = __float_as_uint(__ldg(M.a + id).w);
+                    const unsigned int theta = dbits & 255u, phi = (dbits >> 8) & 255u;
+                    const float st = s_dir[theta];
+                    const float dot = fmaf(st * s_dir[512 + phi], q.ex, fmaf(st * s_dir[768 + phi], q.ey, s_dir[256 + theta] * q.ez));
+                    if (dot < 0.0f) {
+                        const float w = 1.0f - sqrtf(v) * inv_kr;
+                        sr = fmaf(pw.x, w, sr);
+                        sg = fmaf(pw.y, w, sg);
+                        sb = fmaf(pw.z, w, sb);
+                    }
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            sg += __shfl_xor_sync(0xffffffffu, sg, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            far2 = fmaxf(far2, __shfl_xor_sync(0xffffffffu, far2, o));
+        }
+        if (lane == 0) {
+            /* np.dist2[0] (pm.c:147): the search radius^2 until the heap of n photons is full, then the n-th distance^2 */
+            const double r2_density = select ? (double)far2 : (double)R2;
             const double density = 1.0 / ((1.0 - 2.0 / (3.0 * (double)G.cone_k)) * (M_PI * r2_density));
             /* the callers' rescale (renderer.c:845, :878); frt_photons_estimate returns the estimate as pm.c does */
             const double rescale = found_out != nullptr ? 1.0 : (caustic ? 100.0 / (double)found : 10.0 * (double)G.n_photons / (double)found);

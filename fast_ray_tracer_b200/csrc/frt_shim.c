@@ -18,8 +18,12 @@
  * host: if the core fails, the process aborts with a non-zero exit status (no CPU fallback).
  *
  * Environment:
- *   FRT_DEVICE=n            CUDA device ordinal (default 0)
- *   FRT_RANK / FRT_WORLD    row-block partition for multi-process runs (default 0 / 1)
+ *   FRT_DEVICES=auto|all|n|a,b,c   GPUs render_multi() splits the frame's row blocks over, inside the library (default auto:
+ *                           all visible GPUs for frames of >= FRT_AUTO_SAMPLES primary samples or with a photon pass,
+ *                           else one); FRT_DEVICE=n is the one-device spelling
+ *   FRT_LIGHT_GEN=0         upload the reference's area-light sample caches instead of rebuilding them on the device
+ *   FRT_WARM=0              do not start CUDA on a thread while main() builds the scene
+ *   FRT_COUNT_RAYS=1        print the frame's ray counters
  *   FRT_SEED=n              seed of the device RNG (default 0)
  *   FRT_DUMP_SCENE=path     also write the flattened scene as a blob (frt_scene_save)
  *   FRT_DUMP_ONLY=1         write the blob and return a black canvas without touching CUDA
@@ -747,6 +751,47 @@ canvas_digest(Canvas c)
 static bool g_photons_pending, g_photons_caustic, g_photons_global;
 static World g_photons_world;
 
+/*
+ * CUDA start-up behind the host's scene construction.  The generated main() spends its first half second building the
+ * World (the reference's own light-cache constructor alone: 0.5 s for the shipped Cornell light) before it reaches
+ * render_multi(); driver initialisation and the first device's context take as long or longer (1.3 s on a 1-GPU box,
+ * 5 s on an 8-GPU box) and depend on nothing the host is doing.  A constructor of the shim starts them on a thread;
+ * render_multi() joins it.  FRT_WARM=0 switches it off (FRT_DUMP_ONLY runs never touch CUDA).
+ */
+#include <pthread.h>
+static pthread_t g_warm_thread;
+static bool g_warm_started;
+
+static void *
+warm_main(void *arg)
+{
+    (void)arg;
+    if (frt_device_count() > 0) {
+        const char *one = getenv("FRT_DEVICE");
+        frt_trim(one != NULL && *one != '\0' ? (int)strtol(one, NULL, 10) : 0); /* cudaSetDevice: creates that device's context */
+    }
+    return NULL;
+}
+
+__attribute__((constructor)) static void
+warm_start(void)
+{
+    const char *w = getenv("FRT_WARM"), *dump = getenv("FRT_DUMP_ONLY");
+    if ((w != NULL && w[0] == '0') || (dump != NULL && dump[0] != '\0' && dump[0] != '0')) {
+        return;
+    }
+    g_warm_started = pthread_create(&g_warm_thread, NULL, warm_main, NULL) == 0;
+}
+
+static void
+warm_join(void)
+{
+    if (g_warm_started) {
+        pthread_join(g_warm_thread, NULL);
+        g_warm_started = false;
+    }
+}
+
 static double
 ms_since(const struct timespec *t0)
 {
@@ -755,9 +800,15 @@ ms_since(const struct timespec *t0)
     return 1e3 * (double)(t1.tv_sec - t0->tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0->tv_nsec);
 }
 
-/* FRT_DEVICES: "all" (default), a count ("4"), or a list of ordinals ("0,2,3"); FRT_DEVICE=n is the one-device spelling */
+/*
+ * FRT_DEVICES: "auto" (default), "all", a count ("4"), or a list of ordinals ("0,2,3"); FRT_DEVICE=n is the one-device
+ * spelling.  auto: every visible GPU when the frame is worth it, one otherwise -- a CUDA context costs ~0.25 s per device
+ * (measured on an 8 x B200 box: scene creation 0.29 s on one device, 1.8 s on eight, for a Cornell frame of 15 ms), so a
+ * one-shot program only gains from more devices when its frame takes longer than that: FRT_AUTO_SAMPLES (default 2^28)
+ * primary samples, or a photon pass.
+ */
 static int
-pick_devices(int32_t *out, int cap)
+pick_devices(int32_t *out, int cap, double primary_samples, bool photon_pass)
 {
     const int visible = frt_device_count();
     const char *e = getenv("FRT_DEVICES");
@@ -768,7 +819,10 @@ pick_devices(int32_t *out, int cap)
             out[0] = (int32_t)strtol(one, NULL, 10);
             return 1;
         }
-        e = "all";
+        e = "auto";
+    }
+    if (strcmp(e, "auto") == 0) {
+        e = (photon_pass || primary_samples >= (double)env_long("FRT_AUTO_SAMPLES", 1L << 28)) ? "all" : "1";
     }
     if (strcmp(e, "all") == 0) {
         for (n = 0; n < visible && n < cap; ++n) out[n] = n;
@@ -820,7 +874,9 @@ render_on_device(Camera cam, World w, size_t usteps, size_t vsteps, bool jitter)
     }
 
     int32_t devices[64];
-    const int n_dev = pick_devices(devices, 64);
+    warm_join();
+    const int n_dev = pick_devices(devices, 64, (double)cam->hsize * (double)cam->vsize * (double)usteps * (double)vsteps,
+                                   g_photons_pending && g_photons_world == w);
 
     /* light caches rebuilt on the device, checked against a few of the sets the reference built (first, last, spread) */
     frt_light_gen gens[16];
