@@ -23,6 +23,7 @@ FRT_FLAG_NO_SHAFT = 32
 FRT_FLAG_NO_BULK = 64
 FRT_FLAG_NO_SPLIT = 128
 FRT_FLAG_STAGE_TIMES = 256
+FRT_FLAG_F64_SHAFT = 512
 STAGES = ["raygen", "extend", "shade", "light_pre", "shadow_shaft", "shadow_ray", "shadow_exact", "light_final", "gi_trace", "knn", "gi_resolve", "other"]
 
 

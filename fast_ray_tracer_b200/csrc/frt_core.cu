@@ -791,7 +791,7 @@ quadrant_sample(int4 lq, int q, int k)
  * re-trace their rays; a verifying frame takes its visibility counts from those FP64 re-traces, like it does for the
  * per-ray filter.
  */
-template <int MODE>
+template <int MODE, typename T>
 __global__ void __launch_bounds__(256)
 k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
               int light_idx, unsigned int *__restrict__ pending, unsigned int *__restrict__ pprog, unsigned int *__restrict__ retry,
@@ -815,9 +815,9 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         if (t.set_a >= 0) {
             state = 1;
             if (bulk_on) {
-                ShaftD sh;
-                const double over[3] = { (double)t.ox, (double)t.oy, (double)t.oz }; /* FP32 over-point: within 2^-24 |o| of the FP64 one */
-                shaft_d_setup(sh, SF.lbox + 30 * light_idx, over, 1.2e-7, SF.bmax, SF.smin, SF.ealign);
+                ShaftT<T> sh;
+                const T over[3] = { (T)t.ox, (T)t.oy, (T)t.oz }; /* FP32 over-point: within 2^-24 |o| of the FP64 one */
+                shaft_d_setup(sh, SF.lbox + 30 * light_idx, over, (T)1.2e-7, SF.bmax, SF.smin, SF.ealign);
                 const int res = trace_shadow_bulk(SF, root, t.relevant, sh, &prog);
                 if (res != FRT_SH_UNDECIDED) {
                     state = res == FRT_SH_LIT ? 3 : 2;
@@ -851,7 +851,7 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
 }
 
 /* one thread per (undecided hit, quadrant of the light's sample grid): the same walk against the quadrant's bounds */
-template <int MODE>
+template <int MODE, typename T>
 __global__ void __launch_bounds__(256)
 k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int light_idx,
               unsigned int *__restrict__ pending, unsigned int *__restrict__ pprog, const unsigned int *__restrict__ retry)
@@ -869,10 +869,10 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         const int q = (int)(item & 3u);
         if (item < total) {
             h = __ldg(retry + (item >> 2));
-            ShaftD sh;
+            ShaftT<T> sh;
             const LightTmp t = tmp[h];
-            const double over[3] = { (double)t.ox, (double)t.oy, (double)t.oz };
-            shaft_d_setup(sh, SF.lbox + 30 * light_idx + 6 * (q + 1), over, 1.2e-7, SF.bmax, SF.smin, SF.ealign);
+            const T over[3] = { (T)t.ox, (T)t.oy, (T)t.oz };
+            shaft_d_setup(sh, SF.lbox + 30 * light_idx + 6 * (q + 1), over, (T)1.2e-7, SF.bmax, SF.smin, SF.ealign);
             const int res = trace_shadow_bulk(SF, root, t.relevant, sh, &prog);
             state = res == FRT_SH_UNDECIDED ? 1 : (res == FRT_SH_LIT ? 3 : 2);
             if (state >= 2) {
@@ -3864,9 +3864,17 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
 #define FRT_SHADOW_STAGE(M)                                                                                                                       \
     do {                                                                                                                                          \
         tk = tick(FRT_ST_SHADOW_SHAFT);                                                                                                           \
-        k_shadow_bulk<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pprog, retry, bulk_on, split_on);  \
+        if (F.flags & FRT_FLAG_F64_SHAFT) {                                                                                                       \
+            k_shadow_bulk<M, double><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pprog, retry, bulk_on, split_on); \
+        } else {                                                                                                                                  \
+            k_shadow_bulk<M, float><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pprog, retry, bulk_on, split_on); \
+        }                                                                                                                                         \
         if (split_on) {                                                                                                                           \
-            k_shadow_quad<M><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, pprog, retry);                        \
+            if (F.flags & FRT_FLAG_F64_SHAFT) {                                                                                                   \
+                k_shadow_quad<M, double><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, pprog, retry);    \
+            } else {                                                                                                                              \
+                k_shadow_quad<M, float><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, li, sc->pending, pprog, retry);     \
+            }                                                                                                                                     \
             CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, sizeof(unsigned int), s));                                                                \
             launches += 1;                                                                                                                        \
         }                                                                                                                                         \

@@ -917,102 +917,146 @@ node_is_entry_fast(const float4 *fn, const int *prog, const float4 *wsph, int i)
  * mirror's box bounds (en), the rest is covered by relative slacks far above FP64 rounding and far below any feature.
  * Checked like the per-ray filter: FRT_FLAG_VERIFY_F32 traces every ray of a bulk-decided hit in FP64 as well.
  */
-struct ShaftD {
-    double o[3];
-    double ia[3], ib[3]; /* sgn != 0: 1 / min |d_k|, 1 / max |d_k|;  sgn == 0: 1 / max(d_k, tiny), 1 / min(d_k, -tiny) */
+/*
+ * The shaft arithmetic exists in two precisions.  double: the first version (every quantity exact to 1e-12, the only
+ * error of note the FP32 rounding of the mirror's box bounds).  float (the default): on sm_100 an FP64 fmin / fmax /
+ * select expands to several integer instructions and the walk is made of them (ncu, profiles/r1j_k_shadow_bulk.txt), so
+ * the same interval walk in FP32 with every bound pushed outward by the rounding it can have picked up -- relative 1e-6
+ * on a quotient (three roundings of 6e-8 and the reciprocal's), absolute 4e-7 (|bounds| + |origin|) on a slab numerator.
+ * A shaft only decides when its intervals separate, so wider intervals cost decisions within 1e-6 of a boundary, never
+ * correctness; FRT_FLAG_VERIFY_F32 checks every decided ray against the FP64 walk either way.
+ */
+template <typename T> struct ShaftEps;
+template <> struct ShaftEps<double> {
+    static __device__ __forceinline__ double rel() { return 1e-12; }   /* relative slack of a quotient */
+    static __device__ __forceinline__ double arith() { return 1e-12; } /* relative slack of a difference of coordinates */
+    static __device__ __forceinline__ double round32() { return 2.4e-7; } /* mirror bounds rounded to FP32: 2^-22 Bmax */
+    static __device__ __forceinline__ double dist() { return 1e-9; }   /* the light sits at t = 1 +- dist */
+    static __device__ __forceinline__ double tiny() { return 1e-300; }
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
+};
+template <> struct ShaftEps<float> {
+    static __device__ __forceinline__ float rel() { return 1e-6f; }
+    static __device__ __forceinline__ float arith() { return 2e-7f; }
+    static __device__ __forceinline__ float round32() { return 4e-7f; }
+    static __device__ __forceinline__ float dist() { return 2e-6f; }
+    static __device__ __forceinline__ float tiny() { return 1e-30f; }
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+};
+__device__ __forceinline__ float shaft_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double shaft_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float shaft_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double shaft_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float shaft_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ double shaft_abs(double a) { return fabs(a); }
+__device__ __forceinline__ float shaft_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double shaft_sqrt(double a) { return sqrt(a); }
+
+template <typename T>
+struct ShaftT {
+    T o[3];
+    T ia[3], ib[3]; /* sgn != 0: 1 / min |d_k|, 1 / max |d_k|;  sgn == 0: 1 / max(d_k, tiny), 1 / min(d_k, -tiny) */
     int sgn[3]; /* +1 / -1: d_k has that sign on every ray and the reference divides; 0: see above */
-    double en;  /* bound on the error of a slab numerator (b - o_k) */
+    T en;       /* bound on the error of a slab numerator (b - o_k) */
     float dl[3], dh[3]; /* the box of (unnormalised) ray directions p - o, slack included (shaft_sphere) */
 };
+typedef ShaftT<double> ShaftD;
 
+template <typename T>
 __device__ __forceinline__ void
-shaft_d_setup(ShaftD &s, const double *box, const double *over, double orel, float bmax, float smin, float ealign)
+shaft_d_setup(ShaftT<T> &s, const double *box, const T *over, T orel, float bmax, float smin, float ealign)
 {
     /* over: the rays' common origin, known up to orel * |over| per component (the FP32 copy of the over-point in LightTmp:
      * 2^-24; reading it instead of the FP64 record saves the per-hit kernels a 152-byte-strided load) */
     /* box: axis-aligned bounds {min xyz, max xyz} of the light points the rays aim at (the whole light, or one quadrant
      * of its sample grid), measured over every cached sample set at upload and inflated there */
-    double cmax = 0.0, len2max = 0.0, dlo[3], dhi[3];
+    typedef ShaftEps<T> E;
+    T cmax = (T)0, len2max = (T)0, dlo[3], dhi[3];
     for (int k = 0; k < 3; ++k) {
-        const double lo = __ldg(box + k), hi = __ldg(box + 3 + k);
+        const T lo = (T)__ldg(box + k), hi = (T)__ldg(box + 3 + k);
         s.o[k] = over[k];
         dlo[k] = lo - over[k];
         dhi[k] = hi - over[k];
-        cmax = fmax(cmax, fmax(fabs(over[k]), fmax(fabs(lo), fabs(hi))));
-        const double m = fmax(fabs(dlo[k]), fabs(dhi[k]));
+        cmax = shaft_max(cmax, shaft_max(shaft_abs(over[k]), shaft_max(shaft_abs(lo), shaft_abs(hi))));
+        const T m = shaft_max(shaft_abs(dlo[k]), shaft_abs(dhi[k]));
         len2max += m * m;
     }
-    const double sd = (1e-12 + (double)ealign + orel) * 2.0 * cmax + 1e-300;
+    const T sd = (E::arith() + (T)ealign + orel) * (T)2 * cmax + E::tiny();
     /* the reference divides by the LOCAL normalised component when it is >= EPSILON: local = scale * world */
-    const double thr = 2.0 * FRT_EPS * sqrt(len2max) / (double)smin;
+    const T thr = (T)2 * (T)FRT_EPS * shaft_sqrt(len2max) / (T)smin;
     for (int k = 0; k < 3; ++k) {
         dlo[k] -= sd;
         dhi[k] += sd;
         s.dl[k] = (float)dlo[k];
         s.dh[k] = (float)dhi[k];
         s.sgn[k] = dlo[k] > thr ? 1 : (dhi[k] < -thr ? -1 : 0);
-        /* the slab quotients become products with these reciprocals (their rounding, 2^-52, sits in shaft_box_d's 1e-12) */
+        /* the slab quotients become products with these reciprocals (their rounding sits in shaft_box_d's relative slack) */
         if (s.sgn[k] > 0) {
-            s.ia[k] = 1.0 / dlo[k];
-            s.ib[k] = 1.0 / dhi[k];
+            s.ia[k] = (T)1 / dlo[k];
+            s.ib[k] = (T)1 / dhi[k];
         } else if (s.sgn[k] < 0) {
-            s.ia[k] = -1.0 / dhi[k];
-            s.ib[k] = -1.0 / dlo[k];
+            s.ia[k] = (T)-1 / dhi[k];
+            s.ib[k] = (T)-1 / dlo[k];
         } else {
-            s.ia[k] = 1.0 / fmax(dhi[k], 1e-300);
-            s.ib[k] = 1.0 / fmin(dlo[k], -1e-300);
+            s.ia[k] = (T)1 / shaft_max(dhi[k], E::tiny());
+            s.ib[k] = (T)1 / shaft_min(dlo[k], -E::tiny());
         }
     }
-    s.en = 2.4e-7 * (double)bmax + (1e-12 + (double)ealign + orel) * cmax + 1e-300; /* bounds rounded to FP32: 2^-22 Bmax */
+    s.en = E::round32() * ((T)bmax + (sizeof(T) == 4 ? cmax : (T)0)) + (E::arith() + (T)ealign + orel) * cmax + E::tiny();
 }
 
 /* quotient range of n in [n_lo, n_hi] over e in [e_lo, e_hi], e_lo > 0, given ia = 1 / e_lo and ib = 1 / e_hi */
+template <typename T>
 __device__ __forceinline__ void
-shaft_div(double n_lo, double n_hi, double ia, double ib, double &q_lo, double &q_hi)
+shaft_div(T n_lo, T n_hi, T ia, T ib, T &q_lo, T &q_hi)
 {
-    q_lo = n_lo * (n_lo >= 0.0 ? ib : ia);
-    q_hi = n_hi * (n_hi >= 0.0 ? ia : ib);
+    q_lo = n_lo * (n_lo >= (T)0 ? ib : ia);
+    q_hi = n_hi * (n_hi >= (T)0 ? ia : ib);
 }
 
 /* entry / exit of every ray of the shaft through the world box [lo, hi], as intervals */
+template <typename T>
 __device__ __forceinline__ void
-shaft_box_d(const ShaftD &s, const float4 lo, const float4 hi, double &tn_lo, double &tn_hi, double &tf_lo, double &tf_hi)
+shaft_box_d(const ShaftT<T> &s, const float4 lo, const float4 hi, T &tn_lo, T &tn_hi, T &tf_lo, T &tf_hi)
 {
+    typedef ShaftEps<T> E;
     const float l[3] = { lo.x, lo.y, lo.z }, h[3] = { hi.x, hi.y, hi.z };
-    tn_lo = tn_hi = -CUDART_INF;
-    tf_lo = tf_hi = CUDART_INF;
+    tn_lo = tn_hi = -E::inf();
+    tf_lo = tf_hi = E::inf();
     for (int k = 0; k < 3; ++k) {
-        const double nl = (double)l[k] - s.o[k], nh = (double)h[k] - s.o[k];
-        double a_lo = -CUDART_INF, a_hi = CUDART_INF, b_lo = -CUDART_INF, b_hi = CUDART_INF;
+        const T nl = (T)l[k] - s.o[k], nh = (T)h[k] - s.o[k];
+        T a_lo = -E::inf(), a_hi = E::inf(), b_lo = -E::inf(), b_hi = E::inf();
         if (s.sgn[k] > 0) {
             shaft_div(nl - s.en, nl + s.en, s.ia[k], s.ib[k], a_lo, a_hi);
             shaft_div(nh - s.en, nh + s.en, s.ia[k], s.ib[k], b_lo, b_hi);
         } else if (s.sgn[k] < 0) { /* near = hi / d = (-hi) / (-d) */
             shaft_div(-nh - s.en, -nh + s.en, s.ia[k], s.ib[k], a_lo, a_hi);
             shaft_div(-nl - s.en, -nl + s.en, s.ia[k], s.ib[k], b_lo, b_hi);
-        } else if (nl + s.en < 0.0 && nh - s.en > 0.0) { /* ia = 1 / (largest positive d), ib = 1 / (most negative d) */
-            a_hi = fmax((nl + s.en) * s.ia[k], (nh - s.en) * s.ib[k]);
-            b_lo = fmin((nh - s.en) * s.ia[k], (nl + s.en) * s.ib[k]);
+        } else if (nl + s.en < (T)0 && nh - s.en > (T)0) { /* ia = 1 / (largest positive d), ib = 1 / (most negative d) */
+            a_hi = shaft_max((nl + s.en) * s.ia[k], (nh - s.en) * s.ib[k]);
+            b_lo = shaft_min((nh - s.en) * s.ia[k], (nl + s.en) * s.ib[k]);
         }
-        tn_lo = fmax(tn_lo, a_lo);
-        tn_hi = fmax(tn_hi, a_hi);
-        tf_lo = fmin(tf_lo, b_lo);
-        tf_hi = fmin(tf_hi, b_hi);
+        tn_lo = shaft_max(tn_lo, a_lo);
+        tn_hi = shaft_max(tn_hi, a_hi);
+        tf_lo = shaft_min(tf_lo, b_lo);
+        tf_hi = shaft_min(tf_hi, b_hi);
     }
-    /* the reference evaluates the same quotients in the leaf's frame: FP64 rounding of either side */
-    tn_lo -= 1e-12 * fabs(tn_lo);
-    tn_hi += 1e-12 * fabs(tn_hi);
-    tf_lo -= 1e-12 * fabs(tf_lo);
-    tf_hi += 1e-12 * fabs(tf_hi);
+    /* the reference evaluates the same quotients in the leaf's frame (FP64 rounding of either side); in FP32 the products
+     * and reciprocals above carry their own roundings */
+    tn_lo -= E::rel() * shaft_abs(tn_lo);
+    tn_hi += E::rel() * shaft_abs(tn_hi);
+    tf_lo -= E::rel() * shaft_abs(tf_lo);
+    tf_hi += E::rel() * shaft_abs(tf_hi);
 }
 
 /* a WORLD cube leaf over the shaft; false = undecided */
+template <typename T>
 __device__ __forceinline__ bool
-shaft_leaf_span(const ShaftD &sh, const float4 q0, const float4 lo, const float4 hi, SpanD &s)
+shaft_leaf_span(const ShaftT<T> &sh, const float4 q0, const float4 lo, const float4 hi, SpanT<T> &s)
 {
     const int flags = __float_as_int(q0.x);
     s.flags = 0;
-    s.a_lo = s.a_hi = s.b_lo = s.b_hi = 0.0;
+    s.a_lo = s.a_hi = s.b_lo = s.b_hi = (T)0;
     if ((flags & FRT_FN_TYPE_MASK) != FRT_CUBE || !(flags & FRT_FN_FAST) || !(flags & FRT_FN_WORLD) || __float_as_int(q0.z) != 0) {
         return false;
     }
@@ -1040,8 +1084,9 @@ shaft_leaf_span(const ShaftD &sh, const float4 q0, const float4 lo, const float4
  *   (A) a circular cone around the box's axis that contains every corner direction (hence every direction: (u . w) / |w|
  *       is quasi-concave where positive) lies outside the tangent cone: angle(axis, centre) > cone angle + tangent angle.
  */
+template <typename T>
 __device__ __forceinline__ int
-shaft_sphere(const ShaftD &sh, const float4 sp, bool casts)
+shaft_sphere(const ShaftT<T> &sh, const float4 sp, bool casts)
 {
     const float r = sp.w;
     const float mx = sp.x - (float)sh.o[0], my = sp.y - (float)sh.o[1], mz = sp.z - (float)sh.o[2];
@@ -1097,10 +1142,11 @@ shaft_sphere(const ShaftD &sh, const float4 sp, bool casts)
  * One node of the shaft walk.  Returns 0 = no ray of the shaft ends its search here (go on at *next), 1 / 2 = every ray
  * ends it here, lit / shadowed, 3 = cannot tell (a leaf or a CSG node; *next is the node after it).
  */
+template <typename T>
 __device__ __forceinline__ int
-shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const ShaftD &sh, int i, int *next)
+shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const ShaftT<T> &sh, int i, int *next)
 {
-    const double D_lo = 1.0 - 1e-9, D_hi = 1.0 + 1e-9;
+    const T D_lo = (T)1 - ShaftEps<T>::dist(), D_hi = (T)1 + ShaftEps<T>::dist();
     const float4 q0 = __ldg(fnodes + 3 * i);
     const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
     if (!((relevant >> i) & 1u)) {
@@ -1109,13 +1155,13 @@ shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const
     }
     const float4 lo = __ldg(fnodes + 3 * i + 1), hi = __ldg(fnodes + 3 * i + 2);
     const int type = flags & FRT_FN_TYPE_MASK;
-    SpanD s;
+    SpanT<T> s;
     if (type >= FRT_CSG) {
         *next = skip;
         if (!(flags & FRT_FN_NOCULL) && (flags & FRT_FN_WORLD) && __float_as_int(q0.z) == 0) {
-            double tn_lo, tn_hi, tf_lo, tf_hi;
+            T tn_lo, tn_hi, tf_lo, tf_hi;
             shaft_box_d(sh, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-            if (tn_lo > tf_hi || tf_hi < 0.0) {
+            if (tn_lo > tf_hi || tf_hi < (T)0) {
                 return 0;
             }
         }
@@ -1129,12 +1175,12 @@ shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const
         int pc = __float_as_int(lo.w);
         const int pc1 = pc + __float_as_int(hi.w);
         s.flags = 0;
-        s.a_lo = s.a_hi = s.b_lo = s.b_hi = 0.0;
+        s.a_lo = s.a_hi = s.b_lo = s.b_hi = (T)0;
         for (bool first = true; pc < pc1; first = false) {
             const int code = __ldg(SF.csg_prog + pc);
-            SpanD t;
+            SpanT<T> t;
             t.flags = 0;
-            t.a_lo = t.a_hi = t.b_lo = t.b_hi = 0.0;
+            t.a_lo = t.a_hi = t.b_lo = t.b_hi = (T)0;
             /* an operand outside the shaft has no crossing at t > 0: for the crossings at t > 0 it is absent */
             if (((relevant >> code) & 1u) &&
                 !shaft_leaf_span(sh, __ldg(fnodes + 3 * code), __ldg(fnodes + 3 * code + 1), __ldg(fnodes + 3 * code + 2), t)) {
@@ -1145,8 +1191,8 @@ shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const
                 pc += 1;
             } else {
                 const int op = -__ldg(SF.csg_prog + pc + 1) - 1;
-                SpanD r;
-                r.a_lo = r.a_hi = r.b_lo = r.b_hi = 0.0;
+                SpanT<T> r;
+                r.a_lo = r.a_hi = r.b_lo = r.b_hi = (T)0;
                 if (!csg_combine(op, s, t, r)) {
                     return 3;
                 }
@@ -1187,8 +1233,9 @@ shaft_node(const DSceneF &SF, const float4 *fnodes, unsigned int relevant, const
  * Stuck more than FRT_PROG_MAX times: tail 0, the rays walk the tree from X1 on.
  */
 #define FRT_RESUME_NODE_MASK 31
+template <typename T>
 __device__ __forceinline__ int
-trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const ShaftD &sh, unsigned int *prog)
+trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const ShaftT<T> &sh, unsigned int *prog)
 {
     const float4 *fnodes = SF.fnodes;
     int i = root, n_stuck = 0;

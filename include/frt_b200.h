@@ -206,6 +206,7 @@ enum frt_render_flags {
     FRT_FLAG_NO_SHAFT = 32,  /* switch the per-hit shaft culling of the shadow filter off (A/B measurements, tests) */
     FRT_FLAG_NO_BULK = 64,   /* switch the per-hit decision of all shadow rays at once (k_shadow_bulk) off */
     FRT_FLAG_NO_SPLIT = 128, /* ... keep it, but do not retry undecided hits per quadrant of the light's sample grid */
+    FRT_FLAG_F64_SHAFT = 512, /* per-hit / per-quadrant shaft walk in FP64 (the first version) instead of FP32 with outward slack */
     FRT_FLAG_STAGE_TIMES = 256, /* bracket every kernel of the frame with events and fill frt_stats.stage_ms completely (the
                                 shadow-ray and shaft stages are always timed) */
     FRT_FLAG_F64_SHADING = 4 /* evaluate the lighting sums (lighting_microfacet, renderer.c:894-979) in FP64 like the
