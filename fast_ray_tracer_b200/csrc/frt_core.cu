@@ -778,6 +778,7 @@ quadrant_sample(int4 lq, int q, int k)
 
 /* pending entry: hit in bits 0..27, quadrant in bits 28..29, bit 30 = decided by k_shadow_bulk, bit 31 = ... as lit */
 #define FRT_BOX_CHUNKS 512
+#define FRT_QS_MAX 256 /* samples per pending entry up to which k_shadow_f32 tabulates quadrant_sample in shared memory */
 #define FRT_PEND_HIT_MASK 0x0fffffffu
 #define FRT_PEND_BULK 0x40000000u
 #define FRT_PEND_LIT 0x80000000u
@@ -838,7 +839,7 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             const unsigned int slot = warp_append(&cnt->n_pending, keep);
             if (keep) {
                 pending[slot] = h | ((unsigned int)q << 28) | (state >= 2 ? FRT_PEND_BULK : 0u) | (state == 3 ? FRT_PEND_LIT : 0u);
-                pprog[slot] = state == 1 ? prog : FRT_PROG_ROOT(root);
+                pprog[slot] = state == 1 ? (prog | (entry_program_is_fast(prog, SF.entry_fast) ? FRT_PROG_FAST : 0u)) : FRT_PROG_ROOT(root);
             }
         }
     }
@@ -886,7 +887,7 @@ k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         const unsigned int slot = warp_append(&cnt->n_pending, keep);
         if (keep) {
             pending[slot] = h | ((unsigned int)q << 28) | (state >= 2 ? FRT_PEND_BULK : 0u) | (state == 3 ? FRT_PEND_LIT : 0u);
-            pprog[slot] = state == 1 ? prog : FRT_PROG_ROOT(root);
+            pprog[slot] = state == 1 ? (prog | (entry_program_is_fast(prog, SF.entry_fast) ? FRT_PROG_FAST : 0u)) : FRT_PROG_ROOT(root);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -1045,18 +1046,31 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
 {
     constexpr bool COUNT = MODE != 0;
     extern __shared__ float4 s_nodes[];
+    __shared__ unsigned short s_qs[4 * FRT_QS_MAX]; /* sample index of (quadrant, k): quadrant_sample, tabulated per block */
     const float4 *fnodes = SF.fnodes;
-    if (nodes_in_smem) { /* small trees (every scene but the OBJ meshes) are walked out of shared memory */
-        for (int k = threadIdx.x; k < 3 * SF.n_nodes; k += blockDim.x) {
-            s_nodes[k] = SF.fnodes[k];
-        }
-        __syncthreads();
-        fnodes = s_nodes;
-    }
-    const unsigned int n = min(cnt->n_pending, pend_cap); /* (hit, quadrant) entries k_shadow_bulk left to be traced ray by ray */
+    const int *cprog = SF.csg_prog;
     const int NS = S.lights[light_idx].num_samples;
     const int4 lq = split_on ? __ldg(SF.lquad + light_idx) : make_int4(NS, 0, 0, 0);
     const int NSQ = lq.x; /* samples per entry */
+    const bool qs_table = NSQ <= FRT_QS_MAX;
+    if (nodes_in_smem) { /* small trees (every scene but the OBJ meshes) are walked out of shared memory, CSG programs included */
+        for (int k = threadIdx.x; k < 3 * SF.n_nodes; k += blockDim.x) {
+            s_nodes[k] = SF.fnodes[k];
+        }
+        int *s_prog = reinterpret_cast<int *>(s_nodes + 3 * SF.n_nodes);
+        for (int k = threadIdx.x; k < SF.n_csg_prog; k += blockDim.x) {
+            s_prog[k] = SF.csg_prog[k];
+        }
+        fnodes = s_nodes;
+        cprog = s_prog;
+    }
+    if (qs_table) {
+        for (int k = threadIdx.x; k < 4 * NSQ; k += blockDim.x) {
+            s_qs[k] = (unsigned short)quadrant_sample(lq, k / NSQ, k % NSQ);
+        }
+    }
+    __syncthreads();
+    const unsigned int n = min(cnt->n_pending, pend_cap); /* (hit, quadrant) entries k_shadow_bulk left to be traced ray by ray */
     const float *fpts = SF.lpoints + 3 * S.lights[light_idx].point_offset;
     const double *pts = S.lpoints + 3 * S.lights[light_idx].point_offset;
     const unsigned long long total = (unsigned long long)n * (unsigned int)NSQ;
@@ -1080,12 +1094,12 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
             const unsigned int idx = NSQ > 1 ? (unsigned int)__umul64hi(item, ns_magic) : (unsigned int)item; /* item / NSQ, exact while item * NSQ < 2^64 */
             entry = __ldg(pending + idx);
             prog = __ldg(pprog + idx);
-            s = quadrant_sample(lq, (entry >> 28) & 3, (int)(item - (unsigned long long)idx * (unsigned int)NSQ));
+            const int k = (int)(item - (unsigned long long)idx * (unsigned int)NSQ), q = (int)((entry >> 28) & 3u);
+            s = qs_table ? (int)s_qs[q * NSQ + k] : quadrant_sample(lq, q, k);
             h = entry & FRT_PEND_HIT_MASK;
             head = *reinterpret_cast<const float4 *>(tmp + h);
         }
         const int set_a = __float_as_int(head.w);
-        const unsigned int relevant = set_a >= 0 ? tmp[h].relevant : 0u;
         const int bulk = (MODE != 0 && set_a >= 0) ? (int)(entry >> 30) : 0; /* bit 0: decided by k_shadow_bulk, bit 1: as lit */
         int res = FRT_SH_SHADOWED;
         if (set_a >= 0) {
@@ -1116,13 +1130,13 @@ k_shadow_f32(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ r
                 frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
                 const float Df = len2 * rinv;
                 const float D_lo = Df - Df * ed_w, D_hi = Df + Df * ed_w;
-                if (use_start && entry_program_is_fast(prog, SF.entry_fast)) {
-                    res = trace_entry_program<COUNT>(SF, fnodes, prog, w, omax, eo_o, D_lo, D_hi, &n_nodes, &n_flops);
+                if (use_start && (prog & FRT_PROG_FAST)) {
+                    res = trace_entry_program<COUNT>(SF, fnodes, cprog, prog, w, omax, eo_o, D_lo, D_hi, &n_nodes, &n_flops);
                 } else {
                     /* the general walk from X1; a single-node program's tail verdict still ends it right after X1 */
                     const int tail = (use_start && FRT_PROG_COUNT(prog) == 1) ? FRT_PROG_TAIL(prog) : 0;
-                    res = trace_shadow_f32_call<COUNT>(SF, fnodes, root, use_start ? FRT_PROG_NODE(prog, 0) : root, tail, relevant, w, omax, eo_o, ed_w,
-                                                     D_lo, D_hi, &n_nodes, &n_flops);
+                    res = trace_shadow_f32_call<COUNT>(SF, fnodes, root, use_start ? FRT_PROG_NODE(prog, 0) : root, tail, tmp[h].relevant, w, omax,
+                                                     eo_o, ed_w, D_lo, D_hi, &n_nodes, &n_flops);
                 }
                 if (COUNT && (res >> 4)) {
                     atomicAdd(&cnt->undecided_reason[min((res >> 4) & 15, 9)], 1ull);
@@ -1245,7 +1259,7 @@ k_shadow_entry(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
         const int bulk = MODE != 0 ? (int)(entry >> 30) : 0; /* bit 0: decided by k_shadow_bulk, bit 1: as lit */
         const int node = FRT_PROG_NODE(prog, 0);
         const int tail = FRT_PROG_COUNT(prog) == 1 ? FRT_PROG_TAIL(prog) : 0; /* for the general walk from X1 */
-        const bool fast = use_start && S.n_roots == 1 && entry_program_is_fast(prog, SF.entry_fast);
+        const bool fast = use_start && S.n_roots == 1 && (prog & FRT_PROG_FAST) != 0u;
         /* per entry: the origin's error terms */
         const float omax = fmaxf(fmaxf(fabsf(head.x), fabsf(head.y)), fabsf(head.z));
         const float eo_o = 2.0f * FRT_F32_U * omax;
@@ -1284,7 +1298,7 @@ k_shadow_entry(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
                     const float Df = len2 * rinv;
                     const float D_lo = Df - Df * ed_w, D_hi = Df + Df * ed_w;
                     if (fast) {
-                        res = trace_entry_program<COUNT>(SF, fnodes, prog, w, omax, eo_o, D_lo, D_hi, &n_nodes, &n_flops);
+                        res = trace_entry_program<COUNT>(SF, fnodes, SF.csg_prog, prog, w, omax, eo_o, D_lo, D_hi, &n_nodes, &n_flops);
                     } else {
                         res = trace_shadow_f32_call<COUNT>(SF, fnodes, root, node, tail, relevant, w, omax, eo_o, ed_w, D_lo, D_hi, &n_nodes, &n_flops);
                     }
@@ -2829,6 +2843,7 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     if (rc != FRT_OK) return rc;
     rc = upload(sc, prog.data(), prog.size(), &sc->SF.csg_prog);
     if (rc != FRT_OK) return rc;
+    sc->SF.n_csg_prog = (int)prog.size();
     sc->SF.smin = (float)(smin * (1.0 - 1e-6));
     sc->SF.ealign = (float)(2.0 * tilt * (1.0 + 1e-6));
     rc = upload(sc, fn.data(), fn.size(), &sc->SF.fnodes);
@@ -3857,7 +3872,8 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         tock(tk);
                         launches += 1;
                     } else {
-                        const size_t f32_smem = (size_t)sc->S.n_nodes * 48 <= 32768 ? (size_t)sc->S.n_nodes * 48 : 0;
+                        const size_t f32_smem = (size_t)sc->S.n_nodes * 48 + (size_t)sc->SF.n_csg_prog * 4 <= 32768
+                                                    ? (size_t)sc->S.n_nodes * 48 + (size_t)sc->SF.n_csg_prog * 4 : 0;
                         /* many short grid-stride trips balance the uneven per-ray work better than 8 CTAs per SM (measured: 35.0 -> 33.5 ms) */
                         CK(cudaMemsetAsync(&sc->cnt->n_deferred, 0, 2 * sizeof(unsigned int), s)); /* n_deferred, n_pending */
                         /* per hit: every shadow ray at once where the shaft's intervals separate (small trees, area lights) */

@@ -76,6 +76,7 @@ struct DSceneF {
     float ealign;         /* 2 x the largest off-axis / on-axis ratio of a transform treated as axis-aligned (<= 2e-9):
                              a WORLD box test sees the world point up to ealign |o|max, the direction up to ealign, off */
     int n_nodes;
+    int n_csg_prog;          /* words in csg_prog */
     unsigned int entry_fast; /* bit i: node i (< 32) is a WORLD cube leaf, a CSG over WORLD cube leaves or a WORLD ball (entry_node_span) */
 };
 
@@ -742,12 +743,14 @@ csg_combine_sel(int op, const SpanF &L, const SpanF &R, SpanF &out)
  *     bits 0..1  tail: 1 lit, 2 shadowed, 0 = the walk got stuck more often than the program holds (general walk from X1)
  *     bits 2..3  number of nodes (1..3)
  *     bits 4..8, 9..13, 14..18  X1, X2, X3
+ *     bit 19     the rays can run the program without the tree walk (entry_program_is_fast, decided once per entry)
  * A ray evaluates X1, X2, ... in turn and takes the first one's verdict that stops it, else the tail (trace_entry_program).
  * Nodes it can evaluate without the tree walk (DSceneF::entry_fast): WORLD-space cube leaves, outermost CSGs whose program
  * runs over WORLD-space cube leaves (every wall, box and window of the Cornell scene: X's own bounds are not tested -- a
  * ray that misses them misses every operand inside) and WORLD-space balls (DSceneF::wsphere).
  */
 #define FRT_PROG_MAX 3
+#define FRT_PROG_FAST (1u << 19) /* every node of the program is in DSceneF::entry_fast and the tail verdict is known: set by the shaft kernels */
 #define FRT_PROG_ROOT(root) ((1u << 2) | ((unsigned int)(root) << 4)) /* one node, no tail: the general walk from `root` */
 #define FRT_PROG_TAIL(p) ((int)((p) & 3u))
 #define FRT_PROG_COUNT(p) ((int)(((p) >> 2) & 3u))
@@ -756,7 +759,7 @@ csg_combine_sel(int op, const SpanF &L, const SpanF &R, SpanF &out)
 /* one program node as a span (flags 0: the ray does not cross it); false = undecided */
 template <bool COUNT>
 __device__ __forceinline__ bool
-entry_node_span(const DSceneF &SF, const float4 *fnodes, int node, const FrameF &w, float omax, float eo_o, SpanF &s,
+entry_node_span(const DSceneF &SF, const float4 *fnodes, const int *cprog, int node, const FrameF &w, float omax, float eo_o, SpanF &s,
                 unsigned int &visited, unsigned int &cost)
 {
     const float4 q0 = fnodes[3 * node];
@@ -766,7 +769,7 @@ entry_node_span(const DSceneF &SF, const float4 *fnodes, int node, const FrameF 
         int pc = __float_as_int(fnodes[3 * node + 1].w);
         const int pc1 = pc + __float_as_int(fnodes[3 * node + 2].w);
         {
-            const int code = __ldg(SF.csg_prog + pc);
+            const int code = cprog[pc];
             const int lf = __float_as_int(fnodes[3 * code].x);
             box_f(w, fnodes[3 * code + 1], fnodes[3 * code + 2], s.a_lo, s.a_hi, s.b_lo, s.b_hi);
             const bool miss = s.a_lo > s.b_hi;
@@ -774,7 +777,7 @@ entry_node_span(const DSceneF &SF, const float4 *fnodes, int node, const FrameF 
             s.flags = miss ? 0 : ((lf & FRT_FN_CASTS) ? 7 : 1);
         }
         for (pc += 1; pc < pc1; pc += 2) {
-            const int code = __ldg(SF.csg_prog + pc), op = -__ldg(SF.csg_prog + pc + 1) - 1;
+            const int code = cprog[pc], op = -cprog[pc + 1] - 1;
             const int lf = __float_as_int(fnodes[3 * code].x);
             SpanF t, r;
             box_f(w, fnodes[3 * code + 1], fnodes[3 * code + 2], t.a_lo, t.a_hi, t.b_lo, t.b_hi);
@@ -828,8 +831,8 @@ entry_node_span(const DSceneF &SF, const float4 *fnodes, int node, const FrameF 
  * Returns FRT_SH_* like trace_shadow_f32 (reason / node of an undecided ray in bits 4.. for the counting build). */
 template <bool COUNT>
 __device__ __forceinline__ int
-trace_entry_program(const DSceneF &SF, const float4 *fnodes, unsigned int prog, const FrameF &w, float omax, float eo_o, float D_lo,
-                    float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
+trace_entry_program(const DSceneF &SF, const float4 *fnodes, const int *cprog, unsigned int prog, const FrameF &w, float omax, float eo_o,
+                    float D_lo, float D_hi, unsigned long long *nodes_visited, unsigned long long *flops)
 {
     const int n = FRT_PROG_COUNT(prog);
     unsigned int visited = 0, cost = 0;
@@ -837,7 +840,7 @@ trace_entry_program(const DSceneF &SF, const float4 *fnodes, unsigned int prog, 
     for (int k = 0; k < n; ++k) {
         const int node = FRT_PROG_NODE(prog, k);
         SpanF s;
-        if (!entry_node_span<COUNT>(SF, fnodes, node, w, omax, eo_o, s, visited, cost)) {
+        if (!entry_node_span<COUNT>(SF, fnodes, cprog, node, w, omax, eo_o, s, visited, cost)) {
             res = FRT_SH_UNDECIDED | (5 << 4) | ((node & 31) << 8);
             break;
         }
