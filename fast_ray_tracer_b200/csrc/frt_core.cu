@@ -105,11 +105,19 @@ struct HitQ { /* result of k_extend, indexed like the ray queue */
     int *leaf;
 };
 
-struct LightRec { /* one shaded hit handed to k_light (AoS: all lanes of a hit group read the same record) */
-    double over[3], n[3], eye[3];
-    double Ka[3], Kd[3], Ks[3];
-    double Ns;
-    double w[3];
+/*
+ * One shaded hit handed to the light stage (AoS: the lanes of a hit read the same record).  112 bytes: the over-point
+ * stays FP64 (it is the origin of the hit's FP64 shadow rays), everything the light stage only feeds into its FP32
+ * sums -- normal, eye vector, material colours, the path's weight -- is FP32.  The all-FP64 record was 184 bytes and
+ * k_shade, which writes one per hit, ran at 41 % of the HBM peak with 19 % issue utilisation (profiles/r2_k_shade.txt:
+ * 3.9 GB written per launch); k_light_pre and k_light_final read them back.
+ */
+struct alignas(16) LightRec {
+    double over[3];
+    float n[3], eye[3];
+    float Ka[3], Kd[3], Ks[3];
+    float Ns;
+    float w[3];
     int pixel;
     unsigned int rng;
 };
@@ -390,9 +398,9 @@ material_color(const DScene &S, int map, const double *flat, int leaf, const dou
 __global__ void __launch_bounds__(128)
 k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counters *cnt, int level)
 {
-    static_assert(sizeof(LightRec) % 8 == 0, "LightRec is copied as 8-byte words");
-    constexpr int FRT_REC_WORDS = (int)(sizeof(LightRec) / 8);
-    __shared__ unsigned long long s_stage[4][32 * FRT_REC_WORDS];
+    static_assert(sizeof(LightRec) % 16 == 0, "LightRec is copied as 16-byte words");
+    constexpr int FRT_REC_WORDS = (int)(sizeof(LightRec) / 16);
+    __shared__ uint4 s_stage[4][32 * FRT_REC_WORDS];
     const unsigned int n = min(cnt->n_rays[level], F.capacity);
     const int remaining = F.path_length - level;
     int overflow = 0;
@@ -573,8 +581,8 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
                 const unsigned int count = (unsigned int)__popc(wmask);
                 constexpr int W = FRT_REC_WORDS;
                 if (want_rec) {
-                    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&rec);
-                    unsigned long long *dst = s_stage[wib] + (slot - base) * W; /* rank among the warp's records */
+                    const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+                    uint4 *dst = s_stage[wib] + (slot - base) * W; /* rank among the warp's records */
 #pragma unroll
                     for (int k = 0; k < W; ++k) {
                         dst[k] = src[k];
@@ -582,7 +590,7 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
                 }
                 __syncwarp();
                 if (base + count <= F.capacity) {
-                    unsigned long long *g = reinterpret_cast<unsigned long long *>(recs + base);
+                    uint4 *g = reinterpret_cast<uint4 *>(recs + base);
                     for (unsigned int j = lane; j < count * W; j += 32) {
                         g[j] = s_stage[wib][j];
                     }
