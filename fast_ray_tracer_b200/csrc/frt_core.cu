@@ -395,7 +395,15 @@ material_color(const DScene &S, int map, const double *flat, int leaf, const dou
     }
 }
 
-__global__ void __launch_bounds__(128)
+/*
+ * MAPS: some material of the scene has a pattern / texture / bump map; REFRACT: some material lets light through (the
+ * n1 / n2 containers are walked).  A scene without either (the Cornell box: flat materials, one mirror) runs an
+ * instantiation without the pattern interpreter and the container walk: the general one is 14 K SASS instructions with a
+ * 2 KB local frame and stalls on it (profiles/r2_k_shade.txt: 15 % of its instructions are local loads / stores,
+ * long_scoreboard 14 warps per issue).
+ */
+template <bool MAPS, bool REFRACT>
+__global__ void __launch_bounds__(128, (MAPS || REFRACT) ? 4 : 5)
 k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counters *cnt, int level)
 {
     static_assert(sizeof(LightRec) % 16 == 0, "LightRec is copied as 16-byte words");
@@ -436,7 +444,7 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
             point_to_local(S, a.xform, p, lp);
             local_normal(a.type, prm, lp, h.u[i], h.v[i], ln);
             normal_to_world(S, a.xform, ln, nrm);
-            if (M.map_bump >= 0) { /* shape_normal_at, shapes.c:76-86: n += 2*texel - 1, sampled at the hit point */
+            if (MAPS && M.map_bump >= 0) { /* shape_normal_at, shapes.c:76-86: n += 2*texel - 1, sampled at the hit point */
                 double tex[3];
                 pattern_at_shape(S, M.map_bump, leaf, p, NULL, tex, 0);
                 nrm[0] += 2.0 * tex[0] - 1.0;
@@ -461,18 +469,18 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
             double under[3] = { p[0] - nrm[0] * FRT_EPS, p[1] - nrm[1] * FRT_EPS, p[2] - nrm[2] * FRT_EPS };
 
             double Ka[3], Kd[3], Ks[3], refl[3];
-            material_color(S, M.map_Ka, M.Ka, leaf, over, Ka);
-            material_color(S, M.map_Kd, M.Kd, leaf, over, Kd);
-            material_color(S, M.map_Ks, M.Ks, leaf, over, Ks);
-            material_color(S, M.map_refl, M.refl, leaf, over, refl);
+            material_color(S, MAPS ? M.map_Ka : -1, M.Ka, leaf, over, Ka);
+            material_color(S, MAPS ? M.map_Kd : -1, M.Kd, leaf, over, Kd);
+            material_color(S, MAPS ? M.map_Ks : -1, M.Ks, leaf, over, Ks);
+            material_color(S, MAPS ? M.map_refl : -1, M.refl, leaf, over, refl);
             double Ns = M.Ns;
-            if (M.map_Ns >= 0) {
+            if (MAPS && M.map_Ns >= 0) {
                 double tmp[3];
                 pattern_at_shape(S, M.map_Ns, leaf, over, NULL, tmp, 0);
                 Ns = tmp[0];
             }
             double over_d = 1.0 - M.Tr;
-            if (M.map_d >= 0) {
+            if (MAPS && M.map_d >= 0) {
                 double tmp[3];
                 pattern_at_shape(S, M.map_d, leaf, over, NULL, tmp, 0);
                 over_d = tmp[0];
@@ -492,7 +500,7 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
             }
             bool use_schlick = M.reflective && over_d < 1.0;            /* :788 */
             double n1 = 1.0, n2 = 1.0;
-            if (do_refr || (use_schlick && (do_refl || do_refr))) {
+            if (REFRACT && (do_refr || (use_schlick && (do_refl || do_refr)))) {
                 trace_containers(S, r, leaf, n1, n2, &overflow);
             }
             double cos_i = eye[0] * nrm[0] + eye[1] * nrm[1] + eye[2] * nrm[2];
@@ -1970,6 +1978,8 @@ struct frt_scene {
     cudaEvent_t nrays_ev = nullptr;
     LightTmp *ltmp_multi = nullptr; /* mesh mode with several lights: one LightTmp array per light of a shared launch */
     size_t ltmp_multi_cap = 0;
+    bool has_maps = false;       /* some material carries a pattern / texture / bump map (k_shade instantiation) */
+    bool has_refraction = false; /* some material refracts, or is a dissolving mirror: n1 / n2 containers are needed */
     bool mesh_mode = false; /* most leaves have no FP32 fast form (OBJ meshes): shadow rays go straight to k_shadow_mesh */
     double *canvas = nullptr;     /* hsize*vsize*4 doubles */
     double *samples = nullptr;
@@ -3261,6 +3271,17 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     memcpy(C.aperture_args, c.aperture_args, sizeof(C.aperture_args));
 
     sc->cfg = d->config;
+    for (int i = 0; i < d->n_materials; ++i) {
+        const frt_material &m = d->materials[i];
+        if (m.map_Ka >= 0 || m.map_Kd >= 0 || m.map_Ks >= 0 || m.map_Ns >= 0 || m.map_d >= 0 || m.map_bump >= 0 || m.map_refl >= 0) {
+            sc->has_maps = true;
+        }
+        /* the containers feed the refraction ratio and Schlick's reflectance (renderer.c:403-447, :607): needed when a ray can
+         * refract (over_d > 0 with a non-zero Tf under FRT_FLAG_NO_PRUNE too) or when a mirror dissolves (over_d < 1) */
+        if (m.Tr > 0.0 || m.Tf[0] != 0.0 || m.Tf[1] != 0.0 || m.Tf[2] != 0.0 || m.Ni != 1.0) {
+            sc->has_refraction = true;
+        }
+    }
     {
         long leaves = 0, slow = 0;
         for (int i = 0; i < d->n_nodes; ++i) {
@@ -3802,7 +3823,13 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, sc->SF, qi, sc->hq, sc->cnt, level, F.capacity);
             tock(tk);
             tk = tick(FRT_ST_SHADE);
-            k_shade<<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+            if (sc->has_maps) {
+                k_shade<true, true><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+            } else if (sc->has_refraction) {
+                k_shade<false, true><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+            } else {
+                k_shade<false, false><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+            }
             tock(tk);
             launches += 2;
             if (sc->h_nrays != nullptr && level < F.path_length) {
