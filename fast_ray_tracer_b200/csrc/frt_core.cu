@@ -363,6 +363,7 @@ k_raygen(DCamera C, FrameParams F, RayQ q, Counters *cnt, unsigned int first_sam
 
 /* ------------------------------------------------------------------------------------------------ extend */
 
+template <int PRIMS>
 __global__ void __launch_bounds__(256)
 k_extend(DScene S, DSceneF SF, RayQ q, HitQ h, Counters *cnt, int level, unsigned int capacity)
 {
@@ -370,7 +371,7 @@ k_extend(DScene S, DSceneF SF, RayQ q, HitQ h, Counters *cnt, int level, unsigne
     int overflow = 0;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Ray r{ q.ox[i], q.oy[i], q.oz[i], q.dx[i], q.dy[i], q.dz[i] };
-        Hit best = trace_closest_mixed<false>(S, SF, r, &overflow);
+        Hit best = trace_closest_mixed<false, PRIMS>(S, SF, r, &overflow);
         h.t[i] = best.t;
         h.u[i] = best.u;
         h.v[i] = best.v;
@@ -1978,6 +1979,7 @@ struct frt_scene {
     cudaEvent_t nrays_ev = nullptr;
     LightTmp *ltmp_multi = nullptr; /* mesh mode with several lights: one LightTmp array per light of a shared launch */
     size_t ltmp_multi_cap = 0;
+    bool boxes_and_balls = false; /* no leaf type beyond cube / sphere / plane (k_extend instantiation) */
     bool has_maps = false;       /* some material carries a pattern / texture / bump map (k_shade instantiation) */
     bool has_refraction = false; /* some material refracts, or is a dissolving mirror: n1 / n2 containers are needed */
     bool mesh_mode = false; /* most leaves have no FP32 fast form (OBJ meshes): shadow rays go straight to k_shadow_mesh */
@@ -3292,6 +3294,7 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
             }
         }
         sc->mesh_mode = slow * 2 > leaves && d->n_nodes > 64;
+        sc->boxes_and_balls = slow == 0;
         const char *env = getenv("FRT_MESH_MODE");
         if (env != nullptr && *env) {
             sc->mesh_mode = atoi(env) != 0;
@@ -3820,7 +3823,11 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
              * the level can hold, but never more than a few waves */
             int ex_blocks = sm_blocks * 8;
             tk = tick(FRT_ST_EXTEND);
-            k_extend<<<ex_blocks, 256, 0, s>>>(sc->S, sc->SF, qi, sc->hq, sc->cnt, level, F.capacity);
+            if (sc->boxes_and_balls) { /* the scene holds cubes, spheres, planes, CSGs and groups only */
+                k_extend<FRT_PRIMS_BOXES_AND_BALLS><<<ex_blocks, 256, 0, s>>>(sc->S, sc->SF, qi, sc->hq, sc->cnt, level, F.capacity);
+            } else {
+                k_extend<FRT_PRIMS_ALL><<<ex_blocks, 256, 0, s>>>(sc->S, sc->SF, qi, sc->hq, sc->cnt, level, F.capacity);
+            }
             tock(tk);
             tk = tick(FRT_ST_SHADE);
             if (sc->has_maps) {

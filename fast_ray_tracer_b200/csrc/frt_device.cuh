@@ -382,9 +382,28 @@ toroid_intersect(const double *prm, const Ray &r, double t[4])
     return n;
 }
 
+/*
+ * PRIMS: bit t set = a leaf of type t can occur.  A kernel instantiated for the types a scene really contains drops the
+ * code (and the registers) of the others -- the quartic solver of the torus alone is a third of the general body.
+ */
+#define FRT_PRIMS_ALL 0x3ff
+#define FRT_PRIMS_BOXES_AND_BALLS ((1 << FRT_CUBE) | (1 << FRT_SPHERE) | (1 << FRT_PLANE) | (1 << FRT_CSG) | (1 << FRT_GROUP))
+template <int PRIMS = FRT_PRIMS_ALL>
 __device__ __forceinline__ int
 prim_intersect(int type, const double *prm, const Ray &r, double t[4], double uv[2])
 {
+    if (PRIMS != FRT_PRIMS_ALL) { /* the host checked that the scene holds no other type */
+        if (type == FRT_SPHERE) {
+            if (!((PRIMS >> FRT_SPHERE) & 1)) return 0;
+        } else if (type == FRT_PLANE) {
+            if (!((PRIMS >> FRT_PLANE) & 1)) return 0;
+        } else if (type == FRT_CUBE) {
+            if (!((PRIMS >> FRT_CUBE) & 1)) return 0;
+        } else if (!((PRIMS >> FRT_CYLINDER) & 1) && !((PRIMS >> FRT_CONE) & 1) && !((PRIMS >> FRT_TOROID) & 1) &&
+                   !((PRIMS >> FRT_TRIANGLE) & 1) && !((PRIMS >> FRT_SMOOTH_TRIANGLE) & 1)) {
+            return 0;
+        }
+    }
     switch (type) {
     case FRT_SPHERE: { /* sphere_local_intersect, sphere.c:14-40 */
         double a = r.dx * r.dx + r.dy * r.dy + r.dz * r.dz;
@@ -595,7 +614,7 @@ csg_allowed(int op, bool lhit, bool inl, bool inr)
  * reproduced is the shadow early-out of a group nested INSIDE a CSG operand (group.c:105-123).
  * `cur_xf`/`lr` cache the ray in the current node space.  Sets *overflow when the interval stack is too small.
  */
-template <bool COUNT>
+template <bool COUNT, int PRIMS = FRT_PRIMS_ALL>
 __device__ __noinline__ int
 csg_eval_t(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow, unsigned long long *flops)
 {
@@ -635,7 +654,7 @@ csg_eval_t(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow,
         } else {
             NodeB b = load_node_b(S, i);
             double t[4], uv[2];
-            int k = prim_intersect(a.type, S.params + (b.param < 0 ? 0 : b.param), lr, t, uv);
+            int k = prim_intersect<PRIMS>(a.type, S.params + (b.param < 0 ? 0 : b.param), lr, t, uv);
             for (int j = 0; j < k; ++j) {
                 if (n == FRT_CSG_CAP) {
                     *overflow = 1;
@@ -690,10 +709,11 @@ csg_eval_t(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow,
     return n;
 }
 
+template <int PRIMS = FRT_PRIMS_ALL>
 __device__ __forceinline__ int
 csg_eval(const DScene &S, int root, const Ray &wr, CsgHit *buf, int *overflow)
 {
-    return csg_eval_t<false>(S, root, wr, buf, overflow, nullptr);
+    return csg_eval_t<false, PRIMS>(S, root, wr, buf, overflow, nullptr);
 }
 
 /* ---- traversal -------------------------------------------------------------------------------------- */

@@ -1447,7 +1447,7 @@ trace_shadow_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, double dis
  * the exact ray, and the leaf's parameter offset / transform / casts-shadow bit read from its mirror record.  The
  * minimum over the leaves does not depend on which empty subtrees are skipped.
  */
-template <bool CASTERS>
+template <bool CASTERS, int PRIMS = FRT_PRIMS_ALL>
 __device__ __forceinline__ Hit
 trace_closest_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, int *overflow)
 {
@@ -1500,7 +1500,7 @@ trace_closest_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, int *over
                     i = miss ? skip : i + 1;
                 } else {
                     if (!miss) {
-                        const int n = csg_eval(S, i, wr, buf, overflow);
+                        const int n = csg_eval<PRIMS>(S, i, wr, buf, overflow);
                         for (int k = 0; k < n; ++k) {
                             if (buf[k].t > 0 && buf[k].t < best.t &&
                                 (!CASTERS || (__float_as_int(__ldg(fnodes + 3 * buf[k].leaf).x) & FRT_FN_CASTS))) {
@@ -1527,7 +1527,7 @@ trace_closest_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, int *over
                 if (!CASTERS || (flags & FRT_FN_CASTS)) { /* hit(xs, true) skips objects that do not cast shadows */
                     double t[4], uv[2];
                     uv[0] = uv[1] = -1.0;
-                    const int k = prim_intersect(type, S.params + (param < 0 ? 0 : param), lr, t, uv);
+                    const int k = prim_intersect<PRIMS>(type, S.params + (param < 0 ? 0 : param), lr, t, uv);
                     for (int j = 0; j < k; ++j) {
                         if (t[j] > 0 && t[j] < best.t) {
                             best.t = t[j];
