@@ -794,7 +794,7 @@ quadrant_sample(int4 lq, int q, int k)
 }
 
 /* pending entry: hit in bits 0..27, quadrant in bits 28..29, bit 30 = decided by k_shadow_bulk, bit 31 = ... as lit */
-#define FRT_BOX_CHUNKS 512
+#define FRT_BOX_CHUNKS 128
 #define FRT_QS_MAX 256 /* samples per pending entry up to which k_shadow_f32 tabulates quadrant_sample in shared memory */
 #define FRT_PEND_HIT_MASK 0x0fffffffu
 #define FRT_PEND_BULK 0x40000000u
@@ -2955,6 +2955,9 @@ generate_light_cache(frt_scene *sc, const frt_scene_desc *d, const frt_light_gen
         const unsigned long long a = j.a;
         j.a = (a * a) & FRT_LCG_MASK;
         j.c = (a * j.c + j.c) & FRT_LCG_MASK;
+    }
+    for (int b = 0; b < 6; ++b) {
+        P.step2[b] = lcg_jump(1ull << b);
     }
     const size_t smem = (size_t)FRT_LGEN_WARPS * (per_set + 2ull * L.num_samples) * sizeof(double);
     if (smem > 48 * 1024) {

@@ -12,8 +12,8 @@
  *   - drand48 is X' = A X + C mod 2^48, result X' / 2^48 (glibc, drand48-iter.c); set s starts at J^s(X0) with J the
  *     jump over one set's draws -- the host uploads J^(2^b) as (multiplier, increment) pairs and a warp composes the
  *     ones s has bits for;
- *   - one warp per set: lane 0 steps the generator through the set's draws into shared memory (the order IS the
- *     stream), all lanes evaluate the canonical pass, the row / column swaps are applied one by one exactly as
+ *   - one warp per set: the lanes produce the set's draws into shared memory (lane l the draws l, l + 32, ... by jumping
+ *     ahead in the stream), all lanes evaluate the canonical pass, the row / column swaps are applied one by one exactly as
  *     written (lanes over the swapped row / column), then the points leave coalesced -- FP64 for the exact kernels,
  *     FP32 for the filter and the lighting sums (k_to_float is not needed for a generated light);
  *   - every operation is an explicitly rounded IEEE double operation (__dadd_rn ...: no contraction into FMAs), the
@@ -62,6 +62,7 @@ struct LightGenParams {
     int usteps, vsteps, cache_len;
     unsigned long long x0; /* generator state before the first draw of set 0 */
     LcgJump pow2[32];      /* pow2[b] = jump over 2^b sets */
+    LcgJump step2[6];      /* step2[b] = jump over 2^b draws: lane l starts l + 1 draws into its set and strides by 32 */
 };
 
 /*
@@ -81,16 +82,24 @@ k_light_gen(LightGenParams P, double *__restrict__ out64, float *__restrict__ ou
     if (set >= P.cache_len) {
         return; /* whole warps leave; nothing below synchronises across warps */
     }
-    if (lane == 0) {
+    {
+        /* draw k of the set is the state after k + 1 steps from the set's start: lane l jumps l + 1 steps ahead (composed from
+         * the power-of-two jumps) and then strides by 32 -- the draws are the stream's, only the order of evaluation differs */
         unsigned long long x = P.x0;
         for (int b = 0; b < 32; ++b) {
             if ((set >> b) & 1) {
                 x = (P.pow2[b].a * x + P.pow2[b].c) & FRT_LCG_MASK;
             }
         }
-        for (int k = 0; k < per_set; ++k) {
-            x = (FRT_LCG_A * x + FRT_LCG_C) & FRT_LCG_MASK;
+        const int ahead = lane + 1;
+        for (int b = 0; b < 6; ++b) {
+            if ((ahead >> b) & 1) {
+                x = (P.step2[b].a * x + P.step2[b].c) & FRT_LCG_MASK;
+            }
+        }
+        for (int k = lane; k < per_set; k += 32) {
             xi[k] = (double)x * (1.0 / 281474976710656.0); /* exact: x < 2^48, the factor is a power of two */
+            x = (P.step2[5].a * x + P.step2[5].c) & FRT_LCG_MASK;
         }
     }
     __syncwarp();
