@@ -278,8 +278,9 @@ def cuda_arm(args) -> dict:
 
     import fast_ray_tracer_b200 as frt
     from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_NO_PRUNE, FRT_FLAG_STAGE_TIMES
-    from fast_ray_tracer_b200.dist import gather_rows, owned_rows
+    from fast_ray_tracer_b200.dist import gather_rows, owned_rows, reduce_canvas
 
+    gather_mode = os.environ.get("FRT_BENCH_GATHER", "gather")
     sys.path.insert(0, str(REPO / "oracle"))
     from compare import parity_report  # the checker of the parity block below; nothing of oracle/ is on the timed path
 
@@ -311,7 +312,9 @@ def cuda_arm(args) -> dict:
         """One frame of this rank's rows on the device, then (N > 1) the NCCL gather of the rows to rank 0."""
         _, st = sc.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=seed)
         frame = sc.canvas_tensor()
-        if world > 1:
+        if world > 1 and gather_mode == "reduce":
+            canvas = reduce_canvas(frame)
+        elif world > 1:
             canvas = gather_rows(frame.index_select(0, rows_idx), vsize, rank, world, rpb)
         else:
             canvas = frame
@@ -589,6 +592,8 @@ def configs_leg(args, frt, rank, world, local, dev, rpb) -> dict:
             d.config.gi_photon_count = photons
         with frt.Scene(d, device=local) as sc:
             if d.config.include_global and d.config.gi_photon_count > 0:
+                # one untimed pass first (like the warm-up frames: the all-gather's buffers and NCCL channels for this size)
+                trace_photons_distributed(sc, rank, world, bool(d.config.gi_include_caustics), True, seed=6)
                 torch.cuda.synchronize()
                 if world > 1:
                     dist.barrier()

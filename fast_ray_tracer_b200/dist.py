@@ -69,6 +69,15 @@ def gather_rows(local_rows: torch.Tensor, vsize: int, rank: int, world: int, row
     return allbuf.index_select(0, plan["src"])
 
 
+def reduce_canvas(frame: torch.Tensor, group=None) -> Optional[torch.Tensor]:
+    """The other way to get the frame to rank 0: every rank's device canvas is zero outside the rows it rendered (the
+    frame loop clears it), so the sum of the ranks' canvases IS the frame -- one in-place NCCL reduce of the full canvas
+    to rank 0 (x + 0 is exact), no packing kernel, no reorder.  Moves world x the bytes of gather_rows but saves two
+    kernels and two passes over the canvas; which one wins is measured in bench.py (FRT_BENCH_GATHER)."""
+    dist.reduce(frame, dst=0, op=dist.ReduceOp.SUM, group=group)
+    return frame if dist.get_rank(group) == 0 else None
+
+
 def render_distributed(scene, rank: int, world: int, rows_per_block: int = 4, group=None, **render_kw):
     """Render this rank's rows on its GPU and gather the frame on rank 0 (device tensor).  Returns (canvas|None, stats)."""
     vsize = scene.desc.camera.vsize
