@@ -258,17 +258,36 @@ class SharedCanvas:
         rc = frt.load_library().frt_host_register(self.arr.ctypes.data, nbytes)
         if rc != 0:
             raise SystemExit("bench.py: frt_host_register of the shared canvas failed")
+        # a host barrier next to the canvas: one 64-byte slot per rank holding the last step it finished.  The ranks are
+        # processes of one node and the frame is complete when every slot has reached the step -- no device collective
+        # (an NCCL barrier is an all-reduce plus a stream synchronisation: ~0.1 ms of a 2.7 ms step at N = 8)
+        self.flags_path = Path("/dev/shm") / (name + "_flags")
+        if rank == 0:
+            with open(self.flags_path, "wb") as f:
+                f.truncate(64 * 64)
         barrier()
+        self.flags = np.memmap(self.flags_path, dtype=np.int64, mode="r+", shape=(64, 8))
+        if rank == 0:
+            self.flags[...] = -1
+        barrier()
+
+    def arrive_and_wait(self, step: int, world: int):
+        """Every rank calls it after its rows of `step` have landed in the canvas; returns when all ranks have."""
+        self.flags[self.rank, 0] = step
+        while int(self.flags[:world, 0].min()) < step:
+            pass
 
     def close(self, barrier):
         self.frt.load_library().frt_host_unregister(self.arr.ctypes.data)
         barrier()
         del self.arr
+        del self.flags
         if self.rank == 0:
-            try:
-                self.path.unlink()
-            except OSError:
-                pass
+            for p in (self.path, self.flags_path):
+                try:
+                    p.unlink()
+                except OSError:
+                    pass
 
 
 def cuda_arm(args) -> dict:
@@ -424,7 +443,7 @@ def cuda_arm(args) -> dict:
         tk = time.perf_counter()
         e2e_step(k)
         if world > 1:
-            dist.barrier()  # the frame is complete on the host when every rank's rows have landed
+            shared.arrive_and_wait(k, world)  # the frame is complete on the host when every rank's rows have landed
         if rank == 0:
             print(f"[bench] e2e step {k}: {1e3 * (time.perf_counter() - tk):.1f} ms", file=sys.stderr)
     barrier()
@@ -625,6 +644,38 @@ def configs_leg(args, frt, rank, world, local, dev, rpb) -> dict:
     return rows
 
 
+def dropin_leg(args) -> dict:
+    """Rank 0, N=1 only: the drop-in PROGRAM itself -- the reference's generated main() + the reference's host-side scene
+    construction + frt_shim.c + libfrt_b200.so (oracle/_ref/cornell_shipped_b200, built like INTEGRATION.md says) -- run as
+    a process on one GPU: wall time inside its render_multi() (flatten, scene creation with the light cache rebuilt and
+    compared on the device, frame, canvas into the Canvas the program gets back) and of the whole program.  A one-shot
+    process pays CUDA's start-up once (the shim overlaps it with the host's scene construction): both runs are reported,
+    the first (cold driver caches) and the second."""
+    binary = REPO / "oracle" / "_ref" / "cornell_shipped_b200"
+    if not binary.exists():
+        return {"unavailable": f"{binary.name} not built"}
+    runs = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        r = subprocess.run([str(binary)], env=dict(os.environ, FRT_SKIP_PPM="1", FRT_DEVICES="1"), stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, text=True, cwd="/tmp")
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"unavailable": f"{binary.name} exited with {r.returncode}"}
+        info = {}
+        for line in r.stdout.splitlines():
+            if line.startswith("FRT_B200_"):
+                k, _, v = line.partition(" ")
+                info[k] = v
+        runs.append({"program_wall_s": wall, "render_multi_ms": float(info["FRT_B200_RENDER_MULTI_MS"].split()[0]),
+                     "flatten_ms": float(info["FRT_B200_FLATTEN_MS"].split()[0]), "create_ms": float(info["FRT_B200_CREATE_MS"].split()[0]),
+                     "frame_ms": float(info["FRT_B200_FRAME_MS"].split()[0]), "light_cache": info.get("FRT_B200_LIGHT_GEN", "")})
+    return {"program": "oracle/_ref/cornell_shipped_b200 (generated main.c + reference host code + frt_shim.c + libfrt_b200.so), FRT_DEVICES=1",
+            "runs": runs,
+            "note": "render_multi_ms includes waiting for CUDA's start-up (driver + context, started on a thread when the program "
+                    "starts) and the first-use costs of a fresh process (module load, 9 GB of frame buffers); frame_ms is the device time"}
+
+
 def cpu_baseline_leg(args) -> dict:
     """Rank 0, N=1 only: the unmodified reference on the box's host cores, ~10-30 s of work."""
     binary = REF_BIN[args.variant]
@@ -674,6 +725,8 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
+        if world == 1 and not args.no_configs:
+            line["dropin"] = dropin_leg(args)
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         import torch.distributed as dist

@@ -4227,9 +4227,17 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
         if (world == 1) {
             CK(cudaMemcpyAsync(canvas_rgba, sc->canvas, row_bytes * sc->C.vsize, cudaMemcpyDeviceToHost, sc->stream));
         } else {
-            for (int y0 = cfg->rank * rpb; y0 < sc->C.vsize; y0 += world * rpb) {
-                int rows = std::min(rpb, sc->C.vsize - y0);
-                CK(cudaMemcpyAsync((char *)canvas_rgba + row_bytes * y0, (char *)sc->canvas + row_bytes * y0, row_bytes * rows,
+            /* the owned row blocks are equally spaced runs of the canvas: one strided copy for the whole blocks (a block of
+             * rpb rows every world * rpb rows), one plain copy for a last, shorter block */
+            const int first = cfg->rank * rpb;
+            const int full_blocks = first < sc->C.vsize ? (sc->C.vsize - first) / (world * rpb) + (((sc->C.vsize - first) % (world * rpb)) >= rpb ? 1 : 0) : 0;
+            if (full_blocks > 0) {
+                CK(cudaMemcpy2DAsync((char *)canvas_rgba + row_bytes * first, row_bytes * world * rpb, (char *)sc->canvas + row_bytes * first,
+                                     row_bytes * world * rpb, row_bytes * rpb, (size_t)full_blocks, cudaMemcpyDeviceToHost, sc->stream));
+            }
+            const int y0 = first + full_blocks * world * rpb;
+            if (y0 < sc->C.vsize) {
+                CK(cudaMemcpyAsync((char *)canvas_rgba + row_bytes * y0, (char *)sc->canvas + row_bytes * y0, row_bytes * (sc->C.vsize - y0),
                                    cudaMemcpyDeviceToHost, sc->stream));
             }
         }

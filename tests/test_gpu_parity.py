@@ -55,7 +55,7 @@ def test_row_partition_reproduces_the_full_frame(frt):
     desc = frt.SceneDesc.load(GOLDEN / "cornell_exact_96_1spp.frt")
     with frt.Scene(desc) as sc:
         full, _ = sc.render()
-        for world, rpb in ((2, 4), (3, 8), (8, 4)):
+        for world, rpb in ((2, 4), (3, 8), (8, 4), (2, 5), (7, 4), (5, 7)):  # incl. a last, shorter block and uneven block counts
             acc = np.zeros_like(full)
             for rank in range(world):
                 part, st = sc.render(rank=rank, world=world, rows_per_block=rpb)
