@@ -145,7 +145,7 @@ EXPORTS = [
     "frt_ppm16_size", "frt_canvas_encode_ppm16", "frt_encode_ppm16",
     "frt_scene_create_gen", "frt_scene_gen_status", "frt_drand48_advance", "frt_light_points_checksum", "frt_light_points_checksum_host",
     "frt_photons_estimate", "frt_multi_create", "frt_multi_destroy", "frt_multi_device_count", "frt_multi_scene",
-    "frt_multi_render", "frt_multi_photons", "frt_texture_ingest",
+    "frt_multi_render", "frt_multi_photons", "frt_texture_ingest", "frt_tree_with_runs",
 ]
 
 
@@ -199,6 +199,7 @@ def load_library():
     lib.frt_canvas_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.frt_abi_sizeof.argtypes = [C.c_char_p]
     lib.frt_owned_rows.argtypes = [C.POINTER(frt_scene_desc), C.POINTER(frt_render_cfg), C.POINTER(C.c_int32), C.c_int]
+    lib.frt_tree_with_runs.argtypes = [C.POINTER(frt_scene_desc), C.c_void_p, C.c_int, C.c_void_p]
     lib.frt_measure_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.frt_scene_save.argtypes = [C.POINTER(frt_scene_desc), C.c_char_p]
     lib.frt_scene_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(frt_scene_desc))]
@@ -285,6 +286,18 @@ class SceneDesc:
     @property
     def c(self) -> frt_scene_desc:
         return self._ptr.contents
+
+    def tree_with_runs(self):
+        """(nodes, roots) of the tree frt_scene_create uploads: bounding groups inserted over the long runs of triangle
+        children (frt_tree_with_runs); nodes is a ctypes array of frt_node."""
+        lib = load_library()
+        n = lib.frt_tree_with_runs(self._ptr, None, 0, None)
+        if n < 0:
+            raise FrtError(f"frt_tree_with_runs: {lib.frt_last_error().decode(errors='replace')}")
+        nodes = (frt_node * n)()
+        roots = (C.c_int32 * self.c.n_roots)()
+        lib.frt_tree_with_runs(self._ptr, C.cast(nodes, C.c_void_p), n, C.cast(roots, C.c_void_p))
+        return nodes, list(roots)
 
     @property
     def camera(self) -> frt_camera:

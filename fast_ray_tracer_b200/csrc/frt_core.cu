@@ -35,6 +35,7 @@
 #include "frt_patterns.cuh"
 #include "frt_shadow_f32.cuh"
 #include "frt_lightgen.cuh"
+#include "frt_leafruns.h"
 
 /* ------------------------------------------------------------------------------------------------ errors */
 
@@ -1480,7 +1481,7 @@ k_shadow_exact(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
 #ifndef FRT_MESH_MINB
 #define FRT_MESH_MINB 6
 #endif
-template <bool COUNT>
+template <bool COUNT, bool HAS_CSG>
 __global__ void __launch_bounds__(128, FRT_MESH_MINB)
 k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp_base, size_t tmp_stride,
               Counters *cnt, int level, int first_light, int n_lights, int inner_budget, int refill_min)
@@ -1515,8 +1516,8 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
     double dist = 0.0;
     float omax = 0.f, eo_o = 0.f, ed_w = 0.f;
     int cur_xf_f = 0, cur_xf_d = 0, i = 0, sp = 0, n = 0;
-    CsgHit buf[FRT_CSG_CAP];
-    Frame st[FRT_CSG_DEPTH];
+    CsgHit buf[HAS_CSG ? FRT_CSG_CAP : 1]; /* a tree without CSG nodes (OBJ meshes) needs neither list nor stack */
+    Frame st[HAS_CSG ? FRT_CSG_DEPTH : 1];
     int overflow = 0;
     unsigned long long n_shadow = 0, n_nodes = 0, n_flops = 0, n_mismatch = 0;
 
@@ -1575,7 +1576,7 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         bool done = false, result = false;
         /* close every CSG whose left / right operand just ended (csg.c:104-118, :43-71) */
         auto close_frames = [&]() {
-            while (sp > 0 && !done) {
+            while (HAS_CSG && sp > 0 && !done) {
                 Frame &f = st[sp - 1];
                 if (f.mid < 0 && i >= f.right) {
                     f.mid = n;
@@ -1639,7 +1640,8 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             lo = __ldg(fnodes + 3 * i + 1);
             const int flags = __float_as_int(q0.x), skip = __float_as_int(q0.y);
             const int type = flags & FRT_FN_TYPE_MASK;
-            if (type < FRT_CSG) {
+            const bool leaf = type < FRT_CSG;
+            if (leaf && !(flags & FRT_FN_LEAFBOX)) {
                 at_leaf = true;
                 break;
             }
@@ -1648,7 +1650,7 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
                 ++n_nodes;
                 n_flops += FRT_COST_BBOX;
             }
-            bool miss = false;
+            bool miss = false; /* a triangle leaf is culled by the bounds of its vertices like a group by its box */
             if (!(flags & FRT_FN_NOCULL)) {
                 const int xf = __float_as_int(q0.z);
                 float tn_lo, tn_hi, tf_lo, tf_hi;
@@ -1661,12 +1663,15 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
                     }
                     box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
                 }
-                miss = tn_lo > tf_hi || (sp == 0 && tf_hi < 0.0f);
+                miss = tn_lo > tf_hi || ((!HAS_CSG || sp == 0) && tf_hi < 0.0f);
             }
             if (miss) {
                 i = skip;
+            } else if (leaf) {
+                at_leaf = true;
+                break;
             } else {
-                if (type == FRT_CSG) {
+                if (HAS_CSG && type == FRT_CSG) {
                     if (sp == FRT_CSG_DEPTH) {
                         overflow = 1;
                         done = true;
@@ -1676,7 +1681,7 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
                 }
                 i = i + 1;
             }
-            if (sp > 0) {
+            if (HAS_CSG && sp > 0) {
                 close_frames();
             }
         }
@@ -1700,7 +1705,7 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             }
             double t[4], uv[2];
             const int k = prim_intersect_inv(type, S.params + (param < 0 ? 0 : param), lr, inv, t, uv);
-            if (sp == 0) {
+            if (!HAS_CSG || sp == 0) {
                 bool stop = false;
                 double tmin = CUDART_INF;
                 for (int j = 0; j < k; ++j) {
@@ -1726,7 +1731,7 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
                 }
             }
             i = i + 1;
-            if (sp > 0) {
+            if (HAS_CSG && sp > 0) {
                 close_frames();
             }
         }
@@ -1980,6 +1985,7 @@ struct frt_scene {
     LightTmp *ltmp_multi = nullptr; /* mesh mode with several lights: one LightTmp array per light of a shared launch */
     size_t ltmp_multi_cap = 0;
     bool boxes_and_balls = false; /* no leaf type beyond cube / sphere / plane (k_extend instantiation) */
+    bool has_csg = false;         /* the tree holds a CSG node (k_shadow_mesh instantiation) */
     bool has_maps = false;       /* some material carries a pattern / texture / bump map (k_shade instantiation) */
     bool has_refraction = false; /* some material refracts, or is a dissolving mirror: n1 / n2 containers are needed */
     bool mesh_mode = false; /* most leaves have no FP32 fast form (OBJ meshes): shadow rays go straight to k_shadow_mesh */
@@ -2563,6 +2569,7 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
     for (int i = 0; i < d->n_nodes; ++i) {
         const frt_node &n = d->nodes[i];
         const bool inner = n.type >= FRT_CSG;
+        const bool tri = n.type == FRT_TRIANGLE || n.type == FRT_SMOOTH_TRIANGLE;
         int flags = n.type;
         double lo[3], hi[3];
         if (inner) {
@@ -2578,9 +2585,19 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
             }
             if (d->materials[n.material].casts_shadow) flags |= FRT_FN_CASTS;
             if (n.type == FRT_CUBE || n.type == FRT_SPHERE || n.type == FRT_PLANE) flags |= FRT_FN_FAST;
+            if (tri) {
+                /* a triangle's record carries the (padded) bounds of its vertices: the walks cull it like a group before the
+                 * FP64 test -- the reference has no such test, and none is needed for a ray that misses the box */
+                const frt_leafruns::Box b = frt_leafruns::triangle_box(d->prim_params + n.param);
+                for (int k = 0; k < 3; ++k) {
+                    lo[k] = b.lo[k];
+                    hi[k] = b.hi[k];
+                }
+                flags |= FRT_FN_LEAFBOX;
+            }
         }
         bool world = n.xform == 0;
-        if (!world && aligned[n.xform] && (inner || n.type == FRT_CUBE)) {
+        if (!world && aligned[n.xform] && (inner || n.type == FRT_CUBE || tri)) {
             const double *m = d->xforms[n.xform].inv;
             double wlo[3], whi[3];
             for (int k = 0; k < 3; ++k) {
@@ -2600,8 +2617,8 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
             flags |= FRT_FN_NOCULL; /* shadow rays start inside the world group's box: the test never culls */
         }
         if (world) {
-            flags |= FRT_FN_WORLD;
-            if (inner || n.type == FRT_CUBE) {
+            if (!tri) flags |= FRT_FN_WORLD;
+            if (inner || n.type == FRT_CUBE || tri) {
                 for (int k = 0; k < 3; ++k) {
                     if (std::isfinite(lo[k])) bmax = std::max(bmax, fabs(lo[k]));
                     if (std::isfinite(hi[k])) bmax = std::max(bmax, fabs(hi[k]));
@@ -2703,6 +2720,9 @@ build_f32_mirror(frt_scene *sc, const frt_scene_desc *d)
         if (inner) {
             fn[3 * i + 1] = make_float4(down(lo[0]), down(lo[1]), down(lo[2]), 0.f);
             fn[3 * i + 2] = make_float4(up(hi[0]), up(hi[1]), up(hi[2]), 0.f);
+        } else if (tri) {
+            fn[3 * i + 1] = make_float4(down(lo[0]), down(lo[1]), down(lo[2]), __int_as_float_host(n.xform));
+            fn[3 * i + 2] = make_float4(up(hi[0]), up(hi[1]), up(hi[2]), __int_as_float_host(n.material));
         } else {
             fn[3 * i + 1] = make_float4((float)lo[0], (float)lo[1], (float)lo[2], __int_as_float_host(n.xform));
             fn[3 * i + 2] = make_float4((float)hi[0], (float)hi[1], (float)hi[2], __int_as_float_host(n.material));
@@ -3091,10 +3111,30 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
     if (rc != FRT_OK) {
         return rc;
     }
+    const bool timing = getenv("FRT_DEBUG_TIMING") != nullptr;
+    /* bounding groups over the long triangle runs the reference's group_divide leaves behind (frt_leafruns.h): from here
+     * on `d` is the tree with those groups in it; node indices never leave the library */
+    frt_scene_desc with_runs;
+    std::vector<frt_node> run_nodes;
+    std::vector<int32_t> run_roots;
+    {
+        const char *env = getenv("FRT_LEAF_RUNS");
+        long inserted = 0;
+        if ((env == nullptr || atoi(env) != 0) && frt_leafruns::augment(d, run_nodes, run_roots, &inserted)) {
+            with_runs = *d;
+            with_runs.nodes = run_nodes.data();
+            with_runs.n_nodes = (int32_t)run_nodes.size();
+            with_runs.roots = run_roots.data();
+            if (timing) {
+                fprintf(stderr, "[frt] scene_create: %ld groups inserted over triangle runs (%d -> %d nodes)\n", inserted, d->n_nodes,
+                        with_runs.n_nodes);
+            }
+            d = &with_runs;
+        }
+    }
 
     frt_scene *sc = new frt_scene();
     sc->device = device;
-    const bool timing = getenv("FRT_DEBUG_TIMING") != nullptr;
     auto t_start = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
         if (timing) {
@@ -3298,6 +3338,9 @@ scene_create(const frt_scene_desc *d, int device, const frt_light_gen *gens, int
         }
         sc->mesh_mode = slow * 2 > leaves && d->n_nodes > 64;
         sc->boxes_and_balls = slow == 0;
+        for (int i = 0; i < d->n_nodes; ++i) {
+            sc->has_csg = sc->has_csg || d->nodes[i].type == FRT_CSG;
+        }
         const char *env = getenv("FRT_MESH_MODE");
         if (env != nullptr && *env) {
             sc->mesh_mode = atoi(env) != 0;
@@ -3364,6 +3407,28 @@ frt_owned_rows(const frt_scene_desc *d, const frt_render_cfg *cfg, int32_t *rows
         }
     }
     return n;
+}
+
+/* the tree a scene is uploaded with (frt_leafruns.h): host only, no device needed */
+extern "C" int
+frt_tree_with_runs(const frt_scene_desc *d, frt_node *nodes, int cap, int32_t *roots)
+{
+    if (validate_desc(d) != FRT_OK) {
+        return -1;
+    }
+    std::vector<frt_node> out;
+    std::vector<int32_t> r;
+    if (!frt_leafruns::augment(d, out, r, nullptr)) {
+        out.assign(d->nodes, d->nodes + d->n_nodes);
+        r.assign(d->roots, d->roots + d->n_roots);
+    }
+    if (nodes != nullptr && (size_t)cap >= out.size()) {
+        memcpy(nodes, out.data(), out.size() * sizeof(frt_node));
+        if (roots != nullptr) {
+            memcpy(roots, r.data(), r.size() * sizeof(int32_t));
+        }
+    }
+    return (int)out.size();
 }
 
 template <typename T>
@@ -3443,6 +3508,18 @@ wait_for_upload(frt_scene *sc, cudaStream_t s)
         sc->upload_pending = false;
     }
     return FRT_OK;
+}
+
+template <bool COUNT>
+static void
+launch_shadow_mesh(frt_scene *sc, int blocks, cudaStream_t s, const FrameParams &F, LightTmp *tmp, size_t tmp_stride, int level, int first_light,
+                   int n_lights, int inner, int refill)
+{
+    if (sc->has_csg) {
+        k_shadow_mesh<COUNT, true><<<blocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, tmp, tmp_stride, sc->cnt, level, first_light, n_lights, inner, refill);
+    } else {
+        k_shadow_mesh<COUNT, false><<<blocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, tmp, tmp_stride, sc->cnt, level, first_light, n_lights, inner, refill);
+    }
 }
 
 static void
@@ -3872,9 +3949,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                     CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
                     tk = tick(FRT_ST_SHADOW_RAY);
                     if (count) {
-                        k_shadow_mesh<true><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp_multi, sc->capacity, sc->cnt, level, l0, nl, m_inner, m_refill);
+                        launch_shadow_mesh<true>(sc, mblocks, s, F, sc->ltmp_multi, sc->capacity, level, l0, nl, m_inner, m_refill);
                     } else {
-                        k_shadow_mesh<false><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp_multi, sc->capacity, sc->cnt, level, l0, nl, m_inner, m_refill);
+                        launch_shadow_mesh<false>(sc, mblocks, s, F, sc->ltmp_multi, sc->capacity, level, l0, nl, m_inner, m_refill);
                     }
                     tock(tk);
                     tk = tick(FRT_ST_LIGHT_FINAL);
@@ -3910,9 +3987,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
                         tk = tick(FRT_ST_SHADOW_RAY);
                         if (count) {
-                            k_shadow_mesh<true><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, 0, sc->cnt, level, li, 1, m_inner, m_refill);
+                            launch_shadow_mesh<true>(sc, mblocks, s, F, sc->ltmp, 0, level, li, 1, m_inner, m_refill);
                         } else {
-                            k_shadow_mesh<false><<<mblocks, 128, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, 0, sc->cnt, level, li, 1, m_inner, m_refill);
+                            launch_shadow_mesh<false>(sc, mblocks, s, F, sc->ltmp, 0, level, li, 1, m_inner, m_refill);
                         }
                         tock(tk);
                         launches += 1;

@@ -55,7 +55,8 @@ enum {
     FRT_FN_FAST = 64,      /* leaf: the filter has a fast form for this type (cube, sphere, plane);
                               CSG: it has a postfix program that fits the three-register span stack */
     FRT_FN_NOCULL = 128,   /* group: descend without testing its bounds (culling is optional; the root's box is always hit) */
-    FRT_FN_OP_SHIFT = 8    /* CSG: enum frt_csg_op in bits 8..9 */
+    FRT_FN_OP_SHIFT = 8,   /* CSG: enum frt_csg_op in bits 8..9 */
+    FRT_FN_LEAFBOX = 1024  /* triangle leaf: lo / hi are the bounds of its vertices (frame q0.z, like a group's): cull before the FP64 test */
 };
 
 struct DSceneF {
@@ -1271,6 +1272,30 @@ trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const Shaf
 }
 
 /*
+ * A triangle leaf's mirror record holds the bounds of its vertices (FRT_FN_LEAFBOX): true when the ray surely misses
+ * them, surely has them behind its origin (`behind`: no crossing at t <= 0 is wanted), or surely enters them beyond
+ * `t_best`.  The reference tests no box in front of a triangle (triangle.c:11-45); a ray that misses the box of the
+ * vertices by more than the box's padding gets no crossing from its Moeller-Trumbore test either.
+ */
+__device__ __forceinline__ bool
+leaf_box_missed(const DSceneF &SF, const float4 q0, const float4 lo, const float4 hi, const FrameF &w, FrameF &lf, int &cur_xf_f,
+                float omax, float eo, float ed_w, bool behind, double t_best)
+{
+    const int xf = __float_as_int(q0.z);
+    float tn_lo, tn_hi, tf_lo, tf_hi;
+    if (xf == 0) {
+        box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+    } else {
+        if (xf != cur_xf_f) {
+            cur_xf_f = xf;
+            frame_local(lf, SF, xf, w, omax, eo, ed_w);
+        }
+        box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
+    }
+    return tn_lo > tf_hi || (behind && tf_hi < 0.0f) || (double)tn_lo > t_best;
+}
+
+/*
  * The FP64 traversal (trace_shadow, frt_device.cuh) with its CULLS taken from the FP32 mirror: the walk, the group /
  * CSG box tests and the behind-the-origin test use the conservative FP32 slabs of this file (one 48-byte node record,
  * three loads issued together, instead of a header load followed by a dependent bounding-box load), every LEAF is still
@@ -1337,6 +1362,8 @@ trace_shadow_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, double dis
                 }
                 i = i + 1;
             }
+        } else if ((flags & FRT_FN_LEAFBOX) && leaf_box_missed(SF, q0, lo, hi, w, lf, cur_xf_f, omax, eo_w, ed_w, sp == 0, CUDART_INF)) {
+            i = i + 1; /* the ray misses the bounds of the triangle's vertices */
         } else {
             const NodeA a = load_node_a(S, i);
             const NodeB b = load_node_b(S, i);
@@ -1512,6 +1539,9 @@ trace_closest_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, int *over
                     }
                     i = skip;
                 }
+            } else if ((flags & FRT_FN_LEAFBOX) &&
+                       leaf_box_missed(SF, q0, lo, __ldg(fnodes + 3 * i + 2), w, lf, cur_xf_f, omax, eo_o, ed_w, true, best.t)) {
+                i = i + 1; /* the ray misses the bounds of the triangle's vertices, or meets them beyond the best hit */
             } else {
                 const int xform = __float_as_int(lo.w), param = __float_as_int(q0.w);
                 if (xform != cur_xf_d) {

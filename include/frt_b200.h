@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define FRT_ABI_VERSION 6 /* struct layouts (scene blobs carry it); entry points added since: see FRT_API_LEVEL */
-#define FRT_API_LEVEL 2   /* 2: frt_scene_create_gen, frt_render_multi, frt_photons_estimate, frt_light_cache_checksum */
+#define FRT_API_LEVEL 3   /* 2: frt_scene_create_gen, frt_render_multi, frt_photons_estimate, frt_light_cache_checksum; 3: frt_tree_with_runs */
 
 enum frt_status {
     FRT_OK = 0,
@@ -354,6 +354,13 @@ int frt_canvas_download(frt_scene *scene, double *canvas_rgba);
 int frt_canvas_device_ptr(frt_scene *scene, void **device_ptr);
 /* rows owned by (rank, world): writes up to cap row indices, returns the count */
 int frt_owned_rows(const frt_scene_desc *desc, const frt_render_cfg *cfg, int32_t *rows, int cap);
+/*
+ * The tree frt_scene_create uploads: the reference's divided tree (group_divide, group.c:300-370, leaves its straddling
+ * triangles as direct children without a box of their own) with bounding groups inserted over runs of consecutive
+ * triangle children, leaf order untouched.  Returns the node count (-1: malformed description); fills `nodes` / `roots`
+ * (n_roots entries) when cap is large enough.  Host only.
+ */
+int frt_tree_with_runs(const frt_scene_desc *desc, frt_node *nodes, int cap, int32_t *roots);
 
 /*
  * Replaces trace_photons() (photon_tracer.c:203): emits this rank's shard of photons on the device.
