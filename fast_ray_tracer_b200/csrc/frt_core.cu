@@ -2020,6 +2020,10 @@ struct frt_scene {
     GQuery *gq = nullptr, *gq2 = nullptr;     /* radiance-estimate requests of a batch, as queued / sorted by grid cell */
     unsigned int *gq_counts = nullptr, *gq_starts = nullptr;
     size_t gq_cells = 0;
+    size_t gq2_cap = 0;                    /* requests gq2 holds */
+    unsigned int *gq_part = nullptr;       /* per-block sums of the cell scan, and their exclusive scan */
+    size_t gq_part_cap = 0;
+    unsigned int *gq_work = nullptr;       /* k_knn_cell: {next chunk of requests, requests left to k_knn} */
     unsigned int gq_cap = 0;
     unsigned int *gq_n = nullptr;
     double *acc_amb = nullptr, *acc_fg = nullptr;
@@ -3740,6 +3744,16 @@ frt_encode_ppm16(const double *canvas_rgba, int width, int height, int use_scali
 }
 
 static int
+frt_env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v != nullptr && *v) ? atoi(v) : dflt;
+}
+
+static int launch_knn(frt_scene *sc, cudaStream_t s, const GIParams &G, GQuery *q, unsigned int *q_n, unsigned int q_cap, double *acc_amb,
+                      double *acc_fg, int *found, int mode, int *launches);
+
+static int
 render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned int chunk_samples, unsigned int cap_factor)
 {
     const frt_config &g = sc->cfg;
@@ -3876,8 +3890,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     const int eblocks = env_int("FRT_ENTRY_BLOCKS", sm_blocks * 64);
     const int entry_kernel = env_int("FRT_ENTRY_KERNEL", 0); /* 1: one warp per pending entry (k_shadow_entry, A/B measurements: 6.5 vs 5.9 ms) */
     const bool debug_nodes = getenv("FRT_DEBUG_NODES") != nullptr;
-    const int sort_queries = env_int("FRT_KNN_SORT", 0); /* measured: 840 -> 900 ms on the 400 x 400 C5 frame (the requests are not L2-latency bound) */
-    const int knn_list = env_int("FRT_KNN_LIST", 0);     /* 1: the candidate-list kernel k_knn_list (A/B measurements) */
+    const int knn_mode = env_int("FRT_KNN_MODE", 1); /* 1: requests sorted by cell, a lane per request (k_knn_cell); 0: a warp per request (k_knn); 2: k_knn_list */
 
     for (unsigned long long first = 0; first < total; first += chunk) {
         unsigned int n = (unsigned int)std::min<unsigned long long>(chunk, total - first);
@@ -4085,39 +4098,15 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                     }
                     tock(tk);
                     tk = tick(FRT_ST_KNN);
-                    const GQuery *gq_in = sc->gq;
-                    if (sort_queries) { /* counting sort of the batch by photon-grid cell (frt_gi.cuh) */
-                        const PMView &M = sc->pm[1].view.count ? sc->pm[1].view : sc->pm[0].view;
-                        const size_t n_cells = (size_t)M.nx * M.ny * M.nz;
-                        if (M.count && n_cells > 0) {
-                            if (sc->gq_cells < n_cells + 1) {
-                                cudaFree(sc->gq_counts);
-                                cudaFree(sc->gq_starts);
-                                sc->gq_counts = sc->gq_starts = nullptr;
-                                CK(cudaMalloc(&sc->gq_counts, sizeof(unsigned int) * (n_cells + 1)));
-                                CK(cudaMalloc(&sc->gq_starts, sizeof(unsigned int) * (n_cells + 1)));
-                                sc->gq_cells = n_cells + 1;
-                            }
-                            if (sc->gq2 == nullptr) {
-                                CK(cudaMalloc(&sc->gq2, sizeof(GQuery) * (size_t)sc->gq_cap));
-                            }
-                            CK(cudaMemsetAsync(sc->gq_counts, 0, sizeof(unsigned int) * n_cells, s));
-                            k_gq_count<<<sm_blocks * 8, 256, 0, s>>>(M, sc->gq, sc->gq_n, sc->gq_cap, sc->gq_counts);
-                            k_pm_scan<<<1, 1024, 0, s>>>(sc->gq_counts, sc->gq_starts, (unsigned int)n_cells);
-                            k_gq_scatter<<<sm_blocks * 8, 256, 0, s>>>(M, sc->gq, sc->gq_n, sc->gq_cap, sc->gq_starts, sc->gq2);
-                            launches += 3;
-                            gq_in = sc->gq2;
+                    {
+                        int knn_launches = 0;
+                        const int rc_knn = launch_knn(sc, s, G, sc->gq, sc->gq_n, sc->gq_cap, sc->acc_amb, sc->acc_fg, nullptr, knn_mode, &knn_launches);
+                        if (rc_knn != FRT_OK) {
+                            return rc_knn;
                         }
-                    }
-                    if (knn_list) {
-                        k_knn_list<<<sm_blocks * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, gq_in, sc->gq_n, sc->gq_cap,
-                                                                               sc->acc_amb, sc->acc_fg, nullptr);
-                    } else {
-                        k_knn<<<sm_blocks * 16, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, gq_in, sc->gq_n, sc->gq_cap,
-                                                                           sc->acc_amb, sc->acc_fg, nullptr);
+                        launches += knn_launches;
                     }
                     tock(tk);
-                    ++launches;
                 }
                 tk = tick(FRT_ST_GI_RESOLVE);
                 k_gi_resolve<<<sm_blocks * 8, 256, 0, s>>>(F, G, sc->recs, sc->acc_amb, sc->acc_fg, sc->canvas, sc->cnt, level);
@@ -4381,9 +4370,11 @@ pm_free(frt_scene *sc)
     cudaFree(sc->gq2);
     cudaFree(sc->gq_counts);
     cudaFree(sc->gq_starts);
+    cudaFree(sc->gq_part);
+    cudaFree(sc->gq_work);
     sc->gq2 = nullptr;
-    sc->gq_counts = sc->gq_starts = nullptr;
-    sc->gq_cells = 0;
+    sc->gq_counts = sc->gq_starts = sc->gq_part = sc->gq_work = nullptr;
+    sc->gq_cells = sc->gq2_cap = sc->gq_part_cap = 0;
     cudaFree(sc->gq_n);
     cudaFree(sc->acc_amb);
     cudaFree(sc->acc_fg);
@@ -4393,6 +4384,98 @@ pm_free(frt_scene *sc)
     sc->acc_amb = sc->acc_fg = nullptr;
     sc->gq_cap = sc->acc_cap = 0;
     sc->pm_ready = false;
+}
+
+/*
+ * The radiance estimates of one batch of requests (q[0 .. *q_n)): sorted by the photon grid's cell and handed to
+ * k_knn_cell, a lane per request; what that kernel passes on is left in q and goes through k_knn, a warp per request.
+ * q is overwritten.
+ */
+static int
+launch_knn(frt_scene *sc, cudaStream_t s, const GIParams &G, GQuery *q, unsigned int *q_n, unsigned int q_cap, double *acc_amb, double *acc_fg,
+           int *found, int mode, int *launches)
+{
+    const int sm_blocks = sc->sm_count;
+    const bool global_map = sc->pm[1].view.count != 0;
+    const PMView &M = global_map ? sc->pm[1].view : sc->pm[0].view;
+    const size_t n_cells = (size_t)M.nx * M.ny * M.nz;
+    if (mode == 2) {
+        k_knn_list<<<sm_blocks * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, q, q_n, q_cap, acc_amb, acc_fg, found);
+        ++*launches;
+        return FRT_OK;
+    }
+    if (mode == 0 || M.count == 0 || n_cells == 0 || n_cells >= 0xffffffffull) {
+        k_knn<<<sm_blocks * 16, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, q, q_n, q_cap, acc_amb, acc_fg, found);
+        ++*launches;
+        return FRT_OK;
+    }
+    const unsigned int n_part = (unsigned int)((n_cells + FRT_SCAN_CHUNK - 1) / FRT_SCAN_CHUNK);
+    if (sc->gq_cells < n_cells + 1) {
+        cudaFree(sc->gq_counts);
+        cudaFree(sc->gq_starts);
+        sc->gq_counts = sc->gq_starts = nullptr;
+        sc->gq_cells = 0;
+        CK(cudaMalloc(&sc->gq_counts, sizeof(unsigned int) * (n_cells + 1)));
+        CK(cudaMalloc(&sc->gq_starts, sizeof(unsigned int) * (n_cells + 1)));
+        sc->gq_cells = n_cells + 1;
+    }
+    if (sc->gq_part_cap < (size_t)n_part + 1) {
+        cudaFree(sc->gq_part);
+        sc->gq_part = nullptr;
+        sc->gq_part_cap = 0;
+        CK(cudaMalloc(&sc->gq_part, sizeof(unsigned int) * 2 * ((size_t)n_part + 1)));
+        sc->gq_part_cap = (size_t)n_part + 1;
+    }
+    if (sc->gq2_cap < q_cap) {
+        cudaFree(sc->gq2);
+        sc->gq2 = nullptr;
+        sc->gq2_cap = 0;
+        CK(cudaMalloc(&sc->gq2, sizeof(GQuery) * (size_t)q_cap));
+        sc->gq2_cap = q_cap;
+    }
+    if (sc->gq_work == nullptr) {
+        CK(cudaMalloc(&sc->gq_work, 2 * sizeof(unsigned int)));
+        CK(cudaFuncSetAttribute(k_knn_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, FRT_KC_SMEM));
+    }
+    unsigned int *part = sc->gq_part, *part_excl = sc->gq_part + n_part + 1;
+    const bool debug = frt_env_int("FRT_KNN_DEBUG", 0) != 0; /* development aid: the three phases timed, what was passed on counted */
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    if (debug) {
+        for (auto &e : ev) {
+            CK(cudaEventCreate(&e));
+        }
+        CK(cudaEventRecord(ev[0], s));
+    }
+    CK(cudaMemsetAsync(sc->gq_counts, 0, sizeof(unsigned int) * n_cells, s));
+    CK(cudaMemsetAsync(sc->gq_work, 0, 2 * sizeof(unsigned int), s));
+    k_gq_count<<<sm_blocks * 8, 256, 0, s>>>(M, q, q_n, q_cap, sc->gq_counts);
+    k_scan_partial<<<n_part, 1024, 0, s>>>(sc->gq_counts, (unsigned int)n_cells, part);
+    k_pm_scan<<<1, 1024, 0, s>>>(part, part_excl, n_part);
+    k_scan_apply<<<n_part, 1024, 0, s>>>(sc->gq_counts, part_excl, (unsigned int)n_cells, sc->gq_starts);
+    k_gq_scatter<<<sm_blocks * 8, 256, 0, s>>>(M, q, q_n, q_cap, sc->gq_starts, sc->gq2);
+    if (debug) CK(cudaEventRecord(ev[1], s));
+    k_knn_cell<<<sm_blocks * 3, FRT_KC_T, FRT_KC_SMEM, s>>>(M, global_map ? 0 : 1, G, sc->gq2, q_n, q_cap, sc->gq_work, acc_amb, acc_fg, found, q, q_cap);
+    if (debug) CK(cudaEventRecord(ev[2], s));
+    k_knn<<<sm_blocks * 16, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, q, sc->gq_work + 1, q_cap, acc_amb, acc_fg, found);
+    *launches += 7;
+    CK(cudaGetLastError());
+    if (debug) {
+        CK(cudaEventRecord(ev[3], s));
+        CK(cudaStreamSynchronize(s));
+        unsigned int hw[2] = { 0, 0 }, hn = 0;
+        CK(cudaMemcpy(hw, sc->gq_work, sizeof(hw), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&hn, q_n, sizeof(hn), cudaMemcpyDeviceToHost));
+        float t[3] = { 0.f, 0.f, 0.f };
+        for (int k = 0; k < 3; ++k) {
+            cudaEventElapsedTime(&t[k], ev[k], ev[k + 1]);
+        }
+        fprintf(stderr, "[frt] knn batch: %u requests, %zu cells, sort %.2f ms, k_knn_cell %.2f ms, %u passed on to k_knn %.2f ms\n", hn, n_cells, t[0],
+                t[1], hw[1], t[2]);
+        for (auto &e : ev) {
+            cudaEventDestroy(e);
+        }
+    }
+    return FRT_OK;
 }
 
 static int
@@ -5000,10 +5083,14 @@ frt_photons_estimate(frt_scene *sc, int map, int64_t n, const double *pos, const
     if (e == cudaSuccess) e = cudaMemsetAsync(dacc, 0, sizeof(double) * 3 * (size_t)n, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(dfound, 0, sizeof(int) * (size_t)n, s);
     if (e == cudaSuccess) {
-        if (getenv("FRT_KNN_LIST") != nullptr && atoi(getenv("FRT_KNN_LIST")) != 0) {
-            k_knn_list<<<sc->sm_count * 8, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, dq, dn, un, dacc, dacc, dfound);
-        } else {
-            k_knn<<<sc->sm_count * 16, FRT_KNN_WARPS * 32, 0, s>>>(sc->pm[0].view, sc->pm[1].view, G, dq, dn, un, dacc, dacc, dfound);
+        int launches = 0;
+        if (launch_knn(sc, s, G, dq, dn, un, dacc, dacc, dfound, frt_env_int("FRT_KNN_MODE", 1), &launches) != FRT_OK) {
+            cudaStreamSynchronize(s);
+            cudaFree(dq);
+            cudaFree(dn);
+            cudaFree(dacc);
+            cudaFree(dfound);
+            return FRT_ERR_CUDA;
         }
         e = cudaGetLastError();
     }

@@ -1233,6 +1233,396 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
     }
 }
 
+/*
+ * The same estimate with ONE LANE PER REQUEST and the candidates shared by a block (production path).
+ *
+ * k_knn gives every request a warp that pulls its own ~700 candidate photons from L2 twice (ncu: L1 hit rate 8 %, L2 hit
+ * rate 99 %, issue 74 %, L1TEX 66 %): 3 800 warp-instructions and 30 KB of L2 traffic per request, and a final-gather
+ * frame has 655 M of them against 1 M photons.  Here a batch of requests is first sorted by the photon grid's cell
+ * (k_gq_count / scan / k_gq_scatter); a block takes 128 consecutive requests, and for each cell among them streams the
+ * photons of the (2 reach + 1)^3 cells around it -- every photon a request of that cell can reach -- through shared
+ * memory in tiles.  Every lane runs its own request over the tile: the candidate is a broadcast read, the distance is
+ * 6 FP32 operations, and what a candidate costs besides (addresses, global loads, the direction looked up in the
+ * reference's tables, pm.c:54-60, :80-86) is paid once per block, not once per request.
+ *
+ * Selection of the n nearest, per lane: pass 1 counts the photons inside the sphere into the lane's private column of a
+ * shared-memory histogram (128 bins x 16 bit over the squared distance); a sphere with no more than n photons takes them
+ * all (pm.c:147), otherwise the bin B of the n-th nearest follows from the column.  Pass 2 sums the photons of the bins
+ * below B and LISTS the photons of bin B (a handful: 1 / 128 of the sphere), of which the nearest `need` are then taken
+ * in exact (distance, position) order -- the same set k_knn takes.  A request whose bin B holds more than FRT_KC_TIES
+ * photons, or that asks for the other map, is appended to `fallback` and goes through k_knn afterwards.
+ */
+#define FRT_KC_T 128      /* requests (= threads) per block */
+#define FRT_KC_BINS 128
+#define FRT_KC_TIES 16
+#define FRT_KC_TILE_BYTES 22528
+#define FRT_KC_TILE1 (FRT_KC_TILE_BYTES / 16) /* pass 1: position only */
+#define FRT_KC_TILE2 608                      /* pass 2: position, power, direction (36 bytes) */
+#define FRT_KC_SMEM (FRT_KC_TILE_BYTES + FRT_KC_BINS * FRT_KC_T * 2 + FRT_KC_TIES * FRT_KC_T * 8 + 65 * 4)
+
+__global__ void __launch_bounds__(FRT_KC_T, 3)
+k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ queries, const unsigned int *n_queries, unsigned int qcap,
+           unsigned int *work /* [0] next chunk of requests, [1] requests in `fallback` */, double *__restrict__ acc_amb,
+           double *__restrict__ acc_fg, int *__restrict__ found_out, GQuery *__restrict__ fallback, unsigned int fb_cap)
+{
+    extern __shared__ __align__(16) unsigned char kc_raw[];
+    float4 *sP = reinterpret_cast<float4 *>(kc_raw);                                  /* x y z dir.x */
+    float4 *sQ = sP + FRT_KC_TILE2;                                                   /* pass 2: power rgb, dir.y */
+    float *sZ = reinterpret_cast<float *>(sQ + FRT_KC_TILE2);                         /* pass 2: dir.z */
+    unsigned short *hist = reinterpret_cast<unsigned short *>(kc_raw + FRT_KC_TILE_BYTES);
+    float *tdd = reinterpret_cast<float *>(hist + FRT_KC_BINS * FRT_KC_T);
+    unsigned int *tix = reinterpret_cast<unsigned int *>(tdd + FRT_KC_TIES * FRT_KC_T);
+    unsigned int *row_s = tix + FRT_KC_TIES * FRT_KC_T;
+    unsigned int *row_pre = row_s + 32; /* 33 entries: candidates in front of row r */
+    __shared__ unsigned int s_first, s_cur;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned int nq = min(*n_queries, qcap);
+    const float R2 = G.radius * G.radius;
+    const float kscale = (float)FRT_KC_BINS / R2;
+    const unsigned int want_n = (unsigned int)G.n_photons;
+    const float inv_kr = 1.0f / (G.cone_k * G.radius);
+    const int reach = (int)ceilf(G.radius * M.inv_cell);
+    const int side = 2 * reach + 1;
+    const float *tab = M.dir_tab;
+    unsigned short *h = hist + tid; /* this lane's column: bin b at h[b * FRT_KC_T] */
+
+    auto to_fallback = [&](const GQuery &q) {
+        const unsigned int slot = atomicAdd(&work[1], 1u);
+        if (slot < fb_cap) {
+            fallback[slot] = q;
+        }
+    };
+    /* the photon behind candidate c of the current cell's list */
+    auto photon_of = [&](unsigned int c) {
+        int r = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            r += row_pre[r + step] <= c ? step : 0; /* the last row whose first candidate is <= c */
+        }
+        return row_s[r] + (c - row_pre[r]);
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            s_first = atomicAdd(&work[0], (unsigned int)FRT_KC_T);
+        }
+        __syncthreads();
+        const unsigned int first = s_first;
+        if (first >= nq) {
+            break;
+        }
+        const unsigned int qi = first + tid;
+        GQuery q{};
+        bool pending = qi < nq;
+        unsigned int my_cell = 0xffffffffu;
+        if (pending) {
+            q = queries[qi];
+            if (((q.target & 0x40000000u) != 0) != (caustic_map != 0) || side * side > 32) {
+                to_fallback(q);
+                pending = false;
+            } else {
+                my_cell = (unsigned int)pm_cell_of(M, q.x, q.y, q.z);
+            }
+        }
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) {
+                s_cur = 0xffffffffu;
+            }
+            __syncthreads();
+            if (pending) {
+                atomicMin(&s_cur, my_cell);
+            }
+            __syncthreads();
+            const unsigned int cur = s_cur;
+            if (cur == 0xffffffffu) {
+                break;
+            }
+            bool act = pending && my_cell == cur;
+            /* the rows of cells (consecutive in x = one contiguous photon range) within `reach` cells of the cell */
+            if (tid < 32) {
+                const int cx = (int)(cur % (unsigned int)M.nx), cy = (int)((cur / (unsigned int)M.nx) % (unsigned int)M.ny);
+                const int cz = (int)(cur / ((unsigned int)M.nx * (unsigned int)M.ny));
+                unsigned int rs = 0, rl = 0;
+                if (tid < side * side) {
+                    const int z = cz - reach + tid / side, y = cy - reach + tid % side;
+                    if (z >= 0 && z < M.nz && y >= 0 && y < M.ny) {
+                        const int x0 = max(cx - reach, 0), x1 = min(cx + reach, M.nx - 1);
+                        const unsigned int base = (unsigned int)((z * M.ny + y) * M.nx);
+                        rs = __ldg(M.cell_start + base + x0);
+                        rl = __ldg(M.cell_start + base + x1 + 1) - rs;
+                    }
+                }
+                unsigned int incl = rl;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) {
+                        incl += up;
+                    }
+                }
+                row_s[tid] = rs;
+                row_pre[tid + 1] = incl;
+                if (tid == 0) {
+                    row_pre[0] = 0;
+                }
+            }
+            __syncthreads();
+            const unsigned int C = row_pre[32];
+            if (act) {
+                pending = false;
+                if (C > 65535u) { /* a histogram column counts in 16 bits */
+                    to_fallback(q);
+                    act = false;
+                }
+            }
+
+            /* pass 1: photons inside the sphere, histogram of their squared distances */
+            unsigned int cnt = 0;
+            if (act) {
+                for (int b = 0; b < FRT_KC_BINS; ++b) {
+                    h[b * FRT_KC_T] = 0;
+                }
+            }
+            for (unsigned int t0 = 0; t0 < C; t0 += FRT_KC_TILE1) {
+                const unsigned int nt0 = min(C - t0, (unsigned int)FRT_KC_TILE1);
+                __syncthreads();
+                for (unsigned int c = tid; c < nt0; c += FRT_KC_T) {
+                    sP[c] = __ldg(M.a + photon_of(t0 + c));
+                }
+                __syncthreads();
+                if (__any_sync(0xffffffffu, act)) {
+                    auto count = [&](float dd) {
+                        if (act && dd < R2) {
+                            ++cnt;
+                            h[min((unsigned int)(dd * kscale), (unsigned int)FRT_KC_BINS - 1u) * FRT_KC_T] += 1;
+                        }
+                    };
+                    unsigned int c = 0;
+                    for (; c + 4 <= nt0; c += 4) {
+                        const float4 p0 = sP[c], p1 = sP[c + 1], p2 = sP[c + 2], p3 = sP[c + 3];
+                        float dx = p0.x - q.x, dy = p0.y - q.y, dz = p0.z - q.z;
+                        const float d0 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = p1.x - q.x, dy = p1.y - q.y, dz = p1.z - q.z;
+                        const float d1 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = p2.x - q.x, dy = p2.y - q.y, dz = p2.z - q.z;
+                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = p3.x - q.x, dy = p3.y - q.y, dz = p3.z - q.z;
+                        const float d3 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        count(d0);
+                        count(d1);
+                        count(d2);
+                        count(d3);
+                    }
+                    for (; c < nt0; ++c) {
+                        const float4 p0 = sP[c];
+                        const float dx = p0.x - q.x, dy = p0.y - q.y, dz = p0.z - q.z;
+                        count(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                    }
+                }
+            }
+            const bool select = act && cnt > want_n;
+            unsigned int B = 0xffffffffu, need = 0; /* bins below B are taken whole; `need` photons of bin B */
+            if (select) {
+                unsigned int run = 0;
+                int b = 0;
+                for (; b < FRT_KC_BINS - 1; ++b) {
+                    const unsigned int hv = h[b * FRT_KC_T];
+                    if (run + hv >= want_n) {
+                        break;
+                    }
+                    run += hv;
+                }
+                B = (unsigned int)b;
+                need = want_n - run;
+            }
+
+            /* pass 2: sums over the bins below B; the photons of bin B are listed */
+            float sr = 0.f, sg = 0.f, sb = 0.f, far2 = 0.f;
+            unsigned int nt = 0;
+            for (unsigned int t0 = 0; t0 < C; t0 += FRT_KC_TILE2) {
+                const unsigned int nt0 = min(C - t0, (unsigned int)FRT_KC_TILE2);
+                __syncthreads();
+                for (unsigned int c = tid; c < nt0; c += FRT_KC_T) {
+                    const unsigned int p = photon_of(t0 + c);
+                    const float4 a = __ldg(M.a + p), b = __ldg(M.b + p);
+                    const unsigned int dbits = __float_as_uint(a.w);
+                    const unsigned int theta = dbits & 255u, phi = (dbits >> 8) & 255u;
+                    const float st = __ldg(tab + theta);
+                    sP[c] = make_float4(a.x, a.y, a.z, st * __ldg(tab + 512 + phi));
+                    sQ[c] = make_float4(b.x, b.y, b.z, st * __ldg(tab + 768 + phi));
+                    sZ[c] = __ldg(tab + 256 + theta);
+                }
+                __syncthreads();
+                if (__any_sync(0xffffffffu, act)) {
+                    auto visit = [&](unsigned int c, const float4 &p, float dd) {
+                        if (act && dd < R2) {
+                            const unsigned int key = min((unsigned int)(dd * kscale), (unsigned int)FRT_KC_BINS - 1u);
+                            if (key < B) {
+                                const float4 pw = sQ[c];
+                                far2 = fmaxf(far2, dd);
+                                const float dot = fmaf(p.w, q.ex, fmaf(pw.w, q.ey, sZ[c] * q.ez));
+                                if (dot < 0.0f) {
+                                    const float w = 1.0f - sqrtf(dd) * inv_kr;
+                                    sr = fmaf(pw.x, w, sr);
+                                    sg = fmaf(pw.y, w, sg);
+                                    sb = fmaf(pw.z, w, sb);
+                                }
+                            } else if (key == B) {
+                                if (nt < FRT_KC_TIES) {
+                                    tdd[nt * FRT_KC_T + tid] = dd;
+                                    tix[nt * FRT_KC_T + tid] = t0 + c;
+                                }
+                                ++nt;
+                            }
+                        }
+                    };
+                    unsigned int c = 0;
+                    for (; c + 4 <= nt0; c += 4) {
+                        const float4 p0 = sP[c], p1 = sP[c + 1], p2 = sP[c + 2], p3 = sP[c + 3];
+                        float dx = p0.x - q.x, dy = p0.y - q.y, dz = p0.z - q.z;
+                        const float d0 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = p1.x - q.x, dy = p1.y - q.y, dz = p1.z - q.z;
+                        const float d1 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = p2.x - q.x, dy = p2.y - q.y, dz = p2.z - q.z;
+                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = p3.x - q.x, dy = p3.y - q.y, dz = p3.z - q.z;
+                        const float d3 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        visit(c, p0, d0);
+                        visit(c + 1, p1, d1);
+                        visit(c + 2, p2, d2);
+                        visit(c + 3, p3, d3);
+                    }
+                    for (; c < nt0; ++c) {
+                        const float4 p0 = sP[c];
+                        const float dx = p0.x - q.x, dy = p0.y - q.y, dz = p0.z - q.z;
+                        visit(c, p0, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                    }
+                }
+            }
+            if (act) {
+                if (nt > FRT_KC_TIES) {
+                    to_fallback(q); /* a crowded bin: k_knn splits it once more */
+                } else {
+                    /* bin B: the nearest `need` in (distance, position) order */
+                    for (unsigned int k = 0; k < nt; ++k) {
+                        const float v = tdd[k * FRT_KC_T + tid];
+                        unsigned int rank = 0;
+                        for (unsigned int j = 0; j < nt; ++j) {
+                            const float u = tdd[j * FRT_KC_T + tid];
+                            rank += (u < v || (u == v && j < k)) ? 1u : 0u;
+                        }
+                        if (rank < need) {
+                            const unsigned int p = photon_of(tix[k * FRT_KC_T + tid]);
+                            const float4 pw = __ldg(M.b + p);
+                            const unsigned int dbits = __float_as_uint(__ldg(M.a + p).w);
+                            const unsigned int theta = dbits & 255u, phi = (dbits >> 8) & 255u;
+                            const float st = __ldg(tab + theta);
+                            far2 = fmaxf(far2, v);
+                            const float dot = fmaf(st * __ldg(tab + 512 + phi), q.ex, fmaf(st * __ldg(tab + 768 + phi), q.ey, __ldg(tab + 256 + theta) * q.ez));
+                            if (dot < 0.0f) {
+                                const float w = 1.0f - sqrtf(v) * inv_kr;
+                                sr = fmaf(pw.x, w, sr);
+                                sg = fmaf(pw.y, w, sg);
+                                sb = fmaf(pw.z, w, sb);
+                            }
+                        }
+                    }
+                    const unsigned int found = min(cnt, want_n);
+                    if (found_out != nullptr) {
+                        found_out[q.target & 0x3fffffffu] = (int)found;
+                    }
+                    if (found >= 8) { /* pm.c:121: fewer than 8 photons give nothing */
+                        /* np.dist2[0] (pm.c:147): the search radius^2 until the heap of n photons is full, then the n-th distance^2 */
+                        const double r2_density = select ? (double)far2 : (double)R2;
+                        const double density = 1.0 / ((1.0 - 2.0 / (3.0 * (double)G.cone_k)) * (M_PI * r2_density));
+                        const double rescale = found_out != nullptr ? 1.0
+                                                                    : (caustic_map ? 100.0 / (double)found : 10.0 * (double)G.n_photons / (double)found);
+                        const double f = density * rescale;
+                        double *acc = ((q.target & 0x80000000u) ? acc_fg : acc_amb) + 3 * (size_t)(q.target & 0x3fffffffu);
+                        const double vr = f * (double)sr * (double)q.wr, vg = f * (double)sg * (double)q.wg, vb = f * (double)sb * (double)q.wb;
+                        if (vr != 0.0) atomicAdd(acc, vr);
+                        if (vg != 0.0) atomicAdd(acc + 1, vg);
+                        if (vb != 0.0) atomicAdd(acc + 2, vb);
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* exclusive scan of a large array in three launches: per-block sums, k_pm_scan over them, per-block scans */
+#define FRT_SCAN_PER_THREAD 8
+#define FRT_SCAN_CHUNK (1024 * FRT_SCAN_PER_THREAD)
+__global__ void __launch_bounds__(1024)
+k_scan_partial(const unsigned int *__restrict__ counts, unsigned int n, unsigned int *__restrict__ partial)
+{
+    __shared__ unsigned int s_w[32];
+    const size_t base = (size_t)blockIdx.x * FRT_SCAN_CHUNK;
+    unsigned int sum = 0;
+    for (int k = 0; k < FRT_SCAN_PER_THREAD; ++k) {
+        const size_t i = base + (size_t)k * 1024 + threadIdx.x;
+        sum += i < n ? counts[i] : 0u;
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if ((threadIdx.x & 31) == 0) {
+        s_w[threadIdx.x >> 5] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned int v = __reduce_add_sync(0xffffffffu, s_w[threadIdx.x]);
+        if (threadIdx.x == 0) {
+            partial[blockIdx.x] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_apply(const unsigned int *__restrict__ counts, const unsigned int *__restrict__ block_excl, unsigned int n, unsigned int *__restrict__ start)
+{
+    __shared__ unsigned int s_w[32];
+    const size_t base = (size_t)blockIdx.x * FRT_SCAN_CHUNK + (size_t)threadIdx.x * FRT_SCAN_PER_THREAD;
+    unsigned int v[FRT_SCAN_PER_THREAD], sum = 0;
+    for (int k = 0; k < FRT_SCAN_PER_THREAD; ++k) {
+        v[k] = base + k < n ? counts[base + k] : 0u;
+        sum += v[k];
+    }
+    unsigned int incl = sum;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) {
+            incl += up;
+        }
+    }
+    if (lane == 31) {
+        s_w[w] = incl;
+    }
+    __syncthreads();
+    if (w == 0) {
+        unsigned int x = s_w[lane], xi = x;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, xi, o);
+            if (lane >= o) {
+                xi += up;
+            }
+        }
+        s_w[lane] = xi - x;
+    }
+    __syncthreads();
+    unsigned int run = block_excl[blockIdx.x] + s_w[w] + (incl - sum);
+    for (int k = 0; k < FRT_SCAN_PER_THREAD; ++k) {
+        if (base + k < n) {
+            start[base + k] = run;
+        }
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) {
+        start[n] = run;
+    }
+}
+
 /* the ambient slot of shade_hit (renderer.c:737-770): direct ambient + indirect + final gather + caustics, clamped to a
  * sum of sqrt(3) on diffuse surfaces, weighted into the pixel */
 __global__ void __launch_bounds__(256)
