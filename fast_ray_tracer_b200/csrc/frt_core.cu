@@ -2007,7 +2007,7 @@ struct frt_scene {
     struct PMap {
         float4 *ra = nullptr, *rb = nullptr; /* photons as stored / imported */
         unsigned int cap = 0, count = 0;
-        float4 *sa = nullptr, *sb = nullptr; /* sorted by grid cell */
+        float4 *sa = nullptr, *sb = nullptr, *sd = nullptr; /* sorted by grid cell: position + packed direction, power, direction */
         unsigned int *cell_start = nullptr;
         PMView view{};
         bool built = false;
@@ -4093,7 +4093,17 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         ++launches;
                     }
                     if (G.use_final_gather) {
-                        k_fg_trace<<<sm_blocks * 16, 128, 0, s>>>(sc->S, sc->SF, F, G, sc->recs, first, nb, sc->gq, sc->gq_n, sc->gq_cap, sc->cnt, level);
+#define FRT_FG(PR, MP) k_fg_trace<PR, MP><<<sm_blocks * 16, 128, 0, s>>>(sc->S, sc->SF, F, G, sc->recs, first, nb, sc->gq, sc->gq_n, sc->gq_cap, sc->cnt, level)
+                        if (sc->boxes_and_balls && !sc->has_maps) {
+                            FRT_FG(FRT_PRIMS_BOXES_AND_BALLS, false);
+                        } else if (sc->boxes_and_balls) {
+                            FRT_FG(FRT_PRIMS_BOXES_AND_BALLS, true);
+                        } else if (!sc->has_maps) {
+                            FRT_FG(FRT_PRIMS_ALL, false);
+                        } else {
+                            FRT_FG(FRT_PRIMS_ALL, true);
+                        }
+#undef FRT_FG
                         ++launches;
                     }
                     tock(tk);
@@ -4360,6 +4370,7 @@ pm_free(frt_scene *sc)
         cudaFree(m.rb);
         cudaFree(m.sa);
         cudaFree(m.sb);
+        cudaFree(m.sd);
         cudaFree(m.cell_start);
         m = frt_scene::PMap{};
     }
@@ -4596,7 +4607,17 @@ frt_photons_emit(frt_scene *sc, const frt_photon_cfg *cfg, frt_stats *stats)
                 P.count = n;
                 P.seed = mix64(cfg->seed ^ 0x70686f746f6e73ull);
                 const int blocks = (int)std::min<unsigned long long>((n + 127) / 128, (unsigned long long)sc->sm_count * 16);
-                k_photon_trace<<<blocks, 128, 0, sc->stream>>>(sc->S, sc->SF, P, m.ra, m.rb, sc->pm_stored + map, m.cap, sc->cnt);
+#define FRT_PT(PR, MP) k_photon_trace<PR, MP><<<blocks, 128, 0, sc->stream>>>(sc->S, sc->SF, P, m.ra, m.rb, sc->pm_stored + map, m.cap, sc->cnt)
+                if (sc->boxes_and_balls && !sc->has_maps) {
+                    FRT_PT(FRT_PRIMS_BOXES_AND_BALLS, false);
+                } else if (sc->boxes_and_balls) {
+                    FRT_PT(FRT_PRIMS_BOXES_AND_BALLS, true);
+                } else if (!sc->has_maps) {
+                    FRT_PT(FRT_PRIMS_ALL, false);
+                } else {
+                    FRT_PT(FRT_PRIMS_ALL, true);
+                }
+#undef FRT_PT
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(&stored, sc->pm_stored + map, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->stream));
                 CK(cudaStreamSynchronize(sc->stream));
@@ -4714,8 +4735,9 @@ frt_photons_finish(frt_scene *sc)
         frt_scene::PMap &m = sc->pm[map];
         cudaFree(m.sa);
         cudaFree(m.sb);
+        cudaFree(m.sd);
         cudaFree(m.cell_start);
-        m.sa = m.sb = nullptr;
+        m.sa = m.sb = m.sd = nullptr;
         m.cell_start = nullptr;
         m.view = PMView{};
         m.view.dir_tab = sc->pm_dir_tab;
@@ -4765,17 +4787,30 @@ frt_photons_finish(frt_scene *sc)
         CK(cudaMalloc(&m.cell_start, sizeof(unsigned int) * (n_cells + 1)));
         CK(cudaMalloc(&m.sa, sizeof(float4) * (size_t)m.count));
         CK(cudaMalloc(&m.sb, sizeof(float4) * (size_t)m.count));
+        CK(cudaMalloc(&m.sd, sizeof(float4) * (size_t)m.count));
         CK(cudaMemsetAsync(counts, 0, sizeof(unsigned int) * n_cells, sc->stream));
         k_pm_count<<<sc->sm_count * 4, 256, 0, sc->stream>>>(V, m.ra, m.count, counts);
-        k_pm_scan<<<1, 1024, 0, sc->stream>>>(counts, m.cell_start, (unsigned int)n_cells);
+        {
+            /* the scan of the (up to 2^26) cell counts in three launches */
+            const unsigned int n_part = (unsigned int)((n_cells + FRT_SCAN_CHUNK - 1) / FRT_SCAN_CHUNK);
+            unsigned int *part = nullptr;
+            CK(cudaMalloc(&part, sizeof(unsigned int) * 2 * ((size_t)n_part + 1)));
+            k_scan_partial<<<n_part, 1024, 0, sc->stream>>>(counts, (unsigned int)n_cells, part);
+            k_pm_scan<<<1, 1024, 0, sc->stream>>>(part, part + n_part + 1, n_part);
+            k_scan_apply<<<n_part, 1024, 0, sc->stream>>>(counts, part + n_part + 1, (unsigned int)n_cells, m.cell_start);
+            CK(cudaStreamSynchronize(sc->stream));
+            cudaFree(part);
+        }
         /* counts becomes the per-cell write cursor */
         CK(cudaMemcpyAsync(counts, m.cell_start, sizeof(unsigned int) * n_cells, cudaMemcpyDeviceToDevice, sc->stream));
         k_pm_scatter<<<sc->sm_count * 4, 256, 0, sc->stream>>>(V, m.ra, m.rb, m.count, counts, m.sa, m.sb);
+        k_pm_dirs<<<sc->sm_count * 4, 256, 0, sc->stream>>>(m.sa, m.count, sc->pm_dir_tab, m.sd);
         CK(cudaStreamSynchronize(sc->stream));
         CK(cudaGetLastError());
         cudaFree(counts);
         V.a = m.sa;
         V.b = m.sb;
+        V.c = m.sd;
         V.cell_start = m.cell_start;
         m.view = V;
     }

@@ -29,7 +29,8 @@
 #define FRT_KNN_CAP 1024
 
 struct PMView { /* one photon map as the kernels see it */
-    const float4 *a, *b;            /* sorted by cell */
+    const float4 *a, *b;            /* sorted by cell: {position, packed direction} {power} */
+    const float4 *c;                /* sorted by cell: the direction pm_photon_dir (pm.c:80-86) reads from the tables, {x, y, z, 0} */
     const unsigned int *cell_start; /* n_cells + 1 */
     float gx, gy, gz, inv_cell;
     int nx, ny, nz;
@@ -143,6 +144,7 @@ struct SurfaceG { /* the part of prepare_computations (renderer.c:368-495) the G
     int material;
 };
 
+template <bool MAPS>
 __device__ __forceinline__ void
 surface_at(const DScene &S, const Ray &r, const Hit &h, SurfaceG &g)
 {
@@ -158,7 +160,7 @@ surface_at(const DScene &S, const Ray &r, const Hit &h, SurfaceG &g)
     point_to_local(S, a.xform, g.p, lp);
     local_normal(a.type, prm, lp, h.u, h.v, ln);
     normal_to_world(S, a.xform, ln, g.n);
-    if (M.map_bump >= 0) {
+    if (MAPS && M.map_bump >= 0) { /* MAPS = false: the scene binds no pattern to any material, the interpreter is left out */
         double tex[3];
         pattern_at_shape(S, M.map_bump, h.leaf, g.p, NULL, tex, 0);
         g.n[0] += 2.0 * tex[0] - 1.0;
@@ -182,7 +184,7 @@ surface_at(const DScene &S, const Ray &r, const Hit &h, SurfaceG &g)
         g.over[k] = g.p[k] + g.n[k] * FRT_EPS;
         g.under[k] = g.p[k] - g.n[k] * FRT_EPS;
     }
-    material_color(S, M.map_Kd, M.Kd, h.leaf, g.over, g.Kd);
+    material_color(S, MAPS ? M.map_Kd : -1, M.Kd, h.leaf, g.over, g.Kd);
 }
 
 /* ------------------------------------------------------------------------------------------------ photon pass */
@@ -210,6 +212,7 @@ pack_photon_dir(const double d[3])
     return (unsigned int)theta | ((unsigned int)phi << 8);
 }
 
+template <int PRIMS, bool MAPS>
 __global__ void __launch_bounds__(128)
 k_photon_trace(DScene S, DSceneF SF, PhotonParams P, float4 *__restrict__ pa, float4 *__restrict__ pb, unsigned int *stored, unsigned int cap,
                Counters *cnt)
@@ -257,7 +260,7 @@ k_photon_trace(DScene S, DSceneF SF, PhotonParams P, float4 *__restrict__ pa, fl
 
         /* ---- power_at / photon_hit, photon_tracer.c:114-201, as a loop */
         for (int remaining = P.path_length; remaining > 0; --remaining) {
-            const Hit h = trace_closest_mixed<true>(S, SF, r, &overflow); /* hit(xs, true) */
+            const Hit h = trace_closest_mixed<true, PRIMS>(S, SF, r, &overflow); /* hit(xs, true) */
             if (h.leaf < 0) {
                 break;
             }
@@ -265,10 +268,10 @@ k_photon_trace(DScene S, DSceneF SF, PhotonParams P, float4 *__restrict__ pa, fl
                 break;
             }
             SurfaceG g;
-            surface_at(S, r, h, g);
+            surface_at<MAPS>(S, r, h, g);
             const frt_material &M = S.mats[g.material];
             double refl[3];
-            material_color(S, M.map_refl, M.refl, h.leaf, g.over, refl);
+            material_color(S, MAPS ? M.map_refl : -1, M.refl, h.leaf, g.over, refl);
             const double avg_d = (g.Kd[0] + g.Kd[1] + g.Kd[2]) / 3.0;
             if (g.Kd[0] > 0 || g.Kd[1] > 0 || g.Kd[2] > 0) {
                 const bool store = (P.map_type == 0) ? had_specular : had_diffuse;
@@ -456,6 +459,18 @@ k_pm_scatter(PMView M, const float4 *__restrict__ a, const float4 *__restrict__ 
     }
 }
 
+/* pm_photon_dir (pm.c:80-86) for every photon, once: the products the facing test of the radiance estimate multiplies out */
+__global__ void
+k_pm_dirs(const float4 *__restrict__ sa, unsigned int n, const float *__restrict__ tab, float4 *__restrict__ sc)
+{
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned int dbits = __float_as_uint(sa[i].w);
+        const unsigned int theta = dbits & 255u, phi = (dbits >> 8) & 255u;
+        const float st = __ldg(tab + theta);
+        sc[i] = make_float4(st * __ldg(tab + 512 + phi), st * __ldg(tab + 768 + phi), __ldg(tab + 256 + theta), 0.f);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ queries */
 
 /*
@@ -463,6 +478,7 @@ k_pm_scatter(PMView M, const float4 *__restrict__ a, const float4 *__restrict__ 
  * hit, if diffuse, becomes a radiance-estimate request weighted by  pi * Kd * (eye . n) * rands[0]  (shade_hit_gi
  * :626-645, lighting_gi :862-892, the "scale by theta" of :672).
  */
+template <int PRIMS, bool MAPS>
 __global__ void __launch_bounds__(128)
 k_fg_trace(DScene S, DSceneF SF, FrameParams F, GIParams G, const LightRec *__restrict__ recs, unsigned int first_hit, unsigned int n_hits_batch,
            GQuery *__restrict__ queries, unsigned int *n_queries, unsigned int qcap, Counters *cnt, int level)
@@ -493,17 +509,17 @@ k_fg_trace(DScene S, DSceneF SF, FrameParams F, GIParams G, const LightRec *__re
                 double d[3];
                 cosine_hemisphere(n, r1, r2, d);
                 const Ray r{ R->over[0], R->over[1], R->over[2], d[0], d[1], d[2] };
-                const Hit hit = trace_closest_mixed<false>(S, SF, r, &overflow);
+                const Hit hit = trace_closest_mixed<false, PRIMS>(S, SF, r, &overflow); /* instantiated for the primitive types the scene holds, like k_extend */
                 ++n_rays;
                 if (hit.leaf >= 0) {
                     /* color_at_gi tests the diffuse colour at the hit point itself (:331-337) ... */
                     const frt_material &M = S.mats[load_node_a(S, hit.leaf).material];
                     const double p[3] = { r.ox + r.dx * hit.t, r.oy + r.dy * hit.t, r.oz + r.dz * hit.t };
                     double kd0[3];
-                    material_color(S, M.map_Kd, M.Kd, hit.leaf, p, kd0);
+                    material_color(S, MAPS ? M.map_Kd : -1, M.Kd, hit.leaf, p, kd0);
                     if (kd0[0] > 0 || kd0[1] > 0 || kd0[2] > 0) {
                         SurfaceG g; /* ... and lighting_gi uses over_Kd, sampled at over_point (:862-866) */
-                        surface_at(S, r, hit, g);
+                        surface_at<MAPS>(S, r, hit, g);
                         if (g.Kd[0] > 0.0 || g.Kd[1] > 0.0 || g.Kd[2] > 0.0) {
                             const double edn = g.eye[0] * g.n[0] + g.eye[1] * g.n[1] + g.eye[2] * g.n[2];
                             const double base_w = M_PI * r1;
@@ -1255,10 +1271,30 @@ k_knn(PMView MC, PMView MG, GIParams G, const GQuery *__restrict__ queries, cons
 #define FRT_KC_T 128      /* requests (= threads) per block */
 #define FRT_KC_BINS 128
 #define FRT_KC_TIES 16
-#define FRT_KC_TILE_BYTES 22528
-#define FRT_KC_TILE1 (FRT_KC_TILE_BYTES / 16) /* pass 1: position only */
-#define FRT_KC_TILE2 608                      /* pass 2: position, power, direction (36 bytes) */
-#define FRT_KC_SMEM (FRT_KC_TILE_BYTES + FRT_KC_BINS * FRT_KC_T * 2 + FRT_KC_TIES * FRT_KC_T * 8 + 65 * 4)
+#define FRT_KC_BUF_BYTES 11264                 /* one of the two tile buffers */
+#define FRT_KC_TILE1 (FRT_KC_BUF_BYTES / 16)   /* pass 1: position only */
+#define FRT_KC_TILE2 224                       /* pass 2: position, power, direction (48 bytes) */
+#define FRT_KC_SMEM (2 * FRT_KC_BUF_BYTES + FRT_KC_BINS * FRT_KC_T * 2 + FRT_KC_TIES * FRT_KC_T * 8 + 65 * 4)
+
+__device__ __forceinline__ void
+cp_async16(void *smem, const void *gmem)
+{
+    const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+
+__device__ __forceinline__ void
+cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void
+cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 __global__ void __launch_bounds__(FRT_KC_T, 3)
 k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ queries, const unsigned int *n_queries, unsigned int qcap,
@@ -1266,10 +1302,7 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
            double *__restrict__ acc_fg, int *__restrict__ found_out, GQuery *__restrict__ fallback, unsigned int fb_cap)
 {
     extern __shared__ __align__(16) unsigned char kc_raw[];
-    float4 *sP = reinterpret_cast<float4 *>(kc_raw);                                  /* x y z dir.x */
-    float4 *sQ = sP + FRT_KC_TILE2;                                                   /* pass 2: power rgb, dir.y */
-    float *sZ = reinterpret_cast<float *>(sQ + FRT_KC_TILE2);                         /* pass 2: dir.z */
-    unsigned short *hist = reinterpret_cast<unsigned short *>(kc_raw + FRT_KC_TILE_BYTES);
+    unsigned short *hist = reinterpret_cast<unsigned short *>(kc_raw + 2 * FRT_KC_BUF_BYTES);
     float *tdd = reinterpret_cast<float *>(hist + FRT_KC_BINS * FRT_KC_T);
     unsigned int *tix = reinterpret_cast<unsigned int *>(tdd + FRT_KC_TIES * FRT_KC_T);
     unsigned int *row_s = tix + FRT_KC_TIES * FRT_KC_T;
@@ -1284,8 +1317,8 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
     const float inv_kr = 1.0f / (G.cone_k * G.radius);
     const int reach = (int)ceilf(G.radius * M.inv_cell);
     const int side = 2 * reach + 1;
-    const float *tab = M.dir_tab;
-    unsigned short *h = hist + tid; /* this lane's column: bin b at h[b * FRT_KC_T] */
+    unsigned int *h32 = reinterpret_cast<unsigned int *>(hist) + tid; /* this lane's column: bins 2w and 2w + 1 in the halves of h32[w * FRT_KC_T] */
+    auto bin_count = [&](int b) { return (h32[(b >> 1) * FRT_KC_T] >> ((b & 1) * 16)) & 0xffffu; };
 
     auto to_fallback = [&](const GQuery &q) {
         const unsigned int slot = atomicAdd(&work[1], 1u);
@@ -1301,6 +1334,23 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
             r += row_pre[r + step] <= c ? step : 0; /* the last row whose first candidate is <= c */
         }
         return row_s[r] + (c - row_pre[r]);
+    };
+    /* tiles travel global -> shared with cp.async into one buffer while the lanes work on the other */
+    auto buffer = [&](unsigned int k) { return reinterpret_cast<float4 *>(kc_raw + (k & 1u) * FRT_KC_BUF_BYTES); };
+    auto fetch1 = [&](unsigned int t0, unsigned int n, float4 *dst) {
+        for (unsigned int c = tid; c < n; c += FRT_KC_T) {
+            cp_async16(dst + c, M.a + photon_of(t0 + c));
+        }
+        cp_async_commit();
+    };
+    auto fetch2 = [&](unsigned int t0, unsigned int n, float4 *dst) {
+        for (unsigned int c = tid; c < n; c += FRT_KC_T) {
+            const unsigned int p = photon_of(t0 + c);
+            cp_async16(dst + c, M.a + p);
+            cp_async16(dst + FRT_KC_TILE2 + c, M.b + p);
+            cp_async16(dst + 2 * FRT_KC_TILE2 + c, M.c + p);
+        }
+        cp_async_commit();
     };
 
     for (;;) {
@@ -1377,26 +1427,35 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
                     act = false;
                 }
             }
+            const bool warp_act = __any_sync(0xffffffffu, act);
 
             /* pass 1: photons inside the sphere, histogram of their squared distances */
             unsigned int cnt = 0;
             if (act) {
-                for (int b = 0; b < FRT_KC_BINS; ++b) {
-                    h[b * FRT_KC_T] = 0;
+                for (int b = 0; b < FRT_KC_BINS / 2; ++b) {
+                    h32[b * FRT_KC_T] = 0;
                 }
             }
-            for (unsigned int t0 = 0; t0 < C; t0 += FRT_KC_TILE1) {
+            if (C > 0) {
+                fetch1(0, min(C, (unsigned int)FRT_KC_TILE1), buffer(0));
+            }
+            for (unsigned int t0 = 0, k = 0; t0 < C; t0 += FRT_KC_TILE1, ++k) {
                 const unsigned int nt0 = min(C - t0, (unsigned int)FRT_KC_TILE1);
-                __syncthreads();
-                for (unsigned int c = tid; c < nt0; c += FRT_KC_T) {
-                    sP[c] = __ldg(M.a + photon_of(t0 + c));
+                if (t0 + FRT_KC_TILE1 < C) {
+                    fetch1(t0 + FRT_KC_TILE1, min(C - t0 - FRT_KC_TILE1, (unsigned int)FRT_KC_TILE1), buffer(k + 1));
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
                 }
                 __syncthreads();
-                if (__any_sync(0xffffffffu, act)) {
+                if (warp_act) {
+                    const float4 *sP = buffer(k);
                     auto count = [&](float dd) {
                         if (act && dd < R2) {
                             ++cnt;
-                            h[min((unsigned int)(dd * kscale), (unsigned int)FRT_KC_BINS - 1u) * FRT_KC_T] += 1;
+                            /* two 16-bit bins to a word, bumped with a shared-memory reduction: nothing waits for the old value */
+                            const unsigned int key = min((unsigned int)(dd * kscale), (unsigned int)FRT_KC_BINS - 1u);
+                            atomicAdd(h32 + (key >> 1) * FRT_KC_T, 1u << ((key & 1u) * 16u));
                         }
                     };
                     unsigned int c = 0;
@@ -1421,6 +1480,7 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
                         count(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
                     }
                 }
+                __syncthreads(); /* the buffer is refilled two tiles on */
             }
             const bool select = act && cnt > want_n;
             unsigned int B = 0xffffffffu, need = 0; /* bins below B are taken whole; `need` photons of bin B */
@@ -1428,7 +1488,7 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
                 unsigned int run = 0;
                 int b = 0;
                 for (; b < FRT_KC_BINS - 1; ++b) {
-                    const unsigned int hv = h[b * FRT_KC_T];
+                    const unsigned int hv = bin_count(b);
                     if (run + hv >= want_n) {
                         break;
                     }
@@ -1441,28 +1501,27 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
             /* pass 2: sums over the bins below B; the photons of bin B are listed */
             float sr = 0.f, sg = 0.f, sb = 0.f, far2 = 0.f;
             unsigned int nt = 0;
-            for (unsigned int t0 = 0; t0 < C; t0 += FRT_KC_TILE2) {
+            if (C > 0) {
+                fetch2(0, min(C, (unsigned int)FRT_KC_TILE2), buffer(0));
+            }
+            for (unsigned int t0 = 0, k = 0; t0 < C; t0 += FRT_KC_TILE2, ++k) {
                 const unsigned int nt0 = min(C - t0, (unsigned int)FRT_KC_TILE2);
-                __syncthreads();
-                for (unsigned int c = tid; c < nt0; c += FRT_KC_T) {
-                    const unsigned int p = photon_of(t0 + c);
-                    const float4 a = __ldg(M.a + p), b = __ldg(M.b + p);
-                    const unsigned int dbits = __float_as_uint(a.w);
-                    const unsigned int theta = dbits & 255u, phi = (dbits >> 8) & 255u;
-                    const float st = __ldg(tab + theta);
-                    sP[c] = make_float4(a.x, a.y, a.z, st * __ldg(tab + 512 + phi));
-                    sQ[c] = make_float4(b.x, b.y, b.z, st * __ldg(tab + 768 + phi));
-                    sZ[c] = __ldg(tab + 256 + theta);
+                if (t0 + FRT_KC_TILE2 < C) {
+                    fetch2(t0 + FRT_KC_TILE2, min(C - t0 - FRT_KC_TILE2, (unsigned int)FRT_KC_TILE2), buffer(k + 1));
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
                 }
                 __syncthreads();
-                if (__any_sync(0xffffffffu, act)) {
-                    auto visit = [&](unsigned int c, const float4 &p, float dd) {
+                if (warp_act) {
+                    const float4 *sP = buffer(k), *sQ = sP + FRT_KC_TILE2, *sD = sP + 2 * FRT_KC_TILE2;
+                    auto visit = [&](unsigned int c, float dd) {
                         if (act && dd < R2) {
                             const unsigned int key = min((unsigned int)(dd * kscale), (unsigned int)FRT_KC_BINS - 1u);
                             if (key < B) {
-                                const float4 pw = sQ[c];
+                                const float4 pw = sQ[c], dir = sD[c];
                                 far2 = fmaxf(far2, dd);
-                                const float dot = fmaf(p.w, q.ex, fmaf(pw.w, q.ey, sZ[c] * q.ez));
+                                const float dot = fmaf(dir.x, q.ex, fmaf(dir.y, q.ey, dir.z * q.ez));
                                 if (dot < 0.0f) {
                                     const float w = 1.0f - sqrtf(dd) * inv_kr;
                                     sr = fmaf(pw.x, w, sr);
@@ -1489,17 +1548,18 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
                         const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                         dx = p3.x - q.x, dy = p3.y - q.y, dz = p3.z - q.z;
                         const float d3 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                        visit(c, p0, d0);
-                        visit(c + 1, p1, d1);
-                        visit(c + 2, p2, d2);
-                        visit(c + 3, p3, d3);
+                        visit(c, d0);
+                        visit(c + 1, d1);
+                        visit(c + 2, d2);
+                        visit(c + 3, d3);
                     }
                     for (; c < nt0; ++c) {
                         const float4 p0 = sP[c];
                         const float dx = p0.x - q.x, dy = p0.y - q.y, dz = p0.z - q.z;
-                        visit(c, p0, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                        visit(c, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
                     }
                 }
+                __syncthreads();
             }
             if (act) {
                 if (nt > FRT_KC_TIES) {
@@ -1515,12 +1575,9 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
                         }
                         if (rank < need) {
                             const unsigned int p = photon_of(tix[k * FRT_KC_T + tid]);
-                            const float4 pw = __ldg(M.b + p);
-                            const unsigned int dbits = __float_as_uint(__ldg(M.a + p).w);
-                            const unsigned int theta = dbits & 255u, phi = (dbits >> 8) & 255u;
-                            const float st = __ldg(tab + theta);
+                            const float4 pw = __ldg(M.b + p), dir = __ldg(M.c + p);
                             far2 = fmaxf(far2, v);
-                            const float dot = fmaf(st * __ldg(tab + 512 + phi), q.ex, fmaf(st * __ldg(tab + 768 + phi), q.ey, __ldg(tab + 256 + theta) * q.ez));
+                            const float dot = fmaf(dir.x, q.ex, fmaf(dir.y, q.ey, dir.z * q.ez));
                             if (dot < 0.0f) {
                                 const float w = 1.0f - sqrtf(v) * inv_kr;
                                 sr = fmaf(pw.x, w, sr);
