@@ -1451,12 +1451,12 @@ k_knn_cell(PMView M, int caustic_map, GIParams G, const GQuery *__restrict__ que
                 if (warp_act) {
                     const float4 *sP = buffer(k);
                     auto count = [&](float dd) {
-                        if (act && dd < R2) {
-                            ++cnt;
-                            /* two 16-bit bins to a word, bumped with a shared-memory reduction: nothing waits for the old value */
-                            const unsigned int key = min((unsigned int)(dd * kscale), (unsigned int)FRT_KC_BINS - 1u);
-                            atomicAdd(h32 + (key >> 1) * FRT_KC_T, 1u << ((key & 1u) * 16u));
-                        }
+                        /* two 16-bit bins to a word, bumped with a shared-memory reduction: nothing waits for the old value, and
+                         * nothing branches -- a photon outside the sphere adds 0 to the last bin */
+                        const bool in = act && dd < R2;
+                        const unsigned int key = min((unsigned int)(dd * kscale), (unsigned int)FRT_KC_BINS - 1u);
+                        cnt += in ? 1u : 0u;
+                        atomicAdd(h32 + (key >> 1) * FRT_KC_T, in ? 1u << ((key & 1u) * 16u) : 0u);
                     };
                     unsigned int c = 0;
                     for (; c + 4 <= nt0; c += 4) {
