@@ -19,7 +19,9 @@ timed frames it skips rays whose weight is exactly zero, and the JSON line carri
 (`rays_traced_per_frame`).  value = reference-counted rays of the frame / frame time.
 
 Multi-GPU (torchrun, one process per GPU): the frame's row blocks are partitioned over the ranks, the scene is
-replicated, rank 0 gathers the rows over NCCL inside the timed region; "scaling" is strong (one frame, N GPUs).  After
+replicated, and inside the timed region every rank copies its row blocks over NVLink into a canvas on rank 0 (opened
+through CUDA IPC; one strided copy on the rank's render stream, then a barrier -- FRT_BENCH_GATHER=gather selects the
+NCCL gather instead); "scaling" is strong (one frame, N GPUs).  After
 the timed loop the exact variant of the scene goes through the same rows/gather path and is compared with the reference's
 own 800x800 frame (`parity` in the JSON line); the end-to-end steps write each rank's rows straight into one page-locked
 host canvas (shared memory at N > 1).
@@ -297,9 +299,11 @@ def cuda_arm(args) -> dict:
 
     import fast_ray_tracer_b200 as frt
     from fast_ray_tracer_b200.api import FRT_FLAG_COUNT_RAYS, FRT_FLAG_NO_PRUNE, FRT_FLAG_STAGE_TIMES
-    from fast_ray_tracer_b200.dist import gather_rows, owned_rows, reduce_canvas
+    from fast_ray_tracer_b200.dist import PushGather, gather_rows, owned_rows, reduce_canvas
 
-    gather_mode = os.environ.get("FRT_BENCH_GATHER", "gather")
+    # N > 1, how the rows reach rank 0: "push" (default) -- every rank copies its row blocks over NVLink into a canvas on
+    # rank 0 that it opened through CUDA IPC, no collective; "gather" -- pack + NCCL gather + reorder; "reduce" -- NCCL reduce
+    gather_mode = os.environ.get("FRT_BENCH_GATHER", "push")
     sys.path.insert(0, str(REPO / "oracle"))
     from compare import parity_report  # the checker of the parity block below; nothing of oracle/ is on the timed path
 
@@ -327,8 +331,13 @@ def cuda_arm(args) -> dict:
             dist.barrier()
         torch.cuda.synchronize()
 
+    push = PushGather(frt, local, vsize, hsize, rank, world) if (world > 1 and gather_mode == "push") else None
+
     def frame_step(sc, seed):
-        """One frame of this rank's rows on the device, then (N > 1) the NCCL gather of the rows to rank 0."""
+        """One frame of this rank's rows on the device, then (N > 1) the rows brought together on rank 0."""
+        if push is not None:
+            canvas, st = push.render(sc, rows_per_block=rpb, seed=seed)
+            return st, canvas
         _, st = sc.render(rank=rank, world=world, rows_per_block=rpb, download=False, seed=seed)
         frame = sc.canvas_tensor()
         if world > 1 and gather_mode == "reduce":
@@ -378,7 +387,7 @@ def cuda_arm(args) -> dict:
             if os.environ.get("FRT_BENCH_DEBUG"):
                 print(f"[bench] rank {rank} step {k}: device frame {st.frame_ms:.2f} ms, events {ev0.elapsed_time(ev1):.2f} ms, "
                       f"wall {1e3 * (time.perf_counter() - tk):.2f} ms", file=sys.stderr)
-            # the core times its own stream with CUDA events (frame_ms); the torch events bracket the NCCL gather too
+            # the core times its own stream with CUDA events (frame_ms); the torch events bracket the barrier / NCCL gather too
             dev_ms_total += max(st.frame_ms, ev0.elapsed_time(ev1))
             frame_ms.append(st.frame_ms)
             launches += st.kernel_launches
@@ -418,6 +427,8 @@ def cuda_arm(args) -> dict:
                 parity = {"fixture": gold.name, "variant": "exact (cache-size 1), same rows/gather path as the timed frames",
                           "within_1lsb": rep["within_1lsb"], "max_lsb": rep["max_lsb"], "exact": rep["exact"], "pixels": rep["pixels"]}
         barrier()
+    if push is not None:
+        push.close()
 
     # ---- e2e: the reference-facing call with HOST buffers, every step: frt_scene_create_gen(host description) -> the light
     #      cache rebuilt + verified on the device -> frt_render -> this rank's rows copied straight into the caller's
@@ -493,6 +504,9 @@ def cuda_arm(args) -> dict:
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "variant": args.variant, "hsize": hsize, "vsize": vsize, "spp": args.spp * args.spp,
                        "parallelism": f"rows/{world}" if world > 1 else "single", "rows_per_block": rpb,
+                       "rows_to_rank0": ({"push": "peer copy of each rank's row blocks into rank 0's canvas (CUDA IPC over NVLink) + barrier",
+                                          "gather": "pack + NCCL gather + reorder", "reduce": "NCCL reduce of the canvases"}[gather_mode]
+                                         if world > 1 else None),
                        "l2": "256 MiB flush write between timed frames; the 157 MB light-sample cache alone exceeds L2"},
             "frame_ms": ms_per_step,
             "rays_reference_counted_per_frame": ref_rays, "rays_traced_per_frame": traced_rays,

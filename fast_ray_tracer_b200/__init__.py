@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     RenderStats,
     Scene,
     SceneDesc,
+    SharedBuffer,
     device_count,
     encode_ppm16,
     library_path,
@@ -23,6 +24,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "FrtError", "RenderStats", "Scene", "SceneDesc", "device_count", "encode_ppm16", "library_path", "load_library",
+    "FrtError", "RenderStats", "Scene", "SceneDesc", "SharedBuffer", "device_count", "encode_ppm16", "library_path", "load_library",
     "measure_fma_peak", "render", "render_multi",
 ]

@@ -146,6 +146,7 @@ EXPORTS = [
     "frt_scene_create_gen", "frt_scene_gen_status", "frt_drand48_advance", "frt_light_points_checksum", "frt_light_points_checksum_host",
     "frt_photons_estimate", "frt_multi_create", "frt_multi_destroy", "frt_multi_device_count", "frt_multi_scene",
     "frt_multi_render", "frt_multi_photons", "frt_texture_ingest", "frt_tree_with_runs",
+    "frt_shared_buffer_create", "frt_shared_buffer_open", "frt_shared_buffer_close",
 ]
 
 
@@ -200,6 +201,9 @@ def load_library():
     lib.frt_abi_sizeof.argtypes = [C.c_char_p]
     lib.frt_owned_rows.argtypes = [C.POINTER(frt_scene_desc), C.POINTER(frt_render_cfg), C.POINTER(C.c_int32), C.c_int]
     lib.frt_tree_with_runs.argtypes = [C.POINTER(frt_scene_desc), C.c_void_p, C.c_int, C.c_void_p]
+    lib.frt_shared_buffer_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.frt_shared_buffer_open.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.frt_shared_buffer_close.argtypes = [C.c_void_p, C.c_int]
     lib.frt_measure_fma_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.frt_scene_save.argtypes = [C.POINTER(frt_scene_desc), C.c_char_p]
     lib.frt_scene_load.argtypes = [C.c_char_p, C.POINTER(C.POINTER(frt_scene_desc))]
@@ -485,6 +489,40 @@ class MultiScene:
         return RenderStats(extra={"rays_photon": int(st.rays_photon), "photons_stored": [int(x) for x in st.photons_stored]})
 
 
+class SharedBuffer:
+    """A device buffer the node's other processes can write (frt_shared_buffer_*, CUDA IPC).  create() on the owner,
+    open() with the owner's 64-byte handle on a peer; .ptr goes to Scene.render(out_ptr=...)."""
+
+    def __init__(self, ptr: int, handle: bytes, opened: bool, nbytes: int):
+        self.ptr, self.handle, self.opened, self.nbytes = ptr, handle, opened, nbytes
+
+    @classmethod
+    def create(cls, device: int, nbytes: int) -> "SharedBuffer":
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _check(load_library().frt_shared_buffer_create(device, nbytes, C.byref(ptr), handle), "frt_shared_buffer_create")
+        return cls(int(ptr.value), handle.raw, False, nbytes)
+
+    @classmethod
+    def open(cls, device: int, handle: bytes, nbytes: int) -> "SharedBuffer":
+        ptr = C.c_void_p()
+        _check(load_library().frt_shared_buffer_open(device, C.create_string_buffer(handle, 64), C.byref(ptr)), "frt_shared_buffer_open")
+        return cls(int(ptr.value), handle, True, nbytes)
+
+    def as_cuda_array(self, shape, typestr="<f8"):
+        """An object torch.as_tensor(..., device='cuda') accepts (the owner reads its buffer through it)."""
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (self.ptr, False), "version": 2}
+        return v
+
+    def close(self):
+        if self.ptr:
+            load_library().frt_shared_buffer_close(C.c_void_p(self.ptr), int(self.opened))
+            self.ptr = 0
+
+
 class Scene:
     """A scene resident in HBM on one GPU (frt_scene)."""
 
@@ -552,13 +590,17 @@ class Scene:
 
     def render(self, rank: int = 0, world: int = 1, rows_per_block: int = 4, usteps: int = 0, vsteps: int = 0,
                jitter: int = -1, seed: int = 0, flags: int = 0, out: Optional[np.ndarray] = None,
-               download: bool = True):
-        """Render this rank's rows.  Returns (canvas[vsize, hsize, 4] float64 or None, RenderStats)."""
+               download: bool = True, out_ptr: Optional[int] = None):
+        """Render this rank's rows.  Returns (canvas[vsize, hsize, 4] float64 or None, RenderStats).  out_ptr: the address of
+        a canvas the rows are copied to instead (device memory, or a peer's SharedBuffer: no host copy is made)."""
         cam = self.desc.camera
         cfg = frt_render_cfg(device=self.device, rank=rank, world=world, rows_per_block=rows_per_block,
                              usteps=usteps, vsteps=vsteps, jitter=jitter, flags=flags, seed=seed)
         st = frt_stats()
         ptr = None
+        if out_ptr is not None:
+            _check(load_library().frt_render(self._h, C.byref(cfg), C.c_void_p(out_ptr), C.byref(st)), "frt_render")
+            return None, _stats_from(st)
         if download:
             if out is None:
                 out = np.zeros((cam.vsize, cam.hsize, 4), dtype=np.float64)

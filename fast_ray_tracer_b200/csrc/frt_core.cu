@@ -3413,6 +3413,59 @@ frt_owned_rows(const frt_scene_desc *d, const frt_render_cfg *cfg, int32_t *rows
     return n;
 }
 
+/*
+ * A device buffer the other processes of the node can write (CUDA IPC): one process per GPU gathers a frame on one device
+ * without a collective -- every rank passes the opened pointer to frt_render as its canvas and its row blocks travel over
+ * NVLink in one strided copy on its render stream, straight to where they belong.
+ */
+extern "C" int
+frt_shared_buffer_create(int device, size_t bytes, void **device_ptr, void *handle64)
+{
+    if (device_ptr == nullptr || handle64 == nullptr || bytes == 0) {
+        return frt_set_error(FRT_ERR_ARG, "frt_shared_buffer_create: bad argument");
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle travels as 64 bytes");
+    CK(cudaSetDevice(device));
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes)); /* an allocation of its own: the handle names the allocation, not an address inside one */
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return frt_set_error(FRT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, sizeof(h));
+    *device_ptr = p;
+    return FRT_OK;
+}
+
+extern "C" int
+frt_shared_buffer_open(int device, const void *handle64, void **device_ptr)
+{
+    if (device_ptr == nullptr || handle64 == nullptr) {
+        return frt_set_error(FRT_ERR_ARG, "frt_shared_buffer_open: bad argument");
+    }
+    CK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FRT_OK;
+}
+
+extern "C" int
+frt_shared_buffer_close(void *device_ptr, int opened)
+{
+    if (device_ptr == nullptr) {
+        return FRT_OK;
+    }
+    if (opened) {
+        CK(cudaIpcCloseMemHandle(device_ptr));
+    } else {
+        CK(cudaFree(device_ptr));
+    }
+    return FRT_OK;
+}
+
 /* the tree a scene is uploaded with (frt_leafruns.h): host only, no device needed */
 extern "C" int
 frt_tree_with_runs(const frt_scene_desc *d, frt_node *nodes, int cap, int32_t *roots)
@@ -4301,7 +4354,7 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
         const int rpb = cfg->rows_per_block > 0 ? cfg->rows_per_block : 4;
         const size_t row_bytes = (size_t)sc->C.hsize * 4 * sizeof(double);
         if (world == 1) {
-            CK(cudaMemcpyAsync(canvas_rgba, sc->canvas, row_bytes * sc->C.vsize, cudaMemcpyDeviceToHost, sc->stream));
+            CK(cudaMemcpyAsync(canvas_rgba, sc->canvas, row_bytes * sc->C.vsize, cudaMemcpyDefault, sc->stream));
         } else {
             /* the owned row blocks are equally spaced runs of the canvas: one strided copy for the whole blocks (a block of
              * rpb rows every world * rpb rows), one plain copy for a last, shorter block */
@@ -4309,12 +4362,12 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
             const int full_blocks = first < sc->C.vsize ? (sc->C.vsize - first) / (world * rpb) + (((sc->C.vsize - first) % (world * rpb)) >= rpb ? 1 : 0) : 0;
             if (full_blocks > 0) {
                 CK(cudaMemcpy2DAsync((char *)canvas_rgba + row_bytes * first, row_bytes * world * rpb, (char *)sc->canvas + row_bytes * first,
-                                     row_bytes * world * rpb, row_bytes * rpb, (size_t)full_blocks, cudaMemcpyDeviceToHost, sc->stream));
+                                     row_bytes * world * rpb, row_bytes * rpb, (size_t)full_blocks, cudaMemcpyDefault, sc->stream));
             }
             const int y0 = first + full_blocks * world * rpb;
             if (y0 < sc->C.vsize) {
                 CK(cudaMemcpyAsync((char *)canvas_rgba + row_bytes * y0, (char *)sc->canvas + row_bytes * y0, row_bytes * (sc->C.vsize - y0),
-                                   cudaMemcpyDeviceToHost, sc->stream));
+                                   cudaMemcpyDefault, sc->stream));
             }
         }
         CK(cudaEventRecord(e1, sc->stream));

@@ -69,6 +69,40 @@ def gather_rows(local_rows: torch.Tensor, vsize: int, rank: int, world: int, row
     return allbuf.index_select(0, plan["src"])
 
 
+class PushGather:
+    """The frame gathered on rank 0 WITHOUT a collective: rank 0 owns a device canvas the other processes can write (CUDA
+    IPC, frt_shared_buffer_*), every rank hands its pointer to frt_render as the canvas, and its row blocks travel over
+    NVLink in one strided copy on its own render stream, straight to the rows they belong to -- no packing kernel, no
+    NCCL gather, no reorder on rank 0.  A barrier tells rank 0 that every rank's copy has landed."""
+
+    def __init__(self, frt, device: int, vsize: int, hsize: int, rank: int, world: int, group=None):
+        self.rank, self.world, self.group = rank, world, group
+        self.shape = (vsize, hsize, 4)
+        nbytes = vsize * hsize * 4 * 8
+        box = [None]
+        if rank == 0:
+            self.buf = frt.SharedBuffer.create(device, nbytes)
+            box[0] = self.buf.handle
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        if rank != 0:
+            self.buf = frt.SharedBuffer.open(device, box[0], nbytes)
+        self.canvas = torch.as_tensor(self.buf.as_cuda_array(self.shape), device=f"cuda:{device}") if rank == 0 else None
+
+    def render(self, scene, rows_per_block: int = 4, **render_kw):
+        """This rank's rows rendered and pushed; returns (rank 0: the gathered canvas, a device tensor; else None, stats)."""
+        _, st = scene.render(rank=self.rank, world=self.world, rows_per_block=rows_per_block, out_ptr=self.buf.ptr, **render_kw)
+        if self.world > 1:
+            dist.barrier(group=self.group)  # frt_render returned: this rank's copy is complete; the frame when all have arrived
+        return self.canvas, st
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)  # nobody writes the buffer any more
+        self.canvas = None
+        self.buf.close()
+
+
 def reduce_canvas(frame: torch.Tensor, group=None) -> Optional[torch.Tensor]:
     """The other way to get the frame to rank 0: every rank's device canvas is zero outside the rows it rendered (the
     frame loop clears it), so the sum of the ranks' canvases IS the frame -- one in-place NCCL reduce of the full canvas

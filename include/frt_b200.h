@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define FRT_ABI_VERSION 6 /* struct layouts (scene blobs carry it); entry points added since: see FRT_API_LEVEL */
-#define FRT_API_LEVEL 3   /* 2: frt_scene_create_gen, frt_render_multi, frt_photons_estimate, frt_light_cache_checksum; 3: frt_tree_with_runs */
+#define FRT_API_LEVEL 3   /* 2: frt_scene_create_gen, frt_render_multi, frt_photons_estimate, frt_light_cache_checksum; 3: frt_tree_with_runs, frt_shared_buffer_* */
 
 enum frt_status {
     FRT_OK = 0,
@@ -354,6 +354,17 @@ int frt_canvas_download(frt_scene *scene, double *canvas_rgba);
 int frt_canvas_device_ptr(frt_scene *scene, void **device_ptr);
 /* rows owned by (rank, world): writes up to cap row indices, returns the count */
 int frt_owned_rows(const frt_scene_desc *desc, const frt_render_cfg *cfg, int32_t *rows, int cap);
+/*
+ * A device buffer other processes of the node can write through CUDA IPC (one process per GPU: the frame is gathered on
+ * one device without a collective).  The owner creates it and hands the 64-byte handle to its peers; a peer opens it and
+ * passes the pointer to frt_render as `canvas_rgba` (any pointer cudaMemcpyDefault can write is accepted there: pageable
+ * or page-locked host memory, device memory, an opened peer buffer) -- its row blocks then travel over NVLink in one
+ * strided copy on its render stream.  close: opened != 0 for a pointer from _open, 0 for the owner's.
+ */
+int frt_shared_buffer_create(int device, size_t bytes, void **device_ptr, void *handle64);
+int frt_shared_buffer_open(int device, const void *handle64, void **device_ptr);
+int frt_shared_buffer_close(void *device_ptr, int opened);
+
 /*
  * The tree frt_scene_create uploads: the reference's divided tree (group_divide, group.c:300-370, leaves its straddling
  * triangles as direct children without a box of their own) with bounding groups inserted over runs of consecutive

@@ -23,7 +23,7 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
 
     import fast_ray_tracer_b200 as frt
-    from fast_ray_tracer_b200.dist import render_distributed, trace_photons_distributed
+    from fast_ray_tracer_b200.dist import PushGather, render_distributed, trace_photons_distributed
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -34,6 +34,12 @@ def _worker(rank, world, port, q):
         canvas, _ = render_distributed(sc, rank, world)
         if rank == 0:
             out["direct"] = canvas.cpu().numpy()
+        # the same frame brought together without a collective: every rank copies its row blocks into rank 0's canvas
+        push = PushGather(frt, rank, desc.camera.vsize, desc.camera.hsize, rank, world)
+        canvas, _ = push.render(sc)
+        if rank == 0:
+            out["pushed"] = canvas.cpu().numpy()
+        push.close()
     desc = frt.SceneDesc.load(GOLDEN / "cornell_gi_64.frt")
     with frt.Scene(desc, device=rank) as sc:
         trace_photons_distributed(sc, rank, world, False, True, seed=7)
@@ -68,6 +74,7 @@ def test_two_gpus_rows_and_photon_allgather(frt):
     ref = np.load(GOLDEN / "cornell_exact_200.npz")["rgb"].astype(np.float64)
     rep = parity_report(out["direct"][..., :3], ref)
     assert rep["within_1lsb"] >= 0.999, rep
+    assert np.allclose(out["pushed"], out["direct"], rtol=0, atol=1e-12)  # peer copies (CUDA IPC) instead of the NCCL gather
     z = np.load(GOLDEN / "cornell_gi_64.npz")
     a, b = z["rgb"].astype(np.float64), z["rgb_b"].astype(np.float64)
 
@@ -135,3 +142,20 @@ def test_multi_scene_splits_rows_over_the_devices_of_one_process(frt):
     n = gi.config.gi_photon_count
     assert n <= pst.extra["photons_stored"][1] <= n + ms.n_devices * (gi.config.gi_path_length + 1)
     assert rmse(got[..., :3], a) <= 1.25 * rmse(a, b)
+
+
+def test_rows_copied_into_a_shared_device_buffer(frt):
+    """frt_render with a DEVICE canvas (the owner's side of frt_shared_buffer_*): the rows of two 'ranks' rendered one after
+    the other into one buffer are the full frame -- runs on a one-GPU box."""
+    desc = frt.SceneDesc.load(GOLDEN / "cornell_exact_96_1spp.frt")
+    cam = desc.camera
+    buf = frt.SharedBuffer.create(0, cam.vsize * cam.hsize * 4 * 8)
+    try:
+        with frt.Scene(desc) as sc:
+            want, _ = sc.render(seed=2)
+            for r in range(2):
+                sc.render(rank=r, world=2, seed=2, out_ptr=buf.ptr)
+            got = torch.as_tensor(buf.as_cuda_array((cam.vsize, cam.hsize, 4)), device="cuda:0").cpu().numpy()
+        assert np.allclose(got, want, rtol=0, atol=1e-12)
+    finally:
+        buf.close()
