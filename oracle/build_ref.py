@@ -173,6 +173,9 @@ SCENES = {
 }
 
 
+# scenes that load an OBJ file (construct_group_from_obj_file)
+OBJ_SCENES = {"teapot", "bounding_boxes", "sibenik_surrogate"}
+
 # scenes whose blob would be too large to ship on every gpurun snapshot (the light cache alone is 157 MB)
 NO_BLOB = {"cornell_shipped"}
 
@@ -204,12 +207,31 @@ def build_objects(force=False):
     hsrc = REPO / "oracle" / "ref_hooks.c"
     if force or not hooks.exists() or hooks.stat().st_mtime < hsrc.stat().st_mtime:
         run(["gcc", *CFLAGS, "-I", str(REF), "-I", str(REPO / "oracle" / "png_stub"), "-c", str(hsrc), "-o", str(hooks)])
+    objload = OBJ / "frt_objload.o"
+    osrc = LIBDIR / "csrc" / "frt_objload.c"
+    if force or not objload.exists() or objload.stat().st_mtime < osrc.stat().st_mtime:
+        run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-Wall", "-I", str(REF), "-I", str(REPO / "oracle" / "png_stub"), "-c", str(osrc),
+             "-o", str(objload)])
     shim = OBJ / "frt_shim.o"
     ssrc = LIBDIR / "csrc" / "frt_shim.c"
     abi = REPO / "include" / "frt_b200.h"  # the shim embeds FRT_ABI_VERSION and the struct layouts
     if force or not shim.exists() or shim.stat().st_mtime < max(ssrc.stat().st_mtime, abi.stat().st_mtime):
         run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-Wall", "-I", str(REF), "-I", str(REPO / "include"),
              "-I", str(REPO / "oracle" / "png_stub"), "-c", str(ssrc), "-o", str(shim)])
+
+
+def build_objload_check():
+    """oracle/_ref/objload_check: the reference's OBJ loader and the rebuilt one side by side (oracle/objload_check.c)."""
+    exe = OUT / "objload_check"
+    src = REPO / "oracle" / "objload_check.c"
+    replaced = {"renderer__renderer.o", "renderer__photon_tracer.o"}
+    host_objs = [str(obj_path(s)) for s in reference_sources() if obj_path(s).name not in replaced]
+    deps = [src, OBJ / "frt_objload.o", OBJ / "frt_shim.o"]
+    if not exe.exists() or exe.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        run(["gcc", *CFLAGS, "-I", str(REF), "-I", str(REPO / "oracle" / "png_stub"), "-o", str(exe), str(src), *host_objs,
+             str(OBJ / "frt_shim.o"), str(OBJ / "frt_objload.o"), "-Wl,--wrap=construct_group_from_obj_file", "-L", str(LIBDIR), "-lfrt_b200",
+             "-Wl,-rpath,$ORIGIN/../../fast_ray_tracer_b200", "-lm", "-lpthread", "-lz"])
+    return exe
 
 
 def build_pm_oracle():
@@ -265,6 +287,12 @@ def build_scene(name: str, force=False):
     b200_bin = OUT / f"{name}_b200"
     run(["gcc", "-o", str(b200_bin), str(main_o), *host_objs, str(OBJ / "frt_shim.o"), hooks, *WRAPS,
          "-L", str(LIBDIR), "-lfrt_b200", "-Wl,-rpath,$ORIGIN/../../fast_ray_tracer_b200", "-lm", "-lpthread", "-lz"])
+    if name in OBJ_SCENES:
+        # the drop-in with the rebuilt OBJ parse as well (csrc/frt_objload.c behind --wrap=construct_group_from_obj_file;
+        # FRT_OBJLOAD=ref sends the call back to the reference's loader): tests/test_objload.py compares the two blobs
+        run(["gcc", "-o", str(OUT / f"{name}_b200obj"), str(main_o), *host_objs, str(OBJ / "frt_shim.o"), str(OBJ / "frt_objload.o"), hooks,
+             *WRAPS, "-Wl,--wrap=construct_group_from_obj_file", "-L", str(LIBDIR), "-lfrt_b200",
+             "-Wl,-rpath,$ORIGIN/../../fast_ray_tracer_b200", "-lm", "-lpthread", "-lz"])
     return ref_bin, b200_bin
 
 
@@ -306,6 +334,7 @@ def main():
     build_objects(force=args.force)
     build_pm_oracle()
     build_canvas_oracle()
+    build_objload_check()
     for name in names:
         build_scene(name, force=args.force)
         if not args.no_blobs and name not in NO_BLOB:
