@@ -1481,6 +1481,43 @@ k_shadow_exact(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__
 #ifndef FRT_MESH_MINB
 #define FRT_MESH_MINB 6
 #endif
+/* triangle_local_intersect (triangle.c:11-45 / :122-156), the crossing only: prim_intersect's arithmetic, operation for operation */
+__device__ __forceinline__ bool
+triangle_crossing(const double *prm, const Ray &r, double &t)
+{
+    const double p1x = __ldg(prm + 0), p1y = __ldg(prm + 1), p1z = __ldg(prm + 2);
+    const double e1x = __ldg(prm + 9), e1y = __ldg(prm + 10), e1z = __ldg(prm + 11);
+    const double e2x = __ldg(prm + 12), e2y = __ldg(prm + 13), e2z = __ldg(prm + 14);
+    const double cx = r.dy * e2z - r.dz * e2y;
+    const double cy = r.dz * e2x - r.dx * e2z;
+    const double cz = r.dx * e2y - r.dy * e2x;
+    const double det = e1x * cx + e1y * cy + e1z * cz;
+    if (fabs(det) < FRT_EPS) {
+        return false;
+    }
+    const double f = 1.0 / det;
+    const double sx = r.ox - p1x, sy = r.oy - p1y, sz = r.oz - p1z;
+    const double u = f * (sx * cx + sy * cy + sz * cz);
+    if (u < 0 || u > 1) {
+        return false;
+    }
+    const double qx = sy * e1z - sz * e1y;
+    const double qy = sz * e1x - sx * e1z;
+    const double qz = sx * e1y - sy * e1x;
+    const double v = f * (r.dx * qx + r.dy * qy + r.dz * qz);
+    if (v < 0 || (u + v) > 1) {
+        return false;
+    }
+    t = f * (e2x * qx + e2y * qy + e2z * qz);
+    return true;
+}
+
+__device__ __noinline__ int
+prim_intersect_inv_call(int type, const double *prm, const Ray &r, double t[4], double uv[2])
+{
+    return prim_intersect_inv(type, prm, r, inv_dir(r), t, uv);
+}
+
 template <bool COUNT, bool HAS_CSG>
 __global__ void __launch_bounds__(128, FRT_MESH_MINB)
 k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp_base, size_t tmp_stride,
@@ -1510,8 +1547,8 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
 
     bool active = false, exhausted = false;
     unsigned int h = 0;
-    Ray wr{}, lr{};
-    InvDir inv{};
+    Ray lr{}; /* the ray in the frame of transform cur_xf_d; the world ray is re-derived from its item where it is needed again */
+    unsigned long long my_item = 0;
     FrameF w{}, lf{};
     double dist = 0.0;
     float omax = 0.f, eo_o = 0.f, ed_w = 0.f;
@@ -1544,8 +1581,10 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
                 const frt_light &L = S.lights[first_light + lk];
                 tmp = tmp_base + (size_t)lk * tmp_stride;
                 double dist2;
+                Ray wr;
                 shadow_item(S, recs, tmp, S.lpoints + 3 * L.point_offset, L.num_samples, item - cum[lk], false, h, set_a, wr, dist2);
                 if (set_a >= 0) {
+                    my_item = item;
                     dist = normalise_shadow_ray(wr, dist2);
                     w.ox = (float)wr.ox;
                     w.oy = (float)wr.oy;
@@ -1560,7 +1599,6 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
                     frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
                     lf = w;
                     lr = wr;
-                    inv = inv_dir(wr);
                     cur_xf_f = cur_xf_d = 0;
                     i = root;
                     sp = 0;
@@ -1574,6 +1612,22 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             continue;
         }
         bool done = false, result = false;
+        /* the world ray of this lane's item again (a leaf under another transform, the verifying build): same loads, same
+         * operations as at refill */
+        auto world_ray = [&]() {
+            int lk = 0, set_a;
+#pragma unroll
+            for (int k = 1; k < FRT_MESH_LIGHTS; ++k) {
+                lk += my_item >= cum[k] ? 1 : 0;
+            }
+            const frt_light &L = S.lights[first_light + lk];
+            Ray wr;
+            double dist2;
+            unsigned int hh;
+            shadow_item(S, recs, tmp, S.lpoints + 3 * L.point_offset, L.num_samples, my_item - cum[lk], false, hh, set_a, wr, dist2);
+            normalise_shadow_ray(wr, dist2);
+            return wr;
+        };
         /* close every CSG whose left / right operand just ended (csg.c:104-118, :43-71) */
         auto close_frames = [&]() {
             while (HAS_CSG && sp > 0 && !done) {
@@ -1695,17 +1749,30 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             }
             if (xform != cur_xf_d) {
                 cur_xf_d = xform;
+                const Ray wr = world_ray();
                 if (cur_xf_d == 0) {
                     lr = wr;
                 } else {
                     lr = ray_to_local(S, cur_xf_d, wr);
                     if (COUNT) n_flops += FRT_COST_XFORM;
                 }
-                inv = inv_dir(lr);
             }
-            double t[4], uv[2];
-            const int k = prim_intersect_inv(type, S.params + (param < 0 ? 0 : param), lr, inv, t, uv);
-            if (!HAS_CSG || sp == 0) {
+            const bool tri = type == FRT_TRIANGLE || type == FRT_SMOOTH_TRIANGLE;
+            double t[4], uv[2], t_tri = 0.0;
+            int k;
+            if (tri) {
+                /* the leaf of a mesh: Moeller-Trumbore inline, one crossing at most; everything else is a call, so that the
+                 * quartic solver and the quadric bodies do not size this kernel's registers */
+                k = triangle_crossing(S.params + param, lr, t_tri) ? 1 : 0;
+            } else {
+                k = prim_intersect_inv_call(type, S.params + (param < 0 ? 0 : param), lr, t, uv);
+            }
+            if ((!HAS_CSG || sp == 0) && tri) {
+                if (k && !(t_tri <= 0)) {
+                    result = (flags & FRT_FN_CASTS) && t_tri > 0 && t_tri < dist;
+                    done = true;
+                }
+            } else if (!HAS_CSG || sp == 0) {
                 bool stop = false;
                 double tmin = CUDART_INF;
                 for (int j = 0; j < k; ++j) {
@@ -1719,6 +1786,9 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
                     done = true;
                 }
             } else {
+                if (tri) {
+                    t[0] = t_tri;
+                }
                 for (int j = 0; j < k; ++j) {
                     if (n == FRT_CSG_CAP) {
                         overflow = 1;
@@ -1738,7 +1808,7 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         if (done) {
             if (verify) { /* the mixed walk is checked against the pure FP64 walk ray by ray */
                 unsigned long long dn = 0, df = 0;
-                const bool ref = trace_shadow<false>(S, wr, dist, &overflow, &dn, &df);
+                const bool ref = trace_shadow<false>(S, world_ray(), dist, &overflow, &dn, &df);
                 if (ref != result) {
                     ++n_mismatch;
                     result = ref;
