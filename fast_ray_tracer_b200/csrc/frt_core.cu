@@ -406,7 +406,7 @@ material_color(const DScene &S, int map, const double *flat, int leaf, const dou
  */
 template <bool MAPS, bool REFRACT>
 __global__ void __launch_bounds__(128, (MAPS || REFRACT) ? 4 : 5)
-k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counters *cnt, int level)
+k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counters *cnt, int level, int rec_level)
 {
     static_assert(sizeof(LightRec) % 16 == 0, "LightRec is copied as 16-byte words");
     constexpr int FRT_REC_WORDS = (int)(sizeof(LightRec) / 16);
@@ -581,7 +581,7 @@ k_shade(DScene S, FrameParams F, RayQ q, HitQ h, RayQ qn, LightRec *recs, Counte
          * different sectors, none of them whole (152-byte records): the L2 has to fetch every sector it is about to
          * overwrite.  Staged through shared memory the same bytes leave as 256-byte runs. */
         __syncwarp();
-        unsigned int slot = warp_append(&cnt->n_hits[level], want_rec);
+        unsigned int slot = warp_append(&cnt->n_hits[rec_level], want_rec); /* rec_level = 0 for every level: one list of hits, one light stage */
         {
             const unsigned int wmask = __ballot_sync(0xffffffffu, want_rec);
             if (wmask) {
@@ -4023,18 +4023,30 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
         k_raygen<<<rg_blocks, 256, 0, s>>>(C, F, sc->q[0], sc->cnt, (unsigned int)first, n);
         tock(tk);
         ++launches;
+        /* The hits of EVERY level go into one list and meet the lights in one stage (merge_levels): the reflected /
+         * refracted rays of a Cornell frame are 0.5 % of its hits, but lit on their own they cost six more kernels whose
+         * duration is mostly launch, ramp and tail -- a sixth of the frame of one of eight GPUs.  Extend / shade run level by
+         * level (each waits for the count the previous k_shade leaves), the light stage once at the end.  With global
+         * illumination the stages stay per level (the final gather's random streams are keyed on the level). */
+        const bool merge_levels = !F.use_gi && sc->h_nrays != nullptr && env_int("FRT_MERGE_LEVELS", 1) != 0;
         for (int level = 0; level <= F.path_length; ++level) {
+            bool trace = true;
             if (level > 0 && sc->h_nrays != nullptr) {
-                /* the count was copied right behind the previous k_shade; the stream is still busy with that level's light
-                 * stage, so this wait costs nothing -- and the empty tail of the recursion (Cornell: levels 2..5, ~9 launches
+                /* the count was copied right behind the previous k_shade; with a light stage per level the stream is still busy
+                 * with it, so this wait costs nothing -- and the empty tail of the recursion (Cornell: levels 2..5, ~9 launches
                  * of full grids each) is never enqueued */
                 CK(cudaEventSynchronize(sc->nrays_ev));
                 if (sc->h_nrays[0] == 0) {
-                    break;
+                    if (!merge_levels) {
+                        break;
+                    }
+                    trace = false; /* nothing left to trace: on to the one light stage */
                 }
             }
             RayQ &qi = sc->q[level & 1];
             RayQ &qo = sc->q[(level + 1) & 1];
+            const int rec_level = merge_levels ? 0 : level;
+            if (trace) {
             /* level 0 has n rays; deeper levels read their count on the device: size the grid for the worst case
              * the level can hold, but never more than a few waves */
             int ex_blocks = sm_blocks * 8;
@@ -4047,11 +4059,11 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             tock(tk);
             tk = tick(FRT_ST_SHADE);
             if (sc->has_maps) {
-                k_shade<true, true><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+                k_shade<true, true><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level, rec_level);
             } else if (sc->has_refraction) {
-                k_shade<false, true><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+                k_shade<false, true><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level, rec_level);
             } else {
-                k_shade<false, false><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level);
+                k_shade<false, false><<<sm_blocks * 8, 128, 0, s>>>(sc->S, F, qi, sc->hq, qo, sc->recs, sc->cnt, level, rec_level);
             }
             tock(tk);
             launches += 2;
@@ -4059,6 +4071,11 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                 CK(cudaMemcpyAsync(sc->h_nrays, &sc->cnt->n_rays[level + 1], sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
                 CK(cudaEventRecord(sc->nrays_ev, s));
             }
+            }
+            if (merge_levels && trace && level < F.path_length) {
+                continue; /* the next level first */
+            }
+            const int hl = rec_level; /* the level whose hit list the light stage reads */
             if (F.use_gi) {
                 CK(cudaMemsetAsync(sc->acc_amb, 0, sizeof(double) * 3 * (size_t)sc->acc_cap, s));
                 CK(cudaMemsetAsync(sc->acc_fg, 0, sizeof(double) * 3 * (size_t)sc->acc_cap, s));
@@ -4078,24 +4095,24 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                     const int nl = std::min(FRT_MESH_LIGHTS, sc->S.n_lights - l0);
                     tk = tick(FRT_ST_LIGHT_PRE);
                     for (int k = 0; k < nl; ++k) {
-                        launch_light_pre(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
+                        launch_light_pre(sc, F, blocks, hl, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
                     }
                     tock(tk);
                     if (wait_for_upload(sc, s) != FRT_OK) return FRT_ERR_CUDA;
                     CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
                     tk = tick(FRT_ST_SHADOW_RAY);
                     if (count) {
-                        launch_shadow_mesh<true>(sc, mblocks, s, F, sc->ltmp_multi, sc->capacity, level, l0, nl, m_inner, m_refill);
+                        launch_shadow_mesh<true>(sc, mblocks, s, F, sc->ltmp_multi, sc->capacity, hl, l0, nl, m_inner, m_refill);
                     } else {
-                        launch_shadow_mesh<false>(sc, mblocks, s, F, sc->ltmp_multi, sc->capacity, level, l0, nl, m_inner, m_refill);
+                        launch_shadow_mesh<false>(sc, mblocks, s, F, sc->ltmp_multi, sc->capacity, hl, l0, nl, m_inner, m_refill);
                     }
                     tock(tk);
                     tk = tick(FRT_ST_LIGHT_FINAL);
                     for (int k = 0; k < nl; ++k) {
                         if (F.flags & FRT_FLAG_F64_SHADING) {
-                            launch_light_final<double>(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
+                            launch_light_final<double>(sc, F, blocks, hl, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
                         } else {
-                            launch_light_final<float>(sc, F, blocks, level, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
+                            launch_light_final<float>(sc, F, blocks, hl, l0 + k, gw[l0 + k], sc->ltmp_multi + (size_t)k * sc->capacity);
                         }
                     }
                     tock(tk);
@@ -4106,16 +4123,16 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                 for (int li = 0; li < sc->S.n_lights; ++li) {
                     const int blocks = sm_blocks * 8;
                     tk = tick(FRT_ST_LIGHT_PRE);
-                    launch_light_pre(sc, F, blocks, level, li, gw[li], sc->ltmp);
+                    launch_light_pre(sc, F, blocks, hl, li, gw[li], sc->ltmp);
                     tock(tk);
                     if (wait_for_upload(sc, s) != FRT_OK) return FRT_ERR_CUDA;
                     const bool count = (F.flags & FRT_FLAG_COUNT_RAYS) != 0;
                     if (F.flags & FRT_FLAG_F64_SHADOW) {
                         tk = tick(FRT_ST_SHADOW_RAY);
                         if (count) {
-                            k_shadow_exact<true, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_exact<true, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, hl, li, sc->dq, sc->dq_cap);
                         } else {
-                            k_shadow_exact<false, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_exact<false, true><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, hl, li, sc->dq, sc->dq_cap);
                         }
                         tock(tk);
                         launches += 1;
@@ -4123,9 +4140,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                         CK(cudaMemsetAsync(&sc->cnt->mesh_next, 0, sizeof(unsigned long long), s));
                         tk = tick(FRT_ST_SHADOW_RAY);
                         if (count) {
-                            launch_shadow_mesh<true>(sc, mblocks, s, F, sc->ltmp, 0, level, li, 1, m_inner, m_refill);
+                            launch_shadow_mesh<true>(sc, mblocks, s, F, sc->ltmp, 0, hl, li, 1, m_inner, m_refill);
                         } else {
-                            launch_shadow_mesh<false>(sc, mblocks, s, F, sc->ltmp, 0, level, li, 1, m_inner, m_refill);
+                            launch_shadow_mesh<false>(sc, mblocks, s, F, sc->ltmp, 0, hl, li, 1, m_inner, m_refill);
                         }
                         tock(tk);
                         launches += 1;
@@ -4145,9 +4162,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     do {                                                                                                                                          \
         tk = tick(FRT_ST_SHADOW_SHAFT);                                                                                                           \
         if (F.flags & FRT_FLAG_F64_SHAFT) {                                                                                                       \
-            k_shadow_bulk<M, double><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pprog, retry, bulk_on, split_on); \
+            k_shadow_bulk<M, double><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, hl, li, sc->pending, pprog, retry, bulk_on, split_on); \
         } else {                                                                                                                                  \
-            k_shadow_bulk<M, float><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->pending, pprog, retry, bulk_on, split_on); \
+            k_shadow_bulk<M, float><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, hl, li, sc->pending, pprog, retry, bulk_on, split_on); \
         }                                                                                                                                         \
         if (split_on) {                                                                                                                           \
             if (F.flags & FRT_FLAG_F64_SHAFT) {                                                                                                   \
@@ -4179,23 +4196,26 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
 #undef FRT_SHADOW_STAGE
                         tk = tick(FRT_ST_SHADOW_EXACT);
                         if (count) {
-                            k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_exact<true, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, hl, li, sc->dq, sc->dq_cap);
                         } else {
-                            k_shadow_exact<false, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, level, li, sc->dq, sc->dq_cap);
+                            k_shadow_exact<false, false><<<blocks, 256, 0, s>>>(sc->S, sc->SF, F, sc->recs, sc->ltmp, sc->cnt, hl, li, sc->dq, sc->dq_cap);
                         }
                         tock(tk);
                         launches += 3;
                     }
                     tk = tick(FRT_ST_LIGHT_FINAL);
                     if (F.flags & FRT_FLAG_F64_SHADING) {
-                        launch_light_final<double>(sc, F, blocks, level, li, gw[li], sc->ltmp);
+                        launch_light_final<double>(sc, F, blocks, hl, li, gw[li], sc->ltmp);
                     } else {
-                        launch_light_final<float>(sc, F, blocks, level, li, gw[li], sc->ltmp);
+                        launch_light_final<float>(sc, F, blocks, hl, li, gw[li], sc->ltmp);
                     }
                     tock(tk);
                     launches += 2;
                     ++light_launches;
                 }
+            }
+            if (merge_levels) {
+                break; /* every level has been traced and lit */
             }
             if (F.use_gi) {
                 /* the GI block of shade_hit for the hits of this level, in batches that fit the request queue */
