@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/frt_b200.h"
@@ -79,6 +80,7 @@ struct Builder {
     std::vector<Box> boxes;   /* scratch: boxes of the run at hand */
     std::vector<Box> suffix;
     long inserted = 0;
+    int run_min = FRT_RUN_MIN, run_leaf = FRT_RUN_LEAF;
     bool bad = false; /* the description is not the tree it claims to be: upload it as it is */
 
     static bool is_tri(const frt_node &n) { return n.type == FRT_TRIANGLE || n.type == FRT_SMOOTH_TRIANGLE; }
@@ -118,7 +120,7 @@ struct Builder {
             out.push_back(n);
             ++inserted;
         }
-        if (b - a <= FRT_RUN_LEAF) {
+        if (b - a <= run_leaf) {
             for (int j = a; j < b; ++j) {
                 copy_node(run[j], g);
                 out.back().skip = (int32_t)out.size();
@@ -173,7 +175,7 @@ struct Builder {
                     ++e;
                 }
             }
-            if (e - k >= FRT_RUN_MIN) {
+            if (e - k >= (size_t)run_min) {
                 std::vector<int> run(kids.begin() + (long)k, kids.begin() + (long)e);
                 boxes.resize(run.size());
                 for (size_t j = 0; j < run.size(); ++j) {
@@ -215,6 +217,12 @@ augment(const frt_scene_desc *d, std::vector<frt_node> &nodes, std::vector<int32
     }
     Builder b;
     b.d = d;
+    if (const char *v = getenv("FRT_RUN_MIN")) { /* development aid: the two thresholds at run time */
+        b.run_min = std::max(2, atoi(v));
+    }
+    if (const char *v = getenv("FRT_RUN_LEAF")) {
+        b.run_leaf = std::max(1, atoi(v));
+    }
     b.map.assign((size_t)d->n_nodes, -1);
     b.out.reserve((size_t)d->n_nodes + (size_t)d->n_nodes / 2);
     roots.clear();
