@@ -205,7 +205,7 @@ def reference_arm(args) -> dict:
 # ---------------------------------------------------------------------------------------------- CUDA arm
 
 
-TRAFFIC_FILES = [REPO / "profiles" / "r2_traffic_k_shadow_f32.json", REPO / "profiles" / "r1n_traffic_k_shadow_f32.json"]
+TRAFFIC_FILES = [REPO / "profiles" / "r2c_traffic_k_shadow_f32.json", REPO / "profiles" / "r2_traffic_k_shadow_f32.json", REPO / "profiles" / "r1n_traffic_k_shadow_f32.json"]
 FP32_PEAK_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12  # 148 SMs x 128 FP32 lanes x FMA x 1.965 GHz = 74.4 TFLOP/s
 
 
