@@ -1529,12 +1529,29 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
     /* the lights first_light .. first_light + n_lights - 1 (<= FRT_MESH_LIGHTS) share the launch: items are light-major,
      * light k's (hit, sample) pairs follow light k - 1's; its per-hit records are tmp_base + k * tmp_stride */
     const unsigned int nh = min(cnt->n_hits[level], F.capacity);
-    unsigned long long cum[FRT_MESH_LIGHTS + 1];
-    cum[0] = 0;
-    for (int k = 0; k < FRT_MESH_LIGHTS; ++k) {
-        cum[k + 1] = cum[k] + (k < n_lights ? (unsigned long long)nh * (unsigned int)S.lights[first_light + k].num_samples : 0ull);
-    }
-    const unsigned long long total = cum[FRT_MESH_LIGHTS];
+    /* items in front of light k's: recomputed where it is needed (refill, a leaf under another transform) instead of nine
+     * 64-bit values kept alive through the walk -- the walk's own state has to fit the registers */
+    auto items_before = [&](int k) {
+        unsigned long long c = 0;
+        for (int j = 0; j < k && j < n_lights; ++j) {
+            c += (unsigned long long)nh * (unsigned int)S.lights[first_light + j].num_samples;
+        }
+        return c;
+    };
+    auto light_of = [&](unsigned long long item, unsigned long long &before) {
+        int lk = 0;
+        before = 0;
+        for (int j = 0; j + 1 < n_lights; ++j) {
+            const unsigned long long c = (unsigned long long)nh * (unsigned int)S.lights[first_light + j].num_samples;
+            if (item < before + c) {
+                break;
+            }
+            before += c;
+            lk = j + 1;
+        }
+        return lk;
+    };
+    const unsigned long long total = items_before(FRT_MESH_LIGHTS);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&cnt->rays_per_ray, total);
     }
@@ -1549,9 +1566,20 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
     unsigned int h = 0;
     Ray lr{}; /* the ray in the frame of transform cur_xf_d; the world ray is re-derived from its item where it is needed again */
     unsigned long long my_item = 0;
-    FrameF w{}, lf{};
+    FrameF lf{}; /* the ONE current frame: the world ray, or the ray in the frame of transform cur_xf_f */
+    float wox = 0.f, woy = 0.f, woz = 0.f, wdx = 0.f, wdy = 0.f, wdz = 0.f; /* the world ray in FP32: frames are rebuilt from it */
     double dist = 0.0;
     float omax = 0.f, eo_o = 0.f, ed_w = 0.f;
+    auto world_frame = [&](FrameF &f) {
+        f.ox = wox;
+        f.oy = woy;
+        f.oz = woz;
+        f.dx = wdx;
+        f.dy = wdy;
+        f.dz = wdz;
+        const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, fmaf(SF.ealign, omax, eo_o));
+        frame_finish(f, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
+    };
     int cur_xf_f = 0, cur_xf_d = 0, i = 0, sp = 0, n = 0;
     CsgHit buf[HAS_CSG ? FRT_CSG_CAP : 1]; /* a tree without CSG nodes (OBJ meshes) needs neither list nor stack */
     Frame st[HAS_CSG ? FRT_CSG_DEPTH : 1];
@@ -1573,31 +1601,27 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             exhausted = base + (unsigned long long)want >= total;
             const unsigned long long item = base + (unsigned int)__popc(idle & ((1u << lane) - 1u));
             if (!active && item < total) {
-                int set_a, lk = 0;
-#pragma unroll
-                for (int k = 1; k < FRT_MESH_LIGHTS; ++k) {
-                    lk += item >= cum[k] ? 1 : 0;
-                }
+                int set_a;
+                unsigned long long before;
+                const int lk = light_of(item, before);
                 const frt_light &L = S.lights[first_light + lk];
                 tmp = tmp_base + (size_t)lk * tmp_stride;
                 double dist2;
                 Ray wr;
-                shadow_item(S, recs, tmp, S.lpoints + 3 * L.point_offset, L.num_samples, item - cum[lk], false, h, set_a, wr, dist2);
+                shadow_item(S, recs, tmp, S.lpoints + 3 * L.point_offset, L.num_samples, item - before, false, h, set_a, wr, dist2);
                 if (set_a >= 0) {
                     my_item = item;
                     dist = normalise_shadow_ray(wr, dist2);
-                    w.ox = (float)wr.ox;
-                    w.oy = (float)wr.oy;
-                    w.oz = (float)wr.oz;
-                    w.dx = (float)wr.dx;
-                    w.dy = (float)wr.dy;
-                    w.dz = (float)wr.dz;
-                    omax = fmaxf(fmaxf(fabsf(w.ox), fabsf(w.oy)), fabsf(w.oz));
+                    wox = (float)wr.ox;
+                    woy = (float)wr.oy;
+                    woz = (float)wr.oz;
+                    wdx = (float)wr.dx;
+                    wdy = (float)wr.dy;
+                    wdz = (float)wr.dz;
+                    omax = fmaxf(fmaxf(fabsf(wox), fabsf(woy)), fabsf(woz));
                     eo_o = 2.0f * FRT_F32_U * omax;
-                    const float eo_w = fmaf(2.0f * FRT_F32_U, SF.bmax, fmaf(SF.ealign, omax, eo_o));
                     ed_w = FRT_F32_G + SF.ealign; /* the FP64 unit direction rounded to FP32 */
-                    frame_finish(w, eo_w, eo_w, eo_w, ed_w, ed_w, ed_w);
-                    lf = w;
+                    world_frame(lf);
                     lr = wr;
                     cur_xf_f = cur_xf_d = 0;
                     i = root;
@@ -1615,16 +1639,14 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
         /* the world ray of this lane's item again (a leaf under another transform, the verifying build): same loads, same
          * operations as at refill */
         auto world_ray = [&]() {
-            int lk = 0, set_a;
-#pragma unroll
-            for (int k = 1; k < FRT_MESH_LIGHTS; ++k) {
-                lk += my_item >= cum[k] ? 1 : 0;
-            }
+            int set_a;
+            unsigned long long before;
+            const int lk = light_of(my_item, before);
             const frt_light &L = S.lights[first_light + lk];
             Ray wr;
             double dist2;
             unsigned int hh;
-            shadow_item(S, recs, tmp, S.lpoints + 3 * L.point_offset, L.num_samples, my_item - cum[lk], false, hh, set_a, wr, dist2);
+            shadow_item(S, recs, tmp, S.lpoints + 3 * L.point_offset, L.num_samples, my_item - before, false, hh, set_a, wr, dist2);
             normalise_shadow_ray(wr, dist2);
             return wr;
         };
@@ -1708,15 +1730,19 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
             if (!(flags & FRT_FN_NOCULL)) {
                 const int xf = __float_as_int(q0.z);
                 float tn_lo, tn_hi, tf_lo, tf_hi;
-                if (xf == 0) {
-                    box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-                } else {
-                    if (xf != cur_xf_f) {
-                        cur_xf_f = xf;
+                /* ONE current frame, replaced when a node names another one: choosing between two frames per node kept both
+                 * in local memory (a pointer select: 14 % of the kernel's instructions were local loads) */
+                if (xf != cur_xf_f) {
+                    cur_xf_f = xf;
+                    if (xf == 0) {
+                        world_frame(lf);
+                    } else {
+                        FrameF w;
+                        world_frame(w);
                         frame_local(lf, SF, xf, w, omax, eo_o, ed_w);
                     }
-                    box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
                 }
+                box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
                 miss = tn_lo > tf_hi || ((!HAS_CSG || sp == 0) && tf_hi < 0.0f);
             }
             if (miss) {
@@ -3876,8 +3902,38 @@ frt_env_int(const char *name, int dflt)
 static int launch_knn(frt_scene *sc, cudaStream_t s, const GIParams &G, GQuery *q, unsigned int *q_n, unsigned int q_cap, double *acc_amb,
                       double *acc_fg, int *found, int mode, int *launches);
 
+/* The rows this rank owns leave for the caller's canvas (host memory, device memory, a peer's shared buffer) behind the frame's
+ * last kernel: bracketed by ev[2] / ev[3], not waited for here.  The caller's other rows stay untouched. */
 static int
-render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned int chunk_samples, unsigned int cap_factor)
+enqueue_owned_rows(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba)
+{
+    CK(cudaEventRecord(sc->ev[2], sc->stream));
+    const int world = cfg->world > 0 ? cfg->world : 1;
+    const int rpb = cfg->rows_per_block > 0 ? cfg->rows_per_block : 4;
+    const size_t row_bytes = (size_t)sc->C.hsize * 4 * sizeof(double);
+    if (world == 1) {
+        CK(cudaMemcpyAsync(canvas_rgba, sc->canvas, row_bytes * sc->C.vsize, cudaMemcpyDefault, sc->stream));
+    } else {
+        /* the owned row blocks are equally spaced runs of the canvas: one strided copy for the whole blocks (a block of
+         * rpb rows every world * rpb rows), one plain copy for a last, shorter block */
+        const int first = cfg->rank * rpb;
+        const int full_blocks = first < sc->C.vsize ? (sc->C.vsize - first) / (world * rpb) + (((sc->C.vsize - first) % (world * rpb)) >= rpb ? 1 : 0) : 0;
+        if (full_blocks > 0) {
+            CK(cudaMemcpy2DAsync((char *)canvas_rgba + row_bytes * first, row_bytes * world * rpb, (char *)sc->canvas + row_bytes * first,
+                                 row_bytes * world * rpb, row_bytes * rpb, (size_t)full_blocks, cudaMemcpyDefault, sc->stream));
+        }
+        const int y0 = first + full_blocks * world * rpb;
+        if (y0 < sc->C.vsize) {
+            CK(cudaMemcpyAsync((char *)canvas_rgba + row_bytes * y0, (char *)sc->canvas + row_bytes * y0, row_bytes * (sc->C.vsize - y0),
+                               cudaMemcpyDefault, sc->stream));
+        }
+    }
+    CK(cudaEventRecord(sc->ev[3], sc->stream));
+    return FRT_OK;
+}
+
+static int
+render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned int chunk_samples, unsigned int cap_factor, double *canvas_rgba)
 {
     const frt_config &g = sc->cfg;
     DCamera C = sc->C;
@@ -4001,6 +4057,7 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
     };
 
     CK(cudaEventRecord(sc->ev[0], s));
+    bool frame_end_recorded = false;
     CK(cudaMemsetAsync(sc->canvas, 0, cbytes, s));
 
     const std::vector<int> &gw = sc->light_gw; /* lanes per hit in k_light_pre / k_light_final, chosen per light at upload */
@@ -4267,6 +4324,16 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
                 ++launches;
             }
         }
+        if (canvas_rgba != nullptr && first + chunk >= total) {
+            /* the frame's rows travel behind its last kernel, in front of the one wait of the frame (the counters below): a
+             * frame that overflowed its queues is re-run and copied again.  The frame's own time ends here. */
+            CK(cudaEventRecord(sc->ev[1], s));
+            frame_end_recorded = true;
+            const int rc_rows = enqueue_owned_rows(sc, cfg, canvas_rgba);
+            if (rc_rows != FRT_OK) {
+                return rc_rows;
+            }
+        }
         Counters hc;
         CK(cudaMemcpyAsync(&hc, sc->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -4300,7 +4367,9 @@ render_once(frt_scene *sc, const frt_render_cfg *cfg, frt_stats *st, unsigned in
             break;
         }
     }
-    CK(cudaEventRecord(sc->ev[1], s));
+    if (!frame_end_recorded) {
+        CK(cudaEventRecord(sc->ev[1], s));
+    }
     CK(cudaEventSynchronize(sc->ev[1]));
     CK(cudaGetLastError());
     float ms = 0.f;
@@ -4405,7 +4474,7 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
     }
     int rc;
     for (;;) {
-        rc = render_once(sc, cfg, &st, chunk, factor);
+        rc = render_once(sc, cfg, &st, chunk, factor, canvas_rgba);
         if (rc != -1) {
             break;
         }
@@ -4437,33 +4506,10 @@ frt_render(frt_scene *sc, const frt_render_cfg *cfg, double *canvas_rgba, frt_st
         }
     }
     if (canvas_rgba != nullptr) {
-        cudaEvent_t e0 = sc->ev[2], e1 = sc->ev[3];
-        CK(cudaEventRecord(e0, sc->stream));
-        /* only the rows this rank owns are written back; the caller's other rows stay untouched */
-        const int world = cfg->world > 0 ? cfg->world : 1;
-        const int rpb = cfg->rows_per_block > 0 ? cfg->rows_per_block : 4;
-        const size_t row_bytes = (size_t)sc->C.hsize * 4 * sizeof(double);
-        if (world == 1) {
-            CK(cudaMemcpyAsync(canvas_rgba, sc->canvas, row_bytes * sc->C.vsize, cudaMemcpyDefault, sc->stream));
-        } else {
-            /* the owned row blocks are equally spaced runs of the canvas: one strided copy for the whole blocks (a block of
-             * rpb rows every world * rpb rows), one plain copy for a last, shorter block */
-            const int first = cfg->rank * rpb;
-            const int full_blocks = first < sc->C.vsize ? (sc->C.vsize - first) / (world * rpb) + (((sc->C.vsize - first) % (world * rpb)) >= rpb ? 1 : 0) : 0;
-            if (full_blocks > 0) {
-                CK(cudaMemcpy2DAsync((char *)canvas_rgba + row_bytes * first, row_bytes * world * rpb, (char *)sc->canvas + row_bytes * first,
-                                     row_bytes * world * rpb, row_bytes * rpb, (size_t)full_blocks, cudaMemcpyDefault, sc->stream));
-            }
-            const int y0 = first + full_blocks * world * rpb;
-            if (y0 < sc->C.vsize) {
-                CK(cudaMemcpyAsync((char *)canvas_rgba + row_bytes * y0, (char *)sc->canvas + row_bytes * y0, row_bytes * (sc->C.vsize - y0),
-                                   cudaMemcpyDefault, sc->stream));
-            }
-        }
-        CK(cudaEventRecord(e1, sc->stream));
-        CK(cudaEventSynchronize(e1));
+        /* enqueued by render_once behind the frame's last kernel and complete by now (it waited for the stream) */
+        CK(cudaEventSynchronize(sc->ev[3]));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
+        CK(cudaEventElapsedTime(&ms, sc->ev[2], sc->ev[3]));
         st.download_ms = ms;
     }
     if (stats != nullptr) {

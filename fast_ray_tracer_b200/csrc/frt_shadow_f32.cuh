@@ -1272,6 +1272,24 @@ trace_shadow_bulk(const DSceneF &SF, int root, unsigned int relevant, const Shaf
 }
 
 /*
+ * The walks of the mesh path keep ONE current frame -- the world ray, or the ray in the frame of the transform a node names
+ * -- and replace it when a node names another one.  (Choosing between a world and a local frame per node made the compiler
+ * keep both in local memory behind a pointer: 14 % of k_shadow_mesh's instructions were local loads.)
+ */
+__device__ __forceinline__ void
+current_frame(FrameF &cf, int &cur_xf, const DSceneF &SF, int xf, const FrameF &w, float omax, float eo, float ed_w)
+{
+    if (xf != cur_xf) {
+        cur_xf = xf;
+        if (xf == 0) {
+            cf = w;
+        } else {
+            frame_local(cf, SF, xf, w, omax, eo, ed_w);
+        }
+    }
+}
+
+/*
  * A triangle leaf's mirror record holds the bounds of its vertices (FRT_FN_LEAFBOX): true when the ray surely misses
  * them, surely has them behind its origin (`behind`: no crossing at t <= 0 is wanted), or surely enters them beyond
  * `t_best`.  The reference tests no box in front of a triangle (triangle.c:11-45); a ray that misses the box of the
@@ -1283,15 +1301,8 @@ leaf_box_missed(const DSceneF &SF, const float4 q0, const float4 lo, const float
 {
     const int xf = __float_as_int(q0.z);
     float tn_lo, tn_hi, tf_lo, tf_hi;
-    if (xf == 0) {
-        box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-    } else {
-        if (xf != cur_xf_f) {
-            cur_xf_f = xf;
-            frame_local(lf, SF, xf, w, omax, eo, ed_w);
-        }
-        box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-    }
+    current_frame(lf, cur_xf_f, SF, xf, w, omax, eo, ed_w);
+    box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
     return tn_lo > tf_hi || (behind && tf_hi < 0.0f) || (double)tn_lo > t_best;
 }
 
@@ -1339,15 +1350,8 @@ trace_shadow_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, double dis
             if (!(flags & FRT_FN_NOCULL)) {
                 const int xf = __float_as_int(q0.z);
                 float tn_lo, tn_hi, tf_lo, tf_hi;
-                if (xf == 0) {
-                    box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-                } else {
-                    if (xf != cur_xf_f) {
-                        cur_xf_f = xf;
-                        frame_local(lf, SF, xf, w, omax, eo_w, ed_w);
-                    }
-                    box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-                }
+                current_frame(lf, cur_xf_f, SF, xf, w, omax, eo_w, ed_w);
+                box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
                 miss = tn_lo > tf_hi || (sp == 0 && tf_hi < 0.0f);
             }
             if (miss) {
@@ -1513,15 +1517,8 @@ trace_closest_mixed(const DScene &S, const DSceneF &SF, const Ray &wr, int *over
                 const float4 hi = __ldg(fnodes + 3 * i + 2);
                 const int xf = __float_as_int(q0.z);
                 float tn_lo, tn_hi, tf_lo, tf_hi;
-                if (xf == 0) {
-                    box_f(w, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-                } else {
-                    if (xf != cur_xf_f) {
-                        cur_xf_f = xf;
-                        frame_local(lf, SF, xf, w, omax, eo_o, ed_w);
-                    }
-                    box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
-                }
+                current_frame(lf, cur_xf_f, SF, xf, w, omax, eo_o, ed_w);
+                box_f(lf, lo, hi, tn_lo, tn_hi, tf_lo, tf_hi);
                 const bool miss = tn_lo > tf_hi || tf_hi < 0.0f || (double)tn_lo > best.t;
                 if (type == FRT_GROUP) {
                     i = miss ? skip : i + 1;

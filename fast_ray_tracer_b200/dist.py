@@ -69,11 +69,52 @@ def gather_rows(local_rows: torch.Tensor, vsize: int, rank: int, world: int, row
     return allbuf.index_select(0, plan["src"])
 
 
+class HostBarrier:
+    """A barrier for the processes of ONE node that does not touch the device: a 64-byte slot per rank in POSIX shared
+    memory holding the last step the rank reached; wait() returns when every slot has reached the caller's step.  An NCCL
+    barrier is an all-reduce plus a stream synchronisation (~0.1 ms at N = 8) -- too much next to a 2 ms frame."""
+
+    def __init__(self, name: str, rank: int, world: int, group=None):
+        import os
+        from pathlib import Path
+
+        self.rank, self.world, self.step = rank, world, 0
+        self.path = Path("/dev/shm") / name
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(64 * max(world, 1))
+        if world > 1:
+            dist.barrier(group=group)
+        self.flags = np.memmap(self.path, dtype=np.int64, mode="r+", shape=(max(world, 1), 8))
+        if rank == 0:
+            self.flags[...] = 0
+            self.flags.flush()
+        if world > 1:
+            dist.barrier(group=group)
+        self._os = os
+
+    def wait(self):
+        self.step += 1
+        self.flags[self.rank, 0] = self.step
+        while int(self.flags[: self.world, 0].min()) < self.step:
+            pass
+
+    def close(self, group=None):
+        if self.world > 1:
+            dist.barrier(group=group)
+        del self.flags
+        if self.rank == 0:
+            try:
+                self.path.unlink()
+            except OSError:
+                pass
+
+
 class PushGather:
     """The frame gathered on rank 0 WITHOUT a collective: rank 0 owns a device canvas the other processes can write (CUDA
     IPC, frt_shared_buffer_*), every rank hands its pointer to frt_render as the canvas, and its row blocks travel over
     NVLink in one strided copy on its own render stream, straight to the rows they belong to -- no packing kernel, no
-    NCCL gather, no reorder on rank 0.  A barrier tells rank 0 that every rank's copy has landed."""
+    NCCL gather, no reorder on rank 0.  A host barrier in shared memory tells rank 0 that every rank's copy has landed."""
 
     def __init__(self, frt, device: int, vsize: int, hsize: int, rank: int, world: int, group=None):
         self.rank, self.world, self.group = rank, world, group
@@ -88,17 +129,21 @@ class PushGather:
         if rank != 0:
             self.buf = frt.SharedBuffer.open(device, box[0], nbytes)
         self.canvas = torch.as_tensor(self.buf.as_cuda_array(self.shape), device=f"cuda:{device}") if rank == 0 else None
+        import os
+
+        # the ranks share a node (CUDA IPC needs that anyway): frames are fenced with a host barrier in shared memory
+        self.fence = HostBarrier(f"frt_push_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}", rank, world, group) if world > 1 else None
 
     def render(self, scene, rows_per_block: int = 4, **render_kw):
         """This rank's rows rendered and pushed; returns (rank 0: the gathered canvas, a device tensor; else None, stats)."""
         _, st = scene.render(rank=self.rank, world=self.world, rows_per_block=rows_per_block, out_ptr=self.buf.ptr, **render_kw)
-        if self.world > 1:
-            dist.barrier(group=self.group)  # frt_render returned: this rank's copy is complete; the frame when all have arrived
+        if self.fence is not None:
+            self.fence.wait()  # frt_render returned: this rank's copy is complete; the frame when every rank has arrived
         return self.canvas, st
 
     def close(self):
-        if self.world > 1:
-            dist.barrier(group=self.group)  # nobody writes the buffer any more
+        if self.fence is not None:
+            self.fence.close(self.group)  # nobody writes the buffer any more
         self.canvas = None
         self.buf.close()
 

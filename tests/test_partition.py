@@ -70,3 +70,41 @@ def test_gather_rows_gloo_world2(vsize, rpb):
     y = np.arange(vsize)
     assert np.array_equal(canvas[:, 0, 0], y.astype(np.float64))
     assert np.array_equal(canvas[:, 0, 1], ((y // rpb) % world).astype(np.float64))
+
+
+def _fence_worker(rank, world, port, q):
+    import time
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fast_ray_tracer_b200.dist import HostBarrier
+
+    hb = HostBarrier(f"frt_test_fence_{port}", rank, world)
+    seen = []
+    for step in range(5):
+        if rank == 1:
+            time.sleep(0.05)  # rank 0 must wait for the slower rank at every step
+        t0 = time.perf_counter()
+        hb.wait()
+        seen.append((int(hb.flags[:world, 0].min()), time.perf_counter() - t0))
+    hb.close()
+    q.put((rank, seen))
+    dist.destroy_process_group()
+
+
+def test_host_barrier_of_the_push_gather_world2():
+    """dist.HostBarrier (the fence of PushGather): nobody passes step k before every rank has reached it."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fence_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank in range(world):
+        assert [s for s, _ in out[rank]] >= [1, 2, 3, 4, 5] and all(s >= k + 1 for k, (s, _) in enumerate(out[rank]))
+    assert sum(w for _, w in out[0]) > 0.15  # rank 0 waited for rank 1's five naps
