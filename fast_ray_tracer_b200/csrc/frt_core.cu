@@ -364,8 +364,11 @@ k_raygen(DCamera C, FrameParams F, RayQ q, Counters *cnt, unsigned int first_sam
 
 /* ------------------------------------------------------------------------------------------------ extend */
 
+#ifndef FRT_EXTEND_MINB
+#define FRT_EXTEND_MINB 2
+#endif
 template <int PRIMS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FRT_EXTEND_MINB)
 k_extend(DScene S, DSceneF SF, RayQ q, HitQ h, Counters *cnt, int level, unsigned int capacity)
 {
     const unsigned int n = min(cnt->n_rays[level], capacity); /* an overflowed level is clamped; the frame is re-run */
@@ -810,8 +813,11 @@ quadrant_sample(int4 lq, int q, int k)
  * re-trace their rays; a verifying frame takes its visibility counts from those FP64 re-traces, like it does for the
  * per-ray filter.
  */
+#ifndef FRT_SHAFT_MINB
+#define FRT_SHAFT_MINB 4 /* blocks per SM the shaft kernels are compiled for (64 registers, 90 bytes of spills): measured 1.69 / 1.43 / 1.27 ms for bulk + quad at 2 / 3 / 4 (93 / 79 / 64 registers) */
+#endif
 template <int MODE, typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FRT_SHAFT_MINB)
 k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int level,
               int light_idx, unsigned int *__restrict__ pending, unsigned int *__restrict__ pprog, unsigned int *__restrict__ retry,
               int bulk_on, int split_on)
@@ -871,7 +877,7 @@ k_shadow_bulk(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
 
 /* one thread per (undecided hit, quadrant of the light's sample grid): the same walk against the quadrant's bounds */
 template <int MODE, typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FRT_SHAFT_MINB)
 k_shadow_quad(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ recs, LightTmp *__restrict__ tmp, Counters *cnt, int light_idx,
               unsigned int *__restrict__ pending, unsigned int *__restrict__ pprog, const unsigned int *__restrict__ retry)
 {
