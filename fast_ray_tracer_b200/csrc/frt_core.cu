@@ -1878,8 +1878,11 @@ k_shadow_mesh(DScene S, DSceneF SF, FrameParams F, const LightRec *__restrict__ 
  * reference's arithmetic type.  Every geometric DECISION (hit / miss, shadowed / lit) stays in FP64 in k_extend /
  * k_shadow_*.
  */
+#ifndef FRT_FINAL_MINB
+#define FRT_FINAL_MINB 5 /* 48 registers: measured 1.71 / 1.60 / 1.65 ms at 4 / 5 / 6 blocks per SM (the kernel waits on the sample sets it reads: long_scoreboard 7.6) */
+#endif
 template <typename T, int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FRT_FINAL_MINB)
 k_light_final(DScene S, FrameParams F, const LightRec *__restrict__ recs, const LightTmp *__restrict__ tmp, double *__restrict__ canvas,
               const Counters *cnt, int level, int light_idx, const float *__restrict__ flpoints, double *__restrict__ acc_amb)
 {
