@@ -8,9 +8,9 @@
  * in a scratch array of 32 shapes it allocates per line, deep-copies the triangles into a staging group
  * (group_add_children_stage, group.c:50-70) and deep-copies every group once more into the result (:520-526).
  * Here the file is read in one piece and walked once with a hand-written tokenizer and number parser, every triangle is
- * constructed IN PLACE in the children array of the group it ends up in -- by the reference's own triangle() /
- * smooth_triangle() constructors, so a shape is field for field what the reference builds -- and the named groups are
- * installed in the result without a copy.
+ * constructed IN PLACE in the children array of the group it ends up in -- a copy of a prototype the reference's own
+ * triangle() / smooth_triangle() built, with the per-triangle fields filled in by the reference's own vector functions, so a
+ * shape is field for field what the reference builds -- and the named groups are installed in the result without a copy.
  *
  * Same results, checked on the flattened tree (tests/test_objload.py: the scene blob of a program linked with this file
  * equals the blob of the program with the reference's loader, byte for byte):
@@ -250,7 +250,44 @@ typedef struct {
     char *name;
     Shape tris;
     size_t n, cap;
+    size_t expected; /* triangles the counting pass found for this group */
 } named_group;
+
+typedef struct {
+    named_group *g;
+    size_t n, cap, cur;
+} group_table;
+
+/* "g name" (:392-417): the group of that name, made if there is none yet; it becomes the current one */
+static void
+select_group(group_table *t, const char *name)
+{
+    size_t i = 0;
+    for (; i < t->n; ++i) {
+        if (strcmp(name, t->g[i].name) == 0) {
+            break;
+        }
+    }
+    if (i == t->n) {
+        if (t->n == t->cap) {
+            t->cap *= 2;
+            t->g = (named_group *)xrealloc(t->g, t->cap * sizeof(named_group));
+        }
+        memset(&t->g[t->n], 0, sizeof(named_group));
+        t->g[t->n].name = strdup(name);
+        ++t->n;
+    }
+    t->cur = i;
+}
+
+/* fgets(line, 1024): up to 1023 bytes, through the first newline */
+static inline const char *
+line_end(const char *line, const char *file_end)
+{
+    const char *nl = memchr(line, '\n', (size_t)(file_end - line));
+    const char *end = nl != NULL ? nl + 1 : file_end;
+    return end - line > 1023 ? line + 1023 : end;
+}
 
 typedef struct {
     size_t v, t, n;
@@ -299,6 +336,60 @@ checked(const vec4_array *a, size_t index, const char *what)
     return a->v + 4 * (index - 1);
 }
 
+/*
+ * triangle() / smooth_triangle() (triangle.c:69-104, :176-213) spend most of their 740 ns in shape_set_transform (matrix
+ * copies and an inverse of the identity) -- 35 of the 44 ms this file needed for the 47 K triangles of dragon.obj.  Every
+ * triangle of a file gets the same values there, so one prototype of each kind is built by the reference's constructor and
+ * copied; what differs per triangle is filled in as the constructor does it, with the reference's own vector functions
+ * (same object code, same rounding): vertices, edges, the flat normal or the three vertex normals, an intersection list
+ * and a material of its own.
+ */
+static struct shape g_proto_flat, g_proto_smooth;
+static bool g_protos_ready;
+
+static void
+make_prototypes(void)
+{
+    double o[4] = { 0, 0, 0, 1 }, a[4] = { 1, 0, 0, 1 }, b[4] = { 0, 1, 0, 1 }, n[4] = { 0, 0, 1, 0 };
+    triangle(&g_proto_flat, o, a, b);
+    smooth_triangle(&g_proto_smooth, o, a, b, n, n, n);
+    struct shape *protos[2] = { &g_proto_flat, &g_proto_smooth };
+    for (int k = 0; k < 2; ++k) {
+        material_free(protos[k]->material);
+        intersections_free(protos[k]->xs);
+        protos[k]->material = NULL;
+        protos[k]->xs = NULL;
+    }
+    g_protos_ready = true;
+}
+
+static inline void
+construct_triangle(Shape s, bool smooth, double *p1, double *p2, double *p3, double *n1, double *n2, double *n3, Material bound)
+{
+    *s = smooth ? g_proto_smooth : g_proto_flat;
+    s->xs = intersections_empty(1);
+    memcpy(s->fields.triangle.p1, p1, sizeof(Point));
+    memcpy(s->fields.triangle.p2, p2, sizeof(Point));
+    memcpy(s->fields.triangle.p3, p3, sizeof(Point));
+    vector_from_points(p2, p1, s->fields.triangle.e1);
+    vector_from_points(p3, p1, s->fields.triangle.e2);
+    if (smooth) {
+        vector_copy(s->fields.triangle.u_normals.s_normals.n1, n1);
+        vector_copy(s->fields.triangle.u_normals.s_normals.n2, n2);
+        vector_copy(s->fields.triangle.u_normals.s_normals.n3, n3);
+    } else {
+        Vector cross, normal;
+        vector_cross(s->fields.triangle.e2, s->fields.triangle.e1, cross);
+        vector_normalize(cross, normal);
+        memcpy(s->fields.triangle.u_normals.normal, normal, sizeof(Vector));
+    }
+    if (bound != NULL) {
+        shape_set_material(s, bound); /* s->material is NULL: takes a reference, like shape_set_material after the constructor */
+    } else {
+        s->material = material_alloc();
+    }
+}
+
 static double g_last_ms;
 
 double
@@ -329,20 +420,57 @@ frt_construct_group_from_obj_file(const char *file_path, void (*color_space_fn)(
     const char *file_end = text + size;
 
     vec4_array vs = { NULL, 0, 0 }, ts = { NULL, 0, 0 }, ns = { NULL, 0, 0 };
-    named_group *groups = (named_group *)xrealloc(NULL, 16 * sizeof(named_group));
-    size_t n_groups = 1, cap_groups = 16, cur = 0;
-    groups[0].name = strdup("##default_group"); /* :474-478 */
-    groups[0].tris = NULL;
-    groups[0].n = groups[0].cap = 0;
+    group_table gt = { (named_group *)xrealloc(NULL, 16 * sizeof(named_group)), 0, 16, 0 };
+    select_group(&gt, "##default_group"); /* :474-478 */
     Material current_material = NULL;
+    if (!g_protos_ready) {
+        make_prototypes();
+    }
+
+    /* Counting pass over the "f" and "g" lines: every group's triangle array is allocated once, at its final size.  (Grown
+     * by doubling between the three small allocations every triangle makes, a 20 MB array was copied at every step: 29 of
+     * the 45 ms of dragon.obj went into that.) */
+    for (const char *line = text; line < file_end;) {
+        const char *end = line_end(line, file_end);
+        const size_t len = (size_t)(end - line);
+        if (len >= 2 && line[0] == 'f' && line[1] == ' ') {
+            size_t tokens = 0;
+            for (const char *p = line + 2; p < end;) {
+                while (p < end && (*p == ' ' || *p == '\t')) {
+                    ++p;
+                }
+                if (p >= end || *p == '\n' || *p == '\r') {
+                    break;
+                }
+                while (p < end && *p != ' ' && *p != '\t') {
+                    ++p;
+                }
+                ++tokens;
+            }
+            gt.g[gt.cur].expected += tokens > 2 ? tokens - 2 : 0;
+        } else if (len >= 2 && line[0] == 'g' && line[1] == ' ') {
+            char name[MAX_MATERIAL_NAME_LEN];
+            second_word(line, end, name);
+            select_group(&gt, name);
+        }
+        line = end;
+    }
+    for (size_t i = 0; i < gt.n; ++i) {
+        if (gt.g[i].expected > 0) {
+            gt.g[i].tris = array_of_shapes(gt.g[i].expected);
+            if (gt.g[i].tris == NULL) {
+                die("out of memory", NULL);
+            }
+            gt.g[i].cap = gt.g[i].expected;
+        }
+    }
+    gt.cur = 0;
+#define groups gt.g
+#define n_groups gt.n
+#define cur gt.cur
 
     for (const char *line = text; line < file_end;) {
-        /* fgets(line, 1024): up to 1023 bytes, through the first newline */
-        const char *nl = memchr(line, '\n', (size_t)(file_end - line));
-        const char *end = nl != NULL ? nl + 1 : file_end;
-        if (end - line > 1023) {
-            end = line + 1023;
-        }
+        const char *end = line_end(line, file_end);
         const size_t len = (size_t)(end - line);
         if (len >= 2 && line[0] == 'v' && line[1] == ' ') {
             vec4_push(&vs, line, end, 1.0);
@@ -393,18 +521,16 @@ frt_construct_group_from_obj_file(const char *file_path, void (*color_space_fn)(
                     Shape s = g->tris + g->n;
                     double *p1 = checked(&vs, first.v, "v"), *p2 = checked(&vs, prev.v, "v"), *p3 = checked(&vs, fv.v, "v");
                     if (use_normals) {
-                        smooth_triangle(s, p1, p2, p3, checked(&ns, first.n, "vn"), checked(&ns, prev.n, "vn"), checked(&ns, fv.n, "vn"));
+                        construct_triangle(s, true, p1, p2, p3, checked(&ns, first.n, "vn"), checked(&ns, prev.n, "vn"), checked(&ns, fv.n, "vn"),
+                                           current_material);
                     } else {
-                        triangle(s, p1, p2, p3);
+                        construct_triangle(s, false, p1, p2, p3, NULL, NULL, NULL, current_material);
                     }
                     if (use_textures) {
                         vector_copy(s->fields.triangle.t1, checked(&ts, first.t, "vt"));
                         vector_copy(s->fields.triangle.t2, checked(&ts, prev.t, "vt"));
                         vector_copy(s->fields.triangle.t3, checked(&ts, fv.t, "vt"));
                         s->fields.triangle.use_textures = true;
-                    }
-                    if (current_material != NULL) {
-                        shape_set_material(s, current_material);
                     }
                     g->n += 1;
                 }
@@ -414,23 +540,7 @@ frt_construct_group_from_obj_file(const char *file_path, void (*color_space_fn)(
         } else if (len >= 2 && line[0] == 'g' && line[1] == ' ') {
             char name[MAX_MATERIAL_NAME_LEN];
             second_word(line, end, name);
-            size_t i = 0;
-            for (; i < n_groups; ++i) {
-                if (strcmp(name, groups[i].name) == 0) {
-                    break;
-                }
-            }
-            if (i == n_groups) {
-                if (n_groups == cap_groups) {
-                    cap_groups *= 2;
-                    groups = (named_group *)xrealloc(groups, cap_groups * sizeof(named_group));
-                }
-                groups[n_groups].name = strdup(name);
-                groups[n_groups].tris = NULL;
-                groups[n_groups].n = groups[n_groups].cap = 0;
-                ++n_groups;
-            }
-            cur = i;
+            select_group(&gt, name);
         } else if (len >= 6 && strncmp(line, "usemtl", 6) == 0) {
             char name[MAX_MATERIAL_NAME_LEN];
             second_word(line, end, name);
@@ -459,6 +569,8 @@ frt_construct_group_from_obj_file(const char *file_path, void (*color_space_fn)(
         line = end;
     }
 
+    struct timespec t_parsed;
+    clock_gettime(CLOCK_MONOTONIC, &t_parsed);
     /* the result: a group whose children are the non-empty named groups, in the order they were first named (:516-526) */
     group(result_group, NULL, 0);
     size_t nonempty = 0;
@@ -492,6 +604,9 @@ frt_construct_group_from_obj_file(const char *file_path, void (*color_space_fn)(
         free(groups[i].tris);
     }
     free(groups);
+#undef groups
+#undef n_groups
+#undef cur
     free(vs.v);
     free(ts.v);
     free(ns.v);
@@ -505,7 +620,8 @@ frt_construct_group_from_obj_file(const char *file_path, void (*color_space_fn)(
     clock_gettime(CLOCK_MONOTONIC, &t1);
     g_last_ms = 1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec);
     if (getenv("FRT_B200_OBJ_TIMING") != NULL) {
-        printf("FRT_B200_OBJ_MS %.3f (%s)\n", g_last_ms, file_path);
+        printf("FRT_B200_OBJ_MS %.3f (%s; %.3f ms until the last line was read)\n", g_last_ms, file_path,
+               1e3 * (double)(t_parsed.tv_sec - t0.tv_sec) + 1e-6 * (double)(t_parsed.tv_nsec - t0.tv_nsec));
     }
 }
 
