@@ -331,7 +331,14 @@ def cuda_arm(args) -> dict:
             dist.barrier()
         torch.cuda.synchronize()
 
-    push = PushGather(frt, local, vsize, hsize, rank, world) if (world > 1 and gather_mode == "push") else None
+    push = None
+    if world > 1 and gather_mode == "push":
+        try:
+            push = PushGather(frt, local, vsize, hsize, rank, world)
+        except RuntimeError as e:  # raised on every rank alike (CUDA IPC not available between these processes)
+            if rank == 0:
+                print(f"[bench] {e}: the rows are gathered over NCCL instead", file=sys.stderr)
+            gather_mode = "gather"
 
     def frame_step(sc, seed):
         """One frame of this rank's rows on the device, then (N > 1) the rows brought together on rank 0."""

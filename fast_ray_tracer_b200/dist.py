@@ -120,14 +120,27 @@ class PushGather:
         self.rank, self.world, self.group = rank, world, group
         self.shape = (vsize, hsize, 4)
         nbytes = vsize * hsize * 4 * 8
-        box = [None]
+        box, err, self.buf = [None], None, None
         if rank == 0:
-            self.buf = frt.SharedBuffer.create(device, nbytes)
-            box[0] = self.buf.handle
+            try:
+                self.buf = frt.SharedBuffer.create(device, nbytes)
+                box[0] = self.buf.handle
+            except Exception as e:  # every rank has to learn of it: the handle travels as None
+                err = e
         if world > 1:
             dist.broadcast_object_list(box, src=0, group=group)
-        if rank != 0:
-            self.buf = frt.SharedBuffer.open(device, box[0], nbytes)
+        if rank != 0 and box[0] is not None:
+            try:
+                self.buf = frt.SharedBuffer.open(device, box[0], nbytes)
+            except Exception as e:
+                err = e
+        ok = torch.tensor([0 if (err is not None or self.buf is None) else 1], dtype=torch.int32, device=f"cuda:{device}")
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:  # the same verdict on every rank: nobody is left waiting in a collective
+            if self.buf is not None:
+                self.buf.close()
+            raise RuntimeError(f"PushGather: the shared canvas could not be set up on every rank ({err})")
         self.canvas = torch.as_tensor(self.buf.as_cuda_array(self.shape), device=f"cuda:{device}") if rank == 0 else None
         import os
 
