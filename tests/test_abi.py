@@ -56,3 +56,11 @@ def test_product_does_not_import_the_oracle():
         if p.suffix in {".py", ".c", ".cu", ".cuh", ".h"}:
             text = p.read_text()
             assert "oracle/" not in text and "import oracle" not in text and "frt_oracle" not in text, p
+
+
+def test_shared_buffer_fails_loudly_without_a_gpu(frt):
+    """frt_shared_buffer_create is device memory or nothing: no host stand-in on a GPU-less box."""
+    if frt.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(frt.FrtError):
+        frt.SharedBuffer.create(0, 1 << 20)
